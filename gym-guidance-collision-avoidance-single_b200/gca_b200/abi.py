@@ -1,0 +1,99 @@
+"""ctypes mirror of include/gca.h and the loader of libgca.so.
+
+There is no CPU implementation behind this module: if the shared library has not been built
+(`python __graft_entry__.py build`) or no CUDA device is usable, the calls raise.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libgca.so")
+
+GCA_ABI_VERSION = 1
+
+MODE_FAITHFUL, MODE_FAST = 0, 1
+DRAWS_TAPE, DRAWS_PHILOX = 0, 1
+ACT_DISCRETE9, ACT_CONTINUOUS2, ACT_DISCRETE3 = 0, 1, 2
+OBS_VECTOR, OBS_HER, OBS_DHER, OBS_RAW, OBS_NONE = 0, 1, 2, 3, 4
+WALL_NONE, WALL_TERMINAL, WALL_PENALTY = 0, 1, 2
+INFO_NONE, INFO_NMAC, INFO_CONFLICT, INFO_GOAL, INFO_WALL, INFO_MAXSTEPS = range(6)
+INFO_STR = ("", "n", "c", "g", "w", "m")
+
+SLOT_OWNSHIP, SLOT_GOAL, SLOT_RESET = 0x80000000, 0x40000000, 0x20000000
+
+
+class GcaConfig(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        "window_width", "window_height",
+        "minimum_separation", "nmac_dist", "initial_min_dist", "goal_radius",
+        "min_speed", "max_speed", "d_speed", "speed_sigma",
+        "d_heading", "heading_sigma",
+        "ob_window_width", "ob_window_height", "ob_min_speed", "ob_max_speed",
+        "r_nmac", "r_conflict", "r_wall", "r_goal", "r_default")] + [(n, C.c_int32) for n in (
+            "shaped_default", "action_kind", "obs_kind", "wall_kind", "max_steps", "reserved0")]
+
+
+class GcaHostState(C.Structure):
+    _fields_ = [("own_pos", C.c_void_p), ("own_hs", C.c_void_p), ("own_vel", C.c_void_p), ("goal", C.c_void_p),
+                ("no_conflict", C.c_void_p), ("ep_steps", C.c_void_p), ("ipos", C.c_void_p),
+                ("ipos_is_f64", C.c_void_p), ("ivel", C.c_void_p), ("iflag", C.c_void_p)]
+
+
+class GcaOut(C.Structure):
+    _fields_ = [("obs", C.c_void_p), ("achieved", C.c_void_p), ("desired", C.c_void_p), ("reward", C.c_void_p),
+                ("done", C.c_void_p), ("info", C.c_void_p)]
+
+
+class GcaTape(C.Structure):
+    _fields_ = [("values", C.c_void_p), ("stride", C.c_int64), ("cursor", C.c_void_p)]
+
+
+class GcaError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libgca.so (once).  Fails loudly: there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GcaError("libgca.so is not built (%s missing); run `python __graft_entry__.py build`. "
+                       "There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, u32, u64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint32, C.c_uint64
+    P = C.POINTER
+    sigs = {
+        "gca_abi_version": ([], C.c_int),
+        "gca_last_error": ([], C.c_char_p),
+        "gca_obs_dim": ([P(GcaConfig), i32], C.c_int),
+        "gca_create": ([P(GcaConfig), i32, i32, i32, i32, i32, u64, u32, P(vp)], C.c_int),
+        "gca_destroy": ([vp], C.c_int),
+        "gca_set_config": ([vp, P(GcaConfig)], C.c_int),
+        "gca_reset": ([vp, vp, P(GcaTape), P(GcaOut), vp], C.c_int),
+        "gca_step": ([vp, vp, P(GcaTape), i32, P(GcaOut), vp], C.c_int),
+        "gca_step_host": ([vp, vp, i32, P(GcaOut)], C.c_int),
+        "gca_reset_host": ([vp, P(GcaOut)], C.c_int),
+        "gca_get_state": ([vp, P(GcaHostState)], C.c_int),
+        "gca_set_state": ([vp, P(GcaHostState)], C.c_int),
+        "gca_get_tick": ([vp, P(u32)], C.c_int),
+        "gca_set_tick": ([vp, u32], C.c_int),
+        "gca_compute_reward": ([vp, vp, i64, C.c_double, i32, i32, vp, i32, vp], C.c_int),
+    }
+    for name, (argtypes, restype) in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+    if lib.gca_abi_version() != GCA_ABI_VERSION:
+        raise GcaError("libgca.so ABI version %d != expected %d" % (lib.gca_abi_version(), GCA_ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != 0:
+        msg = load().gca_last_error()
+        raise GcaError("libgca call failed (%d): %s" % (status, msg.decode() if msg else "?"))

@@ -1,0 +1,186 @@
+/* gca.h - C ABI of libgca: the batched, device-resident step hot path of the
+ * single-aircraft guidance / collision-avoidance environments, hand-written for sm_100a.
+ *
+ * The reference (xuxiyang1993/gym-guidance-collision-avoidance-single) is pure Python and has
+ * no FFI of its own; each entry point below names the reference interface it replaces
+ * (paths relative to the reference root, PKG = gym_guidance_collision_avoidance_single/envs).
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; every function returns 0 on success or a negative
+ *     gca_status; the message for the calling thread's last failure is gca_last_error().
+ *   - a gca_env handle is bound to one CUDA device and is not thread-safe.
+ *   - entry points taking a `stream` (a cudaStream_t passed as void*) are asynchronous on that
+ *     stream and never synchronise; the *_host entry points synchronise before returning.
+ *   - device state is owned by the handle; input / output buffers are owned by the caller.
+ *   - there is NO CPU implementation behind this ABI: without a usable CUDA device
+ *     gca_create fails with GCA_ERR_CUDA.
+ */
+#ifndef GCA_H_
+#define GCA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCA_ABI_VERSION 1
+
+typedef enum gca_status {
+  GCA_OK = 0,
+  GCA_ERR_INVALID = -1, /* bad argument */
+  GCA_ERR_CUDA = -2,    /* CUDA runtime error (message has the CUDA string) */
+  GCA_ERR_ALLOC = -3,   /* host allocation failed */
+  GCA_ERR_STATE = -4    /* call not valid in the handle's current configuration */
+} gca_status;
+
+/* numerics: FAITHFUL reproduces the reference's mixed f32/f64 arithmetic (SURVEY.md 8(a)
+ * "Numerics contract"): f64-capable intruder positions, f64 observations and rewards.
+ * FAST stores intruder positions in f32 only (a spawn that was retried is rounded to f32, the
+ * one deviation from the reference, Q3) and emits f32 observations / rewards, i.e. exactly what
+ * a baselines VecEnv hands to a learner (dummy_vec_env.py:25-27). */
+enum { GCA_MODE_FAITHFUL = 0, GCA_MODE_FAST = 1 };
+
+/* where random draws come from: TAPE replays values recorded from the reference's global
+ * numpy stream in the reference's consumption order (per-env cursor); PHILOX generates them
+ * on the device with Philox4x32-10 addressed by (seed; env id, tick, slot, block). */
+enum { GCA_DRAWS_TAPE = 0, GCA_DRAWS_PHILOX = 1 };
+
+/* action decoding (a2/a3/a3' in SURVEY.md 8(a)) */
+enum {
+  GCA_ACT_DISCRETE9 = 0,  /* int32 a: a0 = a / 3, a1 = a % 3, delta = (a0-1, a1-1)  PKG/SingleAircraftEnv.py:130-133,300-302;
+                             also the (a0, a1) tuple of Simulators/SingleAircraftMCTSEnv.py:126-130 encoded a0*3+a1 */
+  GCA_ACT_CONTINUOUS2 = 1, /* real a[2] in [-1,1]: delta = (a[0], a[1])              PKG/SingleAircraft2Env.py:292-294 */
+  GCA_ACT_DISCRETE3 = 2    /* int32 a: heading delta a-1, speed += speed_sigma       PKG/SingleAircraftDiscreteHEREnv.py:302-304 */
+};
+
+/* observation layout (a9/a10/a16) */
+enum {
+  GCA_OBS_VECTOR = 0,   /* [intruders x4][own x6][goal x2], normalised   PKG/SingleAircraftEnv.py:100-126 */
+  GCA_OBS_HER = 1,      /* [own x6][intruders x4] + achieved/desired normalised  PKG/SingleAircraftHEREnv.py:103-139 */
+  GCA_OBS_DHER = 2,     /* as HER but achieved/desired are raw pixel positions   PKG/SingleAircraftDiscreteHEREnv.py:128-133 */
+  GCA_OBS_RAW = 3,      /* VECTOR layout, un-normalised values     Simulators/SingleAircraftMCTSEnv.py:98-124 */
+  GCA_OBS_NONE = 4      /* no vector observation (StackEnv: the image comes from gca_raster) */
+};
+
+enum { GCA_WALL_NONE = 0, GCA_WALL_TERMINAL = 1, GCA_WALL_PENALTY = 2 };
+
+/* per-step result code, the reference's info string ('' n c g w m) */
+enum { GCA_INFO_NONE = 0, GCA_INFO_NMAC = 1, GCA_INFO_CONFLICT = 2, GCA_INFO_GOAL = 3, GCA_INFO_WALL = 4, GCA_INFO_MAXSTEPS = 5 };
+
+/* Philox slot namespace: counter = (env id, tick, slot, block) */
+#define GCA_SLOT_OWNSHIP 0x80000000u /* block 0: Box-Muller pair (heading noise, speed noise) */
+#define GCA_SLOT_GOAL 0x40000000u    /* block 0: goal (x, y) of a reset */
+#define GCA_SLOT_RESET 0x20000000u   /* | intruder index: spawn made by a reset */
+                                     /* intruder index alone: respawn made inside a step */
+#define GCA_BLOCK_POS 0u             /* (x, y) */
+#define GCA_BLOCK_SPEED_HEADING 1u   /* (speed, heading) */
+#define GCA_BLOCK_RETRY0 2u          /* + r: r-th re-draw of (x, y) by the rejection loop */
+#define GCA_MAX_SPAWN_RETRIES 64     /* PHILOX only: after this many rejections the position is accepted */
+
+/* Parameters of one environment family.  Field names follow PKG/config.py:4-39 and
+ * Simulators/config.py:4-55; the variant rows follow the reward table of SURVEY.md 8(a). */
+typedef struct gca_config {
+  double window_width, window_height;
+  double minimum_separation, nmac_dist, initial_min_dist, goal_radius;
+  double min_speed, max_speed, d_speed, speed_sigma;
+  double d_heading, heading_sigma;
+  /* values _get_ob re-reads from the Config class on every call (Q12) */
+  double ob_window_width, ob_window_height, ob_min_speed, ob_max_speed;
+  /* reward row */
+  double r_nmac, r_conflict, r_wall, r_goal, r_default;
+  int32_t shaped_default; /* 1: default reward is -dist(own, goal) / 1200; 0: r_default */
+  int32_t action_kind;    /* GCA_ACT_* */
+  int32_t obs_kind;       /* GCA_OBS_* */
+  int32_t wall_kind;      /* GCA_WALL_* */
+  int32_t max_steps;      /* > 0: StackEnv rule - steps >= max_steps ends the episode before intruders move */
+  int32_t reserved0;
+} gca_config;
+
+/* Canonical host-side view of the full simulator state, identical for both modes
+ * (used by gca_get_state / gca_set_state and by the oracle).  Arrays are C-contiguous. */
+typedef struct gca_host_state {
+  float* own_pos;            /* [B][2]   f32 position            PKG/SingleAircraftEnv.py:271 */
+  double* own_hs;            /* [B][2]   heading, speed          :272-273 */
+  double* own_vel;           /* [B][2]   velocity (f32-valued right after reset, :276,:308) */
+  double* goal;              /* [B][2]   :93 */
+  int32_t* no_conflict;      /* [B]      :96 */
+  int32_t* ep_steps;         /* [B]      steps since reset (StackEnv :118; TimeLimit) */
+  double* ipos;              /* [B][N][2] intruder positions (f32-valued unless flagged) */
+  uint8_t* ipos_is_f64;      /* [B][N]   position dtype is f64 (retried spawn, Q3) */
+  float* ivel;               /* [B][N][2] :276 */
+  uint8_t* iflag;            /* [B][N]   Aircraft.conflict :278 */
+} gca_host_state;
+
+/* Device output buffers of one reset/step.  REAL is double in FAITHFUL mode, float in FAST. */
+typedef struct gca_out {
+  void* obs;       /* REAL [B][obs_dim]; may be NULL for GCA_OBS_NONE */
+  void* achieved;  /* REAL [B][2]  HER kinds only, else NULL */
+  void* desired;   /* REAL [B][2]  HER kinds only, else NULL */
+  void* reward;    /* REAL [B]     (ignored by gca_reset) */
+  uint8_t* done;   /* [B] */
+  uint8_t* info;   /* [B] GCA_INFO_* */
+} gca_out;
+
+/* Recorded draws for GCA_DRAWS_TAPE: env b reads values[b*stride + cursor[b]++]. */
+typedef struct gca_tape {
+  const double* values; /* device [B][stride] */
+  int64_t stride;
+  int64_t* cursor;      /* device [B], advanced by the kernels */
+} gca_tape;
+
+typedef struct gca_env gca_env;
+
+int gca_abi_version(void);
+const char* gca_last_error(void);
+
+/* number of REAL elements of one observation row: 4*N + 8 for VECTOR/RAW, 4*N + 6 for HER/DHER, 0 for NONE */
+int gca_obs_dim(const gca_config* cfg, int n_intruders);
+
+/* Replaces B constructions of PKG/SingleAircraftEnv.py:29-43 (and siblings).  Allocates the
+ * device state for n_envs environments with n_intruders intruders each on `device`.
+ * env_id0 is the global id of env 0 (rank offset for multi-GPU sharding). */
+int gca_create(const gca_config* cfg, int n_envs, int n_intruders, int mode, int draws,
+               int device, uint64_t seed, uint32_t env_id0, gca_env** out);
+int gca_destroy(gca_env* env);
+
+/* Update the parameters in place (the reference re-reads Config inside _get_ob, Q12). */
+int gca_set_config(gca_env* env, const gca_config* cfg);
+
+/* reset(): PKG/SingleAircraftEnv.py:66-98 for every env whose mask byte is non-zero
+ * (mask == NULL: all).  Writes obs (and achieved/desired); done/info are cleared. */
+int gca_reset(gca_env* env, const uint8_t* mask, const gca_tape* tape, const gca_out* out, void* stream);
+
+/* step(action): PKG/SingleAircraftEnv.py:128-184 (+ variants) for all envs in one launch.
+ * actions: device int32[B] for the discrete kinds; REAL[B][2] for GCA_ACT_CONTINUOUS2.
+ * auto_reset != 0 applies the VecEnv contract (baselines dummy_vec_env.py:52-55): an env that
+ * finished is reset in the same launch and `obs` holds the reset observation. */
+int gca_step(gca_env* env, const void* actions, const gca_tape* tape, int auto_reset,
+             const gca_out* out, void* stream);
+
+/* Same step driven from HOST memory (the end-to-end path): copies actions host->device,
+ * launches, copies obs/reward/done/info device->host into `host_out` (host pointers with the
+ * same shapes; pinned memory recommended) and synchronises.  PHILOX draws only. */
+int gca_step_host(gca_env* env, const void* actions_host, int auto_reset, const gca_out* host_out);
+int gca_reset_host(gca_env* env, const gca_out* host_out);
+
+/* Full-state access (teacher-forced parity, MCTS root states, checkpointing).  Synchronous. */
+int gca_get_state(gca_env* env, const gca_host_state* dst);
+int gca_set_state(gca_env* env, const gca_host_state* src);
+
+/* Monotone launch counter used as the Philox `tick`. */
+int gca_get_tick(gca_env* env, uint32_t* tick);
+int gca_set_tick(gca_env* env, uint32_t tick);
+
+/* HER relabelling reward, PKG/SingleAircraftHEREnv.py:194-196 (kind GCA_OBS_HER:
+ * -(d > radius), always -0.0f for normalised goals, Q14) and
+ * PKG/SingleAircraftDiscreteHEREnv.py:184-186 (kind GCA_OBS_DHER: d < radius).
+ * ag, g: device [m][2], f64 when is_f64 else f32; out: device float[m]. */
+int gca_compute_reward(const void* ag, const void* g, int64_t m, double radius, int kind,
+                       int is_f64, float* out, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCA_H_ */

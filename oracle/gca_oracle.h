@@ -1,0 +1,73 @@
+/* gca_oracle.h - CPU restatement of the reference's step hot path.
+ *
+ * TEST INFRASTRUCTURE, NOT PRODUCT: only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load this library, and only as the checker or as
+ * the timed CPU baseline.  Nothing under gym-guidance-collision-avoidance-single_b200/ links,
+ * imports or calls it.
+ *
+ * Pinning: the restatement is checked bit-for-bit (flags, counters, positions, rewards,
+ * observations) against traces recorded from the unmodified reference by
+ * tests/golden/make_golden.py (tests/test_oracle_golden.py).  The reference has no tests or
+ * golden vectors of its own.
+ */
+#ifndef GCA_ORACLE_H_
+#define GCA_ORACLE_H_
+
+#include <stdint.h>
+#include "gca.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { GCA_TRIG_LIBM = 0,    /* cos/sin/log from libm: what CPython's math module calls */
+       GCA_TRIG_SHARED = 1 };/* gca_math.h: bit-identical to the CUDA kernels */
+
+typedef struct gca_oracle_batch {
+  int32_t n_envs, n_intr;
+  gca_host_state st;          /* in/out, canonical layout (include/gca.h) */
+  uint8_t* own_vel_is_f32;    /* [B] in/out: ownship velocity still the f32 array made by reset (Q2) */
+  /* draw source */
+  int32_t draws;              /* GCA_DRAWS_* */
+  int32_t trig;               /* GCA_TRIG_* */
+  const double* tape;         /* [B][tape_stride] */
+  int64_t tape_stride;
+  int64_t* cursor;            /* [B] in/out */
+  uint64_t seed;
+  uint32_t tick;
+  uint32_t env_id0;
+  int32_t f32_positions;      /* 1: FAST-mode storage rule (a retried spawn is rounded to f32) */
+  int32_t auto_reset;
+  /* outputs (always f64-valued; an element the reference computes in f32 is that f32 widened) */
+  double* obs;                /* [B][obs_dim] */
+  double* achieved;           /* [B][2] or NULL */
+  double* desired;            /* [B][2] or NULL */
+  double* reward;             /* [B] */
+  uint8_t* done;              /* [B] */
+  uint8_t* info;              /* [B] */
+  double* term_obs;           /* [B][obs_dim] or NULL: observation of the step itself, before any auto-reset */
+} gca_oracle_batch;
+
+/* actions: double[B][2]; discrete kinds use actions[b][0] as the integer code. */
+int gca_oracle_step(const gca_config* cfg, gca_oracle_batch* b, const double* actions);
+int gca_oracle_reset(const gca_config* cfg, gca_oracle_batch* b, const uint8_t* mask);
+/* observation of the current state without stepping (PKG/SingleAircraftEnv.py:100-126) */
+int gca_oracle_observe(const gca_config* cfg, gca_oracle_batch* b);
+
+/* HER relabel reward, same contract as gca_compute_reward but on host arrays */
+int gca_oracle_compute_reward(const double* ag, const double* g, int64_t m, double radius, int kind, float* out);
+int gca_oracle_compute_reward_f32(const float* ag, const float* g, int64_t m, double radius, int kind, float* out);
+int gca_oracle_obs_dim(const gca_config* cfg, int n_intruders);
+
+/* building blocks exposed for unit tests */
+void gca_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+void gca_oracle_sincos(double x, int trig, double* s, double* c);
+double gca_oracle_log(double x, int trig);
+/* the two uniforms / the Box-Muller pair a Philox block yields */
+void gca_oracle_philox_uniform2(uint64_t seed, uint32_t env, uint32_t tick, uint32_t slot, uint32_t block, double u[2]);
+void gca_oracle_philox_normal2(uint64_t seed, uint32_t env, uint32_t tick, uint32_t slot, int trig, double g[2]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

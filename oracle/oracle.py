@@ -1,0 +1,178 @@
+"""ctypes wrapper of the CPU oracle (oracle/libgca_oracle.so).
+
+TEST INFRASTRUCTURE, NOT PRODUCT: imported only by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  It reuses the product's ctypes struct
+definitions (the oracle may look at the product; never the other way round).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(_HERE, "libgca_oracle.so")
+
+TRIG_LIBM, TRIG_SHARED = 0, 1
+
+
+def build(force=False):
+    if force or not os.path.exists(LIB):
+        subprocess.check_call(["make", "-C", _HERE] + (["-B"] if force else []))
+    return LIB
+
+
+def _abi():
+    from gca_b200 import abi
+    return abi
+
+
+class OracleBatch(C.Structure):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    abi = _abi()
+    build()
+    OracleBatch._fields_ = [
+        ("n_envs", C.c_int32), ("n_intr", C.c_int32),
+        ("st", abi.GcaHostState),
+        ("own_vel_is_f32", C.c_void_p),
+        ("draws", C.c_int32), ("trig", C.c_int32),
+        ("tape", C.c_void_p), ("tape_stride", C.c_int64), ("cursor", C.c_void_p),
+        ("seed", C.c_uint64), ("tick", C.c_uint32), ("env_id0", C.c_uint32),
+        ("f32_positions", C.c_int32), ("auto_reset", C.c_int32),
+        ("obs", C.c_void_p), ("achieved", C.c_void_p), ("desired", C.c_void_p), ("reward", C.c_void_p),
+        ("done", C.c_void_p), ("info", C.c_void_p), ("term_obs", C.c_void_p),
+    ]
+    L = C.CDLL(LIB)
+    P = C.POINTER
+    L.gca_oracle_step.argtypes = [P(abi.GcaConfig), P(OracleBatch), C.c_void_p]
+    L.gca_oracle_reset.argtypes = [P(abi.GcaConfig), P(OracleBatch), C.c_void_p]
+    L.gca_oracle_observe.argtypes = [P(abi.GcaConfig), P(OracleBatch)]
+    L.gca_oracle_compute_reward.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_void_p]
+    L.gca_oracle_compute_reward_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_void_p]
+    L.gca_oracle_obs_dim.argtypes = [P(abi.GcaConfig), C.c_int]
+    L.gca_oracle_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gca_oracle_philox4x32_10.restype = None
+    L.gca_oracle_sincos.argtypes = [C.c_double, C.c_int, P(C.c_double), P(C.c_double)]
+    L.gca_oracle_sincos.restype = None
+    L.gca_oracle_log.argtypes = [C.c_double, C.c_int]
+    L.gca_oracle_log.restype = C.c_double
+    L.gca_oracle_philox_uniform2.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+    L.gca_oracle_philox_uniform2.restype = None
+    L.gca_oracle_philox_normal2.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
+    L.gca_oracle_philox_normal2.restype = None
+    _lib = L
+    return L
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data
+
+
+STATE_FIELDS = (("own_pos", np.float32, (2,)), ("own_hs", np.float64, (2,)), ("own_vel", np.float64, (2,)),
+                ("goal", np.float64, (2,)), ("no_conflict", np.int32, ()), ("ep_steps", np.int32, ()),
+                ("ipos", np.float64, ("N", 2)), ("ipos_is_f64", np.uint8, ("N",)), ("ivel", np.float32, ("N", 2)),
+                ("iflag", np.uint8, ("N",)))
+
+
+def empty_state(B, N):
+    """Canonical host state (include/gca.h gca_host_state) as a dict of numpy arrays."""
+    st = {}
+    for name, dt, shp in STATE_FIELDS:
+        shape = (B,) + tuple(N if s == "N" else s for s in shp)
+        st[name] = np.zeros(shape, dt)
+    return st
+
+
+class OracleEnv(object):
+    """B independent environments advanced sequentially on the CPU by the C restatement."""
+
+    def __init__(self, cfg, n_envs, n_intr, draws=1, trig=TRIG_SHARED, seed=0, env_id0=0, f32_positions=False,
+                 auto_reset=False, tape=None):
+        self.L = lib()
+        self.cfg = cfg
+        self.B, self.N = int(n_envs), int(n_intr)
+        self.D = self.L.gca_oracle_obs_dim(C.byref(cfg), self.N)
+        self.state = empty_state(self.B, self.N)
+        self.own_vel_is_f32 = np.ones(self.B, np.uint8)
+        self.draws, self.trig, self.seed, self.env_id0 = draws, trig, seed, env_id0
+        self.f32_positions, self.auto_reset = bool(f32_positions), bool(auto_reset)
+        self.tick = 0
+        self.tape = None if tape is None else np.ascontiguousarray(tape, np.float64)
+        self.cursor = np.zeros(self.B, np.int64)
+        self.obs = np.zeros((self.B, self.D), np.float64)
+        self.term_obs = np.zeros((self.B, self.D), np.float64)
+        self.achieved = np.zeros((self.B, 2), np.float64)
+        self.desired = np.zeros((self.B, 2), np.float64)
+        self.reward = np.zeros(self.B, np.float64)
+        self.done = np.zeros(self.B, np.uint8)
+        self.info = np.zeros(self.B, np.uint8)
+
+    def _batch(self):
+        abi = _abi()
+        b = OracleBatch()
+        b.n_envs, b.n_intr = self.B, self.N
+        st = abi.GcaHostState()
+        for name, _, _ in STATE_FIELDS:
+            setattr(st, name, _p(self.state[name]))
+        b.st = st
+        b.own_vel_is_f32 = _p(self.own_vel_is_f32)
+        b.draws, b.trig = self.draws, self.trig
+        if self.tape is not None:
+            b.tape, b.tape_stride = _p(self.tape), self.tape.shape[1]
+        b.cursor = _p(self.cursor)
+        b.seed, b.tick, b.env_id0 = self.seed, self.tick, self.env_id0
+        b.f32_positions, b.auto_reset = int(self.f32_positions), int(self.auto_reset)
+        b.obs, b.achieved, b.desired = _p(self.obs), _p(self.achieved), _p(self.desired)
+        b.reward, b.done, b.info, b.term_obs = _p(self.reward), _p(self.done), _p(self.info), _p(self.term_obs)
+        return b
+
+    def reset(self, mask=None):
+        b = self._batch()
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        rc = self.L.gca_oracle_reset(C.byref(self.cfg), C.byref(b), _p(m))
+        assert rc == 0, rc
+        self.tick += 1
+        return self.obs
+
+    def step(self, actions):
+        a = np.zeros((self.B, 2), np.float64)
+        actions = np.asarray(actions, np.float64)
+        if actions.ndim == 1:
+            a[:, 0] = actions
+        else:
+            a[:, : actions.shape[1]] = actions
+        b = self._batch()
+        rc = self.L.gca_oracle_step(C.byref(self.cfg), C.byref(b), _p(a))
+        assert rc == 0, rc
+        self.tick += 1
+        return self.obs, self.reward, self.done, self.info
+
+    def observe(self):
+        b = self._batch()
+        rc = self.L.gca_oracle_observe(C.byref(self.cfg), C.byref(b))
+        assert rc == 0, rc
+        return self.obs
+
+
+def compute_reward(ag, g, radius, kind):
+    L = lib()
+    ag = np.ascontiguousarray(ag)
+    g = np.ascontiguousarray(g)
+    m = ag.size // 2
+    out = np.zeros(m, np.float32)
+    if ag.dtype == np.float32 and g.dtype == np.float32:
+        L.gca_oracle_compute_reward_f32(_p(ag), _p(g), m, float(radius), kind, _p(out))
+    else:
+        ag = np.ascontiguousarray(ag, np.float64)
+        g = np.ascontiguousarray(g, np.float64)
+        L.gca_oracle_compute_reward(_p(ag), _p(g), m, float(radius), kind, _p(out))
+    return out.reshape(ag.shape[:-1])

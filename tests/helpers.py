@@ -1,0 +1,73 @@
+"""Shared helpers for the parity tests: golden loading and state plumbing."""
+import os
+
+import numpy as np
+
+from gca_b200 import variants
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+STATE_KEYS = ("own_pos", "own_hs", "own_vel", "goal", "no_conflict", "ep_steps", "ipos", "ipos_is_f64", "ivel", "iflag")
+GOLDEN_VARIANTS = {"env": "SingleAircraftEnv", "env2": "SingleAircraft2Env", "her": "SingleAircraftHEREnv",
+                   "dher": "SingleAircraftDiscreteHEREnv", "mcts": "SingleAircraftMCTSEnv"}
+GOLDEN_N = (0, 1, 3, 80)
+
+
+def config_class(variant_key):
+    if variant_key == "mcts":
+        from Simulators.config import Config
+    else:
+        from gym_guidance_collision_avoidance_single.envs.config import Config
+    return Config
+
+
+def golden_config(variant_key):
+    return variants.make_config(GOLDEN_VARIANTS[variant_key], config_class(variant_key))
+
+
+def load_trace(variant_key, n):
+    return np.load(os.path.join(GOLDEN, "trace_%s_n%d.npz" % (variant_key, n)))
+
+
+def golden_state(g, prefix, sel=None):
+    """Canonical state dict from golden arrays with the given prefix ('s0_', or 'sa_'/'sr_' + index)."""
+    def get(k):
+        a = g[prefix + k]
+        return a if sel is None else a[sel]
+    st = {
+        "own_pos": get("own_pos").astype(np.float32),
+        "own_hs": np.stack([get("own_heading"), get("own_speed")], -1).astype(np.float64),
+        "own_vel": get("own_vel").astype(np.float64),
+        "goal": get("goal").astype(np.float64),
+        "no_conflict": get("no_conflict").astype(np.int32),
+        "ep_steps": get("steps").astype(np.int32),
+        "ipos": get("ipos").astype(np.float64),
+        "ipos_is_f64": get("ipos_is_f64").astype(np.uint8),
+        "ivel": get("ivel").astype(np.float32),
+        "iflag": get("iflag").astype(np.uint8),
+    }
+    return {k: np.ascontiguousarray(v) for k, v in st.items()}, get("own_vel_is_f32").astype(np.uint8)
+
+
+def assert_state_equal(got, want, what="", skip=("ep_steps",), rows=None):
+    for k in STATE_KEYS:
+        if k in skip:
+            continue
+        a, b = got[k], want[k]
+        if rows is not None:
+            a = a[rows]
+        assert a.shape == b.shape, (what, k, a.shape, b.shape)
+        if not np.array_equal(a, b):
+            bad = np.argwhere(a != b)
+            raise AssertionError("%s: state field %s differs at %s: got %r want %r" % (
+                what, k, bad[:4].tolist(), a[tuple(bad[0])], b[tuple(bad[0])]))
+
+
+def golden_actions(variant_key, g):
+    """[traces][T][2] action array of a golden file in the form the batched API takes:
+    int codes in column 0 for the discrete kinds (the MCTS env's (a0, a1) tuple is a0*3+a1)."""
+    a = np.array(g["actions"], np.float64)
+    if variant_key == "mcts":
+        a[..., 0] = a[..., 0] * 3 + a[..., 1]
+        a[..., 1] = 0
+    return a
