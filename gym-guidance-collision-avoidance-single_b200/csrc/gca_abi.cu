@@ -1,0 +1,406 @@
+// gca_abi.cu - the C ABI of include/gca.h: handle lifetime, argument checking, state
+// marshalling and the host-buffer (end-to-end) path.  No exception crosses the boundary.
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "gca.h"
+#include "gca_launch.h"
+
+using namespace gca;
+
+namespace {
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(GCA_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define GCA_CUDA(call)                                   \
+  do {                                                   \
+    cudaError_t e_ = (call);                             \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call);  \
+  } while (0)
+}  // namespace
+
+struct gca_env {
+  int device = 0, mode = 0, draws = 0, tile = 32;
+  gca_config cfg{};
+  uint64_t seed = 0;
+  uint32_t env_id0 = 0;
+  DevState s{};
+  int D = 0;
+  // host path (gca_step_host / gca_reset_host)
+  cudaStream_t stream = nullptr;
+  void* d_actions = nullptr;
+  gca_out d_out{};
+  std::vector<void*> allocs;
+};
+
+namespace {
+size_t real_size(const gca_env* e) { return e->mode == GCA_MODE_FAITHFUL ? sizeof(double) : sizeof(float); }
+
+int check_config(const gca_config* c) {
+  if (!c) return fail(GCA_ERR_INVALID, "config is NULL");
+  if (c->action_kind < GCA_ACT_DISCRETE9 || c->action_kind > GCA_ACT_DISCRETE3) return fail(GCA_ERR_INVALID, "bad action_kind");
+  if (c->obs_kind < GCA_OBS_VECTOR || c->obs_kind > GCA_OBS_NONE) return fail(GCA_ERR_INVALID, "bad obs_kind");
+  if (c->wall_kind < GCA_WALL_NONE || c->wall_kind > GCA_WALL_PENALTY) return fail(GCA_ERR_INVALID, "bad wall_kind");
+  if (!(c->window_width > 0) || !(c->window_height > 0)) return fail(GCA_ERR_INVALID, "window must be positive");
+  return GCA_OK;
+}
+
+template <typename T>
+int dev_alloc(gca_env* e, T** p, size_t count) {
+  void* q = nullptr;
+  GCA_CUDA(cudaMalloc(&q, (count ? count : 1) * sizeof(T)));
+  GCA_CUDA(cudaMemset(q, 0, (count ? count : 1) * sizeof(T)));
+  e->allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return GCA_OK;
+}
+
+StepArgs make_args(const gca_env* e, const void* actions, const gca_tape* tape, const gca_out* out, int auto_reset) {
+  StepArgs a{};
+  a.s = e->s;
+  a.cfg = e->cfg;
+  a.actions = actions;
+  if (tape) {
+    a.tape = tape->values;
+    a.tape_stride = tape->stride;
+    a.cursor = reinterpret_cast<long long*>(tape->cursor);
+  }
+  a.key0 = (uint32_t)e->seed;
+  a.key1 = (uint32_t)(e->seed >> 32);
+  a.env_id0 = e->env_id0;
+  a.D = e->D;
+  a.auto_reset = auto_reset;
+  if (out) {
+    a.obs = out->obs; a.achieved = out->achieved; a.desired = out->desired;
+    a.reward = out->reward; a.done = out->done; a.info = out->info;
+  }
+  return a;
+}
+
+int check_out(const gca_env* e, const gca_out* out, bool need_reward) {
+  if (!out) return fail(GCA_ERR_INVALID, "out is NULL");
+  if (e->cfg.obs_kind != GCA_OBS_NONE && !out->obs) return fail(GCA_ERR_INVALID, "out->obs is NULL");
+  const bool her = e->cfg.obs_kind == GCA_OBS_HER || e->cfg.obs_kind == GCA_OBS_DHER;
+  if (her && (!out->achieved || !out->desired)) return fail(GCA_ERR_INVALID, "HER kinds need achieved/desired buffers");
+  if (need_reward && (!out->reward || !out->done || !out->info)) return fail(GCA_ERR_INVALID, "reward/done/info buffers are NULL");
+  return GCA_OK;
+}
+
+int check_tape(const gca_env* e, const gca_tape* tape) {
+  if (e->draws == GCA_DRAWS_TAPE && (!tape || !tape->values || !tape->cursor))
+    return fail(GCA_ERR_INVALID, "handle was created with GCA_DRAWS_TAPE: a tape is required");
+  return GCA_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int gca_abi_version(void) { return GCA_ABI_VERSION; }
+
+const char* gca_last_error(void) { return g_err.c_str(); }
+
+int gca_obs_dim(const gca_config* cfg, int n) {
+  if (!cfg) return fail(GCA_ERR_INVALID, "config is NULL");
+  switch (cfg->obs_kind) {
+    case GCA_OBS_VECTOR:
+    case GCA_OBS_RAW: return 4 * n + 8;
+    case GCA_OBS_HER:
+    case GCA_OBS_DHER: return 4 * n + 6;
+    default: return 0;
+  }
+}
+
+int gca_create(const gca_config* cfg, int n_envs, int n_intruders, int mode, int draws, int device, uint64_t seed,
+               uint32_t env_id0, gca_env** out) {
+  if (!out) return fail(GCA_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (int rc = check_config(cfg)) return rc;
+  if (n_envs <= 0 || n_intruders < 0 || n_intruders > 4096) return fail(GCA_ERR_INVALID, "n_envs must be > 0 and 0 <= n_intruders <= 4096");
+  if (mode != GCA_MODE_FAITHFUL && mode != GCA_MODE_FAST) return fail(GCA_ERR_INVALID, "bad mode");
+  if (draws != GCA_DRAWS_TAPE && draws != GCA_DRAWS_PHILOX) return fail(GCA_ERR_INVALID, "bad draws");
+  int count = 0;
+  cudaError_t ce = cudaGetDeviceCount(&count);
+  if (ce != cudaSuccess || count <= 0)
+    return fail(GCA_ERR_CUDA, std::string("no usable CUDA device (libgca has no CPU path): ") +
+                                  (ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0"));
+  if (device < 0 || device >= count) return fail(GCA_ERR_INVALID, "device index out of range");
+  GCA_CUDA(cudaSetDevice(device));
+  gca_env* e = new (std::nothrow) gca_env();
+  if (!e) return fail(GCA_ERR_ALLOC, "out of host memory");
+  e->device = device; e->mode = mode; e->draws = draws; e->cfg = *cfg; e->seed = seed; e->env_id0 = env_id0;
+  e->D = gca_obs_dim(cfg, n_intruders);
+  if (const char* t = std::getenv("GCA_TILE")) {
+    const int v = std::atoi(t);
+    if (v == 8 || v == 16 || v == 32) e->tile = v;
+  }
+  DevState& s = e->s;
+  s.B = n_envs; s.N = n_intruders; s.Np = (n_intruders + 1) & ~1; s.W = (n_intruders + 31) / 32;
+  const size_t B = (size_t)n_envs, BN = B * (size_t)s.Np, BW = B * (size_t)s.W;
+  int rc = GCA_OK;
+  if (!rc) rc = dev_alloc(e, &s.own_pos, B);
+  if (!rc) rc = dev_alloc(e, &s.own_hs, B);
+  if (!rc) rc = dev_alloc(e, &s.own_vel, B);
+  if (!rc) rc = dev_alloc(e, &s.own_vel_f32, B);
+  if (!rc) rc = dev_alloc(e, &s.goal, B);
+  if (!rc) rc = dev_alloc(e, &s.counters, B);
+  if (!rc) {
+    if (mode == GCA_MODE_FAITHFUL) rc = dev_alloc(e, reinterpret_cast<double2**>(&s.ipos), BN);
+    else rc = dev_alloc(e, reinterpret_cast<float2**>(&s.ipos), BN);
+  }
+  if (!rc) rc = dev_alloc(e, &s.ivel, BN);
+  if (!rc) rc = dev_alloc(e, &s.iflag, BW);
+  if (!rc) rc = dev_alloc(e, &s.if64, mode == GCA_MODE_FAITHFUL ? BW : 1);
+  if (rc) {
+    gca_destroy(e);
+    return rc;
+  }
+  *out = e;
+  return GCA_OK;
+}
+
+int gca_destroy(gca_env* e) {
+  if (!e) return GCA_OK;
+  cudaSetDevice(e->device);
+  for (void* p : e->allocs) cudaFree(p);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+  return GCA_OK;
+}
+
+int gca_set_config(gca_env* e, const gca_config* cfg) {
+  if (!e) return fail(GCA_ERR_INVALID, "env is NULL");
+  if (int rc = check_config(cfg)) return rc;
+  if (gca_obs_dim(cfg, e->s.N) != e->D) return fail(GCA_ERR_STATE, "obs_kind change would alter the observation size");
+  e->cfg = *cfg;
+  return GCA_OK;
+}
+
+int gca_reset(gca_env* e, const uint8_t* mask, const gca_tape* tape, const gca_out* out, void* stream) {
+  if (!e) return fail(GCA_ERR_INVALID, "env is NULL");
+  if (int rc = check_out(e, out, false)) return rc;
+  if (int rc = check_tape(e, tape)) return rc;
+  GCA_CUDA(cudaSetDevice(e->device));
+  StepArgs a = make_args(e, nullptr, tape, out, 0);
+  a.mask = mask;
+  GCA_CUDA(launch_reset(e->mode == GCA_MODE_FAITHFUL, e->draws == GCA_DRAWS_TAPE, a, (cudaStream_t)stream));
+  return GCA_OK;
+}
+
+int gca_step(gca_env* e, const void* actions, const gca_tape* tape, int auto_reset, const gca_out* out, void* stream) {
+  if (!e) return fail(GCA_ERR_INVALID, "env is NULL");
+  if (!actions) return fail(GCA_ERR_INVALID, "actions is NULL");
+  if (int rc = check_out(e, out, true)) return rc;
+  if (int rc = check_tape(e, tape)) return rc;
+  GCA_CUDA(cudaSetDevice(e->device));
+  const StepArgs a = make_args(e, actions, tape, out, auto_reset);
+  GCA_CUDA(launch_step(e->mode == GCA_MODE_FAITHFUL, e->draws == GCA_DRAWS_TAPE, e->tile, a, (cudaStream_t)stream));
+  return GCA_OK;
+}
+
+int gca_observe(gca_env* e, const gca_out* out, void* stream) {
+  if (!e) return fail(GCA_ERR_INVALID, "env is NULL");
+  if (int rc = check_out(e, out, false)) return rc;
+  GCA_CUDA(cudaSetDevice(e->device));
+  const StepArgs a = make_args(e, nullptr, nullptr, out, 0);
+  GCA_CUDA(launch_observe(e->mode == GCA_MODE_FAITHFUL, a, (cudaStream_t)stream));
+  return GCA_OK;
+}
+
+// ------------------------------------------------------------------------------ host-buffer path
+static int ensure_host_path(gca_env* e) {
+  if (e->stream) return GCA_OK;
+  if (e->draws != GCA_DRAWS_PHILOX) return fail(GCA_ERR_STATE, "the host-buffer path needs GCA_DRAWS_PHILOX");
+  GCA_CUDA(cudaSetDevice(e->device));
+  GCA_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  const size_t B = (size_t)e->s.B, rs = real_size(e);
+  int rc = GCA_OK;
+  uint8_t* p = nullptr;
+  if (!rc) { rc = dev_alloc(e, &p, B * 2 * sizeof(double)); e->d_actions = p; }
+  if (!rc) { rc = dev_alloc(e, &p, B * (size_t)e->D * rs); e->d_out.obs = p; }
+  if (!rc) { rc = dev_alloc(e, &p, B * 2 * rs); e->d_out.achieved = p; }
+  if (!rc) { rc = dev_alloc(e, &p, B * 2 * rs); e->d_out.desired = p; }
+  if (!rc) { rc = dev_alloc(e, &p, B * rs); e->d_out.reward = p; }
+  if (!rc) { rc = dev_alloc(e, &p, B); e->d_out.done = p; }
+  if (!rc) { rc = dev_alloc(e, &p, B); e->d_out.info = p; }
+  return rc;
+}
+
+static int copy_out(gca_env* e, const gca_out* h, bool with_reward) {
+  const size_t B = (size_t)e->s.B, rs = real_size(e);
+  const bool her = e->cfg.obs_kind == GCA_OBS_HER || e->cfg.obs_kind == GCA_OBS_DHER;
+  if (h->obs && e->D) GCA_CUDA(cudaMemcpyAsync(h->obs, e->d_out.obs, B * (size_t)e->D * rs, cudaMemcpyDeviceToHost, e->stream));
+  if (her && h->achieved) GCA_CUDA(cudaMemcpyAsync(h->achieved, e->d_out.achieved, B * 2 * rs, cudaMemcpyDeviceToHost, e->stream));
+  if (her && h->desired) GCA_CUDA(cudaMemcpyAsync(h->desired, e->d_out.desired, B * 2 * rs, cudaMemcpyDeviceToHost, e->stream));
+  if (with_reward && h->reward) GCA_CUDA(cudaMemcpyAsync(h->reward, e->d_out.reward, B * rs, cudaMemcpyDeviceToHost, e->stream));
+  if (h->done) GCA_CUDA(cudaMemcpyAsync(h->done, e->d_out.done, B, cudaMemcpyDeviceToHost, e->stream));
+  if (h->info) GCA_CUDA(cudaMemcpyAsync(h->info, e->d_out.info, B, cudaMemcpyDeviceToHost, e->stream));
+  GCA_CUDA(cudaStreamSynchronize(e->stream));
+  return GCA_OK;
+}
+
+int gca_step_host(gca_env* e, const void* actions_host, int auto_reset, const gca_out* host_out) {
+  if (!e) return fail(GCA_ERR_INVALID, "env is NULL");
+  if (!actions_host || !host_out) return fail(GCA_ERR_INVALID, "actions/out is NULL");
+  if (int rc = ensure_host_path(e)) return rc;
+  const size_t B = (size_t)e->s.B;
+  const size_t abytes = e->cfg.action_kind == GCA_ACT_CONTINUOUS2 ? B * 2 * real_size(e) : B * sizeof(int32_t);
+  GCA_CUDA(cudaMemcpyAsync(e->d_actions, actions_host, abytes, cudaMemcpyHostToDevice, e->stream));
+  if (int rc = gca_step(e, e->d_actions, nullptr, auto_reset, &e->d_out, e->stream)) return rc;
+  return copy_out(e, host_out, true);
+}
+
+int gca_reset_host(gca_env* e, const gca_out* host_out) {
+  if (!e) return fail(GCA_ERR_INVALID, "env is NULL");
+  if (!host_out) return fail(GCA_ERR_INVALID, "out is NULL");
+  if (int rc = ensure_host_path(e)) return rc;
+  if (int rc = gca_reset(e, nullptr, nullptr, &e->d_out, e->stream)) return rc;
+  return copy_out(e, host_out, false);
+}
+
+// ------------------------------------------------------------------------------ full-state access
+int gca_get_state(gca_env* e, const gca_host_state* h) {
+  if (!e || !h) return fail(GCA_ERR_INVALID, "env/state is NULL");
+  GCA_CUDA(cudaSetDevice(e->device));
+  GCA_CUDA(cudaDeviceSynchronize());
+  const DevState& s = e->s;
+  const size_t B = (size_t)s.B, N = (size_t)s.N, Np = (size_t)s.Np, W = (size_t)s.W;
+  if (h->own_pos) GCA_CUDA(cudaMemcpy(h->own_pos, s.own_pos, B * sizeof(float2), cudaMemcpyDeviceToHost));
+  if (h->own_hs) GCA_CUDA(cudaMemcpy(h->own_hs, s.own_hs, B * sizeof(double2), cudaMemcpyDeviceToHost));
+  if (h->own_vel) GCA_CUDA(cudaMemcpy(h->own_vel, s.own_vel, B * sizeof(double2), cudaMemcpyDeviceToHost));
+  if (h->own_vel_is_f32) GCA_CUDA(cudaMemcpy(h->own_vel_is_f32, s.own_vel_f32, B, cudaMemcpyDeviceToHost));
+  if (h->goal) GCA_CUDA(cudaMemcpy(h->goal, s.goal, B * sizeof(double2), cudaMemcpyDeviceToHost));
+  if (h->no_conflict || h->ep_steps || h->tick) {
+    std::vector<int4> c(B);
+    GCA_CUDA(cudaMemcpy(c.data(), s.counters, B * sizeof(int4), cudaMemcpyDeviceToHost));
+    for (size_t b = 0; b < B; ++b) {
+      if (h->no_conflict) h->no_conflict[b] = c[b].x;
+      if (h->ep_steps) h->ep_steps[b] = c[b].y;
+      if (h->tick) h->tick[b] = (uint32_t)c[b].z;
+    }
+  }
+  if (N == 0) return GCA_OK;
+  if (h->ipos) {
+    if (e->mode == GCA_MODE_FAITHFUL) {
+      std::vector<double2> p(B * Np);
+      GCA_CUDA(cudaMemcpy(p.data(), s.ipos, p.size() * sizeof(double2), cudaMemcpyDeviceToHost));
+      for (size_t b = 0; b < B; ++b)
+        for (size_t i = 0; i < N; ++i) {
+          h->ipos[2 * (b * N + i)] = p[b * Np + i].x;
+          h->ipos[2 * (b * N + i) + 1] = p[b * Np + i].y;
+        }
+    } else {
+      std::vector<float2> p(B * Np);
+      GCA_CUDA(cudaMemcpy(p.data(), s.ipos, p.size() * sizeof(float2), cudaMemcpyDeviceToHost));
+      for (size_t b = 0; b < B; ++b)
+        for (size_t i = 0; i < N; ++i) {
+          h->ipos[2 * (b * N + i)] = (double)p[b * Np + i].x;
+          h->ipos[2 * (b * N + i) + 1] = (double)p[b * Np + i].y;
+        }
+    }
+  }
+  if (h->ivel) {
+    std::vector<float2> v(B * Np);
+    GCA_CUDA(cudaMemcpy(v.data(), s.ivel, v.size() * sizeof(float2), cudaMemcpyDeviceToHost));
+    for (size_t b = 0; b < B; ++b)
+      for (size_t i = 0; i < N; ++i) {
+        h->ivel[2 * (b * N + i)] = v[b * Np + i].x;
+        h->ivel[2 * (b * N + i) + 1] = v[b * Np + i].y;
+      }
+  }
+  auto unpack = [&](const uint32_t* dev, uint8_t* dst) -> int {
+    std::vector<uint32_t> w(B * W);
+    GCA_CUDA(cudaMemcpy(w.data(), dev, w.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (size_t b = 0; b < B; ++b)
+      for (size_t i = 0; i < N; ++i) dst[b * N + i] = (w[b * W + i / 32] >> (i % 32)) & 1u;
+    return GCA_OK;
+  };
+  if (h->iflag)
+    if (int rc = unpack(s.iflag, h->iflag)) return rc;
+  if (h->ipos_is_f64) {
+    if (e->mode == GCA_MODE_FAITHFUL) {
+      if (int rc = unpack(s.if64, h->ipos_is_f64)) return rc;
+    } else {
+      std::memset(h->ipos_is_f64, 0, B * N);
+    }
+  }
+  return GCA_OK;
+}
+
+int gca_set_state(gca_env* e, const gca_host_state* h) {
+  if (!e || !h) return fail(GCA_ERR_INVALID, "env/state is NULL");
+  GCA_CUDA(cudaSetDevice(e->device));
+  GCA_CUDA(cudaDeviceSynchronize());
+  const DevState& s = e->s;
+  const size_t B = (size_t)s.B, N = (size_t)s.N, Np = (size_t)s.Np, W = (size_t)s.W;
+  if (h->own_pos) GCA_CUDA(cudaMemcpy(s.own_pos, h->own_pos, B * sizeof(float2), cudaMemcpyHostToDevice));
+  if (h->own_hs) GCA_CUDA(cudaMemcpy(s.own_hs, h->own_hs, B * sizeof(double2), cudaMemcpyHostToDevice));
+  if (h->own_vel) GCA_CUDA(cudaMemcpy(s.own_vel, h->own_vel, B * sizeof(double2), cudaMemcpyHostToDevice));
+  if (h->own_vel_is_f32) GCA_CUDA(cudaMemcpy(s.own_vel_f32, h->own_vel_is_f32, B, cudaMemcpyHostToDevice));
+  if (h->goal) GCA_CUDA(cudaMemcpy(s.goal, h->goal, B * sizeof(double2), cudaMemcpyHostToDevice));
+  if (h->no_conflict || h->ep_steps || h->tick) {
+    std::vector<int4> c(B);
+    GCA_CUDA(cudaMemcpy(c.data(), s.counters, B * sizeof(int4), cudaMemcpyDeviceToHost));
+    for (size_t b = 0; b < B; ++b) {
+      if (h->no_conflict) c[b].x = h->no_conflict[b];
+      if (h->ep_steps) c[b].y = h->ep_steps[b];
+      if (h->tick) c[b].z = (int)h->tick[b];
+    }
+    GCA_CUDA(cudaMemcpy(s.counters, c.data(), B * sizeof(int4), cudaMemcpyHostToDevice));
+  }
+  if (N == 0) return GCA_OK;
+  if (h->ipos) {
+    if (e->mode == GCA_MODE_FAITHFUL) {
+      std::vector<double2> p(B * Np, make_double2(0., 0.));
+      for (size_t b = 0; b < B; ++b)
+        for (size_t i = 0; i < N; ++i) p[b * Np + i] = make_double2(h->ipos[2 * (b * N + i)], h->ipos[2 * (b * N + i) + 1]);
+      GCA_CUDA(cudaMemcpy(s.ipos, p.data(), p.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    } else {
+      std::vector<float2> p(B * Np, make_float2(0.f, 0.f));
+      for (size_t b = 0; b < B; ++b)
+        for (size_t i = 0; i < N; ++i)
+          p[b * Np + i] = make_float2((float)h->ipos[2 * (b * N + i)], (float)h->ipos[2 * (b * N + i) + 1]);
+      GCA_CUDA(cudaMemcpy(s.ipos, p.data(), p.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    }
+  }
+  if (h->ivel) {
+    std::vector<float2> v(B * Np, make_float2(0.f, 0.f));
+    for (size_t b = 0; b < B; ++b)
+      for (size_t i = 0; i < N; ++i) v[b * Np + i] = make_float2(h->ivel[2 * (b * N + i)], h->ivel[2 * (b * N + i) + 1]);
+    GCA_CUDA(cudaMemcpy(s.ivel, v.data(), v.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  }
+  auto pack = [&](const uint8_t* src, uint32_t* dev) -> int {
+    std::vector<uint32_t> w(B * W, 0u);
+    for (size_t b = 0; b < B; ++b)
+      for (size_t i = 0; i < N; ++i)
+        if (src[b * N + i]) w[b * W + i / 32] |= 1u << (i % 32);
+    GCA_CUDA(cudaMemcpy(dev, w.data(), w.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    return GCA_OK;
+  };
+  if (h->iflag)
+    if (int rc = pack(h->iflag, s.iflag)) return rc;
+  if (h->ipos_is_f64 && e->mode == GCA_MODE_FAITHFUL)
+    if (int rc = pack(h->ipos_is_f64, s.if64)) return rc;
+  return GCA_OK;
+}
+
+int gca_compute_reward(const void* ag, const void* g, int64_t m, double radius, int kind, int is_f64, float* out,
+                       int device, void* stream) {
+  if (m < 0 || (m > 0 && (!ag || !g || !out))) return fail(GCA_ERR_INVALID, "bad buffers");
+  if (kind != GCA_OBS_HER && kind != GCA_OBS_DHER) return fail(GCA_ERR_INVALID, "kind must be GCA_OBS_HER or GCA_OBS_DHER");
+  GCA_CUDA(cudaSetDevice(device));
+  GCA_CUDA(launch_compute_reward(ag, g, (long long)m, radius, kind, is_f64, out, (cudaStream_t)stream));
+  return GCA_OK;
+}
+
+}  // extern "C"

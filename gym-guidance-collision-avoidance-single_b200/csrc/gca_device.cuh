@@ -1,0 +1,338 @@
+// gca_device.cuh - device-side building blocks of the step hot path (sm_100a).
+//
+// Compiled with -fmad=false: every arithmetic operation that has to reproduce the reference's
+// NumPy scalar rounding is written with an explicit round-to-nearest intrinsic, and the one
+// place where the reference (through OpenBLAS ddot) fuses is an explicit __fma_rn.
+// Citations: PKG = gym_guidance_collision_avoidance_single/envs of the reference tree.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gca.h"
+#include "gca_math.h"
+
+namespace gca {
+
+// ------------------------------------------------------------------------------ device state
+// SoA, env-major.  One warp reads one env's intruder row as a contiguous segment.
+struct DevState {
+  float2* own_pos;        // [B]
+  double2* own_hs;        // [B]   (heading, speed)
+  double2* own_vel;       // [B]
+  uint8_t* own_vel_f32;   // [B]
+  double2* goal;          // [B]
+  int4* counters;         // [B]   (no_conflict, ep_steps, tick, episodes)
+  void* ipos;             // FAST: float2 [B][Np]   FAITHFUL: double2 [B][Np]
+  float2* ivel;           // [B][Np]
+  uint32_t* iflag;        // [B][W]  bit i%32 of word i/32 = Aircraft.conflict of intruder i
+  uint32_t* if64;         // [B][W]  FAITHFUL only: position dtype is f64 (Q3)
+  int B, N, Np, W;
+};
+
+struct StepArgs {
+  DevState s;
+  gca_config cfg;
+  const void* actions;
+  const double* tape;
+  long long tape_stride;
+  long long* cursor;
+  const uint8_t* mask;    // reset only
+  uint32_t key0, key1, env_id0;
+  int D;                  // observation row length
+  int auto_reset;
+  void* obs;
+  void* achieved;
+  void* desired;
+  void* reward;
+  uint8_t* done;
+  uint8_t* info;
+};
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// ------------------------------------------------------------------------------ Philox4x32-10
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+
+__device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
+  const unsigned long long v = ((unsigned long long)(a >> 5) << 26) | (unsigned long long)(b >> 6);
+  return __dmul_rn((double)v, 1.0 / 9007199254740992.0);
+}
+
+// ------------------------------------------------------------------------------ draw sources
+// A Draws object belongs to one env.  TAPE: values recorded from the reference's global numpy
+// stream, consumed in the reference's order.  PHILOX: counter = (env id, tick, slot, block).
+template <bool TAPE>
+struct Draws;
+
+template <>
+struct Draws<true> {
+  const double* tape;
+  long long cur;
+  __device__ __forceinline__ double next() { return tape[cur++]; }
+};
+
+template <>
+struct Draws<false> {
+  uint32_t k0, k1, env, tick;
+  __device__ __forceinline__ void uniform2(uint32_t slot, uint32_t block, double& u0, double& u1) const {
+    const uint4 w = philox4x32_10(make_uint4(env, tick, slot, block), k0, k1);
+    u0 = u53(w.x, w.y);
+    u1 = u53(w.z, w.w);
+  }
+};
+
+// np.random.uniform(low=[0,0], high=[W,H])   PKG/SingleAircraftEnv.py:240-244
+template <bool TAPE>
+__device__ __forceinline__ void draw_pos(Draws<TAPE>& d, const gca_config& c, uint32_t slot, uint32_t block,
+                                         double& x, double& y) {
+  if constexpr (TAPE) {
+    x = d.next();
+    y = d.next();
+  } else {
+    double u0, u1;
+    d.uniform2(slot, block, u0, u1);
+    x = __dadd_rn(0.0, __dmul_rn(__dadd_rn(c.window_width, -0.0), u0));   // low + (high - low) * u
+    y = __dadd_rn(0.0, __dmul_rn(__dadd_rn(c.window_height, -0.0), u1));
+  }
+}
+
+// random_speed(), random_heading()   PKG/SingleAircraftEnv.py:246-250
+template <bool TAPE>
+__device__ __forceinline__ void draw_speed_heading(Draws<TAPE>& d, const gca_config& c, uint32_t slot,
+                                                   double& speed, double& heading) {
+  if constexpr (TAPE) {
+    speed = d.next();
+    heading = d.next();
+  } else {
+    double u0, u1;
+    d.uniform2(slot, GCA_BLOCK_SPEED_HEADING, u0, u1);
+    speed = __dadd_rn(c.min_speed, __dmul_rn(__dadd_rn(c.max_speed, -c.min_speed), u0));
+    heading = __dadd_rn(0.0, __dmul_rn(6.283185307179586, u1));
+  }
+}
+
+// the two np.random.normal(0, sigma) calls of Ownship.step   PKG/SingleAircraftEnv.py:301,304
+template <bool TAPE>
+__device__ __forceinline__ void draw_own_noise(Draws<TAPE>& d, const gca_config& c, double& nh, double& ns) {
+  if constexpr (TAPE) {
+    nh = d.next();
+    ns = d.next();
+  } else {
+    double u0, u1, sn, cs;
+    d.uniform2(GCA_SLOT_OWNSHIP, 0u, u0, u1);
+    const double r = __dsqrt_rn(__dmul_rn(-2.0, gca_log(__dadd_rn(1.0, -u0))));
+    gca_sincos(__dmul_rn(6.283185307179586, u1), &sn, &cs);
+    nh = __dadd_rn(0.0, __dmul_rn(c.heading_sigma, __dmul_rn(r, cs)));
+    ns = __dadd_rn(0.0, __dmul_rn(c.speed_sigma, __dmul_rn(r, sn)));
+  }
+}
+
+// ------------------------------------------------------------------------------ distances
+// dist(): np.linalg.norm(p1 - p2)   PKG/SingleAircraftEnv.py:312-313
+__device__ __forceinline__ float dist_f32(float ax, float ay, float bx, float by) {
+  const float dx = __fadd_rn(ax, -bx), dy = __fadd_rn(ay, -by);
+  return __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));      // sdot: no FMA
+}
+
+__device__ __forceinline__ double dist_f64(double ax, double ay, double bx, double by) {
+  const double dx = __dadd_rn(ax, -bx), dy = __dadd_rn(ay, -by);
+  return __dsqrt_rn(__fma_rn(dy, dy, __dmul_rn(dx, dx)));                  // ddot tail: FMA on the 2nd product
+}
+
+// position_range.contains(p): inclusive, f32 bounds   PKG/SingleAircraftEnv.py:38-41,153
+__device__ __forceinline__ bool in_map_f32(const gca_config& c, float x, float y) {
+  return x >= 0.0f && y >= 0.0f && x <= (float)c.window_width && y <= (float)c.window_height;
+}
+__device__ __forceinline__ bool in_map_f64(const gca_config& c, double x, double y) {
+  return x >= 0.0 && y >= 0.0 && x <= (double)(float)c.window_width && y <= (double)(float)c.window_height;
+}
+
+// ------------------------------------------------------------------------------ intruder record
+// Position carried as a double that holds either an f32 value (is64 == false) or a true f64.
+struct Intruder {
+  double px, py;
+  float vx, vy;
+  bool is64;
+};
+
+template <bool FAITH>
+__device__ __forceinline__ void load_intruder(const DevState& s, size_t idx, Intruder& it) {
+  if constexpr (FAITH) {
+    const double2 p = reinterpret_cast<const double2*>(s.ipos)[idx];
+    it.px = p.x;
+    it.py = p.y;
+  } else {
+    const float2 p = reinterpret_cast<const float2*>(s.ipos)[idx];
+    it.px = (double)p.x;
+    it.py = (double)p.y;
+  }
+  const float2 v = s.ivel[idx];
+  it.vx = v.x;
+  it.vy = v.y;
+}
+
+template <bool FAITH>
+__device__ __forceinline__ void store_ipos(const DevState& s, size_t idx, double px, double py) {
+  if constexpr (FAITH) reinterpret_cast<double2*>(s.ipos)[idx] = make_double2(px, py);
+  else reinterpret_cast<float2*>(s.ipos)[idx] = make_float2((float)px, (float)py);
+}
+
+// ownship <-> intruder distance and the `< threshold` tests in the dtype the reference uses
+template <bool FAITH>
+__device__ __forceinline__ void separation(const gca_config& c, float ox, float oy, const Intruder& it, double px,
+                                           double py, bool& lt_sep, bool& lt_nmac, bool& lt_init) {
+  if (FAITH && it.is64) {
+    const double d = dist_f64((double)ox, (double)oy, px, py);
+    lt_sep = d < c.minimum_separation;
+    lt_nmac = d < c.nmac_dist;
+    lt_init = d < c.initial_min_dist;
+  } else {
+    const float d = dist_f32(ox, oy, (float)px, (float)py);
+    lt_sep = d < (float)c.minimum_separation;   // f32 scalar vs Python float compares in f32 (NumPy 2)
+    lt_nmac = d < (float)c.nmac_dist;
+    lt_init = d < (float)c.initial_min_dist;
+  }
+}
+
+// Aircraft(random_pos(), random_speed(), random_heading()) + rejection loop
+// PKG/SingleAircraftEnv.py:229-238,269-278 (reset: :80-88)
+template <bool FAITH, bool TAPE>
+__device__ __forceinline__ void spawn(Draws<TAPE>& d, const gca_config& c, uint32_t slot, float ox, float oy,
+                                      Intruder& it) {
+  double x, y, speed, heading, sn, cs;
+  draw_pos(d, c, slot, GCA_BLOCK_POS, x, y);
+  draw_speed_heading(d, c, slot, speed, heading);
+  it.px = (double)(float)x;
+  it.py = (double)(float)y;
+  it.is64 = false;
+  gca_sincos(heading, &sn, &cs);
+  it.vx = (float)__dmul_rn(speed, cs);
+  it.vy = (float)__dmul_rn(speed, sn);
+  int retries = 0;
+  for (;;) {
+    bool a, b, lt_init;
+    separation<FAITH>(c, ox, oy, it, it.px, it.py, a, b, lt_init);
+    if (!lt_init) break;
+    if (!TAPE && retries >= GCA_MAX_SPAWN_RETRIES) break;
+    draw_pos(d, c, slot, GCA_BLOCK_RETRY0 + (uint32_t)retries, x, y);
+    ++retries;
+    if constexpr (FAITH) {       // intruder.position = self.random_pos(): a raw f64 array (Q3)
+      it.px = x;
+      it.py = y;
+      it.is64 = true;
+    } else {                     // FAST storage rule: rounded to f32
+      it.px = (double)(float)x;
+      it.py = (double)(float)y;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ observation
+template <bool FAITH>
+using real_t = typename std::conditional<FAITH, double, float>::type;
+
+__device__ __forceinline__ bool own_first(const gca_config& c) {
+  return c.obs_kind == GCA_OBS_HER || c.obs_kind == GCA_OBS_DHER;
+}
+
+// normalize_velocity() on an f32 velocity   PKG/SingleAircraftEnv.py:104-106
+__device__ __forceinline__ float norm_vel_f32(const gca_config& c, float v) {
+  return __fdiv_rn(__fadd_rn(v, (float)c.max_speed), (float)__dmul_rn(c.max_speed, 2.0));
+}
+__device__ __forceinline__ double norm_vel_f64(const gca_config& c, double v) {
+  return __ddiv_rn(__dadd_rn(v, c.max_speed), __dmul_rn(c.max_speed, 2.0));
+}
+
+// the four entries of intruder i   PKG/SingleAircraftEnv.py:108-114 (raw: Simulators/SingleAircraftMCTSEnv.py:107-112)
+template <bool FAITH>
+__device__ __forceinline__ void write_obs_intruder(const StepArgs& a, size_t env, int i, const Intruder& it,
+                                                   double px, double py) {
+  using R = real_t<FAITH>;
+  const gca_config& c = a.cfg;
+  if (c.obs_kind == GCA_OBS_NONE) return;
+  R o0, o1, o2, o3;
+  if (c.obs_kind == GCA_OBS_RAW) {
+    o0 = (R)px; o1 = (R)py; o2 = (R)it.vx; o3 = (R)it.vy;
+  } else {
+    if (FAITH && it.is64) {
+      o0 = (R)__ddiv_rn(px, c.ob_window_width);
+      o1 = (R)__ddiv_rn(py, c.ob_window_height);
+    } else {
+      o0 = (R)__fdiv_rn((float)px, (float)c.ob_window_width);
+      o1 = (R)__fdiv_rn((float)py, (float)c.ob_window_height);
+    }
+    o2 = (R)norm_vel_f32(c, it.vx);
+    o3 = (R)norm_vel_f32(c, it.vy);
+  }
+  const bool of = own_first(c);
+  R* p = reinterpret_cast<R*>(a.obs) + env * (size_t)a.D + (of ? 6 : 0) + 4 * (size_t)i;
+  if constexpr (FAITH) {
+    reinterpret_cast<double2*>(p)[0] = make_double2(o0, o1);
+    reinterpret_cast<double2*>(p)[1] = make_double2(o2, o3);
+  } else {
+    if (!of) {
+      *reinterpret_cast<float4*>(p) = make_float4(o0, o1, o2, o3);
+    } else {   // HER rows start at element 6: only 8-byte aligned
+      reinterpret_cast<float2*>(p)[0] = make_float2(o0, o1);
+      reinterpret_cast<float2*>(p)[1] = make_float2(o2, o3);
+    }
+  }
+}
+
+// ownship entries, goal entries, achieved/desired   PKG/SingleAircraftEnv.py:115-124,
+// PKG/SingleAircraftHEREnv.py:113-139, PKG/SingleAircraftDiscreteHEREnv.py:128-133
+template <bool FAITH>
+__device__ __forceinline__ void write_obs_own(const StepArgs& a, size_t env, float px, float py, double vx, double vy,
+                                              bool vel_is_f32, double heading, double speed, double gx, double gy) {
+  using R = real_t<FAITH>;
+  const gca_config& c = a.cfg;
+  if (c.obs_kind == GCA_OBS_NONE) return;
+  const bool of = own_first(c);
+  R* row = reinterpret_cast<R*>(a.obs) + env * (size_t)a.D;
+  R* o = row + (of ? 0 : 4 * (size_t)a.s.N);
+  if (c.obs_kind == GCA_OBS_RAW) {
+    o[0] = (R)px; o[1] = (R)py; o[2] = (R)vx; o[3] = (R)vy; o[4] = (R)speed; o[5] = (R)heading;
+    o[6] = (R)gx; o[7] = (R)gy;
+    return;
+  }
+  const float nx = __fdiv_rn(px, (float)c.ob_window_width), ny = __fdiv_rn(py, (float)c.ob_window_height);
+  o[0] = (R)nx;
+  o[1] = (R)ny;
+  if (vel_is_f32) {
+    o[2] = (R)norm_vel_f32(c, (float)vx);
+    o[3] = (R)norm_vel_f32(c, (float)vy);
+  } else {
+    o[2] = (R)norm_vel_f64(c, vx);
+    o[3] = (R)norm_vel_f64(c, vy);
+  }
+  o[4] = (R)__ddiv_rn(__dadd_rn(speed, -c.ob_min_speed), __dadd_rn(c.ob_max_speed, -c.ob_min_speed));
+  o[5] = (R)__ddiv_rn(heading, __dmul_rn(2.0, 3.141592653589793));
+  if (!of) {
+    o[6] = (R)__ddiv_rn(gx, c.ob_window_width);
+    o[7] = (R)__ddiv_rn(gy, c.ob_window_height);
+  } else {
+    R* ag = reinterpret_cast<R*>(a.achieved) + 2 * env;
+    R* dg = reinterpret_cast<R*>(a.desired) + 2 * env;
+    if (c.obs_kind == GCA_OBS_HER) {
+      ag[0] = (R)nx; ag[1] = (R)ny;
+      dg[0] = (R)__ddiv_rn(gx, c.ob_window_width);
+      dg[1] = (R)__ddiv_rn(gy, c.ob_window_height);
+    } else {
+      ag[0] = (R)px; ag[1] = (R)py;
+      dg[0] = (R)gx; dg[1] = (R)gy;
+    }
+  }
+}
+
+}  // namespace gca

@@ -1,0 +1,46 @@
+// gca_reward.cu - HER relabelling reward, one thread per (achieved, desired) pair.
+//   PKG/SingleAircraftHEREnv.py:194-196          -(norm(ag - g) > goal_radius).astype(f32)
+//   PKG/SingleAircraftDiscreteHEREnv.py:184-186   (norm(ag - g) < goal_radius).astype(f32)
+// np.linalg.norm(x, axis=-1) = sqrt(add.reduce(x*x)): plain multiply / add, in the input dtype.
+// 20 bytes per pair (f32) or 36 (f64): purely HBM-bound, 16-byte loads, grid-stride.
+#include "gca_launch.h"
+
+namespace gca {
+
+template <typename T, typename T2>
+__global__ void __launch_bounds__(256) reward_kernel(const T2* __restrict__ ag, const T2* __restrict__ g, long long m,
+                                                     double radius, int kind, float* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+    const T2 a = ag[i], b = g[i];
+    bool gt, lt;
+    if constexpr (sizeof(T) == 8) {
+      const double dx = __dadd_rn(a.x, -b.x), dy = __dadd_rn(a.y, -b.y);
+      const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+      gt = d > radius;
+      lt = d < radius;
+    } else {
+      const float dx = __fadd_rn(a.x, -b.x), dy = __fadd_rn(a.y, -b.y);
+      const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+      gt = d > (float)radius;
+      lt = d < (float)radius;
+    }
+    out[i] = kind == GCA_OBS_HER ? -(gt ? 1.0f : 0.0f) : (lt ? 1.0f : 0.0f);
+  }
+}
+
+cudaError_t launch_compute_reward(const void* ag, const void* g, long long m, double radius, int kind, int is_f64,
+                                  float* out, cudaStream_t st) {
+  if (m <= 0) return cudaSuccess;
+  long long blocks = (m + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (is_f64)
+    reward_kernel<double, double2><<<(unsigned)blocks, 256, 0, st>>>((const double2*)ag, (const double2*)g, m, radius,
+                                                                      kind, out);
+  else
+    reward_kernel<float, float2><<<(unsigned)blocks, 256, 0, st>>>((const float2*)ag, (const float2*)g, m, radius, kind,
+                                                                    out);
+  return cudaGetLastError();
+}
+
+}  // namespace gca

@@ -34,8 +34,9 @@ class GcaConfig(C.Structure):
 
 
 class GcaHostState(C.Structure):
-    _fields_ = [("own_pos", C.c_void_p), ("own_hs", C.c_void_p), ("own_vel", C.c_void_p), ("goal", C.c_void_p),
-                ("no_conflict", C.c_void_p), ("ep_steps", C.c_void_p), ("ipos", C.c_void_p),
+    _fields_ = [("own_pos", C.c_void_p), ("own_hs", C.c_void_p), ("own_vel", C.c_void_p),
+                ("own_vel_is_f32", C.c_void_p), ("goal", C.c_void_p),
+                ("no_conflict", C.c_void_p), ("ep_steps", C.c_void_p), ("tick", C.c_void_p), ("ipos", C.c_void_p),
                 ("ipos_is_f64", C.c_void_p), ("ivel", C.c_void_p), ("iflag", C.c_void_p)]
 
 
@@ -79,8 +80,7 @@ def load():
         "gca_reset_host": ([vp, P(GcaOut)], C.c_int),
         "gca_get_state": ([vp, P(GcaHostState)], C.c_int),
         "gca_set_state": ([vp, P(GcaHostState)], C.c_int),
-        "gca_get_tick": ([vp, P(u32)], C.c_int),
-        "gca_set_tick": ([vp, u32], C.c_int),
+        "gca_observe": ([vp, P(GcaOut), vp], C.c_int),
         "gca_compute_reward": ([vp, vp, i64, C.c_double, i32, i32, vp, i32, vp], C.c_int),
     }
     for name, (argtypes, restype) in sigs.items():

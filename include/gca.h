@@ -103,10 +103,12 @@ typedef struct gca_config {
 typedef struct gca_host_state {
   float* own_pos;            /* [B][2]   f32 position            PKG/SingleAircraftEnv.py:271 */
   double* own_hs;            /* [B][2]   heading, speed          :272-273 */
-  double* own_vel;           /* [B][2]   velocity (f32-valued right after reset, :276,:308) */
+  double* own_vel;           /* [B][2]   velocity :276,:308 */
+  uint8_t* own_vel_is_f32;   /* [B]      velocity is still the f32 array made by reset (Q2) */
   double* goal;              /* [B][2]   :93 */
   int32_t* no_conflict;      /* [B]      :96 */
   int32_t* ep_steps;         /* [B]      steps since reset (StackEnv :118; TimeLimit) */
+  uint32_t* tick;            /* [B]      Philox tick: +1 per step and per explicit reset of that env */
   double* ipos;              /* [B][N][2] intruder positions (f32-valued unless flagged) */
   uint8_t* ipos_is_f64;      /* [B][N]   position dtype is f64 (retried spawn, Q3) */
   float* ivel;               /* [B][N][2] :276 */
@@ -165,13 +167,13 @@ int gca_step(gca_env* env, const void* actions, const gca_tape* tape, int auto_r
 int gca_step_host(gca_env* env, const void* actions_host, int auto_reset, const gca_out* host_out);
 int gca_reset_host(gca_env* env, const gca_out* host_out);
 
-/* Full-state access (teacher-forced parity, MCTS root states, checkpointing).  Synchronous. */
+/* _get_ob() of the current state without stepping (PKG/SingleAircraftEnv.py:100-126). */
+int gca_observe(gca_env* env, const gca_out* out, void* stream);
+
+/* Full-state access (teacher-forced parity, MCTS root states, checkpointing).  Synchronous.
+ * NULL members of the view are skipped. */
 int gca_get_state(gca_env* env, const gca_host_state* dst);
 int gca_set_state(gca_env* env, const gca_host_state* src);
-
-/* Monotone launch counter used as the Philox `tick`. */
-int gca_get_tick(gca_env* env, uint32_t* tick);
-int gca_set_tick(gca_env* env, uint32_t tick);
 
 /* HER relabelling reward, PKG/SingleAircraftHEREnv.py:194-196 (kind GCA_OBS_HER:
  * -(d > radius), always -0.0f for normalised goals, Q14) and

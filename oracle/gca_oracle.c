@@ -92,6 +92,7 @@ typedef struct env_view {
   int64_t* cursor;
   uint64_t seed;
   uint32_t tick, env_id;
+  uint32_t* tick_store;
 } env_view;
 
 static double tape_next(env_view* e) { return e->tape[(*e->cursor)++]; }
@@ -375,7 +376,7 @@ static void bind(env_view* e, const gca_config* cfg, gca_oracle_batch* b, int i)
   e->own_pos = b->st.own_pos + 2 * (size_t)i;
   e->own_hs = b->st.own_hs + 2 * (size_t)i;
   e->own_vel = b->st.own_vel + 2 * (size_t)i;
-  e->own_vel_is_f32 = b->own_vel_is_f32 + i;
+  e->own_vel_is_f32 = b->st.own_vel_is_f32 + i;
   e->goal = b->st.goal + 2 * (size_t)i;
   e->no_conflict = b->st.no_conflict + i;
   e->ep_steps = b->st.ep_steps + i;
@@ -389,7 +390,8 @@ static void bind(env_view* e, const gca_config* cfg, gca_oracle_batch* b, int i)
   e->tape = b->tape ? b->tape + (size_t)i * b->tape_stride : NULL;
   e->cursor = b->cursor ? b->cursor + i : NULL;
   e->seed = b->seed;
-  e->tick = b->tick;
+  e->tick_store = b->st.tick ? b->st.tick + i : NULL;
+  e->tick = e->tick_store ? *e->tick_store : 0u;
   e->env_id = b->env_id0 + (uint32_t)i;
 }
 
@@ -410,6 +412,7 @@ int gca_oracle_step(const gca_config* cfg, gca_oracle_batch* b, const double* ac
       reset_env(&e);
       observe_env(&e, row(b->obs, i, D), row(b->achieved, i, 2), row(b->desired, i, 2));
     }
+    if (e.tick_store) *e.tick_store = e.tick + 1u;   /* an auto-reset shares the step's tick (RESET slots) */
   }
   return GCA_OK;
 }
@@ -423,6 +426,7 @@ int gca_oracle_reset(const gca_config* cfg, gca_oracle_batch* b, const uint8_t* 
     bind(&e, cfg, b, i);
     reset_env(&e);
     observe_env(&e, row(b->obs, i, D), row(b->achieved, i, 2), row(b->desired, i, 2));
+    if (e.tick_store) *e.tick_store = e.tick + 1u;
     if (b->done) b->done[i] = 0;
     if (b->info) b->info[i] = 0;
   }

@@ -26,16 +26,15 @@ enum { GCA_TRIG_LIBM = 0,    /* cos/sin/log from libm: what CPython's math modul
 typedef struct gca_oracle_batch {
   int32_t n_envs, n_intr;
   gca_host_state st;          /* in/out, canonical layout (include/gca.h) */
-  uint8_t* own_vel_is_f32;    /* [B] in/out: ownship velocity still the f32 array made by reset (Q2) */
   /* draw source */
   int32_t draws;              /* GCA_DRAWS_* */
   int32_t trig;               /* GCA_TRIG_* */
   const double* tape;         /* [B][tape_stride] */
   int64_t tape_stride;
   int64_t* cursor;            /* [B] in/out */
-  uint64_t seed;
-  uint32_t tick;
+  uint64_t seed;            /* Philox key; the per-env tick lives in st.tick */
   uint32_t env_id0;
+  uint32_t reserved0;
   int32_t f32_positions;      /* 1: FAST-mode storage rule (a retried spawn is rounded to f32) */
   int32_t auto_reset;
   /* outputs (always f64-valued; an element the reference computes in f32 is that f32 widened) */

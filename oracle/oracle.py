@@ -43,10 +43,9 @@ def lib():
     OracleBatch._fields_ = [
         ("n_envs", C.c_int32), ("n_intr", C.c_int32),
         ("st", abi.GcaHostState),
-        ("own_vel_is_f32", C.c_void_p),
         ("draws", C.c_int32), ("trig", C.c_int32),
         ("tape", C.c_void_p), ("tape_stride", C.c_int64), ("cursor", C.c_void_p),
-        ("seed", C.c_uint64), ("tick", C.c_uint32), ("env_id0", C.c_uint32),
+        ("seed", C.c_uint64), ("env_id0", C.c_uint32), ("reserved0", C.c_uint32),
         ("f32_positions", C.c_int32), ("auto_reset", C.c_int32),
         ("obs", C.c_void_p), ("achieved", C.c_void_p), ("desired", C.c_void_p), ("reward", C.c_void_p),
         ("done", C.c_void_p), ("info", C.c_void_p), ("term_obs", C.c_void_p),
@@ -78,7 +77,8 @@ def _p(a):
 
 
 STATE_FIELDS = (("own_pos", np.float32, (2,)), ("own_hs", np.float64, (2,)), ("own_vel", np.float64, (2,)),
-                ("goal", np.float64, (2,)), ("no_conflict", np.int32, ()), ("ep_steps", np.int32, ()),
+                ("own_vel_is_f32", np.uint8, ()), ("goal", np.float64, (2,)), ("no_conflict", np.int32, ()),
+                ("ep_steps", np.int32, ()), ("tick", np.uint32, ()),
                 ("ipos", np.float64, ("N", 2)), ("ipos_is_f64", np.uint8, ("N",)), ("ivel", np.float32, ("N", 2)),
                 ("iflag", np.uint8, ("N",)))
 
@@ -102,10 +102,9 @@ class OracleEnv(object):
         self.B, self.N = int(n_envs), int(n_intr)
         self.D = self.L.gca_oracle_obs_dim(C.byref(cfg), self.N)
         self.state = empty_state(self.B, self.N)
-        self.own_vel_is_f32 = np.ones(self.B, np.uint8)
+        self.state["own_vel_is_f32"][...] = 1
         self.draws, self.trig, self.seed, self.env_id0 = draws, trig, seed, env_id0
         self.f32_positions, self.auto_reset = bool(f32_positions), bool(auto_reset)
-        self.tick = 0
         self.tape = None if tape is None else np.ascontiguousarray(tape, np.float64)
         self.cursor = np.zeros(self.B, np.int64)
         self.obs = np.zeros((self.B, self.D), np.float64)
@@ -116,6 +115,10 @@ class OracleEnv(object):
         self.done = np.zeros(self.B, np.uint8)
         self.info = np.zeros(self.B, np.uint8)
 
+    @property
+    def own_vel_is_f32(self):
+        return self.state["own_vel_is_f32"]
+
     def _batch(self):
         abi = _abi()
         b = OracleBatch()
@@ -124,12 +127,11 @@ class OracleEnv(object):
         for name, _, _ in STATE_FIELDS:
             setattr(st, name, _p(self.state[name]))
         b.st = st
-        b.own_vel_is_f32 = _p(self.own_vel_is_f32)
         b.draws, b.trig = self.draws, self.trig
         if self.tape is not None:
             b.tape, b.tape_stride = _p(self.tape), self.tape.shape[1]
         b.cursor = _p(self.cursor)
-        b.seed, b.tick, b.env_id0 = self.seed, self.tick, self.env_id0
+        b.seed, b.env_id0 = self.seed, self.env_id0
         b.f32_positions, b.auto_reset = int(self.f32_positions), int(self.auto_reset)
         b.obs, b.achieved, b.desired = _p(self.obs), _p(self.achieved), _p(self.desired)
         b.reward, b.done, b.info, b.term_obs = _p(self.reward), _p(self.done), _p(self.info), _p(self.term_obs)
@@ -140,7 +142,6 @@ class OracleEnv(object):
         m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
         rc = self.L.gca_oracle_reset(C.byref(self.cfg), C.byref(b), _p(m))
         assert rc == 0, rc
-        self.tick += 1
         return self.obs
 
     def step(self, actions):
@@ -153,7 +154,6 @@ class OracleEnv(object):
         b = self._batch()
         rc = self.L.gca_oracle_step(C.byref(self.cfg), C.byref(b), _p(a))
         assert rc == 0, rc
-        self.tick += 1
         return self.obs, self.reward, self.done, self.info
 
     def observe(self):

@@ -7,7 +7,8 @@ from gca_b200 import variants
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
-STATE_KEYS = ("own_pos", "own_hs", "own_vel", "goal", "no_conflict", "ep_steps", "ipos", "ipos_is_f64", "ivel", "iflag")
+STATE_KEYS = ("own_pos", "own_hs", "own_vel", "own_vel_is_f32", "goal", "no_conflict", "ep_steps", "ipos",
+              "ipos_is_f64", "ivel", "iflag")
 GOLDEN_VARIANTS = {"env": "SingleAircraftEnv", "env2": "SingleAircraft2Env", "her": "SingleAircraftHEREnv",
                    "dher": "SingleAircraftDiscreteHEREnv", "mcts": "SingleAircraftMCTSEnv"}
 GOLDEN_N = (0, 1, 3, 80)
@@ -38,6 +39,7 @@ def golden_state(g, prefix, sel=None):
         "own_pos": get("own_pos").astype(np.float32),
         "own_hs": np.stack([get("own_heading"), get("own_speed")], -1).astype(np.float64),
         "own_vel": get("own_vel").astype(np.float64),
+        "own_vel_is_f32": get("own_vel_is_f32").astype(np.uint8),
         "goal": get("goal").astype(np.float64),
         "no_conflict": get("no_conflict").astype(np.int32),
         "ep_steps": get("steps").astype(np.int32),
@@ -46,7 +48,7 @@ def golden_state(g, prefix, sel=None):
         "ivel": get("ivel").astype(np.float32),
         "iflag": get("iflag").astype(np.uint8),
     }
-    return {k: np.ascontiguousarray(v) for k, v in st.items()}, get("own_vel_is_f32").astype(np.uint8)
+    return {k: np.ascontiguousarray(v) for k, v in st.items()}
 
 
 def assert_state_equal(got, want, what="", skip=("ep_steps",), rows=None):

@@ -1,0 +1,264 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the reference goldens
+and against the CPU oracle on the same inputs.
+
+Bars (north star): conflict / NMAC / goal / done flags, conflict counters and draw counts
+bit-exact; positions, headings, rewards and observations within 1e-9 relative of the numpy
+reference in the faithful (fp64) mode.  Against the oracle evaluated with the shared
+sincos/log (gca_math.h) everything is bit-exact, in both modes, at every size.
+"""
+import numpy as np
+import pytest
+
+from helpers import (GOLDEN_N, GOLDEN_VARIANTS, STATE_KEYS, assert_state_equal, config_class, golden_actions,
+                     golden_config, golden_state, load_trace)
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9     # fp64-mode tolerance of the north star (values); flags are compared exactly
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def make_gpu(vk, n, B, mode, draws, seed=0):
+    from gca_b200.batched import BatchedAircraftEnv
+    return BatchedAircraftEnv(GOLDEN_VARIANTS[vk], B, config_class(vk), n_intruders=n, mode=mode, draws=draws, seed=seed)
+
+
+def make_oracle(vk, n, B, draws, trig, seed=0, tape=None, f32=False, auto_reset=False):
+    from oracle import oracle as orc
+    return orc.OracleEnv(golden_config(vk), B, n, draws=draws, trig=trig, seed=seed, tape=tape, f32_positions=f32,
+                         auto_reset=auto_reset)
+
+
+def gpu_actions(env, a):
+    torch = _torch()
+    if env.continuous:
+        return torch.as_tensor(np.ascontiguousarray(a[:, :2]), device=env.device).to(env.real)
+    return torch.as_tensor(np.ascontiguousarray(a[:, 0]).astype(np.int32), device=env.device)
+
+
+def close(a, b):
+    return np.allclose(a, b, rtol=RTOL, atol=1e-300)
+
+
+@pytest.mark.parametrize("n", GOLDEN_N)
+@pytest.mark.parametrize("vk", sorted(GOLDEN_VARIANTS))
+def test_golden_replay_faithful(vk, n):
+    """Free-running replay of the reference traces: same start state, same actions, same draws."""
+    torch = _torch()
+    from oracle import oracle as orc
+    g = load_trace(vk, n)
+    B = g["tape"].shape[0]
+    tape = np.nan_to_num(g["tape"], nan=0.0)
+    env = make_gpu(vk, n, B, "faithful", "tape")
+    ref = make_oracle(vk, n, B, 0, orc.TRIG_SHARED, tape=tape)       # bit-exact twin of the kernel
+    her = vk in ("her", "dher")
+
+    # reset from the tape start
+    env.set_tape(tape)
+    obs = env.reset().cpu().numpy()
+    ref.reset()
+    assert np.array_equal(env.tape_cursor.cpu().numpy(), np.broadcast_to(g["cur_reset0"], (B,)))
+    assert_state_equal(env.get_state(), ref.state, "reset vs oracle %s n=%d" % (vk, n))
+    assert np.array_equal(obs, ref.obs)
+    plain = np.nonzero(g["kind_id"] == 0)[0]
+    assert_state_equal(env.get_state(), golden_state(g, "s0_", plain), "reset vs reference", rows=plain,
+                       skip=("ep_steps", "own_vel", "ivel"))
+    assert close(obs[plain], g["obs0"][plain])
+
+    # engineered start states
+    st = golden_state(g, "s0_")
+    env.set_state(st)
+    for k, v in st.items():
+        ref.state[k][...] = v
+    assert close(env.observe().cpu().numpy(), g["obs0"])
+
+    acts = golden_actions(vk, g)
+    exact = total = 0
+    for t in range(acts.shape[1]):
+        what = "%s n=%d step %d" % (vk, n, t)
+        obs, rew, done, info = env.step(gpu_actions(env, acts[:, t]), auto_reset=False)
+        ref.step(acts[:, t])
+        obs, rew, done, info = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy(), info.cpu().numpy()
+        # --- against the reference itself
+        assert np.array_equal(info, g["event"][:, t]), what
+        assert np.array_equal(done, g["done"][:, t]), what
+        assert np.array_equal(env.tape_cursor.cpu().numpy(), g["cur_after"][:, t]), what
+        assert close(rew, g["reward"][:, t]), what
+        assert close(obs, g["obs"][:, t]), what
+        if her:
+            assert close(env.achieved.cpu().numpy(), g["ag"][:, t]) and close(env.desired.cpu().numpy(), g["dg"][:, t])
+        state = env.get_state()
+        want = golden_state(g, "sa_", (slice(None), t))
+        assert np.array_equal(state["no_conflict"], want["no_conflict"]), what
+        assert np.array_equal(state["iflag"], want["iflag"]), what
+        assert np.array_equal(state["ipos_is_f64"], want["ipos_is_f64"]), what
+        for k in ("own_pos", "own_hs", "ipos", "ivel", "goal"):
+            assert close(state[k], want[k]), (what, k)
+        exact += int(np.array_equal(obs, g["obs"][:, t])) + int(np.array_equal(state["own_pos"], want["own_pos"]))
+        total += 2
+        # --- against the oracle twin: every bit
+        assert np.array_equal(obs, ref.obs) and np.array_equal(rew, ref.reward), what
+        assert_state_equal(state, ref.state, what + " vs oracle", skip=())
+        if done.any():
+            env.reset(mask=done)
+            ref.reset(mask=done)
+            rows = np.nonzero(done)[0]
+            assert close(env.obs.cpu().numpy()[rows], g["reset_obs"][rows, t]), what
+            assert np.array_equal(env.obs.cpu().numpy()[rows], ref.obs[rows]), what
+        assert np.array_equal(env.tape_cursor.cpu().numpy(), g["cur_after_reset"][:, t]), what
+    env.close()
+    print("%s n=%d: %d/%d step outputs bit-identical to the reference" % (vk, n, exact, total))
+
+
+@pytest.mark.parametrize("vk,n", [("env", 80), ("env2", 80), ("her", 3), ("dher", 80), ("mcts", 80)])
+def test_teacher_forced_single_steps(vk, n):
+    """Load each recorded reference state, take ONE step, compare with the next recorded state
+    (chaotic divergence cannot hide a bug)."""
+    g = load_trace(vk, n)
+    B, T = g["actions"].shape[:2]
+    tape = np.nan_to_num(g["tape"], nan=0.0)
+    env = make_gpu(vk, n, B, "faithful", "tape")
+    acts = golden_actions(vk, g)
+    for t in range(1, T):
+        ok = g["done"][:, t - 1] == 0                       # a finished env was reset in between
+        env.set_state(golden_state(g, "sa_", (slice(None), t - 1)))
+        env.set_tape(tape, cursor=g["cur_before"][:, t])
+        obs, rew, done, info = env.step(gpu_actions(env, acts[:, t]), auto_reset=False)
+        assert np.array_equal(info.cpu().numpy()[ok], g["event"][ok, t])
+        assert np.array_equal(done.cpu().numpy()[ok], g["done"][ok, t])
+        assert close(rew.cpu().numpy()[ok], g["reward"][ok, t])
+        assert close(obs.cpu().numpy()[ok], g["obs"][ok, t])
+        st = env.get_state()
+        want = golden_state(g, "sa_", (slice(None), t))
+        assert np.array_equal(st["no_conflict"][ok], want["no_conflict"][ok])
+        assert np.array_equal(st["iflag"][ok], want["iflag"][ok])
+        assert close(st["ipos"][ok], want["ipos"][ok]) and close(st["own_pos"][ok], want["own_pos"][ok])
+    env.close()
+
+
+@pytest.mark.parametrize("mode", ["fast", "faithful"])
+@pytest.mark.parametrize("vk,n,B,T", [("env", 80, 4096, 40), ("env2", 80, 2048, 40), ("her", 33, 1000, 40),
+                                      ("dher", 3, 1000, 60), ("mcts", 80, 1024, 40), ("env", 0, 5000, 30),
+                                      ("env", 1, 777, 60), ("env2", 200, 300, 30)])
+def test_philox_rollout_bit_exact_vs_oracle(vk, n, B, T, mode):
+    """On-device Philox draws, VecEnv auto-reset: every output and the whole state must equal the
+    CPU oracle driven by the same counter-based stream - bit for bit (ragged batch sizes included)."""
+    from oracle import oracle as orc
+    fast = mode == "fast"
+    env = make_gpu(vk, n, B, mode, "philox", seed=1234)
+    ref = make_oracle(vk, n, B, 1, orc.TRIG_SHARED, seed=1234, f32=fast, auto_reset=True)
+    cast = (lambda x: x.astype(np.float32)) if fast else (lambda x: x)
+    assert np.array_equal(env.reset().cpu().numpy(), cast(ref.reset()))
+    rng = np.random.RandomState(5)
+    events = np.zeros(6, np.int64)
+    for t in range(T):
+        if env.continuous:
+            a = rng.uniform(-1, 1, (B, 2))
+            if fast:
+                a = a.astype(np.float32).astype(np.float64)
+        else:
+            a = np.stack([rng.randint(0, 3 if vk == "dher" else 9, B), np.zeros(B)], -1).astype(np.float64)
+        obs, rew, done, info = env.step(gpu_actions(env, a))
+        ref.step(a)
+        info = info.cpu().numpy()
+        assert np.array_equal(info, ref.info), t
+        assert np.array_equal(done.cpu().numpy(), ref.done), t
+        assert np.array_equal(rew.cpu().numpy(), cast(ref.reward)), t
+        assert np.array_equal(obs.cpu().numpy(), cast(ref.obs)), t
+        if env.is_goal_env:
+            assert np.array_equal(env.achieved.cpu().numpy(), cast(ref.achieved))
+            assert np.array_equal(env.desired.cpu().numpy(), cast(ref.desired))
+        events += np.bincount(info, minlength=6)
+    assert_state_equal(env.get_state(), ref.state, "final state", skip=())
+    assert np.array_equal(env.get_state()["tick"], ref.state["tick"])
+    env.close()
+    print(vk, n, mode, "events", events.tolist())
+
+
+def test_full_size_bit_exact_vs_oracle():
+    """BASELINE.json size: 65,536 envs x 80 intruders, fast mode, continuous actions."""
+    from oracle import oracle as orc
+    vk, n, B, T = "env2", 80, 65536, 12
+    env = make_gpu(vk, n, B, "fast", "philox", seed=99)
+    ref = make_oracle(vk, n, B, 1, orc.TRIG_SHARED, seed=99, f32=True, auto_reset=True)
+    assert np.array_equal(env.reset().cpu().numpy(), ref.reset().astype(np.float32))
+    rng = np.random.RandomState(11)
+    for t in range(T):
+        a = rng.uniform(-1, 1, (B, 2)).astype(np.float32).astype(np.float64)
+        obs, rew, done, info = env.step(gpu_actions(env, a))
+        ref.step(a)
+        assert np.array_equal(info.cpu().numpy(), ref.info) and np.array_equal(done.cpu().numpy(), ref.done)
+        assert np.array_equal(obs.cpu().numpy(), ref.obs.astype(np.float32))
+        assert np.array_equal(rew.cpu().numpy(), ref.reward.astype(np.float32))
+    assert_state_equal(env.get_state(), ref.state, "final state", skip=())
+    env.close()
+
+
+def test_step_host_equals_device_path():
+    torch = _torch()
+    a_env = make_gpu("env", 80, 2048, "fast", "philox", seed=3)
+    b_env = make_gpu("env", 80, 2048, "fast", "philox", seed=3)
+    o1 = a_env.reset().cpu().numpy()
+    o2 = b_env.reset_host()
+    assert np.array_equal(o1, o2)
+    rng = np.random.RandomState(0)
+    for _ in range(10):
+        a = rng.randint(0, 9, 2048).astype(np.int32)
+        o, r, d, i = a_env.step(torch.as_tensor(a, device="cuda"))
+        ho, hr, hd, hi = b_env.step_host(a)
+        assert np.array_equal(o.cpu().numpy(), ho) and np.array_equal(r.cpu().numpy(), hr)
+        assert np.array_equal(d.cpu().numpy(), hd) and np.array_equal(i.cpu().numpy(), hi)
+    h2d, d2h = b_env.host_io_bytes()
+    assert h2d == 2048 * 4 and d2h == 2048 * (328 * 4 + 4 + 1 + 1)
+
+
+def test_state_roundtrip_and_independence_of_batch_split():
+    """set_state(get_state()) is the identity, and env b evolves the same whatever batch it sits in
+    (Philox is keyed by the global env id: the basis of multi-GPU sharding)."""
+    from gca_b200.batched import BatchedAircraftEnv
+    torch = _torch()
+    cfgc = config_class("env")
+    whole = BatchedAircraftEnv("SingleAircraftEnv", 600, cfgc, n_intruders=40, seed=5)
+    part = BatchedAircraftEnv("SingleAircraftEnv", 200, cfgc, n_intruders=40, seed=5, env_id0=400)
+    whole.reset(); part.reset()
+    rng = np.random.RandomState(1)
+    for _ in range(25):
+        a = torch.as_tensor(rng.randint(0, 9, 600).astype(np.int32), device="cuda")
+        whole.step(a); part.step(a[400:].contiguous())
+    sw, sp = whole.get_state(), part.get_state()
+    for k in STATE_KEYS:
+        assert np.array_equal(sw[k][400:], sp[k]), k
+    clone = BatchedAircraftEnv("SingleAircraftEnv", 600, cfgc, n_intruders=40, seed=5)
+    clone.set_state(sw)
+    a = torch.as_tensor(rng.randint(0, 9, 600).astype(np.int32), device="cuda")
+    o1 = whole.step(a)[0].cpu().numpy()
+    o2 = clone.step(a)[0].cpu().numpy()
+    assert np.array_equal(o1, o2)
+
+
+def test_compute_reward_matches_reference():
+    import os
+    from helpers import GOLDEN
+    from gca_b200 import abi
+    from gca_b200.batched import compute_reward
+    torch = _torch()
+    g = np.load(os.path.join(GOLDEN, "her_reward.npz"))
+    dev = lambda x: torch.as_tensor(x, device="cuda")
+    r = compute_reward(dev(g["ag_n"]), dev(g["g_n"]), 20.0, abi.OBS_HER).cpu().numpy()
+    assert np.array_equal(r, g["r_her"]) and np.all(np.signbit(r))          # always -0.0 (Q14)
+    assert np.array_equal(compute_reward(dev(g["ag_p"]), dev(g["g_p"]), 20.0, abi.OBS_DHER).cpu().numpy(), g["r_dher"])
+    assert np.array_equal(compute_reward(dev(g["ag_p"]), dev(g["g_p"]), 20.0, abi.OBS_HER).cpu().numpy(), g["r_her_pix"])
+    # f32 inputs (what a VecEnv buffer holds) keep the whole norm in f32, like numpy
+    from oracle import oracle as orc
+    ag32, g32 = g["ag_p"].astype(np.float32), g["g_p"].astype(np.float32)
+    want = orc.compute_reward(ag32, g32, 20.0, abi.OBS_DHER)
+    assert np.array_equal(compute_reward(dev(ag32), dev(g32), 20.0, abi.OBS_DHER).cpu().numpy(), want)
+    # a relabel batch of BASELINE config #3: M = 4 * 65,536 pairs
+    rng = np.random.RandomState(0)
+    ag = rng.uniform(0, 800, (4 * 65536, 2)); gg = ag + rng.uniform(-30, 30, ag.shape)
+    assert np.array_equal(compute_reward(dev(ag), dev(gg), 20.0, abi.OBS_DHER).cpu().numpy(),
+                          orc.compute_reward(ag, gg, 20.0, abi.OBS_DHER))

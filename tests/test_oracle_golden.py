@@ -24,9 +24,8 @@ def test_reset_matches_reference(vk, n):
     env.reset()
     assert np.array_equal(env.cursor, np.broadcast_to(g["cur_reset0"], env.cursor.shape))
     plain = np.nonzero(g["kind_id"] == 0)[0]          # traces whose start state is the untouched reset state
-    want, vel32 = golden_state(g, "s0_", plain)
+    want = golden_state(g, "s0_", plain)
     assert_state_equal(env.state, want, "reset %s n=%d" % (vk, n), rows=plain)
-    assert np.array_equal(env.own_vel_is_f32[plain], vel32)
     assert np.array_equal(env.obs[plain], g["obs0"][plain])
     if vk in ("her", "dher"):
         assert np.array_equal(env.achieved[plain], g["ag0"][plain])
@@ -38,10 +37,9 @@ def test_reset_matches_reference(vk, n):
 def test_free_running_replay_matches_reference(vk, n):
     g = load_trace(vk, n)
     env = make_env(vk, n, g)
-    st, vel32 = golden_state(g, "s0_")
+    st = golden_state(g, "s0_")
     for k, v in st.items():
         env.state[k][...] = v
-    env.own_vel_is_f32[...] = vel32
     env.cursor[...] = g["cur_reset0"]
     her = vk in ("her", "dher")
     assert np.array_equal(env.observe(), g["obs0"])
@@ -61,13 +59,13 @@ def test_free_running_replay_matches_reference(vk, n):
         assert np.array_equal(obs, g["obs"][:, t]), what
         if her:
             assert np.array_equal(env.achieved, g["ag"][:, t]) and np.array_equal(env.desired, g["dg"][:, t]), what
-        want, _ = golden_state(g, "sa_", (slice(None), t))
+        want = golden_state(g, "sa_", (slice(None), t))
         assert_state_equal(env.state, want, what)
         if done.any():                                  # VecEnv-style reset of the finished envs
             env.reset(mask=done)
             rows = np.nonzero(done)[0]
             sel = [int(np.nonzero((sr_where[:, 0] == r) & (sr_where[:, 1] == t))[0][0]) for r in rows]
-            want, _ = golden_state(g, "sr_", sel)
+            want = golden_state(g, "sr_", sel)
             assert_state_equal(env.state, want, what + " reset", rows=rows)
             assert np.array_equal(env.obs[rows], g["reset_obs"][rows, t]), what
         assert np.array_equal(env.cursor, g["cur_after_reset"][:, t]), what
@@ -78,10 +76,9 @@ def test_auto_reset_equals_step_then_reset(vk, n):
     """auto_reset folds the VecEnv contract (dummy_vec_env.py:52-55) into step."""
     g = load_trace(vk, n)
     env = make_env(vk, n, g, auto_reset=True)
-    st, vel32 = golden_state(g, "s0_")
+    st = golden_state(g, "s0_")
     for k, v in st.items():
         env.state[k][...] = v
-    env.own_vel_is_f32[...] = vel32
     env.cursor[...] = g["cur_reset0"]
     for t in range(g["actions"].shape[1]):
         obs, rew, done, info = env.step(golden_actions(vk, g)[:, t])
