@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py - env-steps/s of the batched step hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one launch of the fused step kernel over one batch of 65,536 environments per GPU
+(SingleAircraft2Env, continuous actions, 80 intruders, fast mode, Philox draws, VecEnv
+auto-reset, observation written every step).  Prints ONE JSON line (rank 0).
+
+  value      whole-job env-steps/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        the same metric through the host-buffer C-ABI call (gca_step_host): actions come
+             from pinned host memory and obs/reward/done/info are copied back every step
+  roofline   algorithmic bytes per launch / measured launch duration vs the measured HBM peak
+  cpu_baseline  the CPU oracle port on the box's host cores, on a bounded sample (rank 0, N=1)
+
+--impl reference times the CPU oracle port alone (the reference is Python and cannot travel to
+the GPU box; the port is pinned bit-exact to it by tests/test_oracle_golden.py).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "gym-guidance-collision-avoidance-single_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+ENVS_PER_GPU = 65536
+N_INTRUDERS = 80
+VARIANT = "SingleAircraft2Env"
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+GRAPH_STEPS = 50            # steps captured per CUDA graph (actions cycle through this many batches)
+
+
+def workload_name():
+    return ("%s continuous [-1,1]^2 actions, %d envs/GPU, %d intruders, fast mode (f32 state+obs, f64 ownship), "
+            "Philox draws, auto-reset, vector obs written every step" % (VARIANT, ENVS_PER_GPU, N_INTRUDERS))
+
+
+def algorithmic_bytes_per_env_step(n, continuous=True):
+    """DESIGN.md 'Algorithmic bytes': what one env-step must move in fast mode."""
+    per_intruder = 8 + 8 + 8 + 16            # read pos, read vel, write pos, write 4 f32 obs entries
+    flags = 4 * ((n + 31) // 32)             # conflict-flag words read (written only on a transition)
+    fixed = (16 + 32 + 16 + 1 + 16 + 32      # own_pos r/w, heading+speed r/w, own_vel w, vel flag w, goal r, counters r/w
+             + (8 if continuous else 4)      # action
+             + 4 + 1 + 1                     # reward, done, info
+             + 32)                           # ownship + goal tail of the observation
+    return per_intruder * n + flags + fixed
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the step kernel from the committed ncu summary, if present."""
+    path = os.path.join(ROOT, "profiles", "step_kernel_ncu.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Polls SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.01):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = str(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------- CPU arm
+def oracle_shards(cores, envs, seed):
+    from gca_b200 import variants
+    from gym_guidance_collision_avoidance_single.envs.config import Config
+    from oracle import oracle as orc
+    cfg = variants.make_config(VARIANT, Config)
+    per = envs // cores
+    shards = []
+    for c in range(cores):
+        e = orc.OracleEnv(cfg, per, N_INTRUDERS, draws=1, trig=orc.TRIG_SHARED, seed=seed, env_id0=c * per,
+                          f32_positions=True, auto_reset=True)
+        shards.append(e)
+    return shards
+
+
+def run_cpu(steps, warmup, sample_envs=None, budget_s=20.0):
+    """Time the CPU oracle port: `cores` threads (ctypes releases the GIL), each advancing its own
+    shard of a bounded sample of the workload (same variant, N, fast-mode rules, Philox, auto-reset)."""
+    from concurrent.futures import ThreadPoolExecutor
+    cores = os.cpu_count() or 1
+    if sample_envs is None:
+        sample_envs = 512 * cores
+    shards = oracle_shards(cores, sample_envs, seed=0)
+    per = shards[0].B
+    rng = np.random.RandomState(1)
+    acts = [rng.uniform(-1, 1, (per, 2)).astype(np.float32).astype(np.float64) for _ in range(cores)]
+    pool = ThreadPoolExecutor(cores)
+    list(pool.map(lambda e: e.reset(), shards))
+
+    def one_step():
+        list(pool.map(lambda ea: ea[0].step(ea[1]), zip(shards, acts)))
+    for _ in range(max(warmup, 1)):
+        one_step()
+    t0 = time.perf_counter()
+    one_step()
+    per_step = time.perf_counter() - t0
+    steps = max(1, min(steps, int(budget_s / max(per_step, 1e-6))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    dt = time.perf_counter() - t0
+    pool.shutdown()
+    value = per * cores * steps / dt
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d envs x %d intruders x %d steps (%.1f s), C oracle port (oracle/gca_oracle.c), %d threads"
+                      % (per * cores, N_INTRUDERS, steps, dt, cores)}, steps, dt
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import __graft_entry__ as ge
+    ge.build()
+    cb, steps, dt = run_cpu(args.steps, args.warmup, budget_s=60.0)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+            "config": {"workload": workload_name()},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------- GPU arm
+def main_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        ge.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+
+    from gca_b200.batched import BatchedAircraftEnv
+    from gym_guidance_collision_avoidance_single.envs.config import Config
+
+    B, N = ENVS_PER_GPU, N_INTRUDERS
+    env = BatchedAircraftEnv(VARIANT, B, Config, n_intruders=N, mode="fast", draws="philox", device=local, seed=2024,
+                             env_id0=rank * B)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1 + rank)
+    actions = [torch.rand((B, 2), device="cuda", generator=gen) * 2 - 1 for _ in range(GRAPH_STEPS)]
+    env.reset()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K, W = args.steps, max(args.warmup, 3)
+    # K steps = full graph replays (GRAPH_STEPS launches each) + an eager remainder
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for i in range(W):
+            env.step(actions[i % GRAPH_STEPS])
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for i in range(GRAPH_STEPS):
+            env.step(actions[i])
+    graph.replay()                                    # one untimed replay
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    done_steps = 0
+    for _ in range(K // GRAPH_STEPS):
+        graph.replay()
+        done_steps += GRAPH_STEPS
+    for i in range(K - done_steps):
+        env.step(actions[i])
+    stop.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = start.elapsed_time(stop)
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * K / (ms * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call (GCA_BENCH_KERNEL_ONLY=1 skips it for ncu captures)
+    kernel_only = os.environ.get("GCA_BENCH_KERNEL_ONLY") == "1"
+    host_actions = [a.cpu().numpy() for a in actions[:8]]
+    for i in range(3):
+        env.step_host(host_actions[i % 8])
+    Ke = 3 if kernel_only else max(3, min(K, 300))
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        obs, rew, dn, info = env.step_host(host_actions[i % 8])
+        _ = float(rew[0])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * Ke / float(te.item())
+    h2d, d2h = env.host_io_bytes()
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        bytes_per_launch = algorithmic_bytes_per_env_step(N) * B
+        launch_ms = ms / K
+        achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32+f64", "data": "synthetic",
+            "config": {"workload": workload_name(), "envs_per_gpu": B, "intruders": N,
+                       "l2": "per-step footprint %.0f MB (state+obs) exceeds the 126 MB L2; no flush between steps"
+                             % (bytes_per_launch / 1e6),
+                       "launch": "CUDA graph of %d step launches, replayed" % GRAPH_STEPS},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": Ke, "api": "BatchedAircraftEnv.step_host -> gca_step_host (pinned host buffers)"},
+            "gpu_launches": K,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(), "peak_source": peak_src,
+                         "bytes_per_env_step": algorithmic_bytes_per_env_step(N), "kernel_ms": launch_ms},
+        }
+        if world == 1 and not kernel_only:
+            cb, _, _ = run_cpu(10 ** 9, 1, budget_s=12.0)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        main_reference(args)
+    else:
+        main_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

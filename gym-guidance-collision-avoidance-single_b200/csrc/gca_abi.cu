@@ -31,7 +31,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 }  // namespace
 
 struct gca_env {
-  int device = 0, mode = 0, draws = 0, tile = 32;
+  int device = 0, mode = 0, draws = 0, tile = 8, stages = 4;
   gca_config cfg{};
   uint64_t seed = 0;
   uint32_t env_id0 = 0;
@@ -142,11 +142,16 @@ int gca_create(const gca_config* cfg, int n_envs, int n_intruders, int mode, int
   e->D = gca_obs_dim(cfg, n_intruders);
   if (const char* t = std::getenv("GCA_TILE")) {
     const int v = std::atoi(t);
-    if (v == 8 || v == 16 || v == 32) e->tile = v;
+    if (v == 4 || v == 8 || v == 16 || v == 32) e->tile = v;
+  }
+  if (const char* t = std::getenv("GCA_STAGES")) {
+    const int v = std::atoi(t);
+    if (v >= 1 && v <= 8) e->stages = v;
   }
   DevState& s = e->s;
-  s.B = n_envs; s.N = n_intruders; s.Np = (n_intruders + 1) & ~1; s.W = (n_intruders + 31) / 32;
-  const size_t B = (size_t)n_envs, BN = B * (size_t)s.Np, BW = B * (size_t)s.W;
+  s.B = n_envs; s.N = n_intruders;
+  row_layout(s, mode == GCA_MODE_FAITHFUL);
+  const size_t B = (size_t)n_envs;
   int rc = GCA_OK;
   if (!rc) rc = dev_alloc(e, &s.own_pos, B);
   if (!rc) rc = dev_alloc(e, &s.own_hs, B);
@@ -154,13 +159,8 @@ int gca_create(const gca_config* cfg, int n_envs, int n_intruders, int mode, int
   if (!rc) rc = dev_alloc(e, &s.own_vel_f32, B);
   if (!rc) rc = dev_alloc(e, &s.goal, B);
   if (!rc) rc = dev_alloc(e, &s.counters, B);
-  if (!rc) {
-    if (mode == GCA_MODE_FAITHFUL) rc = dev_alloc(e, reinterpret_cast<double2**>(&s.ipos), BN);
-    else rc = dev_alloc(e, reinterpret_cast<float2**>(&s.ipos), BN);
-  }
-  if (!rc) rc = dev_alloc(e, &s.ivel, BN);
-  if (!rc) rc = dev_alloc(e, &s.iflag, BW);
-  if (!rc) rc = dev_alloc(e, &s.if64, mode == GCA_MODE_FAITHFUL ? BW : 1);
+  if (!rc) rc = dev_alloc(e, &s.irow, B * (size_t)s.row_bytes);
+  if (!rc) rc = dev_alloc(e, &s.sched, 2);
   if (rc) {
     gca_destroy(e);
     return rc;
@@ -204,7 +204,8 @@ int gca_step(gca_env* e, const void* actions, const gca_tape* tape, int auto_res
   if (int rc = check_tape(e, tape)) return rc;
   GCA_CUDA(cudaSetDevice(e->device));
   const StepArgs a = make_args(e, actions, tape, out, auto_reset);
-  GCA_CUDA(launch_step(e->mode == GCA_MODE_FAITHFUL, e->draws == GCA_DRAWS_TAPE, e->tile, a, (cudaStream_t)stream));
+  GCA_CUDA(launch_step(e->mode == GCA_MODE_FAITHFUL, e->draws == GCA_DRAWS_TAPE, e->tile, e->stages, a,
+                       (cudaStream_t)stream));
   return GCA_OK;
 }
 
@@ -274,7 +275,7 @@ int gca_get_state(gca_env* e, const gca_host_state* h) {
   GCA_CUDA(cudaSetDevice(e->device));
   GCA_CUDA(cudaDeviceSynchronize());
   const DevState& s = e->s;
-  const size_t B = (size_t)s.B, N = (size_t)s.N, Np = (size_t)s.Np, W = (size_t)s.W;
+  const size_t B = (size_t)s.B, N = (size_t)s.N;
   if (h->own_pos) GCA_CUDA(cudaMemcpy(h->own_pos, s.own_pos, B * sizeof(float2), cudaMemcpyDeviceToHost));
   if (h->own_hs) GCA_CUDA(cudaMemcpy(h->own_hs, s.own_hs, B * sizeof(double2), cudaMemcpyDeviceToHost));
   if (h->own_vel) GCA_CUDA(cudaMemcpy(h->own_vel, s.own_vel, B * sizeof(double2), cudaMemcpyDeviceToHost));
@@ -289,49 +290,30 @@ int gca_get_state(gca_env* e, const gca_host_state* h) {
       if (h->tick) h->tick[b] = (uint32_t)c[b].z;
     }
   }
-  if (N == 0) return GCA_OK;
-  if (h->ipos) {
-    if (e->mode == GCA_MODE_FAITHFUL) {
-      std::vector<double2> p(B * Np);
-      GCA_CUDA(cudaMemcpy(p.data(), s.ipos, p.size() * sizeof(double2), cudaMemcpyDeviceToHost));
-      for (size_t b = 0; b < B; ++b)
-        for (size_t i = 0; i < N; ++i) {
-          h->ipos[2 * (b * N + i)] = p[b * Np + i].x;
-          h->ipos[2 * (b * N + i) + 1] = p[b * Np + i].y;
+  if (N == 0 || !(h->ipos || h->ivel || h->iflag || h->ipos_is_f64)) return GCA_OK;
+  const bool faith = e->mode == GCA_MODE_FAITHFUL;
+  const size_t RB = (size_t)s.row_bytes;
+  std::vector<uint8_t> rows(B * RB);
+  GCA_CUDA(cudaMemcpy(rows.data(), s.irow, rows.size(), cudaMemcpyDeviceToHost));
+  for (size_t b = 0; b < B; ++b) {
+    const uint8_t* row = rows.data() + b * RB;
+    const float2* vel = reinterpret_cast<const float2*>(row + s.off_vel);
+    const uint32_t* fw = reinterpret_cast<const uint32_t*>(row + s.off_flag);
+    const uint32_t* dw = reinterpret_cast<const uint32_t*>(row + s.off_f64);
+    for (size_t i = 0; i < N; ++i) {
+      const size_t k = b * N + i;
+      if (h->ipos) {
+        if (faith) {
+          const double2 p = reinterpret_cast<const double2*>(row)[i];
+          h->ipos[2 * k] = p.x; h->ipos[2 * k + 1] = p.y;
+        } else {
+          const float2 p = reinterpret_cast<const float2*>(row)[i];
+          h->ipos[2 * k] = (double)p.x; h->ipos[2 * k + 1] = (double)p.y;
         }
-    } else {
-      std::vector<float2> p(B * Np);
-      GCA_CUDA(cudaMemcpy(p.data(), s.ipos, p.size() * sizeof(float2), cudaMemcpyDeviceToHost));
-      for (size_t b = 0; b < B; ++b)
-        for (size_t i = 0; i < N; ++i) {
-          h->ipos[2 * (b * N + i)] = (double)p[b * Np + i].x;
-          h->ipos[2 * (b * N + i) + 1] = (double)p[b * Np + i].y;
-        }
-    }
-  }
-  if (h->ivel) {
-    std::vector<float2> v(B * Np);
-    GCA_CUDA(cudaMemcpy(v.data(), s.ivel, v.size() * sizeof(float2), cudaMemcpyDeviceToHost));
-    for (size_t b = 0; b < B; ++b)
-      for (size_t i = 0; i < N; ++i) {
-        h->ivel[2 * (b * N + i)] = v[b * Np + i].x;
-        h->ivel[2 * (b * N + i) + 1] = v[b * Np + i].y;
       }
-  }
-  auto unpack = [&](const uint32_t* dev, uint8_t* dst) -> int {
-    std::vector<uint32_t> w(B * W);
-    GCA_CUDA(cudaMemcpy(w.data(), dev, w.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    for (size_t b = 0; b < B; ++b)
-      for (size_t i = 0; i < N; ++i) dst[b * N + i] = (w[b * W + i / 32] >> (i % 32)) & 1u;
-    return GCA_OK;
-  };
-  if (h->iflag)
-    if (int rc = unpack(s.iflag, h->iflag)) return rc;
-  if (h->ipos_is_f64) {
-    if (e->mode == GCA_MODE_FAITHFUL) {
-      if (int rc = unpack(s.if64, h->ipos_is_f64)) return rc;
-    } else {
-      std::memset(h->ipos_is_f64, 0, B * N);
+      if (h->ivel) { h->ivel[2 * k] = vel[i].x; h->ivel[2 * k + 1] = vel[i].y; }
+      if (h->iflag) h->iflag[k] = (fw[i / 32] >> (i % 32)) & 1u;
+      if (h->ipos_is_f64) h->ipos_is_f64[k] = faith ? ((dw[i / 32] >> (i % 32)) & 1u) : 0;
     }
   }
   return GCA_OK;
@@ -342,7 +324,7 @@ int gca_set_state(gca_env* e, const gca_host_state* h) {
   GCA_CUDA(cudaSetDevice(e->device));
   GCA_CUDA(cudaDeviceSynchronize());
   const DevState& s = e->s;
-  const size_t B = (size_t)s.B, N = (size_t)s.N, Np = (size_t)s.Np, W = (size_t)s.W;
+  const size_t B = (size_t)s.B, N = (size_t)s.N;
   if (h->own_pos) GCA_CUDA(cudaMemcpy(s.own_pos, h->own_pos, B * sizeof(float2), cudaMemcpyHostToDevice));
   if (h->own_hs) GCA_CUDA(cudaMemcpy(s.own_hs, h->own_hs, B * sizeof(double2), cudaMemcpyHostToDevice));
   if (h->own_vel) GCA_CUDA(cudaMemcpy(s.own_vel, h->own_vel, B * sizeof(double2), cudaMemcpyHostToDevice));
@@ -358,39 +340,30 @@ int gca_set_state(gca_env* e, const gca_host_state* h) {
     }
     GCA_CUDA(cudaMemcpy(s.counters, c.data(), B * sizeof(int4), cudaMemcpyHostToDevice));
   }
-  if (N == 0) return GCA_OK;
-  if (h->ipos) {
-    if (e->mode == GCA_MODE_FAITHFUL) {
-      std::vector<double2> p(B * Np, make_double2(0., 0.));
-      for (size_t b = 0; b < B; ++b)
-        for (size_t i = 0; i < N; ++i) p[b * Np + i] = make_double2(h->ipos[2 * (b * N + i)], h->ipos[2 * (b * N + i) + 1]);
-      GCA_CUDA(cudaMemcpy(s.ipos, p.data(), p.size() * sizeof(double2), cudaMemcpyHostToDevice));
-    } else {
-      std::vector<float2> p(B * Np, make_float2(0.f, 0.f));
-      for (size_t b = 0; b < B; ++b)
-        for (size_t i = 0; i < N; ++i)
-          p[b * Np + i] = make_float2((float)h->ipos[2 * (b * N + i)], (float)h->ipos[2 * (b * N + i) + 1]);
-      GCA_CUDA(cudaMemcpy(s.ipos, p.data(), p.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  if (N == 0 || !(h->ipos || h->ivel || h->iflag || h->ipos_is_f64)) return GCA_OK;
+  const bool faith = e->mode == GCA_MODE_FAITHFUL;
+  const size_t RB = (size_t)s.row_bytes;
+  std::vector<uint8_t> rows(B * RB);
+  GCA_CUDA(cudaMemcpy(rows.data(), s.irow, rows.size(), cudaMemcpyDeviceToHost));   // keep what the view omits
+  for (size_t b = 0; b < B; ++b) {
+    uint8_t* row = rows.data() + b * RB;
+    float2* vel = reinterpret_cast<float2*>(row + s.off_vel);
+    uint32_t* fw = reinterpret_cast<uint32_t*>(row + s.off_flag);
+    uint32_t* dw = reinterpret_cast<uint32_t*>(row + s.off_f64);
+    if (h->iflag) std::memset(fw, 0, (size_t)s.Wp * 4);
+    if (h->ipos_is_f64 && faith) std::memset(dw, 0, (size_t)s.Wp * 4);
+    for (size_t i = 0; i < N; ++i) {
+      const size_t k = b * N + i;
+      if (h->ipos) {
+        if (faith) reinterpret_cast<double2*>(row)[i] = make_double2(h->ipos[2 * k], h->ipos[2 * k + 1]);
+        else reinterpret_cast<float2*>(row)[i] = make_float2((float)h->ipos[2 * k], (float)h->ipos[2 * k + 1]);
+      }
+      if (h->ivel) vel[i] = make_float2(h->ivel[2 * k], h->ivel[2 * k + 1]);
+      if (h->iflag && h->iflag[k]) fw[i / 32] |= 1u << (i % 32);
+      if (h->ipos_is_f64 && faith && h->ipos_is_f64[k]) dw[i / 32] |= 1u << (i % 32);
     }
   }
-  if (h->ivel) {
-    std::vector<float2> v(B * Np, make_float2(0.f, 0.f));
-    for (size_t b = 0; b < B; ++b)
-      for (size_t i = 0; i < N; ++i) v[b * Np + i] = make_float2(h->ivel[2 * (b * N + i)], h->ivel[2 * (b * N + i) + 1]);
-    GCA_CUDA(cudaMemcpy(s.ivel, v.data(), v.size() * sizeof(float2), cudaMemcpyHostToDevice));
-  }
-  auto pack = [&](const uint8_t* src, uint32_t* dev) -> int {
-    std::vector<uint32_t> w(B * W, 0u);
-    for (size_t b = 0; b < B; ++b)
-      for (size_t i = 0; i < N; ++i)
-        if (src[b * N + i]) w[b * W + i / 32] |= 1u << (i % 32);
-    GCA_CUDA(cudaMemcpy(dev, w.data(), w.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    return GCA_OK;
-  };
-  if (h->iflag)
-    if (int rc = pack(h->iflag, s.iflag)) return rc;
-  if (h->ipos_is_f64 && e->mode == GCA_MODE_FAITHFUL)
-    if (int rc = pack(h->ipos_is_f64, s.if64)) return rc;
+  GCA_CUDA(cudaMemcpy(s.irow, rows.data(), rows.size(), cudaMemcpyHostToDevice));
   return GCA_OK;
 }
 

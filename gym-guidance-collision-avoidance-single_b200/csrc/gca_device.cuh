@@ -15,7 +15,12 @@
 namespace gca {
 
 // ------------------------------------------------------------------------------ device state
-// SoA, env-major.  One warp reads one env's intruder row as a contiguous segment.
+// Per-env scalars are SoA by field (lane = env accesses are coalesced).  Everything that is
+// indexed by intruder lives in ONE contiguous, 16-byte aligned row per env:
+//     [ pos[Np] (float2 FAST / double2 FAITHFUL) | vel[Np] float2 | conflict words[Wp] | f64 words[Wp] (FAITHFUL) ]
+// so that a single 1-D bulk (TMA) copy brings an env's whole intruder set into shared memory.
+// bit i%32 of conflict word i/32 = Aircraft.conflict of intruder i; the f64 words flag
+// positions whose dtype became f64 after a retried spawn (Q3).
 struct DevState {
   float2* own_pos;        // [B]
   double2* own_hs;        // [B]   (heading, speed)
@@ -23,12 +28,26 @@ struct DevState {
   uint8_t* own_vel_f32;   // [B]
   double2* goal;          // [B]
   int4* counters;         // [B]   (no_conflict, ep_steps, tick, episodes)
-  void* ipos;             // FAST: float2 [B][Np]   FAITHFUL: double2 [B][Np]
-  float2* ivel;           // [B][Np]
-  uint32_t* iflag;        // [B][W]  bit i%32 of word i/32 = Aircraft.conflict of intruder i
-  uint32_t* if64;         // [B][W]  FAITHFUL only: position dtype is f64 (Q3)
-  int B, N, Np, W;
+  uint8_t* irow;          // [B][row_bytes]
+  unsigned int* sched;    // [2]   dynamic tile scheduler: next tile, finished warps
+  int B, N, Np, W, Wp;
+  int row_bytes, off_vel, off_flag, off_f64;
 };
+
+template <bool FAITH>
+struct pos2 { using type = float2; };
+template <>
+struct pos2<true> { using type = double2; };
+
+__host__ __device__ inline void row_layout(DevState& s, bool faithful) {
+  s.Np = (s.N + 1) & ~1;
+  s.W = (s.N + 31) / 32;
+  s.Wp = ((s.W > 0 ? s.W : 1) + 3) & ~3;
+  s.off_vel = s.Np * (faithful ? 16 : 8);
+  s.off_flag = s.off_vel + s.Np * 8;
+  s.off_f64 = s.off_flag + s.Wp * 4;
+  s.row_bytes = s.off_f64 + (faithful ? s.Wp * 4 : 0);   // a multiple of 16 by construction
+}
 
 struct StepArgs {
   DevState s;
@@ -166,27 +185,40 @@ struct Intruder {
   bool is64;
 };
 
+// row accessors (work on a global row or on its shared-memory copy)
 template <bool FAITH>
-__device__ __forceinline__ void load_intruder(const DevState& s, size_t idx, Intruder& it) {
+__device__ __forceinline__ void load_intruder(const DevState& s, const uint8_t* row, int i, Intruder& it) {
   if constexpr (FAITH) {
-    const double2 p = reinterpret_cast<const double2*>(s.ipos)[idx];
+    const double2 p = reinterpret_cast<const double2*>(row)[i];
     it.px = p.x;
     it.py = p.y;
   } else {
-    const float2 p = reinterpret_cast<const float2*>(s.ipos)[idx];
+    const float2 p = reinterpret_cast<const float2*>(row)[i];
     it.px = (double)p.x;
     it.py = (double)p.y;
   }
-  const float2 v = s.ivel[idx];
+  const float2 v = reinterpret_cast<const float2*>(row + s.off_vel)[i];
   it.vx = v.x;
   it.vy = v.y;
 }
 
 template <bool FAITH>
-__device__ __forceinline__ void store_ipos(const DevState& s, size_t idx, double px, double py) {
-  if constexpr (FAITH) reinterpret_cast<double2*>(s.ipos)[idx] = make_double2(px, py);
-  else reinterpret_cast<float2*>(s.ipos)[idx] = make_float2((float)px, (float)py);
+__device__ __forceinline__ void store_ipos(uint8_t* row, int i, double px, double py) {
+  if constexpr (FAITH) reinterpret_cast<double2*>(row)[i] = make_double2(px, py);
+  else reinterpret_cast<float2*>(row)[i] = make_float2((float)px, (float)py);
 }
+
+__device__ __forceinline__ void store_ivel(const DevState& s, uint8_t* row, int i, float vx, float vy) {
+  reinterpret_cast<float2*>(row + s.off_vel)[i] = make_float2(vx, vy);
+}
+
+__device__ __forceinline__ uint32_t* flag_words(const DevState& s, uint8_t* row) {
+  return reinterpret_cast<uint32_t*>(row + s.off_flag);
+}
+__device__ __forceinline__ uint32_t* f64_words(const DevState& s, uint8_t* row) {
+  return reinterpret_cast<uint32_t*>(row + s.off_f64);
+}
+__device__ __forceinline__ uint8_t* env_row(const DevState& s, size_t env) { return s.irow + env * (size_t)s.row_bytes; }
 
 // ownship <-> intruder distance and the `< threshold` tests in the dtype the reference uses
 template <bool FAITH>
@@ -333,6 +365,38 @@ __device__ __forceinline__ void write_obs_own(const StepArgs& a, size_t env, flo
       dg[0] = (R)gx; dg[1] = (R)gy;
     }
   }
+}
+
+// ------------------------------------------------------------------------------ TMA (1-D bulk copy) + mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy, completion counted in bytes on `bar` (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "GCA_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra GCA_DONE;\n"
+      "bra GCA_WAIT;\n"
+      "GCA_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
 }
 
 }  // namespace gca
