@@ -1,6 +1,8 @@
 // gca_abi.cu - the C ABI of include/gca.h: handle lifetime, argument checking, state
 // marshalling and the host-buffer (end-to-end) path.  No exception crosses the boundary.
+#include <cmath>
 #include <cstdlib>
+#include <limits>
 #include <cstring>
 #include <new>
 #include <string>
@@ -33,6 +35,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 struct gca_env {
   int device = 0, mode = 0, draws = 0, tile = 8, stages = 4;
   gca_config cfg{};
+  Derived k{};
   uint64_t seed = 0;
   uint32_t env_id0 = 0;
   DevState s{};
@@ -66,10 +69,42 @@ int dev_alloc(gca_env* e, T** p, size_t count) {
   return GCA_OK;
 }
 
+// smallest s with sqrt(s) >= thr, i.e. (sqrt(s) < thr) == (s < X); T = float or double
+template <typename T>
+T sq_threshold(T thr) {
+  if (!(thr > 0)) return 0;
+  T c = thr * thr;
+  const T inf = std::numeric_limits<T>::infinity();
+  while (c > 0 && std::sqrt(c) >= thr) c = std::nextafter(c, (T)0);
+  while (std::sqrt(c) < thr) c = std::nextafter(c, inf);
+  return c;
+}
+
+Derived derive(const gca_config& c) {
+  Derived k{};
+  k.sep2_f = sq_threshold<float>((float)c.minimum_separation);
+  k.nmac2_f = sq_threshold<float>((float)c.nmac_dist);
+  k.init2_f = sq_threshold<float>((float)c.initial_min_dist);
+  k.sep2_d = sq_threshold<double>(c.minimum_separation);
+  k.nmac2_d = sq_threshold<double>(c.nmac_dist);
+  k.init2_d = sq_threshold<double>(c.initial_min_dist);
+  k.win_w = (float)c.window_width;
+  k.win_h = (float)c.window_height;
+  k.ob_w = (float)c.ob_window_width;
+  k.ob_h = (float)c.ob_window_height;
+  k.inv_ob_w = 1.0f / k.ob_w;
+  k.inv_ob_h = 1.0f / k.ob_h;
+  k.ms = (float)c.max_speed;
+  k.den = (float)(c.max_speed * 2);
+  k.inv_den = 1.0f / k.den;
+  return k;
+}
+
 StepArgs make_args(const gca_env* e, const void* actions, const gca_tape* tape, const gca_out* out, int auto_reset) {
   StepArgs a{};
   a.s = e->s;
   a.cfg = e->cfg;
+  a.k = e->k;
   a.actions = actions;
   if (tape) {
     a.tape = tape->values;
@@ -138,7 +173,7 @@ int gca_create(const gca_config* cfg, int n_envs, int n_intruders, int mode, int
   GCA_CUDA(cudaSetDevice(device));
   gca_env* e = new (std::nothrow) gca_env();
   if (!e) return fail(GCA_ERR_ALLOC, "out of host memory");
-  e->device = device; e->mode = mode; e->draws = draws; e->cfg = *cfg; e->seed = seed; e->env_id0 = env_id0;
+  e->device = device; e->mode = mode; e->draws = draws; e->cfg = *cfg; e->k = derive(*cfg); e->seed = seed; e->env_id0 = env_id0;
   e->D = gca_obs_dim(cfg, n_intruders);
   if (const char* t = std::getenv("GCA_TILE")) {
     const int v = std::atoi(t);
@@ -183,6 +218,7 @@ int gca_set_config(gca_env* e, const gca_config* cfg) {
   if (int rc = check_config(cfg)) return rc;
   if (gca_obs_dim(cfg, e->s.N) != e->D) return fail(GCA_ERR_STATE, "obs_kind change would alter the observation size");
   e->cfg = *cfg;
+  e->k = derive(*cfg);
   return GCA_OK;
 }
 

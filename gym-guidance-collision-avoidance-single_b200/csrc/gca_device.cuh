@@ -49,9 +49,21 @@ __host__ __device__ inline void row_layout(DevState& s, bool faithful) {
   s.row_bytes = s.off_f64 + (faithful ? s.Wp * 4 : 0);   // a multiple of 16 by construction
 }
 
+// Constants derived from gca_config on the host (gca_abi.cu), exact by construction.
+// `d < thr` on a correctly rounded sqrt is monotone in its argument, so each distance test is
+// done on the squared distance against X = min{ s : sqrt(s) >= thr } - same truth value, no sqrt.
+struct Derived {
+  float sep2_f, nmac2_f, init2_f;     // f32 distances (thr taken as f32, NumPy 2 weak scalars)
+  double sep2_d, nmac2_d, init2_d;    // f64 distances
+  float win_w, win_h;                 // Box bounds are f32 (PKG/SingleAircraftEnv.py:38-41)
+  float ob_w, ob_h, inv_ob_w, inv_ob_h;   // x / Config.window_* in f32, and RN(1/.) for gca_div_const_f32
+  float ms, den, inv_den;             // normalize_velocity: (v + ms) / den in f32
+};
+
 struct StepArgs {
   DevState s;
   gca_config cfg;
+  Derived k;
   const void* actions;
   const double* tape;
   long long tape_stride;
@@ -159,27 +171,38 @@ __device__ __forceinline__ void draw_own_noise(Draws<TAPE>& d, const gca_config&
 
 // ------------------------------------------------------------------------------ distances
 // dist(): np.linalg.norm(p1 - p2)   PKG/SingleAircraftEnv.py:312-313
-__device__ __forceinline__ float dist_f32(float ax, float ay, float bx, float by) {
+//   f32 - f32 : sqrtf(fl(fl(dx*dx) + fl(dy*dy)))         (OpenBLAS sdot, no FMA)
+//   with f64  : sqrt(fma(dy, dy, fl(dx*dx)))             (OpenBLAS ddot tail)
+__device__ __forceinline__ float dist2_f32(float ax, float ay, float bx, float by) {
   const float dx = __fadd_rn(ax, -bx), dy = __fadd_rn(ay, -by);
-  return __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));      // sdot: no FMA
+  return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
 }
-
-__device__ __forceinline__ double dist_f64(double ax, double ay, double bx, double by) {
+__device__ __forceinline__ double dist2_f64(double ax, double ay, double bx, double by) {
   const double dx = __dadd_rn(ax, -bx), dy = __dadd_rn(ay, -by);
-  return __dsqrt_rn(__fma_rn(dy, dy, __dmul_rn(dx, dx)));                  // ddot tail: FMA on the 2nd product
+  return __fma_rn(dy, dy, __dmul_rn(dx, dx));
+}
+__device__ __forceinline__ double dist_f64(double ax, double ay, double bx, double by) {
+  return __dsqrt_rn(dist2_f64(ax, ay, bx, by));
 }
 
 // position_range.contains(p): inclusive, f32 bounds   PKG/SingleAircraftEnv.py:38-41,153
-__device__ __forceinline__ bool in_map_f32(const gca_config& c, float x, float y) {
-  return x >= 0.0f && y >= 0.0f && x <= (float)c.window_width && y <= (float)c.window_height;
+__device__ __forceinline__ bool in_map_f32(const Derived& k, float x, float y) {
+  return x >= 0.0f && y >= 0.0f && x <= k.win_w && y <= k.win_h;
 }
-__device__ __forceinline__ bool in_map_f64(const gca_config& c, double x, double y) {
-  return x >= 0.0 && y >= 0.0 && x <= (double)(float)c.window_width && y <= (double)(float)c.window_height;
+__device__ __forceinline__ bool in_map_f64(const Derived& k, double x, double y) {
+  return x >= 0.0 && y >= 0.0 && x <= (double)k.win_w && y <= (double)k.win_h;
 }
 
 // ------------------------------------------------------------------------------ intruder record
-// Position carried as a double that holds either an f32 value (is64 == false) or a true f64.
-struct Intruder {
+// FAST: everything f32.  FAITHFUL: the position is a double that holds either an f32 value
+// (is64 == false) or a true f64 (a spawn that was retried, Q3).
+template <bool FAITH>
+struct Intr {
+  float px, py, vx, vy;
+  static constexpr bool is64 = false;
+};
+template <>
+struct Intr<true> {
   double px, py;
   float vx, vy;
   bool is64;
@@ -187,15 +210,15 @@ struct Intruder {
 
 // row accessors (work on a global row or on its shared-memory copy)
 template <bool FAITH>
-__device__ __forceinline__ void load_intruder(const DevState& s, const uint8_t* row, int i, Intruder& it) {
+__device__ __forceinline__ void load_intruder(const DevState& s, const uint8_t* row, int i, Intr<FAITH>& it) {
   if constexpr (FAITH) {
     const double2 p = reinterpret_cast<const double2*>(row)[i];
     it.px = p.x;
     it.py = p.y;
   } else {
     const float2 p = reinterpret_cast<const float2*>(row)[i];
-    it.px = (double)p.x;
-    it.py = (double)p.y;
+    it.px = p.x;
+    it.py = p.y;
   }
   const float2 v = reinterpret_cast<const float2*>(row + s.off_vel)[i];
   it.vx = v.x;
@@ -203,9 +226,9 @@ __device__ __forceinline__ void load_intruder(const DevState& s, const uint8_t* 
 }
 
 template <bool FAITH>
-__device__ __forceinline__ void store_ipos(uint8_t* row, int i, double px, double py) {
-  if constexpr (FAITH) reinterpret_cast<double2*>(row)[i] = make_double2(px, py);
-  else reinterpret_cast<float2*>(row)[i] = make_float2((float)px, (float)py);
+__device__ __forceinline__ void store_ipos(uint8_t* row, int i, const Intr<FAITH>& it) {
+  if constexpr (FAITH) reinterpret_cast<double2*>(row)[i] = make_double2(it.px, it.py);
+  else reinterpret_cast<float2*>(row)[i] = make_float2(it.px, it.py);
 }
 
 __device__ __forceinline__ void store_ivel(const DevState& s, uint8_t* row, int i, float vx, float vy) {
@@ -220,41 +243,63 @@ __device__ __forceinline__ uint32_t* f64_words(const DevState& s, uint8_t* row) 
 }
 __device__ __forceinline__ uint8_t* env_row(const DevState& s, size_t env) { return s.irow + env * (size_t)s.row_bytes; }
 
-// ownship <-> intruder distance and the `< threshold` tests in the dtype the reference uses
+// intruder.position += intruder.velocity   PKG/SingleAircraftEnv.py:150, and the map test :153
 template <bool FAITH>
-__device__ __forceinline__ void separation(const gca_config& c, float ox, float oy, const Intruder& it, double px,
-                                           double py, bool& lt_sep, bool& lt_nmac, bool& lt_init) {
-  if (FAITH && it.is64) {
-    const double d = dist_f64((double)ox, (double)oy, px, py);
-    lt_sep = d < c.minimum_separation;
-    lt_nmac = d < c.nmac_dist;
-    lt_init = d < c.initial_min_dist;
+__device__ __forceinline__ bool advance(const Derived& k, Intr<FAITH>& it) {
+  if constexpr (FAITH) {
+    if (it.is64) {                                       // f64 + f32 -> f64
+      it.px = __dadd_rn(it.px, (double)it.vx);
+      it.py = __dadd_rn(it.py, (double)it.vy);
+      return !in_map_f64(k, it.px, it.py);
+    }
+    const float fx = __fadd_rn((float)it.px, it.vx), fy = __fadd_rn((float)it.py, it.vy);
+    it.px = (double)fx;
+    it.py = (double)fy;
+    return !in_map_f32(k, fx, fy);
   } else {
-    const float d = dist_f32(ox, oy, (float)px, (float)py);
-    lt_sep = d < (float)c.minimum_separation;   // f32 scalar vs Python float compares in f32 (NumPy 2)
-    lt_nmac = d < (float)c.nmac_dist;
-    lt_init = d < (float)c.initial_min_dist;
+    it.px = __fadd_rn(it.px, it.vx);
+    it.py = __fadd_rn(it.py, it.vy);
+    return !in_map_f32(k, it.px, it.py);
   }
+}
+
+// ownship <-> intruder `dist < threshold` tests in the dtype the reference uses
+template <bool FAITH>
+__device__ __forceinline__ void separation(const Derived& k, float ox, float oy, const Intr<FAITH>& it, bool& lt_sep,
+                                           bool& lt_nmac, bool& lt_init) {
+  if constexpr (FAITH) {
+    if (it.is64) {
+      const double s2 = dist2_f64((double)ox, (double)oy, it.px, it.py);
+      lt_sep = s2 < k.sep2_d;
+      lt_nmac = s2 < k.nmac2_d;
+      lt_init = s2 < k.init2_d;
+      return;
+    }
+  }
+  const float s2 = dist2_f32(ox, oy, (float)it.px, (float)it.py);
+  lt_sep = s2 < k.sep2_f;
+  lt_nmac = s2 < k.nmac2_f;
+  lt_init = s2 < k.init2_f;
 }
 
 // Aircraft(random_pos(), random_speed(), random_heading()) + rejection loop
 // PKG/SingleAircraftEnv.py:229-238,269-278 (reset: :80-88)
 template <bool FAITH, bool TAPE>
-__device__ __forceinline__ void spawn(Draws<TAPE>& d, const gca_config& c, uint32_t slot, float ox, float oy,
-                                      Intruder& it) {
+__device__ __forceinline__ void spawn(Draws<TAPE>& d, const gca_config& c, const Derived& k, uint32_t slot, float ox,
+                                      float oy, Intr<FAITH>& it) {
   double x, y, speed, heading, sn, cs;
   draw_pos(d, c, slot, GCA_BLOCK_POS, x, y);
   draw_speed_heading(d, c, slot, speed, heading);
-  it.px = (double)(float)x;
-  it.py = (double)(float)y;
-  it.is64 = false;
+  it.px = (float)x;
+  it.py = (float)y;
+  if constexpr (FAITH) it.is64 = false;
   gca_sincos(heading, &sn, &cs);
   it.vx = (float)__dmul_rn(speed, cs);
   it.vy = (float)__dmul_rn(speed, sn);
   int retries = 0;
   for (;;) {
     bool a, b, lt_init;
-    separation<FAITH>(c, ox, oy, it, it.px, it.py, a, b, lt_init);
+    separation<FAITH>(k, ox, oy, it, a, b, lt_init);
     if (!lt_init) break;
     if (!TAPE && retries >= GCA_MAX_SPAWN_RETRIES) break;
     draw_pos(d, c, slot, GCA_BLOCK_RETRY0 + (uint32_t)retries, x, y);
@@ -264,8 +309,8 @@ __device__ __forceinline__ void spawn(Draws<TAPE>& d, const gca_config& c, uint3
       it.py = y;
       it.is64 = true;
     } else {                     // FAST storage rule: rounded to f32
-      it.px = (double)(float)x;
-      it.py = (double)(float)y;
+      it.px = (float)x;
+      it.py = (float)y;
     }
   }
 }
@@ -279,47 +324,55 @@ __device__ __forceinline__ bool own_first(const gca_config& c) {
 }
 
 // normalize_velocity() on an f32 velocity   PKG/SingleAircraftEnv.py:104-106
-__device__ __forceinline__ float norm_vel_f32(const gca_config& c, float v) {
-  return __fdiv_rn(__fadd_rn(v, (float)c.max_speed), (float)__dmul_rn(c.max_speed, 2.0));
+__device__ __forceinline__ float norm_vel_f32(const Derived& k, float v) {
+  return gca_div_const_f32(__fadd_rn(v, k.ms), k.den, k.inv_den);
 }
 __device__ __forceinline__ double norm_vel_f64(const gca_config& c, double v) {
   return __ddiv_rn(__dadd_rn(v, c.max_speed), __dmul_rn(c.max_speed, 2.0));
 }
 
 // the four entries of intruder i   PKG/SingleAircraftEnv.py:108-114 (raw: Simulators/SingleAircraftMCTSEnv.py:107-112)
+// `base` points at the first intruder entry of the env's observation row.
 template <bool FAITH>
-__device__ __forceinline__ void write_obs_intruder(const StepArgs& a, size_t env, int i, const Intruder& it,
-                                                   double px, double py) {
+__device__ __forceinline__ void write_obs_intruder(const StepArgs& a, real_t<FAITH>* base, int i,
+                                                   const Intr<FAITH>& it) {
   using R = real_t<FAITH>;
   const gca_config& c = a.cfg;
+  const Derived& k = a.k;
   if (c.obs_kind == GCA_OBS_NONE) return;
   R o0, o1, o2, o3;
   if (c.obs_kind == GCA_OBS_RAW) {
-    o0 = (R)px; o1 = (R)py; o2 = (R)it.vx; o3 = (R)it.vy;
+    o0 = (R)it.px; o1 = (R)it.py; o2 = (R)it.vx; o3 = (R)it.vy;
   } else {
-    if (FAITH && it.is64) {
-      o0 = (R)__ddiv_rn(px, c.ob_window_width);
-      o1 = (R)__ddiv_rn(py, c.ob_window_height);
+    bool wide = false;
+    if constexpr (FAITH) wide = it.is64;
+    if (wide) {
+      o0 = (R)__ddiv_rn((double)it.px, c.ob_window_width);
+      o1 = (R)__ddiv_rn((double)it.py, c.ob_window_height);
     } else {
-      o0 = (R)__fdiv_rn((float)px, (float)c.ob_window_width);
-      o1 = (R)__fdiv_rn((float)py, (float)c.ob_window_height);
+      o0 = (R)gca_div_const_f32((float)it.px, k.ob_w, k.inv_ob_w);
+      o1 = (R)gca_div_const_f32((float)it.py, k.ob_h, k.inv_ob_h);
     }
-    o2 = (R)norm_vel_f32(c, it.vx);
-    o3 = (R)norm_vel_f32(c, it.vy);
+    o2 = (R)norm_vel_f32(k, it.vx);
+    o3 = (R)norm_vel_f32(k, it.vy);
   }
-  const bool of = own_first(c);
-  R* p = reinterpret_cast<R*>(a.obs) + env * (size_t)a.D + (of ? 6 : 0) + 4 * (size_t)i;
+  R* p = base + 4 * (size_t)i;
   if constexpr (FAITH) {
     reinterpret_cast<double2*>(p)[0] = make_double2(o0, o1);
     reinterpret_cast<double2*>(p)[1] = make_double2(o2, o3);
   } else {
-    if (!of) {
+    if (!own_first(c)) {
       *reinterpret_cast<float4*>(p) = make_float4(o0, o1, o2, o3);
     } else {   // HER rows start at element 6: only 8-byte aligned
       reinterpret_cast<float2*>(p)[0] = make_float2(o0, o1);
       reinterpret_cast<float2*>(p)[1] = make_float2(o2, o3);
     }
   }
+}
+
+template <bool FAITH>
+__device__ __forceinline__ real_t<FAITH>* obs_intruder_base(const StepArgs& a, size_t env) {
+  return reinterpret_cast<real_t<FAITH>*>(a.obs) + env * (size_t)a.D + (own_first(a.cfg) ? 6 : 0);
 }
 
 // ownship entries, goal entries, achieved/desired   PKG/SingleAircraftEnv.py:115-124,
@@ -338,12 +391,13 @@ __device__ __forceinline__ void write_obs_own(const StepArgs& a, size_t env, flo
     o[6] = (R)gx; o[7] = (R)gy;
     return;
   }
-  const float nx = __fdiv_rn(px, (float)c.ob_window_width), ny = __fdiv_rn(py, (float)c.ob_window_height);
+  const Derived& k = a.k;
+  const float nx = gca_div_const_f32(px, k.ob_w, k.inv_ob_w), ny = gca_div_const_f32(py, k.ob_h, k.inv_ob_h);
   o[0] = (R)nx;
   o[1] = (R)ny;
   if (vel_is_f32) {
-    o[2] = (R)norm_vel_f32(c, (float)vx);
-    o[3] = (R)norm_vel_f32(c, (float)vy);
+    o[2] = (R)norm_vel_f32(k, (float)vx);
+    o[3] = (R)norm_vel_f32(k, (float)vy);
   } else {
     o[2] = (R)norm_vel_f64(c, vx);
     o[3] = (R)norm_vel_f64(c, vy);

@@ -36,17 +36,18 @@ constexpr int kMaxStages = 8;
 
 // one warp-round (32 intruders) of an env row held in shared or global memory
 template <bool FAITH>
-__device__ __forceinline__ void load_round(const DevState& s, const uint8_t* row, int r, int lane, Intruder& it,
+__device__ __forceinline__ void load_round(const DevState& s, const uint8_t* row, int r, int lane, Intr<FAITH>& it,
                                            bool& valid, uint32_t& fw) {
   const int i = r * 32 + lane;
   valid = i < s.N;
-  it.px = it.py = 0.0;
+  it.px = it.py = 0;
   it.vx = it.vy = 0.0f;
   if (valid) load_intruder<FAITH>(s, row, i, it);
   fw = reinterpret_cast<const uint32_t*>(row + s.off_flag)[r];
-  uint32_t dw = 0;
-  if constexpr (FAITH) dw = reinterpret_cast<const uint32_t*>(row + s.off_f64)[r];
-  it.is64 = FAITH && ((dw >> lane) & 1u);
+  if constexpr (FAITH) {
+    const uint32_t dw = reinterpret_cast<const uint32_t*>(row + s.off_f64)[r];
+    it.is64 = (dw >> lane) & 1u;
+  }
 }
 
 // reset(): PKG/SingleAircraftEnv.py:66-98 for env `env`, executed by the whole warp.
@@ -56,7 +57,9 @@ __device__ __forceinline__ void reset_env_warp(const StepArgs& a, size_t env, in
                                                double2& goal) {
   const DevState& s = a.s;
   const gca_config& c = a.cfg;
+  const Derived& k = a.k;
   uint8_t* row = env_row(s, env);
+  real_t<FAITH>* obase = obs_intruder_base<FAITH>(a, env);
   const float ox = 50.0f, oy = 50.0f;                     // Ownship(position=(50, 50), ...) :72-76
   if constexpr (TAPE) {
     if (lane == owner) {
@@ -64,12 +67,12 @@ __device__ __forceinline__ void reset_env_warp(const StepArgs& a, size_t env, in
         uint32_t dw = 0;
         for (int j = 0; j < 32 && r * 32 + j < s.N; ++j) {
           const int i = r * 32 + j;
-          Intruder it;
-          spawn<FAITH, TAPE>(d, c, GCA_SLOT_RESET | (uint32_t)i, ox, oy, it);
-          store_ipos<FAITH>(row, i, it.px, it.py);
+          Intr<FAITH> it;
+          spawn<FAITH, TAPE>(d, c, k, GCA_SLOT_RESET | (uint32_t)i, ox, oy, it);
+          store_ipos<FAITH>(row, i, it);
           store_ivel(s, row, i, it.vx, it.vy);
           dw |= (it.is64 ? 1u : 0u) << j;
-          write_obs_intruder<FAITH>(a, env, i, it, it.px, it.py);
+          write_obs_intruder<FAITH>(a, obase, i, it);
         }
         flag_words(s, row)[r] = 0u;
         if constexpr (FAITH) f64_words(s, row)[r] = dw;
@@ -80,15 +83,16 @@ __device__ __forceinline__ void reset_env_warp(const StepArgs& a, size_t env, in
     for (int r = 0; r < s.W; ++r) {
       const int i = r * 32 + lane;
       const bool valid = i < s.N;
-      Intruder it;
-      it.is64 = false;
+      Intr<FAITH> it;
+      bool wide = false;
       if (valid) {
-        spawn<FAITH, TAPE>(d, c, GCA_SLOT_RESET | (uint32_t)i, ox, oy, it);
-        store_ipos<FAITH>(row, i, it.px, it.py);
+        spawn<FAITH, TAPE>(d, c, k, GCA_SLOT_RESET | (uint32_t)i, ox, oy, it);
+        store_ipos<FAITH>(row, i, it);
         store_ivel(s, row, i, it.vx, it.vy);
-        write_obs_intruder<FAITH>(a, env, i, it, it.px, it.py);
+        write_obs_intruder<FAITH>(a, obase, i, it);
+        wide = it.is64;
       }
-      const uint32_t dw = __ballot_sync(FULL, valid && it.is64);
+      const uint32_t dw = __ballot_sync(FULL, wide);
       if (lane == 0) {
         flag_words(s, row)[r] = 0u;
         if constexpr (FAITH) f64_words(s, row)[r] = dw;
@@ -122,6 +126,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) step_kernel(const StepArg
   extern __shared__ __align__(128) uint8_t smem[];
   const DevState& s = a.s;
   const gca_config& c = a.cfg;
+  const Derived& k = a.k;
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
   uint8_t* wsm = smem + (size_t)warp_in_block * warp_smem_bytes(s, stages, TILE);
@@ -232,26 +237,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) step_kernel(const StepArg
         mbar_wait(&bars[q], (phase >> q) & 1u);
         phase ^= 1u << q;
       }
+      real_t<FAITH>* obase = obs_intruder_base<FAITH>(a, env);
       for (int r = 0; r < s.W; ++r) {
-        Intruder it;
+        Intr<FAITH> it;
         bool valid;
         uint32_t fw;
         load_round<FAITH>(s, srow, r, lane, it, valid, fw);
-        // intruder.position += intruder.velocity   :150   (f32 + f32, or f64 + f32 for an f64 position)
-        double npx, npy;
-        bool oob;
-        if (FAITH && it.is64) {
-          npx = __dadd_rn(it.px, (double)it.vx);
-          npy = __dadd_rn(it.py, (double)it.vy);
-          oob = !in_map_f64(c, npx, npy);
-        } else {
-          const float fx = __fadd_rn((float)it.px, it.vx), fy = __fadd_rn((float)it.py, it.vy);
-          npx = (double)fx;
-          npy = (double)fy;
-          oob = !in_map_f32(c, fx, fy);
-        }
+        Intr<FAITH> nx = it;
+        const bool oob = advance<FAITH>(k, nx);                     // intruder.position += velocity :150
         bool lt_sep, lt_nmac, lt_init;
-        separation<FAITH>(c, ox, oy, it, npx, npy, lt_sep, lt_nmac, lt_init);   // :151
+        separation<FAITH>(k, ox, oy, nx, lt_sep, lt_nmac, lt_init); // dist(drone, intruder) :151
         const uint32_t b_nmac = stop ? 0u : __ballot_sync(FULL, valid && lt_sep && lt_nmac);
         const int first = b_nmac ? __ffs(b_nmac) - 1 : 31;          // first NMAC index wins (Q9)
         const bool commit = !stop && valid && lane <= first;
@@ -268,9 +263,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) step_kernel(const StepArg
             if (b_oob) f64_words(s, grow)[r] = reinterpret_cast<const uint32_t*>(srow + s.off_f64)[r] & ~b_oob;
           }
         }
-        if (commit && !oob) store_ipos<FAITH>(grow, r * 32 + lane, npx, npy);
-        if (valid && !(commit && oob))
-          write_obs_intruder<FAITH>(a, env, r * 32 + lane, it, commit ? npx : it.px, commit ? npy : it.py);
+        if (commit && !oob) store_ipos<FAITH>(grow, r * 32 + lane, nx);
+        if (valid && !(commit && oob)) write_obs_intruder<FAITH>(a, obase, r * 32 + lane, commit ? nx : it);
         if (b_nmac) {
           nmac_hit = true;
           stop = true;                                              // later intruders are not touched
@@ -295,6 +289,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) step_kernel(const StepArg
     bool done = false;
     if (has_env) {
       uint8_t* grow = env_row(s, me);
+      real_t<FAITH>* obase = obs_intruder_base<FAITH>(a, me);
       if (!maxstep_hit) {
         // reset_intruder() for every intruder that left the map, in index order   :153-154, :229-238
         for (int r = 0; r < s.W; ++r) {
@@ -304,12 +299,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) step_kernel(const StepArg
             const int j = __ffs(w) - 1;
             w &= w - 1;
             const int i = r * 32 + j;
-            Intruder it;
-            spawn<FAITH, TAPE>(d, c, (uint32_t)i, pos.x, pos.y, it);
-            store_ipos<FAITH>(grow, i, it.px, it.py);
+            Intr<FAITH> it;
+            spawn<FAITH, TAPE>(d, c, k, (uint32_t)i, pos.x, pos.y, it);
+            store_ipos<FAITH>(grow, i, it);
             store_ivel(s, grow, i, it.vx, it.vy);
             set64 |= (it.is64 ? 1u : 0u) << j;
-            write_obs_intruder<FAITH>(a, me, i, it, it.px, it.py);
+            write_obs_intruder<FAITH>(a, obase, i, it);
           }
           if constexpr (FAITH) {
             if (set64) f64_words(s, grow)[r] |= set64;
@@ -326,7 +321,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) step_kernel(const StepArg
         reward = c.r_nmac; done = true; info = GCA_INFO_NMAC;
       } else if (my_conf) {
         reward = c.r_conflict; info = GCA_INFO_CONFLICT;
-      } else if (c.wall_kind != GCA_WALL_NONE && !in_map_f32(c, pos.x, pos.y)) {
+      } else if (c.wall_kind != GCA_WALL_NONE && !in_map_f32(k, pos.x, pos.y)) {
         reward = c.r_wall; done = c.wall_kind == GCA_WALL_TERMINAL; info = GCA_INFO_WALL;
       } else {
         const double dg = dist_f64((double)pos.x, (double)pos.y, goal.x, goal.y);
@@ -468,12 +463,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) observe_kernel(const Step
   for (int e = 0; e < n_tile; ++e) {
     const size_t env = (size_t)(env0 + e);
     const uint8_t* row = env_row(s, env);
+    real_t<FAITH>* obase = obs_intruder_base<FAITH>(a, env);
     for (int r = 0; r < s.W; ++r) {
-      Intruder it;
+      Intr<FAITH> it;
       bool valid;
       uint32_t fw;
       load_round<FAITH>(s, row, r, lane, it, valid, fw);
-      if (valid) write_obs_intruder<FAITH>(a, env, r * 32 + lane, it, it.px, it.py);
+      if (valid) write_obs_intruder<FAITH>(a, obase, r * 32 + lane, it);
     }
   }
   if (lane < n_tile) {
