@@ -3,6 +3,8 @@
 #include <cmath>
 #include <cstdlib>
 #include <limits>
+#include <map>
+#include <mutex>
 #include <cstring>
 #include <new>
 #include <string>
@@ -33,7 +35,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 }  // namespace
 
 struct gca_env {
-  int device = 0, mode = 0, draws = 0, tile = 8, stages = 4;
+  int device = 0, mode = 0, draws = 0, tile = 32, stages = 4;
   gca_config cfg{};
   Derived k{};
   uint64_t seed = 0;
@@ -80,6 +82,18 @@ T sq_threshold(T thr) {
   return c;
 }
 
+// cached exhaustive check that the one-correction division is exact for divisor d
+bool div1_exact(float d) {
+  static std::mutex mu;
+  static std::map<float, bool> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(d);
+  if (it != cache.end()) return it->second;
+  const bool ok = d > 0 && std::isfinite(d) && gca_div1_is_exact(d) != 0;
+  cache[d] = ok;
+  return ok;
+}
+
 Derived derive(const gca_config& c) {
   Derived k{};
   k.sep2_f = sq_threshold<float>((float)c.minimum_separation);
@@ -97,6 +111,7 @@ Derived derive(const gca_config& c) {
   k.ms = (float)c.max_speed;
   k.den = (float)(c.max_speed * 2);
   k.inv_den = 1.0f / k.den;
+  k.div1_ok = div1_exact(k.ob_w) && div1_exact(k.ob_h) && div1_exact(k.den);
   return k;
 }
 
@@ -177,7 +192,7 @@ int gca_create(const gca_config* cfg, int n_envs, int n_intruders, int mode, int
   e->D = gca_obs_dim(cfg, n_intruders);
   if (const char* t = std::getenv("GCA_TILE")) {
     const int v = std::atoi(t);
-    if (v == 4 || v == 8 || v == 16 || v == 32) e->tile = v;
+    if (v == 8 || v == 32) e->tile = v;
   }
   if (const char* t = std::getenv("GCA_STAGES")) {
     const int v = std::atoi(t);

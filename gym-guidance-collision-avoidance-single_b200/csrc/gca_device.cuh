@@ -58,7 +58,20 @@ struct Derived {
   float win_w, win_h;                 // Box bounds are f32 (PKG/SingleAircraftEnv.py:38-41)
   float ob_w, ob_h, inv_ob_w, inv_ob_h;   // x / Config.window_* in f32, and RN(1/.) for gca_div_const_f32
   float ms, den, inv_den;             // normalize_velocity: (v + ms) / den in f32
+  int div1_ok;                        // the one-correction division is exact for ob_w, ob_h and den
 };
+
+// x / d in f32, correctly rounded, for the host-prepared divisors of Derived
+__device__ __forceinline__ float div_prepared(const Derived& k, float x, float d, float inv_d) {
+  float q = __fmul_rn(x, inv_d);
+  float r = __fmaf_rn(-q, d, x);
+  q = __fmaf_rn(r, inv_d, q);
+  if (!k.div1_ok) {                   // general divisor: second Markstein step (gca_div_const_f32)
+    r = __fmaf_rn(-q, d, x);
+    q = __fmaf_rn(r, inv_d, q);
+  }
+  return q;
+}
 
 struct StepArgs {
   DevState s;
@@ -325,7 +338,7 @@ __device__ __forceinline__ bool own_first(const gca_config& c) {
 
 // normalize_velocity() on an f32 velocity   PKG/SingleAircraftEnv.py:104-106
 __device__ __forceinline__ float norm_vel_f32(const Derived& k, float v) {
-  return gca_div_const_f32(__fadd_rn(v, k.ms), k.den, k.inv_den);
+  return div_prepared(k, __fadd_rn(v, k.ms), k.den, k.inv_den);
 }
 __device__ __forceinline__ double norm_vel_f64(const gca_config& c, double v) {
   return __ddiv_rn(__dadd_rn(v, c.max_speed), __dmul_rn(c.max_speed, 2.0));
@@ -350,8 +363,8 @@ __device__ __forceinline__ void write_obs_intruder(const StepArgs& a, real_t<FAI
       o0 = (R)__ddiv_rn((double)it.px, c.ob_window_width);
       o1 = (R)__ddiv_rn((double)it.py, c.ob_window_height);
     } else {
-      o0 = (R)gca_div_const_f32((float)it.px, k.ob_w, k.inv_ob_w);
-      o1 = (R)gca_div_const_f32((float)it.py, k.ob_h, k.inv_ob_h);
+      o0 = (R)div_prepared(k, (float)it.px, k.ob_w, k.inv_ob_w);
+      o1 = (R)div_prepared(k, (float)it.py, k.ob_h, k.inv_ob_h);
     }
     o2 = (R)norm_vel_f32(k, it.vx);
     o3 = (R)norm_vel_f32(k, it.vy);
@@ -392,7 +405,7 @@ __device__ __forceinline__ void write_obs_own(const StepArgs& a, size_t env, flo
     return;
   }
   const Derived& k = a.k;
-  const float nx = gca_div_const_f32(px, k.ob_w, k.inv_ob_w), ny = gca_div_const_f32(py, k.ob_h, k.inv_ob_h);
+  const float nx = div_prepared(k, px, k.ob_w, k.inv_ob_w), ny = div_prepared(k, py, k.ob_h, k.inv_ob_h);
   o[0] = (R)nx;
   o[1] = (R)ny;
   if (vel_is_f32) {

@@ -179,4 +179,25 @@ GCA_HD float gca_div_const_f32(float x, float d, float inv_d) {
   return GCA_FMAF(r, inv_d, q);
 }
 
+// One correction step only.  Exact for a given divisor iff it is exact for all 2^23 significands
+// of x (the computation is invariant under scaling x by powers of two away from underflow):
+// gca_div1_is_exact checks precisely that, and the host selects this variant only when it holds
+// (it does for 800 and for 2 * 8/3 rounded to f32, the divisors of the default Config).
+GCA_HD float gca_div_const_f32_1(float x, float d, float inv_d) {
+  float q = GCA_FMULF(x, inv_d);
+  float r = GCA_FMAF(-q, d, x);
+  return GCA_FMAF(r, inv_d, q);
+}
+
+static inline int gca_div1_is_exact(float d) {   /* host only */
+  const float inv = 1.0f / d;
+  for (uint32_t m = 0; m < (1u << 23); ++m) {
+    const uint32_t u = (127u << 23) | m;
+    float x;
+    memcpy(&x, &u, sizeof x);
+    if (gca_div_const_f32_1(x, d, inv) != x / d) return 0;
+  }
+  return 1;
+}
+
 #endif  // GCA_MATH_H_

@@ -111,6 +111,41 @@ __device__ __forceinline__ void reset_ownship(const gca_config& c, float2& pos, 
   vel = make_double2((double)(float)__dmul_rn(hs.y, cs), (double)(float)__dmul_rn(hs.y, sn));
 }
 
+// The reference's sequential conflict logic for one warp-round of precomputed per-lane facts
+// (PKG/SingleAircraftEnv.py:153-170): first NMAC index wins and freezes every later intruder (Q9),
+// the out-of-map respawn lands before the conflict test but the test uses the old object (Q7),
+// the conflict flag never clears (Q8).  All lanes call it (ballots).
+template <bool FAITH>
+__device__ __forceinline__ void commit_round(const StepArgs& a, uint8_t* grow, const uint8_t* srow,
+                                             real_t<FAITH>* obase, uint32_t* oob_row, int r, int lane,
+                                             const Intr<FAITH>& it, const Intr<FAITH>& nx, bool valid, bool oob,
+                                             bool lt_sep, bool lt_nmac, uint32_t fw, bool& stop, bool& nmac_hit,
+                                             bool& conf_any, int& newconf, bool& oob_any) {
+  const DevState& s = a.s;
+  const uint32_t b_nmac = stop ? 0u : __ballot_sync(FULL, valid && lt_sep && lt_nmac);
+  const int first = b_nmac ? __ffs(b_nmac) - 1 : 31;
+  const bool commit = !stop && valid && lane <= first;
+  const uint32_t b_conf = __ballot_sync(FULL, commit && lt_sep);
+  const uint32_t b_oob = __ballot_sync(FULL, commit && oob);
+  newconf += __popc(b_conf & ~fw);                                // False -> True transitions :161-163
+  conf_any |= b_conf != 0u;
+  oob_any |= b_oob != 0u;
+  const uint32_t nfw = (fw | b_conf) & ~b_oob;                    // a replaced intruder starts with conflict False
+  if (lane == 0) {
+    if (nfw != fw) flag_words(s, grow)[r] = nfw;
+    oob_row[r] = b_oob;
+    if constexpr (FAITH) {
+      if (b_oob) f64_words(s, grow)[r] = reinterpret_cast<const uint32_t*>(srow + s.off_f64)[r] & ~b_oob;
+    }
+  }
+  if (commit && !oob) store_ipos<FAITH>(grow, r * 32 + lane, nx);
+  if (valid && !(commit && oob)) write_obs_intruder<FAITH>(a, obase, r * 32 + lane, commit ? nx : it);
+  if (b_nmac) {
+    nmac_hit = true;
+    stop = true;                                                  // later intruders are not touched
+  }
+}
+
 // shared memory of one warp: [stages][row_bytes] | mbarrier[kMaxStages] | oob words [TILE][W]
 __host__ __device__ inline size_t warp_smem_bytes(const DevState& s, int stages, int tile) {
   const size_t rows = (size_t)stages * (size_t)s.row_bytes;
@@ -119,7 +154,9 @@ __host__ __device__ inline size_t warp_smem_bytes(const DevState& s, int stages,
   return rows + bars + oob;
 }
 
-template <bool FAITH, bool TAPE, int TILE>
+// WC > 0: the number of warp-rounds per env is the compile-time constant WC (rounds are fully
+// unrolled and an env without any conflict / out-of-map event takes a short path); WC == 0: generic.
+template <bool FAITH, bool TAPE, int TILE, int WC>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) step_kernel(const StepArgs a, const int n_tiles,
                                                                    const int stages) {
   using R = real_t<FAITH>;
@@ -222,52 +259,63 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) step_kernel(const StepArg
     }
 
     // -------------------------------------------------------------- phase B: lanes = intruders
-    bool my_nmac = false, my_conf = false;
+    bool my_nmac = false, my_conf = false, my_oob = false;
     int my_newconf = 0;
     for (int e = 0; e < n_tile; ++e) {
       const size_t env = (size_t)(env0 + e);
-      const int q = e % stages;
+      const int q = e & (stages - 1);                               // stages is a power of two
       const uint8_t* srow = ring + (size_t)q * s.row_bytes;        // shared-memory copy of the row
       uint8_t* grow = env_row(s, env);                              // where results go
+      real_t<FAITH>* obase = obs_intruder_base<FAITH>(a, env);
+      uint32_t* oob_row = oob_words + e * s.W;
       const float ox = __shfl_sync(FULL, pos.x, e), oy = __shfl_sync(FULL, pos.y, e);
       bool stop = __shfl_sync(FULL, (int)maxstep_hit, e) != 0;
-      bool nmac_hit = false, conf_any = false;
+      bool nmac_hit = false, conf_any = false, oob_any = false;
       int newconf = 0;
       if (use_tma) {
         mbar_wait(&bars[q], (phase >> q) & 1u);
         phase ^= 1u << q;
       }
-      real_t<FAITH>* obase = obs_intruder_base<FAITH>(a, env);
-      for (int r = 0; r < s.W; ++r) {
-        Intr<FAITH> it;
-        bool valid;
-        uint32_t fw;
-        load_round<FAITH>(s, srow, r, lane, it, valid, fw);
-        Intr<FAITH> nx = it;
-        const bool oob = advance<FAITH>(k, nx);                     // intruder.position += velocity :150
-        bool lt_sep, lt_nmac, lt_init;
-        separation<FAITH>(k, ox, oy, nx, lt_sep, lt_nmac, lt_init); // dist(drone, intruder) :151
-        const uint32_t b_nmac = stop ? 0u : __ballot_sync(FULL, valid && lt_sep && lt_nmac);
-        const int first = b_nmac ? __ffs(b_nmac) - 1 : 31;          // first NMAC index wins (Q9)
-        const bool commit = !stop && valid && lane <= first;
-        const uint32_t b_conf = __ballot_sync(FULL, commit && lt_sep);
-        const uint32_t b_oob = __ballot_sync(FULL, commit && oob);
-        newconf += __popc(b_conf & ~fw);                            // False -> True transitions :161-163
-        conf_any |= b_conf != 0u;
-        // the flag write lands on the old object: a replaced intruder starts with conflict False (Q7, Q8)
-        const uint32_t nfw = (fw | b_conf) & ~b_oob;
-        if (lane == 0) {
-          if (nfw != fw) flag_words(s, grow)[r] = nfw;
-          oob_words[e * s.W + r] = b_oob;
-          if constexpr (FAITH) {
-            if (b_oob) f64_words(s, grow)[r] = reinterpret_cast<const uint32_t*>(srow + s.off_f64)[r] & ~b_oob;
-          }
+      if constexpr (WC > 0) {
+        Intr<FAITH> it[WC], nx[WC];
+        bool valid[WC], oob[WC], lt_sep[WC], lt_nmac[WC];
+        uint32_t fw[WC];
+        bool event = false;
+#pragma unroll
+        for (int r = 0; r < WC; ++r) {
+          bool lt_init;
+          load_round<FAITH>(s, srow, r, lane, it[r], valid[r], fw[r]);
+          nx[r] = it[r];
+          oob[r] = advance<FAITH>(k, nx[r]);                        // intruder.position += velocity :150
+          separation<FAITH>(k, ox, oy, nx[r], lt_sep[r], lt_nmac[r], lt_init);   // dist(drone, intruder) :151
+          event |= valid[r] && (oob[r] || lt_sep[r]);
         }
-        if (commit && !oob) store_ipos<FAITH>(grow, r * 32 + lane, nx);
-        if (valid && !(commit && oob)) write_obs_intruder<FAITH>(a, obase, r * 32 + lane, commit ? nx : it);
-        if (b_nmac) {
-          nmac_hit = true;
-          stop = true;                                              // later intruders are not touched
+        if (!stop && !__any_sync(FULL, event)) {
+          // nobody left the map, nobody is in conflict: positions and observations only
+#pragma unroll
+          for (int r = 0; r < WC; ++r) {
+            if (valid[r]) {
+              store_ipos<FAITH>(grow, r * 32 + lane, nx[r]);
+              write_obs_intruder<FAITH>(a, obase, r * 32 + lane, nx[r]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < WC; ++r)
+            commit_round<FAITH>(a, grow, srow, obase, oob_row, r, lane, it[r], nx[r], valid[r], oob[r], lt_sep[r],
+                                lt_nmac[r], fw[r], stop, nmac_hit, conf_any, newconf, oob_any);
+        }
+      } else {
+        for (int r = 0; r < s.W; ++r) {
+          Intr<FAITH> it;
+          bool valid, lt_sep, lt_nmac, lt_init;
+          uint32_t fw;
+          load_round<FAITH>(s, srow, r, lane, it, valid, fw);
+          Intr<FAITH> nx = it;
+          const bool oob = advance<FAITH>(k, nx);
+          separation<FAITH>(k, ox, oy, nx, lt_sep, lt_nmac, lt_init);
+          commit_round<FAITH>(a, grow, srow, obase, oob_row, r, lane, it, nx, valid, oob, lt_sep, lt_nmac, fw, stop,
+                              nmac_hit, conf_any, newconf, oob_any);
         }
       }
       // the slot is free again: stream the row that is `stages` envs ahead into it
@@ -281,6 +329,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) step_kernel(const StepArg
         my_nmac = nmac_hit;
         my_conf = conf_any;
         my_newconf = newconf;
+        my_oob = oob_any;
       }
     }
     __syncwarp();
@@ -290,7 +339,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) step_kernel(const StepArg
     if (has_env) {
       uint8_t* grow = env_row(s, me);
       real_t<FAITH>* obase = obs_intruder_base<FAITH>(a, me);
-      if (!maxstep_hit) {
+      if (my_oob) {
         // reset_intruder() for every intruder that left the map, in index order   :153-154, :229-238
         for (int r = 0; r < s.W; ++r) {
           uint32_t w = oob_words[lane * s.W + r];
@@ -505,40 +554,49 @@ cudaError_t persistent_grid(K kernel, size_t smem, int n_tiles, unsigned* blocks
   return cudaSuccess;
 }
 
-template <bool FAITH, bool TAPE, int TILE>
+template <bool FAITH, bool TAPE, int TILE, int WC>
 cudaError_t launch_step_t(const StepArgs& a, int stages, cudaStream_t st) {
   const int n_tiles = (int)(((long long)a.s.B + TILE - 1) / TILE);
-  // ring depth: as asked, but never more than the tile holds nor more than ~96 KB per block
-  if (stages > TILE) stages = TILE;
-  if (stages > kMaxStages) stages = kMaxStages;
-  while (stages > 1 && kWarpsPerBlock * warp_smem_bytes(a.s, stages, TILE) > 96 * 1024) --stages;
+  // ring depth: a power of two, never more than the tile holds nor more than ~96 KB per block
+  int pow2 = 1;
+  while (pow2 * 2 <= stages && pow2 * 2 <= TILE && pow2 * 2 <= kMaxStages) pow2 *= 2;
+  stages = pow2;
+  while (stages > 1 && kWarpsPerBlock * warp_smem_bytes(a.s, stages, TILE) > 96 * 1024) stages /= 2;
   const size_t smem = kWarpsPerBlock * warp_smem_bytes(a.s, stages, TILE);
-  // grid size per (kernel, smem) is cached: the occupancy query is not free
+  // grid size per (kernel, smem, tiles) is cached: the occupancy query is not free
   static unsigned cached_blocks = 0;
   static size_t cached_smem = 0;
   static int cached_tiles = -1;
   if (cached_blocks == 0 || cached_smem != smem || cached_tiles != n_tiles) {
-    cudaError_t e = persistent_grid(step_kernel<FAITH, TAPE, TILE>, smem, n_tiles, &cached_blocks);
+    cudaError_t e = persistent_grid(step_kernel<FAITH, TAPE, TILE, WC>, smem, n_tiles, &cached_blocks);
     if (e != cudaSuccess) return e;
     cached_smem = smem;
     cached_tiles = n_tiles;
   }
-  step_kernel<FAITH, TAPE, TILE><<<cached_blocks, kWarpsPerBlock * 32, smem, st>>>(a, n_tiles, stages);
+  step_kernel<FAITH, TAPE, TILE, WC><<<cached_blocks, kWarpsPerBlock * 32, smem, st>>>(a, n_tiles, stages);
   return cudaGetLastError();
+}
+
+template <int TILE, int WC>
+cudaError_t launch_step_w(bool faith, bool tape, const StepArgs& a, int stages, cudaStream_t st) {
+  if (faith)
+    return tape ? launch_step_t<true, true, TILE, WC>(a, stages, st) : launch_step_t<true, false, TILE, WC>(a, stages, st);
+  return tape ? launch_step_t<false, true, TILE, WC>(a, stages, st) : launch_step_t<false, false, TILE, WC>(a, stages, st);
 }
 
 template <int TILE>
 cudaError_t launch_step_tile(bool faith, bool tape, const StepArgs& a, int stages, cudaStream_t st) {
-  if (faith) return tape ? launch_step_t<true, true, TILE>(a, stages, st) : launch_step_t<true, false, TILE>(a, stages, st);
-  return tape ? launch_step_t<false, true, TILE>(a, stages, st) : launch_step_t<false, false, TILE>(a, stages, st);
+  switch (a.s.W) {                       // rounds per env: 1 (N <= 32), 3 (N = 65..96, the 80-intruder case) or generic
+    case 1: return launch_step_w<TILE, 1>(faith, tape, a, stages, st);
+    case 3: return launch_step_w<TILE, 3>(faith, tape, a, stages, st);
+    default: return launch_step_w<TILE, 0>(faith, tape, a, stages, st);
+  }
 }
 }  // namespace
 
 cudaError_t launch_step(bool faith, bool tape, int tile, int stages, const StepArgs& a, cudaStream_t st) {
-  if (tile == 4) return launch_step_tile<4>(faith, tape, a, stages, st);
-  if (tile == 16) return launch_step_tile<16>(faith, tape, a, stages, st);
-  if (tile == 32) return launch_step_tile<32>(faith, tape, a, stages, st);
-  return launch_step_tile<8>(faith, tape, a, stages, st);
+  if (tile == 8) return launch_step_tile<8>(faith, tape, a, stages, st);
+  return launch_step_tile<32>(faith, tape, a, stages, st);
 }
 
 cudaError_t launch_reset(bool faith, bool tape, const StepArgs& a, cudaStream_t st) {

@@ -45,26 +45,31 @@ def main():
                 print("stall %-60s %.2f" % (h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")], v))
     if "--source" in sys.argv:
         n = int(sys.argv[sys.argv.index("--source") + 1])
-        src = ncu(rep, "source")
-        h = src[0]
-        # find columns
-        def col(name):
-            for i, x in enumerate(h):
-                if x == name:
-                    return i
-            return None
-        ci, cs, cx = col("Source"), col("Warp Stall Sampling (All Samples)"), col("# Instructions Executed")
-        body = [r for r in src[1:] if len(r) == len(h)]
+        out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
+                             capture_output=True, text=True).stdout
+        fname, lines, hdr = "", [], None
+        for r in csv.reader(io.StringIO(out)):
+            if len(r) == 2 and r[0] == "File Path":
+                fname = r[1].split("/")[-1]
+            elif r and r[0] == "Line No":
+                hdr = r
+            elif hdr and len(r) == len(hdr) and r[0] != "":
+                lines.append((fname, r))
+        cs, cx = hdr.index("Warp Stall Sampling (All Samples)"), hdr.index("Instructions Executed")
+
         def num(x):
             try:
                 return float(x)
             except Exception:
                 return 0.0
-        tot = sum(num(r[cs]) for r in body) or 1
-        body.sort(key=lambda r: -num(r[cs]))
-        print("total samples", tot)
-        for r in body[:n]:
-            print("%6.2f%% ex=%-9s %s" % (100 * num(r[cs]) / tot, r[cx], r[ci][:150]))
+        tot = sum(num(r[cs]) for _, r in lines) or 1
+        totx = sum(num(r[cx]) for _, r in lines) or 1
+        print("total samples %d, instructions executed %d" % (tot, totx))
+        key = cx if "--by-inst" in sys.argv else cs
+        lines.sort(key=lambda fr: -num(fr[1][key]))
+        for f, r in lines[:n]:
+            print("%5.1f%% smp %5.1f%% inst  %s:%s  %s" % (100 * num(r[cs]) / tot, 100 * num(r[cx]) / totx, f, r[0],
+                                                          r[1].strip()[:110]))
 
 
 if __name__ == "__main__":
