@@ -35,7 +35,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 }  // namespace
 
 struct gca_env {
-  int device = 0, mode = 0, draws = 0, tile = 32, stages = 4;
+  int device = 0, mode = 0, draws = 0, tile = 32, stages = 2;
   gca_config cfg{};
   Derived k{};
   uint64_t seed = 0;
@@ -192,7 +192,7 @@ int gca_create(const gca_config* cfg, int n_envs, int n_intruders, int mode, int
   e->D = gca_obs_dim(cfg, n_intruders);
   if (const char* t = std::getenv("GCA_TILE")) {
     const int v = std::atoi(t);
-    if (v == 8 || v == 32) e->tile = v;
+    if (v == 8 || v == 16 || v == 32) e->tile = v;
   }
   if (const char* t = std::getenv("GCA_STAGES")) {
     const int v = std::atoi(t);

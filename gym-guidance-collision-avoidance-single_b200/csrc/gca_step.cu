@@ -156,8 +156,11 @@ __host__ __device__ inline size_t warp_smem_bytes(const DevState& s, int stages,
 
 // WC > 0: the number of warp-rounds per env is the compile-time constant WC (rounds are fully
 // unrolled and an env without any conflict / out-of-map event takes a short path); WC == 0: generic.
+#ifndef GCA_MINB
+#define GCA_MINB 4
+#endif
 template <bool FAITH, bool TAPE, int TILE, int WC>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) step_kernel(const StepArgs a, const int n_tiles,
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, GCA_MINB) step_kernel(const StepArgs a, const int n_tiles,
                                                                    const int stages) {
   using R = real_t<FAITH>;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -177,12 +180,19 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) step_kernel(const StepArg
   }
   __syncwarp();
   uint32_t phase = 0;                                     // bit q: parity the next wait on slot q expects
+  const bool single_wave = (int)(gridDim.x * kWarpsPerBlock) >= n_tiles;
+  bool first_pass = true;
 
   for (;;) {
     // ---- dynamic tile scheduler
     int tile = 0;
-    if (lane == 0) tile = (int)atomicAdd(&s.sched[0], 1u);
-    tile = __shfl_sync(FULL, tile, 0);
+    if (single_wave) {                                    // every tile has its own resident warp
+      tile = first_pass ? (int)(blockIdx.x * kWarpsPerBlock + warp_in_block) : n_tiles;
+      first_pass = false;
+    } else {
+      if (lane == 0) tile = (int)atomicAdd(&s.sched[0], 1u);
+      tile = __shfl_sync(FULL, tile, 0);
+    }
     if (tile >= n_tiles) break;
     const long long env0 = (long long)tile * TILE;
     const int n_tile = (int)min((long long)TILE, (long long)s.B - env0);
@@ -280,7 +290,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) step_kernel(const StepArg
         Intr<FAITH> it[WC], nx[WC];
         bool valid[WC], oob[WC], lt_sep[WC], lt_nmac[WC];
         uint32_t fw[WC];
-        bool event = false;
 #pragma unroll
         for (int r = 0; r < WC; ++r) {
           bool lt_init;
@@ -288,22 +297,24 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) step_kernel(const StepArg
           nx[r] = it[r];
           oob[r] = advance<FAITH>(k, nx[r]);                        // intruder.position += velocity :150
           separation<FAITH>(k, ox, oy, nx[r], lt_sep[r], lt_nmac[r], lt_init);   // dist(drone, intruder) :151
-          event |= valid[r] && (oob[r] || lt_sep[r]);
         }
-        if (!stop && !__any_sync(FULL, event)) {
-          // nobody left the map, nobody is in conflict: positions and observations only
+        // A round in which nobody left the map and nobody is in conflict only moves positions and
+        // writes observations; the reference's sequential bookkeeping is needed for the others.
+        bool quiet[WC];
 #pragma unroll
-          for (int r = 0; r < WC; ++r) {
+        for (int r = 0; r < WC; ++r) quiet[r] = !__any_sync(FULL, valid[r] && (oob[r] || lt_sep[r]));
+#pragma unroll
+        for (int r = 0; r < WC; ++r) {
+          if (!stop && quiet[r]) {
             if (valid[r]) {
               store_ipos<FAITH>(grow, r * 32 + lane, nx[r]);
               write_obs_intruder<FAITH>(a, obase, r * 32 + lane, nx[r]);
             }
-          }
-        } else {
-#pragma unroll
-          for (int r = 0; r < WC; ++r)
+            if (lane == 0) oob_row[r] = 0u;
+          } else {
             commit_round<FAITH>(a, grow, srow, obase, oob_row, r, lane, it[r], nx[r], valid[r], oob[r], lt_sep[r],
                                 lt_nmac[r], fw[r], stop, nmac_hit, conf_any, newconf, oob_any);
+          }
         }
       } else {
         for (int r = 0; r < s.W; ++r) {
@@ -424,7 +435,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) step_kernel(const StepArg
   }
 
   // ---- last warp out re-arms the scheduler for the next launch
-  if (lane == 0) {
+  if (!single_wave && lane == 0) {
     const unsigned total = gridDim.x * kWarpsPerBlock;
     const unsigned prev = atomicAdd(&s.sched[1], 1u);
     if (prev == total - 1) {
@@ -596,6 +607,7 @@ cudaError_t launch_step_tile(bool faith, bool tape, const StepArgs& a, int stage
 
 cudaError_t launch_step(bool faith, bool tape, int tile, int stages, const StepArgs& a, cudaStream_t st) {
   if (tile == 8) return launch_step_tile<8>(faith, tape, a, stages, st);
+  if (tile == 16) return launch_step_tile<16>(faith, tape, a, stages, st);
   return launch_step_tile<32>(faith, tape, a, stages, st);
 }
 

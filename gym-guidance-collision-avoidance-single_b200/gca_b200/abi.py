@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libgca.so")
+LIB_PATH = os.environ.get("GCA_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libgca.so")
 
 GCA_ABI_VERSION = 1
 
