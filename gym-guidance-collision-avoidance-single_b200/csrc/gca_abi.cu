@@ -228,6 +228,12 @@ int gca_destroy(gca_env* e) {
   return GCA_OK;
 }
 
+int gca_set_seed(gca_env* e, uint64_t seed) {
+  if (!e) return fail(GCA_ERR_INVALID, "env is NULL");
+  e->seed = seed;
+  return GCA_OK;
+}
+
 int gca_set_config(gca_env* e, const gca_config* cfg) {
   if (!e) return fail(GCA_ERR_INVALID, "env is NULL");
   if (int rc = check_config(cfg)) return rc;

@@ -392,6 +392,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, GCA_MINB) step_kernel(con
           info = GCA_INFO_NONE;
         }
       }
+      if (c.time_limit > 0 && cnt.y >= c.time_limit) done = true;    // gym TimeLimit of the registered ids
       reinterpret_cast<R*>(a.reward)[me] = (R)reward;
       a.done[me] = done ? 1 : 0;
       a.info[me] = (uint8_t)info;

@@ -30,7 +30,7 @@ class GcaConfig(C.Structure):
         "d_heading", "heading_sigma",
         "ob_window_width", "ob_window_height", "ob_min_speed", "ob_max_speed",
         "r_nmac", "r_conflict", "r_wall", "r_goal", "r_default")] + [(n, C.c_int32) for n in (
-            "shaped_default", "action_kind", "obs_kind", "wall_kind", "max_steps", "reserved0")]
+            "shaped_default", "action_kind", "obs_kind", "wall_kind", "max_steps", "time_limit")]
 
 
 class GcaHostState(C.Structure):
@@ -74,6 +74,7 @@ def load():
         "gca_create": ([P(GcaConfig), i32, i32, i32, i32, i32, u64, u32, P(vp)], C.c_int),
         "gca_destroy": ([vp], C.c_int),
         "gca_set_config": ([vp, P(GcaConfig)], C.c_int),
+        "gca_set_seed": ([vp, u64], C.c_int),
         "gca_reset": ([vp, vp, P(GcaTape), P(GcaOut), vp], C.c_int),
         "gca_step": ([vp, vp, P(GcaTape), i32, P(GcaOut), vp], C.c_int),
         "gca_step_host": ([vp, vp, i32, P(GcaOut)], C.c_int),

@@ -1,0 +1,266 @@
+"""Single-environment facade: the reference's gym classes served by a batch of one.
+
+Each class keeps the reference's constructor (no required arguments), attributes, spaces,
+`seed / reset / step / close / compute_reward` and return conventions (observation dtypes,
+`int` vs `np.float64` rewards, the `info` string / dict) - see SURVEY.md 8(b) and the quirk list
+Q11, Q13-Q18.  The state lives on the GPU (libgca, faithful mode: the reference's mixed f32/f64
+arithmetic); there is no CPU implementation behind it.
+"""
+import math
+
+import numpy as np
+
+from . import abi, variants
+from .batched import BatchedAircraftEnv, compute_reward as _device_compute_reward
+from .spaces import Box, Dict, Discrete
+
+
+class _SingleBase(object):
+    VARIANT = None
+    metadata = {"render.modes": []}
+    reward_range = (-float("inf"), float("inf"))
+    spec = None
+
+    def _config_class(self):
+        from gym_guidance_collision_avoidance_single.envs.config import Config
+        return Config
+
+    def __init__(self, device=0, seed=None, mode="faithful", time_limit=0, draws="philox", tape=None):
+        self.Config = self._config_class()
+        self.load_config()
+        self.state = None
+        self.viewer = None
+        self._time_limit = int(time_limit)
+        self._batch = BatchedAircraftEnv(self.VARIANT, 1, self.Config, n_intruders=self.intruder_size, mode=mode,
+                                         draws=draws, device=device,
+                                         seed=np.random.randint(2 ** 31) if seed is None else seed)
+        if tape is not None:                          # parity tests: replay recorded numpy draws
+            self._batch.set_tape(tape)
+        if self._time_limit:
+            self._batch.cfg.time_limit = self._time_limit
+            self._batch.refresh_observation_params()
+        self._faithful = mode == "faithful"
+        self._build_spaces()
+        self.position_range = Box(low=np.array([0, 0]), high=np.array([self.window_width, self.window_height]),
+                                  dtype=np.float32)
+        self.np_random = None
+        self.seed(2)                                  # PKG/SingleAircraftEnv.py:43 (unused by the dynamics there)
+
+    # PKG/SingleAircraftEnv.py:49-64
+    def load_config(self):
+        c = self.Config
+        self.window_width = c.window_width
+        self.window_height = c.window_height
+        self.intruder_size = c.intruder_size
+        self.EPISODES = c.EPISODES
+        self.G = c.G
+        self.tick = c.tick
+        self.scale = c.scale
+        self.minimum_separation = c.minimum_separation
+        self.NMAC_dist = c.NMAC_dist
+        self.horizon_dist = c.horizon_dist
+        self.initial_min_dist = c.initial_min_dist
+        self.goal_radius = c.goal_radius
+        self.min_speed = c.min_speed
+        self.max_speed = c.max_speed
+
+    def _build_spaces(self):
+        raise NotImplementedError
+
+    # PKG/SingleAircraftEnv.py:45-47.  The returned list matches gym; the dynamics of the reference
+    # draw from the global numpy stream whatever is passed here (Q1) - use reseed() to re-key ours.
+    def seed(self, seed=None):
+        self.np_random = np.random.RandomState(seed)
+        return [seed]
+
+    def reseed(self, seed):
+        """Re-key the on-device Philox stream that drives this environment's randomness."""
+        abi.check(self._batch.lib.gca_set_seed(self._batch._h, int(seed) & (2 ** 64 - 1)))
+
+    @property
+    def no_conflict(self):
+        """Number of conflicts of the running episode (read by Algorithms/MCTS/Agent.py:52)."""
+        return int(self._batch.get_state()["no_conflict"][0])
+
+    @property
+    def batch(self):
+        return self._batch
+
+    def _obs(self):
+        b = self._batch
+        return np.array(b.obs[0].cpu().numpy(), dtype=np.float64)
+
+    def _format_obs(self):
+        return self._obs()
+
+    def reset(self):
+        self._batch.refresh_observation_params()
+        self._batch.reset()
+        return self._format_obs()
+
+    def _decode(self, action):
+        return action
+
+    def _info(self, code):
+        return abi.INFO_STR[code]
+
+    def step(self, action):
+        import torch
+        b = self._batch
+        b.refresh_observation_params()
+        a = self._decode(action)
+        if b.continuous:
+            t = torch.as_tensor(np.asarray(a, np.float64).reshape(1, 2), device=b.device).to(b.real)
+        else:
+            t = torch.as_tensor(np.asarray([int(a)], np.int32), device=b.device)
+        b.step(t, auto_reset=False)
+        code = int(b.info[0].item())
+        done = bool(b.done[0].item())
+        r = float(b.reward[0].item())
+        if variants.reward_is_int(self.VARIANT, code):
+            reward = int(r)                            # the reference returns Python ints for the constant rows (Q11)
+        else:
+            reward = np.float64(r)
+        return self._format_obs(), reward, done, self._info(code)
+
+    def render(self, mode="human"):
+        raise NotImplementedError("rendering needs an OpenGL display in the reference; only SingleAircraftStackEnv "
+                                  "produces frames here (device rasteriser)")
+
+    def close(self):
+        if getattr(self, "_batch", None) is not None:
+            self._batch.close()
+            self._batch = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SingleAircraftEnv(_SingleBase):
+    """Discrete-9 actions, vector observation (PKG/SingleAircraftEnv.py:14-184)."""
+    VARIANT = "SingleAircraftEnv"
+
+    def _build_spaces(self):
+        dim = self.intruder_size * 4 + 8
+        self.observation_space = Box(low=-1000, high=1000, shape=(dim,), dtype=np.float32)
+        self.action_space = Discrete(9)
+
+
+class SingleAircraft2Env(_SingleBase):
+    """Continuous [-1,1]^2 actions (PKG/SingleAircraft2Env.py:12-176)."""
+    VARIANT = "SingleAircraft2Env"
+
+    def _build_spaces(self):
+        dim = self.intruder_size * 4 + 8
+        self.observation_space = Box(low=-1000, high=1000, shape=(dim,), dtype=np.float32)
+        self.action_space = Box(low=-1, high=1, shape=(2,), dtype=float)
+
+    def _decode(self, action):
+        assert self.action_space.contains(action), "given action is in incorrect shape"   # :127
+        return action
+
+
+class _GoalBase(_SingleBase):
+    def __init__(self, **kw):
+        _SingleBase.__init__(self, **kw)
+
+    def _format_obs(self):
+        b = self._batch
+        obs = np.array(b.obs[0].cpu().numpy(), dtype=np.float64)
+        ag = b.achieved[0].cpu().numpy()
+        dg = np.array(b.desired[0].cpu().numpy(), dtype=np.float64)
+        # achieved_goal is an f32-valued quantity in the reference (Q13)
+        return {"observation": obs, "achieved_goal": ag.astype(np.float32), "desired_goal": dg}
+
+    def _build_spaces(self):
+        # the reference resets inside the constructor to size its spaces (PKG/SingleAircraftHEREnv.py:32-39)
+        obs = self.reset()
+        self.observation_space = Dict(dict(
+            desired_goal=Box(-np.inf, np.inf, shape=obs["achieved_goal"].shape, dtype="float32"),
+            achieved_goal=Box(-np.inf, np.inf, shape=obs["achieved_goal"].shape, dtype="float32"),
+            observation=Box(-np.inf, np.inf, shape=obs["observation"].shape, dtype="float32"),
+        ))
+        self._build_action_space()
+
+    def compute_reward(self, achieved_goal, desired_goal, info):
+        """Vectorised over leading axes like the reference; evaluated on the device."""
+        import torch
+        b = self._batch
+        ag = torch.as_tensor(np.ascontiguousarray(achieved_goal), device=b.device)
+        g = torch.as_tensor(np.ascontiguousarray(desired_goal), device=b.device)
+        scalar = ag.dim() == 1
+        if scalar:
+            ag, g = ag[None], g[None]
+        r = _device_compute_reward(ag, g, self.goal_radius, b.cfg.obs_kind).cpu().numpy()
+        return r[0] if scalar else r
+
+
+class SingleAircraftHEREnv(_GoalBase):
+    """GoalEnv, continuous actions, dict observation (PKG/SingleAircraftHEREnv.py:12-196)."""
+    VARIANT = "SingleAircraftHEREnv"
+
+    def _build_action_space(self):
+        self.action_space = Box(low=-1, high=1, shape=(2,), dtype=float)
+
+    def _decode(self, action):
+        if not self.action_space.contains(action):
+            print("Warn: input action is", action)         # :142-143
+        return action
+
+    def _info(self, code):
+        return {"result": abi.INFO_STR[code]}
+
+
+class SingleAircraftDiscreteHEREnv(_GoalBase):
+    """GoalEnv, Discrete(3) heading-only actions (PKG/SingleAircraftDiscreteHEREnv.py:12-186)."""
+    VARIANT = "SingleAircraftDiscreteHEREnv"
+
+    def _build_action_space(self):
+        self.action_space = Discrete(3)
+
+    def _format_obs(self):
+        d = _GoalBase._format_obs(self)
+        # raw pixel goals: drone.position.copy() is f32, goal.position.copy() is f64 (:131-132)
+        return d
+
+    def _info(self, code):
+        return {}
+
+
+class SingleAircraftMCTSEnv(_SingleBase):
+    """The env Algorithms/MCTS/Agent.py drives (Simulators/SingleAircraftMCTSEnv.py): (a0, a1) tuple
+    actions, raw un-normalised observation, Config-driven reward row."""
+    VARIANT = "SingleAircraftMCTSEnv"
+
+    def _config_class(self):
+        from Simulators.config import Config
+        return Config
+
+    def _build_spaces(self):
+        dim = self.intruder_size * 4 + 8
+        self.observation_space = Box(low=-1000, high=1000, shape=(dim,), dtype=np.float32)
+        self.action_space = Discrete(9)
+
+    def _decode(self, action):
+        if isinstance(action, (tuple, list, np.ndarray)):
+            return int(action[0]) * 3 + int(action[1])
+        return int(action)
+
+    def step(self, action):
+        import torch
+        b = self._batch
+        b.refresh_observation_params()
+        t = torch.as_tensor(np.asarray([self._decode(action)], np.int32), device=b.device)
+        b.step(t, auto_reset=False)
+        code = int(b.info[0].item())
+        r = float(b.reward[0].item())
+        shaped = code == abi.INFO_NONE and not self.Config.sparse_reward
+        reward = np.float64(r) if shaped else r            # Config values are Python floats (-10 / 10 ...)
+        return self._obs(), reward, bool(b.done[0].item()), {"result": abi.INFO_STR[code]}
+
+
+def _unused():  # keep math imported for parity with the reference module namespace
+    return math.pi

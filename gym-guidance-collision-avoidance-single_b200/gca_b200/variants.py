@@ -22,7 +22,7 @@ VARIANTS = {
 }
 
 
-def make_config(variant, cfg_cls):
+def make_config(variant, cfg_cls, time_limit=0):
     """Snapshot the class attributes of `cfg_cls` (the reference's Config idiom,
     PKG/SingleAircraftEnv.py:49-64, :286-297) into a gca_config for `variant`."""
     act, obs, wall, shaped, rewards, use_max = VARIANTS[variant]
@@ -48,6 +48,7 @@ def make_config(variant, cfg_cls):
     c.shaped_default = shaped
     c.action_kind, c.obs_kind, c.wall_kind = act, obs, wall
     c.max_steps = int(cfg_cls.max_steps) if use_max else 0
+    c.time_limit = int(time_limit)
     return c
 
 

@@ -95,7 +95,9 @@ typedef struct gca_config {
   int32_t obs_kind;       /* GCA_OBS_* */
   int32_t wall_kind;      /* GCA_WALL_* */
   int32_t max_steps;      /* > 0: StackEnv rule - steps >= max_steps ends the episode before intruders move */
-  int32_t reserved0;
+  int32_t time_limit;     /* > 0: gym TimeLimit of the registered ids (timestep_limit=10000,
+                             gym_guidance_collision_avoidance_single/__init__.py:9): after the step,
+                             ep_steps >= time_limit also ends the episode (reward/info unchanged) */
 } gca_config;
 
 /* Canonical host-side view of the full simulator state, identical for both modes
@@ -146,6 +148,9 @@ int gca_obs_dim(const gca_config* cfg, int n_intruders);
 int gca_create(const gca_config* cfg, int n_envs, int n_intruders, int mode, int draws,
                int device, uint64_t seed, uint32_t env_id0, gca_env** out);
 int gca_destroy(gca_env* env);
+
+/* Re-key the Philox stream (gym's seed(); the reference's seed() does not touch its dynamics, Q1). */
+int gca_set_seed(gca_env* env, uint64_t seed);
 
 /* Update the parameters in place (the reference re-reads Config inside _get_ob, Q12). */
 int gca_set_config(gca_env* env, const gca_config* cfg);

@@ -406,6 +406,7 @@ int gca_oracle_step(const gca_config* cfg, gca_oracle_batch* b, const double* ac
     *e.ep_steps += 1;                                                    /* StackEnv :118 (a TimeLimit counter elsewhere) */
     ownship_step(&e, actions + 2 * (size_t)i);
     terminal_reward(&e, &b->reward[i], &b->done[i], &b->info[i]);
+    if (cfg->time_limit > 0 && *e.ep_steps >= cfg->time_limit) b->done[i] = 1;   /* gym TimeLimit (registered ids) */
     observe_env(&e, row(b->obs, i, D), row(b->achieved, i, 2), row(b->desired, i, 2));
     if (b->term_obs && D) memcpy(row(b->term_obs, i, D), row(b->obs, i, D), sizeof(double) * D);
     if (b->auto_reset && b->done[i]) {                                   /* baselines dummy_vec_env.py:52-55 */

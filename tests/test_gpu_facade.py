@@ -1,0 +1,148 @@
+"""The reference-facing gym facade (B = 1) and the VecEnv, replayed against the reference traces
+through their public API: same call sequence a user of the reference would write."""
+import numpy as np
+import pytest
+
+from helpers import config_class, load_trace
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+def close(a, b):
+    return np.allclose(a, b, rtol=RTOL, atol=1e-300)
+
+
+def _make(vk, n, **kw):
+    cfgc = config_class(vk)
+    cfgc.intruder_size = n                      # the reference idiom: mutate Config, then construct
+    try:
+        if vk == "mcts":
+            from Simulators.SingleAircraftMCTSEnv import SingleAircraftEnv as cls
+        else:
+            import gym_guidance_collision_avoidance_single.envs as envs
+            cls = {"env": envs.SingleAircraftEnv, "env2": envs.SingleAircraft2Env, "her": envs.SingleAircraftHEREnv,
+                   "dher": envs.SingleAircraftDiscreteHEREnv}[vk]
+        return cls(**kw)
+    finally:
+        cfgc.intruder_size = 80 if vk == "mcts" else 0
+
+
+def _ref_action(vk, a):
+    if vk in ("env", "dher"):
+        return int(a[0])
+    if vk == "mcts":
+        return (int(a[0]), int(a[1]))
+    return np.array(a, np.float64)
+
+
+@pytest.mark.parametrize("vk,n", [("env", 3), ("env", 80), ("env2", 3), ("her", 3), ("dher", 3), ("mcts", 80)])
+def test_single_env_api_replays_reference_trace(vk, n):
+    g = load_trace(vk, n)
+    plain = [int(i) for i in np.nonzero(g["kind_id"] == 0)[0]][:2]
+    for tr in plain:
+        tape = np.nan_to_num(g["tape"][tr:tr + 1], nan=0.0)
+        if vk in ("her", "dher"):               # these constructors reset() once themselves (PKG/SingleAircraftHEREnv.py:32)
+            tape = np.concatenate([tape[:, : int(g["cur_reset0"][tr])], tape], axis=1)
+        env = _make(vk, n, draws="tape", tape=tape)
+        ob = env.reset()
+        her = isinstance(ob, dict)
+        assert close(ob["observation"] if her else ob, g["obs0"][tr])
+        if her:
+            assert ob["achieved_goal"].dtype == np.float32 and ob["desired_goal"].dtype == np.float64
+            assert close(ob["achieved_goal"], g["ag0"][tr]) and close(ob["desired_goal"], g["dg0"][tr])
+        else:
+            assert ob.dtype == np.float64 and ob.shape == (4 * n + 8,)
+        for t in range(g["actions"].shape[1]):
+            ob, r, done, info = env.step(_ref_action(vk, g["actions"][tr, t]))
+            assert close(ob["observation"] if her else ob, g["obs"][tr, t])
+            assert close(r, g["reward"][tr, t])
+            if vk != "mcts":
+                assert isinstance(r, int) == bool(g["reward_is_int"][tr, t]), (vk, t, r)
+            assert done == bool(g["done"][tr, t]) and isinstance(done, bool)
+            code = ("", "n", "c", "g", "w", "m")[g["event"][tr, t]]
+            if vk in ("env", "env2"):
+                assert info == code
+            elif vk == "dher":
+                assert info == {}
+            else:
+                assert info == {"result": code}
+            assert env.no_conflict == int(g["no_conflict"][tr, t])
+            if done:
+                ob = env.reset()
+                assert close(ob["observation"] if her else ob, g["reset_obs"][tr, t])
+        env.close()
+
+
+def test_spaces_and_attributes_match_reference():
+    env = _make("env", 5)
+    assert env.observation_space.shape == (28,) and env.observation_space.dtype == np.float32
+    assert env.action_space.n == 9 and env.intruder_size == 5
+    assert env.seed(3) == [3]
+    assert env.minimum_separation == 18.5 and env.NMAC_dist == 5.0 and env.goal_radius == 20.0
+    env.close()
+    e2 = _make("env2", 0)
+    assert e2.action_space.shape == (2,) and e2.observation_space.shape == (8,)
+    e2.reset()
+    with pytest.raises(AssertionError):
+        e2.step(np.array([1.5, 0.0]))                # PKG/SingleAircraft2Env.py:127
+    e2.close()
+    her = _make("her", 2)
+    sp = her.observation_space.spaces
+    assert sp["observation"].shape == (14,) and sp["achieved_goal"].shape == (2,) and sp["desired_goal"].shape == (2,)
+    r = her.compute_reward(np.array([0.1, 0.2]), np.array([0.7, 0.9]), None)
+    assert r == 0.0 and np.signbit(r) and r.dtype == np.float32            # always -0.0 (Q14)
+    rb = her.compute_reward(np.zeros((5, 4, 2)), np.ones((5, 4, 2)), None)
+    assert rb.shape == (5, 4)
+    her.close()
+    dher = _make("dher", 2)
+    assert dher.action_space.n == 3
+    assert dher.compute_reward(np.array([100.0, 100.0]), np.array([110.0, 100.0]), None) == 1.0
+    assert dher.compute_reward(np.array([100.0, 100.0]), np.array([130.0, 100.0]), None) == 0.0
+    dher.close()
+
+
+def test_registered_ids_and_time_limit():
+    import gym_guidance_collision_avoidance_single as pkg
+    assert set(pkg.registry) >= {"guidance-collision-avoidance-single-v0",
+                                 "guidance-collision-avoidance-single-continuous-action-v0"}
+    env = pkg.make("guidance-collision-avoidance-single-v0", time_limit=7)   # spec default is 10000
+    env.reset()
+    dones = [env.step(4)[2] for _ in range(7)]
+    assert dones == [False] * 6 + [True]
+    env.close()
+
+
+def test_vec_env_interface():
+    import torch
+    from gca_b200.vec_env import AircraftVecEnv, AlreadySteppingError, NotSteppingError
+    venv = AircraftVecEnv("guidance-collision-avoidance-single-v0", 512, n_intruders=20, seed=1)
+    assert venv.num_envs == 512 and venv.observation_space.shape == (88,) and venv.action_space.n == 9
+    obs = venv.reset()
+    assert obs.shape == (512, 88) and obs.dtype == torch.float32 and obs.is_cuda
+    with pytest.raises(NotSteppingError):
+        venv.step_wait()
+    a = torch.randint(0, 9, (512,), device="cuda", dtype=torch.int32)
+    venv.step_async(a)
+    with pytest.raises(AlreadySteppingError):
+        venv.step_async(a)
+    obs, rew, done, info = venv.step_wait()
+    assert rew.shape == (512,) and done.shape == (512,) and info.shape == (512,)
+    # host flavour: numpy in, numpy out, same numbers as the device flavour
+    hv = AircraftVecEnv("guidance-collision-avoidance-single-v0", 512, n_intruders=20, seed=1, host=True)
+    venv2 = AircraftVecEnv("guidance-collision-avoidance-single-v0", 512, n_intruders=20, seed=1)
+    ho = hv.reset()
+    assert isinstance(ho, np.ndarray) and np.array_equal(ho, venv2.reset().cpu().numpy())
+    for _ in range(5):
+        an = np.random.randint(0, 9, 512).astype(np.int32)
+        o_h, r_h, d_h, i_h = hv.step(an)
+        o_d, r_d, d_d, i_d = venv2.step(torch.as_tensor(an, device="cuda"))
+        assert np.array_equal(o_h, o_d.cpu().numpy()) and np.array_equal(r_h, r_d.cpu().numpy())
+        assert d_h.dtype == bool and np.array_equal(d_h, d_d.cpu().numpy().astype(bool))
+    assert AircraftVecEnv.info_strings([0, 1, 2, 3, 4, 5]) == ["", "n", "c", "g", "w", "m"]
+    # goal envs hand back dict observations
+    gv = AircraftVecEnv("guidance-collision-avoidance-single-HER-v0", 64, n_intruders=3)
+    d = gv.reset()
+    assert set(d) == {"observation", "achieved_goal", "desired_goal"} and d["observation"].shape == (64, 18)
+    for v in (venv, hv, venv2, gv):
+        v.close()
