@@ -49,6 +49,26 @@ class GcaTape(C.Structure):
     _fields_ = [("values", C.c_void_p), ("stride", C.c_int64), ("cursor", C.c_void_p)]
 
 
+class GcaMctsConfig(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        "window_width", "window_height", "minimum_separation", "min_speed", "max_speed", "d_speed", "speed_sigma",
+        "position_sigma", "d_heading", "heading_sigma")] + [("simulate_frame", C.c_int32), ("search_depth", C.c_int32)]
+
+
+MCTS_WALL, MCTS_CONFLICT, MCTS_GOAL = 1, 2, 4
+
+
+def make_mcts_config(cfg_cls):
+    """Snapshot Algorithms/MCTS/config_single.py-style class attributes."""
+    c = GcaMctsConfig()
+    for name in ("window_width", "window_height", "minimum_separation", "min_speed", "max_speed", "d_speed",
+                 "speed_sigma", "position_sigma", "d_heading", "heading_sigma"):
+        setattr(c, name, float(getattr(cfg_cls, name)))
+    c.simulate_frame = int(cfg_cls.simulate_frame)
+    c.search_depth = int(cfg_cls.search_depth)
+    return c
+
+
 class GcaError(RuntimeError):
     pass
 

@@ -187,6 +187,45 @@ int gca_set_state(gca_env* env, const gca_host_state* src);
 int gca_compute_reward(const void* ag, const void* g, int64_t m, double radius, int kind,
                        int is_f64, float* out, int device, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * MCTS forward model (Algorithms/MCTS/nodes_single.py) - batched device-side playouts.
+ * Parameters follow Algorithms/MCTS/config_single.py:4-64. */
+typedef struct gca_mcts_config {
+  double window_width, window_height;
+  double minimum_separation;          /* conflict AND goal radius of the model (nodes_single.py:87,95; Q24) */
+  double min_speed, max_speed, d_speed, speed_sigma, position_sigma;
+  double d_heading, heading_sigma;
+  int32_t simulate_frame;             /* sub-frames per move() (config_single.py:59) */
+  int32_t search_depth;               /* moves per playout (config_single.py:61) */
+} gca_mcts_config;
+
+/* Philox counter of the playout kernels: (root id, playout id, what, index) */
+#define GCA_MCTS_DRAW_ACTION 0u       /* index = move number: action = floor(9 * u) */
+#define GCA_MCTS_DRAW_HEADING 1u      /* index = global sub-frame: Box-Muller cos branch * heading_sigma */
+#define GCA_MCTS_DRAW_SPEED 2u        /* index = global sub-frame (only drawn when speed_sigma != 0) */
+#define GCA_MCTS_DRAW_INTRUDER 3u     /* + intruder index; index = global sub-frame (only when position_sigma != 0) */
+
+enum { GCA_MCTS_WALL = 1, GCA_MCTS_CONFLICT = 2, GCA_MCTS_GOAL = 4 };
+
+/* SingleAircraftState.move(action) for m independent states (nodes_single.py:39-100).
+ * states: device double [m][4N+8] raw observation vectors (Simulators/SingleAircraftMCTSEnv.py:98-124),
+ * advanced in place; actions: device int32 [m] (a0*3+a1); flags: device uint8 [m] (GCA_MCTS_* bits).
+ * tape (nullable): the model's np.random.normal values in call order, values[i*stride + cursor[i]++];
+ * without a tape the draws are Philox (seed; root id = id0 + i, playout id 0). */
+int gca_mcts_move(const gca_mcts_config* cfg, int n_intruders, double* states, const int32_t* actions,
+                  uint8_t* flags, int64_t m, const gca_tape* tape, uint64_t seed, uint32_t id0, int first_frame,
+                  int device, void* stream);
+
+/* Node.rollout(search_depth) from n_roots root states, `playouts` independent random playouts each
+ * (nodes_single.py:198-204, common.py:54-55): uniform actions until terminal or `depth` moves, reward()
+ * of the final state (nodes_single.py:25-32).  first_action (nullable, int8 [n_roots][playouts], -1 =
+ * random) forces the first move, which is how a tree policy hands its selected child to the playout.
+ * Outputs: rewards double [n_roots][playouts]; first_out int8 (the first action taken);
+ * flags uint8 (GCA_MCTS_* of the final state). */
+int gca_mcts_playouts(const gca_mcts_config* cfg, int n_intruders, const double* roots, int64_t n_roots,
+                      int playouts, int depth, const int8_t* first_action, uint64_t seed, uint32_t root_id0,
+                      double* rewards, int8_t* first_out, uint8_t* flags, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

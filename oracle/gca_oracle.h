@@ -66,6 +66,20 @@ double gca_oracle_log(double x, int trig);
 void gca_oracle_philox_uniform2(uint64_t seed, uint32_t env, uint32_t tick, uint32_t slot, uint32_t block, double u[2]);
 void gca_oracle_philox_normal2(uint64_t seed, uint32_t env, uint32_t tick, uint32_t slot, int trig, double g[2]);
 
+/* ---- MCTS forward model and search (oracle/gca_oracle_mcts.c) ---- */
+int gca_oracle_mcts_move(const gca_mcts_config* c, int n, double* state, int action, int draws, int trig,
+                         const double* tape, int64_t* cursor, uint64_t seed, uint32_t root, int first_frame,
+                         uint8_t* flags, double* reward);
+int gca_oracle_mcts_rollout(const gca_mcts_config* c, int n, const double* root, int depth_limit, int draws, int trig,
+                            const double* tape, int64_t* cursor, uint64_t seed, uint32_t root_id, uint32_t playout,
+                            int forced_first, double* reward, int8_t* first_out, uint8_t* flags_out);
+int gca_oracle_mcts_playouts(const gca_mcts_config* c, int n, const double* roots, int64_t n_roots, int playouts,
+                             int depth, const int8_t* first_action, uint64_t seed, uint32_t root_id0, int trig,
+                             double* rewards, int8_t* first_out, uint8_t* flags);
+int gca_oracle_mcts_search(const gca_mcts_config* c, int n, const double* root, int sims, int search_depth,
+                           const double* tape, int64_t* cursor, int trig, int* best_action, double* child_n,
+                           double* child_q, int* child_action);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,12 @@ def lib():
     L.gca_oracle_philox_uniform2.restype = None
     L.gca_oracle_philox_normal2.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
     L.gca_oracle_philox_normal2.restype = None
+    MC = abi.GcaMctsConfig
+    vp, i32, i64, u32, u64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_uint32, C.c_uint64, C.c_double
+    L.gca_oracle_mcts_move.argtypes = [P(MC), i32, vp, i32, i32, i32, vp, vp, u64, u32, i32, vp, vp]
+    L.gca_oracle_mcts_rollout.argtypes = [P(MC), i32, vp, i32, i32, i32, vp, vp, u64, u32, u32, i32, vp, vp, vp]
+    L.gca_oracle_mcts_playouts.argtypes = [P(MC), i32, vp, i64, i32, i32, vp, u64, u32, i32, vp, vp, vp]
+    L.gca_oracle_mcts_search.argtypes = [P(MC), i32, vp, i32, i32, vp, vp, i32, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -176,3 +182,59 @@ def compute_reward(ag, g, radius, kind):
         g = np.ascontiguousarray(g, np.float64)
         L.gca_oracle_compute_reward(_p(ag), _p(g), m, float(radius), kind, _p(out))
     return out.reshape(ag.shape[:-1])
+
+
+# ------------------------------------------------------------------------------- MCTS model
+def mcts_move(cfg, n, state, action, tape=None, trig=TRIG_LIBM, seed=0, root=0, first_frame=0):
+    """SingleAircraftState.move on a copy of `state`; action = a0*3+a1.  Returns (state, flags, reward, draws used)."""
+    L = lib()
+    st = np.array(state, np.float64)
+    flags = np.zeros(1, np.uint8)
+    reward = np.zeros(1, np.float64)
+    cur = np.zeros(1, np.int64)
+    t = None if tape is None else np.ascontiguousarray(tape, np.float64)
+    rc = L.gca_oracle_mcts_move(C.byref(cfg), n, _p(st), int(action), 0 if tape is not None else 1, trig, _p(t), _p(cur),
+                                seed, root, first_frame, _p(flags), _p(reward))
+    assert rc == 0
+    return st, int(flags[0]), float(reward[0]), int(cur[0])
+
+
+def mcts_rollout(cfg, n, root, depth, tape=None, trig=TRIG_LIBM, seed=0, root_id=0, playout=0, forced_first=-1):
+    L = lib()
+    r = np.ascontiguousarray(root, np.float64)
+    reward = np.zeros(1, np.float64)
+    first = np.zeros(1, np.int8)
+    flags = np.zeros(1, np.uint8)
+    cur = np.zeros(1, np.int64)
+    t = None if tape is None else np.ascontiguousarray(tape, np.float64)
+    rc = L.gca_oracle_mcts_rollout(C.byref(cfg), n, _p(r), depth, 0 if tape is not None else 1, trig, _p(t), _p(cur),
+                                   seed, root_id, playout, forced_first, _p(reward), _p(first), _p(flags))
+    assert rc == 0
+    return float(reward[0]), int(first[0]), int(flags[0]), int(cur[0])
+
+
+def mcts_playouts(cfg, n, roots, playouts, depth, first_action=None, seed=0, root_id0=0, trig=TRIG_SHARED):
+    L = lib()
+    roots = np.ascontiguousarray(roots, np.float64)
+    R = roots.shape[0]
+    rewards = np.zeros((R, playouts), np.float64)
+    first = np.zeros((R, playouts), np.int8)
+    flags = np.zeros((R, playouts), np.uint8)
+    fa = None if first_action is None else np.ascontiguousarray(first_action, np.int8)
+    rc = L.gca_oracle_mcts_playouts(C.byref(cfg), n, _p(roots), R, playouts, depth, _p(fa), seed, root_id0, trig,
+                                    _p(rewards), _p(first), _p(flags))
+    assert rc == 0
+    return rewards, first, flags
+
+
+def mcts_search(cfg, n, root, sims, depth, tape, trig=TRIG_LIBM):
+    L = lib()
+    r = np.ascontiguousarray(root, np.float64)
+    t = np.ascontiguousarray(tape, np.float64)
+    cur = np.zeros(1, np.int64)
+    best = C.c_int(-1)
+    cn, cq, ca = np.zeros(9), np.zeros(9), np.zeros(9, np.int32)
+    rc = L.gca_oracle_mcts_search(C.byref(cfg), n, _p(r), sims, depth, _p(t), _p(cur), trig, C.byref(best), _p(cn),
+                                  _p(cq), _p(ca))
+    assert rc == 0
+    return best.value, cn, cq, ca, int(cur[0])
