@@ -433,4 +433,28 @@ int gca_compute_reward(const void* ag, const void* g, int64_t m, double radius, 
   return GCA_OK;
 }
 
+int gca_mcts_move(const gca_mcts_config* cfg, int n_intruders, double* states, const int32_t* actions, uint8_t* flags,
+                  int64_t m, const gca_tape* tape, uint64_t seed, uint32_t id0, int first_frame, int device,
+                  void* stream) {
+  if (!cfg || n_intruders < 0 || m < 0 || (m > 0 && (!states || !actions || !flags))) return fail(GCA_ERR_INVALID, "bad arguments");
+  if (tape && (!tape->values || !tape->cursor)) return fail(GCA_ERR_INVALID, "tape needs values and cursor");
+  GCA_CUDA(cudaSetDevice(device));
+  GCA_CUDA(launch_mcts_move(cfg, n_intruders, states, actions, flags, (long long)m, tape ? tape->values : nullptr,
+                            tape ? (long long)tape->stride : 0, tape ? reinterpret_cast<long long*>(tape->cursor) : nullptr,
+                            seed, id0, first_frame, (cudaStream_t)stream));
+  return GCA_OK;
+}
+
+int gca_mcts_playouts(const gca_mcts_config* cfg, int n_intruders, const double* roots, int64_t n_roots, int playouts,
+                      int depth, const int8_t* first_action, uint64_t seed, uint32_t root_id0, double* rewards,
+                      int8_t* first_out, uint8_t* flags, int device, void* stream) {
+  if (!cfg || n_intruders < 0 || n_roots < 0 || playouts <= 0 || depth < 0 || (n_roots > 0 && (!roots || !rewards)))
+    return fail(GCA_ERR_INVALID, "bad arguments");
+  if (cfg->simulate_frame <= 0) return fail(GCA_ERR_INVALID, "simulate_frame must be positive");
+  GCA_CUDA(cudaSetDevice(device));
+  GCA_CUDA(launch_mcts_playouts(cfg, n_intruders, roots, (long long)n_roots, playouts, depth, first_action, seed,
+                                root_id0, rewards, first_out, flags, (cudaStream_t)stream));
+  return GCA_OK;
+}
+
 }  // extern "C"

@@ -10,4 +10,10 @@ cudaError_t launch_reset(bool faith, bool tape, const StepArgs& a, cudaStream_t 
 cudaError_t launch_observe(bool faith, const StepArgs& a, cudaStream_t st);
 cudaError_t launch_compute_reward(const void* ag, const void* g, long long m, double radius, int kind, int is_f64,
                                   float* out, cudaStream_t st);
+cudaError_t launch_mcts_playouts(const gca_mcts_config* cfg, int n, const double* roots, long long n_roots, int playouts,
+                                 int depth, const int8_t* first_action, uint64_t seed, uint32_t root_id0,
+                                 double* rewards, int8_t* first_out, uint8_t* flags, cudaStream_t st);
+cudaError_t launch_mcts_move(const gca_mcts_config* cfg, int n, double* states, const int32_t* actions, uint8_t* flags,
+                             long long m, const double* tape, long long tape_stride, long long* cursor, uint64_t seed,
+                             uint32_t id0, int first_frame, cudaStream_t st);
 }  // namespace gca

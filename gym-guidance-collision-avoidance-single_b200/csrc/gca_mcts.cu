@@ -1,0 +1,349 @@
+// gca_mcts.cu - the MCTS forward model of the reference as batched device-side playouts (sm_100a).
+//
+// Reference: Algorithms/MCTS/nodes_single.py (SingleAircraftState.move :39-100, reward :25-32,
+// is_terminal_state :34-37, rollout :198-204), common.py (rollout_policy :54-55),
+// config_single.py.  All arithmetic is f64 (the model works on Python floats); the quirks are
+// kept: the last intruder is ignored (Q22), speed = clamp(own vy) so the throttle is inert (Q23),
+// conflict and goal both use minimum_separation and there is no NMAC tier (Q24), the wall test
+// is strict (Q6).
+//
+// playout kernel: one warp per playout.  What is sequential in the reference is split so that the
+// expensive f64 work runs lane-parallel:
+//   (1) lane f draws the heading noise of sub-frame f (Philox + Box-Muller)        - parallel
+//   (2) headings are accumulated in the reference's order (h += dpsi; h += noise)    - 2 DADD / frame
+//   (3) lane f evaluates sincos(h_f)                                                 - parallel
+//   (4) the speed / position recurrence (speed_f = clamp(vy_{f-1})) runs as a short uniform
+//       loop fed by shuffles; lane f keeps the ownship position of sub-frame f
+//   (5) sub-frame loop, lanes = intruders: positions advance by repeated f64 addition exactly
+//       like the reference, squared distance against the pre-squared threshold, __any_sync;
+//       the loop ends at the first sub-frame with a wall / conflict / goal event.
+// The kernel is bound by the FP64 pipe (about 8 DFMA-class instructions per intruder per sub-frame),
+// not by HBM: a root state (2.6 KB at N = 80) is read once per playout and stays in registers.
+#include "gca_launch.h"
+
+namespace gca {
+
+struct MctsArgs {
+  gca_mcts_config c;
+  double sep2;              // min{ s : sqrt(s) >= minimum_separation }
+  int n, near, L;
+  // playouts
+  const double* roots;
+  long long n_roots;
+  int playouts, depth;
+  const int8_t* first_action;
+  uint32_t key0, key1, root_id0;
+  double* rewards;
+  int8_t* first_out;
+  uint8_t* flags;
+  // move
+  double* states;
+  const int32_t* actions;
+  long long m;
+  const double* tape;
+  long long tape_stride;
+  long long* cursor;
+  int first_frame;
+};
+
+__device__ __forceinline__ void mcts_uniform2(const MctsArgs& a, uint32_t root, uint32_t playout, uint32_t what,
+                                              uint32_t idx, double& u0, double& u1) {
+  const uint4 w = philox4x32_10(make_uint4(root, playout, what, idx), a.key0, a.key1);
+  u0 = u53(w.x, w.y);
+  u1 = u53(w.z, w.w);
+}
+
+// np.random.normal(0, sigma): Box-Muller cos branch of block (what, idx)
+__device__ __forceinline__ double mcts_normal(const MctsArgs& a, double sigma, uint32_t root, uint32_t playout,
+                                              uint32_t what, uint32_t idx) {
+  if (sigma == 0.0) return 0.0;
+  double u0, u1, sn, cs;
+  mcts_uniform2(a, root, playout, what, idx, u0, u1);
+  const double r = __dsqrt_rn(__dmul_rn(-2.0, gca_log(__dadd_rn(1.0, -u0))));
+  gca_sincos(__dmul_rn(6.283185307179586, u1), &sn, &cs);
+  return __dadd_rn(0.0, __dmul_rn(sigma, __dmul_rn(r, cs)));
+}
+
+__device__ __forceinline__ int mcts_action(const MctsArgs& a, uint32_t root, uint32_t playout, uint32_t move) {
+  double u0, u1;
+  mcts_uniform2(a, root, playout, GCA_MCTS_DRAW_ACTION, move, u0, u1);
+  const int k = (int)__dmul_rn(9.0, u0);
+  return k > 8 ? 8 : k;
+}
+
+__device__ __forceinline__ double clamp_speed(const gca_mcts_config& c, double vy) {
+  const double m = c.max_speed < vy ? c.max_speed : vy;       // min(state[-5], max_speed)
+  return m > c.min_speed ? m : c.min_speed;                   // max(min_speed, .)
+}
+
+__device__ __forceinline__ double shfl_f64(double v, int src) {
+  return __shfl_sync(FULL, v, src);
+}
+
+constexpr int kMctsWarps = 4;
+constexpr int kMaxRounds = 4;       // intruder rounds held in registers (N - 1 <= 128); larger N uses the generic path
+
+// RC > 0: intruder rounds in registers; RC == 0: intruders live in shared memory (any N)
+template <int RC>
+__global__ void __launch_bounds__(kMctsWarps * 32) mcts_playout_kernel(const MctsArgs a) {
+  extern __shared__ double mcts_smem[];
+  const gca_mcts_config& c = a.c;
+  const int lane = threadIdx.x & 31;
+  const int warp_in_block = threadIdx.x >> 5;
+  const long long pid = (long long)blockIdx.x * kMctsWarps + warp_in_block;
+  const long long total = a.n_roots * a.playouts;
+  if (pid >= total) return;
+  const long long r_idx = pid / a.playouts;
+  const uint32_t playout = (uint32_t)(pid - r_idx * a.playouts);
+  const uint32_t root = a.root_id0 + (uint32_t)r_idx;
+  const double* st = a.roots + r_idx * a.L;
+  const double* own = st + 4 * a.n;
+
+  // ---- intruders: lane i + 32 r holds (x, y, vx, vy)
+  double ix[RC > 0 ? RC : 1], iy[RC > 0 ? RC : 1], ivx[RC > 0 ? RC : 1], ivy[RC > 0 ? RC : 1];
+  double* sm = mcts_smem + (size_t)warp_in_block * 4 * a.near;      // RC == 0 only
+  if constexpr (RC > 0) {
+#pragma unroll
+    for (int r = 0; r < RC; ++r) {
+      const int i = r * 32 + lane;
+      const bool v = i < a.near;
+      const double2 p = v ? reinterpret_cast<const double2*>(st)[2 * i] : make_double2(0., 0.);
+      const double2 w = v ? reinterpret_cast<const double2*>(st)[2 * i + 1] : make_double2(0., 0.);
+      ix[r] = p.x; iy[r] = p.y; ivx[r] = w.x; ivy[r] = w.y;
+    }
+  } else {
+    for (int j = lane; j < 4 * a.near; j += 32) sm[j] = st[j];
+    __syncwarp();
+  }
+  double ox = own[0], oy = own[1], vy_prev = own[3], speed = own[4], heading = own[5];
+  const double gx = own[6], gy = own[7];
+  (void)speed;
+
+  const int F = c.simulate_frame;
+  int flags = 0, first = -1;
+  int depth = 0;
+  // ---- one move() per iteration; sub-frames handled in chunks of 32 lanes
+  while (!(flags || depth == a.depth)) {
+    int act;
+    if (depth == 0 && a.first_action && a.first_action[pid] >= 0) act = a.first_action[pid];
+    else act = mcts_action(a, root, playout, (uint32_t)depth);
+    if (first < 0) first = act;
+    const double d_heading = __dmul_rn((double)(act / 3 - 1), c.d_heading);
+    for (int f0 = 0; f0 < F && !flags; f0 += 32) {
+      const int nf = min(32, F - f0);
+      const uint32_t gf = (uint32_t)(depth * F + f0 + lane);
+      // (1) noises of sub-frame f0 + lane
+      double nh = 0.0, nsp = 0.0;
+      if (lane < nf) {
+        nh = mcts_normal(a, c.heading_sigma, root, playout, GCA_MCTS_DRAW_HEADING, gf);
+        nsp = mcts_normal(a, c.speed_sigma, root, playout, GCA_MCTS_DRAW_SPEED, gf);
+      }
+      // (2) headings in the reference's order
+      double my_h = 0.0;
+      for (int f = 0; f < nf; ++f) {
+        heading = __dadd_rn(heading, d_heading);                      // state[-3] += d_heading
+        heading = __dadd_rn(heading, shfl_f64(nh, f));                // state[-3] += normal(0, heading_sigma)
+        if (lane == f) my_h = heading;
+      }
+      // (3) sincos of each sub-frame's heading
+      double sn = 0.0, cs = 1.0;
+      if (lane < nf) gca_sincos(my_h, &sn, &cs);
+      // (4) speed / position recurrence; lane f keeps the ownship position of sub-frame f
+      double my_ox = 0.0, my_oy = 0.0;
+      for (int f = 0; f < nf; ++f) {
+        double sp = clamp_speed(c, vy_prev);                          // state[-4] = clamp(state[-5])  (Q23)
+        sp = __dadd_rn(sp, shfl_f64(nsp, f));                         // += normal(0, speed_sigma)
+        const double vx = __dmul_rn(sp, shfl_f64(cs, f)), vy = __dmul_rn(sp, shfl_f64(sn, f));
+        ox = __dadd_rn(ox, vx);
+        oy = __dadd_rn(oy, vy);
+        vy_prev = vy;
+        if (lane == f) { my_ox = ox; my_oy = oy; }
+      }
+      // per-sub-frame ownship events, evaluated lane-parallel
+      const bool wall = lane < nf && (!(0.0 < my_ox && my_ox < c.window_width) || !(0.0 < my_oy && my_oy < c.window_height));
+      bool goal = false;
+      if (lane < nf) {
+        const double dx = __dadd_rn(my_ox, -gx), dy = __dadd_rn(my_oy, -gy);
+        goal = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < a.sep2;   // metric(own, goal) < minimum_separation
+      }
+      const uint32_t wall_mask = __ballot_sync(FULL, wall), goal_mask = __ballot_sync(FULL, goal);
+      // (5) intruders, sub-frame by sub-frame, until the first event
+      int f_end = nf;
+      for (int f = 0; f < nf; ++f) {
+        const uint32_t gfu = (uint32_t)(depth * F + f0 + f);
+        const double fx = shfl_f64(my_ox, f), fy = shfl_f64(my_oy, f);
+        bool hit = false;
+        if constexpr (RC > 0) {
+#pragma unroll
+          for (int r = 0; r < RC; ++r) {
+            const int i = r * 32 + lane;
+            if (i < a.near) {
+              const double npx = mcts_normal(a, c.position_sigma, root, playout, GCA_MCTS_DRAW_INTRUDER + (uint32_t)i, 2 * gfu);
+              const double npy = mcts_normal(a, c.position_sigma, root, playout, GCA_MCTS_DRAW_INTRUDER + (uint32_t)i, 2 * gfu + 1);
+              ix[r] = __dadd_rn(ix[r], __dadd_rn(ivx[r], npx));      // x += vx + normal(0, position_sigma)
+              iy[r] = __dadd_rn(iy[r], __dadd_rn(ivy[r], npy));
+              const double dx = __dadd_rn(ix[r], -fx), dy = __dadd_rn(iy[r], -fy);
+              hit |= __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < a.sep2;
+            }
+          }
+        } else {
+          for (int i = lane; i < a.near; i += 32) {
+            const double npx = mcts_normal(a, c.position_sigma, root, playout, GCA_MCTS_DRAW_INTRUDER + (uint32_t)i, 2 * gfu);
+            const double npy = mcts_normal(a, c.position_sigma, root, playout, GCA_MCTS_DRAW_INTRUDER + (uint32_t)i, 2 * gfu + 1);
+            const double x = __dadd_rn(sm[4 * i], __dadd_rn(sm[4 * i + 2], npx));
+            const double y = __dadd_rn(sm[4 * i + 1], __dadd_rn(sm[4 * i + 3], npy));
+            sm[4 * i] = x;
+            sm[4 * i + 1] = y;
+            const double dx = __dadd_rn(x, -fx), dy = __dadd_rn(y, -fy);
+            hit |= __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < a.sep2;
+          }
+        }
+        const bool conflict = __any_sync(FULL, hit);
+        // order inside a sub-frame: wall, then conflict, then goal (nodes_single.py:80-98)
+        if ((wall_mask >> f) & 1u) flags = GCA_MCTS_WALL;
+        else if (conflict) flags = GCA_MCTS_CONFLICT;
+        else if ((goal_mask >> f) & 1u) flags = GCA_MCTS_GOAL;
+        if (flags) {
+          f_end = f + 1;
+          break;
+        }
+      }
+      // the ownship state of the playout is the one of the last executed sub-frame
+      ox = shfl_f64(my_ox, f_end - 1);
+      oy = shfl_f64(my_oy, f_end - 1);
+    }
+    ++depth;
+  }
+  if (lane == 0) {
+    double reward;
+    if (flags & (GCA_MCTS_WALL | GCA_MCTS_CONFLICT)) reward = 0.0;
+    else if (flags & GCA_MCTS_GOAL) reward = 1.0;
+    else {
+      const double dx = __dadd_rn(ox, -gx), dy = __dadd_rn(oy, -gy);
+      const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+      reward = __dadd_rn(1.0, -__ddiv_rn(dist, 1200.0));
+    }
+    a.rewards[pid] = reward;
+    if (a.first_out) a.first_out[pid] = (int8_t)first;
+    if (a.flags) a.flags[pid] = (uint8_t)flags;
+  }
+}
+
+// SingleAircraftState.move for m independent states, one thread each, in the reference's own
+// sequential order (used by the drop-in node classes and by the tape-replay parity tests).
+__global__ void __launch_bounds__(128) mcts_move_kernel(const MctsArgs a) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.m) return;
+  const gca_mcts_config& c = a.c;
+  double* st = a.states + k * a.L;
+  double* own = st + 4 * a.n;
+  const int act = a.actions[k];
+  const double d_heading = __dmul_rn((double)(act / 3 - 1), c.d_heading);
+  const double accel = __dmul_rn((double)(act % 3 - 1), c.d_speed);
+  const bool tape = a.tape != nullptr;
+  const double* tp = tape ? a.tape + k * a.tape_stride : nullptr;
+  long long cur = tape ? a.cursor[k] : 0;
+  const uint32_t root = a.root_id0 + (uint32_t)k;
+  int flags = 0;
+  for (int f = 0; f < c.simulate_frame; ++f) {
+    const uint32_t gf = (uint32_t)(a.first_frame + f);
+    for (int i = 0; i < a.near; ++i) {
+      const double nx = tape ? tp[cur++] : mcts_normal(a, c.position_sigma, root, 0u, GCA_MCTS_DRAW_INTRUDER + (uint32_t)i, 2 * gf);
+      st[4 * i] = __dadd_rn(st[4 * i], __dadd_rn(st[4 * i + 2], nx));
+      const double ny = tape ? tp[cur++] : mcts_normal(a, c.position_sigma, root, 0u, GCA_MCTS_DRAW_INTRUDER + (uint32_t)i, 2 * gf + 1);
+      st[4 * i + 1] = __dadd_rn(st[4 * i + 1], __dadd_rn(st[4 * i + 3], ny));
+    }
+    own[4] = __dadd_rn(own[4], accel);
+    own[4] = clamp_speed(c, own[3]);
+    own[4] = __dadd_rn(own[4], tape ? tp[cur++] : mcts_normal(a, c.speed_sigma, root, 0u, GCA_MCTS_DRAW_SPEED, gf));
+    own[5] = __dadd_rn(own[5], d_heading);
+    own[5] = __dadd_rn(own[5], tape ? tp[cur++] : mcts_normal(a, c.heading_sigma, root, 0u, GCA_MCTS_DRAW_HEADING, gf));
+    double sn, cs;
+    gca_sincos(own[5], &sn, &cs);
+    const double vx = __dmul_rn(own[4], cs), vy = __dmul_rn(own[4], sn);
+    own[0] = __dadd_rn(own[0], vx);
+    own[1] = __dadd_rn(own[1], vy);
+    own[2] = vx;
+    own[3] = vy;
+    const double ox = own[0], oy = own[1];
+    if (!(0.0 < ox && ox < c.window_width) || !(0.0 < oy && oy < c.window_height)) {
+      flags = GCA_MCTS_WALL;
+      break;
+    }
+    bool conflict = false;
+    for (int i = 0; i < a.near && !conflict; ++i) {
+      const double dx = __dadd_rn(st[4 * i], -ox), dy = __dadd_rn(st[4 * i + 1], -oy);
+      conflict = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < a.sep2;
+    }
+    if (conflict) {
+      flags = GCA_MCTS_CONFLICT;
+      break;
+    }
+    const double dx = __dadd_rn(ox, -own[6]), dy = __dadd_rn(oy, -own[7]);
+    if (__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < a.sep2) {
+      flags = GCA_MCTS_GOAL;
+      break;
+    }
+  }
+  a.flags[k] = (uint8_t)flags;
+  if (tape) a.cursor[k] = cur;
+}
+
+static double sq_threshold_f64(double thr) {
+  if (!(thr > 0)) return 0;
+  double c = thr * thr;
+  while (c > 0 && sqrt(c) >= thr) c = nextafter(c, 0.0);
+  while (sqrt(c) < thr) c = nextafter(c, INFINITY);
+  return c;
+}
+
+static MctsArgs mcts_base(const gca_mcts_config* cfg, int n) {
+  MctsArgs a{};
+  a.c = *cfg;
+  a.sep2 = sq_threshold_f64(cfg->minimum_separation);
+  a.n = n;
+  a.L = 4 * n + 8;
+  a.near = a.L >= 9 ? (a.L - 9) / 4 : 0;      // (len - 9) // 4: the last intruder is ignored (Q22)
+  return a;
+}
+
+cudaError_t launch_mcts_playouts(const gca_mcts_config* cfg, int n, const double* roots, long long n_roots, int playouts,
+                                 int depth, const int8_t* first_action, uint64_t seed, uint32_t root_id0,
+                                 double* rewards, int8_t* first_out, uint8_t* flags, cudaStream_t st) {
+  MctsArgs a = mcts_base(cfg, n);
+  a.roots = roots; a.n_roots = n_roots; a.playouts = playouts; a.depth = depth; a.first_action = first_action;
+  a.key0 = (uint32_t)seed; a.key1 = (uint32_t)(seed >> 32); a.root_id0 = root_id0;
+  a.rewards = rewards; a.first_out = first_out; a.flags = flags;
+  const long long total = n_roots * playouts;
+  if (total <= 0) return cudaSuccess;
+  const unsigned blocks = (unsigned)((total + kMctsWarps - 1) / kMctsWarps);
+  const int rounds = (a.near + 31) / 32;
+  switch (rounds) {
+    case 0:
+    case 1: mcts_playout_kernel<1><<<blocks, kMctsWarps * 32, 0, st>>>(a); break;
+    case 2: mcts_playout_kernel<2><<<blocks, kMctsWarps * 32, 0, st>>>(a); break;
+    case 3: mcts_playout_kernel<3><<<blocks, kMctsWarps * 32, 0, st>>>(a); break;
+    case 4: mcts_playout_kernel<4><<<blocks, kMctsWarps * 32, 0, st>>>(a); break;
+    default: {
+      const size_t smem = sizeof(double) * kMctsWarps * 4 * (size_t)a.near;
+      cudaError_t e = cudaFuncSetAttribute(mcts_playout_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      mcts_playout_kernel<0><<<blocks, kMctsWarps * 32, smem, st>>>(a);
+    }
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mcts_move(const gca_mcts_config* cfg, int n, double* states, const int32_t* actions, uint8_t* flags,
+                             long long m, const double* tape, long long tape_stride, long long* cursor, uint64_t seed,
+                             uint32_t id0, int first_frame, cudaStream_t st) {
+  MctsArgs a = mcts_base(cfg, n);
+  a.states = states; a.actions = actions; a.flags = flags; a.m = m;
+  a.tape = tape; a.tape_stride = tape_stride; a.cursor = cursor;
+  a.key0 = (uint32_t)seed; a.key1 = (uint32_t)(seed >> 32); a.root_id0 = id0; a.first_frame = first_frame;
+  if (m <= 0) return cudaSuccess;
+  mcts_move_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace gca

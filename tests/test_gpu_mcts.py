@@ -1,0 +1,102 @@
+"""MCTS forward model on the GPU: tape replay of the reference's recorded move() calls, and
+bit-exact agreement of the Philox playout kernel with the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN
+from gca_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+
+def mcts_cfg(**over):
+    from Algorithms.MCTS.config_single import Config
+    c = abi.make_mcts_config(Config)
+    for k, v in over.items():
+        setattr(c, k, v)
+    return c
+
+
+@pytest.mark.parametrize("n", [3, 80])
+def test_move_replays_reference(n):
+    import torch
+    from gca_b200 import mcts
+    g = np.load(os.path.join(GOLDEN, "mcts_n%d.npz" % n))
+    m = len(g["mv_root"])
+    states = torch.as_tensor(g["roots"][g["mv_root"]].copy(), device="cuda")
+    actions = torch.as_tensor((g["mv_action"][:, 0] * 3 + g["mv_action"][:, 1]).astype(np.int32), device="cuda")
+    tape = torch.as_tensor(np.nan_to_num(g["mv_tape"], nan=0.0), device="cuda")
+    cursor = torch.zeros(m, dtype=torch.int64, device="cuda")
+    flags = mcts.move(states, actions, mcts_cfg(), tape=tape, cursor=cursor).cpu().numpy()
+    assert np.array_equal(cursor.cpu().numpy(), g["mv_tape_len"])
+    assert np.array_equal((flags & abi.MCTS_WALL) != 0, g["mv_hit_wall"])
+    assert np.array_equal((flags & abi.MCTS_CONFLICT) != 0, g["mv_conflict"])
+    assert np.array_equal((flags & abi.MCTS_GOAL) != 0, g["mv_reach_goal"])
+    out = states.cpu().numpy()
+    # heading noise comes from the tape; cos/sin are the only non-shared ops: <= 1e-9 relative, almost always exact
+    assert np.allclose(out, g["mv_out_state"], rtol=1e-9, atol=1e-300)
+    print("bit-identical successor states: %d / %d" % (int((out == g["mv_out_state"]).all(1).sum()), m))
+
+
+@pytest.mark.parametrize("n,roots_n,playouts,depth,over", [
+    (80, 64, 100, 3, {}), (3, 200, 50, 3, {}), (1, 50, 20, 2, {}), (0, 50, 20, 3, {}),
+    (200, 16, 30, 3, {}),                                   # generic (shared-memory) intruder path
+    (80, 8, 10, 4, {"simulate_frame": 10}),                 # 40 sub-frames: two lane chunks
+    (20, 32, 20, 3, {"speed_sigma": 0.05, "position_sigma": 0.3}),
+])
+def test_playouts_bit_exact_vs_oracle(n, roots_n, playouts, depth, over):
+    import torch
+    from gca_b200 import mcts
+    from oracle import oracle as orc
+    cfg = mcts_cfg(**over)
+    rng = np.random.RandomState(n + 7)
+    L = 4 * n + 8
+    roots = np.zeros((roots_n, L))
+    for r in range(roots_n):
+        ip = rng.uniform(0, 800, (n, 2)); sp = rng.uniform(5 / 3, 8 / 3, n); hd = rng.uniform(0, 2 * np.pi, n)
+        roots[r, :4 * n] = np.stack([ip[:, 0], ip[:, 1], sp * np.cos(hd), sp * np.sin(hd)], -1).ravel()
+        own = rng.uniform(30, 770, 2); h = rng.uniform(0, 2 * np.pi); s = rng.uniform(5 / 3, 8 / 3)
+        goal = own + rng.uniform(-120, 120, 2) if r % 3 == 0 else rng.uniform(0, 800, 2)
+        if n and r % 4 == 1:                                  # aim at an intruder: conflicts
+            own = ip[rng.randint(max(n - 1, 1))] - 30 * np.array([np.cos(h), np.sin(h)])
+        if r % 7 == 2:                                        # near a wall, heading out
+            own = np.array([rng.uniform(0.5, 15), rng.uniform(100, 700)]); h = np.pi + rng.normal(0, .2)
+        roots[r, 4 * n:] = [own[0], own[1], s * np.cos(h), s * np.sin(h), s, h, goal[0], goal[1]]
+    fa = rng.randint(-1, 9, (roots_n, playouts)).astype(np.int8)
+    want_r, want_f, want_fl = orc.mcts_playouts(cfg, n, roots, playouts, depth, first_action=fa, seed=77, root_id0=5)
+    got_r, got_f, got_fl = mcts.playouts(torch.as_tensor(roots, device="cuda"), playouts, depth=depth, cfg=cfg,
+                                         first_action=torch.as_tensor(fa, device="cuda"), seed=77, root_id0=5)
+    assert np.array_equal(got_fl.cpu().numpy(), want_fl)
+    assert np.array_equal(got_f.cpu().numpy(), want_f)
+    assert np.array_equal(got_r.cpu().numpy(), want_r)
+    print("n=%d flags histogram" % n, np.bincount(want_fl.ravel(), minlength=5).tolist())
+
+
+def test_drop_in_search_classes():
+    """Agent.py:37-41 call sequence on the drop-in classes."""
+    from Algorithms.MCTS.nodes_single import SingleAircraftNode, SingleAircraftState
+    from Algorithms.MCTS.search_single import MCTS
+    g = np.load(os.path.join(GOLDEN, "mcts_n3.npz"))
+    np.random.seed(0)
+    state = SingleAircraftState(state=g["roots"][0])
+    root = SingleAircraftNode(state=state)
+    best = MCTS(root).best_action(30, 2)
+    assert best.state.prev_action in [(a, b) for a in range(3) for b in range(3)]
+    assert len(root.children) == 9 and root.n == 30.0
+    nxt = state.move((1, 1))
+    assert nxt.depth == 1 and nxt.prev_action == (1, 1) and nxt.state.shape == state.state.shape
+    assert 0.0 <= nxt.reward() <= 1.0
+
+
+def test_batched_planner_prefers_safe_actions():
+    import torch
+    from gca_b200 import mcts
+    n = 3
+    root = np.zeros(4 * n + 8)
+    root[:12] = [400, 360, 0, 0, 700, 700, 0, 0, 100, 100, 0, 0]        # a stationary intruder straight ahead (north)
+    root[12:] = [400, 300, 0, 2.5, 2.5, np.pi / 2, 400, 700]            # ownship heading north towards it and the goal
+    acts = mcts.plan_actions(torch.as_tensor(np.tile(root, (16, 1)), device="cuda"), n_simulations=450, seed=1)
+    assert acts.shape == (16, 2)
+    assert (acts[:, 0] != 1).float().mean() > 0.8                        # going straight collides: the planner turns
