@@ -303,10 +303,51 @@ def main_gpu(args):
         if world == 1 and not kernel_only:
             cb, _, _ = run_cpu(10 ** 9, 1, budget_s=12.0)
             line["cpu_baseline"] = cb
+        if not kernel_only:
+            line["mcts"] = bench_mcts(local, with_cpu=(world == 1))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_mcts(device, with_cpu):
+    """Second metric of BASELINE.json: MCTS rollouts/s = completed random playouts (root -> terminal or
+    depth 3, 10 sub-frames per move, N = 80) per second, config #4.  Rank-local (independent roots)."""
+    import torch
+    from gca_b200 import abi, mcts
+    from gca_b200.batched import BatchedAircraftEnv
+    from Simulators.config import Config as SimConfig
+    from Algorithms.MCTS.config_single import Config as MctsConfig
+    R, P, depth = 4096, 100, 3
+    env = BatchedAircraftEnv("SingleAircraftMCTSEnv", R, SimConfig, n_intruders=80, mode="faithful", device=device, seed=2)
+    roots = env.reset().clone()                      # raw observations after reset = MCTS root states
+    cfg = abi.make_mcts_config(MctsConfig)
+    for _ in range(3):
+        mcts.playouts(roots, P, depth=depth, cfg=cfg, seed=5)
+    torch.cuda.synchronize()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    start.record()
+    for i in range(reps):
+        rewards, _, flags = mcts.playouts(roots, P, depth=depth, cfg=cfg, seed=6 + i)
+    stop.record()
+    torch.cuda.synchronize()
+    ms = start.elapsed_time(stop) / reps
+    out = {"metric": "mcts_rollouts_per_sec", "value": R * P / (ms * 1e-3), "unit": "rollouts/s", "roots": R,
+           "playouts_per_root": P, "depth": depth, "intruders": 80, "ms_per_launch": ms,
+           "mean_reward": float(rewards.mean().item()), "terminal_fraction": float((flags != 0).float().mean().item()),
+           "dtype": "f64", "bound": "fp64 pipe (no HBM roofline: a 2.6 KB root is read once per playout)"}
+    env.close()
+    if with_cpu:
+        from oracle import oracle as orc
+        sample = roots[:8].cpu().numpy()
+        t0 = time.perf_counter()
+        orc.mcts_playouts(cfg, 80, sample, 50, depth, seed=6)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 8 * 50 / dt, "unit": "rollouts/s", "cores": 1, "kind": "port",
+                               "sample": "8 roots x 50 playouts, C oracle port (oracle/gca_oracle_mcts.c), 1 thread"}
+    return out
 
 
 def main():

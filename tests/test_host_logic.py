@@ -1,0 +1,107 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/gca.h declares,
+the host-side mirror of the reference interface (config table, spaces, registry, VecEnv state
+machine) behaves like the reference, and the product refuses to run without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from gca_b200 import abi, variants
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "gca.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(gca_[a-z0-9_]+)\s*\(", hdr, re.M))
+    assert len(declared) >= 17
+    lib = ctypes.CDLL(abi.LIB_PATH)
+    missing = [name for name in sorted(declared) if not hasattr(lib, name)]
+    assert not missing, missing
+    assert abi.load().gca_abi_version() == abi.GCA_ABI_VERSION
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(abi.GcaConfig) == 21 * 8 + 6 * 4
+    assert ctypes.sizeof(abi.GcaMctsConfig) == 10 * 8 + 2 * 4
+    assert ctypes.sizeof(abi.GcaHostState) == 12 * 8 and ctypes.sizeof(abi.GcaOut) == 6 * 8
+    assert ctypes.sizeof(abi.GcaTape) == 24
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from gca_b200.batched import BatchedAircraftEnv
+    from gym_guidance_collision_avoidance_single.envs.config import Config
+    with pytest.raises(abi.GcaError):
+        BatchedAircraftEnv("SingleAircraftEnv", 4, Config)
+    # the C ABI itself also refuses: no device -> GCA_ERR_CUDA, never a silent host path
+    lib = abi.load()
+    h = ctypes.c_void_p()
+    cfg = variants.make_config("SingleAircraftEnv", Config)
+    rc = lib.gca_create(ctypes.byref(cfg), 4, 0, abi.MODE_FAST, abi.DRAWS_PHILOX, 0, 0, 0, ctypes.byref(h))
+    assert rc == -2 and b"CUDA" in lib.gca_last_error()
+    import gym_guidance_collision_avoidance_single.envs as envs
+    with pytest.raises(abi.GcaError):
+        envs.SingleAircraftEnv()
+
+
+def test_abi_argument_checking():
+    lib = abi.load()
+    from gym_guidance_collision_avoidance_single.envs.config import Config
+    cfg = variants.make_config("SingleAircraftEnv", Config)
+    h = ctypes.c_void_p()
+    assert lib.gca_create(None, 4, 0, 1, 1, 0, 0, 0, ctypes.byref(h)) == -1
+    assert lib.gca_create(ctypes.byref(cfg), 0, 0, 1, 1, 0, 0, 0, ctypes.byref(h)) == -1
+    assert lib.gca_create(ctypes.byref(cfg), 4, -1, 1, 1, 0, 0, 0, ctypes.byref(h)) == -1
+    assert lib.gca_create(ctypes.byref(cfg), 4, 0, 7, 1, 0, 0, 0, ctypes.byref(h)) == -1
+    bad = variants.make_config("SingleAircraftEnv", Config)
+    bad.obs_kind = 99
+    assert lib.gca_create(ctypes.byref(bad), 4, 0, 1, 1, 0, 0, 0, ctypes.byref(h)) == -1
+    assert b"obs_kind" in lib.gca_last_error()
+    assert lib.gca_obs_dim(ctypes.byref(cfg), 80) == 328
+    assert lib.gca_step(None, None, None, 1, None, None) == -1
+    assert lib.gca_destroy(None) == 0
+
+
+def test_variant_table_matches_reference_reward_rows():
+    from gym_guidance_collision_avoidance_single.envs.config import Config
+    from Simulators.config import Config as Sim
+    rows = {k: variants.make_config(k, Sim if k == "SingleAircraftMCTSEnv" else Config) for k in variants.VARIANTS}
+    r = rows["SingleAircraftEnv"]
+    assert (r.r_nmac, r.r_conflict, r.r_goal, r.shaped_default, r.wall_kind) == (-20, -5, 10, 1, abi.WALL_NONE)
+    r = rows["SingleAircraft2Env"]
+    assert (r.r_nmac, r.r_conflict, r.r_wall, r.r_goal, r.wall_kind) == (-5, -1, -100, 1, abi.WALL_TERMINAL)
+    r = rows["SingleAircraftHEREnv"]
+    assert (r.r_nmac, r.r_conflict, r.r_goal, r.r_default, r.shaped_default) == (-5, -1, 0, -1, 0)
+    r = rows["SingleAircraftDiscreteHEREnv"]
+    assert (r.r_wall, r.r_goal, r.r_default, r.action_kind) == (-5, 1, 0, abi.ACT_DISCRETE3)
+    r = rows["SingleAircraftStackEnv"]
+    assert (r.r_wall, r.r_goal, r.wall_kind, r.max_steps, r.obs_kind) == (-10, 10000, abi.WALL_PENALTY, 1000, abi.OBS_NONE)
+    r = rows["SingleAircraftMCTSEnv"]
+    assert (r.r_nmac, r.r_conflict, r.r_goal, r.obs_kind, r.heading_sigma) == (-1.0, -0.5, 1.0, abi.OBS_RAW, np.radians(4))
+    assert Config.intruder_size == 0 and Sim.intruder_size == 80          # Q28
+    assert (Config.minimum_separation, Config.NMAC_dist, Config.initial_min_dist, Config.goal_radius) == (18.5, 5.0, 100.0, 20.0)
+    assert variants.obs_dim(rows["SingleAircraftEnv"], 80) == 328 and variants.obs_dim(rows["SingleAircraftHEREnv"], 80) == 326
+
+
+def test_registry_and_spaces():
+    import gym_guidance_collision_avoidance_single as pkg
+    assert len(pkg.registry) == 5
+    for spec in pkg.registry.values():
+        assert spec["timestep_limit"] == 10000 and spec["reward_threshold"] == 10.0
+    from gca_b200.spaces import Box, Discrete
+    b = Box(low=-1, high=1, shape=(2,), dtype=float)
+    assert b.contains(np.array([1.0, -1.0])) and not b.contains(np.array([1.0001, 0])) and not b.contains(np.zeros(3))
+    pr = Box(low=np.array([0, 0]), high=np.array([800, 800]), dtype=np.float32)
+    assert pr.contains(np.array([800.0, 0.0], np.float32)) and not pr.contains(np.array([800.0001, 5.0]))   # inclusive (Q6)
+    assert Discrete(9).contains(8) and not Discrete(9).contains(9)
+
+
+def test_bench_algorithmic_bytes():
+    import bench
+    assert bench.algorithmic_bytes_per_env_step(80) == 40 * 80 + 12 + 159
+    assert bench.algorithmic_bytes_per_env_step(0, continuous=False) == 155
