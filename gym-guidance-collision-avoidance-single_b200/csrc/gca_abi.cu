@@ -433,6 +433,21 @@ int gca_compute_reward(const void* ag, const void* g, int64_t m, double radius, 
   return GCA_OK;
 }
 
+int gca_raster(gca_env* e, const uint8_t* sprites, uint8_t* frames, int64_t env_stride, int64_t plane_stride,
+               int n_planes, int slot, const uint8_t* clear_mask, void* stream) {
+  if (!e || !sprites || !frames) return fail(GCA_ERR_INVALID, "env/sprites/frames is NULL");
+  if (e->s.N > GCA_RASTER_MAX_INTRUDERS) return fail(GCA_ERR_STATE, "the rasteriser supports at most 126 intruders");
+  const int W = (int)e->cfg.window_width, H = (int)e->cfg.window_height;
+  if (W != e->cfg.window_width || H != e->cfg.window_height || W % 16 || H % 4 || W <= 0 || H <= 0)
+    return fail(GCA_ERR_STATE, "the rasteriser needs an integer window with width % 16 == 0 and height % 4 == 0");
+  if (n_planes < 1 || slot < 0 || slot >= n_planes) return fail(GCA_ERR_INVALID, "bad plane selection");
+  if (plane_stride % 4 || env_stride % 4) return fail(GCA_ERR_INVALID, "strides must be multiples of 4 bytes");
+  GCA_CUDA(cudaSetDevice(e->device));
+  GCA_CUDA(launch_raster(e->s, e->mode == GCA_MODE_FAITHFUL, W, H, sprites, frames, (long long)env_stride,
+                         (long long)plane_stride, n_planes, slot, clear_mask, (cudaStream_t)stream));
+  return GCA_OK;
+}
+
 int gca_mcts_move(const gca_mcts_config* cfg, int n_intruders, double* states, const int32_t* actions, uint8_t* flags,
                   int64_t m, const gca_tape* tape, uint64_t seed, uint32_t id0, int first_frame, int device,
                   void* stream) {

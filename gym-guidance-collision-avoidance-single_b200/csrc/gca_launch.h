@@ -16,4 +16,7 @@ cudaError_t launch_mcts_playouts(const gca_mcts_config* cfg, int n, const double
 cudaError_t launch_mcts_move(const gca_mcts_config* cfg, int n, double* states, const int32_t* actions, uint8_t* flags,
                              long long m, const double* tape, long long tape_stride, long long* cursor, uint64_t seed,
                              uint32_t id0, int first_frame, cudaStream_t st);
+cudaError_t launch_raster(const DevState& s, bool faithful, int W, int H, const uint8_t* sprites, uint8_t* frames,
+                          long long env_stride, long long plane_stride, int n_planes, int slot,
+                          const uint8_t* clear_mask, cudaStream_t st);
 }  // namespace gca

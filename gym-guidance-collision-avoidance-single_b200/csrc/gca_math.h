@@ -39,6 +39,7 @@
 #define GCA_FDIVF(a, b) __fdiv_rn((a), (b))
 #define GCA_FSQRTF(a) __fsqrt_rn((a))
 #define GCA_FMAF(a, b, c) __fmaf_rn((a), (b), (c))
+#define GCA_RINTF(a) rintf((a))
 #else
 // host: translation units that include this header are built with -ffp-contract=off
 #define GCA_MUL(a, b) ((double)(a) * (double)(b))
@@ -54,6 +55,7 @@
 #define GCA_FDIVF(a, b) ((float)((float)(a) / (float)(b)))
 #define GCA_FSQRTF(a) __builtin_sqrtf((a))
 #define GCA_FMAF(a, b, c) __builtin_fmaf((a), (b), (c))
+#define GCA_RINTF(a) __builtin_rintf((a))
 #endif
 
 GCA_HD uint64_t gca_f64_bits(double x) {

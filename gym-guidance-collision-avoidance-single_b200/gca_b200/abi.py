@@ -103,6 +103,7 @@ def load():
         "gca_set_state": ([vp, P(GcaHostState)], C.c_int),
         "gca_observe": ([vp, P(GcaOut), vp], C.c_int),
         "gca_compute_reward": ([vp, vp, i64, C.c_double, i32, i32, vp, i32, vp], C.c_int),
+        "gca_raster": ([vp, vp, vp, i64, i64, i32, i32, vp, vp], C.c_int),
         "gca_mcts_move": ([P(GcaMctsConfig), i32, vp, vp, vp, i64, P(GcaTape), u64, u32, i32, i32, vp], C.c_int),
         "gca_mcts_playouts": ([P(GcaMctsConfig), i32, vp, i64, i32, i32, vp, u64, u32, vp, vp, vp, i32, vp], C.c_int),
     }

@@ -226,6 +226,23 @@ int gca_mcts_playouts(const gca_mcts_config* cfg, int n_intruders, const double*
                       int playouts, int depth, const int8_t* first_action, uint64_t seed, uint32_t root_id0,
                       double* rewards, int8_t* first_out, uint8_t* flags, int device, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Image observation of SingleAircraftStackEnv (PKG/SingleAircraftStackEnv.py:104-114, 179-214):
+ * render() -> 800x800 RGB frame (white clear; ownship, goal, intruders drawn in that order as 32x32
+ * textured quads rotated by heading - pi/2, src-alpha blending into an 8-bit framebuffer), then
+ * cv2.cvtColor(RGB2GRAY) and cv2.resize(INTER_AREA) by 4 -> uint8 [H/4][W/4], row 0 = top.
+ * The full-resolution frame is never materialised: each output pixel evaluates its 16 samples
+ * against the few sprites whose bounding box touches its cell.  DESIGN.md section 4.5 is the spec
+ * (the GL half of the reference cannot run without a display, so the restatement is the spec).
+ *
+ * sprites: device uint8 [3][32][32][4] = (ownship, goal, intruder) x rows top->bottom x RGBA.
+ * frames : device uint8; env b writes (H/4)*(W/4) bytes at frames + b*env_stride + slot*plane_stride.
+ * clear_mask (nullable, device uint8 [B]): for a non-zero entry the other n_planes-1 planes of that env
+ * are zero-filled first - VecFrameStack's reset of a finished env (vec_frame_stack.py:19-23, Q21). */
+#define GCA_RASTER_MAX_INTRUDERS 126
+int gca_raster(gca_env* env, const uint8_t* sprites, uint8_t* frames, int64_t env_stride, int64_t plane_stride,
+               int n_planes, int slot, const uint8_t* clear_mask, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,6 +80,10 @@ int gca_oracle_mcts_search(const gca_mcts_config* c, int n, const double* root, 
                            const double* tape, int64_t* cursor, int trig, int* best_action, double* child_n,
                            double* child_q, int* child_action);
 
+/* ---- StackEnv image observation (oracle/gca_oracle_raster.c); trig of `b` selects libm / shared sincos ---- */
+int gca_oracle_raster(const gca_config* cfg, const gca_oracle_batch* b, const unsigned char* sprites,
+                      unsigned char* frames, unsigned char* rgb);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,6 +74,7 @@ def lib():
     L.gca_oracle_mcts_rollout.argtypes = [P(MC), i32, vp, i32, i32, i32, vp, vp, u64, u32, u32, i32, vp, vp, vp]
     L.gca_oracle_mcts_playouts.argtypes = [P(MC), i32, vp, i64, i32, i32, vp, u64, u32, i32, vp, vp, vp]
     L.gca_oracle_mcts_search.argtypes = [P(MC), i32, vp, i32, i32, vp, vp, i32, vp, vp, vp, vp]
+    L.gca_oracle_raster.argtypes = [P(abi.GcaConfig), P(OracleBatch), vp, vp, vp]
     _lib = L
     return L
 
@@ -161,6 +162,17 @@ class OracleEnv(object):
         rc = self.L.gca_oracle_step(C.byref(self.cfg), C.byref(b), _p(a))
         assert rc == 0, rc
         return self.obs, self.reward, self.done, self.info
+
+    def raster(self, sprites, want_rgb=False):
+        """Image observation of the current state: uint8 [B, H/4, W/4] (and the full RGB frames)."""
+        W, H = int(self.cfg.window_width), int(self.cfg.window_height)
+        sp = np.ascontiguousarray(sprites, np.uint8)
+        frames = np.zeros((self.B, H // 4, W // 4), np.uint8)
+        rgb = np.zeros((self.B, H, W, 3), np.uint8) if want_rgb else None
+        b = self._batch()
+        rc = self.L.gca_oracle_raster(C.byref(self.cfg), C.byref(b), _p(sp), _p(frames), _p(rgb))
+        assert rc == 0, rc
+        return (frames, rgb) if want_rgb else frames
 
     def observe(self):
         b = self._batch()
