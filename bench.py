@@ -305,6 +305,7 @@ def main_gpu(args):
             line["cpu_baseline"] = cb
         if not kernel_only:
             line["mcts"] = bench_mcts(local, with_cpu=(world == 1))
+            line["stack"] = bench_stack(local)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -347,6 +348,37 @@ def bench_mcts(device, with_cpu):
         dt = time.perf_counter() - t0
         out["cpu_baseline"] = {"value": 8 * 50 / dt, "unit": "rollouts/s", "cores": 1, "kind": "port",
                                "sample": "8 roots x 50 playouts, C oracle port (oracle/gca_oracle_mcts.c), 1 thread"}
+    return out
+
+
+def bench_stack(device):
+    """BASELINE.json config #5: SingleAircraftStackEnv, 4-frame stacked image observation (device rasteriser)."""
+    import torch
+    from gca_b200.stack import ImageBatch
+    from gym_guidance_collision_avoidance_single.envs.config import Config
+    B, N, k = ENVS_PER_GPU, N_INTRUDERS, 4
+    env = ImageBatch(B, Config, n_intruders=N, frame_stack=k, device=device, seed=3)
+    env.reset()
+    acts = [torch.randint(0, 9, (B,), device="cuda", dtype=torch.int32) for _ in range(4)]
+    for i in range(3):
+        env.step(acts[i % 4])
+    torch.cuda.synchronize()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    start.record()
+    for i in range(reps):
+        env.step(acts[i % 4])
+    stop.record()
+    torch.cuda.synchronize()
+    ms = start.elapsed_time(stop) / reps
+    peak, _ = measured_peaks()
+    frame_bytes = env.H * env.W
+    out = {"metric": METRIC, "value": B / (ms * 1e-3), "unit": UNIT, "envs": B, "intruders": N, "frame_stack": k,
+           "ms_per_step": ms, "kernels_per_step": 2,
+           "frame_bytes_per_env_step": frame_bytes,
+           "hbm_frac_frames_only": (B * frame_bytes / (ms * 1e-3) / 1e9) / peak,
+           "note": "step kernel + rasteriser; bound by the rasteriser's per-sample blending (FP32), not by HBM yet"}
+    env.close()
     return out
 
 

@@ -5,11 +5,12 @@
 // resolution frame never exists: >= 95 % of the 200x200 output is background, so
 //   1. the env's sprite poses (ownship, goal, intruders, in draw order) go to shared memory,
 //   2. every sprite ORs its bit into the <= 3x3 cells (8x8 output pixels each) its reach touches,
-//   3. each thread produces 4 consecutive output pixels: an empty cell mask is a plain 0xFFFFFFFF
-//      store; otherwise the 16 samples of each pixel are blended against the cell's sprites in bit
-//      (= draw) order with the shared per-sample arithmetic of gca_raster_spec.h, then
-//      gray -> 4x4 area mean (round half to even).
-// Output bytes: 40 000 per env-step, written once, as 4-byte stores (coalesced per row).
+//   3. the plane is filled with white (16-byte stores),
+//   4. one warp per sprite walks the <= 13x13 output pixels of that sprite's bounding box; the 16
+//      samples of a pixel are blended against the cell's sprites in bit (= draw) order with the
+//      shared per-sample arithmetic of gca_raster_spec.h (fully transparent texels exit early),
+//      then gray -> 4x4 area mean (round half to even); only touched pixels are rewritten.
+// Output bytes: 40 000 per env-step.
 #include "gca_launch.h"
 #include "gca_raster_spec.h"
 
@@ -106,40 +107,69 @@ __global__ void __launch_bounds__(kRasterThreads) raster_kernel(const RasterArgs
   }
   __syncthreads();
 
-  // ---- 3. output pixels, 4 per thread
+  // ---- 3. background: the whole plane is white; ---- 4. sprite-centric pass over covered pixels only
   uint8_t* out = env_base + (long long)a.slot * a.plane_stride;
-  const int quads_per_row = a.ow / 4;
-  const int n_quads = quads_per_row * a.oh;
-  for (int qd = tid; qd < n_quads; qd += kRasterThreads) {
-    const int oy = qd / quads_per_row, ox0 = (qd - oy * quads_per_row) * 4;
-    const uint4 m = cell_mask[(oy >> 3) * a.cells_x + (ox0 >> 3)];
-    uint32_t packed = 0xffffffffu;
-    if (m.x | m.y | m.z | m.w) {
+  {
+    uint4* o4 = reinterpret_cast<uint4*>(out);
+    const int n16 = a.ow * a.oh / 16;
+    const uint4 white = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    for (int i = tid; i < n16; i += kRasterThreads) o4[i] = white;
+  }
+  __syncthreads();
+  // One warp per sprite: lanes walk the output pixels of the sprite's bounding box.  A pixel's value
+  // depends on ALL sprites of its cell (blended in draw order), so pixels shared by two boxes are
+  // computed twice and written twice with the same byte - benign.
+  const int lane = tid & 31, warp = tid >> 5;
+  for (int k0 = warp; k0 < n_sprites; k0 += kRasterThreads / 32) {
+    const gca_sprite_pose me = pose[k0];
+    const float ytop = (float)a.H - me.cy;
+    const int bx0 = max((int)floorf((me.cx - GCA_SPRITE_REACH) * 0.25f), 0);
+    const int bx1 = min((int)floorf((me.cx + GCA_SPRITE_REACH) * 0.25f), a.ow - 1);
+    const int by0 = max((int)floorf((ytop - GCA_SPRITE_REACH) * 0.25f), 0);
+    const int by1 = min((int)floorf((ytop + GCA_SPRITE_REACH) * 0.25f), a.oh - 1);
+    const int nx = bx1 - bx0 + 1, ny = by1 - by0 + 1;
+    if (nx <= 0 || ny <= 0) continue;
+    for (int p = lane; p < nx * ny; p += 32) {
+      const int oy = by0 + p / nx, ox = bx0 + p % nx;
+      const uint4 m = cell_mask[(oy >> 3) * a.cells_x + (ox >> 3)];
       const uint32_t words[4] = {m.x, m.y, m.z, m.w};
-      packed = 0u;
-      for (int px = 0; px < 4; ++px) {
-        int sum = 0;
-        for (int sy = 0; sy < 4; ++sy) {
-          const float wy = (float)a.H - ((float)(4 * oy + sy) + 0.5f);
-          for (int sx = 0; sx < 4; ++sx) {
-            const float wx = (float)(4 * (ox0 + px) + sx) + 0.5f;
-            int r = 255, g = 255, b = 255;                              // white clear
-            for (int w = 0; w < 4; ++w) {
-              uint32_t bits = words[w];
-              while (bits) {
-                const int k = w * 32 + __ffs(bits) - 1;
-                bits &= bits - 1;
-                const gca_sprite_pose sp = pose[k];
-                gca_raster_sample(sp, tex + sp.tex * (32 * 32 * 4), wx, wy, &r, &g, &b);
-              }
-            }
-            sum += gca_gray_u8(r, g, b);
-          }
+      // sprites of the cell that can reach this pixel at all (centre distance test, conservative)
+      const float pcx = (float)(4 * ox) + 2.0f, pcy = (float)a.H - ((float)(4 * oy) + 2.0f);
+      uint32_t live[4];
+      bool any = false;
+      for (int w = 0; w < 4; ++w) {
+        uint32_t bits = words[w], keep = 0u;
+        while (bits) {
+          const int j = __ffs(bits) - 1;
+          bits &= bits - 1;
+          const gca_sprite_pose sp = pose[w * 32 + j];
+          if (fabsf(pcx - sp.cx) <= GCA_SPRITE_REACH + 2.0f && fabsf(pcy - sp.cy) <= GCA_SPRITE_REACH + 2.0f) keep |= 1u << j;
         }
-        packed |= (uint32_t)gca_area16_u8(sum) << (8 * px);
+        live[w] = keep;
+        any |= keep != 0u;
       }
+      if (!any) continue;
+      int sum = 0;
+      bool touched = false;
+      for (int sy = 0; sy < 4; ++sy) {
+        const float wy = (float)a.H - ((float)(4 * oy + sy) + 0.5f);
+        for (int sx = 0; sx < 4; ++sx) {
+          const float wx = (float)(4 * ox + sx) + 0.5f;
+          int r = 255, g = 255, b = 255;                                  // white clear
+          for (int w = 0; w < 4; ++w) {
+            uint32_t bits = live[w];
+            while (bits) {
+              const int k = w * 32 + __ffs(bits) - 1;
+              bits &= bits - 1;
+              const gca_sprite_pose sp = pose[k];
+              touched |= gca_raster_sample(sp, tex + sp.tex * (32 * 32 * 4), wx, wy, &r, &g, &b) != 0;
+            }
+          }
+          sum += gca_gray_u8(r, g, b);
+        }
+      }
+      if (touched) out[oy * a.ow + ox] = (uint8_t)gca_area16_u8(sum);
     }
-    reinterpret_cast<uint32_t*>(out)[qd] = packed;
   }
 }
 

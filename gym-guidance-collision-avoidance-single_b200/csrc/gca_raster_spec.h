@@ -40,21 +40,27 @@ GCA_HD int gca_raster_sample(const gca_sprite_pose sp, const unsigned char* tex,
   const unsigned char* t01 = tex + ((31 - v1) * GCA_SPRITE + u0) * 4;
   const unsigned char* t11 = tex + ((31 - v1) * GCA_SPRITE + u1) * 4;
   const float gu = GCA_FSUBF(1.0f, fu), gv = GCA_FSUBF(1.0f, fv);
-  float ch[4];
-  for (int k = 0; k < 4; ++k) {
-    const float lo = GCA_FADDF(GCA_FMULF((float)t00[k], gu), GCA_FMULF((float)t10[k], fu));
-    const float hi = GCA_FADDF(GCA_FMULF((float)t01[k], gu), GCA_FMULF((float)t11[k], fu));
-    ch[k] = GCA_FADDF(GCA_FMULF(lo, gv), GCA_FMULF(hi, fv));
-  }
+#define GCA_BILERP(k)                                                                                    \
+  GCA_FADDF(GCA_FMULF(GCA_FADDF(GCA_FMULF((float)t00[k], gu), GCA_FMULF((float)t10[k], fu)), gv),        \
+            GCA_FMULF(GCA_FADDF(GCA_FMULF((float)t01[k], gu), GCA_FMULF((float)t11[k], fu)), fv))
   // GL_SRC_ALPHA, GL_ONE_MINUS_SRC_ALPHA into an 8-bit framebuffer (quantised after every draw)
-  const float alpha = GCA_FMULF(ch[3], 0.003921568859368563f);              /* RN(1/255) */
+  const float a255 = GCA_BILERP(3);
+  if (a255 == 0.0f) return 1;                         /* fully transparent: the blend is the identity */
+  const float alpha = GCA_FMULF(a255, 0.003921568859368563f);              /* RN(1/255) */
   const float beta = GCA_FSUBF(1.0f, alpha);
-  int* dst[3] = {r, g, b};
-  for (int k = 0; k < 3; ++k) {
-    const float v = GCA_FADDF(GCA_FMULF(ch[k], alpha), GCA_FMULF((float)*dst[k], beta));
-    int q = (int)GCA_RINTF(v);
-    *dst[k] = gca_clampi(q, 0, 255);
+  {
+    const float v = GCA_FADDF(GCA_FMULF(GCA_BILERP(0), alpha), GCA_FMULF((float)*r, beta));
+    *r = gca_clampi((int)GCA_RINTF(v), 0, 255);
   }
+  {
+    const float v = GCA_FADDF(GCA_FMULF(GCA_BILERP(1), alpha), GCA_FMULF((float)*g, beta));
+    *g = gca_clampi((int)GCA_RINTF(v), 0, 255);
+  }
+  {
+    const float v = GCA_FADDF(GCA_FMULF(GCA_BILERP(2), alpha), GCA_FMULF((float)*b, beta));
+    *b = gca_clampi((int)GCA_RINTF(v), 0, 255);
+  }
+#undef GCA_BILERP
   return 1;
 }
 
