@@ -31,7 +31,23 @@
 
 namespace gca {
 
-constexpr int kWarpsPerBlock = 4;
+// Optional per-warp phase timestamps (build with -DGCA_PHASE_TIMING; tools/phase_timing.py reads them).
+#ifdef GCA_PHASE_TIMING
+__device__ unsigned long long g_phase_stamps[8192 * 8];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define GCA_STAMP(slot)                                                                       \
+  do {                                                                                        \
+    if (lane == 0 && tile < 8192) g_phase_stamps[tile * 8 + (slot)] = gtime();                \
+  } while (0)
+#else
+#define GCA_STAMP(slot) do { } while (0)
+#endif
+
+constexpr int kWarpsPerBlock = 1;   // one warp per block: blocks spread 13-14 per SM instead of 12 or 16 warps
 constexpr int kMaxStages = 8;
 
 // one warp-round (32 intruders) of an env row held in shared or global memory
@@ -157,7 +173,7 @@ __host__ __device__ inline size_t warp_smem_bytes(const DevState& s, int stages,
 // WC > 0: the number of warp-rounds per env is the compile-time constant WC (rounds are fully
 // unrolled and an env without any conflict / out-of-map event takes a short path); WC == 0: generic.
 #ifndef GCA_MINB
-#define GCA_MINB 4
+#define GCA_MINB 16
 #endif
 template <bool FAITH, bool TAPE, int TILE, int WC>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, GCA_MINB) step_kernel(const StepArgs a, const int n_tiles,
@@ -199,6 +215,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, GCA_MINB) step_kernel(con
     const bool has_env = lane < n_tile;
     const size_t me = (size_t)(env0 + (has_env ? lane : 0));
 
+    GCA_STAMP(0);
+#ifdef GCA_PHASE_TIMING
+    if (lane == 0 && tile < 8192) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      g_phase_stamps[tile * 8 + 7] = smid;
+    }
+#endif
     // ---- start streaming the first rows of the tile before any arithmetic
     if (use_tma && lane == 0) {
       const int pre = n_tile < stages ? n_tile : stages;
@@ -268,6 +292,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, GCA_MINB) step_kernel(con
       s.own_vel_f32[me] = 0;
     }
 
+    GCA_STAMP(1);
     // -------------------------------------------------------------- phase B: lanes = intruders
     bool my_nmac = false, my_conf = false, my_oob = false;
     int my_newconf = 0;
@@ -345,6 +370,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, GCA_MINB) step_kernel(con
     }
     __syncwarp();
 
+    GCA_STAMP(2);
     // -------------------------------------------------------------- phase C: respawn, reward, lane = env
     bool done = false;
     if (has_env) {
@@ -399,6 +425,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, GCA_MINB) step_kernel(con
       write_obs_own<FAITH>(a, me, pos.x, pos.y, vel.x, vel.y, false, hs.x, hs.y, goal.x, goal.y);   // :115-124
     }
 
+    GCA_STAMP(3);
     // -------------------------------------------------------------- phase D: VecEnv auto-reset
     // baselines dummy_vec_env.py:52-55: the observation handed back for a finished env is reset()'s
     uint32_t dmask = a.auto_reset ? __ballot_sync(FULL, has_env && done) : 0u;
@@ -433,6 +460,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, GCA_MINB) step_kernel(con
       if constexpr (TAPE) a.cursor[me] = d.cur;
     }
     __syncwarp();
+    GCA_STAMP(4);
   }
 
   // ---- last warp out re-arms the scheduler for the next launch
@@ -611,6 +639,12 @@ cudaError_t launch_step(bool faith, bool tape, int tile, int stages, const StepA
   if (tile == 16) return launch_step_tile<16>(faith, tape, a, stages, st);
   return launch_step_tile<32>(faith, tape, a, stages, st);
 }
+
+#ifdef GCA_PHASE_TIMING
+extern "C" int gca_debug_phase_stamps(unsigned long long* host, int count) {
+  return (int)cudaMemcpyFromSymbol(host, g_phase_stamps, sizeof(unsigned long long) * (size_t)count);
+}
+#endif
 
 cudaError_t launch_reset(bool faith, bool tape, const StepArgs& a, cudaStream_t st) {
   constexpr int TILE = 32;
