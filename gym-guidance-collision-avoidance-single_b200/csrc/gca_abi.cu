@@ -35,7 +35,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 }  // namespace
 
 struct gca_env {
-  int device = 0, mode = 0, draws = 0, tile = 32, stages = 2;
+  int device = 0, mode = 0, draws = 0, group = 4, stages = 4;
   gca_config cfg{};
   Derived k{};
   uint64_t seed = 0;
@@ -131,6 +131,8 @@ StepArgs make_args(const gca_env* e, const void* actions, const gca_tape* tape, 
   a.env_id0 = e->env_id0;
   a.D = e->D;
   a.auto_reset = auto_reset;
+  static const int dbg = std::getenv("GCA_DEBUG_SKIP") ? std::atoi(std::getenv("GCA_DEBUG_SKIP")) : 0;
+  a.debug_skip = dbg;
   if (out) {
     a.obs = out->obs; a.achieved = out->achieved; a.desired = out->desired;
     a.reward = out->reward; a.done = out->done; a.info = out->info;
@@ -152,6 +154,30 @@ int check_tape(const gca_env* e, const gca_tape* tape) {
     return fail(GCA_ERR_INVALID, "handle was created with GCA_DRAWS_TAPE: a tape is required");
   return GCA_OK;
 }
+
+// host copies of the tile-planar intruder planes (gca_get_state / gca_set_state)
+struct HostPlanes {
+  std::vector<uint8_t> pos, vel;
+  std::vector<uint32_t> cf, df;
+  int download(const DevState& s, bool faith) {
+    pos.resize(pos_plane_bytes(s, faith));
+    vel.resize(vel_plane_bytes(s));
+    cf.resize(flag_plane_words(s));
+    df.resize(faith ? flag_plane_words(s) : 1);
+    GCA_CUDA(cudaMemcpy(pos.data(), s.ipos, pos.size(), cudaMemcpyDeviceToHost));
+    GCA_CUDA(cudaMemcpy(vel.data(), s.ivel, vel.size(), cudaMemcpyDeviceToHost));
+    GCA_CUDA(cudaMemcpy(cf.data(), s.cflag, cf.size() * 4, cudaMemcpyDeviceToHost));
+    if (faith) GCA_CUDA(cudaMemcpy(df.data(), s.dflag, df.size() * 4, cudaMemcpyDeviceToHost));
+    return GCA_OK;
+  }
+  int upload(const DevState& s, bool faith) {
+    GCA_CUDA(cudaMemcpy(s.ipos, pos.data(), pos.size(), cudaMemcpyHostToDevice));
+    GCA_CUDA(cudaMemcpy(s.ivel, vel.data(), vel.size(), cudaMemcpyHostToDevice));
+    GCA_CUDA(cudaMemcpy(s.cflag, cf.data(), cf.size() * 4, cudaMemcpyHostToDevice));
+    if (faith) GCA_CUDA(cudaMemcpy(s.dflag, df.data(), df.size() * 4, cudaMemcpyHostToDevice));
+    return GCA_OK;
+  }
+};
 }  // namespace
 
 extern "C" {
@@ -190,9 +216,9 @@ int gca_create(const gca_config* cfg, int n_envs, int n_intruders, int mode, int
   if (!e) return fail(GCA_ERR_ALLOC, "out of host memory");
   e->device = device; e->mode = mode; e->draws = draws; e->cfg = *cfg; e->k = derive(*cfg); e->seed = seed; e->env_id0 = env_id0;
   e->D = gca_obs_dim(cfg, n_intruders);
-  if (const char* t = std::getenv("GCA_TILE")) {
+  if (const char* t = std::getenv("GCA_GROUP")) {      // units (intruder pairs) per pipeline stage
     const int v = std::atoi(t);
-    if (v == 8 || v == 16 || v == 32) e->tile = v;
+    if (v == 2 || v == 4) e->group = v;
   }
   if (const char* t = std::getenv("GCA_STAGES")) {
     const int v = std::atoi(t);
@@ -200,7 +226,7 @@ int gca_create(const gca_config* cfg, int n_envs, int n_intruders, int mode, int
   }
   DevState& s = e->s;
   s.B = n_envs; s.N = n_intruders;
-  row_layout(s, mode == GCA_MODE_FAITHFUL);
+  plane_layout(s);
   const size_t B = (size_t)n_envs;
   int rc = GCA_OK;
   if (!rc) rc = dev_alloc(e, &s.own_pos, B);
@@ -209,7 +235,10 @@ int gca_create(const gca_config* cfg, int n_envs, int n_intruders, int mode, int
   if (!rc) rc = dev_alloc(e, &s.own_vel_f32, B);
   if (!rc) rc = dev_alloc(e, &s.goal, B);
   if (!rc) rc = dev_alloc(e, &s.counters, B);
-  if (!rc) rc = dev_alloc(e, &s.irow, B * (size_t)s.row_bytes);
+  if (!rc) rc = dev_alloc(e, &s.ipos, pos_plane_bytes(s, mode == GCA_MODE_FAITHFUL));
+  if (!rc) rc = dev_alloc(e, &s.ivel, vel_plane_bytes(s));
+  if (!rc) rc = dev_alloc(e, &s.cflag, flag_plane_words(s));
+  if (!rc) rc = dev_alloc(e, &s.dflag, mode == GCA_MODE_FAITHFUL ? flag_plane_words(s) : 1);
   if (!rc) rc = dev_alloc(e, &s.sched, 2);
   if (rc) {
     gca_destroy(e);
@@ -261,7 +290,7 @@ int gca_step(gca_env* e, const void* actions, const gca_tape* tape, int auto_res
   if (int rc = check_tape(e, tape)) return rc;
   GCA_CUDA(cudaSetDevice(e->device));
   const StepArgs a = make_args(e, actions, tape, out, auto_reset);
-  GCA_CUDA(launch_step(e->mode == GCA_MODE_FAITHFUL, e->draws == GCA_DRAWS_TAPE, e->tile, e->stages, a,
+  GCA_CUDA(launch_step(e->mode == GCA_MODE_FAITHFUL, e->draws == GCA_DRAWS_TAPE, e->group, e->stages, a,
                        (cudaStream_t)stream));
   return GCA_OK;
 }
@@ -349,28 +378,27 @@ int gca_get_state(gca_env* e, const gca_host_state* h) {
   }
   if (N == 0 || !(h->ipos || h->ivel || h->iflag || h->ipos_is_f64)) return GCA_OK;
   const bool faith = e->mode == GCA_MODE_FAITHFUL;
-  const size_t RB = (size_t)s.row_bytes;
-  std::vector<uint8_t> rows(B * RB);
-  GCA_CUDA(cudaMemcpy(rows.data(), s.irow, rows.size(), cudaMemcpyDeviceToHost));
+  HostPlanes hp;
+  if (int rc = hp.download(s, faith)) return rc;
   for (size_t b = 0; b < B; ++b) {
-    const uint8_t* row = rows.data() + b * RB;
-    const float2* vel = reinterpret_cast<const float2*>(row + s.off_vel);
-    const uint32_t* fw = reinterpret_cast<const uint32_t*>(row + s.off_flag);
-    const uint32_t* dw = reinterpret_cast<const uint32_t*>(row + s.off_f64);
     for (size_t i = 0; i < N; ++i) {
       const size_t k = b * N + i;
       if (h->ipos) {
         if (faith) {
-          const double2 p = reinterpret_cast<const double2*>(row)[i];
+          const double2 p = *reinterpret_cast<const double2*>(hp.pos.data() + ipos_offset(s, true, b, (int)i));
           h->ipos[2 * k] = p.x; h->ipos[2 * k + 1] = p.y;
         } else {
-          const float2 p = reinterpret_cast<const float2*>(row)[i];
+          const float2 p = *reinterpret_cast<const float2*>(hp.pos.data() + ipos_offset(s, false, b, (int)i));
           h->ipos[2 * k] = (double)p.x; h->ipos[2 * k + 1] = (double)p.y;
         }
       }
-      if (h->ivel) { h->ivel[2 * k] = vel[i].x; h->ivel[2 * k + 1] = vel[i].y; }
-      if (h->iflag) h->iflag[k] = (fw[i / 32] >> (i % 32)) & 1u;
-      if (h->ipos_is_f64) h->ipos_is_f64[k] = faith ? ((dw[i / 32] >> (i % 32)) & 1u) : 0;
+      if (h->ivel) {
+        const float2 v = *reinterpret_cast<const float2*>(hp.vel.data() + ivel_offset(s, b, (int)i));
+        h->ivel[2 * k] = v.x; h->ivel[2 * k + 1] = v.y;
+      }
+      const size_t fi = flag_index(s, b, (int)(i / 32));
+      if (h->iflag) h->iflag[k] = (hp.cf[fi] >> (i % 32)) & 1u;
+      if (h->ipos_is_f64) h->ipos_is_f64[k] = faith ? ((hp.df[fi] >> (i % 32)) & 1u) : 0;
     }
   }
   return GCA_OK;
@@ -399,29 +427,34 @@ int gca_set_state(gca_env* e, const gca_host_state* h) {
   }
   if (N == 0 || !(h->ipos || h->ivel || h->iflag || h->ipos_is_f64)) return GCA_OK;
   const bool faith = e->mode == GCA_MODE_FAITHFUL;
-  const size_t RB = (size_t)s.row_bytes;
-  std::vector<uint8_t> rows(B * RB);
-  GCA_CUDA(cudaMemcpy(rows.data(), s.irow, rows.size(), cudaMemcpyDeviceToHost));   // keep what the view omits
+  HostPlanes hp;
+  if (int rc = hp.download(s, faith)) return rc;                      // keep what the view omits
   for (size_t b = 0; b < B; ++b) {
-    uint8_t* row = rows.data() + b * RB;
-    float2* vel = reinterpret_cast<float2*>(row + s.off_vel);
-    uint32_t* fw = reinterpret_cast<uint32_t*>(row + s.off_flag);
-    uint32_t* dw = reinterpret_cast<uint32_t*>(row + s.off_f64);
-    if (h->iflag) std::memset(fw, 0, (size_t)s.Wp * 4);
-    if (h->ipos_is_f64 && faith) std::memset(dw, 0, (size_t)s.Wp * 4);
+    for (int w = 0; w < s.W; ++w) {
+      if (h->iflag) hp.cf[flag_index(s, b, w)] = 0u;
+      if (h->ipos_is_f64 && faith) hp.df[flag_index(s, b, w)] = 0u;
+    }
     for (size_t i = 0; i < N; ++i) {
       const size_t k = b * N + i;
       if (h->ipos) {
-        if (faith) reinterpret_cast<double2*>(row)[i] = make_double2(h->ipos[2 * k], h->ipos[2 * k + 1]);
-        else reinterpret_cast<float2*>(row)[i] = make_float2((float)h->ipos[2 * k], (float)h->ipos[2 * k + 1]);
+        if (faith) {
+          *reinterpret_cast<double2*>(hp.pos.data() + ipos_offset(s, true, b, (int)i)) =
+              make_double2(h->ipos[2 * k], h->ipos[2 * k + 1]);
+        } else {
+          // FAST positions are stored as non-negative-zero f32 (the map test of the step kernel compares bit
+          // patterns); -0.0 and +0.0 are the same position for every rule of the reference.
+          *reinterpret_cast<float2*>(hp.pos.data() + ipos_offset(s, false, b, (int)i)) =
+              make_float2((float)h->ipos[2 * k] + 0.0f, (float)h->ipos[2 * k + 1] + 0.0f);
+        }
       }
-      if (h->ivel) vel[i] = make_float2(h->ivel[2 * k], h->ivel[2 * k + 1]);
-      if (h->iflag && h->iflag[k]) fw[i / 32] |= 1u << (i % 32);
-      if (h->ipos_is_f64 && faith && h->ipos_is_f64[k]) dw[i / 32] |= 1u << (i % 32);
+      if (h->ivel)
+        *reinterpret_cast<float2*>(hp.vel.data() + ivel_offset(s, b, (int)i)) = make_float2(h->ivel[2 * k], h->ivel[2 * k + 1]);
+      const size_t fi = flag_index(s, b, (int)(i / 32));
+      if (h->iflag && h->iflag[k]) hp.cf[fi] |= 1u << (i % 32);
+      if (h->ipos_is_f64 && faith && h->ipos_is_f64[k]) hp.df[fi] |= 1u << (i % 32);
     }
   }
-  GCA_CUDA(cudaMemcpy(s.irow, rows.data(), rows.size(), cudaMemcpyHostToDevice));
-  return GCA_OK;
+  return hp.upload(s, faith);
 }
 
 int gca_compute_reward(const void* ag, const void* g, int64_t m, double radius, int kind, int is_f64, float* out,

@@ -15,12 +15,20 @@
 namespace gca {
 
 // ------------------------------------------------------------------------------ device state
-// Per-env scalars are SoA by field (lane = env accesses are coalesced).  Everything that is
-// indexed by intruder lives in ONE contiguous, 16-byte aligned row per env:
-//     [ pos[Np] (float2 FAST / double2 FAITHFUL) | vel[Np] float2 | conflict words[Wp] | f64 words[Wp] (FAITHFUL) ]
-// so that a single 1-D bulk (TMA) copy brings an env's whole intruder set into shared memory.
-// bit i%32 of conflict word i/32 = Aircraft.conflict of intruder i; the f64 words flag
-// positions whose dtype became f64 after a retried spawn (Q3).
+// Everything is laid out for "lane = env": a warp owns a tile of 32 consecutive envs and lane e
+// of the warp owns env 32*t + e from the first instruction of a step to the last.
+//   per-env scalars   SoA by field, [B]: one coalesced access per warp.
+//   intruder planes   tile-planar: for tile t and 16-byte unit u the 32 lanes' units are adjacent,
+//                         plane[(t * units + u) * 32 + e]            (512 bytes per (t, u))
+//       pos  FAST     unit u = float4 (x, y) of intruders 2u, 2u+1           units = U = ceil(N/2)
+//            FAITHFUL unit i = double2 (x, y) of intruder i (an f32 value unless flagged)  units = 2U
+//       vel           unit u = float4 (vx, vy) of intruders 2u, 2u+1         units = U
+//       conflict / f64 flag words: word w of env e at  words[(t * Wd + w) * 32 + e]
+//   so that (i) a warp-wide 16-byte access to unit u is one contiguous 512-byte line, (ii) any run of
+//   units of a tile is ONE contiguous block that a single 1-D bulk (TMA) copy brings into shared
+//   memory, where lane e's 16-byte reads are bank-conflict free.
+// bit i%32 of conflict word i/32 = Aircraft.conflict of intruder i; the f64 words flag positions
+// whose dtype became f64 after a retried spawn (Q3).
 struct DevState {
   float2* own_pos;        // [B]
   double2* own_hs;        // [B]   (heading, speed)
@@ -28,10 +36,12 @@ struct DevState {
   uint8_t* own_vel_f32;   // [B]
   double2* goal;          // [B]
   int4* counters;         // [B]   (no_conflict, ep_steps, tick, episodes)
-  uint8_t* irow;          // [B][row_bytes]
+  uint8_t* ipos;          // [T][U or 2U][32] 16-byte units
+  uint8_t* ivel;          // [T][U][32] float4
+  uint32_t* cflag;        // [T][Wd][32]
+  uint32_t* dflag;        // [T][Wd][32]  (FAITHFUL)
   unsigned int* sched;    // [2]   dynamic tile scheduler: next tile, finished warps
-  int B, N, Np, W, Wp;
-  int row_bytes, off_vel, off_flag, off_f64;
+  int B, N, T, U, W, Wd;
 };
 
 template <bool FAITH>
@@ -39,14 +49,31 @@ struct pos2 { using type = float2; };
 template <>
 struct pos2<true> { using type = double2; };
 
-__host__ __device__ inline void row_layout(DevState& s, bool faithful) {
-  s.Np = (s.N + 1) & ~1;
+__host__ __device__ inline void plane_layout(DevState& s) {
+  s.T = (s.B + 31) / 32;
+  s.U = (s.N + 1) / 2;
   s.W = (s.N + 31) / 32;
-  s.Wp = ((s.W > 0 ? s.W : 1) + 3) & ~3;
-  s.off_vel = s.Np * (faithful ? 16 : 8);
-  s.off_flag = s.off_vel + s.Np * 8;
-  s.off_f64 = s.off_flag + s.Wp * 4;
-  s.row_bytes = s.off_f64 + (faithful ? s.Wp * 4 : 0);   // a multiple of 16 by construction
+  s.Wd = s.W > 0 ? s.W : 1;
+}
+__host__ __device__ inline size_t pos_plane_bytes(const DevState& s, bool faithful) {
+  return (size_t)s.T * (size_t)(s.U > 0 ? s.U : 1) * 512u * (faithful ? 2u : 1u);
+}
+__host__ __device__ inline size_t vel_plane_bytes(const DevState& s) { return (size_t)s.T * (size_t)(s.U > 0 ? s.U : 1) * 512u; }
+__host__ __device__ inline size_t flag_plane_words(const DevState& s) { return (size_t)s.T * (size_t)s.Wd * 32u; }
+
+// byte offsets of intruder i of env `env` inside the planes (host side uses them for get/set_state)
+__host__ __device__ inline size_t ipos_offset(const DevState& s, bool faithful, size_t env, int i) {
+  const size_t t = env >> 5, e = env & 31;
+  if (faithful) return ((t * (size_t)(2 * s.U) + (size_t)i) * 32 + e) * 16;
+  return ((t * (size_t)s.U + (size_t)(i >> 1)) * 32 + e) * 16 + (size_t)(i & 1) * 8;
+}
+__host__ __device__ inline size_t ivel_offset(const DevState& s, size_t env, int i) {
+  const size_t t = env >> 5, e = env & 31;
+  return ((t * (size_t)s.U + (size_t)(i >> 1)) * 32 + e) * 16 + (size_t)(i & 1) * 8;
+}
+__host__ __device__ inline size_t flag_index(const DevState& s, size_t env, int w) {
+  const size_t t = env >> 5, e = env & 31;
+  return (t * (size_t)s.Wd + (size_t)w) * 32 + e;
 }
 
 // Constants derived from gca_config on the host (gca_abi.cu), exact by construction.
@@ -85,6 +112,7 @@ struct StepArgs {
   uint32_t key0, key1, env_id0;
   int D;                  // observation row length
   int auto_reset;
+  int debug_skip;         // tuning experiments only (GCA_DEBUG_SKIP): 1 = no observation write-out, 2 = no position stores
   void* obs;
   void* achieved;
   void* desired;
@@ -221,40 +249,33 @@ struct Intr<true> {
   bool is64;
 };
 
-// row accessors (work on a global row or on its shared-memory copy)
+// scattered (one intruder of one env) accessors of the global planes: reset, respawn, observe, raster
 template <bool FAITH>
-__device__ __forceinline__ void load_intruder(const DevState& s, const uint8_t* row, int i, Intr<FAITH>& it) {
+__device__ __forceinline__ void load_intruder(const DevState& s, size_t env, int i, Intr<FAITH>& it) {
   if constexpr (FAITH) {
-    const double2 p = reinterpret_cast<const double2*>(row)[i];
+    const double2 p = *reinterpret_cast<const double2*>(s.ipos + ipos_offset(s, true, env, i));
     it.px = p.x;
     it.py = p.y;
+    it.is64 = (s.dflag[flag_index(s, env, i >> 5)] >> (i & 31)) & 1u;
   } else {
-    const float2 p = reinterpret_cast<const float2*>(row)[i];
+    const float2 p = *reinterpret_cast<const float2*>(s.ipos + ipos_offset(s, false, env, i));
     it.px = p.x;
     it.py = p.y;
   }
-  const float2 v = reinterpret_cast<const float2*>(row + s.off_vel)[i];
+  const float2 v = *reinterpret_cast<const float2*>(s.ivel + ivel_offset(s, env, i));
   it.vx = v.x;
   it.vy = v.y;
 }
 
 template <bool FAITH>
-__device__ __forceinline__ void store_ipos(uint8_t* row, int i, const Intr<FAITH>& it) {
-  if constexpr (FAITH) reinterpret_cast<double2*>(row)[i] = make_double2(it.px, it.py);
-  else reinterpret_cast<float2*>(row)[i] = make_float2(it.px, it.py);
+__device__ __forceinline__ void store_ipos(const DevState& s, size_t env, int i, const Intr<FAITH>& it) {
+  if constexpr (FAITH) *reinterpret_cast<double2*>(s.ipos + ipos_offset(s, true, env, i)) = make_double2(it.px, it.py);
+  else *reinterpret_cast<float2*>(s.ipos + ipos_offset(s, false, env, i)) = make_float2(it.px, it.py);
 }
 
-__device__ __forceinline__ void store_ivel(const DevState& s, uint8_t* row, int i, float vx, float vy) {
-  reinterpret_cast<float2*>(row + s.off_vel)[i] = make_float2(vx, vy);
+__device__ __forceinline__ void store_ivel(const DevState& s, size_t env, int i, float vx, float vy) {
+  *reinterpret_cast<float2*>(s.ivel + ivel_offset(s, env, i)) = make_float2(vx, vy);
 }
-
-__device__ __forceinline__ uint32_t* flag_words(const DevState& s, uint8_t* row) {
-  return reinterpret_cast<uint32_t*>(row + s.off_flag);
-}
-__device__ __forceinline__ uint32_t* f64_words(const DevState& s, uint8_t* row) {
-  return reinterpret_cast<uint32_t*>(row + s.off_f64);
-}
-__device__ __forceinline__ uint8_t* env_row(const DevState& s, size_t env) { return s.irow + env * (size_t)s.row_bytes; }
 
 // intruder.position += intruder.velocity   PKG/SingleAircraftEnv.py:150, and the map test :153
 template <bool FAITH>
@@ -383,6 +404,17 @@ __device__ __forceinline__ void write_obs_intruder(const StepArgs& a, real_t<FAI
   }
 }
 
+// The same four entries for the specialised hot path (FAST, GCA_OBS_VECTOR, one-correction
+// division verified exact for all three divisors on the host): no run-time layout tests.
+__device__ __forceinline__ float div_one(float x, float d, float inv_d) {
+  const float q = __fmul_rn(x, inv_d);
+  return __fmaf_rn(__fmaf_rn(-q, d, x), inv_d, q);
+}
+__device__ __forceinline__ float4 obs_intruder_vec(const Derived& k, float px, float py, float vx, float vy) {
+  return make_float4(div_one(px, k.ob_w, k.inv_ob_w), div_one(py, k.ob_h, k.inv_ob_h),
+                     div_one(__fadd_rn(vx, k.ms), k.den, k.inv_den), div_one(__fadd_rn(vy, k.ms), k.den, k.inv_den));
+}
+
 template <bool FAITH>
 __device__ __forceinline__ real_t<FAITH>* obs_intruder_base(const StepArgs& a, size_t env) {
   return reinterpret_cast<real_t<FAITH>*>(a.obs) + env * (size_t)a.D + (own_first(a.cfg) ? 6 : 0);
@@ -451,6 +483,10 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                    smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// global -> L2 bulk prefetch (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(

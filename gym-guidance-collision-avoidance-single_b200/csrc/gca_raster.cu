@@ -64,16 +64,15 @@ __global__ void __launch_bounds__(kRasterThreads) raster_kernel(const RasterArgs
       p.cx = (float)g.x; p.cy = (float)g.y; p.rc = 1.0f; p.rs = 0.0f; p.tex = 1;
     } else {
       const int i = tid - 2;
-      const uint8_t* row = env_row(s, (size_t)env);
       float px, py;
       if (a.faithful) {
-        const double2 q = reinterpret_cast<const double2*>(row)[i];
+        const double2 q = *reinterpret_cast<const double2*>(s.ipos + ipos_offset(s, true, (size_t)env, i));
         px = (float)q.x; py = (float)q.y;
       } else {
-        const float2 q = reinterpret_cast<const float2*>(row)[i];
+        const float2 q = *reinterpret_cast<const float2*>(s.ipos + ipos_offset(s, false, (size_t)env, i));
         px = q.x; py = q.y;
       }
-      const float2 v = reinterpret_cast<const float2*>(row + s.off_vel)[i];
+      const float2 v = *reinterpret_cast<const float2*>(s.ivel + ivel_offset(s, (size_t)env, i));
       // the intruder's heading is constant for life (:207-211); its direction is that of the velocity
       const float len = __fsqrt_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)));
       const float ch = __fdiv_rn(v.x, len), sh = __fdiv_rn(v.y, len);

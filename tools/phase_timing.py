@@ -21,7 +21,7 @@ for i in range(30):
     env.step(acts[i % 8])
 torch.cuda.synchronize()
 lib = abi.load()
-tiles = int(os.environ.get("GCA_TILE", "32"))
+tiles = 32
 nt = B // tiles
 buf = np.zeros(nt * 8, np.uint64)
 lib.gca_debug_phase_stamps.argtypes = [C.c_void_p, C.c_int]
@@ -50,3 +50,25 @@ print("per-SM finish: min %.2f p10 %.2f median %.2f p90 %.2f max %.2f (n_sm=%d)"
                                                                                     np.percentile(f, 90), f.max(), len(f)))
 cnt = np.bincount(sm.astype(int))
 print("tiles per SM: min %d max %d" % (cnt[cnt > 0].min(), cnt.max()))
+# finish time by SM id (looks for die / GPC structure in the imbalance)
+order = sorted(fin.items())
+print("finish by smid:", " ".join("%d:%.0f" % (k, v_) for k, v_ in order))
+# B duration vs tile index (address structure)
+bd = d[:, 1]
+print("phase B by tile octile:", " ".join("%.1f" % bd[i * nt // 8:(i + 1) * nt // 8].mean() for i in range(8)))
+# per-stage decomposition (every 32nd tile): wait for the TMA load | compute + stage | write-out
+if hasattr(lib, "gca_debug_stage_stamps"):
+    sb = np.zeros(64 * 16 * 4, np.uint64)
+    lib.gca_debug_stage_stamps.argtypes = [C.c_void_p, C.c_int]
+    assert lib.gca_debug_stage_stamps(sb.ctypes.data, sb.size) == 0
+    ss = sb.reshape(64, 16, 4).astype(np.int64)
+    nst = int(os.environ.get("GCA_NSTAGES", "10"))
+    ss = ss[:, :nst]
+    wait = (ss[:, :, 1] - ss[:, :, 0]) / 1e3
+    comp = (ss[:, :, 2] - ss[:, :, 1]) / 1e3
+    wout = (ss[:, :, 3] - ss[:, :, 2]) / 1e3
+    print("per stage (us)   wait %.2f   compute %.2f   write-out %.2f   total %.2f" % (wait.mean(), comp.mean(), wout.mean(),
+                                                                                    ((ss[:, -1, 3] - ss[:, 0, 0]) / 1e3 / nst).mean()))
+    print("wait by stage:", " ".join("%.2f" % x for x in wait.mean(0)))
+    print("compute by stage:", " ".join("%.2f" % x for x in comp.mean(0)))
+    print("write-out by stage:", " ".join("%.2f" % x for x in wout.mean(0)))
