@@ -1,5 +1,6 @@
 // gca_abi.cu - the C ABI of include/gca.h: handle lifetime, argument checking, state
 // marshalling and the host-buffer (end-to-end) path.  No exception crosses the boundary.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <limits>
@@ -35,7 +36,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 }  // namespace
 
 struct gca_env {
-  int device = 0, mode = 0, draws = 0, group = 4, stages = 4;
+  int device = 0, mode = 0, draws = 0;
   gca_config cfg{};
   Derived k{};
   uint64_t seed = 0;
@@ -131,8 +132,6 @@ StepArgs make_args(const gca_env* e, const void* actions, const gca_tape* tape, 
   a.env_id0 = e->env_id0;
   a.D = e->D;
   a.auto_reset = auto_reset;
-  static const int dbg = std::getenv("GCA_DEBUG_SKIP") ? std::atoi(std::getenv("GCA_DEBUG_SKIP")) : 0;
-  a.debug_skip = dbg;
   if (out) {
     a.obs = out->obs; a.achieved = out->achieved; a.desired = out->desired;
     a.reward = out->reward; a.done = out->done; a.info = out->info;
@@ -157,17 +156,20 @@ int check_tape(const gca_env* e, const gca_tape* tape) {
 
 // host copies of the tile-planar intruder planes (gca_get_state / gca_set_state)
 struct HostPlanes {
-  std::vector<uint8_t> pos, vel;
+  std::vector<uint8_t> pos, vel;      // pos: both planes
   std::vector<uint32_t> cf, df;
+  std::vector<int4> cnt;
   int download(const DevState& s, bool faith) {
-    pos.resize(pos_plane_bytes(s, faith));
+    pos.resize(2 * s.pos_plane);
     vel.resize(vel_plane_bytes(s));
     cf.resize(flag_plane_words(s));
     df.resize(faith ? flag_plane_words(s) : 1);
+    cnt.resize((size_t)s.B);
     GCA_CUDA(cudaMemcpy(pos.data(), s.ipos, pos.size(), cudaMemcpyDeviceToHost));
     GCA_CUDA(cudaMemcpy(vel.data(), s.ivel, vel.size(), cudaMemcpyDeviceToHost));
     GCA_CUDA(cudaMemcpy(cf.data(), s.cflag, cf.size() * 4, cudaMemcpyDeviceToHost));
     if (faith) GCA_CUDA(cudaMemcpy(df.data(), s.dflag, df.size() * 4, cudaMemcpyDeviceToHost));
+    GCA_CUDA(cudaMemcpy(cnt.data(), s.counters, cnt.size() * sizeof(int4), cudaMemcpyDeviceToHost));
     return GCA_OK;
   }
   int upload(const DevState& s, bool faith) {
@@ -175,8 +177,11 @@ struct HostPlanes {
     GCA_CUDA(cudaMemcpy(s.ivel, vel.data(), vel.size(), cudaMemcpyHostToDevice));
     GCA_CUDA(cudaMemcpy(s.cflag, cf.data(), cf.size() * 4, cudaMemcpyHostToDevice));
     if (faith) GCA_CUDA(cudaMemcpy(s.dflag, df.data(), df.size() * 4, cudaMemcpyHostToDevice));
+    GCA_CUDA(cudaMemcpy(s.counters, cnt.data(), cnt.size() * sizeof(int4), cudaMemcpyHostToDevice));
     return GCA_OK;
   }
+  // env b's current position plane (gca_device.cuh: tick & 1)
+  uint8_t* plane_of(const DevState& s, size_t b) { return pos.data() + (size_t)(cnt[b].z & 1) * s.pos_plane; }
 };
 }  // namespace
 
@@ -216,17 +221,9 @@ int gca_create(const gca_config* cfg, int n_envs, int n_intruders, int mode, int
   if (!e) return fail(GCA_ERR_ALLOC, "out of host memory");
   e->device = device; e->mode = mode; e->draws = draws; e->cfg = *cfg; e->k = derive(*cfg); e->seed = seed; e->env_id0 = env_id0;
   e->D = gca_obs_dim(cfg, n_intruders);
-  if (const char* t = std::getenv("GCA_GROUP")) {      // units (intruder pairs) per pipeline stage
-    const int v = std::atoi(t);
-    if (v == 2 || v == 4) e->group = v;
-  }
-  if (const char* t = std::getenv("GCA_STAGES")) {
-    const int v = std::atoi(t);
-    if (v >= 1 && v <= 8) e->stages = v;
-  }
   DevState& s = e->s;
   s.B = n_envs; s.N = n_intruders;
-  plane_layout(s);
+  plane_layout(s, mode == GCA_MODE_FAITHFUL);
   const size_t B = (size_t)n_envs;
   int rc = GCA_OK;
   if (!rc) rc = dev_alloc(e, &s.own_pos, B);
@@ -235,11 +232,20 @@ int gca_create(const gca_config* cfg, int n_envs, int n_intruders, int mode, int
   if (!rc) rc = dev_alloc(e, &s.own_vel_f32, B);
   if (!rc) rc = dev_alloc(e, &s.goal, B);
   if (!rc) rc = dev_alloc(e, &s.counters, B);
-  if (!rc) rc = dev_alloc(e, &s.ipos, pos_plane_bytes(s, mode == GCA_MODE_FAITHFUL));
+  if (!rc) rc = dev_alloc(e, &s.ipos, 2 * s.pos_plane);
+  if (!rc) rc = dev_alloc(e, &s.own_b, (size_t)s.T * 32);
+  if (!rc) rc = dev_alloc(e, &s.ev_conf, flag_plane_words(s));
+  if (!rc) rc = dev_alloc(e, &s.ev_gone, flag_plane_words(s));
+  if (!rc) rc = dev_alloc(e, &s.ev_nmac, (size_t)s.T * 32);
+  if (!rc) rc = dev_alloc(e, &s.tile_done, (size_t)s.T);
+  if (!rc) rc = dev_alloc(e, &s.reset_list, (size_t)s.T * 32);
+  if (!rc) rc = dev_alloc(e, &s.reset_count, 1);
+  s.respawn_cap = (int)std::min<size_t>((size_t)s.T * 32 * 4, (size_t)1 << 30);
+  if (!rc) rc = dev_alloc(e, &s.respawn_list, (size_t)s.respawn_cap);
+  if (!rc) rc = dev_alloc(e, &s.respawn_count, 1);
   if (!rc) rc = dev_alloc(e, &s.ivel, vel_plane_bytes(s));
   if (!rc) rc = dev_alloc(e, &s.cflag, flag_plane_words(s));
   if (!rc) rc = dev_alloc(e, &s.dflag, mode == GCA_MODE_FAITHFUL ? flag_plane_words(s) : 1);
-  if (!rc) rc = dev_alloc(e, &s.sched, 2);
   if (rc) {
     gca_destroy(e);
     return rc;
@@ -290,7 +296,7 @@ int gca_step(gca_env* e, const void* actions, const gca_tape* tape, int auto_res
   if (int rc = check_tape(e, tape)) return rc;
   GCA_CUDA(cudaSetDevice(e->device));
   const StepArgs a = make_args(e, actions, tape, out, auto_reset);
-  GCA_CUDA(launch_step(e->mode == GCA_MODE_FAITHFUL, e->draws == GCA_DRAWS_TAPE, e->group, e->stages, a,
+  GCA_CUDA(launch_step(e->mode == GCA_MODE_FAITHFUL, e->draws == GCA_DRAWS_TAPE, a,
                        (cudaStream_t)stream));
   return GCA_OK;
 }
@@ -385,10 +391,10 @@ int gca_get_state(gca_env* e, const gca_host_state* h) {
       const size_t k = b * N + i;
       if (h->ipos) {
         if (faith) {
-          const double2 p = *reinterpret_cast<const double2*>(hp.pos.data() + ipos_offset(s, true, b, (int)i));
+          const double2 p = *reinterpret_cast<const double2*>(hp.plane_of(s, b) + ipos_offset(s, true, b, (int)i));
           h->ipos[2 * k] = p.x; h->ipos[2 * k + 1] = p.y;
         } else {
-          const float2 p = *reinterpret_cast<const float2*>(hp.pos.data() + ipos_offset(s, false, b, (int)i));
+          const float2 p = *reinterpret_cast<const float2*>(hp.plane_of(s, b) + ipos_offset(s, false, b, (int)i));
           h->ipos[2 * k] = (double)p.x; h->ipos[2 * k + 1] = (double)p.y;
         }
       }
@@ -415,37 +421,32 @@ int gca_set_state(gca_env* e, const gca_host_state* h) {
   if (h->own_vel) GCA_CUDA(cudaMemcpy(s.own_vel, h->own_vel, B * sizeof(double2), cudaMemcpyHostToDevice));
   if (h->own_vel_is_f32) GCA_CUDA(cudaMemcpy(s.own_vel_f32, h->own_vel_is_f32, B, cudaMemcpyHostToDevice));
   if (h->goal) GCA_CUDA(cudaMemcpy(s.goal, h->goal, B * sizeof(double2), cudaMemcpyHostToDevice));
-  if (h->no_conflict || h->ep_steps || h->tick) {
-    std::vector<int4> c(B);
-    GCA_CUDA(cudaMemcpy(c.data(), s.counters, B * sizeof(int4), cudaMemcpyDeviceToHost));
-    for (size_t b = 0; b < B; ++b) {
-      if (h->no_conflict) c[b].x = h->no_conflict[b];
-      if (h->ep_steps) c[b].y = h->ep_steps[b];
-      if (h->tick) c[b].z = (int)h->tick[b];
-    }
-    GCA_CUDA(cudaMemcpy(s.counters, c.data(), B * sizeof(int4), cudaMemcpyHostToDevice));
-  }
-  if (N == 0 || !(h->ipos || h->ivel || h->iflag || h->ipos_is_f64)) return GCA_OK;
   const bool faith = e->mode == GCA_MODE_FAITHFUL;
   HostPlanes hp;
   if (int rc = hp.download(s, faith)) return rc;                      // keep what the view omits
   for (size_t b = 0; b < B; ++b) {
+    const int old_plane = hp.cnt[b].z & 1;
+    if (h->no_conflict) hp.cnt[b].x = h->no_conflict[b];
+    if (h->ep_steps) hp.cnt[b].y = h->ep_steps[b];
+    if (h->tick) hp.cnt[b].z = (int)h->tick[b];
+    const int new_plane = hp.cnt[b].z & 1;                            // the tick selects the current position plane
+    const uint8_t* from = hp.pos.data() + (size_t)old_plane * s.pos_plane;
+    uint8_t* to = hp.pos.data() + (size_t)new_plane * s.pos_plane;
     for (int w = 0; w < s.W; ++w) {
       if (h->iflag) hp.cf[flag_index(s, b, w)] = 0u;
       if (h->ipos_is_f64 && faith) hp.df[flag_index(s, b, w)] = 0u;
     }
     for (size_t i = 0; i < N; ++i) {
       const size_t k = b * N + i;
-      if (h->ipos) {
-        if (faith) {
-          *reinterpret_cast<double2*>(hp.pos.data() + ipos_offset(s, true, b, (int)i)) =
-              make_double2(h->ipos[2 * k], h->ipos[2 * k + 1]);
-        } else {
-          // FAST positions are stored as non-negative-zero f32 (the map test of the step kernel compares bit
-          // patterns); -0.0 and +0.0 are the same position for every rule of the reference.
-          *reinterpret_cast<float2*>(hp.pos.data() + ipos_offset(s, false, b, (int)i)) =
-              make_float2((float)h->ipos[2 * k] + 0.0f, (float)h->ipos[2 * k + 1] + 0.0f);
-        }
+      const size_t po = ipos_offset(s, faith, b, (int)i);
+      if (faith) {
+        *reinterpret_cast<double2*>(to + po) = h->ipos ? make_double2(h->ipos[2 * k], h->ipos[2 * k + 1])
+                                                       : *reinterpret_cast<const double2*>(from + po);
+      } else {
+        // FAST positions are stored as non-negative-zero f32 (the map test of the streaming pass compares bit
+        // patterns); -0.0 and +0.0 are the same position for every rule of the reference.
+        *reinterpret_cast<float2*>(to + po) = h->ipos ? make_float2((float)h->ipos[2 * k] + 0.0f, (float)h->ipos[2 * k + 1] + 0.0f)
+                                                      : *reinterpret_cast<const float2*>(from + po);
       }
       if (h->ivel)
         *reinterpret_cast<float2*>(hp.vel.data() + ivel_offset(s, b, (int)i)) = make_float2(h->ivel[2 * k], h->ivel[2 * k + 1]);

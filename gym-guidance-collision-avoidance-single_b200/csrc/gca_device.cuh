@@ -15,18 +15,22 @@
 namespace gca {
 
 // ------------------------------------------------------------------------------ device state
-// Everything is laid out for "lane = env": a warp owns a tile of 32 consecutive envs and lane e
-// of the warp owns env 32*t + e from the first instruction of a step to the last.
+// Everything is laid out for "lane = env": a warp works on a tile of 32 consecutive envs and lane e
+// of the warp touches env 32*t + e only.
 //   per-env scalars   SoA by field, [B]: one coalesced access per warp.
 //   intruder planes   tile-planar: for tile t and 16-byte unit u the 32 lanes' units are adjacent,
 //                         plane[(t * units + u) * 32 + e]            (512 bytes per (t, u))
 //       pos  FAST     unit u = float4 (x, y) of intruders 2u, 2u+1           units = U = ceil(N/2)
 //            FAITHFUL unit i = double2 (x, y) of intruder i (an f32 value unless flagged)  units = 2U
 //       vel           unit u = float4 (vx, vy) of intruders 2u, 2u+1         units = U
-//       conflict / f64 flag words: word w of env e at  words[(t * Wd + w) * 32 + e]
-//   so that (i) a warp-wide 16-byte access to unit u is one contiguous 512-byte line, (ii) any run of
-//   units of a tile is ONE contiguous block that a single 1-D bulk (TMA) copy brings into shared
-//   memory, where lane e's 16-byte reads are bank-conflict free.
+//       conflict / f64 flag words and the per-step event words: word w of env e at words[(t * Wd + w) * 32 + e]
+//   so every warp-wide 16-byte access is one contiguous 512-byte line and any run of units of a tile is
+//   one contiguous block.
+// Positions are double-buffered (two planes).  The plane that holds env e's current positions is
+// tick(e) & 1; a step reads it, writes the other one and increments the tick.  The intruder pass of a
+// step therefore never overwrites its input, which makes it order-free: any warp can advance any 8
+// intruders of any tile at any time, and the rare "the reference's loop returned at intruder i"
+// case (NMAC, Q9) is repaired afterwards from the untouched old plane.
 // bit i%32 of conflict word i/32 = Aircraft.conflict of intruder i; the f64 words flag positions
 // whose dtype became f64 after a retried spawn (Q3).
 struct DevState {
@@ -36,11 +40,22 @@ struct DevState {
   uint8_t* own_vel_f32;   // [B]
   double2* goal;          // [B]
   int4* counters;         // [B]   (no_conflict, ep_steps, tick, episodes)
-  uint8_t* ipos;          // [T][U or 2U][32] 16-byte units
+  uint8_t* ipos;          // [2][T][U or 2U][32] 16-byte units
   uint8_t* ivel;          // [T][U][32] float4
   uint32_t* cflag;        // [T][Wd][32]
   uint32_t* dflag;        // [T][Wd][32]  (FAITHFUL)
-  unsigned int* sched;    // [2]   dynamic tile scheduler: next tile, finished warps
+  // hand-over between the three kernels of a step
+  float4* own_b;          // [T*32] (own x, own y, bits: 1 = the intruder loop runs, 2 = plane parity, -)
+  uint32_t* ev_conf;      // [T][Wd][32] bit i: intruder i is inside the separation radius after its advance
+  uint32_t* ev_gone;      // [T][Wd][32] bit i: intruder i left the map
+  int* ev_nmac;           // [T*32] lowest intruder index inside the NMAC radius (INT_MAX: none)
+  int* tile_done;         // [T]    work items of the streaming pass that have completed for the tile
+  int* reset_list;        // [T*32] envs that finished in this step (PHILOX auto-reset), in arrival order
+  int* reset_count;       // [1]
+  uint32_t* respawn_list; // [respawn_cap] (env << 8 | intruder) of the intruders that left the map in this step (PHILOX)
+  int* respawn_count;     // [1]
+  int respawn_cap;
+  size_t pos_plane;       // bytes of one position plane
   int B, N, T, U, W, Wd;
 };
 
@@ -49,19 +64,17 @@ struct pos2 { using type = float2; };
 template <>
 struct pos2<true> { using type = double2; };
 
-__host__ __device__ inline void plane_layout(DevState& s) {
+__host__ __device__ inline void plane_layout(DevState& s, bool faithful) {
   s.T = (s.B + 31) / 32;
   s.U = (s.N + 1) / 2;
   s.W = (s.N + 31) / 32;
   s.Wd = s.W > 0 ? s.W : 1;
-}
-__host__ __device__ inline size_t pos_plane_bytes(const DevState& s, bool faithful) {
-  return (size_t)s.T * (size_t)(s.U > 0 ? s.U : 1) * 512u * (faithful ? 2u : 1u);
+  s.pos_plane = (size_t)s.T * (size_t)(s.U > 0 ? s.U : 1) * 512u * (faithful ? 2u : 1u);
 }
 __host__ __device__ inline size_t vel_plane_bytes(const DevState& s) { return (size_t)s.T * (size_t)(s.U > 0 ? s.U : 1) * 512u; }
 __host__ __device__ inline size_t flag_plane_words(const DevState& s) { return (size_t)s.T * (size_t)s.Wd * 32u; }
 
-// byte offsets of intruder i of env `env` inside the planes (host side uses them for get/set_state)
+// byte offsets of intruder i of env `env` inside a position plane / the velocity plane
 __host__ __device__ inline size_t ipos_offset(const DevState& s, bool faithful, size_t env, int i) {
   const size_t t = env >> 5, e = env & 31;
   if (faithful) return ((t * (size_t)(2 * s.U) + (size_t)i) * 32 + e) * 16;
@@ -112,7 +125,6 @@ struct StepArgs {
   uint32_t key0, key1, env_id0;
   int D;                  // observation row length
   int auto_reset;
-  int debug_skip;         // tuning experiments only (GCA_DEBUG_SKIP): 1 = no observation write-out, 2 = no position stores
   void* obs;
   void* achieved;
   void* desired;
@@ -122,6 +134,28 @@ struct StepArgs {
 };
 
 constexpr unsigned FULL = 0xffffffffu;
+
+// ------------------------------------------------------------------------------ L2 eviction hints
+// The streaming pass moves ~215 MB per step through a 126 MB L2; nothing of it is touched again before it would
+// have been evicted anyway.  Marking that traffic evict_first keeps the ~10 MB that the other kernels of a step
+// DO come back to (per-env scalars, event words, flag words) resident, so their dependent loads are L2 hits.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ldg_stream(const void* ptr, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(ptr), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void stg_stream(void* ptr, const float4& v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w), "l"(pol)
+               : "memory");
+}
 
 // ------------------------------------------------------------------------------ Philox4x32-10
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
@@ -249,16 +283,18 @@ struct Intr<true> {
   bool is64;
 };
 
-// scattered (one intruder of one env) accessors of the global planes: reset, respawn, observe, raster
+// scattered (one intruder of one env) accessors of the global planes: reset, respawn, repair, observe, raster.
+// `plane` = 0 / 1 selects the position buffer.
 template <bool FAITH>
-__device__ __forceinline__ void load_intruder(const DevState& s, size_t env, int i, Intr<FAITH>& it) {
+__device__ __forceinline__ void load_intruder(const DevState& s, int plane, size_t env, int i, Intr<FAITH>& it) {
+  const uint8_t* base = s.ipos + (size_t)plane * s.pos_plane;
   if constexpr (FAITH) {
-    const double2 p = *reinterpret_cast<const double2*>(s.ipos + ipos_offset(s, true, env, i));
+    const double2 p = *reinterpret_cast<const double2*>(base + ipos_offset(s, true, env, i));
     it.px = p.x;
     it.py = p.y;
     it.is64 = (s.dflag[flag_index(s, env, i >> 5)] >> (i & 31)) & 1u;
   } else {
-    const float2 p = *reinterpret_cast<const float2*>(s.ipos + ipos_offset(s, false, env, i));
+    const float2 p = *reinterpret_cast<const float2*>(base + ipos_offset(s, false, env, i));
     it.px = p.x;
     it.py = p.y;
   }
@@ -268,9 +304,10 @@ __device__ __forceinline__ void load_intruder(const DevState& s, size_t env, int
 }
 
 template <bool FAITH>
-__device__ __forceinline__ void store_ipos(const DevState& s, size_t env, int i, const Intr<FAITH>& it) {
-  if constexpr (FAITH) *reinterpret_cast<double2*>(s.ipos + ipos_offset(s, true, env, i)) = make_double2(it.px, it.py);
-  else *reinterpret_cast<float2*>(s.ipos + ipos_offset(s, false, env, i)) = make_float2(it.px, it.py);
+__device__ __forceinline__ void store_ipos(const DevState& s, int plane, size_t env, int i, const Intr<FAITH>& it) {
+  uint8_t* base = s.ipos + (size_t)plane * s.pos_plane;
+  if constexpr (FAITH) *reinterpret_cast<double2*>(base + ipos_offset(s, true, env, i)) = make_double2(it.px, it.py);
+  else *reinterpret_cast<float2*>(base + ipos_offset(s, false, env, i)) = make_float2(it.px, it.py);
 }
 
 __device__ __forceinline__ void store_ivel(const DevState& s, size_t env, int i, float vx, float vy) {
@@ -464,42 +501,6 @@ __device__ __forceinline__ void write_obs_own(const StepArgs& a, size_t env, flo
       dg[0] = (R)gx; dg[1] = (R)gy;
     }
   }
-}
-
-// ------------------------------------------------------------------------------ TMA (1-D bulk copy) + mbarrier
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// global -> shared bulk copy, completion counted in bytes on `bar` (SASS: UBLKCP)
-__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-// global -> L2 bulk prefetch (no shared-memory destination, no completion to wait for)
-__device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "GCA_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra GCA_DONE;\n"
-      "bra GCA_WAIT;\n"
-      "GCA_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
 }
 
 }  // namespace gca

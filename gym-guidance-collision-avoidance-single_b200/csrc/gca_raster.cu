@@ -65,11 +65,12 @@ __global__ void __launch_bounds__(kRasterThreads) raster_kernel(const RasterArgs
     } else {
       const int i = tid - 2;
       float px, py;
+      const uint8_t* plane = s.ipos + (size_t)(s.counters[env].z & 1) * s.pos_plane;   // the env's current positions
       if (a.faithful) {
-        const double2 q = *reinterpret_cast<const double2*>(s.ipos + ipos_offset(s, true, (size_t)env, i));
+        const double2 q = *reinterpret_cast<const double2*>(plane + ipos_offset(s, true, (size_t)env, i));
         px = (float)q.x; py = (float)q.y;
       } else {
-        const float2 q = *reinterpret_cast<const float2*>(s.ipos + ipos_offset(s, false, (size_t)env, i));
+        const float2 q = *reinterpret_cast<const float2*>(plane + ipos_offset(s, false, (size_t)env, i));
         px = q.x; py = q.y;
       }
       const float2 v = *reinterpret_cast<const float2*>(s.ivel + ivel_offset(s, (size_t)env, i));

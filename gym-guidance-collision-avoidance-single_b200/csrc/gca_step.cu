@@ -1,80 +1,95 @@
-// gca_step.cu - the fused step / reset / observe kernels (sm_100a).
+// gca_step.cu - step / reset / observe of the batched simulator (sm_100a).
 //
-// Mapping: lane = env.  A warp owns a tile of 32 consecutive environments, lane e owns env
-// 32*tile + e for the whole step and never talks to another lane on the hot path:
-//   phase A  ownship kinematics (all the f64 work: Philox + Box-Muller, sincos, clamp), 32 envs
-//            per warp instruction;
-//   phase B  every lane walks ITS env's intruders in index order, two per 16-byte unit: advance,
-//            f32 separation on the squared distance, map test.  A unit without any event (nobody
-//            left the map, nobody inside the separation radius - the overwhelmingly common case)
-//            costs two shared-memory loads, ~25 FP32/integer instructions per intruder, one
-//            coalesced 16-byte position store and one 16-byte observation store per intruder.
-//            Anything else drops to visit_slow(), which is the reference's loop body verbatim
-//            (PKG/SingleAircraftEnv.py:149-170): because a lane visits its intruders sequentially,
-//            "first NMAC index wins and freezes every later intruder" (Q9), "respawn lands before
-//            the conflict test but the test uses the old object" (Q7) and "the flag never clears"
-//            (Q8) need no cross-lane reconstruction;
-//   phase C  respawns of the intruders that left the map (their draws come in index order, like
-//            the reference's), wall / goal / reward / done, observation tail, counters;
-//   phase D  VecEnv auto-reset of finished envs: the warp cooperates, lanes = intruders (PHILOX).
-// Memory pipeline.  State is tile-planar (gca_device.cuh): the positions and velocities of units
-// [u, u+G) of a tile are two contiguous blocks of G*512 bytes, each brought into shared memory by
-// ONE 1-D bulk copy (cp.async.bulk, the TMA engine; SASS UBLKCP) completing on an mbarrier.  Each
-// warp owns a ring of `stages` such buffers, so memory-level parallelism does not depend on
-// registers or occupancy, lane e's 16-byte shared loads are conflict-free, and every global access
-// of the hot path is a full 512-byte line (state) or a private 16-byte store (observation rows).
-// Every byte of state is read once and written at most once per step.
+// One step = three launches on the caller's stream, each shaped for what bounds it:
+//
+//   step_own_kernel        thread = env.  Ownship kinematics (PKG/SingleAircraftEnv.py:299-309): all
+//                          of it f64 (Philox + Box-Muller, sincos, clamp), ~80 bytes per env.
+//                          FP64-pipe bound, a few microseconds.
+//   step_intruders_kernel  warp = 8 intruders x 32 envs, lane = env.  THE streaming pass: advance, map
+//                          test, separation test on the squared distance, observation entries.  It
+//                          reads one position plane and writes the other (gca_device.cuh), so it is
+//                          order-free: work items are tiny (4 KB in, 6 KB out), there are ~10x more of
+//                          them than resident warps, and the hardware block scheduler hands them to
+//                          whichever SM drains fastest - which is what it takes to reach the DRAM
+//                          roofline on a part whose GPCs do not get equal shares of the memory system
+//                          (measured: with one resident warp per 32 envs the same arithmetic ended
+//                          between 32 and 55 us depending on the SM).  Loads are 16 bytes per lane,
+//                          512 contiguous bytes per warp instruction, 8 independent ones in flight per
+//                          lane; positions leave the same way; observation entries are transposed
+//                          through shared memory so that every store covers whole 32-byte sectors of
+//                          the 1312-byte observation rows.  Events (an intruder left the map / is inside
+//                          the separation or NMAC radius) are rare and only RECORDED here as bit masks.
+//   step_finish_kernel     warp = 32 envs, lane = env.  Replays the reference's sequential loop
+//                          semantics from the recorded masks (PKG/SingleAircraftEnv.py:149-170): first
+//                          NMAC index wins and everything after it is put back where it was (Q9),
+//                          respawns happen in index order with the reference's draw order, a replaced
+//                          intruder is tested with its old distance and starts with conflict False (Q7),
+//                          the flag never clears otherwise (Q8); then wall / goal / reward / done, the
+//                          ownship + goal tail of the observation, counters, and the VecEnv auto-reset
+//                          (warp-cooperative, lanes = intruders).
+// Every byte of intruder state is read once and written once per step; nothing is staged in HBM except
+// 16 bytes per env (ownship position for the streaming pass) and the event words.
+#include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <type_traits>
+#include <utility>
 
 #include "gca_device.cuh"
 #include "gca_launch.h"
 
 namespace gca {
 
-// Optional per-warp phase timestamps (build with -DGCA_PHASE_TIMING; tools/phase_timing.py reads them).
+// Optional kernel-level timestamps (build with -DGCA_PHASE_TIMING): first block in / last block out per kernel.
 #ifdef GCA_PHASE_TIMING
-__device__ unsigned long long g_phase_stamps[8192 * 8];
+__device__ unsigned long long g_kstamp[8];   // [kernel][start, end]
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-#define GCA_STAMP(slot)                                                                       \
-  do {                                                                                        \
-    if (lane == 0 && tile < 8192) g_phase_stamps[tile * 8 + (slot)] = gtime();                \
-  } while (0)
-// finer: 4 stamps per pipeline stage for every 32nd tile (64 tiles x 16 stages)
-__device__ unsigned long long g_stage_stamps[64 * 16 * 4];
-#define GCA_STAGE_STAMP(slot)                                                                                   \
-  do {                                                                                                          \
-    if (lane == 0 && (tile & 31) == 0 && tile < 2048 && st < 16) g_stage_stamps[((tile >> 5) * 16 + st) * 4 + (slot)] = gtime(); \
-  } while (0)
+__device__ unsigned long long g_fin[2048 * 8];   // per tile: finish start, end, respawn iterations, resets
+extern "C" int gca_debug_fin(unsigned long long* host) { return (int)cudaMemcpyFromSymbol(host, g_fin, sizeof(g_fin)); }
+#define GCA_KSTAMP_IN(kid) do { if (threadIdx.x == 0) atomicMin(&g_kstamp[2 * (kid)], gtime()); } while (0)
+#define GCA_KSTAMP_OUT(kid) do { if (threadIdx.x == 0) atomicMax(&g_kstamp[2 * (kid) + 1], gtime()); } while (0)
+extern "C" int gca_debug_kstamps(unsigned long long* host, int reset) {
+  int rc = (int)cudaMemcpyFromSymbol(host, g_kstamp, sizeof(g_kstamp));
+  if (reset) {
+    unsigned long long init[8] = {~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0};
+    rc |= (int)cudaMemcpyToSymbol(g_kstamp, init, sizeof(init));
+  }
+  return rc;
+}
 #else
-#define GCA_STAMP(slot) do { } while (0)
-#define GCA_STAGE_STAMP(slot) do { } while (0)
+#define GCA_KSTAMP_IN(kid) do { } while (0)
+#define GCA_KSTAMP_OUT(kid) do { } while (0)
 #endif
 
-constexpr int kWarpsPerBlock = 1;   // one warp per block: blocks spread evenly over the SMs
-constexpr int kMaxStages = 8;
+#ifndef GCA_MINB
+#define GCA_MINB 24
+#endif
+constexpr int kChunkUnits = 4;                    // 16-byte units (intruder pairs) per lane and work item
+constexpr int kChunkIntr = 2 * kChunkUnits;       // 8 intruders
+constexpr int kWarpsB = 1;                        // work items per block of the streaming pass: a warp that stays behind to finish a tile holds no one else
+// staging row of one lane: 8 intruders x 16 bytes of observation entries, plus 16 bytes so that the row stride is
+// an odd multiple of 16 (conflict-free 16-byte shared accesses across a quarter warp)
+constexpr uint32_t kObsRow = 16u * kChunkIntr + 16u;
+constexpr uint32_t kOwnRuns = 1u, kOwnPlane = 2u; // bits of own_b.z
+#ifndef PDL_EARLY
+#define PDL_EARLY 0
+#endif
 
-// shared memory of one warp: [stages][stage bytes] | observation staging [32][row] (OM = 1) |
-// mbarrier[kMaxStages] | conflict words [Wd][32] | out-of-map words [Wd][32] | f64 words [Wd][32] (FAITHFUL)
-__host__ __device__ inline size_t stage_bytes(bool faith, int G) { return (size_t)G * 512u * (faith ? 3u : 2u); }
-// staging row of one lane: the 2G intruders of a stage x 16 bytes of observation entries, plus 16 bytes so that
-// the row stride is an odd multiple of 16 (conflict-free 16-byte shared accesses across a quarter warp)
-__host__ __device__ constexpr uint32_t obs_row_bytes(int G) { return 32u * (uint32_t)G + 16u; }
-__host__ __device__ inline size_t warp_smem_bytes(const DevState& s, bool faith, int G, int stages, int om) {
-  return (size_t)stages * stage_bytes(faith, G) + (om ? 32u * obs_row_bytes(G) : 0u) + kMaxStages * sizeof(uint64_t) +
-         (size_t)s.Wd * 128u * (faith ? 3u : 2u);
-}
+// Programmatic dependent launch: the kernels of a step are launched with programmatic stream serialization, so
+// the next grid is staged (and its blocks scheduled as slots free up) while the current one drains.  A kernel
+// calls pdl_wait() before it touches anything an earlier kernel of the stream wrote.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-// reset(): PKG/SingleAircraftEnv.py:66-98 for env `env`, executed by the whole warp.
+// reset(): PKG/SingleAircraftEnv.py:66-98 for env `env`, executed by the whole warp; positions go to `plane`.
 // PHILOX: lanes = intruders.  TAPE: lane `owner` replays the reference's sequential draw order.
 template <bool FAITH, bool TAPE>
-__device__ __forceinline__ void reset_env_warp(const StepArgs& a, size_t env, int lane, int owner, Draws<TAPE>& d,
-                                               double2& goal) {
+__device__ __forceinline__ void reset_env_warp(const StepArgs& a, size_t env, int plane, int lane, int owner,
+                                               Draws<TAPE>& d, double2& goal) {
   const DevState& s = a.s;
   const gca_config& c = a.cfg;
   const Derived& k = a.k;
@@ -88,7 +103,7 @@ __device__ __forceinline__ void reset_env_warp(const StepArgs& a, size_t env, in
           const int i = r * 32 + j;
           Intr<FAITH> it;
           spawn<FAITH, TAPE>(d, c, k, GCA_SLOT_RESET | (uint32_t)i, ox, oy, it);
-          store_ipos<FAITH>(s, env, i, it);
+          store_ipos<FAITH>(s, plane, env, i, it);
           store_ivel(s, env, i, it.vx, it.vy);
           dw |= (it.is64 ? 1u : 0u) << j;
           write_obs_intruder<FAITH>(a, obase, i, it);
@@ -106,7 +121,7 @@ __device__ __forceinline__ void reset_env_warp(const StepArgs& a, size_t env, in
       bool wide = false;
       if (valid) {
         spawn<FAITH, TAPE>(d, c, k, GCA_SLOT_RESET | (uint32_t)i, ox, oy, it);
-        store_ipos<FAITH>(s, env, i, it);
+        store_ipos<FAITH>(s, plane, env, i, it);
         store_ivel(s, env, i, it.vx, it.vy);
         write_obs_intruder<FAITH>(a, obase, i, it);
         wide = it.is64;
@@ -130,528 +145,627 @@ __device__ __forceinline__ void reset_ownship(const gca_config& c, float2& pos, 
   vel = make_double2((double)(float)__dmul_rn(hs.y, cs), (double)(float)__dmul_rn(hs.y, sn));
 }
 
-// G  : units (intruder pairs) per pipeline stage.
-// OM : 1 = the observation is GCA_OBS_VECTOR with the one-correction division exact (the registered
-//      ids' layout; FAST only): the hot path writes it without run-time layout tests; 0 = generic.
-#ifndef GCA_MINB
-#define GCA_MINB 14
-#endif
-template <bool FAITH, bool TAPE, int G, int OM>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, GCA_MINB) step_kernel(const StepArgs a, const int stages) {
+template <bool TAPE>
+__device__ __forceinline__ Draws<TAPE> make_draws(const StepArgs& a, size_t me, uint32_t tick) {
+  Draws<TAPE> d;
+  if constexpr (TAPE) {
+    d.tape = a.tape + me * (size_t)a.tape_stride;
+    d.cur = a.cursor[me];
+  } else {
+    d.k0 = a.key0; d.k1 = a.key1;
+    d.env = a.env_id0 + (uint32_t)me;
+    d.tick = tick;
+  }
+  return d;
+}
+
+// ------------------------------------------------------------------------------ 1. ownship
+// Ownship.step(a)   PKG/SingleAircraftEnv.py:299-309 (2Env :291-301, DiscreteHER :301-311)
+template <bool FAITH, bool TAPE>
+__global__ void __launch_bounds__(128) step_own_kernel(const StepArgs a) {
   using R = real_t<FAITH>;
-  static_assert(!(FAITH && OM), "the specialised observation writer is FAST only");
-  extern __shared__ __align__(128) uint8_t smem[];
+  const DevState& s = a.s;
+  const gca_config& c = a.cfg;
+  if (PDL_EARLY) pdl_launch_dependents();
+  pdl_wait();
+  GCA_KSTAMP_IN(0);
+  const size_t me = (size_t)blockIdx.x * 128 + threadIdx.x;
+  if (me >= (size_t)s.T * 32) return;
+  if (me >= (size_t)s.B) {                                // padding lanes of the last tile
+    s.own_b[me] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  float2 pos = s.own_pos[me];
+  double2 hs = s.own_hs[me];
+  int4 cnt = s.counters[me];
+  Draws<TAPE> d = make_draws<TAPE>(a, me, (uint32_t)cnt.z);
+  double f0, f1 = 0.0;
+  if (c.action_kind == GCA_ACT_CONTINUOUS2) {
+    const R* act = reinterpret_cast<const R*>(a.actions) + 2 * me;
+    f0 = (double)act[0];
+    f1 = (double)act[1];
+  } else {
+    const int act = reinterpret_cast<const int*>(a.actions)[me];
+    if (c.action_kind == GCA_ACT_DISCRETE9) {
+      f0 = (double)(act / 3 - 1);
+      f1 = (double)(act % 3 - 1);
+    } else {
+      f0 = (double)(act - 1);
+    }
+  }
+  double nh, ns, sn, cs;
+  draw_own_noise(d, c, nh, ns);
+  double heading = __dadd_rn(hs.x, __dmul_rn(c.d_heading, f0));
+  heading = __dadd_rn(heading, nh);
+  double speed = c.action_kind == GCA_ACT_DISCRETE3 ? __dadd_rn(hs.y, c.speed_sigma)      // reference quirk Q16
+                                                    : __dadd_rn(hs.y, __dmul_rn(c.d_speed, f1));
+  const double m = c.max_speed < speed ? c.max_speed : speed;     // min(speed, max_speed)
+  speed = m > c.min_speed ? m : c.min_speed;                      // max(min_speed, .)
+  speed = __dadd_rn(speed, ns);                                   // noise after the clamp (Q5)
+  gca_sincos(heading, &sn, &cs);
+  const double2 vel = make_double2(__dmul_rn(speed, cs), __dmul_rn(speed, sn));
+  hs = make_double2(heading, speed);
+  pos = make_float2((float)__dadd_rn((double)pos.x, vel.x), (float)__dadd_rn((double)pos.y, vel.y));
+  cnt.y += 1;                                                     // StackEnv :118
+  const bool maxstep_hit = c.max_steps > 0 && cnt.y >= c.max_steps;   // StackEnv :134-136: the intruder loop never runs
+  s.own_pos[me] = pos;
+  s.own_hs[me] = hs;
+  s.own_vel[me] = vel;
+  s.own_vel_f32[me] = 0;
+  s.counters[me] = cnt;
+  if constexpr (TAPE) a.cursor[me] = d.cur;
+  const uint32_t bits = (maxstep_hit ? 0u : kOwnRuns) | ((uint32_t)(cnt.z & 1) * kOwnPlane);
+  s.own_b[me] = make_float4(pos.x, pos.y, __uint_as_float(bits), 0.f);
+  for (int w = 0; w < s.W; ++w) {
+    const size_t fi = flag_index(s, me, w);
+    s.ev_conf[fi] = 0u;
+    s.ev_gone[fi] = 0u;
+  }
+  s.ev_nmac[me] = INT_MAX;
+  if ((me & 31) == 0) s.tile_done[me >> 5] = 0;
+  if (me == 0) {
+    *s.reset_count = 0;
+    *s.respawn_count = 0;
+  }
+  GCA_KSTAMP_OUT(0);
+}
+
+// ------------------------------------------------------------------------------ finish (one warp, one tile)
+// Replays the reference's sequential loop semantics for the 32 envs of `tile` from the event words that the
+// streaming pass recorded, then rewards, observation tail, counters, auto-reset.  Called by the warp that
+// completed the tile's last work item (or by step_finish_kernel when there are no intruders).  The event
+// words were produced by other warps of the same launch: they are read with ld.global.cg (L2).
+constexpr int kJobCap = 256;
+template <bool FAITH, bool TAPE>
+__device__ __noinline__ void finish_tile(const StepArgs& a, const int tile, const int lane, uint32_t* jobs) {
+  using R = real_t<FAITH>;
   const DevState& s = a.s;
   const gca_config& c = a.cfg;
   const Derived& k = a.k;
-  constexpr uint32_t kPosUnits = FAITH ? 2u : 1u;                // 16-byte position units per intruder pair
-  constexpr uint32_t kStagePos = G * 512u * kPosUnits, kStageBytes = kStagePos + G * 512u;
-  const int lane = threadIdx.x & 31;
-  const int warp_in_block = threadIdx.x >> 5;
-  static_assert(G == 1 || G == 2 || G == 4 || G == 8, "2G lanes write out one env's entries of a stage");
-  constexpr uint32_t kObsRow = obs_row_bytes(G), kObsStage = 32u * kObsRow;
-  uint8_t* wsm = smem + (size_t)warp_in_block * warp_smem_bytes(s, FAITH, G, stages, OM);
-  uint8_t* ring = wsm;
-  uint8_t* stg = wsm + (size_t)stages * kStageBytes;                            // observation staging, row e = lane e's env
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + (size_t)stages * kStageBytes + (OM ? kObsStage : 0u));
-  uint32_t* cfw = reinterpret_cast<uint32_t*>(bars + kMaxStages) + lane;       // this lane's word w at [w * 32]
-  uint32_t* oobw = cfw + s.Wd * 32;
-  uint32_t* dfw = oobw + s.Wd * 32;                                            // FAITHFUL only
-  if (lane == 0) {
-    for (int q = 0; q < stages; ++q) mbar_init(&bars[q], 1);
-    mbar_fence_init();
-  }
-  __syncwarp();
-  uint32_t phase = 0;                                     // bit q: parity the next wait on slot q expects
-  const int n_tiles = s.T;
-  const int n_pairs = s.N >> 1;                           // units holding two intruders
-  const int n_st = (s.U + G - 1) / G;                     // pipeline stages per tile
-  const bool single_wave = (int)(gridDim.x * kWarpsPerBlock) >= n_tiles;
-  bool first_pass = true;
-
-  for (;;) {
-    // ---- tile scheduler
-    int tile = 0;
-    if (single_wave) {                                    // every tile has its own resident warp
-      tile = first_pass ? (int)(blockIdx.x * kWarpsPerBlock + warp_in_block) : n_tiles;
-      first_pass = false;
-    } else {
-      if (lane == 0) tile = (int)atomicAdd(&s.sched[0], 1u);
-      tile = __shfl_sync(FULL, tile, 0);
-    }
-    if (tile >= n_tiles) break;
-    const size_t env0 = (size_t)tile * 32;
-    const bool has_env = env0 + lane < (size_t)s.B;
-    const size_t me = has_env ? env0 + lane : env0;
-    const uint8_t* tpos = s.ipos + (size_t)tile * s.U * (512u * kPosUnits);   // this tile's planes
-    const uint8_t* tvel = s.ivel + (size_t)tile * s.U * 512u;
-
-    GCA_STAMP(0);
+  const size_t env0 = (size_t)tile * 32;
+  const bool has_env = env0 + lane < (size_t)s.B;
+  const size_t me = has_env ? env0 + lane : env0;
 #ifdef GCA_PHASE_TIMING
-    if (lane == 0 && tile < 8192) {
-      unsigned smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      g_phase_stamps[tile * 8 + 7] = smid;
-    }
+  const unsigned long long fin_t0 = gtime();
+  int fin_respawns = 0, fin_resets = 0;
 #endif
-    // ---- start streaming the first stages of the tile before any arithmetic
-    auto issue_stage = [&](int q, int st) {
-      const int u0 = st * G;
-      const uint32_t nu = (uint32_t)min(G, s.U - u0);
-      uint8_t* dst = ring + (size_t)q * kStageBytes;
-      mbar_expect_tx(&bars[q], nu * 512u * (kPosUnits + 1u));
-      tma_load_1d(dst, tpos + (size_t)u0 * (512u * kPosUnits), nu * 512u * kPosUnits, &bars[q]);
-      tma_load_1d(dst + kStagePos, tvel + (size_t)u0 * 512u, nu * 512u, &bars[q]);
-    };
-    if (lane == 0) {
-      const int pre = n_st < stages ? n_st : stages;
-      for (int q = 0; q < pre; ++q) issue_stage(q, q);
-    }
-    // this lane's flag words -> shared memory (each lane only ever touches its own column)
-    for (int w = 0; w < s.W; ++w) {
-      const size_t fi = ((size_t)tile * s.Wd + w) * 32 + lane;
-      cfw[w * 32] = s.cflag[fi];
-      oobw[w * 32] = 0u;
-      if constexpr (FAITH) dfw[w * 32] = s.dflag[fi];
-    }
 
-    // -------------------------------------------------------------- phase A: ownship
-    float2 pos = make_float2(0.f, 0.f);
-    double2 hs = make_double2(0., 0.), vel = make_double2(0., 0.), goal = make_double2(0., 0.);
-    int4 cnt = make_int4(0, 0, 0, 0);
-    bool maxstep_hit = false;
-    Draws<TAPE> d;
-    if constexpr (TAPE) {
-      d.tape = nullptr;
-      d.cur = 0;
-    } else {
-      d.k0 = a.key0; d.k1 = a.key1; d.env = 0; d.tick = 0;
-    }
-    if (has_env) {
-      pos = s.own_pos[me];
-      hs = s.own_hs[me];
-      goal = s.goal[me];
-      cnt = s.counters[me];
-      if constexpr (TAPE) {
-        d.tape = a.tape + me * (size_t)a.tape_stride;
-        d.cur = a.cursor[me];
-      } else {
-        d.env = a.env_id0 + (uint32_t)me;
-        d.tick = (uint32_t)cnt.z;
-      }
-      // Ownship.step(a)   PKG/SingleAircraftEnv.py:299-309 (2Env :291-301, DiscreteHER :301-311)
-      double f0, f1 = 0.0;
-      if (c.action_kind == GCA_ACT_CONTINUOUS2) {
-        const R* act = reinterpret_cast<const R*>(a.actions) + 2 * me;
-        f0 = (double)act[0];
-        f1 = (double)act[1];
-      } else {
-        const int act = reinterpret_cast<const int*>(a.actions)[me];
-        if (c.action_kind == GCA_ACT_DISCRETE9) {
-          f0 = (double)(act / 3 - 1);
-          f1 = (double)(act % 3 - 1);
-        } else {
-          f0 = (double)(act - 1);
+  float2 pos = make_float2(0.f, 0.f);
+  double2 hs = make_double2(0., 0.), vel = make_double2(0., 0.), goal = make_double2(0., 0.);
+  int4 cnt = make_int4(0, 0, 0, 0);
+  int stop = INT_MAX;
+  constexpr int kWordsAhead = 4;                          // N <= 128: the env's event / flag words live in registers
+  uint32_t wc[kWordsAhead], wg[kWordsAhead], wf[kWordsAhead];
+#pragma unroll
+  for (int w = 0; w < kWordsAhead; ++w) wc[w] = wg[w] = wf[w] = 0u;
+  if (has_env) {
+    // everything this lane needs is requested before any of it is looked at: one round trip
+    pos = s.own_pos[me];
+    hs = s.own_hs[me];
+    vel = s.own_vel[me];
+    goal = s.goal[me];
+    cnt = s.counters[me];
+    if (s.N > 0) {
+      stop = __ldcg(&s.ev_nmac[me]);
+#pragma unroll
+      for (int w = 0; w < kWordsAhead; ++w) {
+        if (w < s.W) {
+          const size_t fi = flag_index(s, me, w);
+          wc[w] = __ldcg(&s.ev_conf[fi]);
+          wg[w] = __ldcg(&s.ev_gone[fi]);
+          wf[w] = s.cflag[fi];
         }
       }
-      // The rest of the tile's planes start moving from HBM into L2 now, behind this
-      // lane's own state loads, so that the DRAM channels work through phase A (FP64-bound, no traffic of its own).
-      if (!(a.debug_skip & 8) && n_st > stages) {
-        const uint32_t total_pos = (uint32_t)s.U * 512u * kPosUnits, total_vel = (uint32_t)s.U * 512u;
-        const uint32_t done_pos = (uint32_t)stages * kStagePos, done_vel = (uint32_t)stages * G * 512u;
-        // 32 lanes split the remainder in 512-byte aligned pieces
-        const uint32_t rem_pos = total_pos - done_pos, rem_vel = total_vel - done_vel;
-        const uint32_t piece_pos = ((rem_pos / 32u) + 511u) & ~511u, piece_vel = ((rem_vel / 32u) + 511u) & ~511u;
-        const uint32_t o_pos = lane * piece_pos, o_vel = lane * piece_vel;
-        if (o_pos < rem_pos) tma_prefetch_l2(tpos + done_pos + o_pos, min(piece_pos, rem_pos - o_pos));
-        if (o_vel < rem_vel) tma_prefetch_l2(tvel + done_vel + o_vel, min(piece_vel, rem_vel - o_vel));
-      }
-      double nh, ns, sn, cs;
-      draw_own_noise(d, c, nh, ns);
-      double heading = __dadd_rn(hs.x, __dmul_rn(c.d_heading, f0));
-      heading = __dadd_rn(heading, nh);
-      double speed = c.action_kind == GCA_ACT_DISCRETE3 ? __dadd_rn(hs.y, c.speed_sigma)      // reference quirk Q16
-                                                        : __dadd_rn(hs.y, __dmul_rn(c.d_speed, f1));
-      const double m = c.max_speed < speed ? c.max_speed : speed;     // min(speed, max_speed)
-      speed = m > c.min_speed ? m : c.min_speed;                      // max(min_speed, .)
-      speed = __dadd_rn(speed, ns);                                   // noise after the clamp (Q5)
-      gca_sincos(heading, &sn, &cs);
-      vel = make_double2(__dmul_rn(speed, cs), __dmul_rn(speed, sn));
-      hs = make_double2(heading, speed);
-      pos = make_float2((float)__dadd_rn((double)pos.x, vel.x), (float)__dadd_rn((double)pos.y, vel.y));
-      cnt.y += 1;                                                     // StackEnv :118
-      maxstep_hit = c.max_steps > 0 && cnt.y >= c.max_steps;          // StackEnv :134-136
-      s.own_pos[me] = pos;
-      s.own_hs[me] = hs;
-      s.own_vel[me] = vel;
-      s.own_vel_f32[me] = 0;
     }
+  }
+  Draws<TAPE> d = make_draws<TAPE>(a, me, (uint32_t)cnt.z);
+#ifdef GCA_PHASE_TIMING
+  unsigned long long fin_t1 = 0, fin_t2 = 0, fin_t3 = 0;
+  if (__any_sync(FULL, cnt.z + stop + (int)wc[0] + (int)wg[0] + (int)wf[0] + (int)goal.x == -12345)) fin_t1 = 1;   // consume the loads
+  fin_t1 += gtime();
+#endif
+  const int cur = cnt.z & 1, nxt = cur ^ 1;               // nxt: the plane this step wrote = the env's next current plane
+  const bool maxstep_hit = c.max_steps > 0 && cnt.y >= c.max_steps;
+  const bool replay = has_env && !maxstep_hit && s.N > 0; // the reference's intruder loop ran for this env
+  R* obase = obs_intruder_base<FAITH>(a, me);
+  // the loop (PKG/SingleAircraftEnv.py:149-170) returned right after intruder `stop` (Q9): later events never happened
+  const bool nmac = replay && stop != INT_MAX;
+  bool conf_any = false;
+  int newconf = 0;
+  const bool words_in_regs = s.W <= kWordsAhead;
+  const bool compact = !TAPE && words_in_regs && s.N > 0 && s.B <= (1 << 24);   // PHILOX draws do not depend on the visiting order
 
-    GCA_STAMP(1);
-    // -------------------------------------------------------------- phase B: this lane's intruders, in index order
-    bool alive = has_env && !maxstep_hit;   // false once the reference's loop has returned (NMAC, Q9) or never ran (max steps)
-    bool nmac = false, conf = false;
-    bool dirty = false;                     // a flag word or an out-of-map word of this env changed
-    int newconf = 0;                        // False -> True transitions of Aircraft.conflict   :161-163
-    R* obase = obs_intruder_base<FAITH>(a, me);
-    uint8_t* gpos = s.ipos + ((size_t)tile * s.U * kPosUnits * 32 + lane) * 16;       // unit u at + u * 512 * kPosUnits
-    const float ox = pos.x, oy = pos.y;
-    const uint32_t wbits = __float_as_uint(k.win_w), hbits = __float_as_uint(k.win_h);
+  auto visited_mask = [&](int w) -> uint32_t {
+    const int lo = w * 32;
+    return stop >= lo + 31 ? 0xffffffffu : (stop < lo ? 0u : (2u << (stop - lo)) - 1u);
+  };
+  // reset_intruder() for intruder i of this lane's env   :153-154, :229-238
+  auto respawn_own = [&](int i, uint32_t& set64) {
+    Intr<FAITH> it;
+    spawn<FAITH, TAPE>(d, c, k, (uint32_t)i, pos.x, pos.y, it);
+    store_ipos<FAITH>(s, nxt, me, i, it);
+    store_ivel(s, me, i, it.vx, it.vy);
+    set64 |= (it.is64 ? 1u : 0u) << (i & 31);
+    write_obs_intruder<FAITH>(a, obase, i, it);
+  };
 
-    for (int st = 0; st < n_st; ++st) {
-      const int q = st & (stages - 1);                              // stages is a power of two
-      GCA_STAGE_STAMP(0);
-      mbar_wait(&bars[q], (phase >> q) & 1u);
-      phase ^= 1u << q;
-      GCA_STAGE_STAMP(1);
-      const uint8_t* sp = ring + (size_t)q * kStageBytes + lane * 16;   // unit g of this stage at + g * 512 (* kPosUnits)
-      const uint8_t* sv = sp + kStagePos;
-      const int u0 = st * G;
-      uint32_t gone = 0;                                            // bit j: intruder 2*u0 + j left the map
-
-      // One iteration of the reference's loop body for intruder i (PKG/SingleAircraftEnv.py:149-170), verbatim;
-      // taken when the streamlined path below saw a conflict in the unit or the loop has already returned.
-      auto visit_slow = [&](int i, const Intr<FAITH>& old) {
-        if (!alive) {                                               // not touched this step: observed where it was
-          write_obs_intruder<FAITH>(a, obase, i, old);
-          return;
-        }
-        Intr<FAITH> nx = old;
-        const bool oob = advance<FAITH>(k, nx);                     // intruder.position += velocity :150, map test :153
-        bool lt_sep, lt_nmac, lt_init;
-        separation<FAITH>(k, ox, oy, nx, lt_sep, lt_nmac, lt_init); // dist(drone, intruder) :151
-        if (oob) {                                                  // replaced by reset_intruder() in phase C :153-154
-          gone |= 1u << (i - 2 * u0);
-        } else {
-          store_ipos<FAITH>(s, me, i, nx);
-          write_obs_intruder<FAITH>(a, obase, i, nx);
-        }
-        if (lt_sep) {                                               // the old object's distance and flag (Q7) :157-163
-          conf = true;
-          const uint32_t bit = 1u << (i & 31), f = cfw[(i >> 5) * 32];
-          if (!(f & bit)) {
-            newconf += 1;
-            cfw[(i >> 5) * 32] = f | bit;
-            dirty = true;
-          }
-          if (lt_nmac) {                                            // return inside the loop :169-170
-            nmac = true;
-            alive = false;
-          }
-        }
-      };
-
-      // the exact path for unit g (dynamic index): both intruders through the reference's loop body
-      auto careful_unit = [&](int g) {
-        const int i0 = 2 * (u0 + g);
-        const float4 vv = *reinterpret_cast<const float4*>(sv + g * 512);
-        Intr<FAITH> o0, o1;
-        o0.vx = vv.x; o0.vy = vv.y; o1.vx = vv.z; o1.vy = vv.w;
-        if constexpr (FAITH) {
-          const double2 p0 = *reinterpret_cast<const double2*>(sp + (2 * g) * 512);
-          const double2 p1 = *reinterpret_cast<const double2*>(sp + (2 * g + 1) * 512);
-          const uint32_t dw = dfw[(i0 >> 5) * 32];
-          o0.px = p0.x; o0.py = p0.y; o1.px = p1.x; o1.py = p1.y;
-          o0.is64 = (dw >> (i0 & 31)) & 1u;
-          o1.is64 = (dw >> ((i0 + 1) & 31)) & 1u;
-        } else {
-          const float4 p = *reinterpret_cast<const float4*>(sp + g * 512);
-          o0.px = p.x; o0.py = p.y; o1.px = p.z; o1.py = p.w;
-        }
-        visit_slow(i0, o0);
-        visit_slow(i0 + 1, o1);
-      };
-
-      bool streamlined = false;
-      if (has_env) {
-        const int nu = min(G, n_pairs - u0);                        // full units (two intruders) of this stage
-        if (nu == G) {
-          // The streamlined path: all 2G intruders of the stage at once, straight-line.  It applies when the
-          // reference's loop is still running for this env and no intruder of the stage is inside the separation
-          // radius.  An intruder that leaves the map is only recorded (`gone`): its slot is refilled in phase C,
-          // which also rewrites its position and observation entries.
-          bool ev = !alive;
-          uint32_t g_gone = 0;
-          if constexpr (FAITH) {
-            Intr<FAITH> n[2 * G];
+  if (replay) {
+    if (words_in_regs) {
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-              const int i0 = 2 * (u0 + g);
-              const float4 vv = *reinterpret_cast<const float4*>(sv + g * 512);
-              const double2 p0 = *reinterpret_cast<const double2*>(sp + (2 * g) * 512);
-              const double2 p1 = *reinterpret_cast<const double2*>(sp + (2 * g + 1) * 512);
-              const uint32_t dw = dfw[(i0 >> 5) * 32];
-              Intr<FAITH>& n0 = n[2 * g];
-              Intr<FAITH>& n1 = n[2 * g + 1];
-              n0.vx = vv.x; n0.vy = vv.y; n1.vx = vv.z; n1.vy = vv.w;
-              n0.px = p0.x; n0.py = p0.y; n1.px = p1.x; n1.py = p1.y;
-              n0.is64 = (dw >> (i0 & 31)) & 1u;
-              n1.is64 = (dw >> ((i0 + 1) & 31)) & 1u;
-              const bool oob0 = advance<FAITH>(k, n0), oob1 = advance<FAITH>(k, n1);
-              bool sep0, sep1, t0, t1;
-              separation<FAITH>(k, ox, oy, n0, sep0, t0, t1);
-              separation<FAITH>(k, ox, oy, n1, sep1, t0, t1);
-              ev |= sep0 | sep1;
-              g_gone |= ((oob0 ? 1u : 0u) | (oob1 ? 2u : 0u)) << (2 * g);
-            }
-            if (!ev) {
-              streamlined = true;
-#pragma unroll
-              for (int g = 0; g < G; ++g) {
-                const int u = u0 + g;
-                *reinterpret_cast<double2*>(gpos + (size_t)(2 * u) * 512) = make_double2(n[2 * g].px, n[2 * g].py);
-                *reinterpret_cast<double2*>(gpos + (size_t)(2 * u + 1) * 512) = make_double2(n[2 * g + 1].px, n[2 * g + 1].py);
-                write_obs_intruder<FAITH>(a, obase, 2 * u, n[2 * g]);
-                write_obs_intruder<FAITH>(a, obase, 2 * u + 1, n[2 * g + 1]);
-              }
-            }
-          } else {
-            float4 np[G], vv[G];
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-              const float4 p = *reinterpret_cast<const float4*>(sp + g * 512);
-              vv[g] = *reinterpret_cast<const float4*>(sv + g * 512);
-              np[g] = make_float4(__fadd_rn(p.x, vv[g].x), __fadd_rn(p.y, vv[g].y),      // position += velocity :150
-                                  __fadd_rn(p.z, vv[g].z), __fadd_rn(p.w, vv[g].w));
-            }
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-              // 0 <= x <= W on f32 bit patterns: a non-negative float is <= W iff its pattern is (as unsigned);
-              // negatives and NaN have larger patterns (FAST positions are never -0.0, see gca_set_state).
-              const bool oob0 = (__float_as_uint(np[g].x) > wbits) | (__float_as_uint(np[g].y) > hbits);
-              const bool oob1 = (__float_as_uint(np[g].z) > wbits) | (__float_as_uint(np[g].w) > hbits);
-              g_gone |= ((oob0 ? 1u : 0u) | (oob1 ? 2u : 0u)) << (2 * g);
-              ev |= (dist2_f32(ox, oy, np[g].x, np[g].y) < k.sep2_f) | (dist2_f32(ox, oy, np[g].z, np[g].w) < k.sep2_f);
-            }
-            if (!ev) {
-              streamlined = true;
-#pragma unroll
-              for (int g = 0; g < G; ++g)
-                if (!(a.debug_skip & 2)) *reinterpret_cast<float4*>(gpos + (size_t)(u0 + g) * 512) = np[g];
-              if constexpr (OM == 1) {
-                // the observation entries go to this lane's staging row; the warp writes the rows out below
-                float4* row = reinterpret_cast<float4*>(stg + lane * kObsRow);
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-                  row[2 * g] = obs_intruder_vec(k, np[g].x, np[g].y, vv[g].x, vv[g].y);
-                  row[2 * g + 1] = obs_intruder_vec(k, np[g].z, np[g].w, vv[g].z, vv[g].w);
-                }
-              } else {
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-                  const int u = u0 + g;
-                  Intr<FAITH> n0, n1;
-                  n0.px = np[g].x; n0.py = np[g].y; n0.vx = vv[g].x; n0.vy = vv[g].y;
-                  n1.px = np[g].z; n1.py = np[g].w; n1.vx = vv[g].z; n1.vy = vv[g].w;
-                  write_obs_intruder<FAITH>(a, obase, 2 * u, n0);
-                  write_obs_intruder<FAITH>(a, obase, 2 * u + 1, n1);
-                }
-              }
-            }
-          }
-          if (streamlined) gone = g_gone;
-        }
-        if (!streamlined) {
-#pragma unroll 1
-          for (int g = 0; g < nu; ++g) careful_unit(g);
-          if ((s.N & 1) && st == n_st - 1) {                        // odd N: the last unit holds one intruder
-            const int g = s.U - 1 - u0, i = s.N - 1;
-            const float2 vv = *reinterpret_cast<const float2*>(sv + g * 512);
-            Intr<FAITH> o;
-            o.vx = vv.x; o.vy = vv.y;
-            if constexpr (FAITH) {
-              const double2 p = *reinterpret_cast<const double2*>(sp + (2 * g) * 512);
-              o.px = p.x; o.py = p.y;
-              o.is64 = (dfw[(i >> 5) * 32] >> (i & 31)) & 1u;
-            } else {
-              const float2 p = *reinterpret_cast<const float2*>(sp + g * 512);
-              o.px = p.x; o.py = p.y;
-            }
-            visit_slow(i, o);
-          }
-        }
-        if (gone) {                                                 // a stage never straddles a 32-intruder word (G | 16)
-          oobw[((2 * u0) >> 5) * 32] |= gone << ((2 * u0) & 31);
-          dirty = true;
-        }
-      }
-      // the slot is free again: stream the stage that is `stages` ahead into it
-      __syncwarp();
-      GCA_STAGE_STAMP(2);
-      if (lane == 0 && st + stages < n_st) issue_stage(q, st + stages);
-      if constexpr (OM == 1) {
-        // Write-out of the staged observation entries, transposed: 2G consecutive lanes store the 2G x 16 contiguous
-        // bytes of ONE env's row, so every store instruction covers whole 32-byte sectors of 16/G rows instead of
-        // 32 half sectors 1312 bytes apart.  Rows of lanes that took the exact path were written there.
-        const uint32_t staged = __ballot_sync(FULL, streamlined);
-        if (staged && !(a.debug_skip & 1)) {
-          constexpr int kLanesPerEnv = 2 * G, kEnvsPerStore = 32 / kLanesPerEnv;
-          const int sub = lane / kLanesPerEnv, chunk = lane % kLanesPerEnv;
-          const uint8_t* src = stg + sub * kObsRow + chunk * 16;
-          float* dst = reinterpret_cast<float*>(a.obs) + (env0 + sub) * (size_t)a.D + 4 * (size_t)(2 * u0 + chunk);
-          const size_t dstep = (size_t)kEnvsPerStore * a.D;
-#pragma unroll
-          for (int it = 0; it < kLanesPerEnv; ++it) {
-            const float4 val = *reinterpret_cast<const float4*>(src + it * kEnvsPerStore * kObsRow);
-            if (a.debug_skip & 4) {   // experiment: same bytes, written as one contiguous 1024*G-byte block per stage
-              *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(a.obs) + env0 * (size_t)a.D * 4 + (size_t)st * (1024 * G) + it * 512 + lane * 16) = val;
-            } else
-            if ((staged >> (it * kEnvsPerStore + sub)) & 1u) *reinterpret_cast<float4*>(dst + it * dstep) = val;
-          }
-          __syncwarp();                                             // staging rows are rewritten by the next stage
-        }
-      }
-      GCA_STAGE_STAMP(3);
-    }
-
-    GCA_STAMP(2);
-    // -------------------------------------------------------------- phase C: respawn, reward
-    bool done = false;
-    if (has_env) {
-      if (dirty) {
-        // reset_intruder() for every intruder that left the map, in index order   :153-154, :229-238
-        for (int w = 0; w < s.W; ++w) {
-          const uint32_t gone = oobw[w * 32];
-          uint32_t rest = gone, set64 = 0;
+      for (int w = 0; w < kWordsAhead; ++w) {
+        const uint32_t vis = visited_mask(w);
+        const uint32_t conf = wc[w] & vis, gone = wg[w] & vis, cf = wf[w];
+        wg[w] = gone;
+        if ((conf | gone) == 0u) continue;
+        const size_t fi = flag_index(s, me, w);
+        newconf += __popc(conf & ~cf);                    // False -> True transitions :161-163 (old object's flag, Q7)
+        conf_any |= conf != 0u;
+        const uint32_t ncf = (cf | conf) & ~gone;         // the flag never clears (Q8); a replaced intruder starts False
+        if (ncf != cf) s.cflag[fi] = ncf;
+        uint32_t set64 = 0;
+        if (!compact) {                                   // TAPE: this lane replays its env's draws in index order
+          uint32_t rest = gone;
           while (rest) {
             const int j = __ffs(rest) - 1;
             rest &= rest - 1;
-            const int i = w * 32 + j;
-            Intr<FAITH> it;
-            spawn<FAITH, TAPE>(d, c, k, (uint32_t)i, pos.x, pos.y, it);
-            store_ipos<FAITH>(s, me, i, it);
-            store_ivel(s, me, i, it.vx, it.vy);
-            set64 |= (it.is64 ? 1u : 0u) << j;
-            write_obs_intruder<FAITH>(a, obase, i, it);
-          }
-          const size_t fi = ((size_t)tile * s.Wd + w) * 32 + lane;
-          s.cflag[fi] = cfw[w * 32] & ~gone;                          // a replaced intruder starts with conflict False
-          if constexpr (FAITH) {
-            if (gone) s.dflag[fi] = (dfw[w * 32] & ~gone) | set64;
+            respawn_own(w * 32 + j, set64);
           }
         }
-      }
-      cnt.x += newconf;
-      // _terminal_reward()   :143-184 and the variant rows of SURVEY.md 8(a)
-      double reward;
-      int info;
-      if (maxstep_hit) {
-        reward = 0.0; done = true; info = GCA_INFO_MAXSTEPS;
-      } else if (nmac) {
-        reward = c.r_nmac; done = true; info = GCA_INFO_NMAC;
-      } else if (conf) {
-        reward = c.r_conflict; info = GCA_INFO_CONFLICT;
-      } else if (c.wall_kind != GCA_WALL_NONE && !in_map_f32(k, pos.x, pos.y)) {
-        reward = c.r_wall; done = c.wall_kind == GCA_WALL_TERMINAL; info = GCA_INFO_WALL;
-      } else {
-        const double dg = dist_f64((double)pos.x, (double)pos.y, goal.x, goal.y);
-        if (dg < c.goal_radius) {
-          reward = c.r_goal; done = true; info = GCA_INFO_GOAL;
-        } else {
-          reward = c.shaped_default ? __ddiv_rn(-dg, 1200.0) : c.r_default;
-          info = GCA_INFO_NONE;
+        if constexpr (FAITH) {
+          if (gone) s.dflag[fi] = (s.dflag[fi] & ~gone) | set64;
         }
       }
-      if (c.time_limit > 0 && cnt.y >= c.time_limit) done = true;    // gym TimeLimit of the registered ids
-      reinterpret_cast<R*>(a.reward)[me] = (R)reward;
-      a.done[me] = done ? 1 : 0;
-      a.info[me] = (uint8_t)info;
-      write_obs_own<FAITH>(a, me, pos.x, pos.y, vel.x, vel.y, false, hs.x, hs.y, goal.x, goal.y);   // :115-124
+    } else {
+      for (int w = 0; w < s.W; ++w) {                     // N > 128: word by word
+        const uint32_t vis = visited_mask(w);
+        const size_t fi = flag_index(s, me, w);
+        const uint32_t conf = __ldcg(&s.ev_conf[fi]) & vis, gone = __ldcg(&s.ev_gone[fi]) & vis;
+        if ((conf | gone) == 0u) continue;
+        const uint32_t cf = s.cflag[fi];
+        newconf += __popc(conf & ~cf);
+        conf_any |= conf != 0u;
+        const uint32_t ncf = (cf | conf) & ~gone;
+        if (ncf != cf) s.cflag[fi] = ncf;
+        uint32_t rest = gone, set64 = 0;
+        while (rest) {
+          const int j = __ffs(rest) - 1;
+          rest &= rest - 1;
+          respawn_own(w * 32 + j, set64);
+        }
+        if constexpr (FAITH) {
+          if (gone) s.dflag[fi] = (s.dflag[fi] & ~gone) | set64;
+        }
+      }
     }
+  }
+#ifdef GCA_PHASE_TIMING
+  fin_t2 = gtime();
+#endif
+  bool done = false;
+  if (has_env) {
+    if (nmac && !a.auto_reset) {
+      // intruders after `stop` were never touched by the reference: put them back where they were
+      // (under auto-reset the env is finished and all of its intruders are about to be replaced)
+      for (int i = stop + 1; i < s.N; ++i) {
+        Intr<FAITH> old;
+        load_intruder<FAITH>(s, cur, me, i, old);
+        store_ipos<FAITH>(s, nxt, me, i, old);
+        write_obs_intruder<FAITH>(a, obase, i, old);
+      }
+    }
+    cnt.x += newconf;
+    // _terminal_reward()   :143-184 and the variant rows of SURVEY.md 8(a)
+    double reward;
+    int info;
+    if (maxstep_hit) {
+      reward = 0.0; done = true; info = GCA_INFO_MAXSTEPS;
+    } else if (nmac) {
+      reward = c.r_nmac; done = true; info = GCA_INFO_NMAC;
+    } else if (conf_any) {
+      reward = c.r_conflict; info = GCA_INFO_CONFLICT;
+    } else if (c.wall_kind != GCA_WALL_NONE && !in_map_f32(k, pos.x, pos.y)) {
+      reward = c.r_wall; done = c.wall_kind == GCA_WALL_TERMINAL; info = GCA_INFO_WALL;
+    } else {
+      const double dg = dist_f64((double)pos.x, (double)pos.y, goal.x, goal.y);
+      if (dg < c.goal_radius) {
+        reward = c.r_goal; done = true; info = GCA_INFO_GOAL;
+      } else {
+        reward = c.shaped_default ? __ddiv_rn(-dg, 1200.0) : c.r_default;
+        info = GCA_INFO_NONE;
+      }
+    }
+    if (c.time_limit > 0 && cnt.y >= c.time_limit) done = true;    // gym TimeLimit of the registered ids
+    reinterpret_cast<R*>(a.reward)[me] = (R)reward;
+    a.done[me] = done ? 1 : 0;
+    a.info[me] = (uint8_t)info;
+    if (!(done && a.auto_reset))                                   // (a finished env shows its reset observation, below)
+      write_obs_own<FAITH>(a, me, pos.x, pos.y, vel.x, vel.y, false, hs.x, hs.y, goal.x, goal.y);   // :115-124
+  }
 
-    GCA_STAMP(3);
-    // -------------------------------------------------------------- phase D: VecEnv auto-reset
-    // baselines dummy_vec_env.py:52-55: the observation handed back for a finished env is reset()'s
-    uint32_t dmask = a.auto_reset ? __ballot_sync(FULL, has_env && done) : 0u;
-    while (dmask) {
+  if constexpr (!TAPE) {
+    if (compact) {
+      // PHILOX: a respawn depends on nothing but (env, tick, intruder) and the ownship position, so the spawns
+      // (FP64-heavy, 0-3 per env) are not done here, one lane per env, but queued for spawn_kernel, which runs one
+      // lane per spawn over the whole batch.  A finished env under auto-reset gets all new intruders anyway.
+      int mine = 0;
+      if (replay && !(done && a.auto_reset)) mine = __popc(wg[0]) + __popc(wg[1]) + __popc(wg[2]) + __popc(wg[3]);
+      int off = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, off, o);
+        if (lane >= o) off += t;
+      }
+      const int total = __shfl_sync(FULL, off, 31);
+      off -= mine;
+      if (total > 0) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(s.respawn_count, total);
+        base = __shfl_sync(FULL, base, 0);
+        if (mine > 0) {
+          uint32_t set64_own[kWordsAhead] = {0u, 0u, 0u, 0u};
+          int at = base + off;
+#pragma unroll
+          for (int w = 0; w < kWordsAhead; ++w) {
+            uint32_t rest = wg[w];
+            while (rest) {
+              const int j = __ffs(rest) - 1;
+              rest &= rest - 1;
+              if (at < s.respawn_cap) s.respawn_list[at] = ((uint32_t)me << 8) | (uint32_t)(w * 32 + j);
+              else respawn_own(w * 32 + j, set64_own[w]);   // (list full: more than 4 respawns per env on average)
+              ++at;
+            }
+          }
+          if constexpr (FAITH) {
+#pragma unroll
+            for (int w = 0; w < kWordsAhead; ++w)
+              if (set64_own[w]) atomicOr(&s.dflag[flag_index(s, me, w)], set64_own[w]);
+          }
+        }
+      }
+    }
+  }
+#ifdef GCA_PHASE_TIMING
+  fin_t3 = gtime();
+#endif
+  // ---- VecEnv auto-reset: the observation handed back for a finished env is reset()'s (dummy_vec_env.py:52-55)
+  const bool resets = a.auto_reset && has_env && done;
+  if constexpr (TAPE) {
+    uint32_t dmask = __ballot_sync(FULL, resets);
+    while (dmask) {                                                 // the tape is sequential: one env at a time
       const int e = __ffs(dmask) - 1;
       dmask &= dmask - 1;
-      const size_t env = env0 + e;
-      __syncwarp();                                                   // lane e's phase B/C stores come first
+      __syncwarp();                                                 // lane e's stores above come first
       Draws<TAPE> de = d;
-      if constexpr (!TAPE) {
-        de.env = __shfl_sync(FULL, d.env, e);
-        de.tick = __shfl_sync(FULL, d.tick, e);
-      }
-      reset_env_warp<FAITH, TAPE>(a, env, lane, e, de, goal);
-      if (lane == e) {
-        if constexpr (TAPE) d = de;
-        reset_ownship(c, pos, hs, vel);
-        s.own_pos[me] = pos;
-        s.own_hs[me] = hs;
-        s.own_vel[me] = vel;
-        s.own_vel_f32[me] = 1;
-        s.goal[me] = goal;
-        cnt.x = 0;
-        cnt.y = 0;
-        cnt.w += 1;
-        write_obs_own<FAITH>(a, me, pos.x, pos.y, vel.x, vel.y, true, hs.x, hs.y, goal.x, goal.y);
-      }
+      const int plane = __shfl_sync(FULL, nxt, e);
+      reset_env_warp<FAITH, TAPE>(a, env0 + e, plane, lane, e, de, goal);
+      if (lane == e) d = de;
     }
-    if (has_env) {
-      cnt.z += 1;                                                     // Philox tick
-      s.counters[me] = cnt;
-      if constexpr (TAPE) a.cursor[me] = d.cur;
+  } else {
+    // PHILOX: the 80 spawns of each finished env are independent of everything else; they are queued for
+    // reset_spawn_kernel (one warp per 32 of them, all finished envs of the batch at once) instead of
+    // serialising this warp.  The scalar part of reset() happens here.
+    const uint32_t rmask = __ballot_sync(FULL, resets);
+    if (rmask) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(s.reset_count, __popc(rmask));
+      base = __shfl_sync(FULL, base, 0);
+      if (resets) {
+        s.reset_list[base + __popc(rmask & ((1u << lane) - 1u))] = (int)me;
+        draw_pos(d, c, GCA_SLOT_GOAL, GCA_BLOCK_POS, goal.x, goal.y);   // Goal(random_pos()) :93
+      }
+#ifdef GCA_PHASE_TIMING
+      fin_resets += __popc(rmask);
+#endif
     }
-    __syncwarp();
-    GCA_STAMP(4);
   }
+  if (resets) {
+    reset_ownship(c, pos, hs, vel);
+    s.own_pos[me] = pos;
+    s.own_hs[me] = hs;
+    s.own_vel[me] = vel;
+    s.own_vel_f32[me] = 1;
+    s.goal[me] = goal;
+    cnt.x = 0;
+    cnt.y = 0;
+    cnt.w += 1;
+    write_obs_own<FAITH>(a, me, pos.x, pos.y, vel.x, vel.y, true, hs.x, hs.y, goal.x, goal.y);
+  }
+  if (has_env) {
+    cnt.z += 1;                                                     // Philox tick; also flips the current position plane
+    s.counters[me] = cnt;
+    if constexpr (TAPE) a.cursor[me] = d.cur;
+  }
+#ifdef GCA_PHASE_TIMING
+  if (lane == 0 && tile < 2048) {
+    g_fin[tile * 8 + 0] = fin_t0; g_fin[tile * 8 + 1] = gtime(); g_fin[tile * 8 + 2] = fin_respawns; g_fin[tile * 8 + 3] = fin_resets;
+    g_fin[tile * 8 + 4] = fin_t1; g_fin[tile * 8 + 5] = fin_t2; g_fin[tile * 8 + 6] = fin_t3;
+  }
+#endif
+}
 
-  // ---- last warp out re-arms the scheduler for the next launch
-  if (!single_wave && lane == 0) {
-    const unsigned total = gridDim.x * kWarpsPerBlock;
-    const unsigned prev = atomicAdd(&s.sched[1], 1u);
-    if (prev == total - 1) {
-      s.sched[0] = 0u;
-      s.sched[1] = 0u;
-      __threadfence();
+// Every spawn of the step (PHILOX; queued by finish_tile): the respawns of intruders that left the map, one lane
+// each, and the N intruders of every env that finished under auto-reset, one warp per 32 of them.  Runs after the
+// streaming pass; the envs' ticks have already been incremented.
+template <bool FAITH>
+__global__ void __launch_bounds__(128) spawn_kernel(const __grid_constant__ StepArgs a) {
+  if (PDL_EARLY) pdl_launch_dependents();
+  pdl_wait();
+  GCA_KSTAMP_IN(3);
+  const DevState& s = a.s;
+  const int lane = threadIdx.x & 31;
+  const int n_warps = gridDim.x * 4, rounds = s.W;
+  const int n_resp = min(*s.respawn_count, s.respawn_cap);
+  const long long resp_warps = (n_resp + 31) / 32, total = resp_warps + (long long)(*s.reset_count) * rounds;
+  for (long long job = (long long)blockIdx.x * 4 + (threadIdx.x >> 5); job < total; job += n_warps) {
+    Draws<false> d;
+    d.k0 = a.key0; d.k1 = a.key1;
+    if (job < resp_warps) {
+      // reset_intruder()   PKG/SingleAircraftEnv.py:153-154, :229-238
+      const int at = (int)job * 32 + lane;
+      if (at < n_resp) {
+        const uint32_t rec = s.respawn_list[at];
+        const size_t env = rec >> 8;
+        const int i = (int)(rec & 0xffu);
+        const int4 cnt = s.counters[env];
+        const float2 own = s.own_pos[env];
+        d.env = a.env_id0 + (uint32_t)env;
+        d.tick = (uint32_t)cnt.z - 1u;                      // the tick of the step that lost the intruder
+        Intr<FAITH> it;
+        spawn<FAITH, false>(d, a.cfg, a.k, (uint32_t)i, own.x, own.y, it);
+        store_ipos<FAITH>(s, cnt.z & 1, env, i, it);
+        store_ivel(s, env, i, it.vx, it.vy);
+        write_obs_intruder<FAITH>(a, obs_intruder_base<FAITH>(a, env), i, it);
+        if constexpr (FAITH) {
+          if (it.is64) atomicOr(&s.dflag[flag_index(s, env, i >> 5)], 1u << (i & 31));
+        }
+      }
+    } else {
+      // reset(): the intruders   PKG/SingleAircraftEnv.py:80-88 (the scalar part happened in finish_tile)
+      const long long rj = job - resp_warps;
+      const size_t env = (size_t)s.reset_list[rj / rounds];
+      const int r = (int)(rj % rounds), i = r * 32 + lane;
+      const int4 cnt = s.counters[env];
+      d.env = a.env_id0 + (uint32_t)env;
+      d.tick = (uint32_t)cnt.z - 1u;                        // the tick of the step that finished the env
+      bool wide = false;
+      if (i < s.N) {
+        Intr<FAITH> it;
+        spawn<FAITH, false>(d, a.cfg, a.k, GCA_SLOT_RESET | (uint32_t)i, 50.0f, 50.0f, it);   // Ownship at (50, 50) :72-76
+        store_ipos<FAITH>(s, cnt.z & 1, env, i, it);
+        store_ivel(s, env, i, it.vx, it.vy);
+        write_obs_intruder<FAITH>(a, obs_intruder_base<FAITH>(a, env), i, it);
+        wide = it.is64;
+      }
+      const uint32_t dw = __ballot_sync(FULL, wide);
+      if (lane == 0) {
+        s.cflag[flag_index(s, env, r)] = 0u;
+        if constexpr (FAITH) s.dflag[flag_index(s, env, r)] = dw;
+      }
     }
   }
+  GCA_KSTAMP_OUT(3);
 }
 
 template <bool FAITH, bool TAPE>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) reset_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(128) step_finish_kernel(const __grid_constant__ StepArgs a) {
+  if (PDL_EARLY) pdl_launch_dependents();
+  pdl_wait();
+  GCA_KSTAMP_IN(2);
+  const long long tile = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (tile < a.s.T) finish_tile<FAITH, TAPE>(a, (int)tile, threadIdx.x & 31, nullptr);
+  GCA_KSTAMP_OUT(2);
+}
+
+// ------------------------------------------------------------------------------ 2. intruders (the streaming pass)
+// OM: 1 = the observation is GCA_OBS_VECTOR with the one-correction division exact (the registered ids'
+// layout; FAST only): entries are computed without run-time layout tests and leave through the transposed
+// shared-memory write-out.  0 = generic (any layout, both modes): per-lane stores.
+template <bool FAITH, bool TAPE, int OM, bool FUSE>
+__global__ void __launch_bounds__(kWarpsB * 32, FUSE ? GCA_MINB : 32) step_intruders_kernel(const __grid_constant__ StepArgs a) {
+  if (PDL_EARLY) pdl_launch_dependents();
+  pdl_wait();
+  GCA_KSTAMP_IN(1);
+  using R = real_t<FAITH>;
+  static_assert(!(FAITH && OM), "the specialised observation path is FAST only");
+  constexpr uint32_t kWarpSmem = OM ? 32 * kObsRow : kJobCap * 4;    // observation staging, later the respawn job list
+  static_assert(kWarpSmem >= kJobCap * 4, "the job list reuses the staging buffer");
+  __shared__ __align__(16) uint8_t stage_smem[kWarpsB * kWarpSmem];
+  const DevState& s = a.s;
+  const Derived& k = a.k;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int n_chunks = (s.U + kChunkUnits - 1) / kChunkUnits;
+  const long long work = (long long)blockIdx.x * kWarpsB + wib;
+  if (work >= (long long)s.T * n_chunks) return;          // (no block-wide barrier below)
+  const int tile = (int)(work / n_chunks), ch = (int)(work - (long long)tile * n_chunks);
+  const size_t me = (size_t)tile * 32 + lane;
+  const bool has_env = me < (size_t)s.B;
+  const float4 ob = s.own_b[me];
+  const uint32_t bits = __float_as_uint(ob.z);
+  const bool runs = (bits & kOwnRuns) != 0;               // false: the reference's loop never ran for this env (max steps)
+  const int par = (bits & kOwnPlane) ? 1 : 0;
+  const float ox = ob.x, oy = ob.y;
+  const int u0 = ch * kChunkUnits, i0 = 2 * u0;
+  const int n_here = min(kChunkIntr, s.N - i0);           // intruders of this work item
+  constexpr size_t kPosUnits = FAITH ? 2 : 1;
+  const size_t unit0 = (size_t)tile * s.U + u0;           // first unit of this work item in the tile-planar order
+  const size_t pos_off = (unit0 * kPosUnits * 32 + lane) * 16;
+  const uint8_t* psrc = s.ipos + (size_t)par * s.pos_plane + pos_off;
+  uint8_t* pdst = s.ipos + (size_t)(par ^ 1) * s.pos_plane + pos_off;
+  const uint8_t* vsrc = s.ivel + (unit0 * 32 + lane) * 16;
+  R* obase = obs_intruder_base<FAITH>(a, me);
+  uint32_t gone = 0, conf = 0, nmac = 0;                  // bit j: intruder i0 + j
+
+  bool fast_done = false;
+  if constexpr (!FAITH) {
+    if (n_here == kChunkIntr) {
+      // ---- all 8 intruders at once, straight-line
+      fast_done = true;
+      float4 p[kChunkUnits], vv[kChunkUnits], np[kChunkUnits];
+      const uint64_t pol = l2_evict_first_policy();
+#pragma unroll
+      for (int g = 0; g < kChunkUnits; ++g) {
+        p[g] = ldg_stream(psrc + g * 512, pol);
+        vv[g] = ldg_stream(vsrc + g * 512, pol);
+      }
+      const uint32_t wbits = __float_as_uint(k.win_w), hbits = __float_as_uint(k.win_h);
+#pragma unroll
+      for (int g = 0; g < kChunkUnits; ++g) {
+        np[g] = make_float4(__fadd_rn(p[g].x, vv[g].x), __fadd_rn(p[g].y, vv[g].y),      // position += velocity :150
+                            __fadd_rn(p[g].z, vv[g].z), __fadd_rn(p[g].w, vv[g].w));
+        // 0 <= x <= W on f32 bit patterns (:153): a non-negative float is <= W iff its pattern is (as unsigned);
+        // negatives and NaN have larger patterns (FAST positions are never -0.0, see gca_set_state).
+        const bool oob0 = (__float_as_uint(np[g].x) > wbits) | (__float_as_uint(np[g].y) > hbits);
+        const bool oob1 = (__float_as_uint(np[g].z) > wbits) | (__float_as_uint(np[g].w) > hbits);
+        gone |= ((oob0 ? 1u : 0u) | (oob1 ? 2u : 0u)) << (2 * g);
+        const float d0 = dist2_f32(ox, oy, np[g].x, np[g].y), d1 = dist2_f32(ox, oy, np[g].z, np[g].w);   // :151
+        conf |= ((d0 < k.sep2_f ? 1u : 0u) | (d1 < k.sep2_f ? 2u : 0u)) << (2 * g);
+        nmac |= ((d0 < k.nmac2_f ? 1u : 0u) | (d1 < k.nmac2_f ? 2u : 0u)) << (2 * g);
+      }
+      if (!runs) {                                          // nobody moves: carry the positions over
+        gone = conf = nmac = 0;
+#pragma unroll
+        for (int g = 0; g < kChunkUnits; ++g) np[g] = p[g];
+      }
+      if (has_env) {
+#pragma unroll
+        for (int g = 0; g < kChunkUnits; ++g) stg_stream(pdst + g * 512, np[g], pol);
+      }
+      if constexpr (OM == 1) {
+        // observation entries -> this lane's staging row -> transposed write-out: 8 consecutive lanes store
+        // the 128 contiguous bytes of ONE env's row, 4 rows per store instruction.
+        uint8_t* stg = stage_smem + wib * kWarpSmem;
+        float4* row = reinterpret_cast<float4*>(stg + lane * kObsRow);
+#pragma unroll
+        for (int g = 0; g < kChunkUnits; ++g) {
+          row[2 * g] = obs_intruder_vec(k, np[g].x, np[g].y, vv[g].x, vv[g].y);
+          row[2 * g + 1] = obs_intruder_vec(k, np[g].z, np[g].w, vv[g].z, vv[g].w);
+        }
+        __syncwarp();
+        const int sub = lane >> 3, chunk = lane & 7;
+        const uint8_t* src = stg + sub * kObsRow + chunk * 16;
+        const size_t env_sub = (size_t)tile * 32 + sub;
+        float* dst = reinterpret_cast<float*>(a.obs) + env_sub * (size_t)a.D + 4 * (size_t)(i0 + chunk);
+        const size_t dstep = 4 * (size_t)a.D;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const float4 val = *reinterpret_cast<const float4*>(src + it * 4 * kObsRow);
+          if (env_sub + 4 * it < (size_t)s.B) stg_stream(dst + it * dstep, val, pol);
+        }
+      } else if (has_env) {
+#pragma unroll
+        for (int g = 0; g < kChunkUnits; ++g) {
+          Intr<FAITH> n0, n1;
+          n0.px = np[g].x; n0.py = np[g].y; n0.vx = vv[g].x; n0.vy = vv[g].y;
+          n1.px = np[g].z; n1.py = np[g].w; n1.vx = vv[g].z; n1.vy = vv[g].w;
+          write_obs_intruder<FAITH>(a, obase, i0 + 2 * g, n0);
+          write_obs_intruder<FAITH>(a, obase, i0 + 2 * g + 1, n1);
+        }
+      }
+    }
+  }
+  if (!fast_done && has_env) {
+    // ---- generic: FAITHFUL positions (f64-capable) and the ragged last work item of a tile
+    uint32_t dw = 0;
+    if constexpr (FAITH) dw = s.dflag[flag_index(s, me, i0 >> 5)] >> (i0 & 31);
+    for (int j = 0; j < n_here; ++j) {
+      const int i = i0 + j;
+      Intr<FAITH> it;
+      const float2 v = *reinterpret_cast<const float2*>(vsrc + (j >> 1) * 512 + (j & 1) * 8);
+      it.vx = v.x; it.vy = v.y;
+      if constexpr (FAITH) {
+        const double2 q = *reinterpret_cast<const double2*>(psrc + j * 512);
+        it.px = q.x; it.py = q.y;
+        it.is64 = (dw >> j) & 1u;
+      } else {
+        const float2 q = *reinterpret_cast<const float2*>(psrc + (j >> 1) * 512 + (j & 1) * 8);
+        it.px = q.x; it.py = q.y;
+      }
+      if (runs) {
+        const bool oob = advance<FAITH>(k, it);             // :150, :153
+        bool lt_sep, lt_nmac, lt_init;
+        separation<FAITH>(k, ox, oy, it, lt_sep, lt_nmac, lt_init);   // :151
+        gone |= (oob ? 1u : 0u) << j;
+        conf |= (lt_sep ? 1u : 0u) << j;
+        nmac |= (lt_nmac ? 1u : 0u) << j;
+      }
+      if constexpr (FAITH) *reinterpret_cast<double2*>(pdst + j * 512) = make_double2(it.px, it.py);
+      else *reinterpret_cast<float2*>(pdst + (j >> 1) * 512 + (j & 1) * 8) = make_float2(it.px, it.py);
+      write_obs_intruder<FAITH>(a, obase, i, it);
+    }
+  }
+  // ---- record the (rare) events; i0 is a multiple of 8, so the 8 bits never straddle a word
+  if (has_env) {
+    const size_t fi = flag_index(s, me, i0 >> 5);
+    if (gone) atomicOr(&s.ev_gone[fi], gone << (i0 & 31));
+    if (conf) atomicOr(&s.ev_conf[fi], conf << (i0 & 31));
+    nmac &= conf;                                           // `if dist < NMAC_dist` sits inside `if dist < minimum_separation`
+    if (nmac) atomicMin(&s.ev_nmac[me], i0 + __ffs(nmac) - 1);
+  }
+  // ---- the warp that completes the tile's last work item finishes the tile (threadfence-reduction pattern):
+  // everything this warp stored is made visible device-wide before it counts itself in.
+  if constexpr (FUSE) {
+    __threadfence();
+    int arrived = 0;
+    if (lane == 0) arrived = atomicAdd(&s.tile_done[tile], 1);
+    arrived = __shfl_sync(FULL, arrived, 0);
+    if (arrived == n_chunks - 1) {
+      __threadfence();
+      __syncwarp();
+      finish_tile<FAITH, TAPE>(a, tile, lane, reinterpret_cast<uint32_t*>(stage_smem + wib * kWarpSmem));
+    }
+  }
+  GCA_KSTAMP_OUT(1);
+}
+
+// ------------------------------------------------------------------------------ reset / observe
+template <bool FAITH, bool TAPE>
+__global__ void __launch_bounds__(128) reset_kernel(const StepArgs a) {
   const DevState& s = a.s;
   const gca_config& c = a.cfg;
   const int lane = threadIdx.x & 31;
-  const long long tile = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  const long long env0 = tile * 32;
-  if (env0 >= s.B) return;
-  const int n_tile = (int)min(32LL, (long long)s.B - env0);
-  const bool has_env = lane < n_tile;
-  const size_t me = (size_t)(env0 + (has_env ? lane : 0));
+  const long long tile = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (tile >= s.T) return;
+  const size_t env0 = (size_t)tile * 32;
+  const bool has_env = env0 + lane < (size_t)s.B;
+  const size_t me = has_env ? env0 + lane : env0;
   const bool selected = has_env && (a.mask == nullptr || a.mask[me] != 0);
   int4 cnt = make_int4(0, 0, 0, 0);
-  Draws<TAPE> d;
-  if constexpr (TAPE) {
-    d.tape = nullptr;
-    d.cur = 0;
-  } else {
-    d.k0 = a.key0; d.k1 = a.key1; d.env = 0; d.tick = 0;
-  }
-  if (has_env) {
-    cnt = s.counters[me];
-    if constexpr (TAPE) {
-      d.tape = a.tape + me * (size_t)a.tape_stride;
-      d.cur = a.cursor[me];
-    } else {
-      d.env = a.env_id0 + (uint32_t)me;
-      d.tick = (uint32_t)cnt.z;
-    }
-  }
+  if (has_env) cnt = s.counters[me];
+  Draws<TAPE> d = make_draws<TAPE>(a, me, (uint32_t)cnt.z);
+  const int nxt = (cnt.z & 1) ^ 1;                       // a reset is a tick too: it writes the other plane
   uint32_t rmask = __ballot_sync(FULL, selected);
   while (rmask) {
     const int e = __ffs(rmask) - 1;
     rmask &= rmask - 1;
-    const size_t env = (size_t)(env0 + e);
     __syncwarp();
     Draws<TAPE> de = d;
     if constexpr (!TAPE) {
       de.env = __shfl_sync(FULL, d.env, e);
       de.tick = __shfl_sync(FULL, d.tick, e);
     }
+    const int plane = __shfl_sync(FULL, nxt, e);
     double2 goal = make_double2(0., 0.);
-    reset_env_warp<FAITH, TAPE>(a, env, lane, e, de, goal);
+    reset_env_warp<FAITH, TAPE>(a, env0 + e, plane, lane, e, de, goal);
     if (lane == e) {
       if constexpr (TAPE) d = de;
       float2 pos;
@@ -674,17 +788,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) reset_kernel(const StepAr
   }
 }
 
-// _get_ob() of the current state   PKG/SingleAircraftEnv.py:100-126; lane = env, plane reads are coalesced
+// _get_ob() of the current state   PKG/SingleAircraftEnv.py:100-126; thread = env, plane reads are coalesced
 template <bool FAITH>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) observe_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(128) observe_kernel(const StepArgs a) {
   const DevState& s = a.s;
-  const long long me_ll = ((long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * 32 + (threadIdx.x & 31);
-  if (me_ll >= s.B) return;
-  const size_t me = (size_t)me_ll;
+  const size_t me = (size_t)blockIdx.x * 128 + threadIdx.x;
+  if (me >= (size_t)s.B) return;
+  const int plane = s.counters[me].z & 1;
   real_t<FAITH>* obase = obs_intruder_base<FAITH>(a, me);
   for (int i = 0; i < s.N; ++i) {
     Intr<FAITH> it;
-    load_intruder<FAITH>(s, me, i, it);
+    load_intruder<FAITH>(s, plane, me, i, it);
     write_obs_intruder<FAITH>(a, obase, i, it);
   }
   const float2 pos = s.own_pos[me];
@@ -693,116 +807,75 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) observe_kernel(const Step
 }
 
 // ------------------------------------------------------------------------------ launchers
-namespace {
-int g_num_sms = 0;
-
-// Grid and dynamic shared memory of the persistent step kernel.  When every tile can have its own resident
-// block, the request is padded so that exactly ceil(tiles / SMs) blocks fit on an SM: the hardware block
-// scheduler then spreads the single wave evenly instead of packing some SMs to the register limit.
-template <typename K>
-cudaError_t persistent_grid(K kernel, size_t need, int n_tiles, unsigned* blocks, size_t* smem) {
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
-  if (g_num_sms == 0) {
-    e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return e;
-  }
-  int sm_smem = 0, reserved = 0, max_optin = 0;
-  cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-  cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, dev);
-  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
-  if (e != cudaSuccess) return e;
-  int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarpsPerBlock * 32, need);
-  if (e != cudaSuccess) return e;
-  if (per_sm < 1) return cudaErrorInvalidConfiguration;
-  const long long want = ((long long)n_tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  const long long cap = (long long)g_num_sms * per_sm;
-  *smem = need;
-  static const int forced = std::getenv("GCA_BLOCKS_PER_SM") ? std::atoi(std::getenv("GCA_BLOCKS_PER_SM")) : 0;   // tuning knob
-  if (want <= cap || forced > 0) {                        // single wave: balance it
-    const int target = forced > 0 ? forced : (int)((want + g_num_sms - 1) / g_num_sms);
-    if (target < per_sm && sm_smem > 0) {
-      size_t padded = ((size_t)sm_smem / (size_t)target - (size_t)reserved) & ~(size_t)127;
-      if (padded > (size_t)max_optin) padded = (size_t)max_optin;
-      int chk = 0;
-      if (padded > need && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&chk, kernel, kWarpsPerBlock * 32, padded) == cudaSuccess &&
-          chk == target)
-        *smem = padded, per_sm = target;
-    }
-  }
-  const long long cap2 = (long long)g_num_sms * per_sm;
-  *blocks = (unsigned)(want < cap2 ? want : cap2);
-  return cudaSuccess;
+// launch with programmatic stream serialization (see pdl_wait above)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned blocks, unsigned threads, cudaStream_t st, Args&&... args) {
+  static const int use_pdl = std::getenv("GCA_NO_PDL") ? 0 : 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
-template <bool FAITH, bool TAPE, int G, int OM>
-cudaError_t launch_step_t(const StepArgs& a, int stages, cudaStream_t st) {
-  const int n_tiles = a.s.T;
-  const int n_st = (a.s.U + G - 1) / G;
-  // ring depth: a power of two, no deeper than the tile has stages, at most ~96 KB per block
-  int pow2 = 1;
-  while (pow2 * 2 <= stages && pow2 < n_st && pow2 * 2 <= kMaxStages) pow2 *= 2;
-  stages = pow2;
-  while (stages > 1 && kWarpsPerBlock * warp_smem_bytes(a.s, FAITH, G, stages, OM) > 96 * 1024) stages /= 2;
-  const size_t need = kWarpsPerBlock * warp_smem_bytes(a.s, FAITH, G, stages, OM);
-  // grid size per (kernel, smem, tiles) is cached: the occupancy query is not free
-  static unsigned cached_blocks = 0;
-  static size_t cached_need = 0, cached_smem = 0;
-  static int cached_tiles = -1;
-  if (cached_blocks == 0 || cached_need != need || cached_tiles != n_tiles) {
-    cudaError_t e = persistent_grid(step_kernel<FAITH, TAPE, G, OM>, need, n_tiles, &cached_blocks, &cached_smem);
-    if (e != cudaSuccess) return e;
-    cached_need = need;
-    cached_tiles = n_tiles;
+template <bool FAITH, bool TAPE>
+static cudaError_t launch_step_t(const StepArgs& a, cudaStream_t st) {
+  const DevState& s = a.s;
+  const unsigned env_blocks = (unsigned)(((size_t)s.T * 32 + 127) / 128);
+  static const int fuse = std::getenv("GCA_FUSE_FINISH") ? std::atoi(std::getenv("GCA_FUSE_FINISH")) : 1;   // tuning knob
+  launch_pdl(step_own_kernel<FAITH, TAPE>, env_blocks, 128, st, a);
+  if (s.N > 0) {
+    const int n_chunks = (s.U + kChunkUnits - 1) / kChunkUnits;
+    const unsigned blocks = (unsigned)(((long long)s.T * n_chunks + kWarpsB - 1) / kWarpsB);
+    const bool vec = !FAITH && a.cfg.obs_kind == GCA_OBS_VECTOR && a.k.div1_ok;
+    if constexpr (FAITH) {
+      if (fuse) launch_pdl(step_intruders_kernel<true, TAPE, 0, true>, blocks, kWarpsB * 32, st, a);
+      else launch_pdl(step_intruders_kernel<true, TAPE, 0, false>, blocks, kWarpsB * 32, st, a);
+    } else if (vec) {
+      if (fuse) launch_pdl(step_intruders_kernel<false, TAPE, 1, true>, blocks, kWarpsB * 32, st, a);
+      else launch_pdl(step_intruders_kernel<false, TAPE, 1, false>, blocks, kWarpsB * 32, st, a);
+    } else {
+      if (fuse) launch_pdl(step_intruders_kernel<false, TAPE, 0, true>, blocks, kWarpsB * 32, st, a);
+      else launch_pdl(step_intruders_kernel<false, TAPE, 0, false>, blocks, kWarpsB * 32, st, a);
+    }
   }
-  const size_t smem = cached_smem;
-  step_kernel<FAITH, TAPE, G, OM><<<cached_blocks, kWarpsPerBlock * 32, smem, st>>>(a, stages);
+  if (s.N == 0 || !fuse) launch_pdl(step_finish_kernel<FAITH, TAPE>, (unsigned)((s.T + 3) / 4), 128, st, a);
+  if constexpr (!TAPE) {
+    if (s.N > 0) {                                        // one warp per tile-equivalent; the warps loop if more is queued
+      const unsigned blocks = (unsigned)((s.T + 3) / 4 < 1184 ? (s.T + 3) / 4 : 1184);
+      launch_pdl(spawn_kernel<FAITH>, blocks, 128, st, a);
+    }
+  }
   return cudaGetLastError();
 }
 
-template <int G>
-cudaError_t launch_step_g(bool faith, bool tape, const StepArgs& a, int stages, cudaStream_t st) {
-  if (faith)
-    return tape ? launch_step_t<true, true, G, 0>(a, stages, st) : launch_step_t<true, false, G, 0>(a, stages, st);
-  const bool vec = a.cfg.obs_kind == GCA_OBS_VECTOR && a.k.div1_ok;
-  if (vec) return tape ? launch_step_t<false, true, G, 1>(a, stages, st) : launch_step_t<false, false, G, 1>(a, stages, st);
-  return tape ? launch_step_t<false, true, G, 0>(a, stages, st) : launch_step_t<false, false, G, 0>(a, stages, st);
+cudaError_t launch_step(bool faith, bool tape, const StepArgs& a, cudaStream_t st) {
+  if (faith) return tape ? launch_step_t<true, true>(a, st) : launch_step_t<true, false>(a, st);
+  return tape ? launch_step_t<false, true>(a, st) : launch_step_t<false, false>(a, st);
 }
-}  // namespace
-
-cudaError_t launch_step(bool faith, bool tape, int group, int stages, const StepArgs& a, cudaStream_t st) {
-  if (group == 2) return launch_step_g<2>(faith, tape, a, stages, st);
-  return launch_step_g<4>(faith, tape, a, stages, st);
-}
-
-#ifdef GCA_PHASE_TIMING
-extern "C" int gca_debug_phase_stamps(unsigned long long* host, int count) {
-  return (int)cudaMemcpyFromSymbol(host, g_phase_stamps, sizeof(unsigned long long) * (size_t)count);
-}
-extern "C" int gca_debug_stage_stamps(unsigned long long* host, int count) {
-  return (int)cudaMemcpyFromSymbol(host, g_stage_stamps, sizeof(unsigned long long) * (size_t)count);
-}
-#endif
 
 cudaError_t launch_reset(bool faith, bool tape, const StepArgs& a, cudaStream_t st) {
-  const unsigned blocks = (unsigned)((a.s.T + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  const unsigned blocks = (unsigned)((a.s.T + 3) / 4);
   if (faith) {
-    if (tape) reset_kernel<true, true><<<blocks, kWarpsPerBlock * 32, 0, st>>>(a);
-    else reset_kernel<true, false><<<blocks, kWarpsPerBlock * 32, 0, st>>>(a);
+    if (tape) reset_kernel<true, true><<<blocks, 128, 0, st>>>(a);
+    else reset_kernel<true, false><<<blocks, 128, 0, st>>>(a);
   } else {
-    if (tape) reset_kernel<false, true><<<blocks, kWarpsPerBlock * 32, 0, st>>>(a);
-    else reset_kernel<false, false><<<blocks, kWarpsPerBlock * 32, 0, st>>>(a);
+    if (tape) reset_kernel<false, true><<<blocks, 128, 0, st>>>(a);
+    else reset_kernel<false, false><<<blocks, 128, 0, st>>>(a);
   }
   return cudaGetLastError();
 }
 
 cudaError_t launch_observe(bool faith, const StepArgs& a, cudaStream_t st) {
-  const unsigned blocks = (unsigned)((a.s.T + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  if (faith) observe_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, st>>>(a);
-  else observe_kernel<false><<<blocks, kWarpsPerBlock * 32, 0, st>>>(a);
+  const unsigned blocks = (unsigned)(((size_t)a.s.B + 127) / 128);
+  if (faith) observe_kernel<true><<<blocks, 128, 0, st>>>(a);
+  else observe_kernel<false><<<blocks, 128, 0, st>>>(a);
   return cudaGetLastError();
 }
 
