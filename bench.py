@@ -4,14 +4,17 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one launch of the fused step kernel over one batch of 65,536 environments per GPU
-(SingleAircraft2Env, continuous actions, 80 intruders, fast mode, Philox draws, VecEnv
-auto-reset, observation written every step).  Prints ONE JSON line (rank 0).
+One "step" = one gca_step over one batch of 65,536 environments per GPU (SingleAircraft2Env,
+continuous actions, 80 intruders, fast mode, Philox draws, VecEnv auto-reset, observation
+written every step): 4 kernels - ownship, intruders (the streaming pass), finish, spawn.
+Prints ONE JSON line (rank 0).
 
   value      whole-job env-steps/s, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e        the same metric through the host-buffer C-ABI call (gca_step_host): actions come
              from pinned host memory and obs/reward/done/info are copied back every step
-  roofline   algorithmic bytes per launch / measured launch duration vs the measured HBM peak
+  roofline   the dominant kernel (step_intruders_kernel): its algorithmic bytes per launch / its
+             launch duration, measured live with CUDA events between the kernels of the step
+             (gca_profile_*), vs the measured HBM peak; `step` gives the same for the whole step
   cpu_baseline  the CPU oracle port on the box's host cores, on a bounded sample (rank 0, N=1)
 
 --impl reference times the CPU oracle port alone (the reference is Python and cannot travel to
@@ -54,6 +57,12 @@ def algorithmic_bytes_per_env_step(n, continuous=True):
              + 4 + 1 + 1                     # reward, done, info
              + 32)                           # ownship + goal tail of the observation
     return per_intruder * n + flags + fixed
+
+
+def streaming_bytes_per_env_step(n):
+    """Algorithmic bytes of the dominant kernel alone (step_intruders_kernel): per intruder 8 (pos r) + 8 (vel r)
+    + 8 (pos w) + 16 (obs entries w); per env and 8-intruder work item 16 (ownship hand-over record)."""
+    return 40 * n + 16 * ((n + 7) // 8)
 
 
 def measured_peaks():
@@ -260,6 +269,16 @@ def main_gpu(args):
     ms = float(t.item())
     value = world * B * K / (ms * 1e-3)
 
+    # ---- the dominant kernel, timed live: CUDA events between the kernels of each step, same workload, right
+    # after the timed region (eager launches; the events sit on the stream the kernels are launched on)
+    Kp = max(20, min(K, 200))
+    env.profile(True)
+    for i in range(Kp):
+        env.step(actions[i % GRAPH_STEPS])
+    prof = env.read_profile()
+    env.profile(False)
+    kernels_per_step = env.kernels_per_step
+
     # ---- end to end through the host-buffer C-ABI call (GCA_BENCH_KERNEL_ONLY=1 skips it for ncu captures)
     kernel_only = os.environ.get("GCA_BENCH_KERNEL_ONLY") == "1"
     host_actions = [a.cpu().numpy() for a in actions[:8]]
@@ -281,24 +300,36 @@ def main_gpu(args):
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        bytes_per_launch = algorithmic_bytes_per_env_step(N) * B
-        launch_ms = ms / K
+        bytes_per_step = algorithmic_bytes_per_env_step(N) * B
+        step_ms = ms / K
+        step_gbs = bytes_per_step / (step_ms * 1e-3) / 1e9
+        bytes_per_launch = streaming_bytes_per_env_step(N) * B
+        launch_ms = prof["intruders_ms"] / max(prof["steps"], 1)
         achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
+        prof_step_ms = (prof["own_ms"] + prof["intruders_ms"] + prof["finish_ms"] + prof["spawn_ms"]) / max(prof["steps"], 1)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32+f64", "data": "synthetic",
             "config": {"workload": workload_name(), "envs_per_gpu": B, "intruders": N,
                        "l2": "per-step footprint %.0f MB (state+obs) exceeds the 126 MB L2; no flush between steps"
-                             % (bytes_per_launch / 1e6),
-                       "launch": "CUDA graph of %d step launches, replayed" % GRAPH_STEPS},
+                             % (bytes_per_step / 1e6),
+                       "launch": "CUDA graph of %d steps (%d kernels each), replayed" % (GRAPH_STEPS, kernels_per_step)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Ke, "api": "BatchedAircraftEnv.step_host -> gca_step_host (pinned host buffers)"},
-            "gpu_launches": K,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "peak_source": peak_src,
-                         "bytes_per_env_step": algorithmic_bytes_per_env_step(N), "kernel_ms": launch_ms},
+            "gpu_launches": K * kernels_per_step,
+            "roofline": {"bound": "hbm", "kernel": "step_intruders_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                         "bytes_per_env_step": streaming_bytes_per_env_step(N), "kernel_ms": launch_ms,
+                         "share_of_step": launch_ms / prof_step_ms if prof_step_ms else None,
+                         "timing": "CUDA events between the kernels of %d eager steps (gca_profile_*)" % prof["steps"],
+                         "kernels_ms": {"own": prof["own_ms"] / max(prof["steps"], 1),
+                                        "intruders": launch_ms,
+                                        "finish": prof["finish_ms"] / max(prof["steps"], 1),
+                                        "spawn": prof["spawn_ms"] / max(prof["steps"], 1)},
+                         "step": {"achieved": step_gbs, "frac": step_gbs / peak,
+                                  "bytes_per_env_step": algorithmic_bytes_per_env_step(N), "ms": step_ms}},
         }
         if world == 1 and not kernel_only:
             cb, _, _ = run_cpu(10 ** 9, 1, budget_s=12.0)

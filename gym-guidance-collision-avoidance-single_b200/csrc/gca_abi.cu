@@ -48,6 +48,10 @@ struct gca_env {
   void* d_actions = nullptr;
   gca_out d_out{};
   std::vector<void*> allocs;
+  // gca_profile_*
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;     // 5 per recorded step
+  std::vector<cudaEvent_t> prof_pool;       // recycled
 };
 
 namespace {
@@ -113,6 +117,16 @@ Derived derive(const gca_config& c) {
   k.den = (float)(c.max_speed * 2);
   k.inv_den = 1.0f / k.den;
   k.div1_ok = div1_exact(k.ob_w) && div1_exact(k.ob_h) && div1_exact(k.den);
+  k.dv_w = c.ob_window_width;
+  k.dv_h = c.ob_window_height;
+  k.dv_speed = c.ob_max_speed - c.ob_min_speed;
+  k.dv_2pi = 2.0 * 3.141592653589793;
+  k.dv_vel = c.max_speed * 2.0;
+  k.dv_shape = 1200.0;
+  k.rc_w = 1.0 / k.dv_w; k.rc_h = 1.0 / k.dv_h; k.rc_speed = 1.0 / k.dv_speed;
+  k.rc_2pi = 1.0 / k.dv_2pi; k.rc_vel = 1.0 / k.dv_vel; k.rc_shape = 1.0 / k.dv_shape;
+  k.ddiv_ok = gca_div_f64_divisor_ok(k.dv_w) && gca_div_f64_divisor_ok(k.dv_h) && gca_div_f64_divisor_ok(k.dv_speed) &&
+              gca_div_f64_divisor_ok(k.dv_2pi) && gca_div_f64_divisor_ok(k.dv_vel) && gca_div_f64_divisor_ok(k.dv_shape);
   return k;
 }
 
@@ -237,7 +251,6 @@ int gca_create(const gca_config* cfg, int n_envs, int n_intruders, int mode, int
   if (!rc) rc = dev_alloc(e, &s.ev_conf, flag_plane_words(s));
   if (!rc) rc = dev_alloc(e, &s.ev_gone, flag_plane_words(s));
   if (!rc) rc = dev_alloc(e, &s.ev_nmac, (size_t)s.T * 32);
-  if (!rc) rc = dev_alloc(e, &s.tile_done, (size_t)s.T);
   if (!rc) rc = dev_alloc(e, &s.reset_list, (size_t)s.T * 32);
   if (!rc) rc = dev_alloc(e, &s.reset_count, 1);
   s.respawn_cap = (int)std::min<size_t>((size_t)s.T * 32 * 4, (size_t)1 << 30);
@@ -258,6 +271,8 @@ int gca_destroy(gca_env* e) {
   if (!e) return GCA_OK;
   cudaSetDevice(e->device);
   for (void* p : e->allocs) cudaFree(p);
+  for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : e->prof_pool) cudaEventDestroy(ev);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
   return GCA_OK;
@@ -296,8 +311,49 @@ int gca_step(gca_env* e, const void* actions, const gca_tape* tape, int auto_res
   if (int rc = check_tape(e, tape)) return rc;
   GCA_CUDA(cudaSetDevice(e->device));
   const StepArgs a = make_args(e, actions, tape, out, auto_reset);
-  GCA_CUDA(launch_step(e->mode == GCA_MODE_FAITHFUL, e->draws == GCA_DRAWS_TAPE, a,
-                       (cudaStream_t)stream));
+  cudaEvent_t* ev = nullptr;
+  cudaEvent_t evs[5];
+  if (e->profiling) {
+    for (int i = 0; i < 5; ++i) {
+      if (!e->prof_pool.empty()) {
+        evs[i] = e->prof_pool.back();
+        e->prof_pool.pop_back();
+      } else {
+        GCA_CUDA(cudaEventCreate(&evs[i]));
+      }
+      e->prof_events.push_back(evs[i]);
+    }
+    ev = evs;
+  }
+  GCA_CUDA(launch_step(e->mode == GCA_MODE_FAITHFUL, e->draws == GCA_DRAWS_TAPE, a, (cudaStream_t)stream, ev));
+  return GCA_OK;
+}
+
+int gca_step_launches(gca_env* e) {
+  if (!e) return fail(GCA_ERR_INVALID, "env is NULL");
+  return step_launch_count(e->draws == GCA_DRAWS_TAPE, e->s.N);
+}
+
+int gca_profile_enable(gca_env* e, int on) {
+  if (!e) return fail(GCA_ERR_INVALID, "env is NULL");
+  e->profiling = on != 0;
+  return GCA_OK;
+}
+
+int gca_profile_read(gca_env* e, gca_step_profile* out) {
+  if (!e || !out) return fail(GCA_ERR_INVALID, "env/out is NULL");
+  GCA_CUDA(cudaSetDevice(e->device));
+  GCA_CUDA(cudaDeviceSynchronize());
+  gca_step_profile p = {};
+  for (size_t i = 0; i + 4 < e->prof_events.size(); i += 5) {
+    float ms[4];
+    for (int j = 0; j < 4; ++j) GCA_CUDA(cudaEventElapsedTime(&ms[j], e->prof_events[i + j], e->prof_events[i + j + 1]));
+    p.steps += 1;
+    p.own_ms += ms[0]; p.intruders_ms += ms[1]; p.finish_ms += ms[2]; p.spawn_ms += ms[3];
+  }
+  e->prof_pool.insert(e->prof_pool.end(), e->prof_events.begin(), e->prof_events.end());
+  e->prof_events.clear();
+  *out = p;
   return GCA_OK;
 }
 

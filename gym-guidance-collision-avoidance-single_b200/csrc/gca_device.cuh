@@ -49,7 +49,6 @@ struct DevState {
   uint32_t* ev_conf;      // [T][Wd][32] bit i: intruder i is inside the separation radius after its advance
   uint32_t* ev_gone;      // [T][Wd][32] bit i: intruder i left the map
   int* ev_nmac;           // [T*32] lowest intruder index inside the NMAC radius (INT_MAX: none)
-  int* tile_done;         // [T]    work items of the streaming pass that have completed for the tile
   int* reset_list;        // [T*32] envs that finished in this step (PHILOX auto-reset), in arrival order
   int* reset_count;       // [1]
   uint32_t* respawn_list; // [respawn_cap] (env << 8 | intruder) of the intruders that left the map in this step (PHILOX)
@@ -99,7 +98,16 @@ struct Derived {
   float ob_w, ob_h, inv_ob_w, inv_ob_h;   // x / Config.window_* in f32, and RN(1/.) for gca_div_const_f32
   float ms, den, inv_den;             // normalize_velocity: (v + ms) / den in f32
   int div1_ok;                        // the one-correction division is exact for ob_w, ob_h and den
+  // f64 divisors of the observation tail / shaped reward and their correctly rounded reciprocals (gca_div_const_f64)
+  double dv_w, dv_h, dv_speed, dv_2pi, dv_vel, dv_shape;       // window w/h, max-min speed, 2*pi, 2*max_speed, 1200
+  double rc_w, rc_h, rc_speed, rc_2pi, rc_vel, rc_shape;
+  int ddiv_ok;                        // all six divisors qualify (gca_div_f64_divisor_ok)
 };
+
+// x / d in f64, correctly rounded, for the host-prepared divisors of Derived
+__device__ __forceinline__ double ddiv_prepared(const Derived& k, double x, double d, double inv_d) {
+  return k.ddiv_ok ? gca_div_const_f64(x, d, inv_d) : __ddiv_rn(x, d);
+}
 
 // x / d in f32, correctly rounded, for the host-prepared divisors of Derived
 __device__ __forceinline__ float div_prepared(const Derived& k, float x, float d, float inv_d) {
@@ -398,8 +406,8 @@ __device__ __forceinline__ bool own_first(const gca_config& c) {
 __device__ __forceinline__ float norm_vel_f32(const Derived& k, float v) {
   return div_prepared(k, __fadd_rn(v, k.ms), k.den, k.inv_den);
 }
-__device__ __forceinline__ double norm_vel_f64(const gca_config& c, double v) {
-  return __ddiv_rn(__dadd_rn(v, c.max_speed), __dmul_rn(c.max_speed, 2.0));
+__device__ __forceinline__ double norm_vel_f64(const gca_config& c, const Derived& k, double v) {
+  return ddiv_prepared(k, __dadd_rn(v, c.max_speed), k.dv_vel, k.rc_vel);
 }
 
 // the four entries of intruder i   PKG/SingleAircraftEnv.py:108-114 (raw: Simulators/SingleAircraftMCTSEnv.py:107-112)
@@ -418,8 +426,8 @@ __device__ __forceinline__ void write_obs_intruder(const StepArgs& a, real_t<FAI
     bool wide = false;
     if constexpr (FAITH) wide = it.is64;
     if (wide) {
-      o0 = (R)__ddiv_rn((double)it.px, c.ob_window_width);
-      o1 = (R)__ddiv_rn((double)it.py, c.ob_window_height);
+      o0 = (R)ddiv_prepared(k, (double)it.px, k.dv_w, k.rc_w);
+      o1 = (R)ddiv_prepared(k, (double)it.py, k.dv_h, k.rc_h);
     } else {
       o0 = (R)div_prepared(k, (float)it.px, k.ob_w, k.inv_ob_w);
       o1 = (R)div_prepared(k, (float)it.py, k.ob_h, k.inv_ob_h);
@@ -481,21 +489,21 @@ __device__ __forceinline__ void write_obs_own(const StepArgs& a, size_t env, flo
     o[2] = (R)norm_vel_f32(k, (float)vx);
     o[3] = (R)norm_vel_f32(k, (float)vy);
   } else {
-    o[2] = (R)norm_vel_f64(c, vx);
-    o[3] = (R)norm_vel_f64(c, vy);
+    o[2] = (R)norm_vel_f64(c, k, vx);
+    o[3] = (R)norm_vel_f64(c, k, vy);
   }
-  o[4] = (R)__ddiv_rn(__dadd_rn(speed, -c.ob_min_speed), __dadd_rn(c.ob_max_speed, -c.ob_min_speed));
-  o[5] = (R)__ddiv_rn(heading, __dmul_rn(2.0, 3.141592653589793));
+  o[4] = (R)ddiv_prepared(k, __dadd_rn(speed, -c.ob_min_speed), k.dv_speed, k.rc_speed);
+  o[5] = (R)ddiv_prepared(k, heading, k.dv_2pi, k.rc_2pi);
   if (!of) {
-    o[6] = (R)__ddiv_rn(gx, c.ob_window_width);
-    o[7] = (R)__ddiv_rn(gy, c.ob_window_height);
+    o[6] = (R)ddiv_prepared(k, gx, k.dv_w, k.rc_w);
+    o[7] = (R)ddiv_prepared(k, gy, k.dv_h, k.rc_h);
   } else {
     R* ag = reinterpret_cast<R*>(a.achieved) + 2 * env;
     R* dg = reinterpret_cast<R*>(a.desired) + 2 * env;
     if (c.obs_kind == GCA_OBS_HER) {
       ag[0] = (R)nx; ag[1] = (R)ny;
-      dg[0] = (R)__ddiv_rn(gx, c.ob_window_width);
-      dg[1] = (R)__ddiv_rn(gy, c.ob_window_height);
+      dg[0] = (R)ddiv_prepared(k, gx, k.dv_w, k.rc_w);
+      dg[1] = (R)ddiv_prepared(k, gy, k.dv_h, k.rc_h);
     } else {
       ag[0] = (R)px; ag[1] = (R)py;
       dg[0] = (R)gx; dg[1] = (R)gy;

@@ -65,12 +65,9 @@ extern "C" int gca_debug_kstamps(unsigned long long* host, int reset) {
 #define GCA_KSTAMP_OUT(kid) do { } while (0)
 #endif
 
-#ifndef GCA_MINB
-#define GCA_MINB 24
-#endif
 constexpr int kChunkUnits = 4;                    // 16-byte units (intruder pairs) per lane and work item
 constexpr int kChunkIntr = 2 * kChunkUnits;       // 8 intruders
-constexpr int kWarpsB = 1;                        // work items per block of the streaming pass: a warp that stays behind to finish a tile holds no one else
+constexpr int kWarpsB = 4;                        // work items per block of the streaming pass
 // staging row of one lane: 8 intruders x 16 bytes of observation entries, plus 16 bytes so that the row stride is
 // an odd multiple of 16 (conflict-free 16-byte shared accesses across a quarter warp)
 constexpr uint32_t kObsRow = 16u * kChunkIntr + 16u;
@@ -222,7 +219,6 @@ __global__ void __launch_bounds__(128) step_own_kernel(const StepArgs a) {
     s.ev_gone[fi] = 0u;
   }
   s.ev_nmac[me] = INT_MAX;
-  if ((me & 31) == 0) s.tile_done[me >> 5] = 0;
   if (me == 0) {
     *s.reset_count = 0;
     *s.respawn_count = 0;
@@ -235,9 +231,8 @@ __global__ void __launch_bounds__(128) step_own_kernel(const StepArgs a) {
 // streaming pass recorded, then rewards, observation tail, counters, auto-reset.  Called by the warp that
 // completed the tile's last work item (or by step_finish_kernel when there are no intruders).  The event
 // words were produced by other warps of the same launch: they are read with ld.global.cg (L2).
-constexpr int kJobCap = 256;
 template <bool FAITH, bool TAPE>
-__device__ __noinline__ void finish_tile(const StepArgs& a, const int tile, const int lane, uint32_t* jobs) {
+__device__ __noinline__ void finish_tile(const StepArgs& a, const int tile, const int lane) {
   using R = real_t<FAITH>;
   const DevState& s = a.s;
   const gca_config& c = a.cfg;
@@ -358,6 +353,25 @@ __device__ __noinline__ void finish_tile(const StepArgs& a, const int tile, cons
       }
     }
   }
+  // PHILOX: a respawn depends on nothing but (env, tick, intruder) and the ownship position, so the spawns
+  // (FP64-heavy, 0-3 per env) are not done here, one lane per env, but queued for spawn_kernel, which runs one
+  // lane per spawn over the whole batch.  The slots are reserved now; the records are written after the reward
+  // section, when the atomic has long returned.
+  int job_mine = 0, job_off = 0, job_total = 0, job_base = 0;
+  if constexpr (!TAPE) {
+    if (compact) {
+      if (replay) job_mine = __popc(wg[0]) + __popc(wg[1]) + __popc(wg[2]) + __popc(wg[3]);
+      job_off = job_mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, job_off, o);
+        if (lane >= o) job_off += t;
+      }
+      job_total = __shfl_sync(FULL, job_off, 31);
+      job_off -= job_mine;
+      if (job_total > 0 && lane == 0) job_base = atomicAdd(s.respawn_count, job_total);
+    }
+  }
 #ifdef GCA_PHASE_TIMING
   fin_t2 = gtime();
 #endif
@@ -390,7 +404,7 @@ __device__ __noinline__ void finish_tile(const StepArgs& a, const int tile, cons
       if (dg < c.goal_radius) {
         reward = c.r_goal; done = true; info = GCA_INFO_GOAL;
       } else {
-        reward = c.shaped_default ? __ddiv_rn(-dg, 1200.0) : c.r_default;
+        reward = c.shaped_default ? ddiv_prepared(k, -dg, k.dv_shape, k.rc_shape) : c.r_default;
         info = GCA_INFO_NONE;
       }
     }
@@ -403,43 +417,26 @@ __device__ __noinline__ void finish_tile(const StepArgs& a, const int tile, cons
   }
 
   if constexpr (!TAPE) {
-    if (compact) {
-      // PHILOX: a respawn depends on nothing but (env, tick, intruder) and the ownship position, so the spawns
-      // (FP64-heavy, 0-3 per env) are not done here, one lane per env, but queued for spawn_kernel, which runs one
-      // lane per spawn over the whole batch.  A finished env under auto-reset gets all new intruders anyway.
-      int mine = 0;
-      if (replay && !(done && a.auto_reset)) mine = __popc(wg[0]) + __popc(wg[1]) + __popc(wg[2]) + __popc(wg[3]);
-      int off = mine;
+    if (compact && job_total > 0) {
+      job_base = __shfl_sync(FULL, job_base, 0);          // (the atomic was issued before the reward section)
+      if (job_mine > 0) {
+        uint32_t set64_own[kWordsAhead] = {0u, 0u, 0u, 0u};
+        int at = job_base + job_off;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(FULL, off, o);
-        if (lane >= o) off += t;
-      }
-      const int total = __shfl_sync(FULL, off, 31);
-      off -= mine;
-      if (total > 0) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(s.respawn_count, total);
-        base = __shfl_sync(FULL, base, 0);
-        if (mine > 0) {
-          uint32_t set64_own[kWordsAhead] = {0u, 0u, 0u, 0u};
-          int at = base + off;
-#pragma unroll
-          for (int w = 0; w < kWordsAhead; ++w) {
-            uint32_t rest = wg[w];
-            while (rest) {
-              const int j = __ffs(rest) - 1;
-              rest &= rest - 1;
-              if (at < s.respawn_cap) s.respawn_list[at] = ((uint32_t)me << 8) | (uint32_t)(w * 32 + j);
-              else respawn_own(w * 32 + j, set64_own[w]);   // (list full: more than 4 respawns per env on average)
-              ++at;
-            }
+        for (int w = 0; w < kWordsAhead; ++w) {
+          uint32_t rest = wg[w];
+          while (rest) {
+            const int j = __ffs(rest) - 1;
+            rest &= rest - 1;
+            if (at < s.respawn_cap) s.respawn_list[at] = ((uint32_t)me << 8) | (uint32_t)(w * 32 + j);
+            else if (!(done && a.auto_reset)) respawn_own(w * 32 + j, set64_own[w]);   // (list full: > 4 respawns per env on average)
+            ++at;
           }
-          if constexpr (FAITH) {
+        }
+        if constexpr (FAITH) {
 #pragma unroll
-            for (int w = 0; w < kWordsAhead; ++w)
-              if (set64_own[w]) atomicOr(&s.dflag[flag_index(s, me, w)], set64_own[w]);
-          }
+          for (int w = 0; w < kWordsAhead; ++w)
+            if (set64_own[w]) atomicOr(&s.dflag[flag_index(s, me, w)], set64_own[w]);
         }
       }
     }
@@ -530,13 +527,16 @@ __global__ void __launch_bounds__(128) spawn_kernel(const __grid_constant__ Step
         const float2 own = s.own_pos[env];
         d.env = a.env_id0 + (uint32_t)env;
         d.tick = (uint32_t)cnt.z - 1u;                      // the tick of the step that lost the intruder
-        Intr<FAITH> it;
-        spawn<FAITH, false>(d, a.cfg, a.k, (uint32_t)i, own.x, own.y, it);
-        store_ipos<FAITH>(s, cnt.z & 1, env, i, it);
-        store_ivel(s, env, i, it.vx, it.vy);
-        write_obs_intruder<FAITH>(a, obs_intruder_base<FAITH>(a, env), i, it);
-        if constexpr (FAITH) {
-          if (it.is64) atomicOr(&s.dflag[flag_index(s, env, i >> 5)], 1u << (i & 31));
+        // ep_steps == 0 after a step: the env finished and was reset (auto-reset); all its intruders are new anyway
+        if (cnt.y != 0 || !a.auto_reset) {
+          Intr<FAITH> it;
+          spawn<FAITH, false>(d, a.cfg, a.k, (uint32_t)i, own.x, own.y, it);
+          store_ipos<FAITH>(s, cnt.z & 1, env, i, it);
+          store_ivel(s, env, i, it.vx, it.vy);
+          write_obs_intruder<FAITH>(a, obs_intruder_base<FAITH>(a, env), i, it);
+          if constexpr (FAITH) {
+            if (it.is64) atomicOr(&s.dflag[flag_index(s, env, i >> 5)], 1u << (i & 31));
+          }
         }
       }
     } else {
@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(128) step_finish_kernel(const __grid_constant_
   pdl_wait();
   GCA_KSTAMP_IN(2);
   const long long tile = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (tile < a.s.T) finish_tile<FAITH, TAPE>(a, (int)tile, threadIdx.x & 31, nullptr);
+  if (tile < a.s.T) finish_tile<FAITH, TAPE>(a, (int)tile, threadIdx.x & 31);
   GCA_KSTAMP_OUT(2);
 }
 
@@ -580,15 +580,14 @@ __global__ void __launch_bounds__(128) step_finish_kernel(const __grid_constant_
 // OM: 1 = the observation is GCA_OBS_VECTOR with the one-correction division exact (the registered ids'
 // layout; FAST only): entries are computed without run-time layout tests and leave through the transposed
 // shared-memory write-out.  0 = generic (any layout, both modes): per-lane stores.
-template <bool FAITH, bool TAPE, int OM, bool FUSE>
-__global__ void __launch_bounds__(kWarpsB * 32, FUSE ? GCA_MINB : 32) step_intruders_kernel(const __grid_constant__ StepArgs a) {
+template <bool FAITH, int OM>
+__global__ void __launch_bounds__(kWarpsB * 32, 32) step_intruders_kernel(const __grid_constant__ StepArgs a) {
   if (PDL_EARLY) pdl_launch_dependents();
   pdl_wait();
   GCA_KSTAMP_IN(1);
   using R = real_t<FAITH>;
   static_assert(!(FAITH && OM), "the specialised observation path is FAST only");
-  constexpr uint32_t kWarpSmem = OM ? 32 * kObsRow : kJobCap * 4;    // observation staging, later the respawn job list
-  static_assert(kWarpSmem >= kJobCap * 4, "the job list reuses the staging buffer");
+  constexpr uint32_t kWarpSmem = OM ? 32 * kObsRow : 16;             // observation staging
   __shared__ __align__(16) uint8_t stage_smem[kWarpsB * kWarpSmem];
   const DevState& s = a.s;
   const Derived& k = a.k;
@@ -721,19 +720,6 @@ __global__ void __launch_bounds__(kWarpsB * 32, FUSE ? GCA_MINB : 32) step_intru
     nmac &= conf;                                           // `if dist < NMAC_dist` sits inside `if dist < minimum_separation`
     if (nmac) atomicMin(&s.ev_nmac[me], i0 + __ffs(nmac) - 1);
   }
-  // ---- the warp that completes the tile's last work item finishes the tile (threadfence-reduction pattern):
-  // everything this warp stored is made visible device-wide before it counts itself in.
-  if constexpr (FUSE) {
-    __threadfence();
-    int arrived = 0;
-    if (lane == 0) arrived = atomicAdd(&s.tile_done[tile], 1);
-    arrived = __shfl_sync(FULL, arrived, 0);
-    if (arrived == n_chunks - 1) {
-      __threadfence();
-      __syncwarp();
-      finish_tile<FAITH, TAPE>(a, tile, lane, reinterpret_cast<uint32_t*>(stage_smem + wib * kWarpSmem));
-    }
-  }
   GCA_KSTAMP_OUT(1);
 }
 
@@ -824,41 +810,46 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned blocks, unsigne
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// ev (nullable): 5 events recorded before / between / after the kernels of the step (gca_profile_*)
 template <bool FAITH, bool TAPE>
-static cudaError_t launch_step_t(const StepArgs& a, cudaStream_t st) {
+static cudaError_t launch_step_t(const StepArgs& a, cudaStream_t st, cudaEvent_t* ev) {
   const DevState& s = a.s;
   const unsigned env_blocks = (unsigned)(((size_t)s.T * 32 + 127) / 128);
-  static const int fuse = std::getenv("GCA_FUSE_FINISH") ? std::atoi(std::getenv("GCA_FUSE_FINISH")) : 1;   // tuning knob
+  auto mark = [&](int i) { if (ev) cudaEventRecord(ev[i], st); };
+  mark(0);
   launch_pdl(step_own_kernel<FAITH, TAPE>, env_blocks, 128, st, a);
+  mark(1);
   if (s.N > 0) {
     const int n_chunks = (s.U + kChunkUnits - 1) / kChunkUnits;
     const unsigned blocks = (unsigned)(((long long)s.T * n_chunks + kWarpsB - 1) / kWarpsB);
-    const bool vec = !FAITH && a.cfg.obs_kind == GCA_OBS_VECTOR && a.k.div1_ok;
     if constexpr (FAITH) {
-      if (fuse) launch_pdl(step_intruders_kernel<true, TAPE, 0, true>, blocks, kWarpsB * 32, st, a);
-      else launch_pdl(step_intruders_kernel<true, TAPE, 0, false>, blocks, kWarpsB * 32, st, a);
-    } else if (vec) {
-      if (fuse) launch_pdl(step_intruders_kernel<false, TAPE, 1, true>, blocks, kWarpsB * 32, st, a);
-      else launch_pdl(step_intruders_kernel<false, TAPE, 1, false>, blocks, kWarpsB * 32, st, a);
+      launch_pdl(step_intruders_kernel<true, 0>, blocks, kWarpsB * 32, st, a);
     } else {
-      if (fuse) launch_pdl(step_intruders_kernel<false, TAPE, 0, true>, blocks, kWarpsB * 32, st, a);
-      else launch_pdl(step_intruders_kernel<false, TAPE, 0, false>, blocks, kWarpsB * 32, st, a);
+      const bool vec = a.cfg.obs_kind == GCA_OBS_VECTOR && a.k.div1_ok;
+      if (vec) launch_pdl(step_intruders_kernel<false, 1>, blocks, kWarpsB * 32, st, a);
+      else launch_pdl(step_intruders_kernel<false, 0>, blocks, kWarpsB * 32, st, a);
     }
   }
-  if (s.N == 0 || !fuse) launch_pdl(step_finish_kernel<FAITH, TAPE>, (unsigned)((s.T + 3) / 4), 128, st, a);
+  mark(2);
+  launch_pdl(step_finish_kernel<FAITH, TAPE>, (unsigned)((s.T + 3) / 4), 128, st, a);
+  mark(3);
   if constexpr (!TAPE) {
     if (s.N > 0) {                                        // one warp per tile-equivalent; the warps loop if more is queued
       const unsigned blocks = (unsigned)((s.T + 3) / 4 < 1184 ? (s.T + 3) / 4 : 1184);
       launch_pdl(spawn_kernel<FAITH>, blocks, 128, st, a);
     }
   }
+  mark(4);
   return cudaGetLastError();
 }
 
-cudaError_t launch_step(bool faith, bool tape, const StepArgs& a, cudaStream_t st) {
-  if (faith) return tape ? launch_step_t<true, true>(a, st) : launch_step_t<true, false>(a, st);
-  return tape ? launch_step_t<false, true>(a, st) : launch_step_t<false, false>(a, st);
+cudaError_t launch_step(bool faith, bool tape, const StepArgs& a, cudaStream_t st, cudaEvent_t* ev) {
+  if (faith) return tape ? launch_step_t<true, true>(a, st, ev) : launch_step_t<true, false>(a, st, ev);
+  return tape ? launch_step_t<false, true>(a, st, ev) : launch_step_t<false, false>(a, st, ev);
 }
+
+// kernels one gca_step launches for this configuration (bench.py's gpu_launches)
+int step_launch_count(bool tape, int n_intruders) { return 2 + (n_intruders > 0 ? 1 : 0) + (!tape && n_intruders > 0 ? 1 : 0); }
 
 cudaError_t launch_reset(bool faith, bool tape, const StepArgs& a, cudaStream_t st) {
   const unsigned blocks = (unsigned)((a.s.T + 3) / 4);

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GCA_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libgca.so")
 
-GCA_ABI_VERSION = 1
+GCA_ABI_VERSION = 2
 
 MODE_FAITHFUL, MODE_FAST = 0, 1
 DRAWS_TAPE, DRAWS_PHILOX = 0, 1
@@ -69,6 +69,12 @@ def make_mcts_config(cfg_cls):
     return c
 
 
+class GcaStepProfile(C.Structure):
+    """gca_step_profile of include/gca.h"""
+    _fields_ = [("steps", C.c_int64), ("own_ms", C.c_double), ("intruders_ms", C.c_double), ("finish_ms", C.c_double),
+                ("spawn_ms", C.c_double)]
+
+
 class GcaError(RuntimeError):
     pass
 
@@ -102,6 +108,9 @@ def load():
         "gca_get_state": ([vp, P(GcaHostState)], C.c_int),
         "gca_set_state": ([vp, P(GcaHostState)], C.c_int),
         "gca_observe": ([vp, P(GcaOut), vp], C.c_int),
+        "gca_step_launches": ([vp], C.c_int),
+        "gca_profile_enable": ([vp, i32], C.c_int),
+        "gca_profile_read": ([vp, P(GcaStepProfile)], C.c_int),
         "gca_compute_reward": ([vp, vp, i64, C.c_double, i32, i32, vp, i32, vp], C.c_int),
         "gca_raster": ([vp, vp, vp, i64, i64, i32, i32, vp, vp], C.c_int),
         "gca_mcts_move": ([P(GcaMctsConfig), i32, vp, vp, vp, i64, P(GcaTape), u64, u32, i32, i32, vp], C.c_int),

@@ -132,8 +132,23 @@ class BatchedAircraftEnv(object):
                 actions = actions.to(torch.int32).reshape(self.num_envs).contiguous()
         abi.check(self.lib.gca_step(self._h, actions.data_ptr(), self._tape_ref(), 1 if auto_reset else 0,
                                     C.byref(self._out), self._stream()))
-        self.launches += 1
+        self.launches += self.kernels_per_step
         return self.obs, self.reward, self.done, self.info
+
+    @property
+    def kernels_per_step(self):
+        """Kernels one step launches (ownship, intruders, finish, spawn)."""
+        return self.lib.gca_step_launches(self._h)
+
+    def profile(self, on):
+        """Per-kernel device timing of step() (CUDA events between the kernels; not inside a graph capture)."""
+        abi.check(self.lib.gca_profile_enable(self._h, 1 if on else 0))
+
+    def read_profile(self):
+        """dict(steps, own_ms, intruders_ms, finish_ms, spawn_ms) summed over the steps recorded since the last read."""
+        p = abi.GcaStepProfile()
+        abi.check(self.lib.gca_profile_read(self._h, C.byref(p)))
+        return {name: getattr(p, name) for name, _ in p._fields_}
 
     def observe(self):
         abi.check(self.lib.gca_observe(self._h, C.byref(self._out), self._stream()))
@@ -180,7 +195,7 @@ class BatchedAircraftEnv(object):
         h, out, views = self._host_buffers()
         views["actions"][...] = np.asarray(actions).reshape(views["actions"].shape)
         abi.check(self.lib.gca_step_host(self._h, h["actions"].data_ptr(), 1 if auto_reset else 0, C.byref(out)))
-        self.launches += 1
+        self.launches += self.kernels_per_step
         return views["obs"], views["reward"], views["done"], views["info"]
 
     def reset_host(self):

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GCA_ABI_VERSION 1
+#define GCA_ABI_VERSION 2
 
 typedef enum gca_status {
   GCA_OK = 0,
@@ -165,6 +165,21 @@ int gca_reset(gca_env* env, const uint8_t* mask, const gca_tape* tape, const gca
  * finished is reset in the same launch and `obs` holds the reset observation. */
 int gca_step(gca_env* env, const void* actions, const gca_tape* tape, int auto_reset,
              const gca_out* out, void* stream);
+
+/* Number of kernels one gca_step launches for this handle (ownship, intruders, finish, spawn: 2 to 4). */
+int gca_step_launches(gca_env* env);
+
+/* Diagnostics: per-kernel device time of gca_step.  While enabled, every gca_step records CUDA events
+ * between its kernels on the caller's stream (do not enable inside a stream capture); gca_profile_read
+ * synchronises the device, sums the recorded intervals and clears them.  This is how bench.py times the
+ * streaming pass for its roofline line.  The reference has no counterpart (its only timing is the wall
+ * clock around a search in Algorithms/MCTS/Agent.py:36-43). */
+typedef struct gca_step_profile {
+  int64_t steps;
+  double own_ms, intruders_ms, finish_ms, spawn_ms; /* summed over `steps` recorded steps */
+} gca_step_profile;
+int gca_profile_enable(gca_env* env, int on);
+int gca_profile_read(gca_env* env, gca_step_profile* out);
 
 /* Same step driven from HOST memory (the end-to-end path): copies actions host->device,
  * launches, copies obs/reward/done/info device->host into `host_out` (host pointers with the

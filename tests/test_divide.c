@@ -26,5 +26,33 @@ int main(void) {
     if (bad2) rc = 1;
     if ((bad1 == 0) != (gca_div1_is_exact(d) != 0) && k < 2) rc = 2;
   }
+  /* f64: gca_div_const_f64 against IEEE division - dense random significands over many exponents, values
+     next to representable quotients' midpoints excluded by nothing: any mismatch is a failure */
+  {
+    const double dd[6] = {800.0, 1.0, 2.0 * 3.141592653589793, (80.0 / 30.0) * 2.0, 1200.0, 777.123456789};
+    uint64_t st = 0x9E3779B97F4A7C15ull, badd = 0, nd = 0;
+    for (int k = 0; k < 6; k++) {
+      const double d = dd[k], inv = 1.0 / d;
+      if (!gca_div_f64_divisor_ok(d)) { printf("divisor %g rejected\n", d); rc = 3; }
+      for (int it = 0; it < 4000000; it++) {
+        st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+        uint64_t mant = st & 0xFFFFFFFFFFFFFull;
+        uint64_t expo = 1023 - 40 + (uint64_t)(it % 80);
+        uint64_t u = (expo << 52) | mant;
+        if (it & 1) u |= 0x8000000000000000ull;
+        double x; memcpy(&x, &u, 8);
+        nd++; if (gca_div_const_f64(x, d, inv) != x / d) badd++;
+      }
+      /* exact multiples, their neighbours, zeros */
+      for (int m = -2000; m <= 2000; m++) {
+        const double base = (double)m * d;
+        const double xs[3] = {base, nextafter(base, 1e300), nextafter(base, -1e300)};
+        for (int j = 0; j < 3; j++) { nd++; if (gca_div_const_f64(xs[j], d, inv) != xs[j] / d) badd++; }
+      }
+      if (gca_div_const_f64(0.0, d, inv) != 0.0 || !signbit(gca_div_const_f64(-0.0, d, inv))) badd++;
+    }
+    printf("f64 n=%llu bad=%llu\n", (unsigned long long)nd, (unsigned long long)badd);
+    if (badd) rc = 4;
+  }
   return rc;
 }

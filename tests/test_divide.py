@@ -16,3 +16,4 @@ def test_constant_division_is_exact():
     assert out.returncode == 0, out.stdout
     lines = out.stdout.strip().splitlines()
     assert "bad_one_step=0 is_exact1=1" in lines[0] and "bad_one_step=0 is_exact1=1" in lines[1]   # default divisors
+    assert lines[-1].startswith("f64") and lines[-1].endswith("bad=0")      # gca_div_const_f64 == IEEE division
