@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(128) step_own_kernel(const StepArgs a) {
 // completed the tile's last work item (or by step_finish_kernel when there are no intruders).  The event
 // words were produced by other warps of the same launch: they are read with ld.global.cg (L2).
 template <bool FAITH, bool TAPE>
-__device__ __noinline__ void finish_tile(const StepArgs& a, const int tile, const int lane) {
+__device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, const int lane) {
   using R = real_t<FAITH>;
   const DevState& s = a.s;
   const gca_config& c = a.cfg;
@@ -598,34 +598,39 @@ __global__ void __launch_bounds__(kWarpsB * 32, 32) step_intruders_kernel(const 
   const int tile = (int)(work / n_chunks), ch = (int)(work - (long long)tile * n_chunks);
   const size_t me = (size_t)tile * 32 + lane;
   const bool has_env = me < (size_t)s.B;
+  const int u0 = ch * kChunkUnits, i0 = 2 * u0;
+  const int n_here = min(kChunkIntr, s.N - i0);           // intruders of this work item
+  constexpr size_t kPosUnits = FAITH ? 2 : 1;
+  const size_t unit0 = (size_t)tile * s.U + u0;           // first unit of this work item in the tile-planar order
+  const uint8_t* vsrc = s.ivel + (unit0 * 32 + lane) * 16;
+  // The velocity loads need nothing from the ownship record: they are issued first, so that they travel while the
+  // record (which says which position plane is current) is still on its way.
+  const uint64_t pol = l2_evict_first_policy();
+  float4 vv[kChunkUnits];
+  const bool full = !FAITH && n_here == kChunkIntr;
+  if (full) {
+#pragma unroll
+    for (int g = 0; g < kChunkUnits; ++g) vv[g] = ldg_stream(vsrc + g * 512, pol);
+  }
   const float4 ob = s.own_b[me];
   const uint32_t bits = __float_as_uint(ob.z);
   const bool runs = (bits & kOwnRuns) != 0;               // false: the reference's loop never ran for this env (max steps)
   const int par = (bits & kOwnPlane) ? 1 : 0;
   const float ox = ob.x, oy = ob.y;
-  const int u0 = ch * kChunkUnits, i0 = 2 * u0;
-  const int n_here = min(kChunkIntr, s.N - i0);           // intruders of this work item
-  constexpr size_t kPosUnits = FAITH ? 2 : 1;
-  const size_t unit0 = (size_t)tile * s.U + u0;           // first unit of this work item in the tile-planar order
   const size_t pos_off = (unit0 * kPosUnits * 32 + lane) * 16;
   const uint8_t* psrc = s.ipos + (size_t)par * s.pos_plane + pos_off;
   uint8_t* pdst = s.ipos + (size_t)(par ^ 1) * s.pos_plane + pos_off;
-  const uint8_t* vsrc = s.ivel + (unit0 * 32 + lane) * 16;
   R* obase = obs_intruder_base<FAITH>(a, me);
   uint32_t gone = 0, conf = 0, nmac = 0;                  // bit j: intruder i0 + j
 
   bool fast_done = false;
   if constexpr (!FAITH) {
-    if (n_here == kChunkIntr) {
+    if (full) {
       // ---- all 8 intruders at once, straight-line
       fast_done = true;
-      float4 p[kChunkUnits], vv[kChunkUnits], np[kChunkUnits];
-      const uint64_t pol = l2_evict_first_policy();
+      float4 p[kChunkUnits], np[kChunkUnits];
 #pragma unroll
-      for (int g = 0; g < kChunkUnits; ++g) {
-        p[g] = ldg_stream(psrc + g * 512, pol);
-        vv[g] = ldg_stream(vsrc + g * 512, pol);
-      }
+      for (int g = 0; g < kChunkUnits; ++g) p[g] = ldg_stream(psrc + g * 512, pol);
       const uint32_t wbits = __float_as_uint(k.win_w), hbits = __float_as_uint(k.win_h);
 #pragma unroll
       for (int g = 0; g < kChunkUnits; ++g) {

@@ -1,2 +1,3 @@
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 1000 --warmup 10 > gpurun_out/bench_now.json 2> gpurun_out/bench_now.err; tail -c 3000 gpurun_out/bench_now.json; tail -3 gpurun_out/bench_now.err
+export GCA_BENCH_KERNEL_ONLY=1
+python bench.py --steps 1000 --warmup 10 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('%.3e'%d['value'], '%.1f us'%(1e3*d['ms_per_step']), d['roofline']['kernels_ms'], '%.3f'%d['roofline']['frac'])"
