@@ -262,3 +262,69 @@ def test_compute_reward_matches_reference():
     ag = rng.uniform(0, 800, (4 * 65536, 2)); gg = ag + rng.uniform(-30, 30, ag.shape)
     assert np.array_equal(compute_reward(dev(ag), dev(gg), 20.0, abi.OBS_DHER).cpu().numpy(),
                           orc.compute_reward(ag, gg, 20.0, abi.OBS_DHER))
+
+
+@pytest.mark.parametrize("mode", ["fast", "faithful"])
+def test_long_rollout_with_explicit_masked_resets_vs_oracle(mode):
+    """No auto-reset: a finished env keeps its terminal state (after an NMAC the intruders behind the hit one
+    must sit where they were, Q9) until the caller resets exactly those envs.  After the first masked reset the
+    envs of one tile no longer agree on which position plane is current; 250 steps with random actions reach
+    every event kind many times.  Everything is compared with the oracle, bit for bit, after every step."""
+    from oracle import oracle as orc
+    vk, n, B, T = "env2", 80, 1536, 250
+    fast = mode == "fast"
+    env = make_gpu(vk, n, B, mode, "philox", seed=77)
+    ref = make_oracle(vk, n, B, 1, orc.TRIG_SHARED, seed=77, f32=fast, auto_reset=False)
+    cast = (lambda x: x.astype(np.float32)) if fast else (lambda x: x)
+    assert np.array_equal(env.reset().cpu().numpy(), cast(ref.reset()))
+    rng = np.random.RandomState(9)
+    events = np.zeros(6, np.int64)
+    resets = 0
+    for t in range(T):
+        a = rng.uniform(-1, 1, (B, 2))
+        if fast:
+            a = a.astype(np.float32).astype(np.float64)
+        obs, rew, done, info = env.step(gpu_actions(env, a), auto_reset=False)
+        ref.step(a)
+        done = done.cpu().numpy()
+        info = info.cpu().numpy()
+        assert np.array_equal(info, ref.info) and np.array_equal(done, ref.done), t
+        assert np.array_equal(rew.cpu().numpy(), cast(ref.reward)), t
+        assert np.array_equal(obs.cpu().numpy(), cast(ref.obs)), t
+        events += np.bincount(info, minlength=6)
+        if t % 10 == 9 or t == T - 1:
+            assert_state_equal(env.get_state(), ref.state, "state at step %d" % t, skip=())
+        if done.any():
+            resets += int(done.sum())
+            o = env.reset(mask=done).cpu().numpy()
+            ref.reset(mask=done)
+            assert np.array_equal(o, cast(ref.obs)), t
+    assert events[1] > 0 and events[2] > 0 and events[4] > 0 and resets > 0, events    # NMAC, conflict, wall all happened
+    env.close()
+    print(mode, "events", events.tolist(), "resets", resets)
+
+
+def test_kernels_per_step_and_profile():
+    """gca_step_launches / gca_profile_*: what bench.py uses for gpu_launches and for the roofline of the
+    dominant kernel."""
+    torch = _torch()
+    env = make_gpu("env", 80, 4096, "fast", "philox", seed=1)
+    assert env.kernels_per_step == 4                      # ownship, intruders, finish, spawn
+    env.reset()
+    a = torch.zeros(4096, dtype=torch.int32, device="cuda")
+    env.profile(True)
+    for _ in range(5):
+        env.step(a)
+    p = env.read_profile()
+    env.profile(False)
+    assert p["steps"] == 5 and p["intruders_ms"] > 0 and p["own_ms"] > 0 and p["finish_ms"] > 0 and p["spawn_ms"] > 0
+    env.step(a)
+    assert env.read_profile()["steps"] == 0
+    env.close()
+    e0 = make_gpu("env", 0, 64, "fast", "philox", seed=1)
+    assert e0.kernels_per_step == 2                       # no intruders: ownship + finish
+    e0.close()
+    g = load_trace("env", 3)
+    et = make_gpu("env", 3, g["tape"].shape[0], "faithful", "tape")
+    assert et.kernels_per_step == 3                       # tape replay respawns in place: no spawn kernel
+    et.close()
