@@ -336,6 +336,7 @@ def main_gpu(args):
             line["cpu_baseline"] = cb
         if not kernel_only:
             line["mcts"] = bench_mcts(local, with_cpu=(world == 1))
+            line["her"] = bench_her(local)
             line["stack"] = bench_stack(local)
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -380,6 +381,41 @@ def bench_mcts(device, with_cpu):
         out["cpu_baseline"] = {"value": 8 * 50 / dt, "unit": "rollouts/s", "cores": 1, "kind": "port",
                                "sample": "8 roots x 50 playouts, C oracle port (oracle/gca_oracle_mcts.c), 1 thread"}
     return out
+
+
+def bench_her(device):
+    """BASELINE.json config #3: SingleAircraftHEREnv (dict observation: observation / achieved_goal / desired_goal)
+    stepped on the device, followed by a relabel batch: compute_reward on M = 4*B (achieved, substitute goal) pairs
+    (k = 4 future goals per transition, Algorithms/DDPG/DDPG.py:38,308-315)."""
+    import torch
+    from gca_b200 import abi
+    from gca_b200.batched import BatchedAircraftEnv, compute_reward
+    from gym_guidance_collision_avoidance_single.envs.config import Config
+    B, N, k = ENVS_PER_GPU, N_INTRUDERS, 4
+    env = BatchedAircraftEnv("SingleAircraftHEREnv", B, Config, n_intruders=N, mode="fast", draws="philox", device=device, seed=4)
+    env.reset()
+    acts = [torch.rand((B, 2), device="cuda") * 2 - 1 for _ in range(8)]
+    goals = torch.rand((k, B, 2), device="cuda")                       # substitute goals (normalised, like desired_goal)
+
+    def one(i):
+        env.step(acts[i % 8])
+        ag = env.achieved.unsqueeze(0).expand(k, B, 2).reshape(k * B, 2)
+        return compute_reward(ag, goals.reshape(k * B, 2), Config.goal_radius, abi.OBS_HER)
+    for i in range(5):
+        one(i)
+    torch.cuda.synchronize()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 200
+    start.record()
+    for i in range(reps):
+        one(i)
+    stop.record()
+    torch.cuda.synchronize()
+    ms = start.elapsed_time(stop) / reps
+    env.close()
+    return {"metric": METRIC, "value": B / (ms * 1e-3), "unit": UNIT, "envs": B, "intruders": N,
+            "relabel_pairs_per_step": k * B, "ms_per_step": ms,
+            "note": "step (dict observation, own-first layout) + HER relabel reward on 4*B pairs, eager launches"}
 
 
 def bench_stack(device):

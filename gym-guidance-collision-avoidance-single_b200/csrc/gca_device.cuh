@@ -159,6 +159,9 @@ __device__ __forceinline__ float4 ldg_stream(const void* ptr, uint64_t pol) {
                : "l"(ptr), "l"(pol));
   return v;
 }
+__device__ __forceinline__ void stg_stream2(void* ptr, float x, float y, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(ptr), "f"(x), "f"(y), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void stg_stream(void* ptr, const float4& v, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z),
                "f"(v.w), "l"(pol)

@@ -65,9 +65,15 @@ extern "C" int gca_debug_kstamps(unsigned long long* host, int reset) {
 #define GCA_KSTAMP_OUT(kid) do { } while (0)
 #endif
 
-constexpr int kChunkUnits = 4;                    // 16-byte units (intruder pairs) per lane and work item
+#ifndef GCA_CHUNK_UNITS
+#define GCA_CHUNK_UNITS 4
+#endif
+#ifndef GCA_WARPS_B
+#define GCA_WARPS_B 4
+#endif
+constexpr int kChunkUnits = GCA_CHUNK_UNITS;      // 16-byte units (intruder pairs) per lane and work item
 constexpr int kChunkIntr = 2 * kChunkUnits;       // 8 intruders
-constexpr int kWarpsB = 4;                        // work items per block of the streaming pass
+constexpr int kWarpsB = GCA_WARPS_B;              // work items per block of the streaming pass
 // staging row of one lane: 8 intruders x 16 bytes of observation entries, plus 16 bytes so that the row stride is
 // an odd multiple of 16 (conflict-free 16-byte shared accesses across a quarter warp)
 constexpr uint32_t kObsRow = 16u * kChunkIntr + 16u;
@@ -579,9 +585,10 @@ __global__ void __launch_bounds__(128) step_finish_kernel(const __grid_constant_
 // ------------------------------------------------------------------------------ 2. intruders (the streaming pass)
 // OM: 1 = the observation is GCA_OBS_VECTOR with the one-correction division exact (the registered ids'
 // layout; FAST only): entries are computed without run-time layout tests and leave through the transposed
-// shared-memory write-out.  0 = generic (any layout, both modes): per-lane stores.
+// shared-memory write-out.  2 = the same for the own-first layouts GCA_OBS_HER / GCA_OBS_DHER, whose intruder
+// entries start 24 bytes into the row: 8-byte stores.  0 = generic (any layout, both modes): per-lane stores.
 template <bool FAITH, int OM>
-__global__ void __launch_bounds__(kWarpsB * 32, 32) step_intruders_kernel(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __grid_constant__ StepArgs a) {
   if (PDL_EARLY) pdl_launch_dependents();
   pdl_wait();
   GCA_KSTAMP_IN(1);
@@ -654,7 +661,7 @@ __global__ void __launch_bounds__(kWarpsB * 32, 32) step_intruders_kernel(const 
 #pragma unroll
         for (int g = 0; g < kChunkUnits; ++g) stg_stream(pdst + g * 512, np[g], pol);
       }
-      if constexpr (OM == 1) {
+      if constexpr (OM != 0) {
         // observation entries -> this lane's staging row -> transposed write-out: 8 consecutive lanes store
         // the 128 contiguous bytes of ONE env's row, 4 rows per store instruction.
         uint8_t* stg = stage_smem + wib * kWarpSmem;
@@ -665,15 +672,23 @@ __global__ void __launch_bounds__(kWarpsB * 32, 32) step_intruders_kernel(const 
           row[2 * g + 1] = obs_intruder_vec(k, np[g].z, np[g].w, vv[g].z, vv[g].w);
         }
         __syncwarp();
-        const int sub = lane >> 3, chunk = lane & 7;
+        constexpr int kLanesPerEnv = kChunkIntr, kEnvsPerStore = 32 / kLanesPerEnv;
+        const int sub = lane / kLanesPerEnv, chunk = lane % kLanesPerEnv;
         const uint8_t* src = stg + sub * kObsRow + chunk * 16;
         const size_t env_sub = (size_t)tile * 32 + sub;
-        float* dst = reinterpret_cast<float*>(a.obs) + env_sub * (size_t)a.D + 4 * (size_t)(i0 + chunk);
-        const size_t dstep = 4 * (size_t)a.D;
+        float* dst = reinterpret_cast<float*>(a.obs) + env_sub * (size_t)a.D + (OM == 2 ? 6 : 0) + 4 * (size_t)(i0 + chunk);
+        const size_t dstep = kEnvsPerStore * (size_t)a.D;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const float4 val = *reinterpret_cast<const float4*>(src + it * 4 * kObsRow);
-          if (env_sub + 4 * it < (size_t)s.B) stg_stream(dst + it * dstep, val, pol);
+        for (int it = 0; it < kLanesPerEnv; ++it) {
+          const float4 val = *reinterpret_cast<const float4*>(src + it * kEnvsPerStore * kObsRow);
+          if (env_sub + kEnvsPerStore * it < (size_t)s.B) {
+            if constexpr (OM == 1) {
+              stg_stream(dst + it * dstep, val, pol);
+            } else {                                        // own-first rows: entries are only 8-byte aligned
+              stg_stream2(dst + it * dstep, val.x, val.y, pol);
+              stg_stream2(dst + it * dstep + 2, val.z, val.w, pol);
+            }
+          }
         }
       } else if (has_env) {
 #pragma unroll
@@ -830,8 +845,9 @@ static cudaError_t launch_step_t(const StepArgs& a, cudaStream_t st, cudaEvent_t
     if constexpr (FAITH) {
       launch_pdl(step_intruders_kernel<true, 0>, blocks, kWarpsB * 32, st, a);
     } else {
-      const bool vec = a.cfg.obs_kind == GCA_OBS_VECTOR && a.k.div1_ok;
-      if (vec) launch_pdl(step_intruders_kernel<false, 1>, blocks, kWarpsB * 32, st, a);
+      const bool own_first = a.cfg.obs_kind == GCA_OBS_HER || a.cfg.obs_kind == GCA_OBS_DHER;
+      if (a.k.div1_ok && a.cfg.obs_kind == GCA_OBS_VECTOR) launch_pdl(step_intruders_kernel<false, 1>, blocks, kWarpsB * 32, st, a);
+      else if (a.k.div1_ok && own_first) launch_pdl(step_intruders_kernel<false, 2>, blocks, kWarpsB * 32, st, a);
       else launch_pdl(step_intruders_kernel<false, 0>, blocks, kWarpsB * 32, st, a);
     }
   }
