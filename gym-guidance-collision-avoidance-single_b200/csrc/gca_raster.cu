@@ -1,23 +1,46 @@
 // gca_raster.cu - image observation of SingleAircraftStackEnv on the device (sm_100a).
 //
 // Reference: PKG/SingleAircraftStackEnv.py:179-214 (render: 800x800 RGB GL frame) and :104-108
-// (preprocess_frame: RGB2GRAY + INTER_AREA / 4).  One CTA per environment.  The 1.9 MB full
-// resolution frame never exists: >= 95 % of the 200x200 output is background, so
-//   1. the env's sprite poses (ownship, goal, intruders, in draw order) go to shared memory,
-//   2. every sprite ORs its bit into the <= 3x3 cells (8x8 output pixels each) its reach touches,
-//   3. the plane is filled with white (16-byte stores),
-//   4. one warp per sprite walks the <= 13x13 output pixels of that sprite's bounding box; the 16
-//      samples of a pixel are blended against the cell's sprites in bit (= draw) order with the
-//      shared per-sample arithmetic of gca_raster_spec.h (fully transparent texels exit early),
-//      then gray -> 4x4 area mean (round half to even); only touched pixels are rewritten.
-// Output bytes: 40 000 per env-step.
+// (preprocess_frame: RGB2GRAY + INTER_AREA / 4).  The per-sample arithmetic is the specification in
+// gca_raster_spec.h (shared with the CPU oracle); this file evaluates exactly that arithmetic, with
+// exact-equivalence shortcuts only (argued where they are made).
+//
+// Persistent CTAs (2 per SM), each looping over environments.  The 1.9 MB full-resolution frame never
+// exists, and the 40 KB output plane is assembled in SHARED memory and leaves with one TMA bulk store:
+//   0. once per CTA: the three 32x32 RGBA textures are expanded to float4 in shared memory; every
+//      bilinear footprint (33x33 corners per texture) is classified: 0 = four transparent texels
+//      (the blend is the identity), 2 = four identical opaque texels (the blend is a replacement),
+//      1 = anything else (the general blend); a summed-area table counts the non-transparent
+//      footprints of any index rectangle;
+//   1. per env: sprite poses in draw order (ownship, goal, intruders) -> shared memory; the plane is
+//      filled with white; every sprite ORs its bit into the <= 2x2 cells (16x16 output pixels) it reaches;
+//   2. one warp per sprite walks the <= 13x13 output pixels of the sprite's bounding box, 32 at a time.
+//      A pixel is LIVE for a sprite if its 4x4 sample block can meet the rotated quad and the footprints
+//      those samples can land on are not all transparent (summed-area query).  The warp keeps the pixels
+//      that are live for its sprite and for no sprite drawn earlier - so every pixel that can differ from
+//      white is shaded exactly once - together with the (<= 4) sprites that are live on it;
+//   3. the kept pixels are shaded two at a time: lane = one of the 16 samples of a pixel, colour state in
+//      registers, the live sprites blended in draw order, gray, warp-wide packed integer reduction,
+//      4x4 area mean (round half to even), one byte into the shared plane;
+//   4. fence.proxy.async + cp.async.bulk shared -> global of the whole plane (UBLKCP); the next env's
+//      fill waits only for the bulk copy to have READ the plane.
+// Output bytes: 40 000 per env-step, written once, fully coalesced.
 #include "gca_launch.h"
 #include "gca_raster_spec.h"
 
 namespace gca {
 
-constexpr int kRasterThreads = 256;
+constexpr int kRasterThreads = 384;
+constexpr int kRasterWarps = kRasterThreads / 32;
 constexpr int kMaxSprites = GCA_RASTER_MAX_INTRUDERS + 2;   // 128 -> 4 mask words per cell
+constexpr int kCorner = GCA_SPRITE + 1;                     // bilinear footprints per axis: iu in [-1, 31]
+constexpr int kSat = kCorner + 1;                           // summed-area table side
+constexpr int kListCap = 64;                                // >= 1 carried + 32 new pixels
+constexpr int kCellShift = 4;                               // cell = 16 x 16 output pixels
+constexpr float kMagic = 12582912.0f;                       // 1.5 * 2^23: x + kMagic rounds x to an integer (RN-even)
+// half extent of the quad (16) + half diagonal of the 4x4 sample block (1.5 * sqrt 2 = 2.1214) + slack
+constexpr float kHitReach = 18.25f;
+constexpr uint32_t kScanCell = 0xfefefefeu;                 // more than 4 live sprites: walk the whole cell mask
 
 struct RasterArgs {
   DevState s;
@@ -30,147 +53,332 @@ struct RasterArgs {
   long long env_stride, plane_stride;
   int n_planes, slot;
   const uint8_t* clear_mask;
+  int bulk_ok;              // plane addresses / size are 16-byte aligned: TMA bulk store
 };
 
-__global__ void __launch_bounds__(kRasterThreads) raster_kernel(const RasterArgs a) {
+// floor of t for t in [-0.5, 31.5] without a conversion instruction: s = RN(t + kMagic) is kMagic + n with n the
+// nearest integer, exactly; n - (n > t) is the floor.  Returns the integer, writes the float.
+__device__ __forceinline__ int floor_small(float t, float* fl) {
+  const float s = __fadd_rn(t, kMagic);
+  const float n = __fadd_rn(s, -kMagic);
+  const int adj = n > t ? 1 : 0;
+  *fl = n > t ? __fadd_rn(n, -1.0f) : n;
+  return (__float_as_int(s) - 0x4B400000) - adj;
+}
+
+// The spec's clamp((int)rintf(v), 0, 255), kept in float.  v = src * alpha + dst * (1 - alpha) with src <= 255 (1 + 2e-6),
+// 0 <= dst <= 255, 0 <= alpha <= 1 + 2e-6 lies in (-0.01, 255.01), so rintf(v) is already in [0, 255] and the clamp is
+// the identity; (v + kMagic) - kMagic is rintf(v) (round to nearest even) for |v| < 2^22.
+__device__ __forceinline__ float quantise_u8(float v) { return __fadd_rn(__fadd_rn(v, kMagic), -kMagic); }
+
+// gca_raster_sample (gca_raster_spec.h) with the 8-bit colour kept in float registers.  Same operations in the
+// same order; the two shortcuts are exact:
+//  * class 0 (four texels with alpha 0): the spec's a255 is 0.0f and it returns without blending;
+//  * class 2 (four texels equal, alpha 255): every bilinear value is c(1+e), |e| < 2e-6, alpha is 1+e', |e'| < 2e-6,
+//    so v = c + d with |d| < 2e-3 for c, dst <= 255 and rintf(v) = c: the blend writes the texel colour.
+__device__ __forceinline__ void raster_sample_fast(const float4 pose, const int tex, const float4* __restrict__ texf,
+                                                   const uint8_t* __restrict__ cls, float wx, float wy, float& r,
+                                                   float& g, float& b) {
+  const float dx = __fadd_rn(wx, -pose.x), dy = __fadd_rn(wy, -pose.y);
+  const float lx = __fadd_rn(__fmul_rn(pose.z, dx), __fmul_rn(pose.w, dy));
+  const float ly = __fadd_rn(__fmul_rn(pose.z, dy), -__fmul_rn(pose.w, dx));
+  if (!(lx >= -GCA_SPRITE_HALF && lx < GCA_SPRITE_HALF && ly >= -GCA_SPRITE_HALF && ly < GCA_SPRITE_HALF)) return;
+  const float tu = __fadd_rn(lx, 15.5f), tv = __fadd_rn(ly, 15.5f);
+  float fu0, fv0;
+  const int iu = floor_small(tu, &fu0), iv = floor_small(tv, &fv0);
+  const int c = cls[tex * (kCorner * kCorner) + (iv + 1) * kCorner + (iu + 1)];
+  if (c == 0) return;
+  const int u0 = max(iu, 0), u1 = min(iu + 1, 31), v0 = max(iv, 0), v1 = min(iv + 1, 31);
+  const float4* t = texf + tex * (GCA_SPRITE * GCA_SPRITE);
+  const float4 t00 = t[(31 - v0) * GCA_SPRITE + u0];
+  if (c == 2) { r = t00.x; g = t00.y; b = t00.z; return; }
+  const float4 t10 = t[(31 - v0) * GCA_SPRITE + u1];
+  const float4 t01 = t[(31 - v1) * GCA_SPRITE + u0];
+  const float4 t11 = t[(31 - v1) * GCA_SPRITE + u1];
+  const float fu = __fadd_rn(tu, -fu0), fv = __fadd_rn(tv, -fv0);
+  const float gu = __fadd_rn(1.0f, -fu), gv = __fadd_rn(1.0f, -fv);
+#define GCA_BIL(k)                                                                                  \
+  __fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(t00.k, gu), __fmul_rn(t10.k, fu)), gv),                   \
+            __fmul_rn(__fadd_rn(__fmul_rn(t01.k, gu), __fmul_rn(t11.k, fu)), fv))
+  const float a255 = GCA_BIL(w);
+  if (a255 == 0.0f) return;
+  const float alpha = __fmul_rn(a255, 0.003921568859368563f);
+  const float beta = __fadd_rn(1.0f, -alpha);
+  r = quantise_u8(__fadd_rn(__fmul_rn(GCA_BIL(x), alpha), __fmul_rn(r, beta)));
+  g = quantise_u8(__fadd_rn(__fmul_rn(GCA_BIL(y), alpha), __fmul_rn(g, beta)));
+  b = quantise_u8(__fadd_rn(__fmul_rn(GCA_BIL(z), alpha), __fmul_rn(b, beta)));
+#undef GCA_BIL
+}
+
+__device__ __forceinline__ int floor_int(float t) {        // floor for |t| < 2^22, no conversion instruction
+  const float s = __fadd_rn(t, kMagic);
+  return (__float_as_int(s) - 0x4B400000) - (__fadd_rn(s, -kMagic) > t ? 1 : 0);
+}
+
+// Is the output pixel centred on (pcx, pcy) LIVE for the sprite: can one of its 16 samples (offsets +-0.5, +-1.5)
+// fall inside the quad on a footprint that is not fully transparent?  Conservative (never false for a sample
+// the spec would blend), deterministic (every warp evaluates the same function, so ownership is consistent).
+__device__ __forceinline__ bool pixel_live(const float4 pose, const uint16_t* __restrict__ sat, float pcx, float pcy) {
+  const float dx = pcx - pose.x, dy = pcy - pose.y;
+  const float lx = pose.z * dx + pose.w * dy, ly = pose.z * dy - pose.w * dx;
+  if (!(fabsf(lx) <= kHitReach && fabsf(ly) <= kHitReach)) return false;
+  // the samples' local coordinates lie within +-rad of the centre's on each axis
+  const float rad = 1.5f * (fabsf(pose.z) + fabsf(pose.w)) + 0.01f;
+  const float tu = lx + 15.5f, tv = ly + 15.5f;
+  const int a0 = min(max(floor_int(tu - rad), -1), 31) + 1, a1 = min(max(floor_int(tu + rad), -1), 31) + 2;
+  const int b0 = min(max(floor_int(tv - rad), -1), 31) + 1, b1 = min(max(floor_int(tv + rad), -1), 31) + 2;
+  const int n = (int)sat[b1 * kSat + a1] - (int)sat[b0 * kSat + a1] - (int)sat[b1 * kSat + a0] + (int)sat[b0 * kSat + a0];
+  return n > 0;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(kRasterThreads, 2) raster_kernel(const RasterArgs a) {
   extern __shared__ __align__(16) uint8_t rsm[];
   const DevState& s = a.s;
-  const int env = blockIdx.x;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_sprites = 2 + s.N;
   const int n_cells = a.cells_x * a.cells_y;
-  uint8_t* tex = rsm;                                                  // [3][32][32][4]
-  gca_sprite_pose* pose = reinterpret_cast<gca_sprite_pose*>(tex + 3 * 32 * 32 * 4);
-  uint4* cell_mask = reinterpret_cast<uint4*>(pose + kMaxSprites);     // [n_cells]
+  const int plane_bytes = a.ow * a.oh;
+  float4* texf = reinterpret_cast<float4*>(rsm);                                   // [3][32][32] RGBA as float
+  uint8_t* plane = rsm + 3 * GCA_SPRITE * GCA_SPRITE * sizeof(float4);             // [oh][ow]
+  uint4* cell_mask = reinterpret_cast<uint4*>(plane + ((plane_bytes + 15) & ~15)); // [n_cells]
+  float4* pose = reinterpret_cast<float4*>(cell_mask + n_cells);                   // [128] (cx, cy, rc, rs)
+  short4* box = reinterpret_cast<short4*>(pose + kMaxSprites);                     // [128] output-pixel bounding boxes
+  uint2* list = reinterpret_cast<uint2*>(box + kMaxSprites) + warp * kListCap;     // per warp: (ox | oy << 16, sprite ids)
+  uint16_t* sat_all = reinterpret_cast<uint16_t*>(reinterpret_cast<uint2*>(box + kMaxSprites) + kRasterWarps * kListCap);
+  uint8_t* cls = reinterpret_cast<uint8_t*>(sat_all + 3 * kSat * kSat);            // [3][33][33]
 
-  for (int i = tid; i < 3 * 32 * 32; i += kRasterThreads)
-    reinterpret_cast<uint32_t*>(tex)[i] = reinterpret_cast<const uint32_t*>(a.sprites)[i];
-  for (int i = tid; i < n_cells; i += kRasterThreads) cell_mask[i] = make_uint4(0u, 0u, 0u, 0u);
+  // ---- 0. textures, footprint classes and their summed-area tables, once per CTA
+  for (int i = tid; i < 3 * GCA_SPRITE * GCA_SPRITE; i += kRasterThreads) {
+    const uchar4 q = reinterpret_cast<const uchar4*>(a.sprites)[i];
+    texf[i] = make_float4((float)q.x, (float)q.y, (float)q.z, (float)q.w);
+  }
+  for (int i = tid; i < 3 * kCorner * kCorner; i += kRasterThreads) {
+    const int t = i / (kCorner * kCorner), c = i % (kCorner * kCorner);
+    const int iv = c / kCorner - 1, iu = c % kCorner - 1;
+    const int u0 = max(iu, 0), u1 = min(iu + 1, 31), v0 = max(iv, 0), v1 = min(iv + 1, 31);
+    const uint32_t* tx = reinterpret_cast<const uint32_t*>(a.sprites) + t * GCA_SPRITE * GCA_SPRITE;
+    const uint32_t q00 = tx[(31 - v0) * GCA_SPRITE + u0], q10 = tx[(31 - v0) * GCA_SPRITE + u1];
+    const uint32_t q01 = tx[(31 - v1) * GCA_SPRITE + u0], q11 = tx[(31 - v1) * GCA_SPRITE + u1];
+    int k = 1;
+    if (((q00 | q10 | q01 | q11) >> 24) == 0u) k = 0;
+    else if ((q00 >> 24) == 255u && q00 == q10 && q00 == q01 && q00 == q11) k = 2;
+    cls[i] = (uint8_t)k;
+  }
+  __syncthreads();
+  // sat[t][b][a] = number of non-transparent footprints with row < b and column < a (rows / columns shifted by +1)
+  for (int i = tid; i < 3 * kSat; i += kRasterThreads) {                            // row prefix sums
+    const int t = i / kSat, b = i % kSat;
+    uint16_t* row = sat_all + (t * kSat + b) * kSat;
+    int acc = 0;
+    row[0] = 0;
+    for (int c = 1; c < kSat; ++c) {
+      if (b >= 1) acc += cls[t * kCorner * kCorner + (b - 1) * kCorner + (c - 1)] != 0;
+      row[c] = (uint16_t)acc;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 3 * kSat; i += kRasterThreads) {                            // column prefix sums
+    const int t = i / kSat, c = i % kSat;
+    uint16_t* col = sat_all + t * kSat * kSat + c;
+    int acc = 0;
+    for (int b = 0; b < kSat; ++b) { acc += col[b * kSat]; col[b * kSat] = (uint16_t)acc; }
+  }
 
-  // ---- 1. sprite poses in draw order: ownship, goal, intruders (PKG/SingleAircraftStackEnv.py:192-212)
-  if (tid < n_sprites) {
-    gca_sprite_pose p;
-    if (tid == 0) {
-      const float2 pos = s.own_pos[env];
-      const double2 hs = s.own_hs[env];
-      double sn, cs;
-      gca_sincos(hs.x, &sn, &cs);
-      p.cx = pos.x; p.cy = pos.y;
-      p.rc = (float)sn;                                                // cos(h - pi/2) = sin h
-      p.rs = -(float)cs;                                               // sin(h - pi/2) = -cos h
-      p.tex = 0;
-    } else if (tid == 1) {
-      const double2 g = s.goal[env];
-      p.cx = (float)g.x; p.cy = (float)g.y; p.rc = 1.0f; p.rs = 0.0f; p.tex = 1;
-    } else {
-      const int i = tid - 2;
-      float px, py;
-      const uint8_t* plane = s.ipos + (size_t)(s.counters[env].z & 1) * s.pos_plane;   // the env's current positions
-      if (a.faithful) {
-        const double2 q = *reinterpret_cast<const double2*>(plane + ipos_offset(s, true, (size_t)env, i));
-        px = (float)q.x; py = (float)q.y;
+  for (int env = blockIdx.x; env < s.B; env += gridDim.x) {
+    // the bulk store of the previous plane must have read shared memory before it is filled again
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncthreads();
+
+    // ---- 1. sprite poses in draw order: ownship, goal, intruders (PKG/SingleAircraftStackEnv.py:192-212)
+    if (tid < n_sprites) {
+      float4 p;
+      if (tid == 0) {
+        const float2 pos = s.own_pos[env];
+        const double2 hs = s.own_hs[env];
+        double sn, cs;
+        gca_sincos(hs.x, &sn, &cs);
+        p = make_float4(pos.x, pos.y, (float)sn, -(float)cs);             // cos(h - pi/2) = sin h, sin(h - pi/2) = -cos h
+      } else if (tid == 1) {
+        const double2 g = s.goal[env];
+        p = make_float4((float)g.x, (float)g.y, 1.0f, 0.0f);
       } else {
-        const float2 q = *reinterpret_cast<const float2*>(plane + ipos_offset(s, false, (size_t)env, i));
-        px = q.x; py = q.y;
-      }
-      const float2 v = *reinterpret_cast<const float2*>(s.ivel + ivel_offset(s, (size_t)env, i));
-      // the intruder's heading is constant for life (:207-211); its direction is that of the velocity
-      const float len = __fsqrt_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)));
-      const float ch = __fdiv_rn(v.x, len), sh = __fdiv_rn(v.y, len);
-      p.cx = px; p.cy = py; p.rc = sh; p.rs = -ch; p.tex = 2;
-    }
-    pose[tid] = p;
-  }
-  // VecFrameStack: a finished env starts from an all-zero stack (vec_frame_stack.py:19-23)
-  uint8_t* env_base = a.frames + (long long)env * a.env_stride;
-  if (a.clear_mask && a.clear_mask[env]) {
-    const int words = a.ow * a.oh / 4;
-    for (int pl = 0; pl < a.n_planes; ++pl) {
-      if (pl == a.slot) continue;
-      uint32_t* dst = reinterpret_cast<uint32_t*>(env_base + (long long)pl * a.plane_stride);
-      for (int i = tid; i < words; i += kRasterThreads) dst[i] = 0u;
-    }
-  }
-  __syncthreads();
-
-  // ---- 2. bin the sprites: cell (cx, cy) = 32x32 full-resolution pixels, y counted from the top row
-  if (tid < n_sprites) {
-    const gca_sprite_pose p = pose[tid];
-    const float ytop = (float)a.H - p.cy;
-    const int x0 = (int)floorf((p.cx - GCA_SPRITE_REACH) * (1.0f / 32.0f));
-    const int x1 = (int)floorf((p.cx + GCA_SPRITE_REACH) * (1.0f / 32.0f));
-    const int y0 = (int)floorf((ytop - GCA_SPRITE_REACH) * (1.0f / 32.0f));
-    const int y1 = (int)floorf((ytop + GCA_SPRITE_REACH) * (1.0f / 32.0f));
-    for (int cy = max(y0, 0); cy <= min(y1, a.cells_y - 1); ++cy)
-      for (int cx = max(x0, 0); cx <= min(x1, a.cells_x - 1); ++cx)
-        atomicOr(reinterpret_cast<unsigned int*>(&cell_mask[cy * a.cells_x + cx]) + (tid >> 5), 1u << (tid & 31));
-  }
-  __syncthreads();
-
-  // ---- 3. background: the whole plane is white; ---- 4. sprite-centric pass over covered pixels only
-  uint8_t* out = env_base + (long long)a.slot * a.plane_stride;
-  {
-    uint4* o4 = reinterpret_cast<uint4*>(out);
-    const int n16 = a.ow * a.oh / 16;
-    const uint4 white = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-    for (int i = tid; i < n16; i += kRasterThreads) o4[i] = white;
-  }
-  __syncthreads();
-  // One warp per sprite: lanes walk the output pixels of the sprite's bounding box.  A pixel's value
-  // depends on ALL sprites of its cell (blended in draw order), so pixels shared by two boxes are
-  // computed twice and written twice with the same byte - benign.
-  const int lane = tid & 31, warp = tid >> 5;
-  for (int k0 = warp; k0 < n_sprites; k0 += kRasterThreads / 32) {
-    const gca_sprite_pose me = pose[k0];
-    const float ytop = (float)a.H - me.cy;
-    const int bx0 = max((int)floorf((me.cx - GCA_SPRITE_REACH) * 0.25f), 0);
-    const int bx1 = min((int)floorf((me.cx + GCA_SPRITE_REACH) * 0.25f), a.ow - 1);
-    const int by0 = max((int)floorf((ytop - GCA_SPRITE_REACH) * 0.25f), 0);
-    const int by1 = min((int)floorf((ytop + GCA_SPRITE_REACH) * 0.25f), a.oh - 1);
-    const int nx = bx1 - bx0 + 1, ny = by1 - by0 + 1;
-    if (nx <= 0 || ny <= 0) continue;
-    for (int p = lane; p < nx * ny; p += 32) {
-      const int oy = by0 + p / nx, ox = bx0 + p % nx;
-      const uint4 m = cell_mask[(oy >> 3) * a.cells_x + (ox >> 3)];
-      const uint32_t words[4] = {m.x, m.y, m.z, m.w};
-      // sprites of the cell that can reach this pixel at all (centre distance test, conservative)
-      const float pcx = (float)(4 * ox) + 2.0f, pcy = (float)a.H - ((float)(4 * oy) + 2.0f);
-      uint32_t live[4];
-      bool any = false;
-      for (int w = 0; w < 4; ++w) {
-        uint32_t bits = words[w], keep = 0u;
-        while (bits) {
-          const int j = __ffs(bits) - 1;
-          bits &= bits - 1;
-          const gca_sprite_pose sp = pose[w * 32 + j];
-          if (fabsf(pcx - sp.cx) <= GCA_SPRITE_REACH + 2.0f && fabsf(pcy - sp.cy) <= GCA_SPRITE_REACH + 2.0f) keep |= 1u << j;
+        const int i = tid - 2;
+        float px, py;
+        const uint8_t* pl = s.ipos + (size_t)(s.counters[env].z & 1) * s.pos_plane;   // the env's current positions
+        if (a.faithful) {
+          const double2 q = *reinterpret_cast<const double2*>(pl + ipos_offset(s, true, (size_t)env, i));
+          px = (float)q.x; py = (float)q.y;
+        } else {
+          const float2 q = *reinterpret_cast<const float2*>(pl + ipos_offset(s, false, (size_t)env, i));
+          px = q.x; py = q.y;
         }
-        live[w] = keep;
-        any |= keep != 0u;
+        const float2 v = *reinterpret_cast<const float2*>(s.ivel + ivel_offset(s, (size_t)env, i));
+        // the intruder's heading is constant for life (:207-211); its direction is that of the velocity
+        const float len = __fsqrt_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)));
+        const float ch = __fdiv_rn(v.x, len), sh = __fdiv_rn(v.y, len);
+        p = make_float4(px, py, sh, -ch);
       }
-      if (!any) continue;
-      int sum = 0;
-      bool touched = false;
-      for (int sy = 0; sy < 4; ++sy) {
-        const float wy = (float)a.H - ((float)(4 * oy + sy) + 0.5f);
-        for (int sx = 0; sx < 4; ++sx) {
-          const float wx = (float)(4 * ox + sx) + 0.5f;
-          int r = 255, g = 255, b = 255;                                  // white clear
-          for (int w = 0; w < 4; ++w) {
-            uint32_t bits = live[w];
-            while (bits) {
-              const int k = w * 32 + __ffs(bits) - 1;
-              bits &= bits - 1;
-              const gca_sprite_pose sp = pose[k];
-              touched |= gca_raster_sample(sp, tex + sp.tex * (32 * 32 * 4), wx, wy, &r, &g, &b) != 0;
-            }
+      pose[tid] = p;
+      // bounding box in output pixels (x0 > x1 or y0 > y1: nothing on the canvas)
+      const float ytop = (float)a.H - p.y;
+      const float fx0 = floorf((p.x - GCA_SPRITE_REACH) * 0.25f), fx1 = floorf((p.x + GCA_SPRITE_REACH) * 0.25f);
+      const float fy0 = floorf((ytop - GCA_SPRITE_REACH) * 0.25f), fy1 = floorf((ytop + GCA_SPRITE_REACH) * 0.25f);
+      box[tid] = make_short4((short)fminf(fmaxf(fx0, 0.0f), (float)a.ow), (short)fminf(fmaxf(fx1, -1.0f), (float)(a.ow - 1)),
+                             (short)fminf(fmaxf(fy0, 0.0f), (float)a.oh), (short)fminf(fmaxf(fy1, -1.0f), (float)(a.oh - 1)));
+    }
+    for (int i = tid; i < n_cells; i += kRasterThreads) cell_mask[i] = make_uint4(0u, 0u, 0u, 0u);
+    {
+      uint4* o4 = reinterpret_cast<uint4*>(plane);                        // white clear
+      const uint4 white = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+      for (int i = tid; i < (plane_bytes + 15) / 16; i += kRasterThreads) o4[i] = white;
+    }
+    // VecFrameStack: a finished env starts from an all-zero stack (vec_frame_stack.py:19-23)
+    uint8_t* env_base = a.frames + (long long)env * a.env_stride;
+    if (a.clear_mask && a.clear_mask[env]) {
+      const int words = plane_bytes / 4;
+      for (int pl = 0; pl < a.n_planes; ++pl) {
+        if (pl == a.slot) continue;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(env_base + (long long)pl * a.plane_stride);
+        for (int i = tid; i < words; i += kRasterThreads) dst[i] = 0u;
+      }
+    }
+    __syncthreads();
+
+    // ---- bin the sprites into cells (their bounding boxes, in output pixels)
+    if (tid < n_sprites) {
+      const short4 bb = box[tid];
+      for (int cy = bb.z >> kCellShift; cy <= (bb.w >> kCellShift) && bb.z <= bb.w; ++cy)
+        for (int cx = bb.x >> kCellShift; cx <= (bb.y >> kCellShift) && bb.x <= bb.y; ++cx)
+          atomicOr(reinterpret_cast<unsigned int*>(&cell_mask[cy * a.cells_x + cx]) + (tid >> 5), 1u << (tid & 31));
+    }
+    __syncthreads();
+
+    // ---- 2 + 3. one warp per sprite
+    const int half = lane >> 4, sidx = lane & 15;
+    const float sxo = (float)(sidx & 3) + 0.5f, syo = (float)(sidx >> 2) + 0.5f;
+    // shade list[i] (lanes 0-15) and list[i + 1] (lanes 16-31, if two)
+    auto shade_pair = [&](int i, bool two) {
+      const bool valid = half == 0 || two;
+      const uint2 e = list[valid ? i + half : i];
+      const int ox = (int)(e.x & 0xffffu), oy = (int)(e.x >> 16);
+      const float wx = __fadd_rn((float)(4 * ox), sxo);
+      const float wy = __fadd_rn((float)a.H, -__fadd_rn((float)(4 * oy), syo));
+      float r = 255.0f, g = 255.0f, b = 255.0f;                            // white clear
+      if (e.y != kScanCell) {
+        uint32_t ids = e.y;                                                // <= 4 sprites in draw order, 0xff ends
+        while ((ids & 0xffu) != 0xffu) {
+          const int j = (int)(ids & 0xffu);
+          ids = (ids >> 8) | 0xff000000u;
+          raster_sample_fast(pose[j], min(j, 2), texf, cls, wx, wy, r, g, b);
+        }
+      } else {
+        const uint4 m = cell_mask[(oy >> kCellShift) * a.cells_x + (ox >> kCellShift)];
+        const uint32_t words[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          uint32_t bits = words[w];
+          while (bits) {
+            const int j = w * 32 + __ffs(bits) - 1;
+            bits &= bits - 1;
+            raster_sample_fast(pose[j], min(j, 2), texf, cls, wx, wy, r, g, b);
           }
-          sum += gca_gray_u8(r, g, b);
         }
       }
-      if (touched) out[oy * a.ow + ox] = (uint8_t)gca_area16_u8(sum);
+      // cv2 RGB2GRAY in exact float arithmetic (every intermediate is an integer < 2^24), then >> 15
+      const float gx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(9798.0f, r), __fmul_rn(19235.0f, g)), __fmul_rn(3735.0f, b)), 16384.0f);
+      const int gray = __float2int_rn(gx) >> 15;
+      const int both = __reduce_add_sync(0xffffffffu, gray << (half * 16));
+      if (sidx == 0 && valid) plane[oy * a.ow + ox] = (uint8_t)gca_area16_u8((both >> (half * 16)) & 0xffff);
+    };
+
+    for (int k0 = warp; k0 < n_sprites; k0 += kRasterWarps) {
+      const float4 me = pose[k0];
+      const uint16_t* my_sat = sat_all + min(k0, 2) * kSat * kSat;
+      const short4 mb = box[k0];
+      const int bx0 = mb.x, by0 = mb.z;
+      const int nx = mb.y - mb.x + 1, ny = mb.w - mb.z + 1;
+      if (nx <= 0 || ny <= 0) continue;
+      int cnt = 0;
+      for (int base = 0; base < nx * ny; base += 32) {
+        // 2. pixels this sprite owns: live for it and for no sprite drawn earlier
+        const int p = base + lane;
+        bool keep = false;
+        uint2 entry = make_uint2(0u, 0u);
+        if (p < nx * ny) {
+          const int oy = by0 + p / nx, ox = bx0 + p % nx;
+          const float pcx = (float)(4 * ox) + 2.0f, pcy = (float)a.H - ((float)(4 * oy) + 2.0f);
+          if (pixel_live(me, my_sat, pcx, pcy)) {
+            const uint4 m = cell_mask[(oy >> kCellShift) * a.cells_x + (ox >> kCellShift)];
+            const uint32_t words[4] = {m.x, m.y, m.z, m.w};
+            uint32_t ids = 0xffffff00u | (uint32_t)k0;
+            int nid = 1;
+            keep = true;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              uint32_t bits = words[w];
+              while (bits && keep) {
+                const int j = w * 32 + __ffs(bits) - 1;
+                bits &= bits - 1;
+                if (j == k0) continue;
+                const short4 jb = box[j];
+                if (ox >= jb.x && ox <= jb.y && oy >= jb.z && oy <= jb.w &&
+                    pixel_live(pose[j], sat_all + min(j, 2) * kSat * kSat, pcx, pcy)) {
+                  if (j < k0) keep = false;                                // an earlier sprite owns this pixel
+                  else if (nid < 4) { ids = (ids & ~(0xffu << (8 * nid))) | ((uint32_t)j << (8 * nid)); ++nid; }
+                  else ids = kScanCell;
+                }
+              }
+            }
+            entry = make_uint2((uint32_t)ox | ((uint32_t)oy << 16), nid > 4 || ids == kScanCell ? kScanCell : ids);
+          }
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) list[cnt + __popc(bal & ((1u << lane) - 1u))] = entry;
+        cnt += __popc(bal);
+        __syncwarp();
+        // 3. shade two pixels per pass, lane = sample; an odd one is carried to the next batch
+        int i = 0;
+        for (; i + 1 < cnt; i += 2) shade_pair(i, true);
+        if (i < cnt) {
+          const uint2 last = list[i];
+          __syncwarp();
+          if (lane == 0) list[0] = last;
+          cnt = 1;
+        } else {
+          cnt = 0;
+        }
+        __syncwarp();
+      }
+      if (cnt) shade_pair(0, false);
+      __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- 4. the finished plane leaves shared memory
+    uint8_t* out = env_base + (long long)a.slot * a.plane_stride;
+    if (a.bulk_ok) {
+      if (tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     :: "l"(out), "r"(smem_u32(plane)), "r"(plane_bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    } else {
+      for (int i = tid; i < plane_bytes / 4; i += kRasterThreads)
+        reinterpret_cast<uint32_t*>(out)[i] = reinterpret_cast<const uint32_t*>(plane)[i];
     }
   }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+size_t raster_smem_bytes(int ow, int oh) {
+  const int cs = 1 << kCellShift;
+  const int cells = ((ow + cs - 1) / cs) * ((oh + cs - 1) / cs);
+  return 3 * GCA_SPRITE * GCA_SPRITE * sizeof(float4) + (((size_t)ow * oh + 15) & ~(size_t)15) + sizeof(uint4) * (size_t)cells +
+         (sizeof(float4) + sizeof(short4)) * kMaxSprites + sizeof(uint2) * kRasterWarps * kListCap +
+         sizeof(uint16_t) * 3 * kSat * kSat + ((3 * kCorner * kCorner + 15) & ~15);
 }
 
 cudaError_t launch_raster(const DevState& s, bool faithful, int W, int H, const uint8_t* sprites, uint8_t* frames,
@@ -178,13 +386,20 @@ cudaError_t launch_raster(const DevState& s, bool faithful, int W, int H, const 
                           const uint8_t* clear_mask, cudaStream_t st) {
   RasterArgs a{};
   a.s = s; a.faithful = faithful ? 1 : 0; a.W = W; a.H = H; a.ow = W / 4; a.oh = H / 4;
-  a.cells_x = (a.ow + 7) / 8; a.cells_y = (a.oh + 7) / 8;
+  a.cells_x = (a.ow + (1 << kCellShift) - 1) >> kCellShift; a.cells_y = (a.oh + (1 << kCellShift) - 1) >> kCellShift;
   a.sprites = sprites; a.frames = frames; a.env_stride = env_stride; a.plane_stride = plane_stride;
   a.n_planes = n_planes; a.slot = slot; a.clear_mask = clear_mask;
-  const size_t smem = 3 * 32 * 32 * 4 + sizeof(gca_sprite_pose) * kMaxSprites + sizeof(uint4) * (size_t)a.cells_x * a.cells_y;
+  a.bulk_ok = ((a.ow * a.oh) % 16 == 0 && env_stride % 16 == 0 && plane_stride % 16 == 0 &&
+               reinterpret_cast<uintptr_t>(frames) % 16 == 0) ? 1 : 0;
+  const size_t smem = raster_smem_bytes(a.ow, a.oh);
+  if (smem > 227 * 1024 || a.ow > 32767 || a.oh > 32767) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  raster_kernel<<<(unsigned)s.B, kRasterThreads, smem, st>>>(a);
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int per_sm = smem * 2 + 2048 <= 227 * 1024 ? 2 : 1;
+  const unsigned grid = (unsigned)min((long long)s.B, (long long)sms * per_sm);
+  raster_kernel<<<grid, kRasterThreads, smem, st>>>(a);
   return cudaGetLastError();
 }
 
