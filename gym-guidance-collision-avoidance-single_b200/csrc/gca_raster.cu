@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(kRasterThreads, 2) raster_kernel(const RasterA
   uint2* list = reinterpret_cast<uint2*>(box + kMaxSprites) + warp * kListCap;     // per warp: (ox | oy << 16, sprite ids)
   uint16_t* sat_all = reinterpret_cast<uint16_t*>(reinterpret_cast<uint2*>(box + kMaxSprites) + kRasterWarps * kListCap);
   uint8_t* cls = reinterpret_cast<uint8_t*>(sat_all + 3 * kSat * kSat);            // [3][33][33]
+  __shared__ int next_sprite;                                                      // dynamic sprite -> warp assignment
 
   // ---- 0. textures, footprint classes and their summed-area tables, once per CTA
   for (int i = tid; i < 3 * GCA_SPRITE * GCA_SPRITE; i += kRasterThreads) {
@@ -229,6 +230,7 @@ __global__ void __launch_bounds__(kRasterThreads, 2) raster_kernel(const RasterA
                              (short)fminf(fmaxf(fy0, 0.0f), (float)a.oh), (short)fminf(fmaxf(fy1, -1.0f), (float)(a.oh - 1)));
     }
     for (int i = tid; i < n_cells; i += kRasterThreads) cell_mask[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) next_sprite = 0;
     {
       uint4* o4 = reinterpret_cast<uint4*>(plane);                        // white clear
       const uint4 white = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
@@ -293,7 +295,11 @@ __global__ void __launch_bounds__(kRasterThreads, 2) raster_kernel(const RasterA
       if (sidx == 0 && valid) plane[oy * a.ow + ox] = (uint8_t)gca_area16_u8((both >> (half * 16)) & 0xffff);
     };
 
-    for (int k0 = warp; k0 < n_sprites; k0 += kRasterWarps) {
+    for (;;) {
+      int k0 = 0;
+      if (lane == 0) k0 = atomicAdd(&next_sprite, 1);                      // sprites own disjoint pixels: any order
+      k0 = __shfl_sync(0xffffffffu, k0, 0);
+      if (k0 >= n_sprites) break;
       const float4 me = pose[k0];
       const uint16_t* my_sat = sat_all + min(k0, 2) * kSat * kSat;
       const short4 mb = box[k0];
