@@ -370,19 +370,21 @@ def bench_mcts(device, with_cpu):
     out = {"metric": "mcts_rollouts_per_sec", "value": R * P / (ms * 1e-3), "unit": "rollouts/s", "roots": R,
            "playouts_per_root": P, "depth": depth, "intruders": 80, "ms_per_launch": ms,
            "mean_reward": float(rewards.mean().item()), "terminal_fraction": float((flags != 0).float().mean().item()),
-           "dtype": "f64", "bound": "fp64 pipe (no HBM roofline: a 2.6 KB root is read once per playout)"}
+           "dtype": "f64", "bound": "fp64 pipe (no HBM roofline: a 2.6 KB root is read once per CTA of 100 playouts)"}
     # FP64 roofline of the playout kernel: f64 operations per launch counted by ncu (profiles/mcts_kernel_ncu.json,
     # same workload) / the launch time measured here, against the measured non-fused DMUL+DADD peak of this pool's
     # B200 (profiles/fp64_peak.json; the parity contract forbids contracting the reference's mul/add pairs into FMAs)
     try:
         with open(os.path.join(ROOT, "profiles", "mcts_kernel_ncu.json")) as f:
-            ops = float(json.load(f)["f64_ops_per_launch"])
+            prof = json.load(f)
+            ops = float(prof["f64_ops_per_launch"])
         with open(os.path.join(ROOT, "profiles", "fp64_peak.json")) as f:
             peak = float(json.load(f)["dmul_dadd_tflops"])
         ach = ops / (ms * 1e-3) / 1e12
         out["roofline"] = {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                            "peak_source": "measured (tools/fp64_peak.cu, separate DMUL+DADD)",
-                           "ops_per_launch": ops, "fp64_pipe_pct_ncu": 45.1}
+                           "ops_per_launch": ops, "kernel": prof.get("kernel"),
+                           "fp64_pipe_pct_ncu": prof.get("fp64_pipe_pct_of_peak_sustained_active")}
     except Exception:
         pass
     env.close()
@@ -458,7 +460,8 @@ def bench_stack(device):
            "ms_per_step": ms, "kernels_per_step": 2,
            "frame_bytes_per_env_step": frame_bytes,
            "hbm_frac_frames_only": (B * frame_bytes / (ms * 1e-3) / 1e9) / peak,
-           "note": "step kernel + rasteriser; bound by the rasteriser's per-sample blending (FP32), not by HBM yet"}
+           "note": "step kernels + rasteriser; bound by the rasteriser's per-sample blending (FP32 issue, "
+                   "profiles/r1_raster_ncu_full.txt), not by HBM"}
     env.close()
     return out
 

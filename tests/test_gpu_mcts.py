@@ -74,6 +74,14 @@ def test_playouts_bit_exact_vs_oracle(n, roots_n, playouts, depth, over):
     print("n=%d flags histogram" % n, np.bincount(want_fl.ravel(), minlength=5).tolist())
 
 
+@pytest.mark.parametrize("n,roots_n,playouts,depth", [(80, 48, 40, 3), (200, 8, 12, 3), (80, 6, 8, 4)])
+def test_warp_per_playout_kernel_bit_exact(n, roots_n, playouts, depth, monkeypatch):
+    """position_sigma == 0 takes the root-cooperative kernel; the warp-per-playout kernel (any sigma) must keep
+    giving the same bits (GCA_MCTS_WARP_KERNEL forces it)."""
+    monkeypatch.setenv("GCA_MCTS_WARP_KERNEL", "1")
+    test_playouts_bit_exact_vs_oracle(n, roots_n, playouts, depth, {})
+
+
 def test_drop_in_search_classes():
     """Agent.py:37-41 call sequence on the drop-in classes."""
     from Algorithms.MCTS.nodes_single import SingleAircraftNode, SingleAircraftState
