@@ -387,10 +387,35 @@ def bench_mcts(device, with_cpu):
                            "fp64_pipe_pct_ncu": prof.get("fp64_pipe_pct_of_peak_sustained_active")}
     except Exception:
         pass
+    # device-resident UCT search: decisions/s = best_action(100 simulations, depth 3) per root
+    try:
+        R2 = 65536
+        env2 = BatchedAircraftEnv("SingleAircraftMCTSEnv", R2, SimConfig, n_intruders=80, mode="faithful", device=device, seed=3)
+        roots2 = env2.reset().clone()
+        env2.close()
+        for _ in range(2):
+            mcts.search(roots2, P, depth, cfg=cfg, seed=1)
+        torch.cuda.synchronize()
+        start.record()
+        for i in range(3):
+            mcts.search(roots2, P, depth, cfg=cfg, seed=2 + i)
+        stop.record()
+        torch.cuda.synchronize()
+        ms2 = start.elapsed_time(stop) / 3
+        out["search"] = {"metric": "mcts_decisions_per_sec", "value": R2 / (ms2 * 1e-3), "unit": "searches/s",
+                         "roots": R2, "simulations": P, "depth": depth, "ms_per_launch": ms2,
+                         "simulations_per_sec": R2 * P / (ms2 * 1e-3),
+                         "api": "gca_mcts_search (UCT tree per root resident on the device, one lane per root)"}
+    except Exception as exc:                                          # pragma: no cover
+        out["search"] = {"error": str(exc)}
     env.close()
     if with_cpu:
         from oracle import oracle as orc
         sample = roots[:8].cpu().numpy()
+        t0 = time.perf_counter()
+        orc.mcts_search_philox(cfg, 80, sample, P, depth, seed=2)
+        out["search"]["cpu_baseline"] = {"value": 8 / (time.perf_counter() - t0), "unit": "searches/s", "cores": 1,
+                                         "kind": "port", "sample": "8 roots x 100 simulations, C oracle port, 1 thread"}
         t0 = time.perf_counter()
         orc.mcts_playouts(cfg, 80, sample, 50, depth, seed=6)
         dt = time.perf_counter() - t0

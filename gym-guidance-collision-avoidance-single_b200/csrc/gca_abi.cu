@@ -366,6 +366,14 @@ int gca_observe(gca_env* e, const gca_out* out, void* stream) {
   return GCA_OK;
 }
 
+int gca_read_counters(gca_env* e, int32_t* counters, void* stream) {
+  if (!e || !counters) return fail(GCA_ERR_INVALID, "env/counters is NULL");
+  GCA_CUDA(cudaSetDevice(e->device));
+  GCA_CUDA(cudaMemcpyAsync(counters, e->s.counters, (size_t)e->s.B * sizeof(int4), cudaMemcpyDeviceToDevice,
+                           (cudaStream_t)stream));
+  return GCA_OK;
+}
+
 // ------------------------------------------------------------------------------ host-buffer path
 static int ensure_host_path(gca_env* e) {
   if (e->stream) return GCA_OK;
@@ -559,6 +567,31 @@ int gca_mcts_playouts(const gca_mcts_config* cfg, int n_intruders, const double*
   GCA_CUDA(cudaSetDevice(device));
   GCA_CUDA(launch_mcts_playouts(cfg, n_intruders, roots, (long long)n_roots, playouts, depth, first_action, seed,
                                 root_id0, rewards, first_out, flags, (cudaStream_t)stream));
+  return GCA_OK;
+}
+
+int64_t gca_mcts_search_workspace(const gca_mcts_config* cfg, int n_intruders, int64_t n_roots, int simulations,
+                                  int depth) {
+  if (!cfg || n_intruders < 0 || n_roots < 0 || simulations < 0 || depth < 0) return -1;
+  return (int64_t)mcts_search_workspace_bytes(cfg, n_intruders, (long long)n_roots, simulations, depth);
+}
+
+int gca_mcts_search(const gca_mcts_config* cfg, int n_intruders, const double* roots, int64_t n_roots, int simulations,
+                    int depth, uint64_t seed, uint32_t root_id0, void* workspace, int64_t workspace_bytes,
+                    int32_t* best_action, double* child_n, double* child_q, int32_t* child_action, int device,
+                    void* stream) {
+  if (!cfg || n_intruders < 0 || n_roots < 0 || simulations < 0 || depth < 0 || (n_roots > 0 && (!roots || !best_action)))
+    return fail(GCA_ERR_INVALID, "bad arguments");
+  if (cfg->simulate_frame <= 0) return fail(GCA_ERR_INVALID, "simulate_frame must be positive");
+  if (cfg->position_sigma != 0.0)
+    return fail(GCA_ERR_STATE, "the device-resident search needs position_sigma == 0 (use the node classes otherwise)");
+  if (simulations > 32000 || depth > 127) return fail(GCA_ERR_INVALID, "at most 32000 simulations and depth 127");
+  const int64_t need = gca_mcts_search_workspace(cfg, n_intruders, n_roots, simulations, depth);
+  if (n_roots > 0 && (!workspace || workspace_bytes < need || reinterpret_cast<uintptr_t>(workspace) % 16))
+    return fail(GCA_ERR_INVALID, "workspace missing, misaligned or smaller than gca_mcts_search_workspace()");
+  GCA_CUDA(cudaSetDevice(device));
+  GCA_CUDA(launch_mcts_search(cfg, n_intruders, roots, (long long)n_roots, simulations, depth, seed, root_id0, workspace,
+                              best_action, child_n, child_q, child_action, (cudaStream_t)stream));
   return GCA_OK;
 }
 

@@ -17,6 +17,10 @@ cudaError_t launch_mcts_playouts(const gca_mcts_config* cfg, int n, const double
 cudaError_t launch_mcts_move(const gca_mcts_config* cfg, int n, double* states, const int32_t* actions, uint8_t* flags,
                              long long m, const double* tape, long long tape_stride, long long* cursor, uint64_t seed,
                              uint32_t id0, int first_frame, cudaStream_t st);
+size_t mcts_search_workspace_bytes(const gca_mcts_config* cfg, int n, long long n_roots, int sims, int depth);
+cudaError_t launch_mcts_search(const gca_mcts_config* cfg, int n, const double* roots, long long n_roots, int sims,
+                               int depth, uint64_t seed, uint32_t root_id0, void* workspace, int32_t* best_action,
+                               double* child_n, double* child_q, int32_t* child_action, cudaStream_t st);
 cudaError_t launch_raster(const DevState& s, bool faithful, int W, int H, const uint8_t* sprites, uint8_t* frames,
                           long long env_stride, long long plane_stride, int n_planes, int slot,
                           const uint8_t* clear_mask, cudaStream_t st);

@@ -38,6 +38,13 @@ struct MctsArgs {
   double* rewards;
   int8_t* first_out;
   uint8_t* flags;
+  // search
+  int sims;
+  uint8_t* workspace;
+  size_t ws_root_stride, ws_cand_off, ws_node_off;
+  int32_t* best_action;
+  double *child_n, *child_q;
+  int32_t* child_action;
   // move
   double* states;
   const int32_t* actions;
@@ -335,6 +342,183 @@ __global__ void __launch_bounds__(kSharedThreads) mcts_playout_shared_kernel(con
   }
 }
 
+// ------------------------------------------------------------------------------ device-resident UCT search
+// MCTS(root).best_action(simulations, search_depth) (search_single.py:8-22; tree_policy / expand / best_child /
+// backpropagate: common.py:47-52, nodes_single.py:188-210) for a batch of roots, position_sigma == 0.  Because the
+// intruders of the model then follow root-only trajectories and a non-terminal node of depth d has executed exactly
+// d * simulate_frame sub-frames, a tree node needs only the ownship (x, y, vy, heading): 80 bytes per node.
+//   mcts_candidates_kernel: CTA per root - phase 1 of the playout kernel, candidate lists written to the workspace;
+//   mcts_search_kernel:     lane per root - the search is sequential in its simulations, and 32 independent roots
+//                           per warp keep every lane busy: selection (UCT in f64 with the shared log), expansion
+//                           (untried actions popped from the end, Q27), rollout, back-propagation.
+// Draws: Philox keyed (seed; root id, simulation index, kind, global sub-frame) - simulation s of a root is
+// "playout" s of the playout kernels.  Bit-exact against gca_oracle_mcts_search_philox.
+struct __align__(16) TreeNode {
+  double ox, oy, vy, heading;
+  double q;
+  int n;
+  short parent;
+  signed char depth, flags, action, untried, n_children, pad;
+  short children[9];
+};
+static_assert(sizeof(TreeNode) == 80, "tree node layout");
+
+// simulate_frame sub-frames of move(action) from global sub-frame depth * F (nodes_single.py:39-100); returns the flags
+__device__ __forceinline__ int lane_move(const MctsArgs& a, const int* __restrict__ cnt, const double2* __restrict__ cand,
+                                         uint32_t root, uint32_t sim, int depth, int act, double gx, double gy,
+                                         double& ox, double& oy, double& vy_prev, double& heading) {
+  const gca_mcts_config& c = a.c;
+  const int F = c.simulate_frame;
+  const double d_heading = __dmul_rn((double)(act / 3 - 1), c.d_heading);
+  for (int f = 0; f < F; ++f) {
+    const int gf = depth * F + f;
+    const double nh = mcts_normal(a, c.heading_sigma, root, sim, GCA_MCTS_DRAW_HEADING, (uint32_t)gf);
+    const double nsp = mcts_normal(a, c.speed_sigma, root, sim, GCA_MCTS_DRAW_SPEED, (uint32_t)gf);
+    double sp = clamp_speed(c, vy_prev);                              // state[-4] = clamp(state[-5])  (Q23)
+    sp = __dadd_rn(sp, nsp);
+    heading = __dadd_rn(heading, d_heading);
+    heading = __dadd_rn(heading, nh);
+    double sn, cs;
+    gca_sincos(heading, &sn, &cs);
+    const double vx = __dmul_rn(sp, cs), vy = __dmul_rn(sp, sn);
+    ox = __dadd_rn(ox, vx);
+    oy = __dadd_rn(oy, vy);
+    vy_prev = vy;
+    if (!(0.0 < ox && ox < c.window_width) || !(0.0 < oy && oy < c.window_height)) return GCA_MCTS_WALL;
+    bool hit = false;
+    const double2* cf = cand + (size_t)gf * a.near;
+    const int nc = cnt[gf];
+    for (int k = 0; k < nc; ++k) {
+      const double2 q = cf[k];
+      const double dx = __dadd_rn(q.x, -ox), dy = __dadd_rn(q.y, -oy);
+      hit |= __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < a.sep2;
+    }
+    if (hit) return GCA_MCTS_CONFLICT;
+    const double dx = __dadd_rn(ox, -gx), dy = __dadd_rn(oy, -gy);
+    if (__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < a.sep2) return GCA_MCTS_GOAL;
+  }
+  return 0;
+}
+
+__device__ __forceinline__ double lane_reward(int flags, double ox, double oy, double gx, double gy) {
+  if (flags & (GCA_MCTS_WALL | GCA_MCTS_CONFLICT)) return 0.0;
+  if (flags & GCA_MCTS_GOAL) return 1.0;
+  const double dx = __dadd_rn(ox, -gx), dy = __dadd_rn(oy, -gy);
+  const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+  return __dadd_rn(1.0, -__ddiv_rn(dist, 1200.0));
+}
+
+// intruder trajectories of one root -> per-sub-frame candidate lists (shared by both users)
+__device__ __forceinline__ void build_candidates(const MctsArgs& a, const double* st, int TF, int* cnt, double2* cand,
+                                                 int tid, int nthreads) {
+  const gca_mcts_config& c = a.c;
+  const double* own = st + 4 * a.n;
+  const double ox0 = own[0], oy0 = own[1];
+  const bool cull = c.speed_sigma == 0.0;
+  const double vmax = fmax(fabs(c.min_speed), fabs(c.max_speed));
+  for (int i = tid; i < a.near; i += nthreads) {
+    const double2 p0 = reinterpret_cast<const double2*>(st)[2 * i];
+    const double2 v0 = reinterpret_cast<const double2*>(st)[2 * i + 1];
+    double x = p0.x, y = p0.y;
+    const double vx = __dadd_rn(v0.x, 0.0), vy = __dadd_rn(v0.y, 0.0);       // vx + normal(0, 0) :54-57
+    for (int f = 0; f < TF; ++f) {
+      x = __dadd_rn(x, vx);
+      y = __dadd_rn(y, vy);
+      bool in = true;
+      if (cull) {
+        const double reach = c.minimum_separation + (double)(f + 1) * vmax * 1.000001 + 0.5;
+        const double dx = x - ox0, dy = y - oy0;
+        in = !(dx * dx + dy * dy >= reach * reach);
+      }
+      if (in) cand[(size_t)f * a.near + atomicAdd(&cnt[f], 1)] = make_double2(x, y);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) mcts_candidates_kernel(const MctsArgs a) {
+  const int TF = a.depth * a.c.simulate_frame;
+  uint8_t* ws = a.workspace + (size_t)blockIdx.x * a.ws_root_stride;
+  int* cnt = reinterpret_cast<int*>(ws);
+  double2* cand = reinterpret_cast<double2*>(ws + a.ws_cand_off);
+  for (int f = threadIdx.x; f < TF; f += 128) cnt[f] = 0;
+  __syncthreads();
+  build_candidates(a, a.roots + (long long)blockIdx.x * a.L, TF, cnt, cand, threadIdx.x, 128);
+}
+
+__global__ void __launch_bounds__(128) mcts_search_kernel(const MctsArgs a) {
+  const long long r_idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r_idx >= a.n_roots) return;
+  const uint32_t root = a.root_id0 + (uint32_t)r_idx;
+  const double* own = a.roots + r_idx * a.L + 4 * a.n;
+  uint8_t* ws = a.workspace + (size_t)r_idx * a.ws_root_stride;
+  const int* cnt = reinterpret_cast<const int*>(ws);
+  const double2* cand = reinterpret_cast<const double2*>(ws + a.ws_cand_off);
+  TreeNode* nodes = reinterpret_cast<TreeNode*>(ws + a.ws_node_off);
+  const double gx = own[6], gy = own[7];
+  const int D = a.depth;
+
+  TreeNode rt{};
+  rt.ox = own[0]; rt.oy = own[1]; rt.vy = own[3]; rt.heading = own[5];
+  rt.parent = -1; rt.action = -1; rt.untried = 9;
+  nodes[0] = rt;
+  int count = 1;
+
+  auto best_child = [&](int v, double c_param) -> int {              // common.py:47-52, np.argmax: first maximum
+    const TreeNode& nv = nodes[v];
+    const double lg2 = __dmul_rn(2.0, gca_log((double)nv.n));
+    int best = -1;
+    double best_w = 0.0;
+    for (int k = 0; k < nv.n_children; ++k) {
+      const int ci = nv.children[k];
+      const double cn = (double)nodes[ci].n;
+      const double w = __dadd_rn(__ddiv_rn(nodes[ci].q, cn), __dmul_rn(c_param, __dsqrt_rn(__ddiv_rn(lg2, cn))));
+      if (best < 0 || w > best_w) { best = ci; best_w = w; }
+    }
+    return best;
+  };
+
+  for (int s = 0; s < a.sims; ++s) {
+    int v = 0;                                                        // tree_policy  search_single.py:16-22
+    while (!(nodes[v].flags || nodes[v].depth == D)) {
+      if (nodes[v].untried > 0) {                                     // expand()  nodes_single.py:188-193
+        const int act = --nodes[v].untried;
+        TreeNode ch = nodes[v];
+        const int pd = ch.depth;
+        ch.flags = (signed char)lane_move(a, cnt, cand, root, (uint32_t)s, pd, act, gx, gy, ch.ox, ch.oy, ch.vy, ch.heading);
+        ch.parent = (short)v; ch.depth = (signed char)(pd + 1); ch.action = (signed char)act; ch.untried = 9;
+        ch.n_children = 0; ch.q = 0.0; ch.n = 0;
+        nodes[count] = ch;
+        nodes[v].children[nodes[v].n_children++] = (short)count;
+        v = count++;
+        break;
+      }
+      v = best_child(v, 1.4);
+    }
+    // rollout()  nodes_single.py:198-204
+    double ox = nodes[v].ox, oy = nodes[v].oy, vy = nodes[v].vy, heading = nodes[v].heading;
+    int flags = nodes[v].flags, depth = nodes[v].depth;
+    while (!(flags || depth == D)) {
+      const int act = mcts_action(a, root, (uint32_t)s, (uint32_t)depth);
+      flags = lane_move(a, cnt, cand, root, (uint32_t)s, depth, act, gx, gy, ox, oy, vy, heading);
+      ++depth;
+    }
+    const double reward = lane_reward(flags, ox, oy, gx, gy);
+    for (int u = v; u >= 0; u = nodes[u].parent) {                    // backpropagate  nodes_single.py:206-210
+      nodes[u].n += 1;
+      nodes[u].q = __dadd_rn(nodes[u].q, reward);
+    }
+  }
+  const int b = best_child(0, 0.0);
+  a.best_action[r_idx] = b >= 0 ? nodes[b].action : -1;
+  for (int k = 0; k < 9; ++k) {
+    const bool has = k < nodes[0].n_children;
+    const int ci = has ? nodes[0].children[k] : 0;
+    if (a.child_n) a.child_n[r_idx * 9 + k] = has ? (double)nodes[ci].n : 0.0;
+    if (a.child_q) a.child_q[r_idx * 9 + k] = has ? nodes[ci].q : 0.0;
+    if (a.child_action) a.child_action[r_idx * 9 + k] = has ? nodes[ci].action : -1;
+  }
+}
+
 // SingleAircraftState.move for m independent states, one thread each, in the reference's own
 // sequential order (used by the drop-in node classes and by the tape-replay parity tests).
 __global__ void __launch_bounds__(128) mcts_move_kernel(const MctsArgs a) {
@@ -446,6 +630,36 @@ cudaError_t launch_mcts_playouts(const gca_mcts_config* cfg, int n, const double
       mcts_playout_kernel<0><<<blocks, kMctsWarps * 32, smem, st>>>(a);
     }
   }
+  return cudaGetLastError();
+}
+
+static void search_layout(int near, long long tf, int sims, size_t* cand_off, size_t* node_off, size_t* stride) {
+  *cand_off = ((size_t)tf * 4 + 15) & ~(size_t)15;
+  *node_off = *cand_off + sizeof(double2) * (size_t)tf * (size_t)near;
+  *stride = *node_off + sizeof(TreeNode) * ((size_t)sims + 1);
+}
+
+size_t mcts_search_workspace_bytes(const gca_mcts_config* cfg, int n, long long n_roots, int sims, int depth) {
+  MctsArgs a = mcts_base(cfg, n);
+  size_t co, no, st;
+  search_layout(a.near, (long long)depth * cfg->simulate_frame, sims, &co, &no, &st);
+  return st * (size_t)(n_roots > 0 ? n_roots : 0);
+}
+
+cudaError_t launch_mcts_search(const gca_mcts_config* cfg, int n, const double* roots, long long n_roots, int sims,
+                               int depth, uint64_t seed, uint32_t root_id0, void* workspace, int32_t* best_action,
+                               double* child_n, double* child_q, int32_t* child_action, cudaStream_t st) {
+  MctsArgs a = mcts_base(cfg, n);
+  a.roots = roots; a.n_roots = n_roots; a.sims = sims; a.depth = depth;
+  a.key0 = (uint32_t)seed; a.key1 = (uint32_t)(seed >> 32); a.root_id0 = root_id0;
+  a.workspace = static_cast<uint8_t*>(workspace);
+  search_layout(a.near, (long long)depth * cfg->simulate_frame, sims, &a.ws_cand_off, &a.ws_node_off, &a.ws_root_stride);
+  a.best_action = best_action; a.child_n = child_n; a.child_q = child_q; a.child_action = child_action;
+  if (n_roots <= 0) return cudaSuccess;
+  mcts_candidates_kernel<<<(unsigned)n_roots, 128, 0, st>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  mcts_search_kernel<<<(unsigned)((n_roots + 31) / 32), 32, 0, st>>>(a);
   return cudaGetLastError();
 }
 

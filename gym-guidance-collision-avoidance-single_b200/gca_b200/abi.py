@@ -108,6 +108,7 @@ def load():
         "gca_get_state": ([vp, P(GcaHostState)], C.c_int),
         "gca_set_state": ([vp, P(GcaHostState)], C.c_int),
         "gca_observe": ([vp, P(GcaOut), vp], C.c_int),
+        "gca_read_counters": ([vp, vp, vp], C.c_int),
         "gca_step_launches": ([vp], C.c_int),
         "gca_profile_enable": ([vp, i32], C.c_int),
         "gca_profile_read": ([vp, P(GcaStepProfile)], C.c_int),
@@ -115,6 +116,8 @@ def load():
         "gca_raster": ([vp, vp, vp, i64, i64, i32, i32, vp, vp], C.c_int),
         "gca_mcts_move": ([P(GcaMctsConfig), i32, vp, vp, vp, i64, P(GcaTape), u64, u32, i32, i32, vp], C.c_int),
         "gca_mcts_playouts": ([P(GcaMctsConfig), i32, vp, i64, i32, i32, vp, u64, u32, vp, vp, vp, i32, vp], C.c_int),
+        "gca_mcts_search_workspace": ([P(GcaMctsConfig), i32, i64, i32, i32], C.c_int64),
+        "gca_mcts_search": ([P(GcaMctsConfig), i32, vp, i64, i32, i32, u64, u32, vp, i64, vp, vp, vp, vp, i32, vp], C.c_int),
     }
     for name, (argtypes, restype) in sigs.items():
         fn = getattr(lib, name)

@@ -155,6 +155,13 @@ class BatchedAircraftEnv(object):
         self.launches += 1
         return self.obs
 
+    def counters(self):
+        """Device int32 [B, 4]: (no_conflict, steps of the current episode, Philox tick, finished episodes)."""
+        torch = _torch()
+        out = torch.empty((self.num_envs, 4), dtype=torch.int32, device=self.device)
+        abi.check(self.lib.gca_read_counters(self._h, out.data_ptr(), self._stream()))
+        return out
+
     # ------------------------------------------------------------------ host-buffer (end-to-end) API
     def _host_buffers(self):
         if self._host is None:

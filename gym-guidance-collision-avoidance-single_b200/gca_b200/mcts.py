@@ -77,6 +77,111 @@ def playouts(roots, n_playouts, depth=None, cfg=None, first_action=None, seed=0,
     return rewards, first, flags
 
 
+_workspaces = {}
+
+
+def search(roots, n_simulations=None, depth=None, cfg=None, seed=0, root_id0=0, return_children=False):
+    """MCTS(root).best_action(no_simulations, search_depth) (search_single.py:8-22) for R roots at once, the UCT
+    trees resident on the device (csrc/gca_mcts.cu: mcts_search_kernel, one lane per root).
+
+    roots: CUDA float64 [R, 4N+8] raw observations of Simulators/SingleAircraftMCTSEnv.  Needs position_sigma == 0
+    (the reference's config); otherwise use the node classes of Algorithms/MCTS.
+    Returns int64 [R, 2] = best_node.state.prev_action per root (Algorithms/MCTS/Agent.py:41), and with
+    return_children also (child_n f64 [R, 9], child_q f64 [R, 9], child_action int32 [R, 9])."""
+    torch = _torch()
+    lib = abi.load()
+    cfg_cls = default_config()
+    cfg = cfg or abi.make_mcts_config(cfg_cls)
+    sims = int(cfg_cls.no_simulation if n_simulations is None else n_simulations)
+    depth = cfg.search_depth if depth is None else int(depth)
+    roots = roots.to(torch.float64).contiguous()
+    assert roots.is_cuda
+    R, L = roots.shape
+    n = (L - 8) // 4
+    dev = roots.device
+    need = int(lib.gca_mcts_search_workspace(C.byref(cfg), n, R, sims, depth))
+    key = (dev.index or 0)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 16), dtype=torch.uint8, device=dev)    # scratch, reused by later calls
+        _workspaces[key] = ws
+    best = torch.empty(R, dtype=torch.int32, device=dev)
+    cn = torch.empty((R, 9), dtype=torch.float64, device=dev)
+    cq = torch.empty((R, 9), dtype=torch.float64, device=dev)
+    ca = torch.empty((R, 9), dtype=torch.int32, device=dev)
+    abi.check(lib.gca_mcts_search(C.byref(cfg), n, roots.data_ptr(), R, sims, depth, int(seed), int(root_id0),
+                                  ws.data_ptr(), ws.numel(), best.data_ptr(), cn.data_ptr(), cq.data_ptr(),
+                                  ca.data_ptr(), dev.index or 0, _stream(dev)))
+    b = best.to(torch.int64)
+    act = torch.stack([b // 3, b % 3], -1)
+    return (act, cn, cq, ca) if return_children else act
+
+
+def run_experiment(num_envs, no_episodes, no_simulations=None, search_depth=None, seed=0, device=0, replan_every=5,
+                   max_steps=None, sim_config=None):
+    """Algorithms/MCTS/Agent.py:12-63 run_experiment, batched: `num_envs` SingleAircraftMCTSEnv instances advance
+    together; every `replan_every` steps (Agent.py:34) each env's raw observation becomes the root of a device-resident
+    UCT search whose best first action is repeated until the next re-plan.  Runs until `no_episodes` episodes have
+    finished (in order of completion) and returns the statistics the reference prints (:55-62) plus throughput."""
+    import time
+    torch = _torch()
+    from .batched import BatchedAircraftEnv
+    if sim_config is None:
+        from Simulators.config import Config as sim_config
+    cfg_cls = default_config()
+    cfg = abi.make_mcts_config(cfg_cls)
+    env = BatchedAircraftEnv("SingleAircraftMCTSEnv", num_envs, sim_config, mode="faithful", device=device, seed=seed)
+    obs = env.reset()
+    B = num_envs
+    dev = obs.device
+    t_in_ep = torch.zeros(B, dtype=torch.int64, device=dev)          # episode_time_step + 1 of each env
+    action = torch.zeros((B, 2), dtype=torch.int64, device=dev)
+    ret = torch.zeros(B, dtype=torch.float64, device=dev)
+    results = {"n": 0, "g": 0, "other": 0}
+    conflicts, returns, lengths = [], [], []
+    episodes = steps = searches = 0
+    search_ms = 0.0
+    t0 = time.perf_counter()
+    while episodes < no_episodes and (max_steps is None or steps < max_steps):
+        replan = (t_in_ep % replan_every) == 0                        # Agent.py:34
+        if bool(replan.any()):
+            idx = replan.nonzero().squeeze(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            action[idx] = search(obs[idx], no_simulations, search_depth, cfg=cfg, seed=seed + 1 + steps)
+            e1.record()
+            torch.cuda.synchronize()
+            search_ms += e0.elapsed_time(e1)
+            searches += int(idx.numel())
+        # no auto-reset: a finished env keeps its final state until its statistics are read (Agent.py:50-52)
+        obs, rew, done, info = env.step((action[:, 0] * 3 + action[:, 1]).to(torch.int32), auto_reset=False)
+        steps += 1
+        ret += rew.to(torch.float64)
+        t_in_ep += 1
+        d = done.bool()
+        if bool(d.any()):
+            for code in info[d].tolist():
+                name = abi.INFO_STR[code]
+                results[name if name in ("n", "g") else "other"] += 1
+            conflicts += env.counters()[d, 0].tolist()                  # env.no_conflict
+            returns += ret[d].tolist()
+            lengths += t_in_ep[d].tolist()
+            episodes += int(d.sum())
+            ret[d] = 0.0
+            t_in_ep[d] = 0
+            obs = env.reset(mask=done)                                  # last_observation = env.reset()
+    wall = time.perf_counter() - t0
+    env.close()
+    n_done = max(episodes, 1)
+    return {"episodes": episodes, "env_steps": steps * B, "searches": searches,
+            "nmac_prob": results["n"] / n_done, "goal_prob": results["g"] / n_done,
+            "average_conflicts": float(np.mean(conflicts)) if conflicts else 0.0,
+            "average_return": float(np.mean(returns)) if returns else 0.0,
+            "average_length": float(np.mean(lengths)) if lengths else 0.0,
+            "search_ms_total": search_ms, "searches_per_sec": searches / (search_ms * 1e-3) if search_ms else 0.0,
+            "wall_s": wall}
+
+
 def plan_actions(obs, n_simulations=None, depth=None, cfg=None, seed=0, root_id0=0):
     """Batched planner: for each of the B raw observations pick the first action with the best mean
     playout reward, spending `n_simulations` playouts per root spread evenly over the 9 actions

@@ -190,6 +190,11 @@ int gca_reset_host(gca_env* env, const gca_out* host_out);
 /* _get_ob() of the current state without stepping (PKG/SingleAircraftEnv.py:100-126). */
 int gca_observe(gca_env* env, const gca_out* out, void* stream);
 
+/* Per-env counters without a host round trip: device int32 [n_envs][4] = (no_conflict - the attribute
+ * Algorithms/MCTS/Agent.py:52 reads after an episode -, steps of the current episode, Philox tick, finished
+ * episodes).  Asynchronous device-to-device copy on `stream`. */
+int gca_read_counters(gca_env* env, int32_t* counters, void* stream);
+
 /* Full-state access (teacher-forced parity, MCTS root states, checkpointing).  Synchronous.
  * NULL members of the view are skipped. */
 int gca_get_state(gca_env* env, const gca_host_state* dst);
@@ -240,6 +245,24 @@ int gca_mcts_move(const gca_mcts_config* cfg, int n_intruders, double* states, c
 int gca_mcts_playouts(const gca_mcts_config* cfg, int n_intruders, const double* roots, int64_t n_roots,
                       int playouts, int depth, const int8_t* first_action, uint64_t seed, uint32_t root_id0,
                       double* rewards, int8_t* first_out, uint8_t* flags, int device, void* stream);
+
+/* MCTS(root).best_action(simulations, search_depth) for n_roots independent roots, the whole UCT tree resident on
+ * the device (search_single.py:8-22 best_action / tree_policy; common.py:47-52 best_child with c = 1.4 in the
+ * tree and c = 0 for the final pick; nodes_single.py:188-193 expand - untried actions popped from the end -,
+ * :198-204 rollout, :206-210 backpropagate; Algorithms/MCTS/Agent.py:37-41 is the call site this replaces).
+ * Requires cfg->position_sigma == 0 (config_single.py:27): the model's intruders then move on root-only
+ * trajectories and a tree node is just the ownship.  Draws are Philox, keyed (seed; root id = root_id0 + r,
+ * simulation index, GCA_MCTS_DRAW_*, global sub-frame).
+ * workspace: device scratch of gca_mcts_search_workspace(...) bytes, caller-owned, 16-byte aligned.
+ * Outputs (device): best_action int32 [n_roots] (a0*3+a1 of the most valuable root child, -1 if simulations == 0);
+ * child_n, child_q double [n_roots][9] and child_action int32 [n_roots][9] (nullable): visit count, value sum and
+ * action of the root's children in creation order (unused slots 0 / 0 / -1). */
+int64_t gca_mcts_search_workspace(const gca_mcts_config* cfg, int n_intruders, int64_t n_roots, int simulations,
+                                  int depth);
+int gca_mcts_search(const gca_mcts_config* cfg, int n_intruders, const double* roots, int64_t n_roots,
+                    int simulations, int depth, uint64_t seed, uint32_t root_id0, void* workspace,
+                    int64_t workspace_bytes, int32_t* best_action, double* child_n, double* child_q,
+                    int32_t* child_action, int device, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Image observation of SingleAircraftStackEnv (PKG/SingleAircraftStackEnv.py:104-114, 179-214):

@@ -79,6 +79,9 @@ int gca_oracle_mcts_playouts(const gca_mcts_config* c, int n, const double* root
 int gca_oracle_mcts_search(const gca_mcts_config* c, int n, const double* root, int sims, int search_depth,
                            const double* tape, int64_t* cursor, int trig, int* best_action, double* child_n,
                            double* child_q, int* child_action);
+int gca_oracle_mcts_search_philox(const gca_mcts_config* c, int n, const double* roots, int64_t n_roots, int sims,
+                                  int search_depth, uint64_t seed, uint32_t root_id0, int trig, int32_t* best_action,
+                                  double* child_n, double* child_q, int32_t* child_action);
 
 /* ---- StackEnv image observation (oracle/gca_oracle_raster.c); trig of `b` selects libm / shared sincos ---- */
 int gca_oracle_raster(const gca_config* cfg, const gca_oracle_batch* b, const unsigned char* sprites,

@@ -182,12 +182,14 @@ typedef struct node {
 static int is_terminal(const node* v, int search_depth) { return v->flags || v->depth == search_depth; }
 
 /* best_child(c_param)  common.py:47-52 */
-static int best_child(const node* nodes, int v, double c_param) {
+static int best_child(const node* nodes, int v, double c_param, int shared_log, int trig) {
   int best = -1;
   double best_w = 0;
   for (int k = 0; k < nodes[v].n_children; ++k) {
     const node* ch = &nodes[nodes[v].children[k]];
-    const double w = (ch->q / ch->n) + c_param * sqrt((2 * log(nodes[v].n) / ch->n));
+    /* np.log of the reference; the device search shares gca_math.h's log, so the Philox search does too */
+    const double lg = shared_log ? gca_oracle_log(nodes[v].n, trig) : log(nodes[v].n);
+    const double w = (ch->q / ch->n) + c_param * sqrt((2 * lg / ch->n));
     if (best < 0 || w > best_w) {     /* np.argmax: first maximum */
       best = nodes[v].children[k];
       best_w = w;
@@ -197,14 +199,13 @@ static int best_child(const node* nodes, int v, double c_param) {
 }
 
 /* MCTS(root).best_action(simulations, search_depth)  search_single.py:8-22 */
-int gca_oracle_mcts_search(const gca_mcts_config* c, int n, const double* root, int sims, int search_depth,
-                           const double* tape, int64_t* cursor, int trig, int* best_action, double* child_n,
-                           double* child_q, int* child_action) {
+static int search_impl(const gca_mcts_config* c, int n, const double* root, int sims, int search_depth, mdraws d,
+                       int* best_action, double* child_n, double* child_q, int* child_action) {
   const int L = 4 * n + 8;
+  const int philox = d.mode == GCA_DRAWS_PHILOX;
   node* nodes = (node*)calloc((size_t)sims + 2, sizeof(node));
   double* scratch = (double*)malloc(sizeof(double) * L);
   if (!nodes || !scratch) return GCA_ERR_ALLOC;
-  mdraws d = {GCA_DRAWS_TAPE, trig, tape, cursor, 0, 0, 0};
   int count = 1;
   nodes[0].parent = -1;
   nodes[0].untried = 9;
@@ -212,6 +213,7 @@ int gca_oracle_mcts_search(const gca_mcts_config* c, int n, const double* root, 
   nodes[0].state = (double*)malloc(sizeof(double) * L);
   memcpy(nodes[0].state, root, sizeof(double) * L);
   for (int s = 0; s < sims; ++s) {
+    d.playout = (uint32_t)s;                                       /* Philox: simulation s is "playout" s of the root */
     int v = 0;                                                     /* tree_policy */
     while (!is_terminal(&nodes[v], search_depth)) {
       if (nodes[v].untried > 0) {                                  /* expand(): nodes_single.py:188-193 */
@@ -223,12 +225,13 @@ int gca_oracle_mcts_search(const gca_mcts_config* c, int n, const double* root, 
         ch->untried = 9;
         ch->state = (double*)malloc(sizeof(double) * L);
         memcpy(ch->state, nodes[v].state, sizeof(double) * L);
-        ch->flags = model_move(c, n, ch->state, a / 3, a % 3, &d, 0);
+        /* sub-frames are numbered from the root (Philox index; the tape ignores it) */
+        ch->flags = model_move(c, n, ch->state, a / 3, a % 3, &d, nodes[v].depth * c->simulate_frame);
         nodes[v].children[nodes[v].n_children++] = count;
         v = count++;
         break;
       }
-      v = best_child(nodes, v, 1.4);
+      v = best_child(nodes, v, 1.4, philox, d.trig);
     }
     memcpy(scratch, nodes[v].state, sizeof(double) * L);           /* rollout */
     const double r = model_rollout(c, n, scratch, nodes[v].flags, nodes[v].depth, search_depth, &d, -1, NULL, NULL);
@@ -237,7 +240,7 @@ int gca_oracle_mcts_search(const gca_mcts_config* c, int n, const double* root, 
       nodes[u].q += r;
     }
   }
-  const int b = best_child(nodes, 0, 0.);
+  const int b = best_child(nodes, 0, 0., philox, d.trig);
   *best_action = b >= 0 ? nodes[b].action : -1;
   for (int k = 0; k < 9; ++k) {
     const int has = k < nodes[0].n_children;
@@ -248,5 +251,30 @@ int gca_oracle_mcts_search(const gca_mcts_config* c, int n, const double* root, 
   for (int i = 0; i < count; ++i) free(nodes[i].state);
   free(nodes);
   free(scratch);
+  return GCA_OK;
+}
+
+int gca_oracle_mcts_search(const gca_mcts_config* c, int n, const double* root, int sims, int search_depth,
+                           const double* tape, int64_t* cursor, int trig, int* best_action, double* child_n,
+                           double* child_q, int* child_action) {
+  mdraws d = {GCA_DRAWS_TAPE, trig, tape, cursor, 0, 0, 0};
+  return search_impl(c, n, root, sims, search_depth, d, best_action, child_n, child_q, child_action);
+}
+
+/* the contract of gca_mcts_search (include/gca.h): Philox draws keyed (seed, root id, simulation, kind, sub-frame) */
+int gca_oracle_mcts_search_philox(const gca_mcts_config* c, int n, const double* roots, int64_t n_roots, int sims,
+                                  int search_depth, uint64_t seed, uint32_t root_id0, int trig, int32_t* best_action,
+                                  double* child_n, double* child_q, int32_t* child_action) {
+  const int L = 4 * n + 8;
+  for (int64_t r = 0; r < n_roots; ++r) {
+    mdraws d = {GCA_DRAWS_PHILOX, trig, NULL, NULL, seed, root_id0 + (uint32_t)r, 0};
+    int best = -1, ca[9];
+    int rc = search_impl(c, n, roots + r * L, sims, search_depth, d, &best, child_n ? child_n + 9 * r : NULL,
+                         child_q ? child_q + 9 * r : NULL, ca);
+    if (rc) return rc;
+    best_action[r] = best;
+    if (child_action)
+      for (int k = 0; k < 9; ++k) child_action[9 * r + k] = ca[k];
+  }
   return GCA_OK;
 }

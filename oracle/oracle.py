@@ -74,6 +74,7 @@ def lib():
     L.gca_oracle_mcts_rollout.argtypes = [P(MC), i32, vp, i32, i32, i32, vp, vp, u64, u32, u32, i32, vp, vp, vp]
     L.gca_oracle_mcts_playouts.argtypes = [P(MC), i32, vp, i64, i32, i32, vp, u64, u32, i32, vp, vp, vp]
     L.gca_oracle_mcts_search.argtypes = [P(MC), i32, vp, i32, i32, vp, vp, i32, vp, vp, vp, vp]
+    L.gca_oracle_mcts_search_philox.argtypes = [P(MC), i32, vp, i64, i32, i32, u64, u32, i32, vp, vp, vp, vp]
     L.gca_oracle_raster.argtypes = [P(abi.GcaConfig), P(OracleBatch), vp, vp, vp]
     _lib = L
     return L
@@ -250,3 +251,17 @@ def mcts_search(cfg, n, root, sims, depth, tape, trig=TRIG_LIBM):
                                   _p(cq), _p(ca))
     assert rc == 0
     return best.value, cn, cq, ca, int(cur[0])
+
+
+def mcts_search_philox(cfg, n, roots, sims, depth, seed=0, root_id0=0, trig=TRIG_SHARED):
+    """The contract of gca_mcts_search on host arrays: (best_action int32 [R], child_n, child_q f64 [R, 9],
+    child_action int32 [R, 9])."""
+    L = lib()
+    roots = np.ascontiguousarray(roots, np.float64)
+    R = roots.shape[0]
+    best = np.zeros(R, np.int32)
+    cn, cq, ca = np.zeros((R, 9)), np.zeros((R, 9)), np.zeros((R, 9), np.int32)
+    rc = L.gca_oracle_mcts_search_philox(C.byref(cfg), n, _p(roots), R, sims, depth, seed, root_id0, trig, _p(best),
+                                         _p(cn), _p(cq), _p(ca))
+    assert rc == 0
+    return best, cn, cq, ca

@@ -52,18 +52,7 @@ def test_playouts_bit_exact_vs_oracle(n, roots_n, playouts, depth, over):
     from oracle import oracle as orc
     cfg = mcts_cfg(**over)
     rng = np.random.RandomState(n + 7)
-    L = 4 * n + 8
-    roots = np.zeros((roots_n, L))
-    for r in range(roots_n):
-        ip = rng.uniform(0, 800, (n, 2)); sp = rng.uniform(5 / 3, 8 / 3, n); hd = rng.uniform(0, 2 * np.pi, n)
-        roots[r, :4 * n] = np.stack([ip[:, 0], ip[:, 1], sp * np.cos(hd), sp * np.sin(hd)], -1).ravel()
-        own = rng.uniform(30, 770, 2); h = rng.uniform(0, 2 * np.pi); s = rng.uniform(5 / 3, 8 / 3)
-        goal = own + rng.uniform(-120, 120, 2) if r % 3 == 0 else rng.uniform(0, 800, 2)
-        if n and r % 4 == 1:                                  # aim at an intruder: conflicts
-            own = ip[rng.randint(max(n - 1, 1))] - 30 * np.array([np.cos(h), np.sin(h)])
-        if r % 7 == 2:                                        # near a wall, heading out
-            own = np.array([rng.uniform(0.5, 15), rng.uniform(100, 700)]); h = np.pi + rng.normal(0, .2)
-        roots[r, 4 * n:] = [own[0], own[1], s * np.cos(h), s * np.sin(h), s, h, goal[0], goal[1]]
+    roots = _random_roots(n, roots_n, n + 7)
     fa = rng.randint(-1, 9, (roots_n, playouts)).astype(np.int8)
     want_r, want_f, want_fl = orc.mcts_playouts(cfg, n, roots, playouts, depth, first_action=fa, seed=77, root_id0=5)
     got_r, got_f, got_fl = mcts.playouts(torch.as_tensor(roots, device="cuda"), playouts, depth=depth, cfg=cfg,
@@ -80,6 +69,64 @@ def test_warp_per_playout_kernel_bit_exact(n, roots_n, playouts, depth, monkeypa
     giving the same bits (GCA_MCTS_WARP_KERNEL forces it)."""
     monkeypatch.setenv("GCA_MCTS_WARP_KERNEL", "1")
     test_playouts_bit_exact_vs_oracle(n, roots_n, playouts, depth, {})
+
+
+def _random_roots(n, roots_n, seed):
+    rng = np.random.RandomState(seed)
+    L = 4 * n + 8
+    roots = np.zeros((roots_n, L))
+    for r in range(roots_n):
+        ip = rng.uniform(0, 800, (n, 2)); sp = rng.uniform(5 / 3, 8 / 3, n); hd = rng.uniform(0, 2 * np.pi, n)
+        roots[r, :4 * n] = np.stack([ip[:, 0], ip[:, 1], sp * np.cos(hd), sp * np.sin(hd)], -1).ravel()
+        own = rng.uniform(30, 770, 2); h = rng.uniform(0, 2 * np.pi); s = rng.uniform(5 / 3, 8 / 3)
+        goal = own + rng.uniform(-120, 120, 2) if r % 3 == 0 else rng.uniform(0, 800, 2)
+        if n and r % 4 == 1:                                  # aim at an intruder: conflicts
+            own = ip[rng.randint(max(n - 1, 1))] - 30 * np.array([np.cos(h), np.sin(h)])
+        if r % 7 == 2:                                        # near a wall, heading out
+            own = np.array([rng.uniform(0.5, 15), rng.uniform(100, 700)]); h = np.pi + rng.normal(0, .2)
+        roots[r, 4 * n:] = [own[0], own[1], s * np.cos(h), s * np.sin(h), s, h, goal[0], goal[1]]
+    return roots
+
+
+@pytest.mark.parametrize("n,roots_n,sims,depth,over", [
+    (80, 96, 100, 3, {}), (3, 64, 100, 3, {}), (1, 40, 30, 2, {}), (0, 40, 50, 3, {}), (200, 12, 40, 3, {}),
+    (80, 16, 200, 4, {}), (20, 40, 60, 3, {"speed_sigma": 0.05}), (80, 8, 0, 3, {}), (80, 8, 5, 3, {}),
+])
+def test_device_tree_search_bit_exact_vs_oracle(n, roots_n, sims, depth, over):
+    """gca_mcts_search (device-resident UCT trees, one lane per root) against the oracle's best_action() with the same
+    Philox draws: the chosen action and the visit counts / value sums of every root child, bit for bit."""
+    import torch
+    from gca_b200 import mcts
+    from oracle import oracle as orc
+    cfg = mcts_cfg(**over)
+    roots = _random_roots(n, roots_n, n + 11)
+    want_b, want_n, want_q, want_a = orc.mcts_search_philox(cfg, n, roots, sims, depth, seed=123, root_id0=9)
+    act, cn, cq, ca = mcts.search(torch.as_tensor(roots, device="cuda"), sims, depth, cfg=cfg, seed=123, root_id0=9,
+                                  return_children=True)
+    assert np.array_equal(ca.cpu().numpy(), want_a)
+    assert np.array_equal(cn.cpu().numpy(), want_n)
+    assert np.array_equal(cq.cpu().numpy(), want_q)
+    best = want_b.astype(np.int64)
+    assert np.array_equal(act.cpu().numpy(), np.stack([best // 3, best % 3], -1))
+    print("n=%d best-action histogram" % n, np.bincount(np.maximum(want_b, 0), minlength=9).tolist())
+
+
+def test_device_tree_search_rejects_position_noise():
+    import torch
+    from gca_b200 import mcts
+    with pytest.raises(abi.GcaError):
+        mcts.search(torch.zeros((2, 16), dtype=torch.float64, device="cuda"), 10, 3, cfg=mcts_cfg(position_sigma=0.5))
+
+
+def test_batched_agent_experiment():
+    """Algorithms/MCTS/Agent.py run_experiment, batched: episodes finish, statistics are well formed, and planning
+    beats a fixed action (fewer conflicts than flying straight)."""
+    from gca_b200 import mcts
+    out = mcts.run_experiment(num_envs=64, no_episodes=24, no_simulations=40, search_depth=3, seed=4, max_steps=1500)
+    assert out["episodes"] >= 24 and out["searches"] > 0
+    assert 0.0 <= out["nmac_prob"] <= 1.0 and 0.0 <= out["goal_prob"] <= 1.0
+    assert out["goal_prob"] > 0.5, out
+    print(out)
 
 
 def test_drop_in_search_classes():
