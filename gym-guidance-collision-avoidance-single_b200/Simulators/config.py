@@ -39,5 +39,5 @@ class Config:
     sparse_reward = False
     conflict_coeff = 0.00025
 
-    # n nearest intruders (used by the Discrete{3,9}HER training envs, out of scope)
+    # n nearest intruders in the observation of SingleAircraftDiscrete9HEREnv (Simulators/config.py:55)
     n = 4

@@ -19,6 +19,9 @@ VARIANTS = {
     "SingleAircraftStackEnv": (abi.ACT_DISCRETE9, abi.OBS_NONE, abi.WALL_PENALTY, 1, (-20, -5, -10, 10000, 0), True),
     # Simulators/SingleAircraftMCTSEnv.py:163-180: rewards come from Simulators/config.py:37-43 (filled by make_config)
     "SingleAircraftMCTSEnv": (abi.ACT_DISCRETE9, abi.OBS_RAW, abi.WALL_NONE, 1, None, False),
+    # Simulators/SingleAircraftDiscrete9HEREnv.py: random ownship start :78-82, n nearest intruders :127-144, rewards
+    # from Simulators/config.py:37-43 (:207-227), out-of-map rule only under sparse_reward (:217-219)
+    "SingleAircraftDiscrete9HEREnv": (abi.ACT_DISCRETE9, abi.OBS_NEAREST, None, 1, None, False),
 }
 
 
@@ -44,11 +47,20 @@ def make_config(variant, cfg_cls, time_limit=0):
         rewards = (cfg_cls.NMAC_penalty, cfg_cls.conflict_penalty, cfg_cls.wall_penalty, cfg_cls.goal_reward,
                    cfg_cls.step_penalty)
         shaped = 0 if cfg_cls.sparse_reward else 1
+    if wall is None:      # `if Config.sparse_reward: if not position_range.contains(drone.position): ... 'w'`
+        wall = abi.WALL_TERMINAL if cfg_cls.sparse_reward else abi.WALL_NONE
     c.r_nmac, c.r_conflict, c.r_wall, c.r_goal, c.r_default = [float(r) for r in rewards]
     c.shaped_default = shaped
     c.action_kind, c.obs_kind, c.wall_kind = act, obs, wall
     c.max_steps = int(cfg_cls.max_steps) if use_max else 0
     c.time_limit = int(time_limit)
+    c.random_start = 0
+    c.nearest_n = 0
+    c.ob_diagonal = 1.0
+    if obs == abi.OBS_NEAREST:
+        c.random_start = 1
+        c.nearest_n = int(cfg_cls.n)
+        c.ob_diagonal = cfg_cls.diagonal
     return c
 
 
@@ -58,6 +70,8 @@ def refresh_observation_params(c, cfg_cls):
     c.ob_window_height = cfg_cls.window_height
     c.ob_min_speed = cfg_cls.min_speed
     c.ob_max_speed = cfg_cls.max_speed
+    if getattr(c, "obs_kind", None) == abi.OBS_NEAREST:
+        c.ob_diagonal = cfg_cls.diagonal      # Config.diagonal is read inside _get_ob as well
 
 
 def obs_dim(c, n):
@@ -65,6 +79,8 @@ def obs_dim(c, n):
         return 4 * n + 8
     if c.obs_kind in (abi.OBS_HER, abi.OBS_DHER):
         return 4 * n + 6
+    if c.obs_kind == abi.OBS_NEAREST:
+        return 4 + 5 * c.nearest_n
     return 0
 
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GCA_ABI_VERSION 2
+#define GCA_ABI_VERSION 3
 
 typedef enum gca_status {
   GCA_OK = 0,
@@ -61,7 +61,10 @@ enum {
   GCA_OBS_HER = 1,      /* [own x6][intruders x4] + achieved/desired normalised  PKG/SingleAircraftHEREnv.py:103-139 */
   GCA_OBS_DHER = 2,     /* as HER but achieved/desired are raw pixel positions   PKG/SingleAircraftDiscreteHEREnv.py:128-133 */
   GCA_OBS_RAW = 3,      /* VECTOR layout, un-normalised values     Simulators/SingleAircraftMCTSEnv.py:98-124 */
-  GCA_OBS_NONE = 4      /* no vector observation (StackEnv: the image comes from gca_raster) */
+  GCA_OBS_NONE = 4,     /* no vector observation (StackEnv: the image comes from gca_raster) */
+  GCA_OBS_NEAREST = 5   /* [own x4][nearest_n intruders x5: x, y, vx, vy, dist / diagonal, nearest first] + achieved /
+                           desired normalised; needs N > nearest_n
+                           Simulators/SingleAircraftDiscrete9HEREnv.py:106-165 */
 };
 
 enum { GCA_WALL_NONE = 0, GCA_WALL_TERMINAL = 1, GCA_WALL_PENALTY = 2 };
@@ -73,6 +76,7 @@ enum { GCA_INFO_NONE = 0, GCA_INFO_NMAC = 1, GCA_INFO_CONFLICT = 2, GCA_INFO_GOA
 #define GCA_SLOT_OWNSHIP 0x80000000u /* block 0: Box-Muller pair (heading noise, speed noise) */
 #define GCA_SLOT_GOAL 0x40000000u    /* block 0: goal (x, y) of a reset */
 #define GCA_SLOT_RESET 0x20000000u   /* | intruder index: spawn made by a reset */
+#define GCA_SLOT_OWN_RESET 0x10000000u /* random_start: ownship drawn by a reset, blocks POS and SPEED_HEADING */
                                      /* intruder index alone: respawn made inside a step */
 #define GCA_BLOCK_POS 0u             /* (x, y) */
 #define GCA_BLOCK_SPEED_HEADING 1u   /* (speed, heading) */
@@ -98,6 +102,11 @@ typedef struct gca_config {
   int32_t time_limit;     /* > 0: gym TimeLimit of the registered ids (timestep_limit=10000,
                              gym_guidance_collision_avoidance_single/__init__.py:9): after the step,
                              ep_steps >= time_limit also ends the episode (reward/info unchanged) */
+  int32_t random_start;   /* 1: reset() draws the ownship - random_pos(), random_speed(), random_heading(), in that
+                             order, before the intruders (Simulators/SingleAircraftDiscrete9HEREnv.py:78-82);
+                             0: (50, 50), min_speed, pi/4 (PKG/SingleAircraftEnv.py:72-76) */
+  int32_t nearest_n;      /* GCA_OBS_NEAREST: Config.n (Simulators/config.py:55), 1..8 */
+  double ob_diagonal;     /* GCA_OBS_NEAREST: Config.diagonal, normalises the distance entry (Simulators/config.py:8) */
 } gca_config;
 
 /* Canonical host-side view of the full simulator state, identical for both modes

@@ -201,10 +201,21 @@ static int in_map(const gca_config* cfg, double x, double y) {
 static void reset_env(env_view* e) {
   const gca_config* cfg = e->cfg;
   double s, c;
-  e->own_pos[0] = 50.0f;
-  e->own_pos[1] = 50.0f;
-  e->own_hs[0] = 3.141592653589793 / 4;
-  e->own_hs[1] = cfg->min_speed;
+  if (cfg->random_start) {   /* Ownship(random_pos(), random_speed(), random_heading())
+                                Simulators/SingleAircraftDiscrete9HEREnv.py:78-82; Aircraft.__init__ :364-372 */
+    double x, y, speed, heading;
+    draw_pos(e, GCA_SLOT_OWN_RESET, GCA_BLOCK_POS, &x, &y);
+    draw_speed_heading(e, GCA_SLOT_OWN_RESET, &speed, &heading);
+    e->own_pos[0] = (float)x;
+    e->own_pos[1] = (float)y;
+    e->own_hs[0] = heading;
+    e->own_hs[1] = speed;
+  } else {
+    e->own_pos[0] = 50.0f;
+    e->own_pos[1] = 50.0f;
+    e->own_hs[0] = 3.141592653589793 / 4;
+    e->own_hs[1] = cfg->min_speed;
+  }
   gca_oracle_sincos(e->own_hs[0], e->trig, &s, &c);
   e->own_vel[0] = (double)(float)(e->own_hs[1] * c);   /* Aircraft.__init__: f32 velocity */
   e->own_vel[1] = (double)(float)(e->own_hs[1] * s);
@@ -225,10 +236,16 @@ static double norm_vel_f64(const gca_config* cfg, double v) { return (v + cfg->m
 
 /* _get_ob()  PKG/SingleAircraftEnv.py:100-126, PKG/SingleAircraftHEREnv.py:103-139,
  * PKG/SingleAircraftDiscreteHEREnv.py:103-133, Simulators/SingleAircraftMCTSEnv.py:98-124 */
+static void observe_nearest(const env_view* e, double* obs, double* ag, double* dg);
+
 static void observe_env(const env_view* e, double* obs, double* ag, double* dg) {
   const gca_config* cfg = e->cfg;
   const int kind = cfg->obs_kind;
   if (kind == GCA_OBS_NONE) return;
+  if (kind == GCA_OBS_NEAREST) {
+    observe_nearest(e, obs, ag, dg);
+    return;
+  }
   const int raw = kind == GCA_OBS_RAW;
   const int own_first = kind == GCA_OBS_HER || kind == GCA_OBS_DHER;
   double* oi = obs + (own_first ? 6 : 0);
@@ -280,6 +297,57 @@ static void observe_env(const env_view* e, double* obs, double* ag, double* dg) 
     ag[0] = e->own_pos[0]; ag[1] = e->own_pos[1];
     dg[0] = e->goal[0]; dg[1] = e->goal[1];
   }
+}
+
+/* _get_ob() of Simulators/SingleAircraftDiscrete9HEREnv.py:106-165 (3HER identical): ownship (x, y, vx, vy), then the
+ * Config.n nearest intruders, nearest first, each (x, y, vx, vy, dist / Config.diagonal).  dist_array is
+ * np.array(dist_list) of f32 / f64 scalars: ordering by value; np.argpartition + argsort of distinct values = the n
+ * smallest in ascending order (ties: lowest index first - they do not occur in the recorded traces). */
+static void observe_nearest(const env_view* e, double* obs, double* ag, double* dg) {
+  const gca_config* cfg = e->cfg;
+  const int k = cfg->nearest_n;
+  int idx[8];
+  double dd[8];
+  int m = 0;
+  for (int i = 0; i < e->n; ++i) {
+    const double d = dist_intruder(e, i);
+    int pos = m;
+    while (pos > 0 && d < dd[pos - 1]) --pos;             /* strict: an equal distance stays behind the earlier index */
+    if (pos >= k) continue;
+    const int last = m < k ? m : k - 1;
+    for (int j = last; j > pos; --j) { dd[j] = dd[j - 1]; idx[j] = idx[j - 1]; }
+    dd[pos] = d;
+    idx[pos] = i;
+    if (m < k) ++m;
+  }
+  obs[0] = (double)(e->own_pos[0] / (float)cfg->ob_window_width);
+  obs[1] = (double)(e->own_pos[1] / (float)cfg->ob_window_height);
+  if (*e->own_vel_is_f32) {
+    obs[2] = norm_vel_f32(cfg, (float)e->own_vel[0]);
+    obs[3] = norm_vel_f32(cfg, (float)e->own_vel[1]);
+  } else {
+    obs[2] = norm_vel_f64(cfg, e->own_vel[0]);
+    obs[3] = norm_vel_f64(cfg, e->own_vel[1]);
+  }
+  for (int j = 0; j < m; ++j) {
+    const int i = idx[j];
+    double* o = obs + 4 + 5 * j;
+    if (e->is64[i]) {
+      o[0] = e->ipos[2 * i] / cfg->ob_window_width;
+      o[1] = e->ipos[2 * i + 1] / cfg->ob_window_height;
+      o[4] = dd[j] / cfg->ob_diagonal;
+    } else {
+      o[0] = (double)((float)e->ipos[2 * i] / (float)cfg->ob_window_width);
+      o[1] = (double)((float)e->ipos[2 * i + 1] / (float)cfg->ob_window_height);
+      o[4] = (double)((float)dd[j] / (float)cfg->ob_diagonal);
+    }
+    o[2] = norm_vel_f32(cfg, e->ivel[2 * i]);
+    o[3] = norm_vel_f32(cfg, e->ivel[2 * i + 1]);
+  }
+  ag[0] = (double)(e->own_pos[0] / (float)cfg->ob_window_width);
+  ag[1] = (double)(e->own_pos[1] / (float)cfg->ob_window_height);
+  dg[0] = e->goal[0] / cfg->ob_window_width;
+  dg[1] = e->goal[1] / cfg->ob_window_height;
 }
 
 /* Ownship.step(a)  PKG/SingleAircraftEnv.py:299-309 (+ 2Env :291-301, DiscreteHER :301-311) */
@@ -474,6 +542,7 @@ int gca_oracle_obs_dim(const gca_config* cfg, int n_intruders) {
     case GCA_OBS_RAW: return 4 * n_intruders + 8;
     case GCA_OBS_HER:
     case GCA_OBS_DHER: return 4 * n_intruders + 6;
+    case GCA_OBS_NEAREST: return 4 + 5 * cfg->nearest_n;
     default: return 0;
   }
 }

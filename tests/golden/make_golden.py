@@ -33,6 +33,7 @@ from gym_guidance_collision_avoidance_single.envs import (  # noqa: E402
     SingleAircraftEnv, SingleAircraft2Env, SingleAircraftHEREnv, SingleAircraftDiscreteHEREnv)
 from gym_guidance_collision_avoidance_single.envs.config import Config as PkgConfig  # noqa: E402
 import SingleAircraftMCTSEnv as mcts_env_mod  # noqa: E402  (Simulators/, uses Simulators/config.py)
+import SingleAircraftDiscrete9HEREnv as d9her_mod  # noqa: E402  (Simulators/, nearest-n observation)
 import config as SimConfigMod  # noqa: E402
 import nodes_single  # noqa: E402
 import search_single  # noqa: E402
@@ -172,7 +173,10 @@ VARIANTS = {
     "her": (SingleAircraftHEREnv, PkgConfig, "c2"),
     "dher": (SingleAircraftDiscreteHEREnv, PkgConfig, "d3"),
     "mcts": (mcts_env_mod.SingleAircraftEnv, SimConfigMod.Config, "t33"),
+    "d9her": (d9her_mod.SingleAircraftDiscrete9HEREnv, SimConfigMod.Config, "d9"),
 }
+# np.argpartition(dist_array, Config.n) of the nearest-n observation needs more than n = 4 intruders
+PLANS = {"d9her": {5: (5, 40), 12: (5, 40), 80: (3, 30)}}
 
 
 def sample_action(kind, rng):
@@ -292,8 +296,11 @@ def make_env_goldens():
     }
     kinds = ["plain", "mid", "near_intruder", "near_goal", "near_wall", "edge_intruders"]
     meta = {}
+    only = os.environ.get("GCA_GOLDEN_ONLY")
     for variant in VARIANTS:
-        for n, (per_kind, T) in plan.items():
+        if only and variant not in only.split(","):
+            continue
+        for n, (per_kind, T) in PLANS.get(variant, plan).items():
             traces, kind_ids = [], []
             seed = 100 * n + 7
             for ki, kind in enumerate(kinds):
@@ -424,7 +431,43 @@ def make_her_reward_golden():
     return {"her_reward": {"pairs": 256}}
 
 
+def make_d9her_reward_golden():
+    """compute_reward / compute_input_reward of Simulators/SingleAircraftDiscrete9HEREnv.py:229-277 (scalar calls)."""
+    rng = np.random.RandomState(9)
+    SimConfigMod.Config.intruder_size = 8
+    np.random.seed(4)
+    env = d9her_mod.SingleAircraftDiscrete9HEREnv()
+    M = 200
+    ag = rng.uniform(0, 1, (M, 2)); g = ag + rng.uniform(-0.06, 0.06, (M, 2))
+    g[:6] = ag[:6] + np.array([[20.0 / 800, 0.0]])
+    r = np.array([env.compute_reward(ag[i].copy(), g[i].copy(), None) for i in range(M)], np.float64)
+    ag_after = ag[0].copy(); env.compute_reward(ag_after, g[0].copy(), None)      # unnormalize_position works in place
+    inputs = np.zeros((M, 26))
+    for i in range(M):
+        ob = env.reset()
+        v = np.concatenate([ob["observation"], ob["desired_goal"]])
+        if i % 3 == 0:       # put a listed intruder close to the ownship
+            k = int(rng.randint(4))
+            v[4 * k + 4: 4 * k + 6] = v[0:2] + rng.uniform(-0.03, 0.03, 2)
+        if i % 5 == 1:       # goal next to the ownship
+            v[-2:] = v[0:2] + rng.uniform(-0.03, 0.03, 2)
+        inputs[i] = v
+    ri = np.array([env.compute_input_reward(inputs[i].copy()) for i in range(M)], np.float64)
+    np.savez_compressed(os.path.join(HERE, "d9her_reward.npz"), ag=ag, g=g, r=r, ag0_after=ag_after, inputs=inputs, ri=ri)
+    return {"d9her_reward": {"pairs": M}}
+
+
 def main():
+    only = os.environ.get("GCA_GOLDEN_ONLY")
+    if only:                                   # add traces of new variants without regenerating the others
+        with open(os.path.join(HERE, "META.json")) as f:
+            meta = json.load(f)
+        meta.update(make_env_goldens())
+        if "d9her" in only.split(","):
+            meta.update(make_d9her_reward_golden())
+        with open(os.path.join(HERE, "META.json"), "w") as f:
+            json.dump(meta, f, indent=1, sort_keys=True)
+        return
     meta = {"numpy": np.__version__, "python": sys.version.split()[0]}
     try:
         from threadpoolctl import threadpool_info
@@ -434,6 +477,7 @@ def main():
     meta.update(make_env_goldens())
     meta.update(make_mcts_goldens())
     meta.update(make_her_reward_golden())
+    meta.update(make_d9her_reward_golden())
     with open(os.path.join(HERE, "META.json"), "w") as f:
         json.dump(meta, f, indent=1, sort_keys=True)
 

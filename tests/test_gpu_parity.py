@@ -9,7 +9,7 @@ sincos/log (gca_math.h) everything is bit-exact, in both modes, at every size.
 import numpy as np
 import pytest
 
-from helpers import (GOLDEN_N, GOLDEN_VARIANTS, STATE_KEYS, assert_state_equal, config_class, golden_actions,
+from helpers import (GOAL_VARIANTS, GOLDEN_CASES, GOLDEN_N, GOLDEN_VARIANTS, STATE_KEYS, assert_state_equal, config_class, golden_actions,
                      golden_config, golden_state, load_trace)
 
 pytestmark = pytest.mark.gpu
@@ -44,8 +44,7 @@ def close(a, b):
     return np.allclose(a, b, rtol=RTOL, atol=1e-300)
 
 
-@pytest.mark.parametrize("n", GOLDEN_N)
-@pytest.mark.parametrize("vk", sorted(GOLDEN_VARIANTS))
+@pytest.mark.parametrize("vk,n", GOLDEN_CASES)
 def test_golden_replay_faithful(vk, n):
     """Free-running replay of the reference traces: same start state, same actions, same draws."""
     torch = _torch()
@@ -55,7 +54,7 @@ def test_golden_replay_faithful(vk, n):
     tape = np.nan_to_num(g["tape"], nan=0.0)
     env = make_gpu(vk, n, B, "faithful", "tape")
     ref = make_oracle(vk, n, B, 0, orc.TRIG_SHARED, tape=tape)       # bit-exact twin of the kernel
-    her = vk in ("her", "dher")
+    her = vk in GOAL_VARIANTS
 
     # reset from the tape start
     env.set_tape(tape)

@@ -4,7 +4,7 @@ info, conflict counter, the number of draws consumed and the full object state, 
 import numpy as np
 import pytest
 
-from helpers import (GOLDEN_N, GOLDEN_VARIANTS, assert_state_equal, golden_actions, golden_config, golden_state,
+from helpers import (GOAL_VARIANTS, GOLDEN_CASES, GOLDEN_N, GOLDEN_VARIANTS, assert_state_equal, golden_actions, golden_config, golden_state,
                      load_trace)
 from oracle import oracle as orc
 
@@ -16,8 +16,7 @@ def make_env(vk, n, g, auto_reset=False):
     return orc.OracleEnv(cfg, B, n, draws=0, trig=orc.TRIG_LIBM, tape=tape, auto_reset=auto_reset)
 
 
-@pytest.mark.parametrize("n", GOLDEN_N)
-@pytest.mark.parametrize("vk", sorted(GOLDEN_VARIANTS))
+@pytest.mark.parametrize("vk,n", GOLDEN_CASES)
 def test_reset_matches_reference(vk, n):
     g = load_trace(vk, n)
     env = make_env(vk, n, g)
@@ -27,13 +26,12 @@ def test_reset_matches_reference(vk, n):
     want = golden_state(g, "s0_", plain)
     assert_state_equal(env.state, want, "reset %s n=%d" % (vk, n), rows=plain)
     assert np.array_equal(env.obs[plain], g["obs0"][plain])
-    if vk in ("her", "dher"):
+    if vk in GOAL_VARIANTS:
         assert np.array_equal(env.achieved[plain], g["ag0"][plain])
         assert np.array_equal(env.desired[plain], g["dg0"][plain])
 
 
-@pytest.mark.parametrize("n", GOLDEN_N)
-@pytest.mark.parametrize("vk", sorted(GOLDEN_VARIANTS))
+@pytest.mark.parametrize("vk,n", GOLDEN_CASES)
 def test_free_running_replay_matches_reference(vk, n):
     g = load_trace(vk, n)
     env = make_env(vk, n, g)
@@ -41,7 +39,7 @@ def test_free_running_replay_matches_reference(vk, n):
     for k, v in st.items():
         env.state[k][...] = v
     env.cursor[...] = g["cur_reset0"]
-    her = vk in ("her", "dher")
+    her = vk in GOAL_VARIANTS
     assert np.array_equal(env.observe(), g["obs0"])
     if her:
         assert np.array_equal(env.achieved, g["ag0"]) and np.array_equal(env.desired, g["dg0"])
