@@ -338,6 +338,7 @@ def main_gpu(args):
             line["mcts"] = bench_mcts(local, with_cpu=(world == 1))
             line["her"] = bench_her(local)
             line["stack"] = bench_stack(local)
+            line["d9her"] = bench_d9her(local)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -356,11 +357,11 @@ def bench_mcts(device, with_cpu):
     env = BatchedAircraftEnv("SingleAircraftMCTSEnv", R, SimConfig, n_intruders=80, mode="faithful", device=device, seed=2)
     roots = env.reset().clone()                      # raw observations after reset = MCTS root states
     cfg = abi.make_mcts_config(MctsConfig)
-    for _ in range(3):
+    for _ in range(20):
         mcts.playouts(roots, P, depth=depth, cfg=cfg, seed=5)
     torch.cuda.synchronize()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 10
+    reps = 100
     start.record()
     for i in range(reps):
         rewards, _, flags = mcts.playouts(roots, P, depth=depth, cfg=cfg, seed=6 + i)
@@ -457,6 +458,35 @@ def bench_her(device):
     return {"metric": METRIC, "value": B / (ms * 1e-3), "unit": UNIT, "envs": B, "intruders": N,
             "relabel_pairs_per_step": k * B, "ms_per_step": ms,
             "note": "step (dict observation, own-first layout) + HER relabel reward on 4*B pairs, eager launches"}
+
+
+def bench_d9her(device):
+    """Simulators/SingleAircraftDiscrete9HEREnv (random ownship start, observation = ownship + the
+    4 nearest intruders, dict goals) - the env the repo's own learners train on.  5 kernels per step (the nearest-n
+    pass runs behind the spawn kernel on the final intruder set)."""
+    import torch
+    from gca_b200.batched import BatchedAircraftEnv
+    from Simulators.config import Config as SimConfig
+    B, N = ENVS_PER_GPU, N_INTRUDERS
+    env = BatchedAircraftEnv("SingleAircraftDiscrete9HEREnv", B, SimConfig, n_intruders=N, mode="fast", draws="philox",
+                             device=device, seed=6)
+    env.reset()
+    acts = [torch.randint(0, 9, (B,), device="cuda", dtype=torch.int32) for _ in range(8)]
+    for i in range(5):
+        env.step(acts[i % 8])
+    torch.cuda.synchronize()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 200
+    start.record()
+    for i in range(reps):
+        env.step(acts[i % 8])
+    stop.record()
+    torch.cuda.synchronize()
+    ms = start.elapsed_time(stop) / reps
+    k = env.kernels_per_step
+    env.close()
+    return {"metric": METRIC, "value": B / (ms * 1e-3), "unit": UNIT, "envs": B, "intruders": N, "ms_per_step": ms,
+            "kernels_per_step": k, "obs_dim": 24, "note": "nearest-4 observation (24 values + goals), eager launches"}
 
 
 def bench_stack(device):

@@ -60,7 +60,9 @@ size_t real_size(const gca_env* e) { return e->mode == GCA_MODE_FAITHFUL ? sizeo
 int check_config(const gca_config* c) {
   if (!c) return fail(GCA_ERR_INVALID, "config is NULL");
   if (c->action_kind < GCA_ACT_DISCRETE9 || c->action_kind > GCA_ACT_DISCRETE3) return fail(GCA_ERR_INVALID, "bad action_kind");
-  if (c->obs_kind < GCA_OBS_VECTOR || c->obs_kind > GCA_OBS_NONE) return fail(GCA_ERR_INVALID, "bad obs_kind");
+  if (c->obs_kind < GCA_OBS_VECTOR || c->obs_kind > GCA_OBS_NEAREST) return fail(GCA_ERR_INVALID, "bad obs_kind");
+  if (c->obs_kind == GCA_OBS_NEAREST && (c->nearest_n < 1 || c->nearest_n > 8 || !(c->ob_diagonal > 0)))
+    return fail(GCA_ERR_INVALID, "GCA_OBS_NEAREST needs 1 <= nearest_n <= 8 and a positive ob_diagonal");
   if (c->wall_kind < GCA_WALL_NONE || c->wall_kind > GCA_WALL_PENALTY) return fail(GCA_ERR_INVALID, "bad wall_kind");
   if (!(c->window_width > 0) || !(c->window_height > 0)) return fail(GCA_ERR_INVALID, "window must be positive");
   return GCA_OK;
@@ -156,7 +158,7 @@ StepArgs make_args(const gca_env* e, const void* actions, const gca_tape* tape, 
 int check_out(const gca_env* e, const gca_out* out, bool need_reward) {
   if (!out) return fail(GCA_ERR_INVALID, "out is NULL");
   if (e->cfg.obs_kind != GCA_OBS_NONE && !out->obs) return fail(GCA_ERR_INVALID, "out->obs is NULL");
-  const bool her = e->cfg.obs_kind == GCA_OBS_HER || e->cfg.obs_kind == GCA_OBS_DHER;
+  const bool her = e->cfg.obs_kind == GCA_OBS_HER || e->cfg.obs_kind == GCA_OBS_DHER || e->cfg.obs_kind == GCA_OBS_NEAREST;
   if (her && (!out->achieved || !out->desired)) return fail(GCA_ERR_INVALID, "HER kinds need achieved/desired buffers");
   if (need_reward && (!out->reward || !out->done || !out->info)) return fail(GCA_ERR_INVALID, "reward/done/info buffers are NULL");
   return GCA_OK;
@@ -212,6 +214,7 @@ int gca_obs_dim(const gca_config* cfg, int n) {
     case GCA_OBS_RAW: return 4 * n + 8;
     case GCA_OBS_HER:
     case GCA_OBS_DHER: return 4 * n + 6;
+    case GCA_OBS_NEAREST: return 4 + 5 * cfg->nearest_n;
     default: return 0;
   }
 }
@@ -222,6 +225,8 @@ int gca_create(const gca_config* cfg, int n_envs, int n_intruders, int mode, int
   *out = nullptr;
   if (int rc = check_config(cfg)) return rc;
   if (n_envs <= 0 || n_intruders < 0 || n_intruders > 4096) return fail(GCA_ERR_INVALID, "n_envs must be > 0 and 0 <= n_intruders <= 4096");
+  if (cfg->obs_kind == GCA_OBS_NEAREST && n_intruders <= cfg->nearest_n)   // np.argpartition(dist_array, Config.n) raises otherwise
+    return fail(GCA_ERR_INVALID, "GCA_OBS_NEAREST needs more intruders than nearest_n");
   if (mode != GCA_MODE_FAITHFUL && mode != GCA_MODE_FAST) return fail(GCA_ERR_INVALID, "bad mode");
   if (draws != GCA_DRAWS_TAPE && draws != GCA_DRAWS_PHILOX) return fail(GCA_ERR_INVALID, "bad draws");
   int count = 0;
@@ -331,7 +336,7 @@ int gca_step(gca_env* e, const void* actions, const gca_tape* tape, int auto_res
 
 int gca_step_launches(gca_env* e) {
   if (!e) return fail(GCA_ERR_INVALID, "env is NULL");
-  return step_launch_count(e->draws == GCA_DRAWS_TAPE, e->s.N);
+  return step_launch_count(e->draws == GCA_DRAWS_TAPE, e->s.N, e->cfg.obs_kind);
 }
 
 int gca_profile_enable(gca_env* e, int on) {
@@ -395,7 +400,7 @@ static int ensure_host_path(gca_env* e) {
 
 static int copy_out(gca_env* e, const gca_out* h, bool with_reward) {
   const size_t B = (size_t)e->s.B, rs = real_size(e);
-  const bool her = e->cfg.obs_kind == GCA_OBS_HER || e->cfg.obs_kind == GCA_OBS_DHER;
+  const bool her = e->cfg.obs_kind == GCA_OBS_HER || e->cfg.obs_kind == GCA_OBS_DHER || e->cfg.obs_kind == GCA_OBS_NEAREST;
   if (h->obs && e->D) GCA_CUDA(cudaMemcpyAsync(h->obs, e->d_out.obs, B * (size_t)e->D * rs, cudaMemcpyDeviceToHost, e->stream));
   if (her && h->achieved) GCA_CUDA(cudaMemcpyAsync(h->achieved, e->d_out.achieved, B * 2 * rs, cudaMemcpyDeviceToHost, e->stream));
   if (her && h->desired) GCA_CUDA(cudaMemcpyAsync(h->desired, e->d_out.desired, B * 2 * rs, cudaMemcpyDeviceToHost, e->stream));

@@ -421,7 +421,7 @@ __device__ __forceinline__ void write_obs_intruder(const StepArgs& a, real_t<FAI
   using R = real_t<FAITH>;
   const gca_config& c = a.cfg;
   const Derived& k = a.k;
-  if (c.obs_kind == GCA_OBS_NONE) return;
+  if (c.obs_kind == GCA_OBS_NONE || c.obs_kind == GCA_OBS_NEAREST) return;   // (NEAREST: nearest_obs_kernel)
   R o0, o1, o2, o3;
   if (c.obs_kind == GCA_OBS_RAW) {
     o0 = (R)it.px; o1 = (R)it.py; o2 = (R)it.vx; o3 = (R)it.vy;
@@ -475,7 +475,7 @@ __device__ __forceinline__ void write_obs_own(const StepArgs& a, size_t env, flo
                                               bool vel_is_f32, double heading, double speed, double gx, double gy) {
   using R = real_t<FAITH>;
   const gca_config& c = a.cfg;
-  if (c.obs_kind == GCA_OBS_NONE) return;
+  if (c.obs_kind == GCA_OBS_NONE || c.obs_kind == GCA_OBS_NEAREST) return;
   const bool of = own_first(c);
   R* row = reinterpret_cast<R*>(a.obs) + env * (size_t)a.D;
   R* o = row + (of ? 0 : 4 * (size_t)a.s.N);
@@ -512,6 +512,88 @@ __device__ __forceinline__ void write_obs_own(const StepArgs& a, size_t env, flo
       dg[0] = (R)gx; dg[1] = (R)gy;
     }
   }
+}
+
+// _get_ob() of Simulators/SingleAircraftDiscrete9HEREnv.py:106-165 for one env: ownship (x, y, vx, vy), then the
+// Config.n nearest intruders, nearest first (ties: lowest index), each (x, y, vx, vy, dist / Config.diagonal), and the
+// normalised achieved / desired goals.  Distances in the dtype the reference computes them in (f32 positions: f32
+// norm; a retried spawn's f64 position: f64 norm), compared by value like np.argpartition / argsort of the mixed array.
+template <bool FAITH>
+__device__ __forceinline__ void write_obs_nearest(const StepArgs& a, size_t env) {
+  using R = real_t<FAITH>;
+  const DevState& s = a.s;
+  const gca_config& c = a.cfg;
+  const Derived& k = a.k;
+  constexpr int KMAX = 8;
+  const int kn = c.nearest_n;
+  const int plane = s.counters[env].z & 1;
+  const float2 own = s.own_pos[env];
+  double dd[KMAX];
+  int idx[KMAX];
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) { dd[j] = 0.0; idx[j] = -1; }
+  int m = 0;
+  for (int i = 0; i < s.N; ++i) {
+    Intr<FAITH> it;
+    load_intruder<FAITH>(s, plane, env, i, it);
+    bool wide = false;
+    if constexpr (FAITH) wide = it.is64;
+    double cd = wide ? dist_f64((double)own.x, (double)own.y, (double)it.px, (double)it.py)
+                     : (double)__fsqrt_rn(dist2_f32(own.x, own.y, (float)it.px, (float)it.py));
+    int ci = i;
+    bool moving = false;                                  // once placed, the displaced entries just shift down
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) {
+      if (j < kn) {
+        const bool take = moving || j >= m || cd < dd[j]; // strict: an equal distance stays behind the earlier index
+        if (take) {
+          const double td = dd[j]; dd[j] = cd; cd = td;
+          const int ti = idx[j]; idx[j] = ci; ci = ti;
+          moving = true;
+        }
+      }
+    }
+    if (m < kn) ++m;
+  }
+  R* row = reinterpret_cast<R*>(a.obs) + env * (size_t)a.D;
+  const float nx = div_prepared(k, own.x, k.ob_w, k.inv_ob_w), ny = div_prepared(k, own.y, k.ob_h, k.inv_ob_h);
+  const double2 vel = s.own_vel[env];
+  row[0] = (R)nx;
+  row[1] = (R)ny;
+  if (s.own_vel_f32[env]) {
+    row[2] = (R)norm_vel_f32(k, (float)vel.x);
+    row[3] = (R)norm_vel_f32(k, (float)vel.y);
+  } else {
+    row[2] = (R)norm_vel_f64(c, k, vel.x);
+    row[3] = (R)norm_vel_f64(c, k, vel.y);
+  }
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) {
+    if (j < m) {
+      Intr<FAITH> it;
+      load_intruder<FAITH>(s, plane, env, idx[j], it);
+      bool wide = false;
+      if constexpr (FAITH) wide = it.is64;
+      R* o = row + 4 + 5 * j;
+      if (wide) {
+        o[0] = (R)ddiv_prepared(k, (double)it.px, k.dv_w, k.rc_w);
+        o[1] = (R)ddiv_prepared(k, (double)it.py, k.dv_h, k.rc_h);
+        o[4] = (R)__ddiv_rn(dd[j], c.ob_diagonal);
+      } else {
+        o[0] = (R)div_prepared(k, (float)it.px, k.ob_w, k.inv_ob_w);
+        o[1] = (R)div_prepared(k, (float)it.py, k.ob_h, k.inv_ob_h);
+        o[4] = (R)__fdiv_rn((float)dd[j], (float)c.ob_diagonal);
+      }
+      o[2] = (R)norm_vel_f32(k, it.vx);
+      o[3] = (R)norm_vel_f32(k, it.vy);
+    }
+  }
+  const double2 goal = s.goal[env];
+  R* ag = reinterpret_cast<R*>(a.achieved) + 2 * env;
+  R* dg = reinterpret_cast<R*>(a.desired) + 2 * env;
+  ag[0] = (R)nx; ag[1] = (R)ny;
+  dg[0] = (R)ddiv_prepared(k, goal.x, k.dv_w, k.rc_w);
+  dg[1] = (R)ddiv_prepared(k, goal.y, k.dv_h, k.rc_h);
 }
 
 }  // namespace gca

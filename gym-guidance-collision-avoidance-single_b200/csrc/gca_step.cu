@@ -92,12 +92,12 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // PHILOX: lanes = intruders.  TAPE: lane `owner` replays the reference's sequential draw order.
 template <bool FAITH, bool TAPE>
 __device__ __forceinline__ void reset_env_warp(const StepArgs& a, size_t env, int plane, int lane, int owner,
-                                               Draws<TAPE>& d, double2& goal) {
+                                               Draws<TAPE>& d, double2& goal, const float ox, const float oy) {
   const DevState& s = a.s;
   const gca_config& c = a.cfg;
   const Derived& k = a.k;
   real_t<FAITH>* obase = obs_intruder_base<FAITH>(a, env);
-  const float ox = 50.0f, oy = 50.0f;                     // Ownship(position=(50, 50), ...) :72-76
+  // (ox, oy): the ownship the new intruders keep their distance from - (50, 50) :72-76, or the random start
   if constexpr (TAPE) {
     if (lane == owner) {
       for (int r = 0; r < s.W; ++r) {
@@ -139,11 +139,22 @@ __device__ __forceinline__ void reset_env_warp(const StepArgs& a, size_t env, in
   }
 }
 
-// ownship state right after reset: min speed, heading pi/4, f32 velocity (Aircraft.__init__ :269-276)
-__device__ __forceinline__ void reset_ownship(const gca_config& c, float2& pos, double2& hs, double2& vel) {
+// ownship state right after reset: (50, 50), min speed, heading pi/4 (PKG/SingleAircraftEnv.py:72-76), or with
+// random_start random_pos(), random_speed(), random_heading() drawn in that order BEFORE the intruders
+// (Simulators/SingleAircraftDiscrete9HEREnv.py:78-82); f32 position and velocity (Aircraft.__init__ :269-276)
+template <bool TAPE>
+__device__ __forceinline__ void reset_ownship(const gca_config& c, Draws<TAPE>& d, float2& pos, double2& hs, double2& vel) {
   double sn, cs;
-  pos = make_float2(50.0f, 50.0f);
-  hs = make_double2(3.141592653589793 / 4, c.min_speed);
+  if (c.random_start) {
+    double x, y, speed, heading;
+    draw_pos(d, c, GCA_SLOT_OWN_RESET, GCA_BLOCK_POS, x, y);
+    draw_speed_heading(d, c, GCA_SLOT_OWN_RESET, speed, heading);
+    pos = make_float2((float)x, (float)y);
+    hs = make_double2(heading, speed);
+  } else {
+    pos = make_float2(50.0f, 50.0f);
+    hs = make_double2(3.141592653589793 / 4, c.min_speed);
+  }
   gca_sincos(hs.x, &sn, &cs);
   vel = make_double2((double)(float)__dmul_rn(hs.y, cs), (double)(float)__dmul_rn(hs.y, sn));
 }
@@ -460,7 +471,9 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
       __syncwarp();                                                 // lane e's stores above come first
       Draws<TAPE> de = d;
       const int plane = __shfl_sync(FULL, nxt, e);
-      reset_env_warp<FAITH, TAPE>(a, env0 + e, plane, lane, e, de, goal);
+      if (lane == e) reset_ownship<TAPE>(c, de, pos, hs, vel);       // (its draws come first on the tape)
+      const float rx = __shfl_sync(FULL, pos.x, e), ry = __shfl_sync(FULL, pos.y, e);
+      reset_env_warp<FAITH, TAPE>(a, env0 + e, plane, lane, e, de, goal, rx, ry);
       if (lane == e) d = de;
     }
   } else {
@@ -482,7 +495,7 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
     }
   }
   if (resets) {
-    reset_ownship(c, pos, hs, vel);
+    if constexpr (!TAPE) reset_ownship<TAPE>(c, d, pos, hs, vel);     // (spawn_kernel reads the new position)
     s.own_pos[me] = pos;
     s.own_hs[me] = hs;
     s.own_vel[me] = vel;
@@ -556,7 +569,8 @@ __global__ void __launch_bounds__(128) spawn_kernel(const __grid_constant__ Step
       bool wide = false;
       if (i < s.N) {
         Intr<FAITH> it;
-        spawn<FAITH, false>(d, a.cfg, a.k, GCA_SLOT_RESET | (uint32_t)i, 50.0f, 50.0f, it);   // Ownship at (50, 50) :72-76
+        const float2 own = s.own_pos[env];                 // (50, 50) :72-76, or the random start finish_tile drew
+        spawn<FAITH, false>(d, a.cfg, a.k, GCA_SLOT_RESET | (uint32_t)i, own.x, own.y, it);
         store_ipos<FAITH>(s, cnt.z & 1, env, i, it);
         store_ivel(s, env, i, it.vx, it.vy);
         write_obs_intruder<FAITH>(a, obs_intruder_base<FAITH>(a, env), i, it);
@@ -771,12 +785,13 @@ __global__ void __launch_bounds__(128) reset_kernel(const StepArgs a) {
     }
     const int plane = __shfl_sync(FULL, nxt, e);
     double2 goal = make_double2(0., 0.);
-    reset_env_warp<FAITH, TAPE>(a, env0 + e, plane, lane, e, de, goal);
+    float2 pos = make_float2(0.f, 0.f);
+    double2 hs = make_double2(0., 0.), vel = make_double2(0., 0.);
+    if (lane == e) reset_ownship<TAPE>(c, de, pos, hs, vel);         // (its draws come first on the tape)
+    const float rx = __shfl_sync(FULL, pos.x, e), ry = __shfl_sync(FULL, pos.y, e);
+    reset_env_warp<FAITH, TAPE>(a, env0 + e, plane, lane, e, de, goal, rx, ry);
     if (lane == e) {
       if constexpr (TAPE) d = de;
-      float2 pos;
-      double2 hs, vel;
-      reset_ownship(c, pos, hs, vel);
       s.own_pos[me] = pos;
       s.own_hs[me] = hs;
       s.own_vel[me] = vel;
@@ -810,6 +825,16 @@ __global__ void __launch_bounds__(128) observe_kernel(const StepArgs a) {
   const float2 pos = s.own_pos[me];
   const double2 hs = s.own_hs[me], vel = s.own_vel[me], goal = s.goal[me];
   write_obs_own<FAITH>(a, me, pos.x, pos.y, vel.x, vel.y, s.own_vel_f32[me] != 0, hs.x, hs.y, goal.x, goal.y);
+}
+
+// GCA_OBS_NEAREST: the observation needs the n nearest of the FINAL intruder set (after respawns / resets), so it is a
+// pass of its own behind the spawn kernel: thread = env, coalesced plane reads (Simulators/SingleAircraftDiscrete9HEREnv.py:106-165)
+template <bool FAITH>
+__global__ void __launch_bounds__(128) nearest_obs_kernel(const __grid_constant__ StepArgs a) {
+  pdl_wait();
+  const size_t me = (size_t)blockIdx.x * 128 + threadIdx.x;
+  if (me >= (size_t)a.s.B) return;
+  write_obs_nearest<FAITH>(a, me);
 }
 
 // ------------------------------------------------------------------------------ launchers
@@ -860,6 +885,8 @@ static cudaError_t launch_step_t(const StepArgs& a, cudaStream_t st, cudaEvent_t
       launch_pdl(spawn_kernel<FAITH>, blocks, 128, st, a);
     }
   }
+  if (a.cfg.obs_kind == GCA_OBS_NEAREST)
+    launch_pdl(nearest_obs_kernel<FAITH>, (unsigned)(((size_t)s.B + 127) / 128), 128, st, a);
   mark(4);
   return cudaGetLastError();
 }
@@ -870,7 +897,9 @@ cudaError_t launch_step(bool faith, bool tape, const StepArgs& a, cudaStream_t s
 }
 
 // kernels one gca_step launches for this configuration (bench.py's gpu_launches)
-int step_launch_count(bool tape, int n_intruders) { return 2 + (n_intruders > 0 ? 1 : 0) + (!tape && n_intruders > 0 ? 1 : 0); }
+int step_launch_count(bool tape, int n_intruders, int obs_kind) {
+  return 2 + (n_intruders > 0 ? 1 : 0) + (!tape && n_intruders > 0 ? 1 : 0) + (obs_kind == GCA_OBS_NEAREST ? 1 : 0);
+}
 
 cudaError_t launch_reset(bool faith, bool tape, const StepArgs& a, cudaStream_t st) {
   const unsigned blocks = (unsigned)((a.s.T + 3) / 4);
@@ -881,12 +910,16 @@ cudaError_t launch_reset(bool faith, bool tape, const StepArgs& a, cudaStream_t 
     if (tape) reset_kernel<false, true><<<blocks, 128, 0, st>>>(a);
     else reset_kernel<false, false><<<blocks, 128, 0, st>>>(a);
   }
+  if (a.cfg.obs_kind == GCA_OBS_NEAREST) return launch_observe(faith, a, st);
   return cudaGetLastError();
 }
 
 cudaError_t launch_observe(bool faith, const StepArgs& a, cudaStream_t st) {
   const unsigned blocks = (unsigned)(((size_t)a.s.B + 127) / 128);
-  if (faith) observe_kernel<true><<<blocks, 128, 0, st>>>(a);
+  if (a.cfg.obs_kind == GCA_OBS_NEAREST) {
+    if (faith) nearest_obs_kernel<true><<<blocks, 128, 0, st>>>(a);
+    else nearest_obs_kernel<false><<<blocks, 128, 0, st>>>(a);
+  } else if (faith) observe_kernel<true><<<blocks, 128, 0, st>>>(a);
   else observe_kernel<false><<<blocks, 128, 0, st>>>(a);
   return cudaGetLastError();
 }

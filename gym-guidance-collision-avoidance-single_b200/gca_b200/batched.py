@@ -49,7 +49,7 @@ class BatchedAircraftEnv(object):
         self.device = torch.device("cuda", device)
         self.real = torch.float64 if self.mode == abi.MODE_FAITHFUL else torch.float32
         self.obs_dim = variants.obs_dim(self.cfg, self.n_intruders)
-        self.is_goal_env = self.cfg.obs_kind in (abi.OBS_HER, abi.OBS_DHER)
+        self.is_goal_env = self.cfg.obs_kind in (abi.OBS_HER, abi.OBS_DHER, abi.OBS_NEAREST)
         self.continuous = self.cfg.action_kind == abi.ACT_CONTINUOUS2
         handle = C.c_void_p()
         abi.check(self.lib.gca_create(C.byref(self.cfg), self.num_envs, self.n_intruders, self.mode, self.draws,

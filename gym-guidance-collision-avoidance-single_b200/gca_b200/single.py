@@ -262,5 +262,73 @@ class SingleAircraftMCTSEnv(_SingleBase):
         return self._obs(), reward, bool(b.done[0].item()), {"result": abi.INFO_STR[code]}
 
 
+class SingleAircraftDiscrete9HEREnv(_GoalBase):
+    """The training env of the repo's own learners (Simulators/SingleAircraftDiscrete9HEREnv.py, used by
+    Algorithms/pytorch/dqn_her.py and Algorithms/A2C): random ownship start (:78-82), observation = ownship
+    (x, y, vx, vy) + the Config.n nearest intruders (x, y, vx, vy, dist / Config.diagonal) (:106-144), dict goals,
+    Discrete(9) actions, reward row of Simulators/config.py:37-43.  Needs Config.intruder_size > Config.n."""
+    VARIANT = "SingleAircraftDiscrete9HEREnv"
+
+    def _config_class(self):
+        from Simulators.config import Config
+        return Config
+
+    def _build_spaces(self):
+        obs = self.reset()                                  # the reference resets in its constructor (:31)
+        # a flat Box of observation + desired goal, as the learners concatenate them (:42)
+        self.observation_space = Box(low=-1000, high=1000, shape=(obs["observation"].shape[0] + 2,), dtype=np.float32)
+        self.action_space = Discrete(9)
+
+    def _info(self, code):
+        return {"result": abi.INFO_STR[code]}
+
+    def step(self, action):
+        ob, reward, done, info = _SingleBase.step(self, action)
+        code = abi.INFO_STR.index(info["result"])
+        shaped = code == abi.INFO_NONE and not self.Config.sparse_reward
+        return ob, (np.float64(reward) if shaped else float(reward)), done, info
+
+    def unnormalize_position(self, position):               # :279-283 - in place, like the reference
+        position[0] = position[0] * self.Config.window_width
+        position[1] = position[1] * self.Config.window_height
+        return position
+
+    def compute_reward(self, achieved_goal, desired_goal, info):
+        """:229-243 - scalar (one pair per call); un-normalises its arguments IN PLACE like the reference does."""
+        c = self.Config
+        achieved_goal = self.unnormalize_position(achieved_goal)
+        desired_goal = self.unnormalize_position(desired_goal)
+        d = np.linalg.norm((achieved_goal - desired_goal), axis=-1)
+        if d < self.goal_radius:
+            return c.goal_reward
+        return c.step_penalty if c.sparse_reward else - d / 1200
+
+    def compute_input_reward(self, new_inputs):
+        """:245-277 - reward of a relabelled (observation + goal) vector.  The reference indexes the intruder entries
+        with stride 4 (idx * 4 + 4) although each has 5 values: kept."""
+        c = self.Config
+
+        def metric(x1, y1, x2, y2):
+            return math.sqrt((x1 - x2) ** 2 + (y1 - y2) ** 2)
+        ownx = new_inputs[0] * c.window_width
+        owny = new_inputs[1] * c.window_height
+        gx = new_inputs[-2] * c.window_width
+        gy = new_inputs[-1] * c.window_height
+        dist_goal = metric(ownx, owny, gx, gy)
+        if c.intruder_size != 0:
+            for idx in range(c.n):
+                intrux = new_inputs[idx * 4 + 4] * c.window_width
+                intruy = new_inputs[idx * 4 + 5] * c.window_height
+                dist_intruder = metric(ownx, owny, intrux, intruy)
+                if dist_intruder < self.minimum_separation:
+                    reward = c.conflict_penalty
+                    if dist_intruder < self.NMAC_dist:
+                        reward = c.NMAC_penalty
+                    return reward
+        if dist_goal < self.goal_radius:
+            return c.goal_reward
+        return c.step_penalty if c.sparse_reward else -dist_goal / 1200
+
+
 def _unused():  # keep math imported for parity with the reference module namespace
     return math.pi

@@ -19,30 +19,33 @@ def _make(vk, n, **kw):
     try:
         if vk == "mcts":
             from Simulators.SingleAircraftMCTSEnv import SingleAircraftEnv as cls
+        elif vk == "d9her":
+            from Simulators.SingleAircraftDiscrete9HEREnv import SingleAircraftDiscrete9HEREnv as cls
         else:
             import gym_guidance_collision_avoidance_single.envs as envs
             cls = {"env": envs.SingleAircraftEnv, "env2": envs.SingleAircraft2Env, "her": envs.SingleAircraftHEREnv,
                    "dher": envs.SingleAircraftDiscreteHEREnv}[vk]
         return cls(**kw)
     finally:
-        cfgc.intruder_size = 80 if vk == "mcts" else 0
+        cfgc.intruder_size = 80 if vk in ("mcts", "d9her") else 0
 
 
 def _ref_action(vk, a):
-    if vk in ("env", "dher"):
+    if vk in ("env", "dher", "d9her"):
         return int(a[0])
     if vk == "mcts":
         return (int(a[0]), int(a[1]))
     return np.array(a, np.float64)
 
 
-@pytest.mark.parametrize("vk,n", [("env", 3), ("env", 80), ("env2", 3), ("her", 3), ("dher", 3), ("mcts", 80)])
+@pytest.mark.parametrize("vk,n", [("env", 3), ("env", 80), ("env2", 3), ("her", 3), ("dher", 3), ("mcts", 80),
+                                  ("d9her", 12), ("d9her", 80)])
 def test_single_env_api_replays_reference_trace(vk, n):
     g = load_trace(vk, n)
     plain = [int(i) for i in np.nonzero(g["kind_id"] == 0)[0]][:2]
     for tr in plain:
         tape = np.nan_to_num(g["tape"][tr:tr + 1], nan=0.0)
-        if vk in ("her", "dher"):               # these constructors reset() once themselves (PKG/SingleAircraftHEREnv.py:32)
+        if vk in ("her", "dher", "d9her"):      # these constructors reset() once themselves (PKG/SingleAircraftHEREnv.py:32)
             tape = np.concatenate([tape[:, : int(g["cur_reset0"][tr])], tape], axis=1)
         env = _make(vk, n, draws="tape", tape=tape)
         ob = env.reset()
@@ -57,7 +60,7 @@ def test_single_env_api_replays_reference_trace(vk, n):
             ob, r, done, info = env.step(_ref_action(vk, g["actions"][tr, t]))
             assert close(ob["observation"] if her else ob, g["obs"][tr, t])
             assert close(r, g["reward"][tr, t])
-            if vk != "mcts":
+            if vk not in ("mcts", "d9her"):
                 assert isinstance(r, int) == bool(g["reward_is_int"][tr, t]), (vk, t, r)
             assert done == bool(g["done"][tr, t]) and isinstance(done, bool)
             code = ("", "n", "c", "g", "w", "m")[g["event"][tr, t]]
@@ -146,3 +149,20 @@ def test_vec_env_interface():
     assert set(d) == {"observation", "achieved_goal", "desired_goal"} and d["observation"].shape == (64, 18)
     for v in (venv, hv, venv2, gv):
         v.close()
+
+
+def test_discrete9her_rewards_match_reference():
+    """compute_reward (scalar, un-normalises its arguments in place) and compute_input_reward (stride-4 indexing quirk)
+    of Simulators/SingleAircraftDiscrete9HEREnv.py:229-277 against values recorded from the reference."""
+    import os
+    from helpers import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "d9her_reward.npz"))
+    env = _make("d9her", 8)
+    assert env.observation_space.shape == (26,) and env.action_space.n == 9
+    for i in range(len(g["r"])):
+        assert env.compute_reward(g["ag"][i].copy(), g["g"][i].copy(), None) == g["r"][i]
+        assert env.compute_input_reward(g["inputs"][i].copy()) == g["ri"][i]
+    a0 = g["ag"][0].copy()
+    env.compute_reward(a0, g["g"][0].copy(), None)
+    assert np.array_equal(a0, g["ag0_after"])
+    env.close()

@@ -113,7 +113,8 @@ def test_golden_replay_faithful(vk, n):
     print("%s n=%d: %d/%d step outputs bit-identical to the reference" % (vk, n, exact, total))
 
 
-@pytest.mark.parametrize("vk,n", [("env", 80), ("env2", 80), ("her", 3), ("dher", 80), ("mcts", 80)])
+@pytest.mark.parametrize("vk,n", [("env", 80), ("env2", 80), ("her", 3), ("dher", 80), ("mcts", 80), ("d9her", 80),
+                                  ("d9her", 12)])
 def test_teacher_forced_single_steps(vk, n):
     """Load each recorded reference state, take ONE step, compare with the next recorded state
     (chaotic divergence cannot hide a bug)."""
@@ -142,7 +143,8 @@ def test_teacher_forced_single_steps(vk, n):
 @pytest.mark.parametrize("mode", ["fast", "faithful"])
 @pytest.mark.parametrize("vk,n,B,T", [("env", 80, 4096, 40), ("env2", 80, 2048, 40), ("her", 33, 1000, 40),
                                       ("dher", 3, 1000, 60), ("mcts", 80, 1024, 40), ("env", 0, 5000, 30),
-                                      ("env", 1, 777, 60), ("env2", 200, 300, 30)])
+                                      ("env", 1, 777, 60), ("env2", 200, 300, 30), ("d9her", 80, 2048, 60),
+                                      ("d9her", 5, 999, 80), ("d9her", 33, 500, 40)])
 def test_philox_rollout_bit_exact_vs_oracle(vk, n, B, T, mode):
     """On-device Philox draws, VecEnv auto-reset: every output and the whole state must equal the
     CPU oracle driven by the same counter-based stream - bit for bit (ragged batch sizes included)."""

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert ctypes.sizeof(abi.GcaConfig) == 21 * 8 + 6 * 4
+    assert ctypes.sizeof(abi.GcaConfig) == 21 * 8 + 8 * 4 + 8
     assert ctypes.sizeof(abi.GcaMctsConfig) == 10 * 8 + 2 * 4
     assert ctypes.sizeof(abi.GcaHostState) == 12 * 8 and ctypes.sizeof(abi.GcaOut) == 6 * 8
     assert ctypes.sizeof(abi.GcaTape) == 24
@@ -70,7 +70,11 @@ def test_abi_argument_checking():
 def test_variant_table_matches_reference_reward_rows():
     from gym_guidance_collision_avoidance_single.envs.config import Config
     from Simulators.config import Config as Sim
-    rows = {k: variants.make_config(k, Sim if k == "SingleAircraftMCTSEnv" else Config) for k in variants.VARIANTS}
+    rows = {k: variants.make_config(k, Sim if k in ("SingleAircraftMCTSEnv", "SingleAircraftDiscrete9HEREnv") else Config)
+            for k in variants.VARIANTS}
+    r = rows["SingleAircraftDiscrete9HEREnv"]
+    assert (r.obs_kind, r.random_start, r.nearest_n, r.ob_diagonal, r.wall_kind) == (abi.OBS_NEAREST, 1, 4, 800, abi.WALL_NONE)
+    assert variants.obs_dim(r, 80) == 24
     r = rows["SingleAircraftEnv"]
     assert (r.r_nmac, r.r_conflict, r.r_goal, r.shaped_default, r.wall_kind) == (-20, -5, 10, 1, abi.WALL_NONE)
     r = rows["SingleAircraft2Env"]
