@@ -339,6 +339,7 @@ def main_gpu(args):
             line["her"] = bench_her(local)
             line["stack"] = bench_stack(local)
             line["d9her"] = bench_d9her(local)
+            line["her_replay"] = bench_her_replay(local)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -487,6 +488,36 @@ def bench_d9her(device):
     env.close()
     return {"metric": METRIC, "value": B / (ms * 1e-3), "unit": UNIT, "envs": B, "intruders": N, "ms_per_step": ms,
             "kernels_per_step": k, "obs_dim": 24, "note": "nearest-4 observation (24 values + goals), eager launches"}
+
+
+def bench_her_replay(device):
+    """HER "future" relabelling sampler (baselines her_sampler.py:19-61) on a device-resident
+    episode buffer: gather of six rows per transition + goal substitution + reward.  Pure data movement: algorithmic
+    bytes = 2 * (2 dim_o + dim_u + 4 dim_g) * 4 + 16 per transition (rows read once, written once; r + 3 int32 out)."""
+    import torch
+    from gca_b200 import abi, replay
+    E, T, dim_o, dim_u, batch = 4096, 50, 4 * N_INTRUDERS + 6, 2, 262144
+    g = torch.Generator(device="cuda").manual_seed(0)
+    eb = {"o": torch.rand((E, T + 1, dim_o), device="cuda", generator=g), "u": torch.rand((E, T, dim_u), device="cuda", generator=g),
+          "g": torch.rand((E, T, 2), device="cuda", generator=g), "ag": torch.rand((E, T + 1, 2), device="cuda", generator=g)}
+    for i in range(5):
+        replay.sample_her_transitions(eb, batch, 4, 20.0, abi.OBS_HER, seed=1, call=i)
+    torch.cuda.synchronize()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 50
+    start.record()
+    for i in range(reps):
+        replay.sample_her_transitions(eb, batch, 4, 20.0, abi.OBS_HER, seed=1, call=10 + i)
+    stop.record()
+    torch.cuda.synchronize()
+    ms = start.elapsed_time(stop) / reps
+    bytes_per = 2 * (2 * dim_o + dim_u + 4 * 2) * 4 + 16
+    peak, src = measured_peaks()
+    gbs = batch * bytes_per / (ms * 1e-3) / 1e9
+    return {"metric": "her_transitions_per_sec", "value": batch / (ms * 1e-3), "unit": "transitions/s", "batch": batch,
+            "episodes": E, "T": T, "dim_o": dim_o, "ms_per_launch": ms, "bytes_per_transition": bytes_per,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                         "peak_source": src, "note": "includes the torch.empty of the output tensors per call"}}
 
 
 def bench_stack(device):

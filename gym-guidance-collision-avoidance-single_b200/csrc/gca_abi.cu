@@ -536,6 +536,25 @@ int gca_compute_reward(const void* ag, const void* g, int64_t m, double radius, 
   return GCA_OK;
 }
 
+int gca_her_sample(const gca_her_episodes* ep, int64_t n_episodes, int T, int dim_o, int dim_u, int dim_g, int is_f64,
+                   int64_t batch, double future_p, double goal_radius, int reward_kind, const gca_her_draws* draws,
+                   uint64_t seed, uint32_t call, const gca_her_transitions* out, int device, void* stream) {
+  if (!ep || !out || n_episodes <= 0 || T <= 0 || dim_o <= 0 || dim_u <= 0 || batch < 0)
+    return fail(GCA_ERR_INVALID, "bad arguments");
+  if (dim_g != 2) return fail(GCA_ERR_INVALID, "goals are 2-D (achieved_goal / desired_goal of the GoalEnv variants)");
+  if (reward_kind != GCA_OBS_HER && reward_kind != GCA_OBS_DHER) return fail(GCA_ERR_INVALID, "reward_kind must be GCA_OBS_HER or GCA_OBS_DHER");
+  if (!ep->o || !ep->u || !ep->g || !ep->ag) return fail(GCA_ERR_INVALID, "episode arrays are NULL");
+  if (batch > 0 && (!out->o || !out->u || !out->g || !out->ag || !out->o_2 || !out->ag_2 || !out->r))
+    return fail(GCA_ERR_INVALID, "transition arrays are NULL");
+  if (draws && (!draws->episode_idxs || !draws->t_samples || !draws->u_her || !draws->u_offset))
+    return fail(GCA_ERR_INVALID, "draws need all four arrays");
+  if (!(future_p >= 0.0 && future_p <= 1.0)) return fail(GCA_ERR_INVALID, "future_p must be in [0, 1]");
+  GCA_CUDA(cudaSetDevice(device));
+  GCA_CUDA(launch_her_sample(ep, (long long)n_episodes, T, dim_o, dim_u, dim_g, is_f64, (long long)batch, future_p,
+                             goal_radius, reward_kind, draws, seed, call, out, (cudaStream_t)stream));
+  return GCA_OK;
+}
+
 int gca_raster(gca_env* e, const uint8_t* sprites, uint8_t* frames, int64_t env_stride, int64_t plane_stride,
                int n_planes, int slot, const uint8_t* clear_mask, void* stream) {
   if (!e || !sprites || !frames) return fail(GCA_ERR_INVALID, "env/sprites/frames is NULL");

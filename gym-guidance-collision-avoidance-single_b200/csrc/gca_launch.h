@@ -21,6 +21,9 @@ size_t mcts_search_workspace_bytes(const gca_mcts_config* cfg, int n, long long 
 cudaError_t launch_mcts_search(const gca_mcts_config* cfg, int n, const double* roots, long long n_roots, int sims,
                                int depth, uint64_t seed, uint32_t root_id0, void* workspace, int32_t* best_action,
                                double* child_n, double* child_q, int32_t* child_action, cudaStream_t st);
+cudaError_t launch_her_sample(const gca_her_episodes* ep, long long E, int T, int dim_o, int dim_u, int dim_g, int is_f64,
+                              long long batch, double future_p, double radius, int kind, const gca_her_draws* dr,
+                              uint64_t seed, uint32_t call, const gca_her_transitions* out, cudaStream_t st);
 cudaError_t launch_raster(const DevState& s, bool faithful, int W, int H, const uint8_t* sprites, uint8_t* frames,
                           long long env_stride, long long plane_stride, int n_planes, int slot,
                           const uint8_t* clear_mask, cudaStream_t st);

@@ -50,6 +50,18 @@ class GcaTape(C.Structure):
     _fields_ = [("values", C.c_void_p), ("stride", C.c_int64), ("cursor", C.c_void_p)]
 
 
+class GcaHerEpisodes(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("o", "u", "g", "ag")]
+
+
+class GcaHerDraws(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("episode_idxs", "t_samples", "u_her", "u_offset")]
+
+
+class GcaHerTransitions(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("o", "u", "g", "ag", "o_2", "ag_2", "r", "episode", "t", "future_t")]
+
+
 class GcaMctsConfig(C.Structure):
     _fields_ = [(n, C.c_double) for n in (
         "window_width", "window_height", "minimum_separation", "min_speed", "max_speed", "d_speed", "speed_sigma",
@@ -115,6 +127,8 @@ def load():
         "gca_profile_read": ([vp, P(GcaStepProfile)], C.c_int),
         "gca_compute_reward": ([vp, vp, i64, C.c_double, i32, i32, vp, i32, vp], C.c_int),
         "gca_raster": ([vp, vp, vp, i64, i64, i32, i32, vp, vp], C.c_int),
+        "gca_her_sample": ([P(GcaHerEpisodes), i64, i32, i32, i32, i32, i32, i64, C.c_double, C.c_double, i32,
+                            P(GcaHerDraws), u64, u32, P(GcaHerTransitions), i32, vp], C.c_int),
         "gca_mcts_move": ([P(GcaMctsConfig), i32, vp, vp, vp, i64, P(GcaTape), u64, u32, i32, i32, vp], C.c_int),
         "gca_mcts_playouts": ([P(GcaMctsConfig), i32, vp, i64, i32, i32, vp, u64, u32, vp, vp, vp, i32, vp], C.c_int),
         "gca_mcts_search_workspace": ([P(GcaMctsConfig), i32, i64, i32, i32], C.c_int64),

@@ -236,6 +236,41 @@ typedef struct gca_mcts_config {
 
 enum { GCA_MCTS_WALL = 1, GCA_MCTS_CONFLICT = 2, GCA_MCTS_GOAL = 4 };
 
+/* ---- HER replay: the "future" relabelling sampler of baselines (Algorithms/baselines-master/baselines/her/
+ * her_sampler.py:19-61 _sample_her_transitions, called by replay_buffer.py:sample with o_2 = o[:, 1:], ag_2 = ag[:, 1:])
+ * on an episode buffer that lives on the device.  For each of `batch` transitions: episode e and time t are drawn,
+ * rows o[e][t], u[e][t], g[e][t], ag[e][t], o_2 = o[e][t+1], ag_2 = ag[e][t+1] are gathered, with probability
+ * future_p = 1 - 1 / (1 + replay_k) the goal is replaced by ag[e][t + 1 + int(u * (T - t))], and the reward is
+ * recomputed by the env's compute_reward(ag_2, g) (reward_kind GCA_OBS_HER / GCA_OBS_DHER, goals are 2-D).
+ * All arrays are REAL = double (is_f64, what baselines' numpy buffers hold) or float. */
+typedef struct gca_her_episodes {
+  const void* o;  /* REAL [n_episodes][T+1][dim_o] */
+  const void* u;  /* REAL [n_episodes][T][dim_u] */
+  const void* g;  /* REAL [n_episodes][T][dim_g] */
+  const void* ag; /* REAL [n_episodes][T+1][dim_g] */
+} gca_her_episodes;
+
+/* the four np.random calls of the sampler, in call order, as device arrays of length batch; a NULL gca_her_draws*
+ * means Philox: counter (b & 0xffffffff, b >> 32, call, block), block 0 -> (episode, t) = (int(u0 * E), int(u1 * T)),
+ * block 1 -> (u_her, u_offset) */
+typedef struct gca_her_draws {
+  const int64_t* episode_idxs; /* np.random.randint(0, rollout_batch_size, batch_size) */
+  const int64_t* t_samples;    /* np.random.randint(T, size=batch_size) */
+  const double* u_her;         /* np.random.uniform(size=batch_size) < future_p */
+  const double* u_offset;      /* np.random.uniform(size=batch_size) * (T - t_samples) */
+} gca_her_draws;
+
+typedef struct gca_her_transitions {
+  void *o, *u, *g, *ag, *o_2, *ag_2; /* REAL [batch][dim] */
+  float* r;                          /* [batch] */
+  int32_t *episode, *t, *future_t;   /* [batch] (nullable) what was drawn; future_t = -1 where the goal was kept */
+} gca_her_transitions;
+
+int gca_her_sample(const gca_her_episodes* episodes, int64_t n_episodes, int T, int dim_o, int dim_u, int dim_g,
+                   int is_f64, int64_t batch, double future_p, double goal_radius, int reward_kind,
+                   const gca_her_draws* draws, uint64_t seed, uint32_t call, const gca_her_transitions* out, int device,
+                   void* stream);
+
 /* SingleAircraftState.move(action) for m independent states (nodes_single.py:39-100).
  * states: device double [m][4N+8] raw observation vectors (Simulators/SingleAircraftMCTSEnv.py:98-124),
  * advanced in place; actions: device int32 [m] (a0*3+a1); flags: device uint8 [m] (GCA_MCTS_* bits).

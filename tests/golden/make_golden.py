@@ -457,6 +457,57 @@ def make_d9her_reward_golden():
     return {"d9her_reward": {"pairs": M}}
 
 
+def make_her_sampler_golden():
+    """Outputs of the unmodified baselines sampler (her_sampler.py:19-61) on synthetic episode batches, with the four
+    np.random draws recorded; reward_fun = compute_reward of the two GoalEnv variants of the package."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "ref_her_sampler", os.path.join(REF, "Algorithms", "baselines-master", "baselines", "her", "her_sampler.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    PkgConfig.intruder_size = 0
+    np.random.seed(3)
+    her, dher = SingleAircraftHEREnv(), SingleAircraftDiscreteHEREnv()
+    rng = np.random.RandomState(11)
+    out = {}
+    for name, env, E, T, dim_o, batch, k, pix in (("her", her, 6, 12, 10, 256, 4, False), ("dher", dher, 9, 30, 18, 512, 4, True),
+                                                  ("none", dher, 5, 7, 6, 64, 0, True)):
+        scale = 800.0 if pix else 1.0
+        ag = np.cumsum(rng.normal(0, 6.0 if pix else 0.008, (E, T + 1, 2)), axis=1) + rng.uniform(0.2, 0.8, (E, 1, 2)) * scale
+        eb = {"o": rng.uniform(-1, 1, (E, T + 1, dim_o)), "u": rng.uniform(-1, 1, (E, T, 1 if pix else 2)),
+              "g": np.repeat(rng.uniform(0.1, 0.9, (E, 1, 2)) * scale, T, axis=1), "ag": ag}
+        eb2 = dict(eb); eb2["o_2"] = eb["o"][:, 1:, :]; eb2["ag_2"] = eb["ag"][:, 1:, :]      # replay_buffer.py:46-47
+        fn = mod.make_sample_her_transitions("future" if k else "none", k,
+                                             lambda ag_2, g, info, env=env: env.compute_reward(ag_2, g, info))
+        calls = []
+        orig = {n: getattr(np.random, n) for n in ("randint", "uniform")}
+
+        def wrap(n):
+            def f(*a, **kw):
+                v = orig[n](*a, **kw)
+                calls.append(np.array(v))
+                return v
+            return f
+        for n in orig:
+            setattr(np.random, n, wrap(n))
+        try:
+            np.random.seed(21)
+            tr = fn(eb2, batch)
+        finally:
+            for n, f in orig.items():
+                setattr(np.random, n, f)
+        assert len(calls) == 4
+        for key, v in eb.items():
+            out["%s_ep_%s" % (name, key)] = v
+        for key, v in zip(("episode_idxs", "t_samples", "u_her", "u_offset"), calls):
+            out["%s_draw_%s" % (name, key)] = v
+        for key in ("o", "u", "g", "ag", "o_2", "ag_2", "r"):
+            out["%s_tr_%s" % (name, key)] = np.asarray(tr[key])
+        out["%s_meta" % name] = np.array([k, batch, env.goal_radius, 2 if pix else 1], np.float64)
+    np.savez_compressed(os.path.join(HERE, "her_sampler.npz"), **out)
+    return {"her_sampler": {"cases": 3}}
+
+
 def main():
     only = os.environ.get("GCA_GOLDEN_ONLY")
     if only:                                   # add traces of new variants without regenerating the others
@@ -465,6 +516,8 @@ def main():
         meta.update(make_env_goldens())
         if "d9her" in only.split(","):
             meta.update(make_d9her_reward_golden())
+        if "her_sampler" in only.split(","):
+            meta.update(make_her_sampler_golden())
         with open(os.path.join(HERE, "META.json"), "w") as f:
             json.dump(meta, f, indent=1, sort_keys=True)
         return
@@ -478,6 +531,7 @@ def main():
     meta.update(make_mcts_goldens())
     meta.update(make_her_reward_golden())
     meta.update(make_d9her_reward_golden())
+    meta.update(make_her_sampler_golden())
     with open(os.path.join(HERE, "META.json"), "w") as f:
         json.dump(meta, f, indent=1, sort_keys=True)
 
