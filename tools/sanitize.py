@@ -37,3 +37,44 @@ for t in range(5):
     img.step(torch.randint(0, 9, (16,), device="cuda", dtype=torch.int32))
 torch.cuda.synchronize()
 print("ok stack")
+img.close()
+
+# Discrete9HER: random start + nearest-n observation kernel
+from Simulators.config import Config as SimConfig  # noqa: E402
+for B, N, mode in ((200, 80, "fast"), (70, 5, "faithful")):
+    env = BatchedAircraftEnv("SingleAircraftDiscrete9HEREnv", B, SimConfig, n_intruders=N, mode=mode, seed=5)
+    env.reset()
+    for t in range(40):
+        o, r, d, i = env.step(torch.randint(0, 9, (B,), device="cuda", dtype=torch.int32), auto_reset=(t % 2 == 0))
+        if t % 5 == 0 and bool(d.any()):
+            env.reset(mask=d)
+    env.observe()
+    env.counters()
+    torch.cuda.synchronize()
+    env.close()
+    print("ok d9her", B, N, mode, flush=True)
+
+# MCTS: both playout kernels, the move kernel, the device-resident search
+from gca_b200 import abi, mcts, replay  # noqa: E402
+from Algorithms.MCTS.config_single import Config as MctsConfig  # noqa: E402
+cfg = abi.make_mcts_config(MctsConfig)
+env = BatchedAircraftEnv("SingleAircraftMCTSEnv", 48, SimConfig, n_intruders=80, mode="faithful", seed=2)
+roots = env.reset().clone()
+env.close()
+mcts.playouts(roots, 37, depth=3, cfg=cfg, seed=1)
+os.environ["GCA_MCTS_WARP_KERNEL"] = "1"
+mcts.playouts(roots, 11, depth=3, cfg=cfg, seed=1)
+del os.environ["GCA_MCTS_WARP_KERNEL"]
+mcts.search(roots, 60, 3, cfg=cfg, seed=4)
+mcts.move(roots.clone(), torch.randint(0, 9, (48,), device="cuda", dtype=torch.int32), cfg)
+torch.cuda.synchronize()
+print("ok mcts", flush=True)
+
+# HER replay sampler, odd row widths
+for dt, dim_o in ((torch.float32, 326), (torch.float64, 27), (torch.float32, 24)):
+    E, T = 9, 13
+    eb = {"o": torch.rand((E, T + 1, dim_o), device="cuda", dtype=dt), "u": torch.rand((E, T, 2), device="cuda", dtype=dt),
+          "g": torch.rand((E, T, 2), device="cuda", dtype=dt), "ag": torch.rand((E, T + 1, 2), device="cuda", dtype=dt)}
+    replay.sample_her_transitions(eb, 501, 4, 0.1, abi.OBS_DHER, seed=3, call=1)
+torch.cuda.synchronize()
+print("ok her replay")
