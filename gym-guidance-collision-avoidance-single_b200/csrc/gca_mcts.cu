@@ -251,6 +251,10 @@ __global__ void __launch_bounds__(kMctsWarps * 32) mcts_playout_kernel(const Mct
 // instructions per playout at N = 80 (the 79 x 30 distance tests collapse to ~45).
 constexpr int kSharedThreads = 128;
 
+__device__ __forceinline__ int lane_move(const MctsArgs& a, const int* __restrict__ cnt, const double2* __restrict__ cand,
+                                         uint32_t root, uint32_t sim, int depth, int act, double gx, double gy,
+                                         double& ox, double& oy, double& vy_prev, double& heading);
+
 __global__ void __launch_bounds__(kSharedThreads) mcts_playout_shared_kernel(const MctsArgs a) {
   extern __shared__ __align__(16) uint8_t mcts_sh[];
   const gca_mcts_config& c = a.c;
@@ -299,34 +303,7 @@ __global__ void __launch_bounds__(kSharedThreads) mcts_playout_shared_kernel(con
       if (depth == 0 && a.first_action && a.first_action[pid] >= 0) act = a.first_action[pid];
       else act = mcts_action(a, root, (uint32_t)p, (uint32_t)depth);
       if (first < 0) first = act;
-      const double d_heading = __dmul_rn((double)(act / 3 - 1), c.d_heading);
-      for (int f = 0; f < F; ++f) {
-        const int gf = depth * F + f;
-        const double nh = mcts_normal(a, c.heading_sigma, root, (uint32_t)p, GCA_MCTS_DRAW_HEADING, (uint32_t)gf);
-        const double nsp = mcts_normal(a, c.speed_sigma, root, (uint32_t)p, GCA_MCTS_DRAW_SPEED, (uint32_t)gf);
-        double sp = clamp_speed(c, vy_prev);                              // state[-4] = clamp(state[-5])  (Q23)
-        sp = __dadd_rn(sp, nsp);
-        heading = __dadd_rn(heading, d_heading);
-        heading = __dadd_rn(heading, nh);
-        double sn, cs;
-        gca_sincos(heading, &sn, &cs);
-        const double vx = __dmul_rn(sp, cs), vy = __dmul_rn(sp, sn);
-        ox = __dadd_rn(ox, vx);
-        oy = __dadd_rn(oy, vy);
-        vy_prev = vy;
-        if (!(0.0 < ox && ox < c.window_width) || !(0.0 < oy && oy < c.window_height)) { flags = GCA_MCTS_WALL; break; }
-        bool hit = false;
-        const double2* cf = cand + (size_t)gf * a.near;
-        const int nc = cnt[gf];
-        for (int k = 0; k < nc; ++k) {
-          const double2 q = cf[k];
-          const double dx = __dadd_rn(q.x, -ox), dy = __dadd_rn(q.y, -oy);
-          hit |= __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < a.sep2;
-        }
-        if (hit) { flags = GCA_MCTS_CONFLICT; break; }
-        const double dx = __dadd_rn(ox, -gx), dy = __dadd_rn(oy, -gy);
-        if (__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < a.sep2) { flags = GCA_MCTS_GOAL; break; }
-      }
+      flags = lane_move(a, cnt, cand, root, (uint32_t)p, depth, act, gx, gy, ox, oy, vy_prev, heading);
     }
     double reward;
     if (flags & (GCA_MCTS_WALL | GCA_MCTS_CONFLICT)) reward = 0.0;
@@ -363,7 +340,10 @@ struct __align__(16) TreeNode {
 };
 static_assert(sizeof(TreeNode) == 80, "tree node layout");
 
-// simulate_frame sub-frames of move(action) from global sub-frame depth * F (nodes_single.py:39-100); returns the flags
+// simulate_frame sub-frames of move(action) from global sub-frame depth * F (nodes_single.py:39-100); returns the flags.
+// One lane runs the whole move, sub-frame by sub-frame.  (Batching the state-independent noise / sincos chains of
+// several sub-frames for instruction-level parallelism was measured: 2 at a time -5 %, 5 at a time -25 % - the extra
+// registers cost more occupancy than the parallel chains return.)
 __device__ __forceinline__ int lane_move(const MctsArgs& a, const int* __restrict__ cnt, const double2* __restrict__ cand,
                                          uint32_t root, uint32_t sim, int depth, int act, double gx, double gy,
                                          double& ox, double& oy, double& vy_prev, double& heading) {
@@ -376,8 +356,8 @@ __device__ __forceinline__ int lane_move(const MctsArgs& a, const int* __restric
     const double nsp = mcts_normal(a, c.speed_sigma, root, sim, GCA_MCTS_DRAW_SPEED, (uint32_t)gf);
     double sp = clamp_speed(c, vy_prev);                              // state[-4] = clamp(state[-5])  (Q23)
     sp = __dadd_rn(sp, nsp);
-    heading = __dadd_rn(heading, d_heading);
-    heading = __dadd_rn(heading, nh);
+    heading = __dadd_rn(heading, d_heading);                          // state[-3] += d_heading
+    heading = __dadd_rn(heading, nh);                                 // state[-3] += normal(0, heading_sigma)
     double sn, cs;
     gca_sincos(heading, &sn, &cs);
     const double vx = __dmul_rn(sp, cs), vy = __dmul_rn(sp, sn);
@@ -477,35 +457,52 @@ __global__ void __launch_bounds__(128) mcts_search_kernel(const MctsArgs a) {
     return best;
   };
 
-  for (int s = 0; s < a.sims; ++s) {
-    int v = 0;                                                        // tree_policy  search_single.py:16-22
-    while (!(nodes[v].flags || nodes[v].depth == D)) {
-      if (nodes[v].untried > 0) {                                     // expand()  nodes_single.py:188-193
-        const int act = --nodes[v].untried;
-        TreeNode ch = nodes[v];
-        const int pd = ch.depth;
-        ch.flags = (signed char)lane_move(a, cnt, cand, root, (uint32_t)s, pd, act, gx, gy, ch.ox, ch.oy, ch.vy, ch.heading);
-        ch.parent = (short)v; ch.depth = (signed char)(pd + 1); ch.action = (signed char)act; ch.untried = 9;
-        ch.n_children = 0; ch.q = 0.0; ch.n = 0;
+  // One loop iteration = at most one model move per lane.  A lane that finished a simulation back-propagates, selects
+  // and (lazily) starts the next one in the same iteration, so the 32 roots of a warp execute lane_move together
+  // whatever simulation / phase each of them is in (the simulations of ONE root stay strictly sequential).
+  int s = 0, v = 0, flags = 0, depth = 0;
+  bool expand = false, running = false;
+  double ox = 0.0, oy = 0.0, vy = 0.0, heading = 0.0;
+  while (s < a.sims) {
+    if (!running) {
+      // tree_policy (search_single.py:16-22): walk down by UCT until a node with an untried action (or a terminal one)
+      v = 0;
+      expand = false;
+      while (!(nodes[v].flags || nodes[v].depth == D)) {
+        if (nodes[v].untried > 0) { expand = true; break; }
+        v = best_child(v, 1.4);
+      }
+      ox = nodes[v].ox; oy = nodes[v].oy; vy = nodes[v].vy; heading = nodes[v].heading;
+      flags = nodes[v].flags; depth = nodes[v].depth;
+      running = true;
+    }
+    if (!(flags || depth == D)) {
+      // the expansion move (action popped from the end, nodes_single.py:188-193) and the rollout moves (random actions,
+      // :198-204) are the same model step
+      int act;
+      if (expand) act = --nodes[v].untried;
+      else act = mcts_action(a, root, (uint32_t)s, (uint32_t)depth);
+      flags = lane_move(a, cnt, cand, root, (uint32_t)s, depth, act, gx, gy, ox, oy, vy, heading);
+      ++depth;
+      if (expand) {                                                   // the new child: the state after this one move
+        TreeNode ch{};
+        ch.ox = ox; ch.oy = oy; ch.vy = vy; ch.heading = heading;
+        ch.flags = (signed char)flags; ch.parent = (short)v; ch.depth = (signed char)depth; ch.action = (signed char)act;
+        ch.untried = 9;
         nodes[count] = ch;
         nodes[v].children[nodes[v].n_children++] = (short)count;
         v = count++;
-        break;
+        expand = false;
       }
-      v = best_child(v, 1.4);
     }
-    // rollout()  nodes_single.py:198-204
-    double ox = nodes[v].ox, oy = nodes[v].oy, vy = nodes[v].vy, heading = nodes[v].heading;
-    int flags = nodes[v].flags, depth = nodes[v].depth;
-    while (!(flags || depth == D)) {
-      const int act = mcts_action(a, root, (uint32_t)s, (uint32_t)depth);
-      flags = lane_move(a, cnt, cand, root, (uint32_t)s, depth, act, gx, gy, ox, oy, vy, heading);
-      ++depth;
-    }
-    const double reward = lane_reward(flags, ox, oy, gx, gy);
-    for (int u = v; u >= 0; u = nodes[u].parent) {                    // backpropagate  nodes_single.py:206-210
-      nodes[u].n += 1;
-      nodes[u].q = __dadd_rn(nodes[u].q, reward);
+    if (flags || depth == D) {
+      const double reward = lane_reward(flags, ox, oy, gx, gy);
+      for (int u = v; u >= 0; u = nodes[u].parent) {                  // backpropagate  nodes_single.py:206-210
+        nodes[u].n += 1;
+        nodes[u].q = __dadd_rn(nodes[u].q, reward);
+      }
+      running = false;
+      ++s;
     }
   }
   const int b = best_child(0, 0.0);
