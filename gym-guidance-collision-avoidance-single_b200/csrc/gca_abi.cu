@@ -536,6 +536,17 @@ int gca_compute_reward(const void* ag, const void* g, int64_t m, double radius, 
   return GCA_OK;
 }
 
+int gca_monitor_update(const void* reward, int is_f64, const uint8_t* done, int64_t n_envs, float* ep_return,
+                       int32_t* ep_length, gca_episode_record* ring, int64_t ring_capacity,
+                       unsigned long long* ring_count, uint32_t step, int device, void* stream) {
+  if (n_envs < 0 || ring_capacity <= 0 || (n_envs > 0 && (!reward || !done || !ep_return || !ep_length || !ring || !ring_count)))
+    return fail(GCA_ERR_INVALID, "bad arguments");
+  GCA_CUDA(cudaSetDevice(device));
+  GCA_CUDA(launch_monitor_update(reward, is_f64, done, (long long)n_envs, ep_return, ep_length, ring,
+                                 (long long)ring_capacity, ring_count, step, (cudaStream_t)stream));
+  return GCA_OK;
+}
+
 int gca_her_sample(const gca_her_episodes* ep, int64_t n_episodes, int T, int dim_o, int dim_u, int dim_g, int is_f64,
                    int64_t batch, double future_p, double goal_radius, int reward_kind, const gca_her_draws* draws,
                    uint64_t seed, uint32_t call, const gca_her_transitions* out, int device, void* stream) {

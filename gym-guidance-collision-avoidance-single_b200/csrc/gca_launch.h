@@ -21,6 +21,9 @@ size_t mcts_search_workspace_bytes(const gca_mcts_config* cfg, int n, long long 
 cudaError_t launch_mcts_search(const gca_mcts_config* cfg, int n, const double* roots, long long n_roots, int sims,
                                int depth, uint64_t seed, uint32_t root_id0, void* workspace, int32_t* best_action,
                                double* child_n, double* child_q, int32_t* child_action, cudaStream_t st);
+cudaError_t launch_monitor_update(const void* reward, int is_f64, const uint8_t* done, long long n, float* ep_return,
+                                  int32_t* ep_length, gca_episode_record* ring, long long cap, unsigned long long* count,
+                                  uint32_t step, cudaStream_t st);
 cudaError_t launch_her_sample(const gca_her_episodes* ep, long long E, int T, int dim_o, int dim_u, int dim_g, int is_f64,
                               long long batch, double future_p, double radius, int kind, const gca_her_draws* dr,
                               uint64_t seed, uint32_t call, const gca_her_transitions* out, cudaStream_t st);

@@ -43,4 +43,47 @@ cudaError_t launch_compute_reward(const void* ag, const void* g, long long m, do
   return cudaGetLastError();
 }
 
+// VecMonitor.step_wait (baselines common/vec_env/vec_monitor.py:21-37) for the whole batch: thread = env.  Finished
+// episodes are appended to a device ring (warp-aggregated slot reservation: one atomic per warp).
+template <typename R>
+__global__ void __launch_bounds__(256) monitor_kernel(const R* __restrict__ reward, const uint8_t* __restrict__ done,
+                                                      long long n, float* __restrict__ ep_return,
+                                                      int32_t* __restrict__ ep_length, gca_episode_record* __restrict__ ring,
+                                                      long long cap, unsigned long long* __restrict__ count, uint32_t step) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < n;
+  float ret = 0.0f;
+  int len = 0;
+  bool fin = false;
+  if (valid) {
+    ret = __fadd_rn(ep_return[i], (float)reward[i]);       // self.eprets += rews  (float32)
+    len = ep_length[i] + 1;                                // self.eplens += 1
+    fin = done[i] != 0;
+    ep_return[i] = fin ? 0.0f : ret;
+    ep_length[i] = fin ? 0 : len;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, fin);
+  if (m) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(count, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (fin) {
+      gca_episode_record rec;
+      rec.env = (int32_t)i; rec.length = len; rec.ep_return = ret; rec.step = step;
+      ring[(base + __popc(m & ((1u << lane) - 1u))) % (unsigned long long)cap] = rec;
+    }
+  }
+}
+
+cudaError_t launch_monitor_update(const void* reward, int is_f64, const uint8_t* done, long long n, float* ep_return,
+                                  int32_t* ep_length, gca_episode_record* ring, long long cap, unsigned long long* count,
+                                  uint32_t step, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (is_f64) monitor_kernel<double><<<blocks, 256, 0, st>>>((const double*)reward, done, n, ep_return, ep_length, ring, cap, count, step);
+  else monitor_kernel<float><<<blocks, 256, 0, st>>>((const float*)reward, done, n, ep_return, ep_length, ring, cap, count, step);
+  return cudaGetLastError();
+}
+
 }  // namespace gca

@@ -127,6 +127,7 @@ def load():
         "gca_profile_read": ([vp, P(GcaStepProfile)], C.c_int),
         "gca_compute_reward": ([vp, vp, i64, C.c_double, i32, i32, vp, i32, vp], C.c_int),
         "gca_raster": ([vp, vp, vp, i64, i64, i32, i32, vp, vp], C.c_int),
+        "gca_monitor_update": ([vp, i32, vp, i64, vp, vp, vp, i64, vp, u32, i32, vp], C.c_int),
         "gca_her_sample": ([P(GcaHerEpisodes), i64, i32, i32, i32, i32, i32, i64, C.c_double, C.c_double, i32,
                             P(GcaHerDraws), u64, u32, P(GcaHerTransitions), i32, vp], C.c_int),
         "gca_mcts_move": ([P(GcaMctsConfig), i32, vp, vp, vp, i64, P(GcaTape), u64, u32, i32, i32, vp], C.c_int),

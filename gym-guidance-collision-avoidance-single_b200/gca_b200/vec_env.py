@@ -41,7 +41,7 @@ class AircraftVecEnv(object):
         variant = _CLASS_OF.get(env, env)
         registered = env in _CLASS_OF
         if config is None:
-            if variant == "SingleAircraftMCTSEnv":
+            if variant in ("SingleAircraftMCTSEnv", "SingleAircraftDiscrete9HEREnv"):
                 from Simulators.config import Config as config
             else:
                 from gym_guidance_collision_avoidance_single.envs.config import Config as config
@@ -61,7 +61,7 @@ class AircraftVecEnv(object):
             self.observation_space = Dict(dict(
                 desired_goal=Box(-np.inf, np.inf, shape=(2,), dtype="float32"),
                 achieved_goal=Box(-np.inf, np.inf, shape=(2,), dtype="float32"),
-                observation=Box(-np.inf, np.inf, shape=(4 * n + 6,), dtype="float32")))
+                observation=Box(-np.inf, np.inf, shape=(b.obs_dim,), dtype="float32")))
         else:
             self.observation_space = Box(low=-1000, high=1000, shape=(4 * n + 8,), dtype=np.float32)
         if b.continuous:

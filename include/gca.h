@@ -236,6 +236,22 @@ typedef struct gca_mcts_config {
 
 enum { GCA_MCTS_WALL = 1, GCA_MCTS_CONFLICT = 2, GCA_MCTS_GOAL = 4 };
 
+/* ---- episode statistics (baselines common/vec_env/vec_monitor.py:21-37 VecMonitor.step_wait, bench/monitor.py:54-78):
+ * ep_return += reward (float32 accumulation, like np.zeros(num_envs, 'f')), ep_length += 1, and for every finished env
+ * a record (env, length, return, step) is appended to a ring on the device and its accumulators restart at 0 - no
+ * host synchronisation per step; the host drains the ring whenever it likes.  reward: REAL [n_envs] as written by
+ * gca_step (is_f64 = FAITHFUL mode); ring_count: device counter of all records ever appended (slot = count % cap). */
+typedef struct gca_episode_record {
+  int32_t env;
+  int32_t length;
+  float ep_return;
+  uint32_t step;
+} gca_episode_record;
+
+int gca_monitor_update(const void* reward, int is_f64, const uint8_t* done, int64_t n_envs, float* ep_return,
+                       int32_t* ep_length, gca_episode_record* ring, int64_t ring_capacity,
+                       unsigned long long* ring_count, uint32_t step, int device, void* stream);
+
 /* ---- HER replay: the "future" relabelling sampler of baselines (Algorithms/baselines-master/baselines/her/
  * her_sampler.py:19-61 _sample_her_transitions, called by replay_buffer.py:sample with o_2 = o[:, 1:], ag_2 = ag[:, 1:])
  * on an episode buffer that lives on the device.  For each of `batch` transitions: episode e and time t are drawn,

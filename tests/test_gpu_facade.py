@@ -166,3 +166,40 @@ def test_discrete9her_rewards_match_reference():
     env.compute_reward(a0, g["g"][0].copy(), None)
     assert np.array_equal(a0, g["ag0_after"])
     env.close()
+
+
+def test_vec_monitor_equals_baselines_vec_monitor(tmp_path):
+    """AircraftVecMonitor (device accumulators + episode ring, gca_monitor_update) against VecMonitor's arithmetic
+    (vec_monitor.py:21-37: float32 eprets += rews, eplens += 1, record + restart on done) and the monitor.csv format."""
+    import torch
+    from gca_b200.vec_env import AircraftVecEnv
+    from gca_b200.vec_monitor import AircraftVecMonitor
+    B = 300
+    venv = AircraftVecEnv("guidance-collision-avoidance-single-continuous-action-v0", B, n_intruders=20, seed=5)
+    mon = AircraftVecMonitor(venv, filename=str(tmp_path / "run"))
+    mon.reset()
+    eprets, eplens = np.zeros(B, "f"), np.zeros(B, "i")
+    want, got = [], []
+    rng = np.random.RandomState(0)
+    for t in range(400):
+        a = torch.as_tensor(rng.uniform(-1, 1, (B, 2)).astype(np.float32), device="cuda")
+        obs, rews, dones, infos = mon.step(a)
+        rews, dones = rews.cpu().numpy(), dones.cpu().numpy()
+        eprets += rews
+        eplens += 1
+        for i in range(B):
+            if dones[i]:
+                want.append((i, float(eprets[i]), int(eplens[i])))
+                eprets[i] = 0
+                eplens[i] = 0
+        if t % 97 == 0:
+            got += mon.drain()
+    got += mon.drain()
+    assert len(want) > 50
+    assert [(e["env"], e["r"], e["l"]) for e in got] == want
+    assert all(e["t"] > 0 for e in got)
+    mon.close()
+    lines = open(str(tmp_path / "run.monitor.csv")).read().splitlines()
+    assert lines[0].startswith('# {"t_start": ') and lines[1] == "r,l,t" and len(lines) == 2 + len(want)
+    r, l, t = lines[2].split(",")
+    assert float(r) == want[0][1] and int(l) == want[0][2]
