@@ -9,11 +9,11 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GCA_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libgca.so")
 
-GCA_ABI_VERSION = 3
+GCA_ABI_VERSION = 4
 
 MODE_FAITHFUL, MODE_FAST = 0, 1
 DRAWS_TAPE, DRAWS_PHILOX = 0, 1
-ACT_DISCRETE9, ACT_CONTINUOUS2, ACT_DISCRETE3 = 0, 1, 2
+ACT_DISCRETE9, ACT_CONTINUOUS2, ACT_DISCRETE3, ACT_DISCRETE3_HEADING = 0, 1, 2, 3
 OBS_VECTOR, OBS_HER, OBS_DHER, OBS_RAW, OBS_NONE, OBS_NEAREST = 0, 1, 2, 3, 4, 5
 WALL_NONE, WALL_TERMINAL, WALL_PENALTY = 0, 1, 2
 INFO_NONE, INFO_NMAC, INFO_CONFLICT, INFO_GOAL, INFO_WALL, INFO_MAXSTEPS = range(6)
@@ -31,7 +31,8 @@ class GcaConfig(C.Structure):
         "ob_window_width", "ob_window_height", "ob_min_speed", "ob_max_speed",
         "r_nmac", "r_conflict", "r_wall", "r_goal", "r_default")] + [(n, C.c_int32) for n in (
             "shaped_default", "action_kind", "obs_kind", "wall_kind", "max_steps", "time_limit", "random_start",
-            "nearest_n")] + [("ob_diagonal", C.c_double)]
+            "nearest_n")] + [("ob_diagonal", C.c_double), ("conflict_coeff", C.c_double), ("goal_margin", C.c_double),
+                             ("shaped_nearest", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class GcaHostState(C.Structure):
@@ -43,7 +44,7 @@ class GcaHostState(C.Structure):
 
 class GcaOut(C.Structure):
     _fields_ = [("obs", C.c_void_p), ("achieved", C.c_void_p), ("desired", C.c_void_p), ("reward", C.c_void_p),
-                ("done", C.c_void_p), ("info", C.c_void_p)]
+                ("done", C.c_void_p), ("info", C.c_void_p), ("nearest", C.c_void_p)]
 
 
 class GcaTape(C.Structure):

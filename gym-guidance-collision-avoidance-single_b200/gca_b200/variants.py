@@ -22,6 +22,9 @@ VARIANTS = {
     # Simulators/SingleAircraftDiscrete9HEREnv.py: random ownship start :78-82, n nearest intruders :127-144, rewards
     # from Simulators/config.py:37-43 (:207-227), out-of-map rule only under sparse_reward (:217-219)
     "SingleAircraftDiscrete9HEREnv": (abi.ACT_DISCRETE9, abi.OBS_NEAREST, None, 1, None, False),
+    # Simulators/SingleAircraftDiscrete3HEREnv.py: as 9HER with Discrete(3) heading-only actions (:407-411), the goal drawn
+    # 100 px inside the map (:349-353) and the nearest-intruder term added to the default reward (:225-232)
+    "SingleAircraftDiscrete3HEREnv": (abi.ACT_DISCRETE3_HEADING, abi.OBS_NEAREST, None, 1, None, False),
 }
 
 
@@ -57,10 +60,17 @@ def make_config(variant, cfg_cls, time_limit=0):
     c.random_start = 0
     c.nearest_n = 0
     c.ob_diagonal = 1.0
+    c.conflict_coeff = 0.0
+    c.goal_margin = 0.0
+    c.shaped_nearest = 0
     if obs == abi.OBS_NEAREST:
         c.random_start = 1
         c.nearest_n = int(cfg_cls.n)
         c.ob_diagonal = cfg_cls.diagonal
+    if variant == "SingleAircraftDiscrete3HEREnv":
+        c.conflict_coeff = cfg_cls.conflict_coeff
+        c.goal_margin = 100.0
+        c.shaped_nearest = 1
     return c
 
 

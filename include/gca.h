@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GCA_ABI_VERSION 3
+#define GCA_ABI_VERSION 4
 
 typedef enum gca_status {
   GCA_OK = 0,
@@ -52,7 +52,8 @@ enum {
   GCA_ACT_DISCRETE9 = 0,  /* int32 a: a0 = a / 3, a1 = a % 3, delta = (a0-1, a1-1)  PKG/SingleAircraftEnv.py:130-133,300-302;
                              also the (a0, a1) tuple of Simulators/SingleAircraftMCTSEnv.py:126-130 encoded a0*3+a1 */
   GCA_ACT_CONTINUOUS2 = 1, /* real a[2] in [-1,1]: delta = (a[0], a[1])              PKG/SingleAircraft2Env.py:292-294 */
-  GCA_ACT_DISCRETE3 = 2    /* int32 a: heading delta a-1, speed += speed_sigma       PKG/SingleAircraftDiscreteHEREnv.py:302-304 */
+  GCA_ACT_DISCRETE3 = 2,   /* int32 a: heading delta a-1, speed += speed_sigma       PKG/SingleAircraftDiscreteHEREnv.py:302-304 */
+  GCA_ACT_DISCRETE3_HEADING = 3 /* int32 a: heading delta a-1, speed only clamped   Simulators/SingleAircraftDiscrete3HEREnv.py:407-411 */
 };
 
 /* observation layout (a9/a10/a16) */
@@ -107,6 +108,12 @@ typedef struct gca_config {
                              0: (50, 50), min_speed, pi/4 (PKG/SingleAircraftEnv.py:72-76) */
   int32_t nearest_n;      /* GCA_OBS_NEAREST: Config.n (Simulators/config.py:55), 1..8 */
   double ob_diagonal;     /* GCA_OBS_NEAREST: Config.diagonal, normalises the distance entry (Simulators/config.py:8) */
+  /* Simulators/SingleAircraftDiscrete3HEREnv.py */
+  double conflict_coeff;  /* shaped_nearest: r = conflict_coeff * dist_nearest_intruder - 0.1 when that distance is below
+                             3 * minimum_separation, added to the default reward (:225-232; Simulators/config.py:44) */
+  double goal_margin;     /* > 0: the goal is drawn in [margin, window - margin]^2 (random_goal_pos :349-353) */
+  int32_t shaped_nearest; /* 1: track dist_nearest_intruder over the intruders the loop visited (:185,:191) */
+  int32_t reserved0;
 } gca_config;
 
 /* Canonical host-side view of the full simulator state, identical for both modes
@@ -134,6 +141,8 @@ typedef struct gca_out {
   void* reward;    /* REAL [B]     (ignored by gca_reset) */
   uint8_t* done;   /* [B] */
   uint8_t* info;   /* [B] GCA_INFO_* */
+  void* nearest;   /* REAL [B] or NULL; shaped_nearest only: dist_nearest_intruder of the step, the value
+                      Simulators/SingleAircraftDiscrete3HEREnv.py:178 returns in place of info (9999 if no intruder) */
 } gca_out;
 
 /* Recorded draws for GCA_DRAWS_TAPE: env b reads values[b*stride + cursor[b]++]. */

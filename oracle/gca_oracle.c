@@ -222,6 +222,15 @@ static void reset_env(env_view* e) {
   *e->own_vel_is_f32 = 1;
   for (int i = 0; i < e->n; ++i) spawn(e, i, GCA_SLOT_RESET | (uint32_t)i);
   draw_pos(e, GCA_SLOT_GOAL, GCA_BLOCK_POS, &e->goal[0], &e->goal[1]);
+  if (cfg->goal_margin > 0 && e->draws == GCA_DRAWS_PHILOX) {
+    /* random_goal_pos(): uniform(low=[m, m], high=[W - m, H - m])  Simulators/SingleAircraftDiscrete3HEREnv.py:349-353;
+     * draw_pos gave W * u: recover u is not exact, so draw again from the same block */
+    double u[2];
+    gca_oracle_philox_uniform2(e->seed, e->env_id, e->tick, GCA_SLOT_GOAL, GCA_BLOCK_POS, u);
+    const double m = cfg->goal_margin;
+    e->goal[0] = m + ((cfg->window_width - m) - m) * u[0];
+    e->goal[1] = m + ((cfg->window_height - m) - m) * u[1];
+  }
   *e->no_conflict = 0;
   *e->ep_steps = 0;
 }
@@ -362,7 +371,7 @@ static void ownship_step(env_view* e, const double* action) {
     f0 = action[0];
     f1 = action[1];
   } else {
-    f0 = (double)((int)action[0] - 1);
+    f0 = (double)((int)action[0] - 1);                  /* DISCRETE3 and DISCRETE3_HEADING */
   }
   draw_own_noise(e, &nh, &ns);
   double heading = e->own_hs[0], speed = e->own_hs[1];
@@ -385,8 +394,12 @@ static void ownship_step(env_view* e, const double* action) {
 }
 
 /* _terminal_reward()  PKG/SingleAircraftEnv.py:143-184 and the variant rows of SURVEY.md 8(a) */
-static void terminal_reward(env_view* e, double* reward, uint8_t* done, uint8_t* info) {
+static void terminal_reward(env_view* e, double* reward, uint8_t* done, uint8_t* info, double* nearest) {
   const gca_config* cfg = e->cfg;
+  /* self.dist_nearest_intruder = 9999 (Simulators/SingleAircraftDiscrete3HEREnv.py:185): value + dtype of the holder */
+  double dnear = 9999.0;
+  int near_is64 = 1, near_set = 0;
+  if (nearest) *nearest = dnear;
   if (cfg->max_steps > 0 && *e->ep_steps >= cfg->max_steps) {            /* StackEnv :134-136 */
     *reward = 0.0; *done = 1; *info = GCA_INFO_MAXSTEPS;
     return;
@@ -402,6 +415,10 @@ static void terminal_reward(env_view* e, double* reward, uint8_t* done, uint8_t*
       e->ipos[2 * i + 1] = (double)((float)e->ipos[2 * i + 1] + e->ivel[2 * i + 1]);
     }
     double d = dist_intruder(e, i);
+    if (!(dnear < d)) {            /* min(dist_intruder, self.dist_nearest_intruder): the first argument wins ties :191 */
+      dnear = d; near_is64 = is64; near_set = 1;
+    }
+    if (nearest) *nearest = dnear;
     int old_flag = e->iflag[i], replaced = 0;
     if (!in_map(cfg, e->ipos[2 * i], e->ipos[2 * i + 1])) {
       spawn(e, i, (uint32_t)i);                                          /* :153-154 */
@@ -433,6 +450,18 @@ static void terminal_reward(env_view* e, double* reward, uint8_t* done, uint8_t*
     return;
   }
   *reward = cfg->shaped_default ? -dg / 1200 : cfg->r_default;
+  if (cfg->shaped_nearest) {       /* :225-232 - NumPy 2 weak scalars: an f32 distance keeps the arithmetic in f32 */
+    const double thr = 3 * cfg->minimum_separation;
+    if (near_set ? lt_thr(dnear, near_is64, thr) : dnear < thr) {
+      if (near_is64) {
+        const double r = cfg->conflict_coeff * dnear - 0.1;
+        *reward = cfg->shaped_default ? -dg / 1200 + r : cfg->r_default + r;
+      } else {
+        const float r = (float)((float)cfg->conflict_coeff * (float)dnear) - (float)0.1;
+        *reward = cfg->shaped_default ? -dg / 1200 + (double)r : (double)((float)cfg->r_default + r);
+      }
+    }
+  }
   *done = 0;
   *info = GCA_INFO_NONE;
 }
@@ -473,7 +502,7 @@ int gca_oracle_step(const gca_config* cfg, gca_oracle_batch* b, const double* ac
     bind(&e, cfg, b, i);
     *e.ep_steps += 1;                                                    /* StackEnv :118 (a TimeLimit counter elsewhere) */
     ownship_step(&e, actions + 2 * (size_t)i);
-    terminal_reward(&e, &b->reward[i], &b->done[i], &b->info[i]);
+    terminal_reward(&e, &b->reward[i], &b->done[i], &b->info[i], b->nearest ? &b->nearest[i] : NULL);
     if (cfg->time_limit > 0 && *e.ep_steps >= cfg->time_limit) b->done[i] = 1;   /* gym TimeLimit (registered ids) */
     observe_env(&e, row(b->obs, i, D), row(b->achieved, i, 2), row(b->desired, i, 2));
     if (b->term_obs && D) memcpy(row(b->term_obs, i, D), row(b->obs, i, D), sizeof(double) * D);

@@ -45,6 +45,7 @@ typedef struct gca_oracle_batch {
   uint8_t* done;              /* [B] */
   uint8_t* info;              /* [B] */
   double* term_obs;           /* [B][obs_dim] or NULL: observation of the step itself, before any auto-reset */
+  double* nearest;            /* [B] or NULL: dist_nearest_intruder (shaped_nearest variants) */
 } gca_oracle_batch;
 
 /* actions: double[B][2]; discrete kinds use actions[b][0] as the integer code. */

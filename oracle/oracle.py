@@ -48,7 +48,7 @@ def lib():
         ("seed", C.c_uint64), ("env_id0", C.c_uint32), ("reserved0", C.c_uint32),
         ("f32_positions", C.c_int32), ("auto_reset", C.c_int32),
         ("obs", C.c_void_p), ("achieved", C.c_void_p), ("desired", C.c_void_p), ("reward", C.c_void_p),
-        ("done", C.c_void_p), ("info", C.c_void_p), ("term_obs", C.c_void_p),
+        ("done", C.c_void_p), ("info", C.c_void_p), ("term_obs", C.c_void_p), ("nearest", C.c_void_p),
     ]
     L = C.CDLL(LIB)
     P = C.POINTER
@@ -122,6 +122,7 @@ class OracleEnv(object):
         self.reward = np.zeros(self.B, np.float64)
         self.done = np.zeros(self.B, np.uint8)
         self.info = np.zeros(self.B, np.uint8)
+        self.nearest = np.zeros(self.B, np.float64)
 
     @property
     def own_vel_is_f32(self):
@@ -143,6 +144,7 @@ class OracleEnv(object):
         b.f32_positions, b.auto_reset = int(self.f32_positions), int(self.auto_reset)
         b.obs, b.achieved, b.desired = _p(self.obs), _p(self.achieved), _p(self.desired)
         b.reward, b.done, b.info, b.term_obs = _p(self.reward), _p(self.done), _p(self.info), _p(self.term_obs)
+        b.nearest = _p(self.nearest)
         return b
 
     def reset(self, mask=None):

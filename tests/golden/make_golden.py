@@ -34,6 +34,7 @@ from gym_guidance_collision_avoidance_single.envs import (  # noqa: E402
 from gym_guidance_collision_avoidance_single.envs.config import Config as PkgConfig  # noqa: E402
 import SingleAircraftMCTSEnv as mcts_env_mod  # noqa: E402  (Simulators/, uses Simulators/config.py)
 import SingleAircraftDiscrete9HEREnv as d9her_mod  # noqa: E402  (Simulators/, nearest-n observation)
+import SingleAircraftDiscrete3HEREnv as d3her_mod  # noqa: E402  (Simulators/, + nearest-intruder reward term)
 import config as SimConfigMod  # noqa: E402
 import nodes_single  # noqa: E402
 import search_single  # noqa: E402
@@ -174,9 +175,10 @@ VARIANTS = {
     "dher": (SingleAircraftDiscreteHEREnv, PkgConfig, "d3"),
     "mcts": (mcts_env_mod.SingleAircraftEnv, SimConfigMod.Config, "t33"),
     "d9her": (d9her_mod.SingleAircraftDiscrete9HEREnv, SimConfigMod.Config, "d9"),
+    "d3her": (d3her_mod.SingleAircraftDiscrete3HEREnv, SimConfigMod.Config, "d3"),
 }
 # np.argpartition(dist_array, Config.n) of the nearest-n observation needs more than n = 4 intruders
-PLANS = {"d9her": {5: (5, 40), 12: (5, 40), 80: (3, 30)}}
+PLANS = {"d9her": {5: (5, 40), 12: (5, 40), 80: (3, 30)}, "d3her": {5: (5, 40), 12: (5, 40), 80: (3, 30)}}
 
 
 def sample_action(kind, rng):
@@ -204,6 +206,8 @@ def ref_action(kind, a):
 def info_code(info):
     if isinstance(info, dict):
         info = info.get("result", "")
+    if not isinstance(info, str):            # Discrete3HER returns dist_nearest_intruder in place of info (:178)
+        return 255
     return INFO_CODE[info]
 
 
@@ -213,7 +217,8 @@ def run_trace(variant, n, seed, kind, T):
     rng = np.random.RandomState((1000003 * seed + 17) % (2 ** 32))   # private: never touches the global stream
     np.random.seed(seed)
     env = cls()                                          # HER ctors reset() here; draws discarded
-    rec = {k: [] for k in ("actions", "obs", "ag", "dg", "reward", "reward_is_int", "done", "info", "event",
+    rec = {k: [] for k in ("actions", "obs", "ag", "dg", "reward", "reward_is_int", "done", "info", "event", "nearest",
+                           "reward_is_f32",
                            "no_conflict", "cur_before", "cur_after", "cur_after_reset", "reset_obs",
                            "reset_ag", "reset_dg")}
     states_after, states_reset, reset_steps = [], [], []
@@ -245,6 +250,8 @@ def run_trace(variant, n, seed, kind, T):
             rec["reward_is_int"].append(np.uint8(isinstance(r, int)))
             rec["done"].append(np.uint8(bool(done)))
             rec["info"].append(np.uint8(info_code(info)))
+            rec["nearest"].append(np.float64(info) if not isinstance(info, (str, dict)) else np.float64(np.nan))
+            rec["reward_is_f32"].append(np.uint8(isinstance(r, np.float32)))
             rec["event"].append(np.uint8(INFO_CODE[last_event[0]]))
             rec["no_conflict"].append(np.int32(env.no_conflict))
             states_after.append(snapshot(env, n))

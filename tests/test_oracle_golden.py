@@ -52,6 +52,8 @@ def test_free_running_replay_matches_reference(vk, n):
         assert np.array_equal(info, g["event"][:, t]), what
         assert np.array_equal(done, g["done"][:, t]), what
         assert np.array_equal(rew, g["reward"][:, t]), what
+        if vk == "d3her":                           # the 4th return value of Discrete3HER.step: dist_nearest_intruder
+            assert np.array_equal(env.nearest, g["nearest"][:, t]), what
         assert np.array_equal(env.state["no_conflict"], g["no_conflict"][:, t]), what
         assert np.array_equal(env.cursor, g["cur_after"][:, t]), what
         assert np.array_equal(obs, g["obs"][:, t]), what
