@@ -59,7 +59,7 @@ size_t real_size(const gca_env* e) { return e->mode == GCA_MODE_FAITHFUL ? sizeo
 
 int check_config(const gca_config* c) {
   if (!c) return fail(GCA_ERR_INVALID, "config is NULL");
-  if (c->action_kind < GCA_ACT_DISCRETE9 || c->action_kind > GCA_ACT_DISCRETE3) return fail(GCA_ERR_INVALID, "bad action_kind");
+  if (c->action_kind < GCA_ACT_DISCRETE9 || c->action_kind > GCA_ACT_DISCRETE3_HEADING) return fail(GCA_ERR_INVALID, "bad action_kind");
   if (c->obs_kind < GCA_OBS_VECTOR || c->obs_kind > GCA_OBS_NEAREST) return fail(GCA_ERR_INVALID, "bad obs_kind");
   if (c->obs_kind == GCA_OBS_NEAREST && (c->nearest_n < 1 || c->nearest_n > 8 || !(c->ob_diagonal > 0)))
     return fail(GCA_ERR_INVALID, "GCA_OBS_NEAREST needs 1 <= nearest_n <= 8 and a positive ob_diagonal");
@@ -151,6 +151,7 @@ StepArgs make_args(const gca_env* e, const void* actions, const gca_tape* tape, 
   if (out) {
     a.obs = out->obs; a.achieved = out->achieved; a.desired = out->desired;
     a.reward = out->reward; a.done = out->done; a.info = out->info;
+    a.nearest = out->nearest;
   }
   return a;
 }

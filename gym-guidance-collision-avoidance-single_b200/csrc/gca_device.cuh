@@ -139,6 +139,7 @@ struct StepArgs {
   void* reward;
   uint8_t* done;
   uint8_t* info;
+  void* nearest;          // REAL [B] or nullptr (shaped_nearest variants)
 };
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -222,6 +223,23 @@ __device__ __forceinline__ void draw_pos(Draws<TAPE>& d, const gca_config& c, ui
     x = __dadd_rn(0.0, __dmul_rn(__dadd_rn(c.window_width, -0.0), u0));   // low + (high - low) * u
     y = __dadd_rn(0.0, __dmul_rn(__dadd_rn(c.window_height, -0.0), u1));
   }
+}
+
+// Goal(random_pos()) :93, or random_goal_pos() = uniform(low=[m, m], high=[W - m, H - m]) with goal_margin m
+// (Simulators/SingleAircraftDiscrete3HEREnv.py:349-353)
+template <bool TAPE>
+__device__ __forceinline__ void draw_goal(Draws<TAPE>& d, const gca_config& c, double& x, double& y) {
+  if constexpr (!TAPE) {
+    if (c.goal_margin > 0) {
+      double u0, u1;
+      d.uniform2(GCA_SLOT_GOAL, GCA_BLOCK_POS, u0, u1);
+      const double m = c.goal_margin;
+      x = __dadd_rn(m, __dmul_rn(__dadd_rn(__dadd_rn(c.window_width, -m), -m), u0));   // low + (high - low) * u
+      y = __dadd_rn(m, __dmul_rn(__dadd_rn(__dadd_rn(c.window_height, -m), -m), u1));
+      return;
+    }
+  }
+  draw_pos(d, c, GCA_SLOT_GOAL, GCA_BLOCK_POS, x, y);
 }
 
 // random_speed(), random_heading()   PKG/SingleAircraftEnv.py:246-250

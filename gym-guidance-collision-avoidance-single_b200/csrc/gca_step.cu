@@ -114,7 +114,7 @@ __device__ __forceinline__ void reset_env_warp(const StepArgs& a, size_t env, in
         s.cflag[flag_index(s, env, r)] = 0u;
         if constexpr (FAITH) s.dflag[flag_index(s, env, r)] = dw;
       }
-      draw_pos(d, c, GCA_SLOT_GOAL, GCA_BLOCK_POS, goal.x, goal.y);   // Goal(random_pos()) :93
+      draw_goal(d, c, goal.x, goal.y);   // Goal(random_pos()) :93
     }
   } else {
     for (int r = 0; r < s.W; ++r) {
@@ -135,7 +135,7 @@ __device__ __forceinline__ void reset_env_warp(const StepArgs& a, size_t env, in
         if constexpr (FAITH) s.dflag[flag_index(s, env, r)] = dw;
       }
     }
-    if (lane == owner) draw_pos(d, c, GCA_SLOT_GOAL, GCA_BLOCK_POS, goal.x, goal.y);
+    if (lane == owner) draw_goal(d, c, goal.x, goal.y);
   }
 }
 
@@ -321,6 +321,23 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
     write_obs_intruder<FAITH>(a, obase, i, it);
   };
 
+  // self.dist_nearest_intruder (Simulators/SingleAircraftDiscrete3HEREnv.py:185,191): min over the intruders the loop
+  // visited of the distance it measured - the advanced position of the OLD object, which the plane this step wrote
+  // still holds for every intruder (respawns come later).  Python's min(d, current) keeps d on ties; value and dtype.
+  double dnear = 9999.0;
+  bool near64 = true, near_set = false;
+  if (c.shaped_nearest && replay) {
+    const int last = stop < s.N - 1 ? stop : s.N - 1;
+    for (int i = 0; i <= last; ++i) {
+      Intr<FAITH> it;
+      load_intruder<FAITH>(s, nxt, me, i, it);
+      bool wide = false;
+      if constexpr (FAITH) wide = it.is64;
+      const double dd = wide ? dist_f64((double)pos.x, (double)pos.y, (double)it.px, (double)it.py)
+                             : (double)__fsqrt_rn(dist2_f32(pos.x, pos.y, (float)it.px, (float)it.py));
+      if (!(dnear < dd)) { dnear = dd; near64 = wide; near_set = true; }
+    }
+  }
   if (replay) {
     if (words_in_regs) {
 #pragma unroll
@@ -423,12 +440,26 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
       } else {
         reward = c.shaped_default ? ddiv_prepared(k, -dg, k.dv_shape, k.rc_shape) : c.r_default;
         info = GCA_INFO_NONE;
+        if (c.shaped_nearest) {                            // :225-232 (NumPy 2 weak scalars: an f32 distance stays f32)
+          const double thr = 3 * c.minimum_separation;
+          const bool lt = near_set ? (near64 ? dnear < thr : (float)dnear < (float)thr) : dnear < thr;
+          if (lt) {
+            if (near64) {
+              const double r = __dadd_rn(__dmul_rn(c.conflict_coeff, dnear), -0.1);
+              reward = __dadd_rn(reward, r);
+            } else {
+              const float r = __fadd_rn(__fmul_rn((float)c.conflict_coeff, (float)dnear), -(float)0.1);
+              reward = c.shaped_default ? __dadd_rn(reward, (double)r) : (double)__fadd_rn((float)c.r_default, r);
+            }
+          }
+        }
       }
     }
     if (c.time_limit > 0 && cnt.y >= c.time_limit) done = true;    // gym TimeLimit of the registered ids
     reinterpret_cast<R*>(a.reward)[me] = (R)reward;
     a.done[me] = done ? 1 : 0;
     a.info[me] = (uint8_t)info;
+    if (a.nearest) reinterpret_cast<R*>(a.nearest)[me] = (R)dnear;
     if (!(done && a.auto_reset))                                   // (a finished env shows its reset observation, below)
       write_obs_own<FAITH>(a, me, pos.x, pos.y, vel.x, vel.y, false, hs.x, hs.y, goal.x, goal.y);   // :115-124
   }
@@ -487,7 +518,7 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
       base = __shfl_sync(FULL, base, 0);
       if (resets) {
         s.reset_list[base + __popc(rmask & ((1u << lane) - 1u))] = (int)me;
-        draw_pos(d, c, GCA_SLOT_GOAL, GCA_BLOCK_POS, goal.x, goal.y);   // Goal(random_pos()) :93
+        draw_goal(d, c, goal.x, goal.y);   // Goal(random_pos()) :93
       }
 #ifdef GCA_PHASE_TIMING
       fin_resets += __popc(rmask);

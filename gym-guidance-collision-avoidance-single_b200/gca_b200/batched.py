@@ -63,10 +63,13 @@ class BatchedAircraftEnv(object):
             self.reward = torch.zeros((B,), dtype=self.real, device=self.device)
             self.done = torch.zeros((B,), dtype=torch.uint8, device=self.device)
             self.info = torch.zeros((B,), dtype=torch.uint8, device=self.device)
+        # dist_nearest_intruder of the step (Simulators/SingleAircraftDiscrete3HEREnv.py:178), shaped_nearest variants only
+        self.nearest = torch.zeros((B,), dtype=self.real, device=self.device) if self.cfg.shaped_nearest else None
         self._out = abi.GcaOut(self.obs.data_ptr() if self.obs_dim else None,
                                self.achieved.data_ptr() if self.is_goal_env else None,
                                self.desired.data_ptr() if self.is_goal_env else None,
-                               self.reward.data_ptr(), self.done.data_ptr(), self.info.data_ptr())
+                               self.reward.data_ptr(), self.done.data_ptr(), self.info.data_ptr(),
+                               self.nearest.data_ptr() if self.nearest is not None else None)
         self._tape = None
         self._tape_keep = None
         self._host = None

@@ -330,5 +330,22 @@ class SingleAircraftDiscrete9HEREnv(_GoalBase):
         return c.step_penalty if c.sparse_reward else -dist_goal / 1200
 
 
+class SingleAircraftDiscrete3HEREnv(SingleAircraftDiscrete9HEREnv):
+    """Simulators/SingleAircraftDiscrete3HEREnv.py: the 9HER env with Discrete(3) heading-only actions (:407-411), the goal
+    drawn 100 px inside the map (:349-353), the nearest-intruder term in the default reward (:225-232) - and step()
+    returning dist_nearest_intruder where gym's info would be (:178)."""
+    VARIANT = "SingleAircraftDiscrete3HEREnv"
+
+    def _build_spaces(self):
+        SingleAircraftDiscrete9HEREnv._build_spaces(self)
+        self.action_space = Discrete(3)
+        self.dist_nearest_intruder = 9999
+
+    def step(self, action):
+        ob, reward, done, _ = _SingleBase.step(self, action)
+        self.dist_nearest_intruder = float(self._batch.nearest[0].item())
+        return ob, np.float64(reward), done, self.dist_nearest_intruder
+
+
 def _unused():  # keep math imported for parity with the reference module namespace
     return math.pi

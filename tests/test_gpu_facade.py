@@ -21,17 +21,19 @@ def _make(vk, n, **kw):
             from Simulators.SingleAircraftMCTSEnv import SingleAircraftEnv as cls
         elif vk == "d9her":
             from Simulators.SingleAircraftDiscrete9HEREnv import SingleAircraftDiscrete9HEREnv as cls
+        elif vk == "d3her":
+            from Simulators.SingleAircraftDiscrete3HEREnv import SingleAircraftDiscrete3HEREnv as cls
         else:
             import gym_guidance_collision_avoidance_single.envs as envs
             cls = {"env": envs.SingleAircraftEnv, "env2": envs.SingleAircraft2Env, "her": envs.SingleAircraftHEREnv,
                    "dher": envs.SingleAircraftDiscreteHEREnv}[vk]
         return cls(**kw)
     finally:
-        cfgc.intruder_size = 80 if vk in ("mcts", "d9her") else 0
+        cfgc.intruder_size = 80 if vk in ("mcts", "d9her", "d3her") else 0
 
 
 def _ref_action(vk, a):
-    if vk in ("env", "dher", "d9her"):
+    if vk in ("env", "dher", "d9her", "d3her"):
         return int(a[0])
     if vk == "mcts":
         return (int(a[0]), int(a[1]))
@@ -39,13 +41,13 @@ def _ref_action(vk, a):
 
 
 @pytest.mark.parametrize("vk,n", [("env", 3), ("env", 80), ("env2", 3), ("her", 3), ("dher", 3), ("mcts", 80),
-                                  ("d9her", 12), ("d9her", 80)])
+                                  ("d9her", 12), ("d9her", 80), ("d3her", 12)])
 def test_single_env_api_replays_reference_trace(vk, n):
     g = load_trace(vk, n)
     plain = [int(i) for i in np.nonzero(g["kind_id"] == 0)[0]][:2]
     for tr in plain:
         tape = np.nan_to_num(g["tape"][tr:tr + 1], nan=0.0)
-        if vk in ("her", "dher", "d9her"):      # these constructors reset() once themselves (PKG/SingleAircraftHEREnv.py:32)
+        if vk in ("her", "dher", "d9her", "d3her"):   # these constructors reset() once themselves (PKG/SingleAircraftHEREnv.py:32)
             tape = np.concatenate([tape[:, : int(g["cur_reset0"][tr])], tape], axis=1)
         env = _make(vk, n, draws="tape", tape=tape)
         ob = env.reset()
@@ -60,7 +62,7 @@ def test_single_env_api_replays_reference_trace(vk, n):
             ob, r, done, info = env.step(_ref_action(vk, g["actions"][tr, t]))
             assert close(ob["observation"] if her else ob, g["obs"][tr, t])
             assert close(r, g["reward"][tr, t])
-            if vk not in ("mcts", "d9her"):
+            if vk not in ("mcts", "d9her", "d3her"):
                 assert isinstance(r, int) == bool(g["reward_is_int"][tr, t]), (vk, t, r)
             assert done == bool(g["done"][tr, t]) and isinstance(done, bool)
             code = ("", "n", "c", "g", "w", "m")[g["event"][tr, t]]
@@ -68,6 +70,8 @@ def test_single_env_api_replays_reference_trace(vk, n):
                 assert info == code
             elif vk == "dher":
                 assert info == {}
+            elif vk == "d3her":
+                assert close(info, g["nearest"][tr, t])
             else:
                 assert info == {"result": code}
             assert env.no_conflict == int(g["no_conflict"][tr, t])

@@ -90,6 +90,9 @@ def test_golden_replay_faithful(vk, n):
         assert close(obs, g["obs"][:, t]), what
         if her:
             assert close(env.achieved.cpu().numpy(), g["ag"][:, t]) and close(env.desired.cpu().numpy(), g["dg"][:, t])
+        if vk == "d3her":
+            assert close(env.nearest.cpu().numpy(), g["nearest"][:, t]), what
+            assert np.array_equal(env.nearest.cpu().numpy(), ref.nearest), what
         state = env.get_state()
         want = golden_state(g, "sa_", (slice(None), t))
         assert np.array_equal(state["no_conflict"], want["no_conflict"]), what
@@ -114,7 +117,7 @@ def test_golden_replay_faithful(vk, n):
 
 
 @pytest.mark.parametrize("vk,n", [("env", 80), ("env2", 80), ("her", 3), ("dher", 80), ("mcts", 80), ("d9her", 80),
-                                  ("d9her", 12)])
+                                  ("d9her", 12), ("d3her", 80)])
 def test_teacher_forced_single_steps(vk, n):
     """Load each recorded reference state, take ONE step, compare with the next recorded state
     (chaotic divergence cannot hide a bug)."""
@@ -144,7 +147,8 @@ def test_teacher_forced_single_steps(vk, n):
 @pytest.mark.parametrize("vk,n,B,T", [("env", 80, 4096, 40), ("env2", 80, 2048, 40), ("her", 33, 1000, 40),
                                       ("dher", 3, 1000, 60), ("mcts", 80, 1024, 40), ("env", 0, 5000, 30),
                                       ("env", 1, 777, 60), ("env2", 200, 300, 30), ("d9her", 80, 2048, 60),
-                                      ("d9her", 5, 999, 80), ("d9her", 33, 500, 40)])
+                                      ("d9her", 5, 999, 80), ("d9her", 33, 500, 40), ("d3her", 80, 2048, 60),
+                                      ("d3her", 7, 640, 80)])
 def test_philox_rollout_bit_exact_vs_oracle(vk, n, B, T, mode):
     """On-device Philox draws, VecEnv auto-reset: every output and the whole state must equal the
     CPU oracle driven by the same counter-based stream - bit for bit (ragged batch sizes included)."""
@@ -162,7 +166,7 @@ def test_philox_rollout_bit_exact_vs_oracle(vk, n, B, T, mode):
             if fast:
                 a = a.astype(np.float32).astype(np.float64)
         else:
-            a = np.stack([rng.randint(0, 3 if vk == "dher" else 9, B), np.zeros(B)], -1).astype(np.float64)
+            a = np.stack([rng.randint(0, 3 if vk in ("dher", "d3her") else 9, B), np.zeros(B)], -1).astype(np.float64)
         obs, rew, done, info = env.step(gpu_actions(env, a))
         ref.step(a)
         info = info.cpu().numpy()
@@ -173,6 +177,8 @@ def test_philox_rollout_bit_exact_vs_oracle(vk, n, B, T, mode):
         if env.is_goal_env:
             assert np.array_equal(env.achieved.cpu().numpy(), cast(ref.achieved))
             assert np.array_equal(env.desired.cpu().numpy(), cast(ref.desired))
+        if env.nearest is not None:
+            assert np.array_equal(env.nearest.cpu().numpy(), cast(ref.nearest)), t
         events += np.bincount(info, minlength=6)
     assert_state_equal(env.get_state(), ref.state, "final state", skip=())
     assert np.array_equal(env.get_state()["tick"], ref.state["tick"])
