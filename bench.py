@@ -317,7 +317,9 @@ def main_gpu(args):
                        "launch": "CUDA graph of %d steps (%d kernels each), replayed" % (GRAPH_STEPS, kernels_per_step)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": Ke, "api": "BatchedAircraftEnv.step_host -> gca_step_host (pinned host buffers)"},
+                    "steps": Ke, "api": "BatchedAircraftEnv.step_host -> gca_step_host (pinned host buffers)",
+                    "host_link_gbs": (h2d + d2h) * (e2e_value / world / B) / 1e9,
+                    "note": "bound by the device->host copy of the observations over PCIe, not by the kernels"},
             "gpu_launches": K * kernels_per_step,
             "roofline": {"bound": "hbm", "kernel": "step_intruders_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
