@@ -212,6 +212,8 @@ def main_gpu(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # NCCL would print its banner on stdout,
+            os.environ["NCCL_DEBUG"] = "WARN"                           # ahead of the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist.barrier()
 
