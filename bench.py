@@ -465,6 +465,32 @@ def bench_her(device):
             "note": "step (dict observation, own-first layout) + HER relabel reward on 4*B pairs, eager launches"}
 
 
+def graph_step_ms(step_fn, n_batches, reps=6):
+    """ms per step of `step_fn(i)` captured as a CUDA graph of n_batches steps and replayed (same launch mode as the
+    headline number); warm-up on a side stream as graph capture requires."""
+    import torch
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for i in range(3):
+            step_fn(i % n_batches)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for i in range(n_batches):
+            step_fn(i)
+    graph.replay()
+    torch.cuda.synchronize()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(reps):
+        graph.replay()
+    stop.record()
+    torch.cuda.synchronize()
+    return start.elapsed_time(stop) / (reps * n_batches)
+
+
 def bench_d9her(device):
     """Simulators/SingleAircraftDiscrete9HEREnv (random ownship start, observation = ownship + the
     4 nearest intruders, dict goals) - the env the repo's own learners train on.  5 kernels per step (the nearest-n
@@ -487,11 +513,23 @@ def bench_d9her(device):
         env.step(acts[i % 8])
     stop.record()
     torch.cuda.synchronize()
-    ms = start.elapsed_time(stop) / reps
+    ms_eager = start.elapsed_time(stop) / reps
+    acts50 = [torch.randint(0, 9, (B,), device="cuda", dtype=torch.int32) for _ in range(GRAPH_STEPS)]
+    ms = graph_step_ms(lambda i: env.step(acts50[i]), GRAPH_STEPS)
     k = env.kernels_per_step
     env.close()
-    return {"metric": METRIC, "value": B / (ms * 1e-3), "unit": UNIT, "envs": B, "intruders": N, "ms_per_step": ms,
-            "kernels_per_step": k, "obs_dim": 24, "note": "nearest-4 observation (24 values + goals), eager launches"}
+    out = {"metric": METRIC, "value": B / (ms * 1e-3), "unit": UNIT, "envs": B, "intruders": N, "ms_per_step": ms,
+           "ms_per_step_eager": ms_eager, "kernels_per_step": k, "obs_dim": 24,
+           "note": "nearest-4 observation (24 values + goals); CUDA graph of %d steps replayed" % GRAPH_STEPS}
+    # the Discrete(3) sibling: + nearest-intruder reward term measured in the finish kernel
+    env3 = BatchedAircraftEnv("SingleAircraftDiscrete3HEREnv", B, SimConfig, n_intruders=N, mode="fast", draws="philox",
+                              device=device, seed=7)
+    env3.reset()
+    acts3 = [torch.randint(0, 3, (B,), device="cuda", dtype=torch.int32) for _ in range(GRAPH_STEPS)]
+    ms3 = graph_step_ms(lambda i: env3.step(acts3[i]), GRAPH_STEPS)
+    env3.close()
+    out["d3her"] = {"value": B / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3}
+    return out
 
 
 def bench_her_replay(device):

@@ -257,6 +257,7 @@ int gca_create(const gca_config* cfg, int n_envs, int n_intruders, int mode, int
   if (!rc) rc = dev_alloc(e, &s.ev_conf, flag_plane_words(s));
   if (!rc) rc = dev_alloc(e, &s.ev_gone, flag_plane_words(s));
   if (!rc) rc = dev_alloc(e, &s.ev_nmac, (size_t)s.T * 32);
+  if (!rc) rc = dev_alloc(e, &s.ev_near, (size_t)s.T * 32);
   if (!rc) rc = dev_alloc(e, &s.reset_list, (size_t)s.T * 32);
   if (!rc) rc = dev_alloc(e, &s.reset_count, 1);
   s.respawn_cap = (int)std::min<size_t>((size_t)s.T * 32 * 4, (size_t)1 << 30);

@@ -5,6 +5,7 @@
 // place where the reference (through OpenBLAS ddot) fuses is an explicit __fma_rn.
 // Citations: PKG = gym_guidance_collision_avoidance_single/envs of the reference tree.
 #pragma once
+#include <math_constants.h>
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -49,6 +50,7 @@ struct DevState {
   uint32_t* ev_conf;      // [T][Wd][32] bit i: intruder i is inside the separation radius after its advance
   uint32_t* ev_gone;      // [T][Wd][32] bit i: intruder i left the map
   int* ev_nmac;           // [T*32] lowest intruder index inside the NMAC radius (INT_MAX: none)
+  uint32_t* ev_near;      // [T*32] shaped_nearest, FAST: bits of the smallest squared ownship-intruder distance of the step
   int* reset_list;        // [T*32] envs that finished in this step (PHILOX auto-reset), in arrival order
   int* reset_count;       // [1]
   uint32_t* respawn_list; // [respawn_cap] (env << 8 | intruder) of the intruders that left the map in this step (PHILOX)
@@ -536,82 +538,135 @@ __device__ __forceinline__ void write_obs_own(const StepArgs& a, size_t env, flo
 // Config.n nearest intruders, nearest first (ties: lowest index), each (x, y, vx, vy, dist / Config.diagonal), and the
 // normalised achieved / desired goals.  Distances in the dtype the reference computes them in (f32 positions: f32
 // norm; a retried spawn's f64 position: f64 norm), compared by value like np.argpartition / argsort of the mixed array.
-template <bool FAITH>
-__device__ __forceinline__ void write_obs_nearest(const StepArgs& a, size_t env) {
+// Four lanes per env: sub-lane q scans every 4th position unit into a private sorted list of the KN best, the four
+// lists are merged by shuffles (every sub-lane ends with the same full list) and each sub-lane writes the entries of
+// one winner - 4x the threads of a lane-per-env pass and 4x shorter chains.  The list is a branch-free insertion
+// network on keys ordered by (distance, index): FAST packs the f32 distance bits (non-negative floats order like
+// unsigned integers) and the index into one 64-bit word; FAITHFUL compares f32 / f64 distances by value as doubles.
+// A list of the KN >= nearest_n best has the nearest_n best as its prefix.  Must be called by all 32 lanes of a warp;
+// `valid` masks the envs past the end of the batch.
+struct NearKeyF64 {
+  double d;
+  int i;
+};
+__device__ __forceinline__ bool near_less(const NearKeyF64& x, const NearKeyF64& y) {
+  return x.d < y.d || (x.d == y.d && x.i < y.i);
+}
+__device__ __forceinline__ bool near_less(unsigned long long x, unsigned long long y) { return x < y; }
+__device__ __forceinline__ NearKeyF64 near_shfl(const NearKeyF64& v, int src) {
+  NearKeyF64 r;
+  r.d = __shfl_sync(FULL, v.d, src);
+  r.i = __shfl_sync(FULL, v.i, src);
+  return r;
+}
+__device__ __forceinline__ unsigned long long near_shfl(unsigned long long v, int src) { return __shfl_sync(FULL, v, src); }
+
+template <bool FAITH, int KN>
+__device__ __forceinline__ void write_obs_nearest(const StepArgs& a, size_t env, const int q, const bool valid) {
   using R = real_t<FAITH>;
+  using Key = typename std::conditional<FAITH, NearKeyF64, unsigned long long>::type;
   const DevState& s = a.s;
   const gca_config& c = a.cfg;
   const Derived& k = a.k;
-  constexpr int KMAX = 8;
   const int kn = c.nearest_n;
   const int plane = s.counters[env].z & 1;
   const float2 own = s.own_pos[env];
-  double dd[KMAX];
-  int idx[KMAX];
+  Key slot[KN];
 #pragma unroll
-  for (int j = 0; j < KMAX; ++j) { dd[j] = 0.0; idx[j] = -1; }
-  int m = 0;
-  for (int i = 0; i < s.N; ++i) {
-    Intr<FAITH> it;
-    load_intruder<FAITH>(s, plane, env, i, it);
-    bool wide = false;
-    if constexpr (FAITH) wide = it.is64;
-    double cd = wide ? dist_f64((double)own.x, (double)own.y, (double)it.px, (double)it.py)
-                     : (double)__fsqrt_rn(dist2_f32(own.x, own.y, (float)it.px, (float)it.py));
-    int ci = i;
-    bool moving = false;                                  // once placed, the displaced entries just shift down
-#pragma unroll
-    for (int j = 0; j < KMAX; ++j) {
-      if (j < kn) {
-        const bool take = moving || j >= m || cd < dd[j]; // strict: an equal distance stays behind the earlier index
-        if (take) {
-          const double td = dd[j]; dd[j] = cd; cd = td;
-          const int ti = idx[j]; idx[j] = ci; ci = ti;
-          moving = true;
-        }
-      }
-    }
-    if (m < kn) ++m;
+  for (int j = 0; j < KN; ++j) {
+    if constexpr (FAITH) { slot[j].d = CUDART_INF; slot[j].i = INT_MAX; }
+    else slot[j] = ~0ull;
   }
+  auto consider = [&](Key key) {                          // sorted insertion: KN compare-exchanges, no branches
+#pragma unroll
+    for (int j = 0; j < KN; ++j) {
+      const bool lt = near_less(key, slot[j]);
+      const Key lo = lt ? key : slot[j], hi = lt ? slot[j] : key;
+      slot[j] = lo;
+      key = hi;
+    }
+  };
+  // ---- scan: positions only (velocities are fetched for the winners)
+  const uint8_t* pbase = s.ipos + (size_t)plane * s.pos_plane;
+  if constexpr (FAITH) {
+    for (int i = q; i < s.N; i += 4) {
+      const double2 p = *reinterpret_cast<const double2*>(pbase + ipos_offset(s, true, env, i));
+      const bool wide = (s.dflag[flag_index(s, env, i >> 5)] >> (i & 31)) & 1u;
+      NearKeyF64 key;
+      key.d = wide ? dist_f64((double)own.x, (double)own.y, p.x, p.y)
+                   : (double)__fsqrt_rn(dist2_f32(own.x, own.y, (float)p.x, (float)p.y));
+      key.i = i;
+      consider(key);
+    }
+  } else {
+    for (int i = 2 * q; i < s.N; i += 8) {                // a 16-byte unit holds intruders i and i + 1
+      const float4 p = *reinterpret_cast<const float4*>(pbase + ipos_offset(s, false, env, i));
+      const float d0 = __fsqrt_rn(dist2_f32(own.x, own.y, p.x, p.y)), d1 = __fsqrt_rn(dist2_f32(own.x, own.y, p.z, p.w));
+      consider(((unsigned long long)__float_as_uint(d0) << 32) | (unsigned)i);
+      if (i + 1 < s.N) consider(((unsigned long long)__float_as_uint(d1) << 32) | (unsigned)(i + 1));
+    }
+  }
+  // ---- merge: every sub-lane inserts the ORIGINAL lists of the other three
+  const int lane = threadIdx.x & 31, base = lane & ~3;
+  Key orig[KN];
+#pragma unroll
+  for (int j = 0; j < KN; ++j) orig[j] = slot[j];
+#pragma unroll
+  for (int r = 1; r < 4; ++r) {
+    const int src = base + ((q + r) & 3);
+#pragma unroll
+    for (int j = 0; j < KN; ++j) consider(near_shfl(orig[j], src));
+  }
+  // ---- output: sub-lane q writes winners q and q + 4; sub-lane 0 also the ownship entries, sub-lane 1 the goals
   R* row = reinterpret_cast<R*>(a.obs) + env * (size_t)a.D;
   const float nx = div_prepared(k, own.x, k.ob_w, k.inv_ob_w), ny = div_prepared(k, own.y, k.ob_h, k.inv_ob_h);
-  const double2 vel = s.own_vel[env];
-  row[0] = (R)nx;
-  row[1] = (R)ny;
-  if (s.own_vel_f32[env]) {
-    row[2] = (R)norm_vel_f32(k, (float)vel.x);
-    row[3] = (R)norm_vel_f32(k, (float)vel.y);
-  } else {
-    row[2] = (R)norm_vel_f64(c, k, vel.x);
-    row[3] = (R)norm_vel_f64(c, k, vel.y);
-  }
 #pragma unroll
-  for (int j = 0; j < KMAX; ++j) {
-    if (j < m) {
-      Intr<FAITH> it;
-      load_intruder<FAITH>(s, plane, env, idx[j], it);
-      bool wide = false;
-      if constexpr (FAITH) wide = it.is64;
-      R* o = row + 4 + 5 * j;
-      if (wide) {
-        o[0] = (R)ddiv_prepared(k, (double)it.px, k.dv_w, k.rc_w);
-        o[1] = (R)ddiv_prepared(k, (double)it.py, k.dv_h, k.rc_h);
-        o[4] = (R)__ddiv_rn(dd[j], c.ob_diagonal);
-      } else {
-        o[0] = (R)div_prepared(k, (float)it.px, k.ob_w, k.inv_ob_w);
-        o[1] = (R)div_prepared(k, (float)it.py, k.ob_h, k.inv_ob_h);
-        o[4] = (R)__fdiv_rn((float)dd[j], (float)c.ob_diagonal);
+  for (int j = 0; j < KN; ++j) {
+    if (valid && j < kn && (j & 3) == q) {
+      int wi;
+      double wd;
+      if constexpr (FAITH) { wi = slot[j].i; wd = slot[j].d; }
+      else { wi = (int)(unsigned)slot[j]; wd = (double)__uint_as_float((unsigned)(slot[j] >> 32)); }
+      if (wi >= 0 && wi < s.N) {
+        Intr<FAITH> it;
+        load_intruder<FAITH>(s, plane, env, wi, it);
+        bool wide = false;
+        if constexpr (FAITH) wide = it.is64;
+        R* o = row + 4 + 5 * j;
+        if (wide) {
+          o[0] = (R)ddiv_prepared(k, (double)it.px, k.dv_w, k.rc_w);
+          o[1] = (R)ddiv_prepared(k, (double)it.py, k.dv_h, k.rc_h);
+          o[4] = (R)__ddiv_rn(wd, c.ob_diagonal);
+        } else {
+          o[0] = (R)div_prepared(k, (float)it.px, k.ob_w, k.inv_ob_w);
+          o[1] = (R)div_prepared(k, (float)it.py, k.ob_h, k.inv_ob_h);
+          o[4] = (R)__fdiv_rn((float)wd, (float)c.ob_diagonal);
+        }
+        o[2] = (R)norm_vel_f32(k, it.vx);
+        o[3] = (R)norm_vel_f32(k, it.vy);
       }
-      o[2] = (R)norm_vel_f32(k, it.vx);
-      o[3] = (R)norm_vel_f32(k, it.vy);
     }
   }
-  const double2 goal = s.goal[env];
-  R* ag = reinterpret_cast<R*>(a.achieved) + 2 * env;
-  R* dg = reinterpret_cast<R*>(a.desired) + 2 * env;
-  ag[0] = (R)nx; ag[1] = (R)ny;
-  dg[0] = (R)ddiv_prepared(k, goal.x, k.dv_w, k.rc_w);
-  dg[1] = (R)ddiv_prepared(k, goal.y, k.dv_h, k.rc_h);
+  if (valid && q == 0) {
+    const double2 vel = s.own_vel[env];
+    row[0] = (R)nx;
+    row[1] = (R)ny;
+    if (s.own_vel_f32[env]) {
+      row[2] = (R)norm_vel_f32(k, (float)vel.x);
+      row[3] = (R)norm_vel_f32(k, (float)vel.y);
+    } else {
+      row[2] = (R)norm_vel_f64(c, k, vel.x);
+      row[3] = (R)norm_vel_f64(c, k, vel.y);
+    }
+  }
+  if (valid && q == 1) {
+    const double2 goal = s.goal[env];
+    R* ag = reinterpret_cast<R*>(a.achieved) + 2 * env;
+    R* dg = reinterpret_cast<R*>(a.desired) + 2 * env;
+    ag[0] = (R)nx; ag[1] = (R)ny;
+    dg[0] = (R)ddiv_prepared(k, goal.x, k.dv_w, k.rc_w);
+    dg[1] = (R)ddiv_prepared(k, goal.y, k.dv_h, k.rc_h);
+  }
 }
 
 }  // namespace gca

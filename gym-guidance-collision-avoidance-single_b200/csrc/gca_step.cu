@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(128) step_own_kernel(const StepArgs a) {
     s.ev_gone[fi] = 0u;
   }
   s.ev_nmac[me] = INT_MAX;
+  if (c.shaped_nearest) s.ev_near[me] = 0x7f800000u;              // +inf
   if (me == 0) {
     *s.reset_count = 0;
     *s.respawn_count = 0;
@@ -327,15 +328,27 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
   double dnear = 9999.0;
   bool near64 = true, near_set = false;
   if (c.shaped_nearest && replay) {
-    const int last = stop < s.N - 1 ? stop : s.N - 1;
-    for (int i = 0; i <= last; ++i) {
-      Intr<FAITH> it;
-      load_intruder<FAITH>(s, nxt, me, i, it);
-      bool wide = false;
-      if constexpr (FAITH) wide = it.is64;
-      const double dd = wide ? dist_f64((double)pos.x, (double)pos.y, (double)it.px, (double)it.py)
-                             : (double)__fsqrt_rn(dist2_f32(pos.x, pos.y, (float)it.px, (float)it.py));
-      if (!(dnear < dd)) { dnear = dd; near64 = wide; near_set = true; }
+    const uint8_t* pbase = s.ipos + (size_t)nxt * s.pos_plane;
+    if constexpr (!FAITH) {
+      // FAST: one dtype.  Without an NMAC every intruder was visited: sqrt of the smallest squared distance the
+      // streaming pass recorded (sqrt is monotone).  After an NMAC at `stop` the visited prefix has no other distance
+      // below NMAC_dist (it would have ended the loop earlier), so the minimum is the distance of `stop` itself.
+      if (stop == INT_MAX) {
+        dnear = (double)__fsqrt_rn(__uint_as_float(__ldcg(&s.ev_near[me])));
+      } else {
+        const float2 p = *reinterpret_cast<const float2*>(pbase + ipos_offset(s, false, me, stop));
+        dnear = (double)__fsqrt_rn(dist2_f32(pos.x, pos.y, p.x, p.y));
+      }
+      near64 = false; near_set = true;
+    } else {
+      const int last = stop < s.N - 1 ? stop : s.N - 1;
+      for (int i = 0; i <= last; ++i) {
+        const double2 p = *reinterpret_cast<const double2*>(pbase + ipos_offset(s, true, me, i));
+        const bool wide = (s.dflag[flag_index(s, me, i >> 5)] >> (i & 31)) & 1u;
+        const double dd = wide ? dist_f64((double)pos.x, (double)pos.y, p.x, p.y)
+                               : (double)__fsqrt_rn(dist2_f32(pos.x, pos.y, (float)p.x, (float)p.y));
+        if (!(dnear < dd)) { dnear = dd; near64 = wide; near_set = true; }
+      }
     }
   }
   if (replay) {
@@ -674,6 +687,7 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
   uint8_t* pdst = s.ipos + (size_t)(par ^ 1) * s.pos_plane + pos_off;
   R* obase = obs_intruder_base<FAITH>(a, me);
   uint32_t gone = 0, conf = 0, nmac = 0;                  // bit j: intruder i0 + j
+  float near2 = __uint_as_float(0x7f800000u);             // FAST + shaped_nearest: smallest squared distance of this item
 
   bool fast_done = false;
   if constexpr (!FAITH) {
@@ -696,6 +710,7 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
         const float d0 = dist2_f32(ox, oy, np[g].x, np[g].y), d1 = dist2_f32(ox, oy, np[g].z, np[g].w);   // :151
         conf |= ((d0 < k.sep2_f ? 1u : 0u) | (d1 < k.sep2_f ? 2u : 0u)) << (2 * g);
         nmac |= ((d0 < k.nmac2_f ? 1u : 0u) | (d1 < k.nmac2_f ? 2u : 0u)) << (2 * g);
+        near2 = fminf(near2, fminf(d0, d1));
       }
       if (!runs) {                                          // nobody moves: carry the positions over
         gone = conf = nmac = 0;
@@ -771,6 +786,7 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
         gone |= (oob ? 1u : 0u) << j;
         conf |= (lt_sep ? 1u : 0u) << j;
         nmac |= (lt_nmac ? 1u : 0u) << j;
+        if constexpr (!FAITH) near2 = fminf(near2, dist2_f32(ox, oy, it.px, it.py));
       }
       if constexpr (FAITH) *reinterpret_cast<double2*>(pdst + j * 512) = make_double2(it.px, it.py);
       else *reinterpret_cast<float2*>(pdst + (j >> 1) * 512 + (j & 1) * 8) = make_float2(it.px, it.py);
@@ -784,6 +800,9 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
     if (conf) atomicOr(&s.ev_conf[fi], conf << (i0 & 31));
     nmac &= conf;                                           // `if dist < NMAC_dist` sits inside `if dist < minimum_separation`
     if (nmac) atomicMin(&s.ev_nmac[me], i0 + __ffs(nmac) - 1);
+    if constexpr (!FAITH) {                                 // non-negative floats order like their bit patterns
+      if (a.cfg.shaped_nearest && runs) atomicMin(&s.ev_near[me], __float_as_uint(near2));
+    }
   }
   GCA_KSTAMP_OUT(1);
 }
@@ -863,9 +882,12 @@ __global__ void __launch_bounds__(128) observe_kernel(const StepArgs a) {
 template <bool FAITH>
 __global__ void __launch_bounds__(128) nearest_obs_kernel(const __grid_constant__ StepArgs a) {
   pdl_wait();
-  const size_t me = (size_t)blockIdx.x * 128 + threadIdx.x;
-  if (me >= (size_t)a.s.B) return;
-  write_obs_nearest<FAITH>(a, me);
+  const size_t t = (size_t)blockIdx.x * 128 + threadIdx.x;       // 4 lanes per env, 32 envs per block
+  const size_t me = t >> 2;
+  const bool valid = me < (size_t)a.s.B;
+  if (__ballot_sync(FULL, valid) == 0u) return;
+  if (a.cfg.nearest_n <= 4) write_obs_nearest<FAITH, 4>(a, valid ? me : (size_t)a.s.B - 1, (int)(t & 3), valid);
+  else write_obs_nearest<FAITH, 8>(a, valid ? me : (size_t)a.s.B - 1, (int)(t & 3), valid);
 }
 
 // ------------------------------------------------------------------------------ launchers
@@ -917,7 +939,7 @@ static cudaError_t launch_step_t(const StepArgs& a, cudaStream_t st, cudaEvent_t
     }
   }
   if (a.cfg.obs_kind == GCA_OBS_NEAREST)
-    launch_pdl(nearest_obs_kernel<FAITH>, (unsigned)(((size_t)s.B + 127) / 128), 128, st, a);
+    launch_pdl(nearest_obs_kernel<FAITH>, (unsigned)(((size_t)s.B + 31) / 32), 128, st, a);
   mark(4);
   return cudaGetLastError();
 }
@@ -948,8 +970,9 @@ cudaError_t launch_reset(bool faith, bool tape, const StepArgs& a, cudaStream_t 
 cudaError_t launch_observe(bool faith, const StepArgs& a, cudaStream_t st) {
   const unsigned blocks = (unsigned)(((size_t)a.s.B + 127) / 128);
   if (a.cfg.obs_kind == GCA_OBS_NEAREST) {
-    if (faith) nearest_obs_kernel<true><<<blocks, 128, 0, st>>>(a);
-    else nearest_obs_kernel<false><<<blocks, 128, 0, st>>>(a);
+    const unsigned nb = (unsigned)(((size_t)a.s.B + 31) / 32);
+    if (faith) nearest_obs_kernel<true><<<nb, 128, 0, st>>>(a);
+    else nearest_obs_kernel<false><<<nb, 128, 0, st>>>(a);
   } else if (faith) observe_kernel<true><<<blocks, 128, 0, st>>>(a);
   else observe_kernel<false><<<blocks, 128, 0, st>>>(a);
   return cudaGetLastError();
