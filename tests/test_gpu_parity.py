@@ -335,3 +335,48 @@ def test_kernels_per_step_and_profile():
     et = make_gpu("env", 3, g["tape"].shape[0], "faithful", "tape")
     assert et.kernels_per_step == 3                       # tape replay respawns in place: no spawn kernel
     et.close()
+
+
+@pytest.mark.parametrize("case", range(8))
+def test_random_configurations_bit_exact_vs_oracle(case):
+    """Non-default parameters (window, radii, speeds, noise, intruder count, batch size drawn at random per case; the
+    constant-division fast paths do not all qualify then): kernels and oracle must still agree on every bit."""
+    from gca_b200 import variants
+    from gca_b200.batched import BatchedAircraftEnv
+    from oracle import oracle as orc
+    rng = np.random.RandomState(1000 + case)
+    vk = ["env", "env2", "her", "dher", "mcts", "d9her", "d3her", "env2"][case]
+    base = config_class(vk)
+    W, H = [(800, 800), (640, 480), (1024, 768), (500, 900)][rng.randint(4)]
+    over = dict(window_width=W, window_height=H, diagonal=float(rng.choice([800, 1000, 1131.37])),
+                minimum_separation=float(rng.uniform(10, 30)), NMAC_dist=float(rng.uniform(2, 8)),
+                initial_min_dist=float(rng.uniform(40, 120)), goal_radius=float(rng.uniform(10, 40)),
+                min_speed=float(rng.uniform(1.0, 2.0)), max_speed=float(rng.uniform(2.2, 3.5)),
+                d_speed=float(rng.uniform(0.05, 0.3)), speed_sigma=float(rng.uniform(0.0, 0.1)),
+                d_heading=float(rng.uniform(0.02, 0.2)), heading_sigma=float(rng.uniform(0.0, 0.1)))
+    cfg_cls = type("Cfg%d" % case, (base,), over)
+    n = int(rng.randint(6, 100))
+    B = int(rng.randint(100, 700))
+    mode = "fast" if case % 2 == 0 else "faithful"
+    fast = mode == "fast"
+    cfg = variants.make_config(GOLDEN_VARIANTS[vk], cfg_cls)
+    env = BatchedAircraftEnv(GOLDEN_VARIANTS[vk], B, cfg_cls, n_intruders=n, mode=mode, draws="philox", seed=77 + case)
+    ref = orc.OracleEnv(cfg, B, n, draws=1, trig=orc.TRIG_SHARED, seed=77 + case, f32_positions=fast, auto_reset=True)
+    cast = (lambda x: x.astype(np.float32)) if fast else (lambda x: x)
+    assert np.array_equal(env.reset().cpu().numpy(), cast(ref.reset()))
+    for t in range(40):
+        if env.continuous:
+            a = rng.uniform(-1, 1, (B, 2))
+            if fast:
+                a = a.astype(np.float32).astype(np.float64)
+        else:
+            a = np.stack([rng.randint(0, 3 if vk in ("dher", "d3her") else 9, B), np.zeros(B)], -1).astype(np.float64)
+        obs, rew, done, info = env.step(gpu_actions(env, a))
+        ref.step(a)
+        assert np.array_equal(info.cpu().numpy(), ref.info), (vk, t)
+        assert np.array_equal(done.cpu().numpy(), ref.done), (vk, t)
+        assert np.array_equal(rew.cpu().numpy(), cast(ref.reward)), (vk, t)
+        assert np.array_equal(obs.cpu().numpy(), cast(ref.obs)), (vk, t)
+    assert_state_equal(env.get_state(), ref.state, "final state", skip=())
+    env.close()
+    print(vk, mode, "W,H", W, H, "N", n, "B", B)
