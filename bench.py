@@ -344,6 +344,7 @@ def main_gpu(args):
             line["stack"] = bench_stack(local)
             line["d9her"] = bench_d9her(local)
             line["her_replay"] = bench_her_replay(local)
+            line["n0"] = bench_n0(local)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -560,6 +561,28 @@ def bench_her_replay(device):
             "episodes": E, "T": T, "dim_o": dim_o, "ms_per_launch": ms, "bytes_per_transition": bytes_per,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                          "peak_source": src, "note": "includes the torch.empty of the output tensors per call"}}
+
+
+def bench_n0(device):
+    """SURVEY 8(d) input #1 at the package default `Config.intruder_size = 0` (PKG/config.py:9): SingleAircraftEnv,
+    discrete actions, no intruders - 2 kernels per step, 155 algorithmic bytes per env-step.  65,536 envs are 10 MB of
+    state (L2 resident); 4 Mi envs make it HBM bound."""
+    import torch
+    from gca_b200.batched import BatchedAircraftEnv
+    from gym_guidance_collision_avoidance_single.envs.config import Config
+    peak, src = measured_peaks()
+    out = {"metric": METRIC, "unit": UNIT, "intruders": 0, "bytes_per_env_step": algorithmic_bytes_per_env_step(0, continuous=False)}
+    for B in (ENVS_PER_GPU, 4 * 1024 * 1024):
+        env = BatchedAircraftEnv("SingleAircraftEnv", B, Config, n_intruders=0, mode="fast", draws="philox", device=device, seed=8)
+        env.reset()
+        acts = [torch.randint(0, 9, (B,), device="cuda", dtype=torch.int32) for _ in range(GRAPH_STEPS)]
+        ms = graph_step_ms(lambda i: env.step(acts[i]), GRAPH_STEPS)
+        k = env.kernels_per_step
+        env.close()
+        gbs = B * out["bytes_per_env_step"] / (ms * 1e-3) / 1e9
+        out["envs_%d" % B] = {"value": B / (ms * 1e-3), "ms_per_step": ms, "kernels_per_step": k, "hbm_gbs": gbs,
+                              "hbm_frac": gbs / peak, "note": "L2 resident" if B == ENVS_PER_GPU else "HBM bound"}
+    return out
 
 
 def bench_stack(device):
