@@ -549,6 +549,14 @@ int gca_monitor_update(const void* reward, int is_f64, const uint8_t* done, int6
   return GCA_OK;
 }
 
+int gca_stats_update(const uint8_t* done, const uint8_t* info, int64_t n_envs, unsigned long long* stats, int device,
+                     void* stream) {
+  if (n_envs < 0 || (n_envs > 0 && (!done || !info || !stats))) return fail(GCA_ERR_INVALID, "bad arguments");
+  GCA_CUDA(cudaSetDevice(device));
+  GCA_CUDA(launch_stats_update(done, info, (long long)n_envs, stats, (cudaStream_t)stream));
+  return GCA_OK;
+}
+
 int gca_her_sample(const gca_her_episodes* ep, int64_t n_episodes, int T, int dim_o, int dim_u, int dim_g, int is_f64,
                    int64_t batch, double future_p, double goal_radius, int reward_kind, const gca_her_draws* draws,
                    uint64_t seed, uint32_t call, const gca_her_transitions* out, int device, void* stream) {

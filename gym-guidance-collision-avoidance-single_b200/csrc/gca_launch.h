@@ -24,6 +24,8 @@ cudaError_t launch_mcts_search(const gca_mcts_config* cfg, int n, const double* 
 cudaError_t launch_monitor_update(const void* reward, int is_f64, const uint8_t* done, long long n, float* ep_return,
                                   int32_t* ep_length, gca_episode_record* ring, long long cap, unsigned long long* count,
                                   uint32_t step, cudaStream_t st);
+cudaError_t launch_stats_update(const uint8_t* done, const uint8_t* info, long long n, unsigned long long* stats,
+                                cudaStream_t st);
 cudaError_t launch_her_sample(const gca_her_episodes* ep, long long E, int T, int dim_o, int dim_u, int dim_g, int is_f64,
                               long long batch, double future_p, double radius, int kind, const gca_her_draws* dr,
                               uint64_t seed, uint32_t call, const gca_her_transitions* out, cudaStream_t st);

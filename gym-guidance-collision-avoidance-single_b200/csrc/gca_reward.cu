@@ -86,4 +86,29 @@ cudaError_t launch_monitor_update(const void* reward, int is_f64, const uint8_t*
   return cudaGetLastError();
 }
 
+// step / episode / outcome counters of one step, thread = env, one atomic per warp and non-zero counter
+__global__ void __launch_bounds__(256) stats_kernel(const uint8_t* __restrict__ done, const uint8_t* __restrict__ info,
+                                                    long long n, unsigned long long* __restrict__ stats) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < n;
+  const int code = valid ? info[i] : -1;
+  const bool fin = valid && done[i] != 0;
+  const int lane = threadIdx.x & 31;
+  const unsigned counts[7] = {
+      (unsigned)__popc(__ballot_sync(0xffffffffu, valid)), (unsigned)__popc(__ballot_sync(0xffffffffu, fin)),
+      (unsigned)__popc(__ballot_sync(0xffffffffu, code == GCA_INFO_NMAC)),
+      (unsigned)__popc(__ballot_sync(0xffffffffu, code == GCA_INFO_CONFLICT)),
+      (unsigned)__popc(__ballot_sync(0xffffffffu, code == GCA_INFO_GOAL)),
+      (unsigned)__popc(__ballot_sync(0xffffffffu, code == GCA_INFO_WALL)),
+      (unsigned)__popc(__ballot_sync(0xffffffffu, code == GCA_INFO_MAXSTEPS))};
+  if (lane < 7 && counts[lane]) atomicAdd(&stats[lane], (unsigned long long)counts[lane]);
+}
+
+cudaError_t launch_stats_update(const uint8_t* done, const uint8_t* info, long long n, unsigned long long* stats,
+                                cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(done, info, n, stats);
+  return cudaGetLastError();
+}
+
 }  // namespace gca

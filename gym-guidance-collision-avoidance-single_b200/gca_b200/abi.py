@@ -70,6 +70,7 @@ class GcaMctsConfig(C.Structure):
 
 
 MCTS_WALL, MCTS_CONFLICT, MCTS_GOAL = 1, 2, 4
+STAT_NAMES = ("steps", "episodes", "nmac", "conflict_steps", "goal", "wall", "maxsteps")
 
 
 def make_mcts_config(cfg_cls):
@@ -129,6 +130,7 @@ def load():
         "gca_compute_reward": ([vp, vp, i64, C.c_double, i32, i32, vp, i32, vp], C.c_int),
         "gca_raster": ([vp, vp, vp, i64, i64, i32, i32, vp, vp], C.c_int),
         "gca_monitor_update": ([vp, i32, vp, i64, vp, vp, vp, i64, vp, u32, i32, vp], C.c_int),
+        "gca_stats_update": ([vp, vp, i64, vp, i32, vp], C.c_int),
         "gca_her_sample": ([P(GcaHerEpisodes), i64, i32, i32, i32, i32, i32, i64, C.c_double, C.c_double, i32,
                             P(GcaHerDraws), u64, u32, P(GcaHerTransitions), i32, vp], C.c_int),
         "gca_mcts_move": ([P(GcaMctsConfig), i32, vp, vp, vp, i64, P(GcaTape), u64, u32, i32, i32, vp], C.c_int),

@@ -53,6 +53,16 @@ class ResultsWriter(object):
             self.f = None
 
 
+def reduce_stats(counters, reduce=True):
+    """Sum a rank's counter tensor over the process group (if one is initialised) and name the entries."""
+    import torch
+    t = counters.clone()
+    if reduce and torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+    v = t.cpu().tolist()
+    return dict(zip(abi.STAT_NAMES, v[: len(abi.STAT_NAMES)]))
+
+
 class AircraftVecMonitor(object):
     """VecMonitor(venv, filename) for an AircraftVecEnv that keeps its outputs on the device."""
 
@@ -69,6 +79,7 @@ class AircraftVecMonitor(object):
         self.cap = int(ring_capacity)
         self._ring = torch.zeros((self.cap, 4), dtype=torch.int32, device=dev)          # gca_episode_record x cap
         self._count = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._stats = torch.zeros(8, dtype=torch.int64, device=dev)                     # gca_stats_update counters
         self._drained = 0
         self._step = 0
         self._times = {}
@@ -92,6 +103,8 @@ class AircraftVecMonitor(object):
                                            self._ring.data_ptr(), self.cap, self._count.data_ptr(),
                                            self._step & 0xffffffff, b.device.index or 0,
                                            C.c_void_p(torch.cuda.current_stream(b.device).cuda_stream)))
+        abi.check(b.lib.gca_stats_update(dones.data_ptr(), infos.data_ptr(), self.num_envs, self._stats.data_ptr(),
+                                         b.device.index or 0, C.c_void_p(torch.cuda.current_stream(b.device).cuda_stream)))
         self._times[self._step & 0xffffffff] = round(time.time() - self.tstart, 6)
         self._step += 1
         return obs, rews, dones, infos
@@ -123,6 +136,12 @@ class AircraftVecMonitor(object):
             out.append(dict(epinfo, env=int(r["env"])))
         self._times = {}                                      # every step so far has been drained
         return out
+
+    def stats(self, reduce=True):
+        """Counters since construction {steps, episodes, nmac, conflict_steps, goal, wall, maxsteps}; with `reduce` and an
+        initialised torch.distributed group they are summed over all ranks (the one collective of the path: a 64-byte
+        all-reduce per call, NCCL over NVLink when the group's backend is nccl)."""
+        return reduce_stats(self._stats, reduce)
 
     def close(self):
         self.drain()

@@ -261,6 +261,14 @@ int gca_monitor_update(const void* reward, int is_f64, const uint8_t* done, int6
                        int32_t* ep_length, gca_episode_record* ring, int64_t ring_capacity,
                        unsigned long long* ring_count, uint32_t step, int device, void* stream);
 
+/* Batch-wide counters for the optional statistics reduce across GPUs (the figures Algorithms/MCTS/Agent.py:55-62
+ * prints): stats[GCA_STAT_*] += ... over the n_envs envs of one step.  info: the GCA_INFO_* codes gca_step wrote.
+ * stats: device uint64 [GCA_STAT_COUNT], accumulated with one atomic per warp and counter. */
+enum { GCA_STAT_STEPS = 0, GCA_STAT_EPISODES = 1, GCA_STAT_NMAC = 2, GCA_STAT_CONFLICT_STEPS = 3, GCA_STAT_GOAL = 4,
+       GCA_STAT_WALL = 5, GCA_STAT_MAXSTEPS = 6, GCA_STAT_COUNT = 8 };
+int gca_stats_update(const uint8_t* done, const uint8_t* info, int64_t n_envs, unsigned long long* stats, int device,
+                     void* stream);
+
 /* ---- HER replay: the "future" relabelling sampler of baselines (Algorithms/baselines-master/baselines/her/
  * her_sampler.py:19-61 _sample_her_transitions, called by replay_buffer.py:sample with o_2 = o[:, 1:], ag_2 = ag[:, 1:])
  * on an episode buffer that lives on the device.  For each of `batch` transitions: episode e and time t are drawn,

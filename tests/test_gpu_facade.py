@@ -184,11 +184,16 @@ def test_vec_monitor_equals_baselines_vec_monitor(tmp_path):
     mon.reset()
     eprets, eplens = np.zeros(B, "f"), np.zeros(B, "i")
     want, got = [], []
+    counts = {"steps": 0, "episodes": 0, "nmac": 0, "conflict_steps": 0, "goal": 0, "wall": 0, "maxsteps": 0}
     rng = np.random.RandomState(0)
     for t in range(400):
         a = torch.as_tensor(rng.uniform(-1, 1, (B, 2)).astype(np.float32), device="cuda")
         obs, rews, dones, infos = mon.step(a)
-        rews, dones = rews.cpu().numpy(), dones.cpu().numpy()
+        rews, dones, codes = rews.cpu().numpy(), dones.cpu().numpy(), infos.cpu().numpy()
+        counts["steps"] += B
+        counts["episodes"] += int(dones.astype(bool).sum())
+        for name, code in (("nmac", 1), ("conflict_steps", 2), ("goal", 3), ("wall", 4), ("maxsteps", 5)):
+            counts[name] += int((codes == code).sum())
         eprets += rews
         eplens += 1
         for i in range(B):
@@ -202,6 +207,7 @@ def test_vec_monitor_equals_baselines_vec_monitor(tmp_path):
     assert len(want) > 50
     assert [(e["env"], e["r"], e["l"]) for e in got] == want
     assert all(e["t"] > 0 for e in got)
+    assert mon.stats() == counts and counts["wall"] > 0 and counts["episodes"] == len(want)
     mon.close()
     lines = open(str(tmp_path / "run.monitor.csv")).read().splitlines()
     assert lines[0].startswith('# {"t_start": ') and lines[1] == "r,l,t" and len(lines) == 2 + len(want)

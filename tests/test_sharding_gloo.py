@@ -47,8 +47,15 @@ def _worker(rank, world, port, per_rank, out_dir):
     ids = torch.tensor([rank * per_rank, (rank + 1) * per_rank - 1])
     gathered = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
     dist.all_gather(gathered, ids)
+    # the one optional collective of the path: the statistics reduce of AircraftVecMonitor.stats()
+    from gca_b200.vec_monitor import reduce_stats
+    codes, dones = env.info, env.done
+    mine = torch.tensor([per_rank, int(dones.sum()), int((codes == 1).sum()), int((codes == 2).sum()),
+                         int((codes == 3).sum()), int((codes == 4).sum()), int((codes == 5).sum()), 0])
+    total = reduce_stats(mine)
     if rank == 0:
         np.save(os.path.join(out_dir, "meta.npy"), np.array([t.item()] + [int(x) for g in gathered for x in g]))
+        np.save(os.path.join(out_dir, "stats.npy"), np.array([total["steps"], total["episodes"], total["conflict_steps"]]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -71,3 +78,5 @@ def test_two_rank_sharding(tmp_path):
         whole.step(acts[t])
     sharded = np.concatenate([np.load(tmp_path / ("obs_%d.npy" % r)) for r in range(world)])
     assert np.array_equal(sharded, whole.obs)                # results do not depend on the number of ranks
+    stats = np.load(tmp_path / "stats.npy")                  # summed over the two ranks = the unsharded batch's last step
+    assert stats.tolist() == [world * per_rank, int(whole.done.sum()), int((whole.info == 2).sum())]
