@@ -345,6 +345,7 @@ def main_gpu(args):
             line["d9her"] = bench_d9her(local)
             line["her_replay"] = bench_her_replay(local)
             line["n0"] = bench_n0(local)
+            line["faithful"] = bench_faithful(local)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -583,6 +584,27 @@ def bench_n0(device):
         out["envs_%d" % B] = {"value": B / (ms * 1e-3), "ms_per_step": ms, "kernels_per_step": k, "hbm_gbs": gbs,
                               "hbm_frac": gbs / peak, "note": "L2 resident" if B == ENVS_PER_GPU else "HBM bound"}
     return out
+
+
+def bench_faithful(device):
+    """The headline workload in FAITHFUL mode: the reference's mixed f32 / f64 arithmetic with f64-capable intruder
+    positions (16 B each, both planes) and f64 observations (2 624 B per env) - what the 1e-9 parity contract is
+    stated on.  Algorithmic bytes per env-step: 16 + 8 + 16 + 32 per intruder + the fixed part of the fast path."""
+    import torch
+    from gca_b200.batched import BatchedAircraftEnv
+    from gym_guidance_collision_avoidance_single.envs.config import Config
+    B, N = ENVS_PER_GPU, N_INTRUDERS
+    env = BatchedAircraftEnv(VARIANT, B, Config, n_intruders=N, mode="faithful", draws="philox", device=device, seed=9)
+    env.reset()
+    acts = [torch.rand((B, 2), device="cuda", dtype=torch.float64) * 2 - 1 for _ in range(GRAPH_STEPS)]
+    ms = graph_step_ms(lambda i: env.step(acts[i]), GRAPH_STEPS)
+    env.close()
+    peak, src = measured_peaks()
+    bytes_per = (16 + 8 + 16 + 32) * N + algorithmic_bytes_per_env_step(0) + 32
+    gbs = B * bytes_per / (ms * 1e-3) / 1e9
+    return {"metric": METRIC, "value": B / (ms * 1e-3), "unit": UNIT, "envs": B, "intruders": N, "ms_per_step": ms,
+            "dtype": "f64 observations, f32/f64 positions", "bytes_per_env_step": bytes_per, "hbm_gbs": gbs,
+            "hbm_frac": gbs / peak}
 
 
 def bench_stack(device):
