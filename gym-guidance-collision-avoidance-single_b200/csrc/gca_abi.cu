@@ -260,9 +260,9 @@ int gca_create(const gca_config* cfg, int n_envs, int n_intruders, int mode, int
   if (!rc) rc = dev_alloc(e, &s.ev_near, (size_t)s.T * 32);
   if (!rc) rc = dev_alloc(e, &s.reset_list, (size_t)s.T * 32);
   if (!rc) rc = dev_alloc(e, &s.reset_count, 1);
-  s.respawn_cap = (int)std::min<size_t>((size_t)s.T * 32 * 4, (size_t)1 << 30);
+  s.respawn_cap = (int)std::min<size_t>((size_t)s.T * 128, (size_t)1 << 30);   // kTileRespawnCap records per tile
   if (!rc) rc = dev_alloc(e, &s.respawn_list, (size_t)s.respawn_cap);
-  if (!rc) rc = dev_alloc(e, &s.respawn_count, 1);
+  if (!rc) rc = dev_alloc(e, &s.respawn_count, (size_t)s.T);
   if (!rc) rc = dev_alloc(e, &s.ivel, vel_plane_bytes(s));
   if (!rc) rc = dev_alloc(e, &s.cflag, flag_plane_words(s));
   if (!rc) rc = dev_alloc(e, &s.dflag, mode == GCA_MODE_FAITHFUL ? flag_plane_words(s) : 1);

@@ -54,7 +54,7 @@ struct DevState {
   int* reset_list;        // [T*32] envs that finished in this step (PHILOX auto-reset), in arrival order
   int* reset_count;       // [1]
   uint32_t* respawn_list; // [respawn_cap] (env << 8 | intruder) of the intruders that left the map in this step (PHILOX)
-  int* respawn_count;     // [1]
+  int* respawn_count;     // [T] records of each tile's segment of respawn_list
   int respawn_cap;
   size_t pos_plane;       // bytes of one position plane
   int B, N, T, U, W, Wd;

@@ -73,6 +73,7 @@ extern "C" int gca_debug_kstamps(unsigned long long* host, int reset) {
 #endif
 constexpr int kChunkUnits = GCA_CHUNK_UNITS;      // 16-byte units (intruder pairs) per lane and work item
 constexpr int kChunkIntr = 2 * kChunkUnits;       // 8 intruders
+constexpr int kTileRespawnCap = 128;              // respawn records per tile (32 envs) and step; beyond that the lane spawns in place
 constexpr int kWarpsB = GCA_WARPS_B;              // work items per block of the streaming pass
 // staging row of one lane: 8 intruders x 16 bytes of observation entries, plus 16 bytes so that the row stride is
 // an odd multiple of 16 (conflict-free 16-byte shared accesses across a quarter warp)
@@ -239,7 +240,6 @@ __global__ void __launch_bounds__(128) step_own_kernel(const StepArgs a) {
   if (c.shaped_nearest) s.ev_near[me] = 0x7f800000u;              // +inf
   if (me == 0) {
     *s.reset_count = 0;
-    *s.respawn_count = 0;
   }
   GCA_KSTAMP_OUT(0);
 }
@@ -402,8 +402,7 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
   }
   // PHILOX: a respawn depends on nothing but (env, tick, intruder) and the ownship position, so the spawns
   // (FP64-heavy, 0-3 per env) are not done here, one lane per env, but queued for spawn_kernel, which runs one
-  // lane per spawn over the whole batch.  The slots are reserved now; the records are written after the reward
-  // section, when the atomic has long returned.
+  // lane per spawn over the whole batch.  The records go to the tile's own segment of the respawn list.
   int job_mine = 0, job_off = 0, job_total = 0, job_base = 0;
   if constexpr (!TAPE) {
     if (compact) {
@@ -416,8 +415,11 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
       }
       job_total = __shfl_sync(FULL, job_off, 31);
       job_off -= job_mine;
-      if (job_total > 0 && lane == 0) job_base = atomicAdd(s.respawn_count, job_total);
+      // every tile owns a fixed segment of the respawn list: no batch-wide counter (2,048 warps adding to one address
+      // cost each of them ~3 us of waiting), the spawn kernel reads the per-tile counts
+      job_base = tile * kTileRespawnCap;
     }
+    if (lane == 0) s.respawn_count[tile] = job_total;     // (0 when the spawns were made in place)
   }
 #ifdef GCA_PHASE_TIMING
   fin_t2 = gtime();
@@ -479,7 +481,6 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
 
   if constexpr (!TAPE) {
     if (compact && job_total > 0) {
-      job_base = __shfl_sync(FULL, job_base, 0);          // (the atomic was issued before the reward section)
       if (job_mine > 0) {
         uint32_t set64_own[kWordsAhead] = {0u, 0u, 0u, 0u};
         int at = job_base + job_off;
@@ -489,7 +490,7 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
           while (rest) {
             const int j = __ffs(rest) - 1;
             rest &= rest - 1;
-            if (at < s.respawn_cap) s.respawn_list[at] = ((uint32_t)me << 8) | (uint32_t)(w * 32 + j);
+            if (at < job_base + kTileRespawnCap) s.respawn_list[at] = ((uint32_t)me << 8) | (uint32_t)(w * 32 + j);
             else if (!(done && a.auto_reset)) respawn_own(w * 32 + j, set64_own[w]);   // (list full: > 4 respawns per env on average)
             ++at;
           }
@@ -574,16 +575,16 @@ __global__ void __launch_bounds__(128) spawn_kernel(const __grid_constant__ Step
   const DevState& s = a.s;
   const int lane = threadIdx.x & 31;
   const int n_warps = gridDim.x * 4, rounds = s.W;
-  const int n_resp = min(*s.respawn_count, s.respawn_cap);
-  const long long resp_warps = (n_resp + 31) / 32, total = resp_warps + (long long)(*s.reset_count) * rounds;
+  // jobs: one per tile (that tile's respawn records, usually one round of lanes), then `rounds` per finished env
+  const long long resp_warps = s.T, total = resp_warps + (long long)(*s.reset_count) * rounds;
   for (long long job = (long long)blockIdx.x * 4 + (threadIdx.x >> 5); job < total; job += n_warps) {
     Draws<false> d;
     d.k0 = a.key0; d.k1 = a.key1;
     if (job < resp_warps) {
       // reset_intruder()   PKG/SingleAircraftEnv.py:153-154, :229-238
-      const int at = (int)job * 32 + lane;
-      if (at < n_resp) {
-        const uint32_t rec = s.respawn_list[at];
+      const int n_resp = min(s.respawn_count[job], kTileRespawnCap);
+      for (int at = lane; at < n_resp; at += 32) {
+        const uint32_t rec = s.respawn_list[job * kTileRespawnCap + at];
         const size_t env = rec >> 8;
         const int i = (int)(rec & 0xffu);
         const int4 cnt = s.counters[env];
@@ -933,8 +934,9 @@ static cudaError_t launch_step_t(const StepArgs& a, cudaStream_t st, cudaEvent_t
   launch_pdl(step_finish_kernel<FAITH, TAPE>, (unsigned)((s.T + 3) / 4), 128, st, a);
   mark(3);
   if constexpr (!TAPE) {
-    if (s.N > 0) {                                        // one warp per tile-equivalent; the warps loop if more is queued
-      const unsigned blocks = (unsigned)((s.T + 3) / 4 < 1184 ? (s.T + 3) / 4 : 1184);
+    if (s.N > 0) {                                        // one warp per tile + half as many again for the reset jobs
+      const long long want = ((long long)s.T + s.T / 2 + 3) / 4;   // (the warps loop if more is queued)
+      const unsigned blocks = (unsigned)(want < 2368 ? want : 2368);
       launch_pdl(spawn_kernel<FAITH>, blocks, 128, st, a);
     }
   }
