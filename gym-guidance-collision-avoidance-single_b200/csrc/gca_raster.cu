@@ -35,7 +35,7 @@ constexpr int kRasterWarps = kRasterThreads / 32;
 constexpr int kMaxSprites = GCA_RASTER_MAX_INTRUDERS + 2;   // 128 -> 4 mask words per cell
 constexpr int kCorner = GCA_SPRITE + 1;                     // bilinear footprints per axis: iu in [-1, 31]
 constexpr int kSat = kCorner + 1;                           // summed-area table side
-constexpr int kListCap = 64;                                // >= 1 carried + 32 new pixels
+constexpr int kListCap = 40;                                // >= 1 carried + 32 new pixels + 1 odd simple pixel
 constexpr int kCellShift = 4;                               // cell = 16 x 16 output pixels
 constexpr float kMagic = 12582912.0f;                       // 1.5 * 2^23: x + kMagic rounds x to an integer (RN-even)
 // half extent of the quad (16) + half diagonal of the 4x4 sample block (1.5 * sqrt 2 = 2.1214) + slack
@@ -76,22 +76,25 @@ __device__ __forceinline__ float quantise_u8(float v) { return __fadd_rn(__fadd_
 //  * class 0 (four texels with alpha 0): the spec's a255 is 0.0f and it returns without blending;
 //  * class 2 (four texels equal, alpha 255): every bilinear value is c(1+e), |e| < 2e-6, alpha is 1+e', |e'| < 2e-6,
 //    so v = c + d with |d| < 2e-3 for c, dst <= 255 and rintf(v) = c: the blend writes the texel colour.
-__device__ __forceinline__ void raster_sample_fast(const float4 pose, const int tex, const float4* __restrict__ texf,
-                                                   const uint8_t* __restrict__ cls, float wx, float wy, float& r,
-                                                   float& g, float& b) {
+// where a sample falls in a sprite's texture: false if outside the quad
+__device__ __forceinline__ bool sample_locate(const float4 pose, float wx, float wy, int& iu, int& iv, float& tu, float& tv,
+                                              float& fu0, float& fv0) {
   const float dx = __fadd_rn(wx, -pose.x), dy = __fadd_rn(wy, -pose.y);
   const float lx = __fadd_rn(__fmul_rn(pose.z, dx), __fmul_rn(pose.w, dy));
   const float ly = __fadd_rn(__fmul_rn(pose.z, dy), -__fmul_rn(pose.w, dx));
-  if (!(lx >= -GCA_SPRITE_HALF && lx < GCA_SPRITE_HALF && ly >= -GCA_SPRITE_HALF && ly < GCA_SPRITE_HALF)) return;
-  const float tu = __fadd_rn(lx, 15.5f), tv = __fadd_rn(ly, 15.5f);
-  float fu0, fv0;
-  const int iu = floor_small(tu, &fu0), iv = floor_small(tv, &fv0);
-  const int c = cls[tex * (kCorner * kCorner) + (iv + 1) * kCorner + (iu + 1)];
-  if (c == 0) return;
+  if (!(lx >= -GCA_SPRITE_HALF && lx < GCA_SPRITE_HALF && ly >= -GCA_SPRITE_HALF && ly < GCA_SPRITE_HALF)) return false;
+  tu = __fadd_rn(lx, 15.5f);
+  tv = __fadd_rn(ly, 15.5f);
+  iu = floor_small(tu, &fu0);
+  iv = floor_small(tv, &fv0);
+  return true;
+}
+
+// the general bilinear fetch + alpha blend of one located sample (t: the sprite's 32x32 float4 texture)
+__device__ __forceinline__ void sample_blend(const float4* __restrict__ t, int iu, int iv, float tu, float tv, float fu0,
+                                             float fv0, float& r, float& g, float& b) {
   const int u0 = max(iu, 0), u1 = min(iu + 1, 31), v0 = max(iv, 0), v1 = min(iv + 1, 31);
-  const float4* t = texf + tex * (GCA_SPRITE * GCA_SPRITE);
   const float4 t00 = t[(31 - v0) * GCA_SPRITE + u0];
-  if (c == 2) { r = t00.x; g = t00.y; b = t00.z; return; }
   const float4 t10 = t[(31 - v0) * GCA_SPRITE + u1];
   const float4 t01 = t[(31 - v1) * GCA_SPRITE + u0];
   const float4 t11 = t[(31 - v1) * GCA_SPRITE + u1];
@@ -108,6 +111,29 @@ __device__ __forceinline__ void raster_sample_fast(const float4 pose, const int 
   g = quantise_u8(__fadd_rn(__fmul_rn(GCA_BIL(y), alpha), __fmul_rn(g, beta)));
   b = quantise_u8(__fadd_rn(__fmul_rn(GCA_BIL(z), alpha), __fmul_rn(b, beta)));
 #undef GCA_BIL
+}
+
+__device__ __forceinline__ void raster_sample_fast(const float4 pose, const int tex, const float4* __restrict__ texf,
+                                                   const uint8_t* __restrict__ cls, float wx, float wy, float& r,
+                                                   float& g, float& b) {
+  int iu, iv;
+  float tu, tv, fu0, fv0;
+  if (!sample_locate(pose, wx, wy, iu, iv, tu, tv, fu0, fv0)) return;
+  const int c = cls[tex * (kCorner * kCorner) + (iv + 1) * kCorner + (iu + 1)];
+  if (c == 0) return;
+  const float4* t = texf + tex * (GCA_SPRITE * GCA_SPRITE);
+  if (c == 2) {
+    const float4 t00 = t[(31 - max(iv, 0)) * GCA_SPRITE + max(iu, 0)];
+    r = t00.x; g = t00.y; b = t00.z;
+    return;
+  }
+  sample_blend(t, iu, iv, tu, tv, fu0, fv0, r, g, b);
+}
+
+// cv2 RGB2GRAY in exact float arithmetic (every intermediate is an integer < 2^24), then >> 15
+__device__ __forceinline__ int gray_of(float r, float g, float b) {
+  const float gx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(9798.0f, r), __fmul_rn(19235.0f, g)), __fmul_rn(3735.0f, b)), 16384.0f);
+  return __float2int_rn(gx) >> 15;
 }
 
 __device__ __forceinline__ int floor_int(float t) {        // floor for |t| < 2^22, no conversion instruction
@@ -146,7 +172,11 @@ __global__ void __launch_bounds__(kRasterThreads, 2) raster_kernel(const RasterA
   float4* pose = reinterpret_cast<float4*>(cell_mask + n_cells);                   // [128] (cx, cy, rc, rs)
   short4* box = reinterpret_cast<short4*>(pose + kMaxSprites);                     // [128] output-pixel bounding boxes
   uint2* list = reinterpret_cast<uint2*>(box + kMaxSprites) + warp * kListCap;     // per warp: (ox | oy << 16, sprite ids)
-  uint16_t* sat_all = reinterpret_cast<uint16_t*>(reinterpret_cast<uint2*>(box + kMaxSprites) + kRasterWarps * kListCap);
+  uint32_t* wsm = reinterpret_cast<uint32_t*>(reinterpret_cast<uint2*>(box + kMaxSprites) + kRasterWarps * kListCap) + warp * 96;
+  uint32_t* slist = wsm;                                                           // per warp: 32 simple pixels (ox | oy << 16)
+  int* acc = reinterpret_cast<int*>(wsm + 32);                                     //           their gray sums
+  uint16_t* queue = reinterpret_cast<uint16_t*>(wsm + 64);                         //           deferred samples (slot << 4 | sample)
+  uint16_t* sat_all = reinterpret_cast<uint16_t*>(reinterpret_cast<uint32_t*>(reinterpret_cast<uint2*>(box + kMaxSprites) + kRasterWarps * kListCap) + kRasterWarps * 96);
   uint8_t* cls = reinterpret_cast<uint8_t*>(sat_all + 3 * kSat * kSat);            // [3][33][33]
   __shared__ int next_sprite;                                                      // dynamic sprite -> warp assignment
 
@@ -288,9 +318,7 @@ __global__ void __launch_bounds__(kRasterThreads, 2) raster_kernel(const RasterA
           }
         }
       }
-      // cv2 RGB2GRAY in exact float arithmetic (every intermediate is an integer < 2^24), then >> 15
-      const float gx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(9798.0f, r), __fmul_rn(19235.0f, g)), __fmul_rn(3735.0f, b)), 16384.0f);
-      const int gray = __float2int_rn(gx) >> 15;
+      const int gray = gray_of(r, g, b);
       const int both = __reduce_add_sync(0xffffffffu, gray << (half * 16));
       if (sidx == 0 && valid) plane[oy * a.ow + ox] = (uint8_t)gca_area16_u8((both >> (half * 16)) & 0xffff);
     };
@@ -340,11 +368,77 @@ __global__ void __launch_bounds__(kRasterThreads, 2) raster_kernel(const RasterA
             entry = make_uint2((uint32_t)ox | ((uint32_t)oy << 16), nid > 4 || ids == kScanCell ? kScanCell : ids);
           }
         }
-        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-        if (keep) list[cnt + __popc(bal & ((1u << lane) - 1u))] = entry;
-        cnt += __popc(bal);
+        // simple pixels (this sprite is the only live one: the destination is white, blending order is moot) take the
+        // deferred path below; the others, and an odd simple one, the ordered path
+        const bool simple = keep && entry.y == (0xffffff00u | (uint32_t)k0);
+        const uint32_t bs = __ballot_sync(0xffffffffu, simple);
+        const uint32_t bc = __ballot_sync(0xffffffffu, keep && !simple);
+        const int ns = __popc(bs) & ~1;                                    // simple pixels shaded in pairs
+        if (simple) {
+          const int rk = __popc(bs & ((1u << lane) - 1u));
+          if (rk < ns) slist[rk] = entry.x;
+          else list[cnt + __popc(bc)] = entry;                             // the odd one out
+        }
+        if (keep && !simple) list[cnt + __popc(bc & ((1u << lane) - 1u))] = entry;
+        cnt += __popc(bc) + (__popc(bs) & 1);
         __syncwarp();
-        // 3. shade two pixels per pass, lane = sample; an odd one is carried to the next batch
+        // 3a. simple pixels: lane = sample; transparent and uniform-opaque footprints are settled at once, the general
+        // blends are queued and done 32 at a time with every lane busy
+        {
+          const float4* mytex = texf + min(k0, 2) * (GCA_SPRITE * GCA_SPRITE);
+          const uint8_t* mycls = cls + min(k0, 2) * (kCorner * kCorner);
+          int qn = 0;
+          auto flush = [&](int start, int n) {
+            if (lane < n) {
+              const int q = queue[start + lane], slot = q >> 4, sm = q & 15;
+              const uint32_t e = slist[slot];
+              const float wx = __fadd_rn((float)(4 * (int)(e & 0xffffu)), (float)(sm & 3) + 0.5f);
+              const float wy = __fadd_rn((float)a.H, -__fadd_rn((float)(4 * (int)(e >> 16)), (float)(sm >> 2) + 0.5f));
+              int iu, iv;
+              float tu, tv, fu0, fv0;
+              float r = 255.0f, g = 255.0f, b = 255.0f;                    // white clear
+              if (sample_locate(me, wx, wy, iu, iv, tu, tv, fu0, fv0)) sample_blend(mytex, iu, iv, tu, tv, fu0, fv0, r, g, b);
+              atomicAdd(&acc[slot], gray_of(r, g, b));
+            }
+            __syncwarp();
+          };
+          for (int i = 0; i < ns; i += 2) {
+            const uint32_t e = slist[i + half];
+            const float wx = __fadd_rn((float)(4 * (int)(e & 0xffffu)), sxo);
+            const float wy = __fadd_rn((float)a.H, -__fadd_rn((float)(4 * (int)(e >> 16)), syo));
+            int iu, iv;
+            float tu, tv, fu0, fv0;
+            int gray = 255;                                                // outside the quad / transparent: white
+            bool defer = false;
+            if (sample_locate(me, wx, wy, iu, iv, tu, tv, fu0, fv0)) {
+              const int c = mycls[(iv + 1) * kCorner + (iu + 1)];
+              if (c == 2) {
+                const float4 t00 = mytex[(31 - max(iv, 0)) * GCA_SPRITE + max(iu, 0)];
+                gray = gray_of(t00.x, t00.y, t00.z);
+              } else if (c == 1) {
+                defer = true;
+                gray = 0;
+              }
+            }
+            const int both = __reduce_add_sync(0xffffffffu, gray << (half * 16));
+            if (sidx == 0) acc[i + half] = (both >> (half * 16)) & 0xffff;
+            const uint32_t bd = __ballot_sync(0xffffffffu, defer);
+            if (defer) queue[qn + __popc(bd & ((1u << lane) - 1u))] = (uint16_t)(((i + half) << 4) | sidx);
+            qn += __popc(bd);
+            __syncwarp();
+            if (qn >= 32) {
+              flush(qn - 32, 32);
+              qn -= 32;
+            }
+          }
+          if (qn) flush(0, qn);
+          for (int l = lane; l < ns; l += 32) {
+            const uint32_t e = slist[l];
+            plane[(int)(e >> 16) * a.ow + (int)(e & 0xffffu)] = (uint8_t)gca_area16_u8(acc[l]);
+          }
+          __syncwarp();
+        }
+        // 3b. the ordered path: two pixels per pass, lane = sample; an odd one is carried to the next batch
         int i = 0;
         for (; i + 1 < cnt; i += 2) shade_pair(i, true);
         if (i < cnt) {
@@ -384,6 +478,7 @@ size_t raster_smem_bytes(int ow, int oh) {
   const int cells = ((ow + cs - 1) / cs) * ((oh + cs - 1) / cs);
   return 3 * GCA_SPRITE * GCA_SPRITE * sizeof(float4) + (((size_t)ow * oh + 15) & ~(size_t)15) + sizeof(uint4) * (size_t)cells +
          (sizeof(float4) + sizeof(short4)) * kMaxSprites + sizeof(uint2) * kRasterWarps * kListCap +
+         sizeof(uint32_t) * kRasterWarps * 96 +
          sizeof(uint16_t) * 3 * kSat * kSat + ((3 * kCorner * kCorner + 15) & ~15);
 }
 
