@@ -91,6 +91,7 @@ __device__ __forceinline__ double shfl_f64(double v, int src) {
 
 constexpr int kMctsWarps = 4;
 constexpr int kMaxRounds = 4;       // intruder rounds held in registers (N - 1 <= 128); larger N uses the generic path
+static_assert(kMaxRounds == 4, "launch_mcts_playouts dispatches on 1..4 rounds");
 
 // RC > 0: intruder rounds in registers; RC == 0: intruders live in shared memory (any N)
 template <int RC>
