@@ -137,9 +137,13 @@ def test_drop_in_search_classes():
     np.random.seed(0)
     state = SingleAircraftState(state=g["roots"][0])
     root = SingleAircraftNode(state=state)
-    best = MCTS(root).best_action(30, 2)
+    best = MCTS(root).best_action(30, 2, device=False)         # the reference's structure: tree in Python objects
     assert best.state.prev_action in [(a, b) for a in range(3) for b in range(3)]
     assert len(root.children) == 9 and root.n == 30.0
+    root2 = SingleAircraftNode(state=SingleAircraftState(state=g["roots"][0]))
+    best2 = MCTS(root2).best_action(30, 2)                     # default: the whole search on the device
+    assert best2.state.prev_action in [(a, b) for a in range(3) for b in range(3)]
+    assert best2.parent is root2 and best2.state.depth == 1 and root2.children == [best2]
     nxt = state.move((1, 1))
     assert nxt.depth == 1 and nxt.prev_action == (1, 1) and nxt.state.shape == state.state.shape
     assert 0.0 <= nxt.reward() <= 1.0
