@@ -914,7 +914,15 @@ template <bool FAITH, bool TAPE>
 static cudaError_t launch_step_t(const StepArgs& a, cudaStream_t st, cudaEvent_t* ev) {
   const DevState& s = a.s;
   const unsigned env_blocks = (unsigned)(((size_t)s.T * 32 + 127) / 128);
-  auto mark = [&](int i) { if (ev) cudaEventRecord(ev[i], st); };
+  // profiling events; inside a stream capture they must be EXTERNAL records to become event-record nodes of the graph
+  // (a plain record would only be a capture-internal dependency and could not be timed)
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (ev) cudaStreamIsCapturing(st, &cap);
+  auto mark = [&](int i) {
+    if (!ev) return;
+    if (cap == cudaStreamCaptureStatusActive) cudaEventRecordWithFlags(ev[i], st, cudaEventRecordExternal);
+    else cudaEventRecord(ev[i], st);
+  };
   mark(0);
   launch_pdl(step_own_kernel<FAITH, TAPE>, env_blocks, 128, st, a);
   mark(1);
