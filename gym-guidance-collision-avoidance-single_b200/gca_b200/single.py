@@ -262,6 +262,20 @@ class SingleAircraftMCTSEnv(_SingleBase):
         return self._obs(), reward, bool(b.done[0].item()), {"result": abi.INFO_STR[code]}
 
 
+class SimSingleAircraftEnv(SingleAircraftMCTSEnv):
+    """Simulators/SingleAircraftEnv.py: the registered env with the reward row of Simulators/config.py and an info dict
+    (normalised vector observation, integer action 0..8)."""
+    VARIANT = "SimSingleAircraftEnv"
+
+    def _decode(self, action):
+        return int(action)
+
+
+class SingleAircraftRandomEnv(SimSingleAircraftEnv):
+    """Simulators/SingleAircraftRandomEnv.py: as above with the ownship drawn at reset (:71-73)."""
+    VARIANT = "SingleAircraftRandomEnv"
+
+
 class SingleAircraftDiscrete9HEREnv(_GoalBase):
     """The training env of the repo's own learners (Simulators/SingleAircraftDiscrete9HEREnv.py, used by
     Algorithms/pytorch/dqn_her.py and Algorithms/A2C): random ownship start (:78-82), observation = ownship

@@ -25,6 +25,10 @@ VARIANTS = {
     # Simulators/SingleAircraftDiscrete3HEREnv.py: as 9HER with Discrete(3) heading-only actions (:407-411), the goal drawn
     # 100 px inside the map (:349-353) and the nearest-intruder term added to the default reward (:225-232)
     "SingleAircraftDiscrete3HEREnv": (abi.ACT_DISCRETE3_HEADING, abi.OBS_NEAREST, None, 1, None, False),
+    # Simulators/SingleAircraftEnv.py ("deprecated" copy of the registered env): Config-driven reward row (:168-185), no
+    # out-of-map rule (:175-176 commented), info dict (:139); SingleAircraftRandomEnv.py: the same with a random start (:71-73)
+    "SimSingleAircraftEnv": (abi.ACT_DISCRETE9, abi.OBS_VECTOR, abi.WALL_NONE, 1, None, False),
+    "SingleAircraftRandomEnv": (abi.ACT_DISCRETE9, abi.OBS_VECTOR, abi.WALL_NONE, 1, None, False),
 }
 
 
@@ -67,6 +71,8 @@ def make_config(variant, cfg_cls, time_limit=0):
         c.random_start = 1
         c.nearest_n = int(cfg_cls.n)
         c.ob_diagonal = cfg_cls.diagonal
+    if variant == "SingleAircraftRandomEnv":
+        c.random_start = 1
     if variant == "SingleAircraftDiscrete3HEREnv":
         c.conflict_coeff = cfg_cls.conflict_coeff
         c.goal_margin = 100.0

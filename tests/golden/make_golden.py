@@ -35,6 +35,8 @@ from gym_guidance_collision_avoidance_single.envs.config import Config as PkgCon
 import SingleAircraftMCTSEnv as mcts_env_mod  # noqa: E402  (Simulators/, uses Simulators/config.py)
 import SingleAircraftDiscrete9HEREnv as d9her_mod  # noqa: E402  (Simulators/, nearest-n observation)
 import SingleAircraftDiscrete3HEREnv as d3her_mod  # noqa: E402  (Simulators/, + nearest-intruder reward term)
+import SingleAircraftEnv as simenv_mod  # noqa: E402  (Simulators/ copy: Config-driven rewards)
+import SingleAircraftRandomEnv as rndenv_mod  # noqa: E402  (Simulators/, random ownship start)
 import config as SimConfigMod  # noqa: E402
 import nodes_single  # noqa: E402
 import search_single  # noqa: E402
@@ -176,9 +178,11 @@ VARIANTS = {
     "mcts": (mcts_env_mod.SingleAircraftEnv, SimConfigMod.Config, "t33"),
     "d9her": (d9her_mod.SingleAircraftDiscrete9HEREnv, SimConfigMod.Config, "d9"),
     "d3her": (d3her_mod.SingleAircraftDiscrete3HEREnv, SimConfigMod.Config, "d3"),
+    "simenv": (simenv_mod.SingleAircraftEnv, SimConfigMod.Config, "d9"),
+    "rndenv": (rndenv_mod.SingleAircraftRandomEnv, SimConfigMod.Config, "d9"),
 }
 # np.argpartition(dist_array, Config.n) of the nearest-n observation needs more than n = 4 intruders
-PLANS = {"d9her": {5: (5, 40), 12: (5, 40), 80: (3, 30)}, "d3her": {5: (5, 40), 12: (5, 40), 80: (3, 30)}}
+PLANS = {"simenv": {3: (3, 40), 80: (2, 25)}, "rndenv": {3: (3, 40), 80: (2, 25)}, "d9her": {5: (5, 40), 12: (5, 40), 80: (3, 30)}, "d3her": {5: (5, 40), 12: (5, 40), 80: (3, 30)}}
 
 
 def sample_action(kind, rng):

@@ -11,16 +11,17 @@ STATE_KEYS = ("own_pos", "own_hs", "own_vel", "own_vel_is_f32", "goal", "no_conf
               "ipos_is_f64", "ivel", "iflag")
 GOLDEN_VARIANTS = {"env": "SingleAircraftEnv", "env2": "SingleAircraft2Env", "her": "SingleAircraftHEREnv",
                    "dher": "SingleAircraftDiscreteHEREnv", "mcts": "SingleAircraftMCTSEnv",
-                   "d9her": "SingleAircraftDiscrete9HEREnv", "d3her": "SingleAircraftDiscrete3HEREnv"}
+                   "d9her": "SingleAircraftDiscrete9HEREnv", "d3her": "SingleAircraftDiscrete3HEREnv",
+                   "simenv": "SimSingleAircraftEnv", "rndenv": "SingleAircraftRandomEnv"}
 GOLDEN_N = (0, 1, 3, 80)
-GOLDEN_N_BY_VARIANT = {"d9her": (5, 12, 80), "d3her": (5, 12, 80)}     # the nearest-n observation needs more than Config.n = 4 intruders
+GOLDEN_N_BY_VARIANT = {"d9her": (5, 12, 80), "d3her": (5, 12, 80), "simenv": (3, 80), "rndenv": (3, 80)}     # the nearest-n observation needs more than Config.n = 4 intruders
 # every (variant key, N) with a recorded trace file
 GOLDEN_CASES = [(vk, n) for vk in sorted(GOLDEN_VARIANTS) for n in GOLDEN_N_BY_VARIANT.get(vk, GOLDEN_N)]
 GOAL_VARIANTS = ("her", "dher", "d9her", "d3her")          # dict observation: achieved / desired goal outputs
 
 
 def config_class(variant_key):
-    if variant_key in ("mcts", "d9her", "d3her"):
+    if variant_key in ("mcts", "d9her", "d3her", "simenv", "rndenv"):
         from Simulators.config import Config
     else:
         from gym_guidance_collision_avoidance_single.envs.config import Config

@@ -23,17 +23,21 @@ def _make(vk, n, **kw):
             from Simulators.SingleAircraftDiscrete9HEREnv import SingleAircraftDiscrete9HEREnv as cls
         elif vk == "d3her":
             from Simulators.SingleAircraftDiscrete3HEREnv import SingleAircraftDiscrete3HEREnv as cls
+        elif vk == "simenv":
+            from Simulators.SingleAircraftEnv import SingleAircraftEnv as cls
+        elif vk == "rndenv":
+            from Simulators.SingleAircraftRandomEnv import SingleAircraftRandomEnv as cls
         else:
             import gym_guidance_collision_avoidance_single.envs as envs
             cls = {"env": envs.SingleAircraftEnv, "env2": envs.SingleAircraft2Env, "her": envs.SingleAircraftHEREnv,
                    "dher": envs.SingleAircraftDiscreteHEREnv}[vk]
         return cls(**kw)
     finally:
-        cfgc.intruder_size = 80 if vk in ("mcts", "d9her", "d3her") else 0
+        cfgc.intruder_size = 80 if vk in ("mcts", "d9her", "d3her", "simenv", "rndenv") else 0
 
 
 def _ref_action(vk, a):
-    if vk in ("env", "dher", "d9her", "d3her"):
+    if vk in ("env", "dher", "d9her", "d3her", "simenv", "rndenv"):
         return int(a[0])
     if vk == "mcts":
         return (int(a[0]), int(a[1]))
@@ -41,7 +45,7 @@ def _ref_action(vk, a):
 
 
 @pytest.mark.parametrize("vk,n", [("env", 3), ("env", 80), ("env2", 3), ("her", 3), ("dher", 3), ("mcts", 80),
-                                  ("d9her", 12), ("d9her", 80), ("d3her", 12)])
+                                  ("d9her", 12), ("d9her", 80), ("d3her", 12), ("simenv", 3), ("rndenv", 80)])
 def test_single_env_api_replays_reference_trace(vk, n):
     g = load_trace(vk, n)
     plain = [int(i) for i in np.nonzero(g["kind_id"] == 0)[0]][:2]
@@ -62,7 +66,7 @@ def test_single_env_api_replays_reference_trace(vk, n):
             ob, r, done, info = env.step(_ref_action(vk, g["actions"][tr, t]))
             assert close(ob["observation"] if her else ob, g["obs"][tr, t])
             assert close(r, g["reward"][tr, t])
-            if vk not in ("mcts", "d9her", "d3her"):
+            if vk not in ("mcts", "d9her", "d3her", "simenv", "rndenv"):
                 assert isinstance(r, int) == bool(g["reward_is_int"][tr, t]), (vk, t, r)
             assert done == bool(g["done"][tr, t]) and isinstance(done, bool)
             code = ("", "n", "c", "g", "w", "m")[g["event"][tr, t]]

@@ -70,7 +70,8 @@ def test_abi_argument_checking():
 def test_variant_table_matches_reference_reward_rows():
     from gym_guidance_collision_avoidance_single.envs.config import Config
     from Simulators.config import Config as Sim
-    rows = {k: variants.make_config(k, Sim if k in ("SingleAircraftMCTSEnv", "SingleAircraftDiscrete9HEREnv", "SingleAircraftDiscrete3HEREnv") else Config)
+    rows = {k: variants.make_config(k, Sim if k not in ("SingleAircraftEnv", "SingleAircraft2Env", "SingleAircraftHEREnv", "SingleAircraftDiscreteHEREnv",
+                                                     "SingleAircraftStackEnv") else Config)
             for k in variants.VARIANTS}
     r = rows["SingleAircraftDiscrete9HEREnv"]
     assert (r.obs_kind, r.random_start, r.nearest_n, r.ob_diagonal, r.wall_kind) == (abi.OBS_NEAREST, 1, 4, 800, abi.WALL_NONE)
