@@ -37,9 +37,15 @@ _CLASS_OF = {
 
 class AircraftVecEnv(object):
     def __init__(self, env, num_envs, config=None, n_intruders=None, mode="fast", device=0, seed=0, env_id0=0,
-                 host=False, time_limit=None):
+                 host=False, time_limit=None, frame_stack=1, sprites=None):
+        """frame_stack / sprites apply to the image variant only (SingleAircraftStackEnv): k > 1 is baselines'
+        VecFrameStack(venv, k) (common/vec_env/vec_frame_stack.py) with the frames kept in a ring on the device."""
         variant = _CLASS_OF.get(env, env)
         registered = env in _CLASS_OF
+        self._image = None
+        if variant == "SingleAircraftStackEnv":
+            self._init_image(num_envs, config, n_intruders, mode, device, seed, env_id0, host, frame_stack, sprites)
+            return
         if config is None:
             if variant in ("SingleAircraftMCTSEnv", "SingleAircraftDiscrete9HEREnv"):
                 from Simulators.config import Config as config
@@ -71,6 +77,25 @@ class AircraftVecEnv(object):
         self._pending = None
         self.closed = False
 
+    def _init_image(self, num_envs, config, n_intruders, mode, device, seed, env_id0, host, frame_stack, sprites):
+        from .stack import ImageBatch
+        if host:
+            raise ValueError("the image variant keeps its frames on the device (host=False)")
+        self.variant = "SingleAircraftStackEnv"
+        self.num_envs, self.host = int(num_envs), False
+        self._image = ImageBatch(num_envs, config, n_intruders=n_intruders, frame_stack=frame_stack, device=device,
+                                 seed=seed, env_id0=env_id0, mode=mode, sprites=sprites)
+        self.batch = self._image.batch
+        k = self._image.k
+        # PKG/SingleAircraftStackEnv.py:34-35 (200 x 200 x 1 uint8), repeated k times on the last axis by VecFrameStack
+        self.observation_space = Box(low=0, high=255, shape=(self._image.H, self._image.W, k), dtype=np.uint8)
+        self.action_space = Discrete(9)
+        self._pending = None
+        self.closed = False
+
+    def _image_obs(self):
+        return self._image.stacked() if self._image.k > 1 else self._image.frame()
+
     # ------------------------------------------------------------------ VecEnv interface
     def _pack_obs(self, obs):
         b = self.batch
@@ -82,6 +107,9 @@ class AircraftVecEnv(object):
         return {"observation": b.obs, "achieved_goal": b.achieved, "desired_goal": b.desired}
 
     def reset(self):
+        if self._image is not None:
+            self._image.reset()
+            return self._image_obs()
         if self.host:
             return self._pack_obs(self.batch.reset_host())
         return self._pack_obs(self.batch.reset())
@@ -89,7 +117,10 @@ class AircraftVecEnv(object):
     def step_async(self, actions):
         if self._pending is not None:
             raise AlreadySteppingError()
-        if self.host:
+        if self._image is not None:
+            _, rew, done, info = self._image.step(actions, auto_reset=True)
+            self._pending = ("img", (rew, done, info))
+        elif self.host:
             self._pending = ("host", np.asarray(actions))
         else:
             # the launch is asynchronous on the current CUDA stream: this IS the async half
@@ -100,6 +131,9 @@ class AircraftVecEnv(object):
             raise NotSteppingError()
         kind, payload = self._pending
         self._pending = None
+        if kind == "img":
+            rew, done, info = payload
+            return self._image_obs(), rew, done, info
         if kind == "host":
             obs, rew, done, info = self.batch.step_host(payload, auto_reset=True)
             return self._pack_obs(obs), rew, done.astype(bool), info

@@ -217,3 +217,29 @@ def test_vec_monitor_equals_baselines_vec_monitor(tmp_path):
     assert lines[0].startswith('# {"t_start": ') and lines[1] == "r,l,t" and len(lines) == 2 + len(want)
     r, l, t = lines[2].split(",")
     assert float(r) == want[0][1] and int(l) == want[0][2]
+
+
+def test_vec_env_image_variant_with_frame_stack():
+    """The registered stack id through the VecEnv interface: uint8 frames [B, 200, 200, k] on the device, k = 4 being
+    baselines' VecFrameStack (roll, zero on done, newest frame last)."""
+    import torch
+    from gca_b200.vec_env import AircraftVecEnv
+    B, k = 10, 4
+    venv = AircraftVecEnv("guidance-collision-avoidance-single-stack-v0", B, n_intruders=12, seed=2, frame_stack=k)
+    assert venv.observation_space.shape == (200, 200, k) and venv.observation_space.dtype == np.uint8
+    obs = venv.reset()
+    assert obs.shape == (B, 200, 200, k) and obs.dtype == torch.uint8 and obs.is_cuda
+    stacked = obs.cpu().numpy().copy()
+    assert not stacked[..., :-1].any() and (stacked[..., -1] == 255).mean() > 0.9
+    rng = np.random.RandomState(0)
+    for t in range(6):
+        obs, rew, done, info = venv.step(torch.as_tensor(rng.randint(0, 9, B).astype(np.int32), device="cuda"))
+        new = obs.cpu().numpy()
+        d = done.cpu().numpy().astype(bool)
+        stacked = np.roll(stacked, -1, axis=-1)
+        stacked[d] = 0
+        assert np.array_equal(new[..., :-1], stacked[..., :-1]), t
+        stacked[..., -1] = new[..., -1]
+    single = AircraftVecEnv("guidance-collision-avoidance-single-stack-v0", 3, n_intruders=5, seed=2)
+    assert single.reset().shape == (3, 200, 200, 1)
+    venv.close(); single.close()
