@@ -351,7 +351,9 @@ def main_gpu(args):
         if world == 1 and not kernel_only:
             cb, _, _ = run_cpu(10 ** 9, 1, budget_s=12.0)
             line["cpu_baseline"] = cb
-        if not kernel_only:
+        if not kernel_only and (world == 1 or os.environ.get("GCA_BENCH_EXTRAS") == "1"):
+            # the other configs / metrics of BASELINE.json; at N > 1 they would only repeat rank 0's single-GPU numbers
+            # while the other ranks wait in the barrier (GCA_BENCH_EXTRAS=1 forces them)
             line["mcts"] = bench_mcts(local, with_cpu=(world == 1))
             line["her"] = bench_her(local)
             line["stack"] = bench_stack(local)
