@@ -7,6 +7,12 @@
 // conflict and goal both use minimum_separation and there is no NMAC tier (Q24), the wall test
 // is strict (Q6).
 //
+// Three users of the model (details at each kernel):
+//   mcts_playout_shared_kernel  position_sigma == 0 (the reference's setting): one CTA per root, intruder trajectories
+//                               shared by the root's playouts, one playout per lane;
+//   mcts_playout_kernel<RC>     any sigma: one warp per playout (below);
+//   mcts_candidates_kernel + mcts_search_kernel   the whole UCT search of a root in one lane, trees resident in HBM.
+//
 // playout kernel: one warp per playout.  What is sequential in the reference is split so that the
 // expensive f64 work runs lane-parallel:
 //   (1) lane f draws the heading noise of sub-frame f (Philox + Box-Muller)        - parallel

@@ -19,9 +19,12 @@
 //      those samples can land on are not all transparent (summed-area query).  The warp keeps the pixels
 //      that are live for its sprite and for no sprite drawn earlier - so every pixel that can differ from
 //      white is shaded exactly once - together with the (<= 4) sprites that are live on it;
-//   3. the kept pixels are shaded two at a time: lane = one of the 16 samples of a pixel, colour state in
-//      registers, the live sprites blended in draw order, gray, warp-wide packed integer reduction,
-//      4x4 area mean (round half to even), one byte into the shared plane;
+//   3. the kept pixels are shaded two at a time, lane = one of the 16 samples of a pixel.  Pixels on which only
+//      this sprite is live (the destination is white: ~98 % of them) take a deferred path: transparent and
+//      uniform-opaque footprints are settled at once, the samples that need the general bilinear blend are
+//      queued and blended 32 at a time with every lane busy, their grays added by shared-memory atomics.  The
+//      others take the ordered path: colour state in registers, the live sprites blended in draw order.  Then
+//      gray, warp-wide packed integer reduction, 4x4 area mean (round half to even), one byte into the plane;
 //   4. fence.proxy.async + cp.async.bulk shared -> global of the whole plane (UBLKCP); the next env's
 //      fill waits only for the bulk copy to have READ the plane.
 // Output bytes: 40 000 per env-step, written once, fully coalesced.
