@@ -436,6 +436,29 @@ __device__ __forceinline__ double norm_vel_f64(const gca_config& c, const Derive
 // the four entries of intruder i   PKG/SingleAircraftEnv.py:108-114 (raw: Simulators/SingleAircraftMCTSEnv.py:107-112)
 // `base` points at the first intruder entry of the env's observation row.
 template <bool FAITH>
+__device__ __forceinline__ void obs_intruder_entries(const StepArgs& a, const Intr<FAITH>& it, real_t<FAITH>& o0,
+                                                     real_t<FAITH>& o1, real_t<FAITH>& o2, real_t<FAITH>& o3) {
+  using R = real_t<FAITH>;
+  const gca_config& c = a.cfg;
+  const Derived& k = a.k;
+  if (c.obs_kind == GCA_OBS_RAW) {
+    o0 = (R)it.px; o1 = (R)it.py; o2 = (R)it.vx; o3 = (R)it.vy;
+  } else {
+    bool wide = false;
+    if constexpr (FAITH) wide = it.is64;
+    if (wide) {
+      o0 = (R)ddiv_prepared(k, (double)it.px, k.dv_w, k.rc_w);
+      o1 = (R)ddiv_prepared(k, (double)it.py, k.dv_h, k.rc_h);
+    } else {
+      o0 = (R)div_prepared(k, (float)it.px, k.ob_w, k.inv_ob_w);
+      o1 = (R)div_prepared(k, (float)it.py, k.ob_h, k.inv_ob_h);
+    }
+    o2 = (R)norm_vel_f32(k, it.vx);
+    o3 = (R)norm_vel_f32(k, it.vy);
+  }
+}
+
+template <bool FAITH>
 __device__ __forceinline__ void write_obs_intruder(const StepArgs& a, real_t<FAITH>* base, int i,
                                                    const Intr<FAITH>& it) {
   using R = real_t<FAITH>;

@@ -653,7 +653,9 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
   GCA_KSTAMP_IN(1);
   using R = real_t<FAITH>;
   static_assert(!(FAITH && OM), "the specialised observation path is FAST only");
-  constexpr uint32_t kWarpSmem = OM ? 32 * kObsRow : 16;             // observation staging
+  // observation staging: FAST specialised layouts 8 x 16 bytes per lane, FAITHFUL 8 x 32 bytes per lane (+ 16: odd stride)
+  constexpr uint32_t kObsRow64 = 32u * kChunkIntr + 16u;
+  constexpr uint32_t kWarpSmem = OM ? 32 * kObsRow : (FAITH ? 32 * kObsRow64 : 16);
   __shared__ __align__(16) uint8_t stage_smem[kWarpsB * kWarpSmem];
   const DevState& s = a.s;
   const Derived& k = a.k;
@@ -759,6 +761,67 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
           n1.px = np[g].z; n1.py = np[g].w; n1.vx = vv[g].z; n1.vy = vv[g].w;
           write_obs_intruder<FAITH>(a, obase, i0 + 2 * g, n0);
           write_obs_intruder<FAITH>(a, obase, i0 + 2 * g + 1, n1);
+        }
+      }
+    }
+  }
+  if constexpr (FAITH) {
+    if (n_here == kChunkIntr) {
+      // ---- FAITHFUL, a full work item: the 8 position units and 4 velocity units are requested before any of them is
+      // looked at; the f64 observation entries (32 bytes per intruder) leave through a transposed shared-memory
+      // write-out - 16 consecutive lanes store the 256 contiguous bytes of ONE env's row, whole 32-byte sectors
+      // (a lane storing its own 16-byte pieces 2 624 bytes apart touched 32 half-used sectors per instruction)
+      fast_done = true;
+      const bool stage = a.cfg.obs_kind != GCA_OBS_NONE && a.cfg.obs_kind != GCA_OBS_NEAREST;
+      double2 pq[kChunkIntr];
+      float4 vq[kChunkUnits];
+#pragma unroll
+      for (int g = 0; g < kChunkUnits; ++g) vq[g] = ldg_stream(vsrc + g * 512, pol);
+#pragma unroll
+      for (int j = 0; j < kChunkIntr; ++j) {
+        const float4 raw = ldg_stream(psrc + j * 512, pol);
+        pq[j] = make_double2(__hiloint2double(__float_as_int(raw.y), __float_as_int(raw.x)),
+                             __hiloint2double(__float_as_int(raw.w), __float_as_int(raw.z)));
+      }
+      const uint32_t dw = has_env ? s.dflag[flag_index(s, me, i0 >> 5)] >> (i0 & 31) : 0u;
+      uint8_t* stg = stage_smem + wib * kWarpSmem;
+      double2* row = reinterpret_cast<double2*>(stg + lane * kObsRow64);
+#pragma unroll
+      for (int j = 0; j < kChunkIntr; ++j) {
+        Intr<FAITH> it;
+        it.px = pq[j].x; it.py = pq[j].y;
+        it.vx = (j & 1) ? vq[j >> 1].z : vq[j >> 1].x;
+        it.vy = (j & 1) ? vq[j >> 1].w : vq[j >> 1].y;
+        it.is64 = (dw >> j) & 1u;
+        if (runs) {
+          const bool oob = advance<FAITH>(k, it);             // :150, :153
+          bool lt_sep, lt_nmac, lt_init;
+          separation<FAITH>(k, ox, oy, it, lt_sep, lt_nmac, lt_init);   // :151
+          gone |= (oob ? 1u : 0u) << j;
+          conf |= (lt_sep ? 1u : 0u) << j;
+          nmac |= (lt_nmac ? 1u : 0u) << j;
+        }
+        if (has_env) *reinterpret_cast<double2*>(pdst + j * 512) = make_double2(it.px, it.py);
+        if (stage) {
+          double o0, o1, o2, o3;
+          obs_intruder_entries<FAITH>(a, it, o0, o1, o2, o3);
+          row[2 * j] = make_double2(o0, o1);
+          row[2 * j + 1] = make_double2(o2, o3);
+        }
+      }
+      if (stage) {
+        __syncwarp();
+        const int sub = lane >> 4, piece = lane & 15;       // 16 lanes x 16 bytes = one env's 8 intruders
+        const size_t row_off = (own_first(a.cfg) ? 6 : 0) + 4 * (size_t)i0;
+#pragma unroll 4
+        for (int it2 = 0; it2 < 16; ++it2) {
+          const int e = sub + 2 * it2;
+          const size_t env_e = (size_t)tile * 32 + e;
+          if (env_e < (size_t)s.B) {
+            const double2 val = *reinterpret_cast<const double2*>(stg + e * kObsRow64 + piece * 16);
+            double* dst = reinterpret_cast<double*>(a.obs) + env_e * (size_t)a.D + row_off + 2 * (size_t)piece;
+            *reinterpret_cast<double2*>(dst) = val;
+          }
         }
       }
     }
