@@ -9,17 +9,17 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GCA_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libgca.so")
 
-GCA_ABI_VERSION = 4
+GCA_ABI_VERSION = 5
 
 MODE_FAITHFUL, MODE_FAST = 0, 1
 DRAWS_TAPE, DRAWS_PHILOX = 0, 1
 ACT_DISCRETE9, ACT_CONTINUOUS2, ACT_DISCRETE3, ACT_DISCRETE3_HEADING = 0, 1, 2, 3
-OBS_VECTOR, OBS_HER, OBS_DHER, OBS_RAW, OBS_NONE, OBS_NEAREST = 0, 1, 2, 3, 4, 5
+OBS_VECTOR, OBS_HER, OBS_DHER, OBS_RAW, OBS_NONE, OBS_NEAREST, OBS_RAW6 = 0, 1, 2, 3, 4, 5, 6
 WALL_NONE, WALL_TERMINAL, WALL_PENALTY = 0, 1, 2
 INFO_NONE, INFO_NMAC, INFO_CONFLICT, INFO_GOAL, INFO_WALL, INFO_MAXSTEPS = range(6)
 INFO_STR = ("", "n", "c", "g", "w", "m")
 
-SLOT_OWNSHIP, SLOT_GOAL, SLOT_RESET = 0x80000000, 0x40000000, 0x20000000
+SLOT_OWNSHIP, SLOT_GOAL, SLOT_RESET, SLOT_TURN = 0x80000000, 0x40000000, 0x20000000, 0x08000000
 
 
 class GcaConfig(C.Structure):
@@ -32,14 +32,15 @@ class GcaConfig(C.Structure):
         "r_nmac", "r_conflict", "r_wall", "r_goal", "r_default")] + [(n, C.c_int32) for n in (
             "shaped_default", "action_kind", "obs_kind", "wall_kind", "max_steps", "time_limit", "random_start",
             "nearest_n")] + [("ob_diagonal", C.c_double), ("conflict_coeff", C.c_double), ("goal_margin", C.c_double),
-                             ("shaped_nearest", C.c_int32), ("reserved0", C.c_int32)]
+                             ("shaped_nearest", C.c_int32), ("intruder_turns", C.c_int32),
+                             ("position_drift", C.c_double), ("turn_prob", C.c_double), ("turn_max_deg", C.c_double)]
 
 
 class GcaHostState(C.Structure):
     _fields_ = [("own_pos", C.c_void_p), ("own_hs", C.c_void_p), ("own_vel", C.c_void_p),
                 ("own_vel_is_f32", C.c_void_p), ("goal", C.c_void_p),
                 ("no_conflict", C.c_void_p), ("ep_steps", C.c_void_p), ("tick", C.c_void_p), ("ipos", C.c_void_p),
-                ("ipos_is_f64", C.c_void_p), ("ivel", C.c_void_p), ("iflag", C.c_void_p)]
+                ("ipos_is_f64", C.c_void_p), ("ivel", C.c_void_p), ("iflag", C.c_void_p), ("ihs", C.c_void_p)]
 
 
 class GcaOut(C.Structure):

@@ -16,7 +16,7 @@ _STATE_FIELDS = (("own_pos", np.float32, (2,)), ("own_hs", np.float64, (2,)), ("
                  ("own_vel_is_f32", np.uint8, ()), ("goal", np.float64, (2,)), ("no_conflict", np.int32, ()),
                  ("ep_steps", np.int32, ()), ("tick", np.uint32, ()),
                  ("ipos", np.float64, ("N", 2)), ("ipos_is_f64", np.uint8, ("N",)), ("ivel", np.float32, ("N", 2)),
-                 ("iflag", np.uint8, ("N",)))
+                 ("iflag", np.uint8, ("N",)), ("ihs", np.float64, ("N", 2)))
 
 
 def _torch():

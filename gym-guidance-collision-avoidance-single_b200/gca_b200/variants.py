@@ -19,6 +19,10 @@ VARIANTS = {
     "SingleAircraftStackEnv": (abi.ACT_DISCRETE9, abi.OBS_NONE, abi.WALL_PENALTY, 1, (-20, -5, -10, 10000, 0), True),
     # Simulators/SingleAircraftMCTSEnv.py:163-180: rewards come from Simulators/config.py:37-43 (filled by make_config)
     "SingleAircraftMCTSEnv": (abi.ACT_DISCRETE9, abi.OBS_RAW, abi.WALL_NONE, 1, None, False),
+    # Simulators/SingleAircraftMCTSRandIntruderEnv.py: the MCTS env whose intruders turn at random after every step
+    # (_update_headings :166-174), drift by Config.position_sigma per step (:183) and show (speed, heading) in the raw
+    # observation (:133-140); reward row from Simulators/config.py:37-43 (:207-227); info is the bare string (:164)
+    "SingleAircraftMCTSRandIntruderEnv": (abi.ACT_DISCRETE9, abi.OBS_RAW6, abi.WALL_NONE, 1, None, False),
     # Simulators/SingleAircraftDiscrete9HEREnv.py: random ownship start :78-82, n nearest intruders :127-144, rewards
     # from Simulators/config.py:37-43 (:207-227), out-of-map rule only under sparse_reward (:217-219)
     "SingleAircraftDiscrete9HEREnv": (abi.ACT_DISCRETE9, abi.OBS_NEAREST, None, 1, None, False),
@@ -67,6 +71,15 @@ def make_config(variant, cfg_cls, time_limit=0):
     c.conflict_coeff = 0.0
     c.goal_margin = 0.0
     c.shaped_nearest = 0
+    c.intruder_turns = 0
+    c.position_drift = 0.0
+    c.turn_prob = 0.0
+    c.turn_max_deg = 0.0
+    if variant == "SingleAircraftMCTSRandIntruderEnv":
+        c.intruder_turns = 1
+        c.position_drift = float(cfg_cls.position_sigma)     # :82, :183
+        c.turn_prob = 0.1                                    # :170
+        c.turn_max_deg = 10.0                                # :173
     if obs == abi.OBS_NEAREST:
         c.random_start = 1
         c.nearest_n = int(cfg_cls.n)
@@ -97,6 +110,8 @@ def obs_dim(c, n):
         return 4 * n + 6
     if c.obs_kind == abi.OBS_NEAREST:
         return 4 + 5 * c.nearest_n
+    if c.obs_kind == abi.OBS_RAW6:
+        return 6 * n + 8
     return 0
 
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GCA_ABI_VERSION 4
+#define GCA_ABI_VERSION 5
 
 typedef enum gca_status {
   GCA_OK = 0,
@@ -63,9 +63,11 @@ enum {
   GCA_OBS_DHER = 2,     /* as HER but achieved/desired are raw pixel positions   PKG/SingleAircraftDiscreteHEREnv.py:128-133 */
   GCA_OBS_RAW = 3,      /* VECTOR layout, un-normalised values     Simulators/SingleAircraftMCTSEnv.py:98-124 */
   GCA_OBS_NONE = 4,     /* no vector observation (StackEnv: the image comes from gca_raster) */
-  GCA_OBS_NEAREST = 5   /* [own x4][nearest_n intruders x5: x, y, vx, vy, dist / diagonal, nearest first] + achieved /
+  GCA_OBS_NEAREST = 5,  /* [own x4][nearest_n intruders x5: x, y, vx, vy, dist / diagonal, nearest first] + achieved /
                            desired normalised; needs N > nearest_n
                            Simulators/SingleAircraftDiscrete9HEREnv.py:106-165 */
+  GCA_OBS_RAW6 = 6      /* [intruders x6: x, y, vx, vy, speed, heading][own x6][goal x2], un-normalised
+                           Simulators/SingleAircraftMCTSRandIntruderEnv.py:124-152 */
 };
 
 enum { GCA_WALL_NONE = 0, GCA_WALL_TERMINAL = 1, GCA_WALL_PENALTY = 2 };
@@ -78,6 +80,8 @@ enum { GCA_INFO_NONE = 0, GCA_INFO_NMAC = 1, GCA_INFO_CONFLICT = 2, GCA_INFO_GOA
 #define GCA_SLOT_GOAL 0x40000000u    /* block 0: goal (x, y) of a reset */
 #define GCA_SLOT_RESET 0x20000000u   /* | intruder index: spawn made by a reset */
 #define GCA_SLOT_OWN_RESET 0x10000000u /* random_start: ownship drawn by a reset, blocks POS and SPEED_HEADING */
+#define GCA_SLOT_TURN 0x08000000u    /* | intruder index, block 0: (p, u) of _update_headings - the intruder turns by
+                                        radians(-turn_max_deg + 2 * turn_max_deg * u) when p < turn_prob */
                                      /* intruder index alone: respawn made inside a step */
 #define GCA_BLOCK_POS 0u             /* (x, y) */
 #define GCA_BLOCK_SPEED_HEADING 1u   /* (speed, heading) */
@@ -113,7 +117,15 @@ typedef struct gca_config {
                              3 * minimum_separation, added to the default reward (:225-232; Simulators/config.py:44) */
   double goal_margin;     /* > 0: the goal is drawn in [margin, window - margin]^2 (random_goal_pos :349-353) */
   int32_t shaped_nearest; /* 1: track dist_nearest_intruder over the intruders the loop visited (:185,:191) */
-  int32_t reserved0;
+  /* Simulators/SingleAircraftMCTSRandIntruderEnv.py */
+  int32_t intruder_turns; /* 1: after _terminal_reward every intruder draws p = uniform() and, when p < turn_prob, turns by
+                             radians(uniform(-turn_max_deg, turn_max_deg)): heading += delta, velocity = f32(speed * (cos,
+                             sin)) (_update_headings :166-174, change_heading :332-336); needs per-intruder (heading,
+                             speed) state */
+  double position_drift;  /* added to both velocity components of every intruder advance, in f32:
+                             position += velocity + Config.position_sigma (:183 - a constant, not a draw) */
+  double turn_prob;       /* 0.1 (:170) */
+  double turn_max_deg;    /* 10 (:173) */
 } gca_config;
 
 /* Canonical host-side view of the full simulator state, identical for both modes
@@ -131,6 +143,8 @@ typedef struct gca_host_state {
   uint8_t* ipos_is_f64;      /* [B][N]   position dtype is f64 (retried spawn, Q3) */
   float* ivel;               /* [B][N][2] :276 */
   uint8_t* iflag;            /* [B][N]   Aircraft.conflict :278 */
+  double* ihs;               /* [B][N][2] intruder (heading, speed), kept only by intruder_turns handles
+                                (Simulators/SingleAircraftMCTSRandIntruderEnv.py:322-323); ignored otherwise */
 } gca_host_state;
 
 /* Device output buffers of one reset/step.  REAL is double in FAITHFUL mode, float in FAST. */
@@ -157,7 +171,8 @@ typedef struct gca_env gca_env;
 int gca_abi_version(void);
 const char* gca_last_error(void);
 
-/* number of REAL elements of one observation row: 4*N + 8 for VECTOR/RAW, 4*N + 6 for HER/DHER, 0 for NONE */
+/* number of REAL elements of one observation row: 4*N + 8 for VECTOR/RAW, 4*N + 6 for HER/DHER, 6*N + 8 for RAW6,
+ * 4 + 5*nearest_n for NEAREST, 0 for NONE */
 int gca_obs_dim(const gca_config* cfg, int n_intruders);
 
 /* Replaces B constructions of PKG/SingleAircraftEnv.py:29-43 (and siblings).  Allocates the
@@ -184,7 +199,8 @@ int gca_reset(gca_env* env, const uint8_t* mask, const gca_tape* tape, const gca
 int gca_step(gca_env* env, const void* actions, const gca_tape* tape, int auto_reset,
              const gca_out* out, void* stream);
 
-/* Number of kernels one gca_step launches for this handle (ownship, intruders, finish, spawn: 2 to 4). */
+/* Number of kernels one gca_step launches for this handle (ownship, intruders, finish, spawn, and the observation
+ * pass of the NEAREST / RAW6 kinds: 2 to 5). */
 int gca_step_launches(gca_env* env);
 
 /* Diagnostics: per-kernel device time of gca_step.  While enabled, every gca_step records CUDA events

@@ -86,6 +86,7 @@ typedef struct env_view {
   uint8_t* is64;
   float* ivel;
   uint8_t* iflag;
+  double* ihs;   /* (heading, speed) per intruder; NULL unless the variant keeps them (intruder_turns) */
   /* draws */
   int draws, trig, f32_positions;
   const double* tape;
@@ -173,6 +174,10 @@ static void spawn(env_view* e, int i, uint32_t slot) {
   e->ivel[2 * i] = (float)(speed * c);
   e->ivel[2 * i + 1] = (float)(speed * s);
   e->iflag[i] = 0;
+  if (e->ihs) {   /* Aircraft.speed / Aircraft.heading  Simulators/SingleAircraftMCTSRandIntruderEnv.py:322-323 */
+    e->ihs[2 * i] = heading;
+    e->ihs[2 * i + 1] = speed;
+  }
   int retries = 0;
   for (;;) {
     double d = dist_intruder(e, i);
@@ -255,14 +260,19 @@ static void observe_env(const env_view* e, double* obs, double* ag, double* dg) 
     observe_nearest(e, obs, ag, dg);
     return;
   }
-  const int raw = kind == GCA_OBS_RAW;
+  const int raw = kind == GCA_OBS_RAW || kind == GCA_OBS_RAW6;
+  const int per = kind == GCA_OBS_RAW6 ? 6 : 4;
   const int own_first = kind == GCA_OBS_HER || kind == GCA_OBS_DHER;
   double* oi = obs + (own_first ? 6 : 0);
-  double* oo = obs + (own_first ? 0 : 4 * e->n);
+  double* oo = obs + (own_first ? 0 : per * e->n);
   for (int i = 0; i < e->n; ++i) {
     double px = e->ipos[2 * i], py = e->ipos[2 * i + 1];
     float vx = e->ivel[2 * i], vy = e->ivel[2 * i + 1];
-    if (raw) {
+    if (kind == GCA_OBS_RAW6) {   /* (x, y, vx, vy, speed, heading)  Simulators/SingleAircraftMCTSRandIntruderEnv.py:133-140 */
+      oi[6 * i] = px; oi[6 * i + 1] = py; oi[6 * i + 2] = vx; oi[6 * i + 3] = vy;
+      oi[6 * i + 4] = e->ihs ? e->ihs[2 * i + 1] : 0.0;
+      oi[6 * i + 5] = e->ihs ? e->ihs[2 * i] : 0.0;
+    } else if (raw) {
       oi[4 * i] = px; oi[4 * i + 1] = py; oi[4 * i + 2] = vx; oi[4 * i + 3] = vy;
     } else {
       if (e->is64[i]) {
@@ -294,7 +304,7 @@ static void observe_env(const env_view* e, double* obs, double* ag, double* dg) 
     oo[5] = e->own_hs[0] / (2 * 3.141592653589793);
   }
   if (!own_first) {
-    double* og = obs + 4 * e->n + 6;
+    double* og = obs + per * e->n + 6;
     og[0] = raw ? e->goal[0] : e->goal[0] / cfg->ob_window_width;
     og[1] = raw ? e->goal[1] : e->goal[1] / cfg->ob_window_height;
   } else if (kind == GCA_OBS_HER) {
@@ -407,12 +417,19 @@ static void terminal_reward(env_view* e, double* reward, uint8_t* done, uint8_t*
   int conflict = 0;
   for (int i = 0; i < e->n; ++i) {
     int is64 = e->is64[i];
+    float vx = e->ivel[2 * i], vy = e->ivel[2 * i + 1];
+    if (cfg->position_drift != 0.0) {
+      /* intruder.position += intruder.velocity + self.position_sigma: the f32 velocity array plus a Python float stays
+       * f32 (NumPy 2 weak scalars)  Simulators/SingleAircraftMCTSRandIntruderEnv.py:183 */
+      vx = vx + (float)cfg->position_drift;
+      vy = vy + (float)cfg->position_drift;
+    }
     if (is64) {
-      e->ipos[2 * i] = e->ipos[2 * i] + (double)e->ivel[2 * i];
-      e->ipos[2 * i + 1] = e->ipos[2 * i + 1] + (double)e->ivel[2 * i + 1];
+      e->ipos[2 * i] = e->ipos[2 * i] + (double)vx;
+      e->ipos[2 * i + 1] = e->ipos[2 * i + 1] + (double)vy;
     } else {
-      e->ipos[2 * i] = (double)((float)e->ipos[2 * i] + e->ivel[2 * i]);
-      e->ipos[2 * i + 1] = (double)((float)e->ipos[2 * i + 1] + e->ivel[2 * i + 1]);
+      e->ipos[2 * i] = (double)((float)e->ipos[2 * i] + vx);
+      e->ipos[2 * i + 1] = (double)((float)e->ipos[2 * i + 1] + vy);
     }
     double d = dist_intruder(e, i);
     if (!(dnear < d)) {            /* min(dist_intruder, self.dist_nearest_intruder): the first argument wins ties :191 */
@@ -466,6 +483,36 @@ static void terminal_reward(env_view* e, double* reward, uint8_t* done, uint8_t*
   *info = GCA_INFO_NONE;
 }
 
+/* _update_headings()  Simulators/SingleAircraftMCTSRandIntruderEnv.py:166-174 and Aircraft.change_heading :332-336:
+ * for every intruder of the CURRENT list (a respawned one included) p = np.random.uniform(); if p < .1 the heading
+ * moves by math.radians(np.random.uniform(-10, 10)) and the f32 velocity is rebuilt from (speed, heading).
+ * math.radians(x) is x * (pi / 180) in C doubles. */
+static void update_headings(env_view* e) {
+  const gca_config* cfg = e->cfg;
+  if (!e->ihs) return;
+  for (int i = 0; i < e->n; ++i) {
+    double p, raw;
+    if (e->draws == GCA_DRAWS_TAPE) {
+      p = tape_next(e);
+      if (!(p < cfg->turn_prob)) continue;
+      raw = tape_next(e);
+    } else {
+      double u[2];
+      gca_oracle_philox_uniform2(e->seed, e->env_id, e->tick, GCA_SLOT_TURN | (uint32_t)i, 0u, u);
+      p = u[0];
+      if (!(p < cfg->turn_prob)) continue;
+      raw = -cfg->turn_max_deg + (cfg->turn_max_deg - -cfg->turn_max_deg) * u[1];   /* numpy: low + (high - low) * u */
+    }
+    double s, c;
+    const double heading = e->ihs[2 * i] + raw * (3.141592653589793 / 180.0);
+    const double speed = e->ihs[2 * i + 1];
+    e->ihs[2 * i] = heading;
+    gca_oracle_sincos(heading, e->trig, &s, &c);
+    e->ivel[2 * i] = (float)(speed * c);
+    e->ivel[2 * i + 1] = (float)(speed * s);
+  }
+}
+
 static void bind(env_view* e, const gca_config* cfg, gca_oracle_batch* b, int i) {
   const int n = b->n_intr;
   e->cfg = cfg;
@@ -481,6 +528,7 @@ static void bind(env_view* e, const gca_config* cfg, gca_oracle_batch* b, int i)
   e->is64 = b->st.ipos_is_f64 + (size_t)i * n;
   e->ivel = b->st.ivel + 2 * (size_t)i * n;
   e->iflag = b->st.iflag + (size_t)i * n;
+  e->ihs = b->st.ihs ? b->st.ihs + 2 * (size_t)i * n : NULL;
   e->draws = b->draws;
   e->trig = b->trig;
   e->f32_positions = b->f32_positions;
@@ -504,6 +552,7 @@ int gca_oracle_step(const gca_config* cfg, gca_oracle_batch* b, const double* ac
     ownship_step(&e, actions + 2 * (size_t)i);
     terminal_reward(&e, &b->reward[i], &b->done[i], &b->info[i], b->nearest ? &b->nearest[i] : NULL);
     if (cfg->time_limit > 0 && *e.ep_steps >= cfg->time_limit) b->done[i] = 1;   /* gym TimeLimit (registered ids) */
+    if (cfg->intruder_turns) update_headings(&e);                        /* step(): after _terminal_reward, before _get_ob */
     observe_env(&e, row(b->obs, i, D), row(b->achieved, i, 2), row(b->desired, i, 2));
     if (b->term_obs && D) memcpy(row(b->term_obs, i, D), row(b->obs, i, D), sizeof(double) * D);
     if (b->auto_reset && b->done[i]) {                                   /* baselines dummy_vec_env.py:52-55 */
@@ -572,6 +621,7 @@ int gca_oracle_obs_dim(const gca_config* cfg, int n_intruders) {
     case GCA_OBS_HER:
     case GCA_OBS_DHER: return 4 * n_intruders + 6;
     case GCA_OBS_NEAREST: return 4 + 5 * cfg->nearest_n;
+    case GCA_OBS_RAW6: return 6 * n_intruders + 8;
     default: return 0;
   }
 }

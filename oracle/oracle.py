@@ -88,7 +88,7 @@ STATE_FIELDS = (("own_pos", np.float32, (2,)), ("own_hs", np.float64, (2,)), ("o
                 ("own_vel_is_f32", np.uint8, ()), ("goal", np.float64, (2,)), ("no_conflict", np.int32, ()),
                 ("ep_steps", np.int32, ()), ("tick", np.uint32, ()),
                 ("ipos", np.float64, ("N", 2)), ("ipos_is_f64", np.uint8, ("N",)), ("ivel", np.float32, ("N", 2)),
-                ("iflag", np.uint8, ("N",)))
+                ("iflag", np.uint8, ("N",)), ("ihs", np.float64, ("N", 2)))
 
 
 def empty_state(B, N):
@@ -134,6 +134,8 @@ class OracleEnv(object):
         b.n_envs, b.n_intr = self.B, self.N
         st = abi.GcaHostState()
         for name, _, _ in STATE_FIELDS:
+            if name == "ihs" and not self.cfg.intruder_turns:   # kept only by the variant whose intruders turn
+                continue
             setattr(st, name, _p(self.state[name]))
         b.st = st
         b.draws, b.trig = self.draws, self.trig

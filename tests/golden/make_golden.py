@@ -37,6 +37,7 @@ import SingleAircraftDiscrete9HEREnv as d9her_mod  # noqa: E402  (Simulators/, n
 import SingleAircraftDiscrete3HEREnv as d3her_mod  # noqa: E402  (Simulators/, + nearest-intruder reward term)
 import SingleAircraftEnv as simenv_mod  # noqa: E402  (Simulators/ copy: Config-driven rewards)
 import SingleAircraftRandomEnv as rndenv_mod  # noqa: E402  (Simulators/, random ownship start)
+import SingleAircraftMCTSRandIntruderEnv as mctsrnd_mod  # noqa: E402  (Simulators/, intruders that turn at random)
 import config as SimConfigMod  # noqa: E402
 import nodes_single  # noqa: E402
 import search_single  # noqa: E402
@@ -92,6 +93,7 @@ def snapshot(env, n):
         "ipos_is_f64": np.zeros((n,), np.uint8),
         "ivel": np.zeros((n, 2), np.float32),
         "iflag": np.zeros((n,), np.uint8),
+        "ihs": np.zeros((n, 2), np.float64),        # Aircraft.heading, Aircraft.speed (SingleAircraftMCTSRandIntruderEnv)
     }
     assert d.position.dtype == np.float32
     for i, it in enumerate(env.intruder_list):
@@ -100,12 +102,14 @@ def snapshot(env, n):
         assert it.velocity.dtype == np.float32
         st["ivel"][i] = it.velocity
         st["iflag"][i] = bool(it.conflict)
+        if hasattr(it, "change_heading"):            # only the random-intruder env keeps using them after __init__
+            st["ihs"][i] = (it.heading, it.speed)
     return st
 
 
 def snapshot_keys():
     return ("own_pos", "own_pos_dtype_is_f32", "own_vel", "own_vel_is_f32", "own_heading", "own_speed", "goal",
-            "no_conflict", "steps", "ipos", "ipos_is_f64", "ivel", "iflag")
+            "no_conflict", "steps", "ipos", "ipos_is_f64", "ivel", "iflag", "ihs")
 
 
 def obs_arrays(variant, ob):
@@ -180,9 +184,10 @@ VARIANTS = {
     "d3her": (d3her_mod.SingleAircraftDiscrete3HEREnv, SimConfigMod.Config, "d3"),
     "simenv": (simenv_mod.SingleAircraftEnv, SimConfigMod.Config, "d9"),
     "rndenv": (rndenv_mod.SingleAircraftRandomEnv, SimConfigMod.Config, "d9"),
+    "mctsrnd": (mctsrnd_mod.SingleAircraftEnv, SimConfigMod.Config, "t33"),
 }
 # np.argpartition(dist_array, Config.n) of the nearest-n observation needs more than n = 4 intruders
-PLANS = {"simenv": {3: (3, 40), 80: (2, 25)}, "rndenv": {3: (3, 40), 80: (2, 25)}, "d9her": {5: (5, 40), 12: (5, 40), 80: (3, 30)}, "d3her": {5: (5, 40), 12: (5, 40), 80: (3, 30)}}
+PLANS = {"mctsrnd": {1: (4, 40), 3: (5, 40), 80: (3, 30)}, "simenv": {3: (3, 40), 80: (2, 25)}, "rndenv": {3: (3, 40), 80: (2, 25)}, "d9her": {5: (5, 40), 12: (5, 40), 80: (3, 30)}, "d3her": {5: (5, 40), 12: (5, 40), 80: (3, 30)}}
 
 
 def sample_action(kind, rng):

@@ -8,20 +8,22 @@ from gca_b200 import variants
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 STATE_KEYS = ("own_pos", "own_hs", "own_vel", "own_vel_is_f32", "goal", "no_conflict", "ep_steps", "ipos",
-              "ipos_is_f64", "ivel", "iflag")
+              "ipos_is_f64", "ivel", "iflag", "ihs")
 GOLDEN_VARIANTS = {"env": "SingleAircraftEnv", "env2": "SingleAircraft2Env", "her": "SingleAircraftHEREnv",
                    "dher": "SingleAircraftDiscreteHEREnv", "mcts": "SingleAircraftMCTSEnv",
                    "d9her": "SingleAircraftDiscrete9HEREnv", "d3her": "SingleAircraftDiscrete3HEREnv",
-                   "simenv": "SimSingleAircraftEnv", "rndenv": "SingleAircraftRandomEnv"}
+                   "simenv": "SimSingleAircraftEnv", "rndenv": "SingleAircraftRandomEnv",
+                   "mctsrnd": "SingleAircraftMCTSRandIntruderEnv"}
 GOLDEN_N = (0, 1, 3, 80)
-GOLDEN_N_BY_VARIANT = {"d9her": (5, 12, 80), "d3her": (5, 12, 80), "simenv": (3, 80), "rndenv": (3, 80)}     # the nearest-n observation needs more than Config.n = 4 intruders
+GOLDEN_N_BY_VARIANT = {"d9her": (5, 12, 80), "d3her": (5, 12, 80), "simenv": (3, 80), "rndenv": (3, 80),
+                       "mctsrnd": (1, 3, 80)}     # the nearest-n observation needs more than Config.n = 4 intruders
 # every (variant key, N) with a recorded trace file
 GOLDEN_CASES = [(vk, n) for vk in sorted(GOLDEN_VARIANTS) for n in GOLDEN_N_BY_VARIANT.get(vk, GOLDEN_N)]
 GOAL_VARIANTS = ("her", "dher", "d9her", "d3her")          # dict observation: achieved / desired goal outputs
 
 
 def config_class(variant_key):
-    if variant_key in ("mcts", "d9her", "d3her", "simenv", "rndenv"):
+    if variant_key in ("mcts", "d9her", "d3her", "simenv", "rndenv", "mctsrnd"):
         from Simulators.config import Config
     else:
         from gym_guidance_collision_avoidance_single.envs.config import Config
@@ -54,6 +56,9 @@ def golden_state(g, prefix, sel=None):
         "ivel": get("ivel").astype(np.float32),
         "iflag": get("iflag").astype(np.uint8),
     }
+    # intruder (heading, speed): state only of the variant whose intruders turn (recorded as zeros elsewhere; absent
+    # from the trace files made before that variant existed)
+    st["ihs"] = get("ihs").astype(np.float64) if prefix + "ihs" in g.files else np.zeros(st["ipos"].shape, np.float64)
     return {k: np.ascontiguousarray(v) for k, v in st.items()}
 
 
@@ -75,7 +80,7 @@ def golden_actions(variant_key, g):
     """[traces][T][2] action array of a golden file in the form the batched API takes:
     int codes in column 0 for the discrete kinds (the MCTS env's (a0, a1) tuple is a0*3+a1)."""
     a = np.array(g["actions"], np.float64)
-    if variant_key == "mcts":
+    if variant_key in ("mcts", "mctsrnd"):
         a[..., 0] = a[..., 0] * 3 + a[..., 1]
         a[..., 1] = 0
     return a
