@@ -358,6 +358,7 @@ def main_gpu(args):
             line["her"] = bench_her(local)
             line["stack"] = bench_stack(local)
             line["d9her"] = bench_d9her(local)
+            line["mctsrnd"] = bench_mctsrnd(local)
             line["her_replay"] = bench_her_replay(local)
             line["n0"] = bench_n0(local)
             line["faithful"] = bench_faithful(local)
@@ -547,6 +548,33 @@ def bench_d9her(device):
     env3.close()
     out["d3her"] = {"value": B / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3}
     return out
+
+
+def bench_mctsrnd(device):
+    """Simulators/SingleAircraftMCTSRandIntruderEnv (intruders that turn at random after every step,
+    per-step drift, six raw entries per intruder).  5 kernels per step: the turn / observation pass runs behind the
+    spawn kernel on the final intruder set, one lane per (env, intruder).  Algorithmic bytes per env-step: per intruder
+    24 (position r/w, velocity r) in the streaming pass + 8 + 8 + 16 (position, velocity, heading / speed read again)
+    + 24 (six f32 entries written) = 80, plus the per-env scalars."""
+    import torch
+    from gca_b200.batched import BatchedAircraftEnv
+    from Simulators.config import Config as SimConfig
+    B, N = ENVS_PER_GPU, N_INTRUDERS
+    env = BatchedAircraftEnv("SingleAircraftMCTSRandIntruderEnv", B, SimConfig, n_intruders=N, mode="fast",
+                             draws="philox", device=device, seed=8)
+    env.reset()
+    acts = [torch.randint(0, 9, (B,), device="cuda", dtype=torch.int32) for _ in range(GRAPH_STEPS)]
+    for i in range(5):
+        env.step(acts[i])
+    ms = graph_step_ms(lambda i: env.step(acts[i]), GRAPH_STEPS)
+    k = env.kernels_per_step
+    env.close()
+    peak, _ = measured_peaks()
+    bytes_per_env_step = 80 * N + 122
+    gbs = bytes_per_env_step * B / (ms * 1e-3) / 1e9
+    return {"metric": METRIC, "value": B / (ms * 1e-3), "unit": UNIT, "envs": B, "intruders": N, "ms_per_step": ms,
+            "kernels_per_step": k, "obs_dim": 6 * N + 8, "bytes_per_env_step": bytes_per_env_step,
+            "hbm_frac": gbs / peak, "note": "CUDA graph of %d steps replayed" % GRAPH_STEPS}
 
 
 def bench_her_replay(device):

@@ -60,7 +60,9 @@ size_t real_size(const gca_env* e) { return e->mode == GCA_MODE_FAITHFUL ? sizeo
 int check_config(const gca_config* c) {
   if (!c) return fail(GCA_ERR_INVALID, "config is NULL");
   if (c->action_kind < GCA_ACT_DISCRETE9 || c->action_kind > GCA_ACT_DISCRETE3_HEADING) return fail(GCA_ERR_INVALID, "bad action_kind");
-  if (c->obs_kind < GCA_OBS_VECTOR || c->obs_kind > GCA_OBS_NEAREST) return fail(GCA_ERR_INVALID, "bad obs_kind");
+  if (c->obs_kind < GCA_OBS_VECTOR || c->obs_kind > GCA_OBS_RAW6) return fail(GCA_ERR_INVALID, "bad obs_kind");
+  if (c->intruder_turns && !(c->turn_prob >= 0.0 && c->turn_prob <= 1.0 && c->turn_max_deg >= 0.0))
+    return fail(GCA_ERR_INVALID, "intruder_turns needs 0 <= turn_prob <= 1 and turn_max_deg >= 0");
   if (c->obs_kind == GCA_OBS_NEAREST && (c->nearest_n < 1 || c->nearest_n > 8 || !(c->ob_diagonal > 0)))
     return fail(GCA_ERR_INVALID, "GCA_OBS_NEAREST needs 1 <= nearest_n <= 8 and a positive ob_diagonal");
   if (c->wall_kind < GCA_WALL_NONE || c->wall_kind > GCA_WALL_PENALTY) return fail(GCA_ERR_INVALID, "bad wall_kind");
@@ -129,8 +131,12 @@ Derived derive(const gca_config& c) {
   k.rc_2pi = 1.0 / k.dv_2pi; k.rc_vel = 1.0 / k.dv_vel; k.rc_shape = 1.0 / k.dv_shape;
   k.ddiv_ok = gca_div_f64_divisor_ok(k.dv_w) && gca_div_f64_divisor_ok(k.dv_h) && gca_div_f64_divisor_ok(k.dv_speed) &&
               gca_div_f64_divisor_ok(k.dv_2pi) && gca_div_f64_divisor_ok(k.dv_vel) && gca_div_f64_divisor_ok(k.dv_shape);
+  k.drift_f = (float)c.position_drift;
+  k.has_drift = c.position_drift != 0.0 ? 1 : 0;
   return k;
 }
+
+bool keeps_ihs(const gca_config& c) { return c.intruder_turns != 0 || c.obs_kind == GCA_OBS_RAW6; }
 
 StepArgs make_args(const gca_env* e, const void* actions, const gca_tape* tape, const gca_out* out, int auto_reset) {
   StepArgs a{};
@@ -176,7 +182,12 @@ struct HostPlanes {
   std::vector<uint8_t> pos, vel;      // pos: both planes
   std::vector<uint32_t> cf, df;
   std::vector<int4> cnt;
+  std::vector<double2> hs;            // (heading, speed) plane, handles that keep it
   int download(const DevState& s, bool faith) {
+    if (s.ihs) {
+      hs.resize((size_t)s.T * (size_t)s.N * 32);
+      GCA_CUDA(cudaMemcpy(hs.data(), s.ihs, hs.size() * sizeof(double2), cudaMemcpyDeviceToHost));
+    }
     pos.resize(2 * s.pos_plane);
     vel.resize(vel_plane_bytes(s));
     cf.resize(flag_plane_words(s));
@@ -190,6 +201,7 @@ struct HostPlanes {
     return GCA_OK;
   }
   int upload(const DevState& s, bool faith) {
+    if (s.ihs) GCA_CUDA(cudaMemcpy(s.ihs, hs.data(), hs.size() * sizeof(double2), cudaMemcpyHostToDevice));
     GCA_CUDA(cudaMemcpy(s.ipos, pos.data(), pos.size(), cudaMemcpyHostToDevice));
     GCA_CUDA(cudaMemcpy(s.ivel, vel.data(), vel.size(), cudaMemcpyHostToDevice));
     GCA_CUDA(cudaMemcpy(s.cflag, cf.data(), cf.size() * 4, cudaMemcpyHostToDevice));
@@ -216,6 +228,7 @@ int gca_obs_dim(const gca_config* cfg, int n) {
     case GCA_OBS_HER:
     case GCA_OBS_DHER: return 4 * n + 6;
     case GCA_OBS_NEAREST: return 4 + 5 * cfg->nearest_n;
+    case GCA_OBS_RAW6: return 6 * n + 8;
     default: return 0;
   }
 }
@@ -266,6 +279,7 @@ int gca_create(const gca_config* cfg, int n_envs, int n_intruders, int mode, int
   if (!rc) rc = dev_alloc(e, &s.ivel, vel_plane_bytes(s));
   if (!rc) rc = dev_alloc(e, &s.cflag, flag_plane_words(s));
   if (!rc) rc = dev_alloc(e, &s.dflag, mode == GCA_MODE_FAITHFUL ? flag_plane_words(s) : 1);
+  if (!rc && keeps_ihs(*cfg) && n_intruders > 0) rc = dev_alloc(e, &s.ihs, (size_t)s.T * (size_t)s.N * 32);
   if (rc) {
     gca_destroy(e);
     return rc;
@@ -295,6 +309,8 @@ int gca_set_config(gca_env* e, const gca_config* cfg) {
   if (!e) return fail(GCA_ERR_INVALID, "env is NULL");
   if (int rc = check_config(cfg)) return rc;
   if (gca_obs_dim(cfg, e->s.N) != e->D) return fail(GCA_ERR_STATE, "obs_kind change would alter the observation size");
+  if (keeps_ihs(*cfg) && !e->s.ihs && e->s.N > 0)
+    return fail(GCA_ERR_STATE, "the handle was created without per-intruder (heading, speed) state");
   e->cfg = *cfg;
   e->k = derive(*cfg);
   return GCA_OK;
@@ -338,7 +354,7 @@ int gca_step(gca_env* e, const void* actions, const gca_tape* tape, int auto_res
 
 int gca_step_launches(gca_env* e) {
   if (!e) return fail(GCA_ERR_INVALID, "env is NULL");
-  return step_launch_count(e->draws == GCA_DRAWS_TAPE, e->s.N, e->cfg.obs_kind);
+  return step_launch_count(e->draws == GCA_DRAWS_TAPE, e->s.N, e->cfg.obs_kind, e->cfg.intruder_turns && e->s.ihs);
 }
 
 int gca_profile_enable(gca_env* e, int on) {
@@ -453,7 +469,7 @@ int gca_get_state(gca_env* e, const gca_host_state* h) {
       if (h->tick) h->tick[b] = (uint32_t)c[b].z;
     }
   }
-  if (N == 0 || !(h->ipos || h->ivel || h->iflag || h->ipos_is_f64)) return GCA_OK;
+  if (N == 0 || !(h->ipos || h->ivel || h->iflag || h->ipos_is_f64 || h->ihs)) return GCA_OK;
   const bool faith = e->mode == GCA_MODE_FAITHFUL;
   HostPlanes hp;
   if (int rc = hp.download(s, faith)) return rc;
@@ -476,6 +492,10 @@ int gca_get_state(gca_env* e, const gca_host_state* h) {
       const size_t fi = flag_index(s, b, (int)(i / 32));
       if (h->iflag) h->iflag[k] = (hp.cf[fi] >> (i % 32)) & 1u;
       if (h->ipos_is_f64) h->ipos_is_f64[k] = faith ? ((hp.df[fi] >> (i % 32)) & 1u) : 0;
+      if (h->ihs) {
+        const double2 v = s.ihs ? hp.hs[ihs_index(s, b, (int)i)] : make_double2(0.0, 0.0);
+        h->ihs[2 * k] = v.x; h->ihs[2 * k + 1] = v.y;
+      }
     }
   }
   return GCA_OK;
@@ -524,6 +544,7 @@ int gca_set_state(gca_env* e, const gca_host_state* h) {
       const size_t fi = flag_index(s, b, (int)(i / 32));
       if (h->iflag && h->iflag[k]) hp.cf[fi] |= 1u << (i % 32);
       if (h->ipos_is_f64 && faith && h->ipos_is_f64[k]) hp.df[fi] |= 1u << (i % 32);
+      if (h->ihs && s.ihs) hp.hs[ihs_index(s, b, (int)i)] = make_double2(h->ihs[2 * k], h->ihs[2 * k + 1]);
     }
   }
   return hp.upload(s, faith);

@@ -45,6 +45,8 @@ struct DevState {
   uint8_t* ivel;          // [T][U][32] float4
   uint32_t* cflag;        // [T][Wd][32]
   uint32_t* dflag;        // [T][Wd][32]  (FAITHFUL)
+  double2* ihs;           // [T][N][32] (heading, speed) of every intruder - only handles whose intruders turn or whose
+                          // observation shows them keep it (Simulators/SingleAircraftMCTSRandIntruderEnv.py), else nullptr
   // hand-over between the three kernels of a step
   float4* own_b;          // [T*32] (own x, own y, bits: 1 = the intruder loop runs, 2 = plane parity, -)
   uint32_t* ev_conf;      // [T][Wd][32] bit i: intruder i is inside the separation radius after its advance
@@ -85,6 +87,10 @@ __host__ __device__ inline size_t ivel_offset(const DevState& s, size_t env, int
   const size_t t = env >> 5, e = env & 31;
   return ((t * (size_t)s.U + (size_t)(i >> 1)) * 32 + e) * 16 + (size_t)(i & 1) * 8;
 }
+__host__ __device__ inline size_t ihs_index(const DevState& s, size_t env, int i) {
+  const size_t t = env >> 5, e = env & 31;
+  return (t * (size_t)s.N + (size_t)i) * 32 + e;
+}
 __host__ __device__ inline size_t flag_index(const DevState& s, size_t env, int w) {
   const size_t t = env >> 5, e = env & 31;
   return (t * (size_t)s.Wd + (size_t)w) * 32 + e;
@@ -104,6 +110,8 @@ struct Derived {
   double dv_w, dv_h, dv_speed, dv_2pi, dv_vel, dv_shape;       // window w/h, max-min speed, 2*pi, 2*max_speed, 1200
   double rc_w, rc_h, rc_speed, rc_2pi, rc_vel, rc_shape;
   int ddiv_ok;                        // all six divisors qualify (gca_div_f64_divisor_ok)
+  float drift_f;                      // f32(position_drift), added to the f32 velocity of every advance
+  int has_drift;                      // position_drift != 0
 };
 
 // x / d in f64, correctly rounded, for the host-prepared divisors of Derived
@@ -305,12 +313,14 @@ __device__ __forceinline__ bool in_map_f64(const Derived& k, double x, double y)
 template <bool FAITH>
 struct Intr {
   float px, py, vx, vy;
+  double heading, speed;             // set by spawn() only (Aircraft.heading / .speed)
   static constexpr bool is64 = false;
 };
 template <>
 struct Intr<true> {
   double px, py;
   float vx, vy;
+  double heading, speed;             // set by spawn() only
   bool is64;
 };
 
@@ -345,22 +355,32 @@ __device__ __forceinline__ void store_ivel(const DevState& s, size_t env, int i,
   *reinterpret_cast<float2*>(s.ivel + ivel_offset(s, env, i)) = make_float2(vx, vy);
 }
 
-// intruder.position += intruder.velocity   PKG/SingleAircraftEnv.py:150, and the map test :153
+// the spawn's (heading, speed) for the handles that keep them
+template <bool FAITH>
+__device__ __forceinline__ void store_ihs(const DevState& s, size_t env, int i, const Intr<FAITH>& it) {
+  if (s.ihs) s.ihs[ihs_index(s, env, i)] = make_double2(it.heading, it.speed);
+}
+
+// intruder.position += intruder.velocity   PKG/SingleAircraftEnv.py:150, and the map test :153;
+// `+= intruder.velocity + self.position_sigma` (f32 array + Python float: an f32 sum) with a position drift
+// (Simulators/SingleAircraftMCTSRandIntruderEnv.py:183)
 template <bool FAITH>
 __device__ __forceinline__ bool advance(const Derived& k, Intr<FAITH>& it) {
+  const float vx = k.has_drift ? __fadd_rn(it.vx, k.drift_f) : it.vx;
+  const float vy = k.has_drift ? __fadd_rn(it.vy, k.drift_f) : it.vy;
   if constexpr (FAITH) {
     if (it.is64) {                                       // f64 + f32 -> f64
-      it.px = __dadd_rn(it.px, (double)it.vx);
-      it.py = __dadd_rn(it.py, (double)it.vy);
+      it.px = __dadd_rn(it.px, (double)vx);
+      it.py = __dadd_rn(it.py, (double)vy);
       return !in_map_f64(k, it.px, it.py);
     }
-    const float fx = __fadd_rn((float)it.px, it.vx), fy = __fadd_rn((float)it.py, it.vy);
+    const float fx = __fadd_rn((float)it.px, vx), fy = __fadd_rn((float)it.py, vy);
     it.px = (double)fx;
     it.py = (double)fy;
     return !in_map_f32(k, fx, fy);
   } else {
-    it.px = __fadd_rn(it.px, it.vx);
-    it.py = __fadd_rn(it.py, it.vy);
+    it.px = __fadd_rn(it.px, vx);
+    it.py = __fadd_rn(it.py, vy);
     return !in_map_f32(k, it.px, it.py);
   }
 }
@@ -398,6 +418,8 @@ __device__ __forceinline__ void spawn(Draws<TAPE>& d, const gca_config& c, const
   gca_sincos(heading, &sn, &cs);
   it.vx = (float)__dmul_rn(speed, cs);
   it.vy = (float)__dmul_rn(speed, sn);
+  it.heading = heading;
+  it.speed = speed;
   int retries = 0;
   for (;;) {
     bool a, b, lt_init;
@@ -464,7 +486,7 @@ __device__ __forceinline__ void write_obs_intruder(const StepArgs& a, real_t<FAI
   using R = real_t<FAITH>;
   const gca_config& c = a.cfg;
   const Derived& k = a.k;
-  if (c.obs_kind == GCA_OBS_NONE || c.obs_kind == GCA_OBS_NEAREST) return;   // (NEAREST: nearest_obs_kernel)
+  if (c.obs_kind == GCA_OBS_NONE || c.obs_kind == GCA_OBS_NEAREST || c.obs_kind == GCA_OBS_RAW6) return;   // (NEAREST: nearest_obs_kernel, RAW6: turn_obs_kernel)
   R o0, o1, o2, o3;
   if (c.obs_kind == GCA_OBS_RAW) {
     o0 = (R)it.px; o1 = (R)it.py; o2 = (R)it.vx; o3 = (R)it.vy;
@@ -521,8 +543,8 @@ __device__ __forceinline__ void write_obs_own(const StepArgs& a, size_t env, flo
   if (c.obs_kind == GCA_OBS_NONE || c.obs_kind == GCA_OBS_NEAREST) return;
   const bool of = own_first(c);
   R* row = reinterpret_cast<R*>(a.obs) + env * (size_t)a.D;
-  R* o = row + (of ? 0 : 4 * (size_t)a.s.N);
-  if (c.obs_kind == GCA_OBS_RAW) {
+  R* o = row + (of ? 0 : (c.obs_kind == GCA_OBS_RAW6 ? 6 : 4) * (size_t)a.s.N);
+  if (c.obs_kind == GCA_OBS_RAW || c.obs_kind == GCA_OBS_RAW6) {
     o[0] = (R)px; o[1] = (R)py; o[2] = (R)vx; o[3] = (R)vy; o[4] = (R)speed; o[5] = (R)heading;
     o[6] = (R)gx; o[7] = (R)gy;
     return;

@@ -6,7 +6,7 @@
 
 namespace gca {
 cudaError_t launch_step(bool faith, bool tape, const StepArgs& a, cudaStream_t st, cudaEvent_t* ev);
-int step_launch_count(bool tape, int n_intruders, int obs_kind);
+int step_launch_count(bool tape, int n_intruders, int obs_kind, bool turns);
 cudaError_t launch_reset(bool faith, bool tape, const StepArgs& a, cudaStream_t st);
 cudaError_t launch_observe(bool faith, const StepArgs& a, cudaStream_t st);
 cudaError_t launch_compute_reward(const void* ag, const void* g, long long m, double radius, int kind, int is_f64,

@@ -109,6 +109,7 @@ __device__ __forceinline__ void reset_env_warp(const StepArgs& a, size_t env, in
           spawn<FAITH, TAPE>(d, c, k, GCA_SLOT_RESET | (uint32_t)i, ox, oy, it);
           store_ipos<FAITH>(s, plane, env, i, it);
           store_ivel(s, env, i, it.vx, it.vy);
+          store_ihs<FAITH>(s, env, i, it);
           dw |= (it.is64 ? 1u : 0u) << j;
           write_obs_intruder<FAITH>(a, obase, i, it);
         }
@@ -127,6 +128,7 @@ __device__ __forceinline__ void reset_env_warp(const StepArgs& a, size_t env, in
         spawn<FAITH, TAPE>(d, c, k, GCA_SLOT_RESET | (uint32_t)i, ox, oy, it);
         store_ipos<FAITH>(s, plane, env, i, it);
         store_ivel(s, env, i, it.vx, it.vy);
+        store_ihs<FAITH>(s, env, i, it);
         write_obs_intruder<FAITH>(a, obase, i, it);
         wide = it.is64;
       }
@@ -318,6 +320,7 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
     spawn<FAITH, TAPE>(d, c, k, (uint32_t)i, pos.x, pos.y, it);
     store_ipos<FAITH>(s, nxt, me, i, it);
     store_ivel(s, me, i, it.vx, it.vy);
+    store_ihs<FAITH>(s, me, i, it);
     set64 |= (it.is64 ? 1u : 0u) << (i & 31);
     write_obs_intruder<FAITH>(a, obase, i, it);
   };
@@ -503,6 +506,24 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
       }
     }
   }
+  if constexpr (TAPE) {
+    // _update_headings() (Simulators/SingleAircraftMCTSRandIntruderEnv.py:166-174): step() runs it after
+    // _terminal_reward whatever that returned, on the current intruder list, in index order - on the tape its draws
+    // sit between the loop's respawns and the VecEnv reset's.  (PHILOX: turn_obs_kernel, one lane per intruder.)
+    if (c.intruder_turns && has_env && s.ihs) {
+      for (int i = 0; i < s.N; ++i) {
+        const double p = d.next();
+        if (!(p < c.turn_prob)) continue;
+        const double raw = d.next();                                // np.random.uniform(-10, 10) as recorded
+        double2 ih = s.ihs[ihs_index(s, me, i)];
+        double sn, cs;
+        ih.x = __dadd_rn(ih.x, __dmul_rn(raw, 3.141592653589793 / 180.0));   // math.radians
+        gca_sincos(ih.x, &sn, &cs);
+        s.ihs[ihs_index(s, me, i)] = ih;
+        store_ivel(s, me, i, (float)__dmul_rn(ih.y, cs), (float)__dmul_rn(ih.y, sn));
+      }
+    }
+  }
 #ifdef GCA_PHASE_TIMING
   fin_t3 = gtime();
 #endif
@@ -597,6 +618,7 @@ __global__ void __launch_bounds__(128) spawn_kernel(const __grid_constant__ Step
           spawn<FAITH, false>(d, a.cfg, a.k, (uint32_t)i, own.x, own.y, it);
           store_ipos<FAITH>(s, cnt.z & 1, env, i, it);
           store_ivel(s, env, i, it.vx, it.vy);
+          store_ihs<FAITH>(s, env, i, it);
           write_obs_intruder<FAITH>(a, obs_intruder_base<FAITH>(a, env), i, it);
           if constexpr (FAITH) {
             if (it.is64) atomicOr(&s.dflag[flag_index(s, env, i >> 5)], 1u << (i & 31));
@@ -618,6 +640,7 @@ __global__ void __launch_bounds__(128) spawn_kernel(const __grid_constant__ Step
         spawn<FAITH, false>(d, a.cfg, a.k, GCA_SLOT_RESET | (uint32_t)i, own.x, own.y, it);
         store_ipos<FAITH>(s, cnt.z & 1, env, i, it);
         store_ivel(s, env, i, it.vx, it.vy);
+        store_ihs<FAITH>(s, env, i, it);
         write_obs_intruder<FAITH>(a, obs_intruder_base<FAITH>(a, env), i, it);
         wide = it.is64;
       }
@@ -703,8 +726,13 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
       const uint32_t wbits = __float_as_uint(k.win_w), hbits = __float_as_uint(k.win_h);
 #pragma unroll
       for (int g = 0; g < kChunkUnits; ++g) {
-        np[g] = make_float4(__fadd_rn(p[g].x, vv[g].x), __fadd_rn(p[g].y, vv[g].y),      // position += velocity :150
-                            __fadd_rn(p[g].z, vv[g].z), __fadd_rn(p[g].w, vv[g].w));
+        float4 dv = vv[g];
+        if constexpr (OM == 0) {                            // (a handle with a position drift never takes the specialised paths)
+          if (k.has_drift) dv = make_float4(__fadd_rn(dv.x, k.drift_f), __fadd_rn(dv.y, k.drift_f),
+                                            __fadd_rn(dv.z, k.drift_f), __fadd_rn(dv.w, k.drift_f));
+        }
+        np[g] = make_float4(__fadd_rn(p[g].x, dv.x), __fadd_rn(p[g].y, dv.y),      // position += velocity :150
+                            __fadd_rn(p[g].z, dv.z), __fadd_rn(p[g].w, dv.w));
         // 0 <= x <= W on f32 bit patterns (:153): a non-negative float is <= W iff its pattern is (as unsigned);
         // negatives and NaN have larger patterns (FAST positions are never -0.0, see gca_set_state).
         const bool oob0 = (__float_as_uint(np[g].x) > wbits) | (__float_as_uint(np[g].y) > hbits);
@@ -772,7 +800,7 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
       // write-out - 16 consecutive lanes store the 256 contiguous bytes of ONE env's row, whole 32-byte sectors
       // (a lane storing its own 16-byte pieces 2 624 bytes apart touched 32 half-used sectors per instruction)
       fast_done = true;
-      const bool stage = a.cfg.obs_kind != GCA_OBS_NONE && a.cfg.obs_kind != GCA_OBS_NEAREST;
+      const bool stage = a.cfg.obs_kind != GCA_OBS_NONE && a.cfg.obs_kind != GCA_OBS_NEAREST && a.cfg.obs_kind != GCA_OBS_RAW6;
       double2 pq[kChunkIntr];
       float4 vq[kChunkUnits];
 #pragma unroll
@@ -954,6 +982,68 @@ __global__ void __launch_bounds__(128) nearest_obs_kernel(const __grid_constant_
   else write_obs_nearest<FAITH, 8>(a, valid ? me : (size_t)a.s.B - 1, (int)(t & 3), valid);
 }
 
+// Simulators/SingleAircraftMCTSRandIntruderEnv.py: _update_headings (:166-174, TURN) and the six raw entries per intruder
+// of _get_ob (:133-140).  Both need the FINAL intruder set of the step (after respawns / resets), so this is a pass of
+// its own behind spawn_kernel, like nearest_obs_kernel.  warp = one intruder of the 32 envs of a tile, lane = env:
+// plane reads are the tile-planar lines.  A turn depends on (env, tick, intruder) only (Philox slot GCA_SLOT_TURN).
+// TAPE handles replay the turns inside finish_tile (draw order) and run this pass with TURN = false.
+template <bool FAITH, bool TURN>
+__global__ void __launch_bounds__(128) turn_obs_kernel(const __grid_constant__ StepArgs a) {
+  pdl_wait();
+  using R = real_t<FAITH>;
+  const DevState& s = a.s;
+  const gca_config& c = a.cfg;
+  const int lane = threadIdx.x & 31;
+  const int per_tile = (s.N + 3) / 4;
+  const int tile = (int)(blockIdx.x / per_tile);
+  const int i = (int)(blockIdx.x % per_tile) * 4 + (threadIdx.x >> 5);
+  const size_t me = (size_t)tile * 32 + lane;
+  if (i >= s.N || me >= (size_t)s.B) return;
+  const int4 cnt = s.counters[me];
+  Intr<FAITH> it;
+  load_intruder<FAITH>(s, cnt.z & 1, me, i, it);
+  double2 ih = s.ihs ? s.ihs[ihs_index(s, me, i)] : make_double2(0.0, 0.0);
+  if constexpr (TURN) {
+    // ep_steps == 0 after a step: the env finished and was reset (auto-reset) - the turns of its old intruders are moot
+    if (c.intruder_turns && s.ihs && !(a.auto_reset && cnt.y == 0)) {
+      Draws<false> d;
+      d.k0 = a.key0; d.k1 = a.key1;
+      d.env = a.env_id0 + (uint32_t)me;
+      d.tick = (uint32_t)cnt.z - 1u;                        // the tick of the step that just ran
+      double p, u;
+      d.uniform2(GCA_SLOT_TURN | (uint32_t)i, 0u, p, u);
+      if (p < c.turn_prob) {
+        // math.radians(np.random.uniform(-10, 10)): low + (high - low) * u, then * (pi / 180)
+        const double raw = __dadd_rn(-c.turn_max_deg, __dmul_rn(__dadd_rn(c.turn_max_deg, c.turn_max_deg), u));
+        double sn, cs;
+        ih.x = __dadd_rn(ih.x, __dmul_rn(raw, 3.141592653589793 / 180.0));
+        gca_sincos(ih.x, &sn, &cs);
+        it.vx = (float)__dmul_rn(ih.y, cs);                 // change_heading :332-336
+        it.vy = (float)__dmul_rn(ih.y, sn);
+        s.ihs[ihs_index(s, me, i)] = ih;
+        store_ivel(s, me, i, it.vx, it.vy);
+      }
+    }
+  }
+  if (c.obs_kind == GCA_OBS_RAW6) {
+    R* o = reinterpret_cast<R*>(a.obs) + me * (size_t)a.D + 6 * (size_t)i;
+    if constexpr (FAITH) {
+      reinterpret_cast<double2*>(o)[0] = make_double2(it.px, it.py);
+      reinterpret_cast<double2*>(o)[1] = make_double2((double)it.vx, (double)it.vy);
+      reinterpret_cast<double2*>(o)[2] = make_double2(ih.y, ih.x);
+    } else {
+      reinterpret_cast<float2*>(o)[0] = make_float2(it.px, it.py);
+      reinterpret_cast<float2*>(o)[1] = make_float2(it.vx, it.vy);
+      reinterpret_cast<float2*>(o)[2] = make_float2((float)ih.y, (float)ih.x);
+    }
+  }
+}
+
+static bool has_turn_pass(const StepArgs& a) {
+  return a.s.N > 0 && (a.cfg.obs_kind == GCA_OBS_RAW6 || (a.cfg.intruder_turns && a.s.ihs));
+}
+static unsigned turn_blocks(const DevState& s) { return (unsigned)((size_t)s.T * (size_t)((s.N + 3) / 4)); }
+
 // ------------------------------------------------------------------------------ launchers
 // launch with programmatic stream serialization (see pdl_wait above)
 template <typename... KArgs, typename... Args>
@@ -996,8 +1086,9 @@ static cudaError_t launch_step_t(const StepArgs& a, cudaStream_t st, cudaEvent_t
       launch_pdl(step_intruders_kernel<true, 0>, blocks, kWarpsB * 32, st, a);
     } else {
       const bool own_first = a.cfg.obs_kind == GCA_OBS_HER || a.cfg.obs_kind == GCA_OBS_DHER;
-      if (a.k.div1_ok && a.cfg.obs_kind == GCA_OBS_VECTOR) launch_pdl(step_intruders_kernel<false, 1>, blocks, kWarpsB * 32, st, a);
-      else if (a.k.div1_ok && own_first) launch_pdl(step_intruders_kernel<false, 2>, blocks, kWarpsB * 32, st, a);
+      const bool special = a.k.div1_ok && !a.k.has_drift;
+      if (special && a.cfg.obs_kind == GCA_OBS_VECTOR) launch_pdl(step_intruders_kernel<false, 1>, blocks, kWarpsB * 32, st, a);
+      else if (special && own_first) launch_pdl(step_intruders_kernel<false, 2>, blocks, kWarpsB * 32, st, a);
       else launch_pdl(step_intruders_kernel<false, 0>, blocks, kWarpsB * 32, st, a);
     }
   }
@@ -1013,6 +1104,7 @@ static cudaError_t launch_step_t(const StepArgs& a, cudaStream_t st, cudaEvent_t
   }
   if (a.cfg.obs_kind == GCA_OBS_NEAREST)
     launch_pdl(nearest_obs_kernel<FAITH>, (unsigned)(((size_t)s.B + 31) / 32), 128, st, a);
+  if (has_turn_pass(a)) launch_pdl(turn_obs_kernel<FAITH, !TAPE>, turn_blocks(s), 128, st, a);
   mark(4);
   return cudaGetLastError();
 }
@@ -1023,8 +1115,9 @@ cudaError_t launch_step(bool faith, bool tape, const StepArgs& a, cudaStream_t s
 }
 
 // kernels one gca_step launches for this configuration (bench.py's gpu_launches)
-int step_launch_count(bool tape, int n_intruders, int obs_kind) {
-  return 2 + (n_intruders > 0 ? 1 : 0) + (!tape && n_intruders > 0 ? 1 : 0) + (obs_kind == GCA_OBS_NEAREST ? 1 : 0);
+int step_launch_count(bool tape, int n_intruders, int obs_kind, bool turns) {
+  return 2 + (n_intruders > 0 ? 1 : 0) + (!tape && n_intruders > 0 ? 1 : 0) + (obs_kind == GCA_OBS_NEAREST ? 1 : 0) +
+         (n_intruders > 0 && (obs_kind == GCA_OBS_RAW6 || turns) ? 1 : 0);
 }
 
 cudaError_t launch_reset(bool faith, bool tape, const StepArgs& a, cudaStream_t st) {
@@ -1037,6 +1130,10 @@ cudaError_t launch_reset(bool faith, bool tape, const StepArgs& a, cudaStream_t 
     else reset_kernel<false, false><<<blocks, 128, 0, st>>>(a);
   }
   if (a.cfg.obs_kind == GCA_OBS_NEAREST) return launch_observe(faith, a, st);
+  if (a.cfg.obs_kind == GCA_OBS_RAW6 && a.s.N > 0) {       // the intruder entries of the reset observation
+    if (faith) turn_obs_kernel<true, false><<<turn_blocks(a.s), 128, 0, st>>>(a);
+    else turn_obs_kernel<false, false><<<turn_blocks(a.s), 128, 0, st>>>(a);
+  }
   return cudaGetLastError();
 }
 
@@ -1048,6 +1145,10 @@ cudaError_t launch_observe(bool faith, const StepArgs& a, cudaStream_t st) {
     else nearest_obs_kernel<false><<<nb, 128, 0, st>>>(a);
   } else if (faith) observe_kernel<true><<<blocks, 128, 0, st>>>(a);
   else observe_kernel<false><<<blocks, 128, 0, st>>>(a);
+  if (a.cfg.obs_kind == GCA_OBS_RAW6 && a.s.N > 0) {       // (observe_kernel wrote the ownship / goal tail)
+    if (faith) turn_obs_kernel<true, false><<<turn_blocks(a.s), 128, 0, st>>>(a);
+    else turn_obs_kernel<false, false><<<turn_blocks(a.s), 128, 0, st>>>(a);
+  }
   return cudaGetLastError();
 }
 

@@ -262,6 +262,23 @@ class SingleAircraftMCTSEnv(_SingleBase):
         return self._obs(), reward, bool(b.done[0].item()), {"result": abi.INFO_STR[code]}
 
 
+class SingleAircraftMCTSRandIntruderEnv(SingleAircraftMCTSEnv):
+    """Simulators/SingleAircraftMCTSRandIntruderEnv.py, the env of Algorithms/MCTS/Agent_RandInt.py: the MCTS env whose
+    intruders turn at random after every step (:166-174) and drift by Config.position_sigma (:183); the raw observation
+    carries six entries per intruder (:133-140) although the declared space keeps 4 N + 8 (:50-51); `info` is the bare
+    result string (:164)."""
+    VARIANT = "SingleAircraftMCTSRandIntruderEnv"
+
+    def load_config(self):
+        super(SingleAircraftMCTSRandIntruderEnv, self).load_config()
+        self.d_heading = self.Config.d_heading                  # :81-82
+        self.position_sigma = self.Config.position_sigma
+
+    def step(self, action):
+        ob, reward, done, info = super(SingleAircraftMCTSRandIntruderEnv, self).step(action)
+        return ob, reward, done, info["result"]
+
+
 class SimSingleAircraftEnv(SingleAircraftMCTSEnv):
     """Simulators/SingleAircraftEnv.py: the registered env with the reward row of Simulators/config.py and an info dict
     (normalised vector observation, integer action 0..8)."""

@@ -19,6 +19,8 @@ def _make(vk, n, **kw):
     try:
         if vk == "mcts":
             from Simulators.SingleAircraftMCTSEnv import SingleAircraftEnv as cls
+        elif vk == "mctsrnd":
+            from Simulators.SingleAircraftMCTSRandIntruderEnv import SingleAircraftEnv as cls
         elif vk == "d9her":
             from Simulators.SingleAircraftDiscrete9HEREnv import SingleAircraftDiscrete9HEREnv as cls
         elif vk == "d3her":
@@ -33,19 +35,20 @@ def _make(vk, n, **kw):
                    "dher": envs.SingleAircraftDiscreteHEREnv}[vk]
         return cls(**kw)
     finally:
-        cfgc.intruder_size = 80 if vk in ("mcts", "d9her", "d3her", "simenv", "rndenv") else 0
+        cfgc.intruder_size = 80 if vk in ("mcts", "mctsrnd", "d9her", "d3her", "simenv", "rndenv") else 0
 
 
 def _ref_action(vk, a):
     if vk in ("env", "dher", "d9her", "d3her", "simenv", "rndenv"):
         return int(a[0])
-    if vk == "mcts":
+    if vk in ("mcts", "mctsrnd"):
         return (int(a[0]), int(a[1]))
     return np.array(a, np.float64)
 
 
 @pytest.mark.parametrize("vk,n", [("env", 3), ("env", 80), ("env2", 3), ("her", 3), ("dher", 3), ("mcts", 80),
-                                  ("d9her", 12), ("d9her", 80), ("d3her", 12), ("simenv", 3), ("rndenv", 80)])
+                                  ("d9her", 12), ("d9her", 80), ("d3her", 12), ("simenv", 3), ("rndenv", 80),
+                                  ("mctsrnd", 3), ("mctsrnd", 80)])
 def test_single_env_api_replays_reference_trace(vk, n):
     g = load_trace(vk, n)
     plain = [int(i) for i in np.nonzero(g["kind_id"] == 0)[0]][:2]
@@ -61,16 +64,16 @@ def test_single_env_api_replays_reference_trace(vk, n):
             assert ob["achieved_goal"].dtype == np.float32 and ob["desired_goal"].dtype == np.float64
             assert close(ob["achieved_goal"], g["ag0"][tr]) and close(ob["desired_goal"], g["dg0"][tr])
         else:
-            assert ob.dtype == np.float64 and ob.shape == (4 * n + 8,)
+            assert ob.dtype == np.float64 and ob.shape == ((6 if vk == "mctsrnd" else 4) * n + 8,)
         for t in range(g["actions"].shape[1]):
             ob, r, done, info = env.step(_ref_action(vk, g["actions"][tr, t]))
             assert close(ob["observation"] if her else ob, g["obs"][tr, t])
             assert close(r, g["reward"][tr, t])
-            if vk not in ("mcts", "d9her", "d3her", "simenv", "rndenv"):
+            if vk not in ("mcts", "mctsrnd", "d9her", "d3her", "simenv", "rndenv"):
                 assert isinstance(r, int) == bool(g["reward_is_int"][tr, t]), (vk, t, r)
             assert done == bool(g["done"][tr, t]) and isinstance(done, bool)
             code = ("", "n", "c", "g", "w", "m")[g["event"][tr, t]]
-            if vk in ("env", "env2"):
+            if vk in ("env", "env2", "mctsrnd"):     # (the random-intruder env returns the bare string, :164)
                 assert info == code
             elif vk == "dher":
                 assert info == {}

@@ -71,7 +71,8 @@ def test_free_running_replay_matches_reference(vk, n):
         assert np.array_equal(env.cursor, g["cur_after_reset"][:, t]), what
 
 
-@pytest.mark.parametrize("vk,n", [("env", 80), ("env2", 3), ("her", 80), ("dher", 3), ("mcts", 80)])
+@pytest.mark.parametrize("vk,n", [("env", 80), ("env2", 3), ("her", 80), ("dher", 3), ("mcts", 80),
+                                  ("mctsrnd", 80), ("mctsrnd", 3)])
 def test_auto_reset_equals_step_then_reset(vk, n):
     """auto_reset folds the VecEnv contract (dummy_vec_env.py:52-55) into step."""
     g = load_trace(vk, n)
