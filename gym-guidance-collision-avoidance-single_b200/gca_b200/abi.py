@@ -67,21 +67,28 @@ class GcaHerTransitions(C.Structure):
 class GcaMctsConfig(C.Structure):
     _fields_ = [(n, C.c_double) for n in (
         "window_width", "window_height", "minimum_separation", "min_speed", "max_speed", "d_speed", "speed_sigma",
-        "position_sigma", "d_heading", "heading_sigma")] + [("simulate_frame", C.c_int32), ("search_depth", C.c_int32)]
+        "position_sigma", "d_heading", "heading_sigma")] + [("simulate_frame", C.c_int32), ("search_depth", C.c_int32),
+                                                            ("random_intruders", C.c_int32), ("reserved0", C.c_int32),
+                                                            ("turn_prob", C.c_double), ("turn_max_deg", C.c_double)]
 
 
 MCTS_WALL, MCTS_CONFLICT, MCTS_GOAL = 1, 2, 4
 STAT_NAMES = ("steps", "episodes", "nmac", "conflict_steps", "goal", "wall", "maxsteps")
 
 
-def make_mcts_config(cfg_cls):
-    """Snapshot Algorithms/MCTS/config_single.py-style class attributes."""
+def make_mcts_config(cfg_cls, random_intruders=False):
+    """Snapshot Algorithms/MCTS/config_single.py-style class attributes.  random_intruders selects the model of
+    Algorithms/MCTS/nodes_single_randintru.py (6 N + 8 state vectors, intruders that turn with probability 0.1 per
+    sub-frame by up to 10 degrees, :64-65)."""
     c = GcaMctsConfig()
     for name in ("window_width", "window_height", "minimum_separation", "min_speed", "max_speed", "d_speed",
                  "speed_sigma", "position_sigma", "d_heading", "heading_sigma"):
         setattr(c, name, float(getattr(cfg_cls, name)))
     c.simulate_frame = int(cfg_cls.simulate_frame)
     c.search_depth = int(cfg_cls.search_depth)
+    c.random_intruders = 1 if random_intruders else 0
+    c.turn_prob = 0.1 if random_intruders else 0.0
+    c.turn_max_deg = 10.0 if random_intruders else 0.0
     return c
 
 

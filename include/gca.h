@@ -251,6 +251,15 @@ typedef struct gca_mcts_config {
   double d_heading, heading_sigma;
   int32_t simulate_frame;             /* sub-frames per move() (config_single.py:59) */
   int32_t search_depth;               /* moves per playout (config_single.py:61) */
+  /* Algorithms/MCTS/nodes_single_randintru.py (the model of Agent_RandInt.py): state vectors are the 6 N + 8 raw
+   * observation of Simulators/SingleAircraftMCTSRandIntruderEnv.py (x, y, vx, vy, speed, heading per intruder); ALL N
+   * intruders are seen ((len - 8) // 6, :47); after its advance every intruder draws np.random.random() and, below
+   * turn_prob, turns by radians(uniform(-turn_max_deg, turn_max_deg)) - f64 velocity = speed * (cos, sin) (:64-71);
+   * the speed clamp reads the speed itself (:74, the index bug Q23 of nodes_single.py is fixed there). */
+  int32_t random_intruders;
+  int32_t reserved0;
+  double turn_prob;                   /* 0.1 (:64) */
+  double turn_max_deg;                /* 10 (:65) */
 } gca_mcts_config;
 
 /* Philox counter of the playout kernels: (root id, playout id, what, index) */
@@ -258,6 +267,7 @@ typedef struct gca_mcts_config {
 #define GCA_MCTS_DRAW_HEADING 1u      /* index = global sub-frame: Box-Muller cos branch * heading_sigma */
 #define GCA_MCTS_DRAW_SPEED 2u        /* index = global sub-frame (only drawn when speed_sigma != 0) */
 #define GCA_MCTS_DRAW_INTRUDER 3u     /* + intruder index; index = global sub-frame (only when position_sigma != 0) */
+#define GCA_MCTS_DRAW_TURN 0x40000000u /* + intruder index; index = global sub-frame: (p, u) of a random_intruders turn */
 
 enum { GCA_MCTS_WALL = 1, GCA_MCTS_CONFLICT = 2, GCA_MCTS_GOAL = 4 };
 
@@ -320,7 +330,8 @@ int gca_her_sample(const gca_her_episodes* episodes, int64_t n_episodes, int T, 
                    const gca_her_draws* draws, uint64_t seed, uint32_t call, const gca_her_transitions* out, int device,
                    void* stream);
 
-/* SingleAircraftState.move(action) for m independent states (nodes_single.py:39-100).
+/* SingleAircraftState.move(action) for m independent states (nodes_single.py:39-100; with cfg->random_intruders
+ * nodes_single_randintru.py:39-116 on [m][6N+8] vectors, tape order per intruder: normal, normal, random(), [uniform]).
  * states: device double [m][4N+8] raw observation vectors (Simulators/SingleAircraftMCTSEnv.py:98-124),
  * advanced in place; actions: device int32 [m] (a0*3+a1); flags: device uint8 [m] (GCA_MCTS_* bits).
  * tape (nullable): the model's np.random.normal values in call order, values[i*stride + cursor[i]++];
@@ -343,8 +354,9 @@ int gca_mcts_playouts(const gca_mcts_config* cfg, int n_intruders, const double*
  * the device (search_single.py:8-22 best_action / tree_policy; common.py:47-52 best_child with c = 1.4 in the
  * tree and c = 0 for the final pick; nodes_single.py:188-193 expand - untried actions popped from the end -,
  * :198-204 rollout, :206-210 backpropagate; Algorithms/MCTS/Agent.py:37-41 is the call site this replaces).
- * Requires cfg->position_sigma == 0 (config_single.py:27): the model's intruders then move on root-only
- * trajectories and a tree node is just the ownship.  Draws are Philox, keyed (seed; root id = root_id0 + r,
+ * Requires cfg->position_sigma == 0 (config_single.py:27) and no random_intruders: the model's intruders then move on
+ * root-only trajectories and a tree node is just the ownship (GCA_ERR_STATE otherwise: the drop-in node classes then
+ * run the tree on the host with device move / rollout).  Draws are Philox, keyed (seed; root id = root_id0 + r,
  * simulation index, GCA_MCTS_DRAW_*, global sub-frame).
  * workspace: device scratch of gca_mcts_search_workspace(...) bytes, caller-owned, 16-byte aligned.
  * Outputs (device): best_action int32 [n_roots] (a0*3+a1 of the most valuable root child, -1 if simulations == 0);

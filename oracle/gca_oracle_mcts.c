@@ -43,6 +43,29 @@ static int draw_action(mdraws* d, uint32_t move) {
   return a > 8 ? 8 : a;
 }
 
+/* np.random.random() < turn_prob -> math.radians(np.random.uniform(-10, 10))  nodes_single_randintru.py:64-65.
+ * Returns 1 and the heading change when the intruder turns. */
+static int draw_turn(mdraws* d, const gca_mcts_config* c, uint32_t intruder, uint32_t gf, double* delta) {
+  double p, raw;
+  if (d->mode == GCA_DRAWS_TAPE) {
+    p = mt_next(d);
+    if (!(p < c->turn_prob)) return 0;
+    raw = mt_next(d);
+  } else {
+    double u[2];
+    gca_oracle_philox_uniform2(d->seed, d->root, d->playout, GCA_MCTS_DRAW_TURN + intruder, gf, u);
+    p = u[0];
+    if (!(p < c->turn_prob)) return 0;
+    raw = -c->turn_max_deg + (c->turn_max_deg - -c->turn_max_deg) * u[1];
+  }
+  *delta = raw * (3.141592653589793 / 180.0);
+  return 1;
+}
+
+/* length of a state vector and entries per intruder of the two models */
+static int per_intruder(const gca_mcts_config* c) { return c->random_intruders ? 6 : 4; }
+static int state_len(const gca_mcts_config* c, int n) { return per_intruder(c) * n + 8; }
+
 static double metric(double x1, double y1, double x2, double y2) {   /* nodes_single.py:123-126 */
   double dx = x1 - x2, dy = y1 - y2;
   return sqrt(dx * dx + dy * dy);
@@ -51,22 +74,36 @@ static double metric(double x1, double y1, double x2, double y2) {   /* nodes_si
 /* SingleAircraftState.move(action)  nodes_single.py:39-100.  `frame0` numbers the sub-frames of a
  * playout globally (Philox index); returns the GCA_MCTS_* flags of the successor. */
 static int model_move(const gca_mcts_config* c, int n, double* st, int a0, int a1, mdraws* d, int frame0) {
-  const int L = 4 * n + 8;
-  const int near = L >= 9 ? (L - 9) / 4 : 0;            /* (len - 9) // 4 = N - 1: the last intruder is ignored (Q22) */
+  const int per = per_intruder(c);
+  const int L = state_len(c, n);
+  /* (len - 9) // 4 = N - 1: the last intruder is ignored (Q22); nodes_single_randintru.py:47 has (len - 8) // 6 = N */
+  const int near = c->random_intruders ? n : (L >= 9 ? (L - 9) / 4 : 0);
   const double d_heading = (double)(a0 - 1) * c->d_heading;
   const double accel = (double)(a1 - 1) * c->d_speed;
-  double* own = st + 4 * n;                              /* x y vx vy speed heading */
-  double* goal = st + 4 * n + 6;
+  double* own = st + per * n;                            /* x y vx vy speed heading */
+  double* goal = st + per * n + 6;
   int flags = 0;
   for (int f = 0; f < c->simulate_frame; ++f) {
     const uint32_t gf = (uint32_t)(frame0 + f);
-    for (int i = 0; i < near; ++i) {                     /* :54-57 */
-      st[4 * i] += st[4 * i + 2] + draw_normal(d, c->position_sigma, GCA_MCTS_DRAW_INTRUDER + (uint32_t)i, 2 * gf);
-      st[4 * i + 1] += st[4 * i + 3] + draw_normal(d, c->position_sigma, GCA_MCTS_DRAW_INTRUDER + (uint32_t)i, 2 * gf + 1);
+    for (int i = 0; i < near; ++i) {                     /* :54-57 (nodes_single_randintru.py:54-71) */
+      double* it = st + per * i;
+      it[0] += it[2] + draw_normal(d, c->position_sigma, GCA_MCTS_DRAW_INTRUDER + (uint32_t)i, 2 * gf);
+      it[1] += it[3] + draw_normal(d, c->position_sigma, GCA_MCTS_DRAW_INTRUDER + (uint32_t)i, 2 * gf + 1);
+      double delta;
+      if (c->random_intruders && draw_turn(d, c, (uint32_t)i, gf, &delta)) {
+        double s, co;
+        const double heading = it[5] + delta;
+        gca_oracle_sincos(heading, d->trig, &s, &co);
+        it[2] = it[4] * co;
+        it[3] = it[4] * s;
+        it[5] = heading;
+      }
     }
-    own[4] += accel;                                     /* :59 - overwritten by the next line */
+    own[4] += accel;                                     /* :59 - overwritten by the next line in nodes_single.py */
     {
-      const double m = c->max_speed < own[3] ? c->max_speed : own[3];   /* min(state[-5], max): own vy (Q23) */
+      const double v = c->random_intruders ? own[4] : own[3];           /* min(state[-5], max): own vy (Q23); the
+                                                                            random-intruder model clamps the speed (:74) */
+      const double m = c->max_speed < v ? c->max_speed : v;
       own[4] = m > c->min_speed ? m : c->min_speed;
     }
     own[4] += draw_normal(d, c->speed_sigma, GCA_MCTS_DRAW_SPEED, gf);
@@ -88,7 +125,7 @@ static int model_move(const gca_mcts_config* c, int n, double* st, int a0, int a
     }
     int conflict = 0;
     for (int i = 0; i < near; ++i)
-      if (metric(st[4 * i], st[4 * i + 1], ox, oy) < c->minimum_separation) {
+      if (metric(st[per * i], st[per * i + 1], ox, oy) < c->minimum_separation) {
         conflict = 1;
         break;
       }
@@ -105,10 +142,10 @@ static int model_move(const gca_mcts_config* c, int n, double* st, int a0, int a
 }
 
 /* reward()  nodes_single.py:25-32 */
-static double model_reward(int n, const double* st, int flags) {
+static double model_reward(const gca_mcts_config* c, int n, const double* st, int flags) {
   if (flags & (GCA_MCTS_WALL | GCA_MCTS_CONFLICT)) return 0.0;
   if (flags & GCA_MCTS_GOAL) return 1.0;
-  const double* own = st + 4 * n;
+  const double* own = st + per_intruder(c) * n;
   const double dx = own[0] - own[6], dy = own[1] - own[7];
   return 1 - sqrt(dx * dx + dy * dy) / 1200.0;
 }
@@ -119,7 +156,7 @@ int gca_oracle_mcts_move(const gca_mcts_config* c, int n, double* state, int act
   mdraws d = {draws, trig, tape, cursor, seed, root, 0u};
   const int f = model_move(c, n, state, action / 3, action % 3, &d, first_frame);
   if (flags) *flags = (uint8_t)f;
-  if (reward) *reward = model_reward(n, state, f);
+  if (reward) *reward = model_reward(c, n, state, f);
   return GCA_OK;
 }
 
@@ -135,13 +172,13 @@ static double model_rollout(const gca_mcts_config* c, int n, double* st, int fla
   }
   if (first_out) *first_out = first;
   if (flags_out) *flags_out = flags;
-  return model_reward(n, st, flags);
+  return model_reward(c, n, st, flags);
 }
 
 int gca_oracle_mcts_rollout(const gca_mcts_config* c, int n, const double* root, int depth_limit, int draws, int trig,
                             const double* tape, int64_t* cursor, uint64_t seed, uint32_t root_id, uint32_t playout,
                             int forced_first, double* reward, int8_t* first_out, uint8_t* flags_out) {
-  const int L = 4 * n + 8;
+  const int L = state_len(c, n);
   double* st = (double*)malloc(sizeof(double) * L);
   if (!st) return GCA_ERR_ALLOC;
   memcpy(st, root, sizeof(double) * L);
@@ -158,7 +195,7 @@ int gca_oracle_mcts_rollout(const gca_mcts_config* c, int n, const double* root,
 int gca_oracle_mcts_playouts(const gca_mcts_config* c, int n, const double* roots, int64_t n_roots, int playouts,
                              int depth, const int8_t* first_action, uint64_t seed, uint32_t root_id0, int trig,
                              double* rewards, int8_t* first_out, uint8_t* flags) {
-  const int L = 4 * n + 8;
+  const int L = state_len(c, n);
   for (int64_t r = 0; r < n_roots; ++r)
     for (int p = 0; p < playouts; ++p) {
       const int64_t k = r * playouts + p;
@@ -201,7 +238,7 @@ static int best_child(const node* nodes, int v, double c_param, int shared_log, 
 /* MCTS(root).best_action(simulations, search_depth)  search_single.py:8-22 */
 static int search_impl(const gca_mcts_config* c, int n, const double* root, int sims, int search_depth, mdraws d,
                        int* best_action, double* child_n, double* child_q, int* child_action) {
-  const int L = 4 * n + 8;
+  const int L = state_len(c, n);
   const int philox = d.mode == GCA_DRAWS_PHILOX;
   node* nodes = (node*)calloc((size_t)sims + 2, sizeof(node));
   double* scratch = (double*)malloc(sizeof(double) * L);
@@ -265,7 +302,7 @@ int gca_oracle_mcts_search(const gca_mcts_config* c, int n, const double* root, 
 int gca_oracle_mcts_search_philox(const gca_mcts_config* c, int n, const double* roots, int64_t n_roots, int sims,
                                   int search_depth, uint64_t seed, uint32_t root_id0, int trig, int32_t* best_action,
                                   double* child_n, double* child_q, int32_t* child_action) {
-  const int L = 4 * n + 8;
+  const int L = state_len(c, n);
   for (int64_t r = 0; r < n_roots; ++r) {
     mdraws d = {GCA_DRAWS_PHILOX, trig, NULL, NULL, seed, root_id0 + (uint32_t)r, 0};
     int best = -1, ca[9];

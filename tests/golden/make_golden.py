@@ -40,6 +40,7 @@ import SingleAircraftRandomEnv as rndenv_mod  # noqa: E402  (Simulators/, random
 import SingleAircraftMCTSRandIntruderEnv as mctsrnd_mod  # noqa: E402  (Simulators/, intruders that turn at random)
 import config as SimConfigMod  # noqa: E402
 import nodes_single  # noqa: E402
+import nodes_single_randintru  # noqa: E402  (6-field intruders that turn at random)
 import search_single  # noqa: E402
 import config_single  # noqa: E402
 
@@ -55,7 +56,7 @@ class Tape(object):
         self._orig = {}
 
     def __enter__(self):
-        for name in ("uniform", "normal", "randint"):
+        for name in ("uniform", "normal", "randint", "random"):
             self._orig[name] = getattr(np.random, name)
             setattr(np.random, name, self._wrap(self._orig[name]))
         return self
@@ -431,6 +432,78 @@ def make_mcts_goldens():
     return meta
 
 
+def make_mctsrnd_model_goldens():
+    """move() and rollout() of Algorithms/MCTS/nodes_single_randintru.py on raw observations of
+    Simulators/SingleAircraftMCTSRandIntruderEnv (6 N + 8 values); draw order per intruder and sub-frame:
+    normal, normal, random(), [uniform(-10, 10)]."""
+    meta = {}
+    kinds = ["plain", "mid", "near_intruder", "near_goal", "near_wall"]
+    mod = nodes_single_randintru
+    for n, count in ((3, 20), (20, 10)):
+        SimConfigMod.Config.intruder_size = n
+        rng = np.random.RandomState(777 + n)
+        np.random.seed(777 + n)
+        roots = []
+        for c in range(count):
+            env = mctsrnd_mod.SingleAircraftEnv()
+            env.reset()
+            kind = kinds[c % len(kinds)]
+            override(env, kind, rng, n)
+            if kind == "near_intruder":
+                it = env.intruder_list[int(rng.randint(n))]
+                r, th = rng.uniform(8.0, 45.0), rng.uniform(0, 2 * math.pi)
+                env.drone.position[:] = (np.asarray(it.position, np.float64)
+                                         - r * np.array([math.cos(th), math.sin(th)])).astype(np.float32)
+                env.drone.heading = float(th + rng.normal(0, 0.15))
+            for _ in range(int(rng.randint(0, 4)) if kind != "near_intruder" else 1):
+                env.step((int(rng.randint(3)), int(rng.randint(3))))
+            roots.append(np.asarray(env._get_ob(), np.float64))
+        roots = np.asarray(roots)
+        mv = {k: [] for k in ("root", "action", "tape", "out_state", "hit_wall", "conflict", "reach_goal", "reward")}
+        ro = {k: [] for k in ("root", "depth", "tape", "reward")}
+        for ri, root in enumerate(roots):
+            for a0 in range(3):
+                for a1 in range(3):
+                    np.random.seed(17000 + 9 * ri + 3 * a0 + a1)
+                    with Tape() as tape:
+                        s2 = mod.SingleAircraftState(state=root.copy()).move((a0, a1))
+                    mv["root"].append(ri); mv["action"].append((a0, a1)); mv["tape"].append(np.asarray(tape.values))
+                    mv["out_state"].append(np.asarray(s2.state, np.float64))
+                    mv["hit_wall"].append(s2.hit_wall); mv["conflict"].append(s2.conflict)
+                    mv["reach_goal"].append(s2.reach_goal); mv["reward"].append(np.float64(s2.reward()))
+            for depth in (1, 2, 3):
+                for rep in range(3):
+                    np.random.seed(19000 + 31 * ri + 7 * depth + rep)
+                    node = mod.SingleAircraftNode(mod.SingleAircraftState(state=root.copy()))
+                    with Tape() as tape:
+                        r = node.rollout(depth)
+                    ro["root"].append(ri); ro["depth"].append(depth); ro["tape"].append(np.asarray(tape.values))
+                    ro["reward"].append(np.float64(r))
+
+        def pad(lst):
+            L = max(len(x) for x in lst)
+            arr = np.full((len(lst), L), np.nan)
+            for i, x in enumerate(lst):
+                arr[i, : len(x)] = x
+            return arr, np.asarray([len(x) for x in lst], np.int64)
+        out = {"roots": roots}
+        for name, d in (("mv", mv), ("ro", ro)):
+            for k, v in d.items():
+                if k == "tape":
+                    out[name + "_tape"], out[name + "_tape_len"] = pad(v)
+                else:
+                    out[name + "_" + k] = np.asarray(v)
+        fn = os.path.join(HERE, "mctsrnd_model_n%d.npz" % n)
+        np.savez_compressed(fn, **out)
+        turns = int(sum(len(t) for t in mv["tape"]))
+        meta["mctsrnd_model_n%d" % n] = {"roots": len(roots), "moves": len(mv["root"]), "rollouts": len(ro["root"]),
+                                         "move_draws": turns,
+                                         "move_flags": [int(np.sum(mv["hit_wall"])), int(np.sum(mv["conflict"])),
+                                                        int(np.sum(mv["reach_goal"]))]}
+        print(fn, meta["mctsrnd_model_n%d" % n])
+    return meta
+
+
 def make_her_reward_golden():
     """compute_reward of both GoalEnv variants on random + engineered pairs."""
     rng = np.random.RandomState(5)
@@ -534,6 +607,8 @@ def main():
             meta.update(make_d9her_reward_golden())
         if "her_sampler" in only.split(","):
             meta.update(make_her_sampler_golden())
+        if "mctsrnd_model" in only.split(","):
+            meta.update(make_mctsrnd_model_goldens())
         with open(os.path.join(HERE, "META.json"), "w") as f:
             json.dump(meta, f, indent=1, sort_keys=True)
         return
@@ -545,6 +620,7 @@ def main():
         meta["threadpools"] = str(e)
     meta.update(make_env_goldens())
     meta.update(make_mcts_goldens())
+    meta.update(make_mctsrnd_model_goldens())
     meta.update(make_her_reward_golden())
     meta.update(make_d9her_reward_golden())
     meta.update(make_her_sampler_golden())

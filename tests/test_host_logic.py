@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(abi.GcaConfig) == 21 * 8 + 8 * 4 + 8 + 16 + 8 + 3 * 8
-    assert ctypes.sizeof(abi.GcaMctsConfig) == 10 * 8 + 2 * 4
+    assert ctypes.sizeof(abi.GcaMctsConfig) == 10 * 8 + 4 * 4 + 2 * 8
     assert ctypes.sizeof(abi.GcaHostState) == 13 * 8 and ctypes.sizeof(abi.GcaOut) == 7 * 8
     assert ctypes.sizeof(abi.GcaTape) == 24
 

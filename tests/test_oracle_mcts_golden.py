@@ -10,15 +10,19 @@ from gca_b200 import abi
 from oracle import oracle as orc
 
 
-def mcts_cfg():
+def mcts_cfg(rnd=False):
     from Algorithms.MCTS.config_single import Config
-    return abi.make_mcts_config(Config)
+    return abi.make_mcts_config(Config, random_intruders=rnd)
 
 
-@pytest.mark.parametrize("n", [3, 80])
-def test_move_matches_reference(n):
-    g = np.load(os.path.join(GOLDEN, "mcts_n%d.npz" % n))
-    cfg = mcts_cfg()
+# (file stem, N): nodes_single.py on 4 N + 8 states, nodes_single_randintru.py on 6 N + 8 states
+MODEL_CASES = [("mcts", 3), ("mcts", 80), ("mctsrnd_model", 3), ("mctsrnd_model", 20)]
+
+
+@pytest.mark.parametrize("stem,n", MODEL_CASES)
+def test_move_matches_reference(stem, n):
+    g = np.load(os.path.join(GOLDEN, "%s_n%d.npz" % (stem, n)))
+    cfg = mcts_cfg(stem != "mcts")
     seen = set()
     for k in range(len(g["mv_root"])):
         root = g["roots"][g["mv_root"][k]]
@@ -35,10 +39,10 @@ def test_move_matches_reference(n):
     assert {0, abi.MCTS_WALL, abi.MCTS_CONFLICT, abi.MCTS_GOAL} <= seen      # every branch exercised
 
 
-@pytest.mark.parametrize("n", [3, 80])
-def test_rollout_matches_reference(n):
-    g = np.load(os.path.join(GOLDEN, "mcts_n%d.npz" % n))
-    cfg = mcts_cfg()
+@pytest.mark.parametrize("stem,n", MODEL_CASES)
+def test_rollout_matches_reference(stem, n):
+    g = np.load(os.path.join(GOLDEN, "%s_n%d.npz" % (stem, n)))
+    cfg = mcts_cfg(stem != "mcts")
     for k in range(len(g["ro_root"])):
         root = g["roots"][g["ro_root"][k]]
         tape = np.nan_to_num(g["ro_tape"][k], nan=0.0)
