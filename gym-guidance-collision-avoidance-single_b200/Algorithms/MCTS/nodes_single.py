@@ -21,6 +21,12 @@ def _next_id():
 
 
 class SingleAircraftState(MCTSState):
+    RANDOM_INTRUDERS = False     # True in nodes_single_randintru.py: 6 values per intruder, intruders that turn
+
+    @classmethod
+    def model_config(cls):
+        return abi.make_mcts_config(Config, random_intruders=cls.RANDOM_INTRUDERS)
+
     def __init__(self, state, hit_wall=False, conflict=False, reach_goal=False, prev_action=None, depth=0):
         MCTSState.__init__(self, np.asarray(state, dtype=np.float64))
         self.hit_wall = hit_wall
@@ -52,8 +58,8 @@ class SingleAircraftState(MCTSState):
         st = torch.as_tensor(self.state[None].copy(), device="cuda")
         code = torch.tensor([int(action[0]) * 3 + int(action[1])], dtype=torch.int32, device="cuda")
         seed = int(np.random.randint(2 ** 31))          # the reference draws from the global numpy stream
-        flags = int(_dev.move(st, code, abi.make_mcts_config(Config), seed=seed, id0=_next_id())[0].item())
-        return SingleAircraftState(st[0].cpu().numpy(), bool(flags & abi.MCTS_WALL), bool(flags & abi.MCTS_CONFLICT),
+        flags = int(_dev.move(st, code, self.model_config(), seed=seed, id0=_next_id())[0].item())
+        return type(self)(st[0].cpu().numpy(), bool(flags & abi.MCTS_WALL), bool(flags & abi.MCTS_CONFLICT),
                                    bool(flags & abi.MCTS_GOAL), tuple(action), self.depth + 1)
 
     def get_legal_actions(self):
@@ -66,11 +72,13 @@ class SingleAircraftState(MCTSState):
 
     def dist_intruder(self):
         distance = 5000
-        for i in range((len(self.state) - 9) // 4):
-            d = self.metric(self.state[4 * i], self.state[4 * i + 1], self.ownx, self.owny)
+        # (len - 9) // 4 intruders of 4 values (:112), (len - 8) // 6 of 6 values in nodes_single_randintru.py:126
+        k, near = (6, (len(self.state) - 8) // 6) if self.RANDOM_INTRUDERS else (4, (len(self.state) - 9) // 4)
+        for i in range(near):
+            d = self.metric(self.state[k * i], self.state[k * i + 1], self.ownx, self.owny)
             if d < distance:
                 distance = d
-                self.nearest_x, self.nearest_y = self.state[4 * i], self.state[4 * i + 1]
+                self.nearest_x, self.nearest_y = self.state[k * i], self.state[k * i + 1]
         return distance
 
     def metric(self, x1, y1, x2, y2):
@@ -99,7 +107,7 @@ class SingleAircraftNode(MCTSNode):
 
     def expand(self):
         action = self.untried_actions.pop()              # (2, 2) first (Q27)
-        child = SingleAircraftNode(self.state.move(action), parent=self)
+        child = type(self)(self.state.move(action), parent=self)
         self.children.append(child)
         return child
 
@@ -113,7 +121,7 @@ class SingleAircraftNode(MCTSNode):
         if s.is_terminal_state(search_depth):
             return s.reward()
         root = torch.as_tensor(s.state[None].copy(), device="cuda")
-        r, _, _ = _dev.playouts(root, 1, depth=search_depth - s.depth, cfg=abi.make_mcts_config(Config),
+        r, _, _ = _dev.playouts(root, 1, depth=search_depth - s.depth, cfg=s.model_config(),
                                 seed=int(np.random.randint(2 ** 31)), root_id0=_next_id())
         return float(r[0, 0].item())
 

@@ -22,6 +22,8 @@ class MCTS(object):
         from .nodes_single import SingleAircraftNode
         if Config.position_sigma != 0 or simulations <= 0 or self.root.children:
             return None
+        if getattr(self.root.state, "RANDOM_INTRUDERS", False):      # nodes_single_randintru.py: every playout moves its own intruders
+            return None
         cfg = abi.make_mcts_config(Config)
         root_state = torch.as_tensor(np.asarray(self.root.state.state, np.float64)[None], device="cuda")
         action = dev.search(root_state, simulations, search_depth, cfg=cfg, seed=int(np.random.randint(2 ** 31)))

@@ -630,6 +630,8 @@ int gca_mcts_playouts(const gca_mcts_config* cfg, int n_intruders, const double*
   if (!cfg || n_intruders < 0 || n_roots < 0 || playouts <= 0 || depth < 0 || (n_roots > 0 && (!roots || !rewards)))
     return fail(GCA_ERR_INVALID, "bad arguments");
   if (cfg->simulate_frame <= 0) return fail(GCA_ERR_INVALID, "simulate_frame must be positive");
+  if (cfg->random_intruders && (size_t)n_intruders * 6 * 4 * sizeof(double) > 200 * 1024)
+    return fail(GCA_ERR_INVALID, "random_intruders playouts keep 4 x 6 N doubles in shared memory: at most 1066 intruders");
   GCA_CUDA(cudaSetDevice(device));
   GCA_CUDA(launch_mcts_playouts(cfg, n_intruders, roots, (long long)n_roots, playouts, depth, first_action, seed,
                                 root_id0, rewards, first_out, flags, (cudaStream_t)stream));
@@ -649,8 +651,8 @@ int gca_mcts_search(const gca_mcts_config* cfg, int n_intruders, const double* r
   if (!cfg || n_intruders < 0 || n_roots < 0 || simulations < 0 || depth < 0 || (n_roots > 0 && (!roots || !best_action)))
     return fail(GCA_ERR_INVALID, "bad arguments");
   if (cfg->simulate_frame <= 0) return fail(GCA_ERR_INVALID, "simulate_frame must be positive");
-  if (cfg->position_sigma != 0.0)
-    return fail(GCA_ERR_STATE, "the device-resident search needs position_sigma == 0 (use the node classes otherwise)");
+  if (cfg->position_sigma != 0.0 || cfg->random_intruders)
+    return fail(GCA_ERR_STATE, "the device-resident search needs position_sigma == 0 and no random_intruders (use the node classes otherwise)");
   if (simulations > 32000 || depth > 127) return fail(GCA_ERR_INVALID, "at most 32000 simulations and depth 127");
   const int64_t need = gca_mcts_search_workspace(cfg, n_intruders, n_roots, simulations, depth);
   if (n_roots > 0 && (!workspace || workspace_bytes < need || reinterpret_cast<uintptr_t>(workspace) % 16))

@@ -35,6 +35,7 @@ struct MctsArgs {
   gca_mcts_config c;
   double sep2;              // min{ s : sqrt(s) >= minimum_separation }
   int n, near, L;
+  int per;                  // entries per intruder of a state vector: 4 (nodes_single.py), 6 (nodes_single_randintru.py)
   // playouts
   const double* roots;
   long long n_roots;
@@ -79,6 +80,18 @@ __device__ __forceinline__ double mcts_normal(const MctsArgs& a, double sigma, u
   return __dadd_rn(0.0, __dmul_rn(sigma, __dmul_rn(r, cs)));
 }
 
+// nodes_single_randintru.py:64-65: np.random.random() < 0.1 -> heading += math.radians(np.random.uniform(-10, 10)).
+// Philox block (GCA_MCTS_DRAW_TURN + intruder, global sub-frame) = (p, u).  True and the heading change on a turn.
+__device__ __forceinline__ bool mcts_turn(const MctsArgs& a, uint32_t root, uint32_t playout, uint32_t intruder,
+                                          uint32_t gf, double& delta) {
+  double p, u;
+  mcts_uniform2(a, root, playout, GCA_MCTS_DRAW_TURN + intruder, gf, p, u);
+  if (!(p < a.c.turn_prob)) return false;
+  const double raw = __dadd_rn(-a.c.turn_max_deg, __dmul_rn(__dadd_rn(a.c.turn_max_deg, a.c.turn_max_deg), u));
+  delta = __dmul_rn(raw, 3.141592653589793 / 180.0);
+  return true;
+}
+
 __device__ __forceinline__ int mcts_action(const MctsArgs& a, uint32_t root, uint32_t playout, uint32_t move) {
   double u0, u1;
   mcts_uniform2(a, root, playout, GCA_MCTS_DRAW_ACTION, move, u0, u1);
@@ -99,9 +112,13 @@ constexpr int kMctsWarps = 4;
 constexpr int kMaxRounds = 4;       // intruder rounds held in registers (N - 1 <= 128); larger N uses the generic path
 static_assert(kMaxRounds == 4, "launch_mcts_playouts dispatches on 1..4 rounds");
 
-// RC > 0: intruder rounds in registers; RC == 0: intruders live in shared memory (any N)
-template <int RC>
+// RC > 0: intruder rounds in registers; RC == 0: intruders live in shared memory (any N).
+// RND (with RC == 0): the model of nodes_single_randintru.py - six entries per intruder, every intruder may turn after
+// its advance, the ownship speed is a state of its own (clamped on itself, :73-75).
+template <int RC, bool RND = false>
 __global__ void __launch_bounds__(kMctsWarps * 32) mcts_playout_kernel(const MctsArgs a) {
+  static_assert(!(RND && RC != 0), "the random-intruder model keeps its intruders in shared memory");
+  constexpr int PER = RND ? 6 : 4;
   extern __shared__ double mcts_smem[];
   const gca_mcts_config& c = a.c;
   const int lane = threadIdx.x & 31;
@@ -113,11 +130,11 @@ __global__ void __launch_bounds__(kMctsWarps * 32) mcts_playout_kernel(const Mct
   const uint32_t playout = (uint32_t)(pid - r_idx * a.playouts);
   const uint32_t root = a.root_id0 + (uint32_t)r_idx;
   const double* st = a.roots + r_idx * a.L;
-  const double* own = st + 4 * a.n;
+  const double* own = st + a.per * a.n;
 
   // ---- intruders: lane i + 32 r holds (x, y, vx, vy)
   double ix[RC > 0 ? RC : 1], iy[RC > 0 ? RC : 1], ivx[RC > 0 ? RC : 1], ivy[RC > 0 ? RC : 1];
-  double* sm = mcts_smem + (size_t)warp_in_block * 4 * a.near;      // RC == 0 only
+  double* sm = mcts_smem + (size_t)warp_in_block * PER * a.near;    // RC == 0 only
   if constexpr (RC > 0) {
 #pragma unroll
     for (int r = 0; r < RC; ++r) {
@@ -128,7 +145,7 @@ __global__ void __launch_bounds__(kMctsWarps * 32) mcts_playout_kernel(const Mct
       ix[r] = p.x; iy[r] = p.y; ivx[r] = w.x; ivy[r] = w.y;
     }
   } else {
-    for (int j = lane; j < 4 * a.near; j += 32) sm[j] = st[j];
+    for (int j = lane; j < PER * a.near; j += 32) sm[j] = st[j];
     __syncwarp();
   }
   double ox = own[0], oy = own[1], vy_prev = own[3], speed = own[4], heading = own[5];
@@ -145,6 +162,8 @@ __global__ void __launch_bounds__(kMctsWarps * 32) mcts_playout_kernel(const Mct
     else act = mcts_action(a, root, playout, (uint32_t)depth);
     if (first < 0) first = act;
     const double d_heading = __dmul_rn((double)(act / 3 - 1), c.d_heading);
+    const double accel = __dmul_rn((double)(act % 3 - 1), c.d_speed);
+    (void)accel;
     for (int f0 = 0; f0 < F && !flags; f0 += 32) {
       const int nf = min(32, F - f0);
       const uint32_t gf = (uint32_t)(depth * F + f0 + lane);
@@ -167,8 +186,11 @@ __global__ void __launch_bounds__(kMctsWarps * 32) mcts_playout_kernel(const Mct
       // (4) speed / position recurrence; lane f keeps the ownship position of sub-frame f
       double my_ox = 0.0, my_oy = 0.0;
       for (int f = 0; f < nf; ++f) {
-        double sp = clamp_speed(c, vy_prev);                          // state[-4] = clamp(state[-5])  (Q23)
+        double sp;
+        if constexpr (RND) sp = clamp_speed(c, __dadd_rn(speed, accel));   // state[-4] += a; state[-4] = clamp(state[-4])
+        else sp = clamp_speed(c, vy_prev);                            // state[-4] = clamp(state[-5])  (Q23)
         sp = __dadd_rn(sp, shfl_f64(nsp, f));                         // += normal(0, speed_sigma)
+        speed = sp;
         const double vx = __dmul_rn(sp, shfl_f64(cs, f)), vy = __dmul_rn(sp, shfl_f64(sn, f));
         ox = __dadd_rn(ox, vx);
         oy = __dadd_rn(oy, vy);
@@ -206,10 +228,21 @@ __global__ void __launch_bounds__(kMctsWarps * 32) mcts_playout_kernel(const Mct
           for (int i = lane; i < a.near; i += 32) {
             const double npx = mcts_normal(a, c.position_sigma, root, playout, GCA_MCTS_DRAW_INTRUDER + (uint32_t)i, 2 * gfu);
             const double npy = mcts_normal(a, c.position_sigma, root, playout, GCA_MCTS_DRAW_INTRUDER + (uint32_t)i, 2 * gfu + 1);
-            const double x = __dadd_rn(sm[4 * i], __dadd_rn(sm[4 * i + 2], npx));
-            const double y = __dadd_rn(sm[4 * i + 1], __dadd_rn(sm[4 * i + 3], npy));
-            sm[4 * i] = x;
-            sm[4 * i + 1] = y;
+            const double x = __dadd_rn(sm[PER * i], __dadd_rn(sm[PER * i + 2], npx));
+            const double y = __dadd_rn(sm[PER * i + 1], __dadd_rn(sm[PER * i + 3], npy));
+            sm[PER * i] = x;
+            sm[PER * i + 1] = y;
+            if constexpr (RND) {                                      // the turn follows the advance (:64-71)
+              double delta;
+              if (mcts_turn(a, root, playout, (uint32_t)i, gfu, delta)) {
+                double tsn, tcs;
+                const double h = __dadd_rn(sm[6 * i + 5], delta);
+                gca_sincos(h, &tsn, &tcs);
+                sm[6 * i + 2] = __dmul_rn(sm[6 * i + 4], tcs);
+                sm[6 * i + 3] = __dmul_rn(sm[6 * i + 4], tsn);
+                sm[6 * i + 5] = h;
+              }
+            }
             const double dx = __dadd_rn(x, -fx), dy = __dadd_rn(y, -fy);
             hit |= __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < a.sep2;
           }
@@ -271,7 +304,7 @@ __global__ void __launch_bounds__(kSharedThreads) mcts_playout_shared_kernel(con
   const long long r_idx = blockIdx.x;
   const uint32_t root = a.root_id0 + (uint32_t)r_idx;
   const double* st = a.roots + r_idx * a.L;
-  const double* own = st + 4 * a.n;
+  const double* own = st + a.per * a.n;
   const double ox0 = own[0], oy0 = own[1];
   const double gx = own[6], gy = own[7];
 
@@ -399,7 +432,7 @@ __device__ __forceinline__ double lane_reward(int flags, double ox, double oy, d
 __device__ __forceinline__ void build_candidates(const MctsArgs& a, const double* st, int TF, int* cnt, double2* cand,
                                                  int tid, int nthreads) {
   const gca_mcts_config& c = a.c;
-  const double* own = st + 4 * a.n;
+  const double* own = st + a.per * a.n;
   const double ox0 = own[0], oy0 = own[1];
   const bool cull = c.speed_sigma == 0.0;
   const double vmax = fmax(fabs(c.min_speed), fabs(c.max_speed));
@@ -436,7 +469,7 @@ __global__ void __launch_bounds__(128) mcts_search_kernel(const MctsArgs a) {
   const long long r_idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r_idx >= a.n_roots) return;
   const uint32_t root = a.root_id0 + (uint32_t)r_idx;
-  const double* own = a.roots + r_idx * a.L + 4 * a.n;
+  const double* own = a.roots + r_idx * a.L + a.per * a.n;
   uint8_t* ws = a.workspace + (size_t)r_idx * a.ws_root_stride;
   const int* cnt = reinterpret_cast<const int*>(ws);
   const double2* cand = reinterpret_cast<const double2*>(ws + a.ws_cand_off);
@@ -530,7 +563,7 @@ __global__ void __launch_bounds__(128) mcts_move_kernel(const MctsArgs a) {
   if (k >= a.m) return;
   const gca_mcts_config& c = a.c;
   double* st = a.states + k * a.L;
-  double* own = st + 4 * a.n;
+  double* own = st + a.per * a.n;
   const int act = a.actions[k];
   const double d_heading = __dmul_rn((double)(act / 3 - 1), c.d_heading);
   const double accel = __dmul_rn((double)(act % 3 - 1), c.d_speed);
@@ -542,13 +575,32 @@ __global__ void __launch_bounds__(128) mcts_move_kernel(const MctsArgs a) {
   for (int f = 0; f < c.simulate_frame; ++f) {
     const uint32_t gf = (uint32_t)(a.first_frame + f);
     for (int i = 0; i < a.near; ++i) {
+      double* it = st + a.per * i;
       const double nx = tape ? tp[cur++] : mcts_normal(a, c.position_sigma, root, 0u, GCA_MCTS_DRAW_INTRUDER + (uint32_t)i, 2 * gf);
-      st[4 * i] = __dadd_rn(st[4 * i], __dadd_rn(st[4 * i + 2], nx));
+      it[0] = __dadd_rn(it[0], __dadd_rn(it[2], nx));
       const double ny = tape ? tp[cur++] : mcts_normal(a, c.position_sigma, root, 0u, GCA_MCTS_DRAW_INTRUDER + (uint32_t)i, 2 * gf + 1);
-      st[4 * i + 1] = __dadd_rn(st[4 * i + 1], __dadd_rn(st[4 * i + 3], ny));
+      it[1] = __dadd_rn(it[1], __dadd_rn(it[3], ny));
+      if (c.random_intruders) {                       // nodes_single_randintru.py:64-71
+        double delta = 0.0;
+        bool turn;
+        if (tape) {
+          turn = tp[cur++] < c.turn_prob;             // np.random.random()
+          if (turn) delta = __dmul_rn(tp[cur++], 3.141592653589793 / 180.0);   // math.radians(np.random.uniform(-10, 10))
+        } else {
+          turn = mcts_turn(a, root, 0u, (uint32_t)i, gf, delta);
+        }
+        if (turn) {
+          double tsn, tcs;
+          const double h = __dadd_rn(it[5], delta);
+          gca_sincos(h, &tsn, &tcs);
+          it[2] = __dmul_rn(it[4], tcs);
+          it[3] = __dmul_rn(it[4], tsn);
+          it[5] = h;
+        }
+      }
     }
     own[4] = __dadd_rn(own[4], accel);
-    own[4] = clamp_speed(c, own[3]);
+    own[4] = clamp_speed(c, c.random_intruders ? own[4] : own[3]);     // (:74 clamps the speed; nodes_single.py:60 reads vy, Q23)
     own[4] = __dadd_rn(own[4], tape ? tp[cur++] : mcts_normal(a, c.speed_sigma, root, 0u, GCA_MCTS_DRAW_SPEED, gf));
     own[5] = __dadd_rn(own[5], d_heading);
     own[5] = __dadd_rn(own[5], tape ? tp[cur++] : mcts_normal(a, c.heading_sigma, root, 0u, GCA_MCTS_DRAW_HEADING, gf));
@@ -566,7 +618,7 @@ __global__ void __launch_bounds__(128) mcts_move_kernel(const MctsArgs a) {
     }
     bool conflict = false;
     for (int i = 0; i < a.near && !conflict; ++i) {
-      const double dx = __dadd_rn(st[4 * i], -ox), dy = __dadd_rn(st[4 * i + 1], -oy);
+      const double dx = __dadd_rn(st[a.per * i], -ox), dy = __dadd_rn(st[a.per * i + 1], -oy);
       conflict = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < a.sep2;
     }
     if (conflict) {
@@ -596,8 +648,10 @@ static MctsArgs mcts_base(const gca_mcts_config* cfg, int n) {
   a.c = *cfg;
   a.sep2 = sq_threshold_f64(cfg->minimum_separation);
   a.n = n;
-  a.L = 4 * n + 8;
-  a.near = a.L >= 9 ? (a.L - 9) / 4 : 0;      // (len - 9) // 4: the last intruder is ignored (Q22)
+  a.per = cfg->random_intruders ? 6 : 4;
+  a.L = a.per * n + 8;
+  // (len - 9) // 4: the last intruder is ignored (Q22); nodes_single_randintru.py:47 has (len - 8) // 6 = N
+  a.near = cfg->random_intruders ? n : (a.L >= 9 ? (a.L - 9) / 4 : 0);
   return a;
 }
 
@@ -613,6 +667,14 @@ cudaError_t launch_mcts_playouts(const gca_mcts_config* cfg, int n, const double
   // position_sigma == 0: root-cooperative kernel (intruder trajectories shared by the root's playouts)
   const long long tf = (long long)depth * cfg->simulate_frame;
   const size_t shared_smem = (((size_t)tf * 4 + 15) & ~(size_t)15) + sizeof(double2) * (size_t)tf * (size_t)a.near;
+  const unsigned pblocks = (unsigned)((total + kMctsWarps - 1) / kMctsWarps);
+  if (cfg->random_intruders) {                // every playout moves its own intruders: one warp per playout
+    const size_t smem = sizeof(double) * kMctsWarps * 6 * (size_t)a.near;
+    cudaError_t e = cudaFuncSetAttribute(mcts_playout_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    mcts_playout_kernel<0, true><<<pblocks, kMctsWarps * 32, smem, st>>>(a);
+    return cudaGetLastError();
+  }
   if (cfg->position_sigma == 0.0 && shared_smem <= 160 * 1024 && !getenv("GCA_MCTS_WARP_KERNEL")) {
     cudaError_t e = cudaFuncSetAttribute(mcts_playout_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shared_smem);
     if (e != cudaSuccess) return e;

@@ -39,7 +39,7 @@ def move(states, actions, cfg=None, tape=None, cursor=None, seed=0, id0=0, first
     cfg = cfg or abi.make_mcts_config(default_config())
     assert states.dtype == torch.float64 and states.is_contiguous() and states.is_cuda
     m, L = states.shape
-    n = (L - 8) // 4
+    n = (L - 8) // (6 if cfg.random_intruders else 4)
     actions = actions.to(torch.int32).contiguous()
     flags = torch.zeros(m, dtype=torch.uint8, device=states.device)
     tp = None
@@ -63,7 +63,7 @@ def playouts(roots, n_playouts, depth=None, cfg=None, first_action=None, seed=0,
     depth = cfg.search_depth if depth is None else int(depth)
     assert roots.dtype == torch.float64 and roots.is_contiguous() and roots.is_cuda
     R, L = roots.shape
-    n = (L - 8) // 4
+    n = (L - 8) // (6 if cfg.random_intruders else 4)
     dev = roots.device
     rewards = torch.empty((R, n_playouts), dtype=torch.float64, device=dev)
     first = torch.empty((R, n_playouts), dtype=torch.int8, device=dev)
@@ -97,7 +97,7 @@ def search(roots, n_simulations=None, depth=None, cfg=None, seed=0, root_id0=0, 
     roots = roots.to(torch.float64).contiguous()
     assert roots.is_cuda
     R, L = roots.shape
-    n = (L - 8) // 4
+    n = (L - 8) // (6 if cfg.random_intruders else 4)
     dev = roots.device
     need = int(lib.gca_mcts_search_workspace(C.byref(cfg), n, R, sims, depth))
     key = (dev.index or 0)

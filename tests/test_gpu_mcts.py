@@ -19,17 +19,21 @@ def mcts_cfg(**over):
     return c
 
 
-@pytest.mark.parametrize("n", [3, 80])
-def test_move_replays_reference(n):
+RND = {"random_intruders": 1, "turn_prob": 0.1, "turn_max_deg": 10.0}     # the model of nodes_single_randintru.py
+
+
+@pytest.mark.parametrize("stem,n", [("mcts", 3), ("mcts", 80), ("mctsrnd_model", 3), ("mctsrnd_model", 20)])
+def test_move_replays_reference(stem, n):
     import torch
     from gca_b200 import mcts
-    g = np.load(os.path.join(GOLDEN, "mcts_n%d.npz" % n))
+    g = np.load(os.path.join(GOLDEN, "%s_n%d.npz" % (stem, n)))
+    over = RND if stem != "mcts" else {}
     m = len(g["mv_root"])
     states = torch.as_tensor(g["roots"][g["mv_root"]].copy(), device="cuda")
     actions = torch.as_tensor((g["mv_action"][:, 0] * 3 + g["mv_action"][:, 1]).astype(np.int32), device="cuda")
     tape = torch.as_tensor(np.nan_to_num(g["mv_tape"], nan=0.0), device="cuda")
     cursor = torch.zeros(m, dtype=torch.int64, device="cuda")
-    flags = mcts.move(states, actions, mcts_cfg(), tape=tape, cursor=cursor).cpu().numpy()
+    flags = mcts.move(states, actions, mcts_cfg(**over), tape=tape, cursor=cursor).cpu().numpy()
     assert np.array_equal(cursor.cpu().numpy(), g["mv_tape_len"])
     assert np.array_equal((flags & abi.MCTS_WALL) != 0, g["mv_hit_wall"])
     assert np.array_equal((flags & abi.MCTS_CONFLICT) != 0, g["mv_conflict"])
@@ -45,6 +49,8 @@ def test_move_replays_reference(n):
     (200, 16, 30, 3, {}),                                   # generic (shared-memory) intruder path
     (80, 8, 10, 4, {"simulate_frame": 10}),                 # 40 sub-frames: two lane chunks
     (20, 32, 20, 3, {"speed_sigma": 0.05, "position_sigma": 0.3}),
+    (80, 48, 40, 3, RND), (3, 100, 50, 3, RND), (1, 40, 20, 2, RND), (0, 20, 10, 3, RND),
+    (33, 24, 20, 4, dict(RND, speed_sigma=0.05, position_sigma=0.3, turn_prob=0.5)),
 ])
 def test_playouts_bit_exact_vs_oracle(n, roots_n, playouts, depth, over):
     import torch
@@ -52,7 +58,7 @@ def test_playouts_bit_exact_vs_oracle(n, roots_n, playouts, depth, over):
     from oracle import oracle as orc
     cfg = mcts_cfg(**over)
     rng = np.random.RandomState(n + 7)
-    roots = _random_roots(n, roots_n, n + 7)
+    roots = _random_roots(n, roots_n, n + 7, six=bool(over.get("random_intruders")))
     fa = rng.randint(-1, 9, (roots_n, playouts)).astype(np.int8)
     want_r, want_f, want_fl = orc.mcts_playouts(cfg, n, roots, playouts, depth, first_action=fa, seed=77, root_id0=5)
     got_r, got_f, got_fl = mcts.playouts(torch.as_tensor(roots, device="cuda"), playouts, depth=depth, cfg=cfg,
@@ -71,8 +77,23 @@ def test_warp_per_playout_kernel_bit_exact(n, roots_n, playouts, depth, monkeypa
     test_playouts_bit_exact_vs_oracle(n, roots_n, playouts, depth, {})
 
 
-def _random_roots(n, roots_n, seed):
+def _random_roots(n, roots_n, seed, six=False):
+    """Raw observations: 4 values per intruder (Simulators/SingleAircraftMCTSEnv), or six - + speed, heading - for the
+    random-intruder model."""
     rng = np.random.RandomState(seed)
+    roots = _random_roots4(n, roots_n, rng)
+    if not six:
+        return roots
+    out = np.zeros((roots_n, 6 * n + 8))
+    out[:, 6 * n:] = roots[:, 4 * n:]
+    it = roots[:, :4 * n].reshape(roots_n, n, 4)
+    speed = np.hypot(it[..., 2], it[..., 3])
+    heading = np.arctan2(it[..., 3], it[..., 2])
+    out[:, :6 * n] = np.concatenate([it, speed[..., None], heading[..., None]], -1).reshape(roots_n, 6 * n)
+    return out
+
+
+def _random_roots4(n, roots_n, rng):
     L = 4 * n + 8
     roots = np.zeros((roots_n, L))
     for r in range(roots_n):
@@ -116,6 +137,25 @@ def test_device_tree_search_rejects_position_noise():
     from gca_b200 import mcts
     with pytest.raises(abi.GcaError):
         mcts.search(torch.zeros((2, 16), dtype=torch.float64, device="cuda"), 10, 3, cfg=mcts_cfg(position_sigma=0.5))
+    with pytest.raises(abi.GcaError):      # the random-intruder model: every playout moves its own intruders
+        mcts.search(torch.zeros((2, 20), dtype=torch.float64, device="cuda"), 10, 3, cfg=mcts_cfg(**RND))
+
+
+def test_drop_in_random_intruder_classes():
+    """Agent_RandInt.py:37-41 call sequence on the drop-in classes of nodes_single_randintru.py (host tree, device
+    move / rollout)."""
+    from Algorithms.MCTS.nodes_single_randintru import SingleAircraftNode, SingleAircraftState
+    from Algorithms.MCTS.search_single import MCTS
+    g = np.load(os.path.join(GOLDEN, "mctsrnd_model_n3.npz"))
+    np.random.seed(0)
+    state = SingleAircraftState(state=g["roots"][0])
+    root = SingleAircraftNode(state=state)
+    best = MCTS(root).best_action(30, 2)
+    assert best.state.prev_action in [(a, b) for a in range(3) for b in range(3)]
+    assert len(root.children) == 9 and root.n == 30.0 and all(type(c) is SingleAircraftNode for c in root.children)
+    nxt = state.move((1, 1))
+    assert type(nxt) is SingleAircraftState and nxt.depth == 1 and nxt.state.shape == (6 * 3 + 8,)
+    assert 0.0 <= nxt.reward() <= 1.0 and nxt.dist_intruder() > 0
 
 
 def test_batched_agent_experiment():
