@@ -568,13 +568,32 @@ def bench_mctsrnd(device):
         env.step(acts[i])
     ms = graph_step_ms(lambda i: env.step(acts[i]), GRAPH_STEPS)
     k = env.kernels_per_step
+    # the planner model of Agent_RandInt.py (nodes_single_randintru.py) on these observations: every playout moves and
+    # turns its own intruders, one warp per playout
+    from gca_b200 import abi, mcts
+    from Algorithms.MCTS.config_single import Config as MctsConfig
+    R, P, depth = 2048, 100, 3
+    roots = env.obs[:R].double().contiguous()
+    mcfg = abi.make_mcts_config(MctsConfig, random_intruders=True)
+    mcts.playouts(roots, P, depth=depth, cfg=mcfg, seed=1)
+    torch.cuda.synchronize()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for rep_i in range(3):
+        mcts.playouts(roots, P, depth=depth, cfg=mcfg, seed=2 + rep_i)
+    stop.record()
+    torch.cuda.synchronize()
+    pms = start.elapsed_time(stop) / 3
     env.close()
     peak, _ = measured_peaks()
     bytes_per_env_step = 80 * N + 122
     gbs = bytes_per_env_step * B / (ms * 1e-3) / 1e9
     return {"metric": METRIC, "value": B / (ms * 1e-3), "unit": UNIT, "envs": B, "intruders": N, "ms_per_step": ms,
             "kernels_per_step": k, "obs_dim": 6 * N + 8, "bytes_per_env_step": bytes_per_env_step,
-            "hbm_frac": gbs / peak, "note": "CUDA graph of %d steps replayed" % GRAPH_STEPS}
+            "hbm_frac": gbs / peak, "note": "CUDA graph of %d steps replayed" % GRAPH_STEPS,
+            "model": {"metric": "mcts_rollouts_per_sec", "value": R * P / (pms * 1e-3), "unit": "rollouts/s", "roots": R,
+                      "playouts_per_root": P, "depth": depth, "intruders": N, "ms_per_launch": pms,
+                      "kernel": "mcts_playout_kernel<0, true> (nodes_single_randintru.py model, FP64 bound)"}}
 
 
 def bench_her_replay(device):

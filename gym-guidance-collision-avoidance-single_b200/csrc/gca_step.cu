@@ -984,57 +984,90 @@ __global__ void __launch_bounds__(128) nearest_obs_kernel(const __grid_constant_
 
 // Simulators/SingleAircraftMCTSRandIntruderEnv.py: _update_headings (:166-174, TURN) and the six raw entries per intruder
 // of _get_ob (:133-140).  Both need the FINAL intruder set of the step (after respawns / resets), so this is a pass of
-// its own behind spawn_kernel, like nearest_obs_kernel.  warp = one intruder of the 32 envs of a tile, lane = env:
-// plane reads are the tile-planar lines.  A turn depends on (env, tick, intruder) only (Philox slot GCA_SLOT_TURN).
-// TAPE handles replay the turns inside finish_tile (draw order) and run this pass with TURN = false.
+// its own behind spawn_kernel, like nearest_obs_kernel.  A turn depends on (env, tick, intruder) only (Philox slot
+// GCA_SLOT_TURN).  TAPE handles replay the turns inside finish_tile (draw order) and run this pass with TURN = false.
+// block = 8 intruders of the 32 envs of a tile; warp = one 16-byte plane unit (intruders 2u, 2u + 1), lane = env, so
+// every plane read is a whole 512-byte line.  The six entries per intruder go through shared memory and leave as the
+// 8 x 24 (FAST) / 8 x 48 (FAITHFUL) contiguous bytes of each env's row - a lane storing its own entries 1952 bytes
+// apart touched 32 partly used sectors per instruction and the pass was bound by L1 store sectors (first cut: 83 us).
+constexpr int kTurnIntr = 8;                          // intruders per block
 template <bool FAITH, bool TURN>
 __global__ void __launch_bounds__(128) turn_obs_kernel(const __grid_constant__ StepArgs a) {
   pdl_wait();
   using R = real_t<FAITH>;
+  using V2 = typename std::conditional<FAITH, double2, float2>::type;
+  constexpr int kRowV2 = 3 * kTurnIntr;               // V2 elements of one env's piece
+  constexpr int kRowStride = kRowV2 + 1;              // (+ 1: conflict-free 8 / 16-byte shared accesses by lane = env)
+  __shared__ V2 stage[32 * kRowStride];
   const DevState& s = a.s;
   const gca_config& c = a.cfg;
-  const int lane = threadIdx.x & 31;
-  const int per_tile = (s.N + 3) / 4;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int per_tile = (s.N + kTurnIntr - 1) / kTurnIntr;
   const int tile = (int)(blockIdx.x / per_tile);
-  const int i = (int)(blockIdx.x % per_tile) * 4 + (threadIdx.x >> 5);
+  const int i0 = (int)(blockIdx.x % per_tile) * kTurnIntr;
   const size_t me = (size_t)tile * 32 + lane;
-  if (i >= s.N || me >= (size_t)s.B) return;
-  const int4 cnt = s.counters[me];
-  Intr<FAITH> it;
-  load_intruder<FAITH>(s, cnt.z & 1, me, i, it);
-  double2 ih = s.ihs ? s.ihs[ihs_index(s, me, i)] : make_double2(0.0, 0.0);
-  if constexpr (TURN) {
+  const bool has_env = me < (size_t)s.B;
+  const bool obs = c.obs_kind == GCA_OBS_RAW6;
+  const int u = i0 / 2 + wib;                          // this warp's plane unit
+  if (has_env && 2 * u < s.N) {
+    const int4 cnt = s.counters[me];
+    const int plane = cnt.z & 1;
+    const uint8_t* pbase = s.ipos + (size_t)plane * s.pos_plane;
+    double px[2], py[2];
+    if constexpr (FAITH) {
+      const double2 p0 = *reinterpret_cast<const double2*>(pbase + ipos_offset(s, true, me, 2 * u));
+      const double2 p1 = *reinterpret_cast<const double2*>(pbase + ipos_offset(s, true, me, 2 * u) + 512);   // unit 2u + 1
+      px[0] = p0.x; py[0] = p0.y; px[1] = p1.x; py[1] = p1.y;
+    } else {
+      const float4 p = *reinterpret_cast<const float4*>(pbase + ipos_offset(s, false, me, 2 * u));
+      px[0] = p.x; py[0] = p.y; px[1] = p.z; py[1] = p.w;
+    }
+    const float4 v = *reinterpret_cast<const float4*>(s.ivel + ivel_offset(s, me, 2 * u));
+    float vx[2] = {v.x, v.z}, vy[2] = {v.y, v.w};
     // ep_steps == 0 after a step: the env finished and was reset (auto-reset) - the turns of its old intruders are moot
-    if (c.intruder_turns && s.ihs && !(a.auto_reset && cnt.y == 0)) {
-      Draws<false> d;
-      d.k0 = a.key0; d.k1 = a.key1;
-      d.env = a.env_id0 + (uint32_t)me;
-      d.tick = (uint32_t)cnt.z - 1u;                        // the tick of the step that just ran
-      double p, u;
-      d.uniform2(GCA_SLOT_TURN | (uint32_t)i, 0u, p, u);
-      if (p < c.turn_prob) {
-        // math.radians(np.random.uniform(-10, 10)): low + (high - low) * u, then * (pi / 180)
-        const double raw = __dadd_rn(-c.turn_max_deg, __dmul_rn(__dadd_rn(c.turn_max_deg, c.turn_max_deg), u));
-        double sn, cs;
-        ih.x = __dadd_rn(ih.x, __dmul_rn(raw, 3.141592653589793 / 180.0));
-        gca_sincos(ih.x, &sn, &cs);
-        it.vx = (float)__dmul_rn(ih.y, cs);                 // change_heading :332-336
-        it.vy = (float)__dmul_rn(ih.y, sn);
-        s.ihs[ihs_index(s, me, i)] = ih;
-        store_ivel(s, me, i, it.vx, it.vy);
+    const bool turns = TURN && c.intruder_turns && s.ihs && !(a.auto_reset && cnt.y == 0);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = 2 * u + h;
+      if (i >= s.N) break;
+      double2 ih = s.ihs ? s.ihs[ihs_index(s, me, i)] : make_double2(0.0, 0.0);
+      if (turns) {
+        Draws<false> d;
+        d.k0 = a.key0; d.k1 = a.key1;
+        d.env = a.env_id0 + (uint32_t)me;
+        d.tick = (uint32_t)cnt.z - 1u;                      // the tick of the step that just ran
+        double p, uu;
+        d.uniform2(GCA_SLOT_TURN | (uint32_t)i, 0u, p, uu);
+        if (p < c.turn_prob) {
+          // math.radians(np.random.uniform(-10, 10)): low + (high - low) * u, then * (pi / 180)
+          const double raw = __dadd_rn(-c.turn_max_deg, __dmul_rn(__dadd_rn(c.turn_max_deg, c.turn_max_deg), uu));
+          double sn, cs;
+          ih.x = __dadd_rn(ih.x, __dmul_rn(raw, 3.141592653589793 / 180.0));
+          gca_sincos(ih.x, &sn, &cs);
+          vx[h] = (float)__dmul_rn(ih.y, cs);               // change_heading :332-336
+          vy[h] = (float)__dmul_rn(ih.y, sn);
+          s.ihs[ihs_index(s, me, i)] = ih;
+          store_ivel(s, me, i, vx[h], vy[h]);
+        }
+      }
+      if (obs) {
+        V2* o = stage + lane * kRowStride + 3 * (i - i0);
+        o[0] = V2{(R)px[h], (R)py[h]};
+        o[1] = V2{(R)vx[h], (R)vy[h]};
+        o[2] = V2{(R)ih.y, (R)ih.x};
       }
     }
   }
-  if (c.obs_kind == GCA_OBS_RAW6) {
-    R* o = reinterpret_cast<R*>(a.obs) + me * (size_t)a.D + 6 * (size_t)i;
-    if constexpr (FAITH) {
-      reinterpret_cast<double2*>(o)[0] = make_double2(it.px, it.py);
-      reinterpret_cast<double2*>(o)[1] = make_double2((double)it.vx, (double)it.vy);
-      reinterpret_cast<double2*>(o)[2] = make_double2(ih.y, ih.x);
-    } else {
-      reinterpret_cast<float2*>(o)[0] = make_float2(it.px, it.py);
-      reinterpret_cast<float2*>(o)[1] = make_float2(it.vx, it.vy);
-      reinterpret_cast<float2*>(o)[2] = make_float2((float)ih.y, (float)ih.x);
+  if (!obs) return;                                    // (uniform over the block)
+  __syncthreads();
+  const int n_here = min(kTurnIntr, s.N - i0);
+  const int row_v2 = 3 * n_here;                       // valid V2 elements per env
+  for (int idx = threadIdx.x; idx < 32 * kRowV2; idx += 128) {
+    const int e = idx / kRowV2, j = idx - e * kRowV2;
+    const size_t env = (size_t)tile * 32 + e;
+    if (j < row_v2 && env < (size_t)s.B) {
+      R* dst = reinterpret_cast<R*>(a.obs) + env * (size_t)a.D + 6 * (size_t)i0;     // 8-byte (FAST) / 16-byte aligned
+      reinterpret_cast<V2*>(dst)[j] = stage[e * kRowStride + j];
     }
   }
 }
@@ -1042,7 +1075,7 @@ __global__ void __launch_bounds__(128) turn_obs_kernel(const __grid_constant__ S
 static bool has_turn_pass(const StepArgs& a) {
   return a.s.N > 0 && (a.cfg.obs_kind == GCA_OBS_RAW6 || (a.cfg.intruder_turns && a.s.ihs));
 }
-static unsigned turn_blocks(const DevState& s) { return (unsigned)((size_t)s.T * (size_t)((s.N + 3) / 4)); }
+static unsigned turn_blocks(const DevState& s) { return (unsigned)((size_t)s.T * (size_t)((s.N + kTurnIntr - 1) / kTurnIntr)); }
 
 // ------------------------------------------------------------------------------ launchers
 // launch with programmatic stream serialization (see pdl_wait above)

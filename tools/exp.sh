@@ -1,3 +1,5 @@
 # scratch GPU run
 set -x
-python -m pytest tests/test_gpu_mcts.py -m gpu -x -q > gpurun_out/mcts_pytest.log 2>&1; tail -15 gpurun_out/mcts_pytest.log
+python -m pytest tests -m gpu -x -q -k "mctsrnd or random_configurations" > gpurun_out/rnd_pytest.log 2>&1; tail -5 gpurun_out/rnd_pytest.log
+python tools/mctsrnd_bench.py > gpurun_out/mctsrnd_bench.json 2> gpurun_out/mctsrnd_bench.err; cat gpurun_out/mctsrnd_bench.json; tail -3 gpurun_out/mctsrnd_bench.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/mctsrnd_launches.csv python tools/mctsrnd_bench.py > gpurun_out/mctsrnd_ncu.log 2>&1
