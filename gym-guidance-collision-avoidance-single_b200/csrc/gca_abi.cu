@@ -133,6 +133,7 @@ Derived derive(const gca_config& c) {
               gca_div_f64_divisor_ok(k.dv_2pi) && gca_div_f64_divisor_ok(k.dv_vel) && gca_div_f64_divisor_ok(k.dv_shape);
   k.drift_f = (float)c.position_drift;
   k.has_drift = c.position_drift != 0.0 ? 1 : 0;
+  k.turn_thresh = c.turn_prob > 0.0 ? (unsigned long long)std::ceil(std::ldexp(c.turn_prob < 1.0 ? c.turn_prob : 1.0, 53)) : 0ull;
   return k;
 }
 

@@ -112,6 +112,8 @@ struct Derived {
   int ddiv_ok;                        // all six divisors qualify (gca_div_f64_divisor_ok)
   float drift_f;                      // f32(position_drift), added to the f32 velocity of every advance
   int has_drift;                      // position_drift != 0
+  // u53(...) < turn_prob on the 53-bit integer: v * 2^-53 < t  <=>  v < ceil(t * 2^53) (both sides exact)
+  unsigned long long turn_thresh;
 };
 
 // x / d in f64, correctly rounded, for the host-prepared divisors of Derived

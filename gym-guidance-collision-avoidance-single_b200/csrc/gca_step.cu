@@ -992,13 +992,15 @@ __global__ void __launch_bounds__(128) nearest_obs_kernel(const __grid_constant_
 // apart touched 32 partly used sectors per instruction and the pass was bound by L1 store sectors (first cut: 83 us).
 constexpr int kTurnIntr = 8;                          // intruders per block
 template <bool FAITH, bool TURN>
-__global__ void __launch_bounds__(128) turn_obs_kernel(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(128, 16) turn_obs_kernel(const __grid_constant__ StepArgs a) {
   pdl_wait();
   using R = real_t<FAITH>;
   using V2 = typename std::conditional<FAITH, double2, float2>::type;
   constexpr int kRowV2 = 3 * kTurnIntr;               // V2 elements of one env's piece
   constexpr int kRowStride = kRowV2 + 1;              // (+ 1: conflict-free 8 / 16-byte shared accesses by lane = env)
   __shared__ V2 stage[32 * kRowStride];
+  __shared__ uint16_t turn_list[32 * kTurnIntr];      // (env lane << 3 | intruder - i0) of the intruders that turn
+  __shared__ int turn_count;
   const DevState& s = a.s;
   const gca_config& c = a.cfg;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -1008,7 +1010,11 @@ __global__ void __launch_bounds__(128) turn_obs_kernel(const __grid_constant__ S
   const size_t me = (size_t)tile * 32 + lane;
   const bool has_env = me < (size_t)s.B;
   const bool obs = c.obs_kind == GCA_OBS_RAW6;
+  const bool may_turn = TURN && c.intruder_turns && s.ihs;
   const int u = i0 / 2 + wib;                          // this warp's plane unit
+  if (TURN && threadIdx.x == 0) turn_count = 0;
+  if (TURN) __syncthreads();
+  // ---- phase 1, lane = env: plane reads, who turns, the entries as they stand
   if (has_env && 2 * u < s.N) {
     const int4 cnt = s.counters[me];
     const int plane = cnt.z & 1;
@@ -1023,34 +1029,24 @@ __global__ void __launch_bounds__(128) turn_obs_kernel(const __grid_constant__ S
       px[0] = p.x; py[0] = p.y; px[1] = p.z; py[1] = p.w;
     }
     const float4 v = *reinterpret_cast<const float4*>(s.ivel + ivel_offset(s, me, 2 * u));
-    float vx[2] = {v.x, v.z}, vy[2] = {v.y, v.w};
-    // ep_steps == 0 after a step: the env finished and was reset (auto-reset) - the turns of its old intruders are moot
-    const bool turns = TURN && c.intruder_turns && s.ihs && !(a.auto_reset && cnt.y == 0);
+    const float vx[2] = {v.x, v.z}, vy[2] = {v.y, v.w};
+    // one Philox block holds the p of both intruders of the unit; p < turn_prob is decided on the 53-bit integers, so
+    // the ~90 % that fly on cost no f64 work.  ep_steps == 0 after a step: the env finished and was reset
+    // (auto-reset) - the turns of its old intruders are moot.
+    bool turn_h[2] = {false, false};
+    if (may_turn && !(a.auto_reset && cnt.y == 0)) {
+      const uint4 w = philox4x32_10(make_uint4(a.env_id0 + (uint32_t)me, (uint32_t)cnt.z - 1u, GCA_SLOT_TURN | (uint32_t)u, 0u),
+                                    a.key0, a.key1);
+      turn_h[0] = (((unsigned long long)(w.x >> 5) << 26) | (unsigned long long)(w.y >> 6)) < a.k.turn_thresh;
+      turn_h[1] = (((unsigned long long)(w.z >> 5) << 26) | (unsigned long long)(w.w >> 6)) < a.k.turn_thresh;
+    }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int i = 2 * u + h;
       if (i >= s.N) break;
-      double2 ih = s.ihs ? s.ihs[ihs_index(s, me, i)] : make_double2(0.0, 0.0);
-      if (turns) {
-        Draws<false> d;
-        d.k0 = a.key0; d.k1 = a.key1;
-        d.env = a.env_id0 + (uint32_t)me;
-        d.tick = (uint32_t)cnt.z - 1u;                      // the tick of the step that just ran
-        double p, uu;
-        d.uniform2(GCA_SLOT_TURN | (uint32_t)i, 0u, p, uu);
-        if (p < c.turn_prob) {
-          // math.radians(np.random.uniform(-10, 10)): low + (high - low) * u, then * (pi / 180)
-          const double raw = __dadd_rn(-c.turn_max_deg, __dmul_rn(__dadd_rn(c.turn_max_deg, c.turn_max_deg), uu));
-          double sn, cs;
-          ih.x = __dadd_rn(ih.x, __dmul_rn(raw, 3.141592653589793 / 180.0));
-          gca_sincos(ih.x, &sn, &cs);
-          vx[h] = (float)__dmul_rn(ih.y, cs);               // change_heading :332-336
-          vy[h] = (float)__dmul_rn(ih.y, sn);
-          s.ihs[ihs_index(s, me, i)] = ih;
-          store_ivel(s, me, i, vx[h], vy[h]);
-        }
-      }
+      if (turn_h[h]) turn_list[atomicAdd(&turn_count, 1)] = (uint16_t)((lane << 3) | (i - i0));
       if (obs) {
+        const double2 ih = s.ihs ? s.ihs[ihs_index(s, me, i)] : make_double2(0.0, 0.0);
         V2* o = stage + lane * kRowStride + 3 * (i - i0);
         o[0] = V2{(R)px[h], (R)py[h]};
         o[1] = V2{(R)vx[h], (R)vy[h]};
@@ -1058,8 +1054,38 @@ __global__ void __launch_bounds__(128) turn_obs_kernel(const __grid_constant__ S
       }
     }
   }
-  if (!obs) return;                                    // (uniform over the block)
+  if (!TURN && !obs) return;
   __syncthreads();
+  // ---- phase 2, thread = one turning intruder of the block (about 26 of 256): the f64 work runs densely instead of
+  // once per warp that holds a turner (97 % of them).  change_heading :332-336
+  if constexpr (TURN) {
+    for (int k = threadIdx.x; k < turn_count; k += 128) {
+      const int e = turn_list[k] >> 3, i = i0 + (turn_list[k] & 7);
+      const size_t env = (size_t)tile * 32 + e;
+      Draws<false> d;
+      d.k0 = a.key0; d.k1 = a.key1;
+      d.env = a.env_id0 + (uint32_t)env;
+      d.tick = (uint32_t)s.counters[env].z - 1u;            // the tick of the step that just ran
+      double uu, unused, sn, cs;
+      d.uniform2(GCA_SLOT_TURN | (uint32_t)i, 1u, uu, unused);
+      // math.radians(np.random.uniform(-10, 10)): low + (high - low) * u, then * (pi / 180)
+      const double raw = __dadd_rn(-c.turn_max_deg, __dmul_rn(__dadd_rn(c.turn_max_deg, c.turn_max_deg), uu));
+      double2 ih = s.ihs[ihs_index(s, env, i)];
+      ih.x = __dadd_rn(ih.x, __dmul_rn(raw, 3.141592653589793 / 180.0));
+      gca_sincos(ih.x, &sn, &cs);
+      const float nvx = (float)__dmul_rn(ih.y, cs), nvy = (float)__dmul_rn(ih.y, sn);
+      s.ihs[ihs_index(s, env, i)] = ih;
+      store_ivel(s, env, i, nvx, nvy);
+      if (obs) {
+        V2* o = stage + e * kRowStride + 3 * (i - i0);
+        o[1] = V2{(R)nvx, (R)nvy};
+        o[2] = V2{(R)ih.y, (R)ih.x};
+      }
+    }
+    if (!obs) return;
+    __syncthreads();
+  }
+  // ---- phase 3: each env's piece of the row leaves as contiguous bytes
   const int n_here = min(kTurnIntr, s.N - i0);
   const int row_v2 = 3 * n_here;                       // valid V2 elements per env
   for (int idx = threadIdx.x; idx < 32 * kRowV2; idx += 128) {

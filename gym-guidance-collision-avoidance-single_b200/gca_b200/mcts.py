@@ -118,19 +118,24 @@ def search(roots, n_simulations=None, depth=None, cfg=None, seed=0, root_id0=0, 
 
 
 def run_experiment(num_envs, no_episodes, no_simulations=None, search_depth=None, seed=0, device=0, replan_every=5,
-                   max_steps=None, sim_config=None):
+                   max_steps=None, sim_config=None, random_intruders=False):
     """Algorithms/MCTS/Agent.py:12-63 run_experiment, batched: `num_envs` SingleAircraftMCTSEnv instances advance
     together; every `replan_every` steps (Agent.py:34) each env's raw observation becomes the root of a device-resident
     UCT search whose best first action is repeated until the next re-plan.  Runs until `no_episodes` episodes have
-    finished (in order of completion) and returns the statistics the reference prints (:55-62) plus throughput."""
+    finished (in order of completion) and returns the statistics the reference prints (:55-62) plus throughput.
+
+    random_intruders: Algorithms/MCTS/Agent_RandInt.py instead - Simulators/SingleAircraftMCTSRandIntruderEnv driven by
+    the nodes_single_randintru.py model.  Every playout of that model moves its own intruders, so there is no
+    device-resident tree: each decision spends its simulations as root-parallel playouts (`plan_actions`)."""
     import time
     torch = _torch()
     from .batched import BatchedAircraftEnv
     if sim_config is None:
         from Simulators.config import Config as sim_config
     cfg_cls = default_config()
-    cfg = abi.make_mcts_config(cfg_cls)
-    env = BatchedAircraftEnv("SingleAircraftMCTSEnv", num_envs, sim_config, mode="faithful", device=device, seed=seed)
+    cfg = abi.make_mcts_config(cfg_cls, random_intruders=random_intruders)
+    variant = "SingleAircraftMCTSRandIntruderEnv" if random_intruders else "SingleAircraftMCTSEnv"
+    env = BatchedAircraftEnv(variant, num_envs, sim_config, mode="faithful", device=device, seed=seed)
     obs = env.reset()
     B = num_envs
     dev = obs.device
@@ -148,7 +153,10 @@ def run_experiment(num_envs, no_episodes, no_simulations=None, search_depth=None
             idx = replan.nonzero().squeeze(1)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            action[idx] = search(obs[idx], no_simulations, search_depth, cfg=cfg, seed=seed + 1 + steps)
+            if random_intruders:
+                action[idx] = plan_actions(obs[idx], no_simulations, search_depth, cfg=cfg, seed=seed + 1 + steps)
+            else:
+                action[idx] = search(obs[idx], no_simulations, search_depth, cfg=cfg, seed=seed + 1 + steps)
             e1.record()
             torch.cuda.synchronize()
             search_ms += e0.elapsed_time(e1)

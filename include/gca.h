@@ -80,8 +80,9 @@ enum { GCA_INFO_NONE = 0, GCA_INFO_NMAC = 1, GCA_INFO_CONFLICT = 2, GCA_INFO_GOA
 #define GCA_SLOT_GOAL 0x40000000u    /* block 0: goal (x, y) of a reset */
 #define GCA_SLOT_RESET 0x20000000u   /* | intruder index: spawn made by a reset */
 #define GCA_SLOT_OWN_RESET 0x10000000u /* random_start: ownship drawn by a reset, blocks POS and SPEED_HEADING */
-#define GCA_SLOT_TURN 0x08000000u    /* | intruder index, block 0: (p, u) of _update_headings - the intruder turns by
-                                        radians(-turn_max_deg + 2 * turn_max_deg * u) when p < turn_prob */
+#define GCA_SLOT_TURN 0x08000000u    /* _update_headings: | pair index j, block 0 -> (p of intruder 2j, p of intruder 2j + 1);
+                                        an intruder i with p < turn_prob takes u = first uniform of (| i, block 1) and
+                                        turns by radians(-turn_max_deg + 2 * turn_max_deg * u) */
                                      /* intruder index alone: respawn made inside a step */
 #define GCA_BLOCK_POS 0u             /* (x, y) */
 #define GCA_BLOCK_SPEED_HEADING 1u   /* (speed, heading) */

@@ -497,11 +497,12 @@ static void update_headings(env_view* e) {
       if (!(p < cfg->turn_prob)) continue;
       raw = tape_next(e);
     } else {
-      double u[2];
-      gca_oracle_philox_uniform2(e->seed, e->env_id, e->tick, GCA_SLOT_TURN | (uint32_t)i, 0u, u);
-      p = u[0];
+      double u[2];   /* one block serves the p of an intruder pair; the (rare) turn draws its angle from a block of its own */
+      gca_oracle_philox_uniform2(e->seed, e->env_id, e->tick, GCA_SLOT_TURN | (uint32_t)(i >> 1), 0u, u);
+      p = u[i & 1];
       if (!(p < cfg->turn_prob)) continue;
-      raw = -cfg->turn_max_deg + (cfg->turn_max_deg - -cfg->turn_max_deg) * u[1];   /* numpy: low + (high - low) * u */
+      gca_oracle_philox_uniform2(e->seed, e->env_id, e->tick, GCA_SLOT_TURN | (uint32_t)i, 1u, u);
+      raw = -cfg->turn_max_deg + (cfg->turn_max_deg - -cfg->turn_max_deg) * u[0];   /* numpy: low + (high - low) * u */
     }
     double s, c;
     const double heading = e->ihs[2 * i] + raw * (3.141592653589793 / 180.0);

@@ -169,6 +169,16 @@ def test_batched_agent_experiment():
     print(out)
 
 
+def test_batched_random_intruder_agent_experiment():
+    """Agent_RandInt.py batched: the random-intruder env planned with root-parallel playouts of its own model."""
+    from gca_b200 import mcts
+    out = mcts.run_experiment(num_envs=48, no_episodes=12, no_simulations=36, search_depth=3, seed=5, max_steps=1200,
+                              random_intruders=True)
+    assert out["episodes"] >= 12 and out["searches"] > 0
+    assert 0.0 <= out["nmac_prob"] <= 1.0 and out["goal_prob"] > 0.4, out
+    print(out)
+
+
 def test_drop_in_search_classes():
     """Agent.py:37-41 call sequence on the drop-in classes."""
     from Algorithms.MCTS.nodes_single import SingleAircraftNode, SingleAircraftState

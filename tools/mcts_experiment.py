@@ -20,8 +20,11 @@ def main():
     ap.add_argument("--no_simulations", "-s", type=int, default=100)
     ap.add_argument("--search_depth", "-d", type=int, default=3)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--random-intruders", action="store_true",
+                    help="Agent_RandInt.py: SingleAircraftMCTSRandIntruderEnv + the nodes_single_randintru.py model")
     args = ap.parse_args()
-    out = mcts.run_experiment(args.envs, args.episodes, args.no_simulations, args.search_depth, seed=args.seed)
+    out = mcts.run_experiment(args.envs, args.episodes, args.no_simulations, args.search_depth, seed=args.seed,
+                              random_intruders=args.random_intruders)
     print("----------------------------------------")
     print("intruders: ", 80)
     print("search depth: ", args.search_depth)
