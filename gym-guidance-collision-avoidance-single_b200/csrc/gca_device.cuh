@@ -315,14 +315,12 @@ __device__ __forceinline__ bool in_map_f64(const Derived& k, double x, double y)
 template <bool FAITH>
 struct Intr {
   float px, py, vx, vy;
-  double heading, speed;             // set by spawn() only (Aircraft.heading / .speed)
   static constexpr bool is64 = false;
 };
 template <>
 struct Intr<true> {
   double px, py;
   float vx, vy;
-  double heading, speed;             // set by spawn() only
   bool is64;
 };
 
@@ -357,19 +355,18 @@ __device__ __forceinline__ void store_ivel(const DevState& s, size_t env, int i,
   *reinterpret_cast<float2*>(s.ivel + ivel_offset(s, env, i)) = make_float2(vx, vy);
 }
 
-// the spawn's (heading, speed) for the handles that keep them
-template <bool FAITH>
-__device__ __forceinline__ void store_ihs(const DevState& s, size_t env, int i, const Intr<FAITH>& it) {
-  if (s.ihs) s.ihs[ihs_index(s, env, i)] = make_double2(it.heading, it.speed);
+// where spawn() leaves the (heading, speed) of intruder i - nullptr for the handles that do not keep them
+__device__ __forceinline__ double2* ihs_slot(const DevState& s, size_t env, int i) {
+  return s.ihs ? s.ihs + ihs_index(s, env, i) : nullptr;
 }
 
 // intruder.position += intruder.velocity   PKG/SingleAircraftEnv.py:150, and the map test :153;
 // `+= intruder.velocity + self.position_sigma` (f32 array + Python float: an f32 sum) with a position drift
 // (Simulators/SingleAircraftMCTSRandIntruderEnv.py:183)
-template <bool FAITH>
+template <bool FAITH, bool DRIFT = false>
 __device__ __forceinline__ bool advance(const Derived& k, Intr<FAITH>& it) {
-  const float vx = k.has_drift ? __fadd_rn(it.vx, k.drift_f) : it.vx;
-  const float vy = k.has_drift ? __fadd_rn(it.vy, k.drift_f) : it.vy;
+  const float vx = DRIFT ? __fadd_rn(it.vx, k.drift_f) : it.vx;
+  const float vy = DRIFT ? __fadd_rn(it.vy, k.drift_f) : it.vy;
   if constexpr (FAITH) {
     if (it.is64) {                                       // f64 + f32 -> f64
       it.px = __dadd_rn(it.px, (double)vx);
@@ -410,18 +407,17 @@ __device__ __forceinline__ void separation(const Derived& k, float ox, float oy,
 // PKG/SingleAircraftEnv.py:229-238,269-278 (reset: :80-88)
 template <bool FAITH, bool TAPE>
 __device__ __forceinline__ void spawn(Draws<TAPE>& d, const gca_config& c, const Derived& k, uint32_t slot, float ox,
-                                      float oy, Intr<FAITH>& it) {
+                                      float oy, Intr<FAITH>& it, double2* hs_out) {
   double x, y, speed, heading, sn, cs;
   draw_pos(d, c, slot, GCA_BLOCK_POS, x, y);
   draw_speed_heading(d, c, slot, speed, heading);
+  if (hs_out) *hs_out = make_double2(heading, speed);    // Aircraft.heading / .speed, kept by the turning-intruder variant
   it.px = (float)x;
   it.py = (float)y;
   if constexpr (FAITH) it.is64 = false;
   gca_sincos(heading, &sn, &cs);
   it.vx = (float)__dmul_rn(speed, cs);
   it.vy = (float)__dmul_rn(speed, sn);
-  it.heading = heading;
-  it.speed = speed;
   int retries = 0;
   for (;;) {
     bool a, b, lt_init;

@@ -106,10 +106,9 @@ __device__ __forceinline__ void reset_env_warp(const StepArgs& a, size_t env, in
         for (int j = 0; j < 32 && r * 32 + j < s.N; ++j) {
           const int i = r * 32 + j;
           Intr<FAITH> it;
-          spawn<FAITH, TAPE>(d, c, k, GCA_SLOT_RESET | (uint32_t)i, ox, oy, it);
+          spawn<FAITH, TAPE>(d, c, k, GCA_SLOT_RESET | (uint32_t)i, ox, oy, it, ihs_slot(s, env, i));
           store_ipos<FAITH>(s, plane, env, i, it);
           store_ivel(s, env, i, it.vx, it.vy);
-          store_ihs<FAITH>(s, env, i, it);
           dw |= (it.is64 ? 1u : 0u) << j;
           write_obs_intruder<FAITH>(a, obase, i, it);
         }
@@ -125,10 +124,9 @@ __device__ __forceinline__ void reset_env_warp(const StepArgs& a, size_t env, in
       Intr<FAITH> it;
       bool wide = false;
       if (valid) {
-        spawn<FAITH, TAPE>(d, c, k, GCA_SLOT_RESET | (uint32_t)i, ox, oy, it);
+        spawn<FAITH, TAPE>(d, c, k, GCA_SLOT_RESET | (uint32_t)i, ox, oy, it, ihs_slot(s, env, i));
         store_ipos<FAITH>(s, plane, env, i, it);
         store_ivel(s, env, i, it.vx, it.vy);
-        store_ihs<FAITH>(s, env, i, it);
         write_obs_intruder<FAITH>(a, obase, i, it);
         wide = it.is64;
       }
@@ -317,10 +315,9 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
   // reset_intruder() for intruder i of this lane's env   :153-154, :229-238
   auto respawn_own = [&](int i, uint32_t& set64) {
     Intr<FAITH> it;
-    spawn<FAITH, TAPE>(d, c, k, (uint32_t)i, pos.x, pos.y, it);
+    spawn<FAITH, TAPE>(d, c, k, (uint32_t)i, pos.x, pos.y, it, ihs_slot(s, me, i));
     store_ipos<FAITH>(s, nxt, me, i, it);
     store_ivel(s, me, i, it.vx, it.vy);
-    store_ihs<FAITH>(s, me, i, it);
     set64 |= (it.is64 ? 1u : 0u) << (i & 31);
     write_obs_intruder<FAITH>(a, obase, i, it);
   };
@@ -615,10 +612,9 @@ __global__ void __launch_bounds__(128) spawn_kernel(const __grid_constant__ Step
         // ep_steps == 0 after a step: the env finished and was reset (auto-reset); all its intruders are new anyway
         if (cnt.y != 0 || !a.auto_reset) {
           Intr<FAITH> it;
-          spawn<FAITH, false>(d, a.cfg, a.k, (uint32_t)i, own.x, own.y, it);
+          spawn<FAITH, false>(d, a.cfg, a.k, (uint32_t)i, own.x, own.y, it, ihs_slot(s, env, i));
           store_ipos<FAITH>(s, cnt.z & 1, env, i, it);
           store_ivel(s, env, i, it.vx, it.vy);
-          store_ihs<FAITH>(s, env, i, it);
           write_obs_intruder<FAITH>(a, obs_intruder_base<FAITH>(a, env), i, it);
           if constexpr (FAITH) {
             if (it.is64) atomicOr(&s.dflag[flag_index(s, env, i >> 5)], 1u << (i & 31));
@@ -637,10 +633,9 @@ __global__ void __launch_bounds__(128) spawn_kernel(const __grid_constant__ Step
       if (i < s.N) {
         Intr<FAITH> it;
         const float2 own = s.own_pos[env];                 // (50, 50) :72-76, or the random start finish_tile drew
-        spawn<FAITH, false>(d, a.cfg, a.k, GCA_SLOT_RESET | (uint32_t)i, own.x, own.y, it);
+        spawn<FAITH, false>(d, a.cfg, a.k, GCA_SLOT_RESET | (uint32_t)i, own.x, own.y, it, ihs_slot(s, env, i));
         store_ipos<FAITH>(s, cnt.z & 1, env, i, it);
         store_ivel(s, env, i, it.vx, it.vy);
-        store_ihs<FAITH>(s, env, i, it);
         write_obs_intruder<FAITH>(a, obs_intruder_base<FAITH>(a, env), i, it);
         wide = it.is64;
       }
@@ -669,8 +664,11 @@ __global__ void __launch_bounds__(128) step_finish_kernel(const __grid_constant_
 // layout; FAST only): entries are computed without run-time layout tests and leave through the transposed
 // shared-memory write-out.  2 = the same for the own-first layouts GCA_OBS_HER / GCA_OBS_DHER, whose intruder
 // entries start 24 bytes into the row: 8-byte stores.  0 = generic (any layout, both modes): per-lane stores.
-template <bool FAITH, int OM>
+// DRIFT: every advance adds Config.position_sigma to the velocity (the random-intruder env); generic layout only, so the
+// instruction streams of the other instantiations are what they were without it.
+template <bool FAITH, int OM, bool DRIFT = false>
 __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __grid_constant__ StepArgs a) {
+  static_assert(!(DRIFT && OM), "a handle with a position drift takes the generic observation path");
   if (PDL_EARLY) pdl_launch_dependents();
   pdl_wait();
   GCA_KSTAMP_IN(1);
@@ -727,10 +725,9 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
 #pragma unroll
       for (int g = 0; g < kChunkUnits; ++g) {
         float4 dv = vv[g];
-        if constexpr (OM == 0) {                            // (a handle with a position drift never takes the specialised paths)
-          if (k.has_drift) dv = make_float4(__fadd_rn(dv.x, k.drift_f), __fadd_rn(dv.y, k.drift_f),
-                                            __fadd_rn(dv.z, k.drift_f), __fadd_rn(dv.w, k.drift_f));
-        }
+        if constexpr (DRIFT)                                // position += velocity + position_sigma (f32 sum first)
+          dv = make_float4(__fadd_rn(dv.x, k.drift_f), __fadd_rn(dv.y, k.drift_f), __fadd_rn(dv.z, k.drift_f),
+                           __fadd_rn(dv.w, k.drift_f));
         np[g] = make_float4(__fadd_rn(p[g].x, dv.x), __fadd_rn(p[g].y, dv.y),      // position += velocity :150
                             __fadd_rn(p[g].z, dv.z), __fadd_rn(p[g].w, dv.w));
         // 0 <= x <= W on f32 bit patterns (:153): a non-negative float is <= W iff its pattern is (as unsigned);
@@ -822,7 +819,7 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
         it.vy = (j & 1) ? vq[j >> 1].w : vq[j >> 1].y;
         it.is64 = (dw >> j) & 1u;
         if (runs) {
-          const bool oob = advance<FAITH>(k, it);             // :150, :153
+          const bool oob = advance<FAITH, DRIFT>(k, it);      // :150, :153
           bool lt_sep, lt_nmac, lt_init;
           separation<FAITH>(k, ox, oy, it, lt_sep, lt_nmac, lt_init);   // :151
           gone |= (oob ? 1u : 0u) << j;
@@ -872,7 +869,7 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
         it.px = q.x; it.py = q.y;
       }
       if (runs) {
-        const bool oob = advance<FAITH>(k, it);             // :150, :153
+        const bool oob = advance<FAITH, DRIFT>(k, it);      // :150, :153
         bool lt_sep, lt_nmac, lt_init;
         separation<FAITH>(k, ox, oy, it, lt_sep, lt_nmac, lt_init);   // :151
         gone |= (oob ? 1u : 0u) << j;
@@ -1142,12 +1139,14 @@ static cudaError_t launch_step_t(const StepArgs& a, cudaStream_t st, cudaEvent_t
     const int n_chunks = (s.U + kChunkUnits - 1) / kChunkUnits;
     const unsigned blocks = (unsigned)(((long long)s.T * n_chunks + kWarpsB - 1) / kWarpsB);
     if constexpr (FAITH) {
-      launch_pdl(step_intruders_kernel<true, 0>, blocks, kWarpsB * 32, st, a);
+      if (a.k.has_drift) launch_pdl(step_intruders_kernel<true, 0, true>, blocks, kWarpsB * 32, st, a);
+      else launch_pdl(step_intruders_kernel<true, 0>, blocks, kWarpsB * 32, st, a);
     } else {
       const bool own_first = a.cfg.obs_kind == GCA_OBS_HER || a.cfg.obs_kind == GCA_OBS_DHER;
       const bool special = a.k.div1_ok && !a.k.has_drift;
       if (special && a.cfg.obs_kind == GCA_OBS_VECTOR) launch_pdl(step_intruders_kernel<false, 1>, blocks, kWarpsB * 32, st, a);
       else if (special && own_first) launch_pdl(step_intruders_kernel<false, 2>, blocks, kWarpsB * 32, st, a);
+      else if (a.k.has_drift) launch_pdl(step_intruders_kernel<false, 0, true>, blocks, kWarpsB * 32, st, a);
       else launch_pdl(step_intruders_kernel<false, 0>, blocks, kWarpsB * 32, st, a);
     }
   }
