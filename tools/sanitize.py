@@ -54,6 +54,23 @@ for B, N, mode in ((200, 80, "fast"), (70, 5, "faithful")):
     env.close()
     print("ok d9her", B, N, mode, flush=True)
 
+# random-intruder env: heading / speed plane, drift instantiation of the streaming pass, turn + six-entry observation pass
+rnd_roots = None
+for B, N, mode in ((200, 80, "fast"), (70, 5, "faithful"), (45, 7, "fast"), (33, 1, "faithful")):
+    env = BatchedAircraftEnv("SingleAircraftMCTSRandIntruderEnv", B, SimConfig, n_intruders=N, mode=mode, seed=6)
+    env.reset()
+    for t in range(40):
+        o, r, d, i = env.step(torch.randint(0, 9, (B,), device="cuda", dtype=torch.int32), auto_reset=(t % 2 == 0))
+        if t % 5 == 0 and bool(d.any()):
+            env.reset(mask=d)
+    env.observe()
+    env.set_state(env.get_state())
+    if rnd_roots is None:
+        rnd_roots = env.obs[:24].double().contiguous().clone()
+    torch.cuda.synchronize()
+    env.close()
+    print("ok mctsrnd", B, N, mode, flush=True)
+
 # MCTS: both playout kernels, the move kernel, the device-resident search
 from gca_b200 import abi, mcts, replay  # noqa: E402
 from Algorithms.MCTS.config_single import Config as MctsConfig  # noqa: E402
@@ -67,6 +84,9 @@ mcts.playouts(roots, 11, depth=3, cfg=cfg, seed=1)
 del os.environ["GCA_MCTS_WARP_KERNEL"]
 mcts.search(roots, 60, 3, cfg=cfg, seed=4)
 mcts.move(roots.clone(), torch.randint(0, 9, (48,), device="cuda", dtype=torch.int32), cfg)
+rcfg = abi.make_mcts_config(MctsConfig, random_intruders=True)      # the nodes_single_randintru.py model
+mcts.playouts(rnd_roots, 9, depth=3, cfg=rcfg, seed=1)
+mcts.move(rnd_roots.clone(), torch.randint(0, 9, (24,), device="cuda", dtype=torch.int32), rcfg)
 torch.cuda.synchronize()
 print("ok mcts", flush=True)
 
