@@ -593,7 +593,7 @@ def bench_mctsrnd(device):
             "hbm_frac": gbs / peak, "note": "CUDA graph of %d steps replayed" % GRAPH_STEPS,
             "model": {"metric": "mcts_rollouts_per_sec", "value": R * P / (pms * 1e-3), "unit": "rollouts/s", "roots": R,
                       "playouts_per_root": P, "depth": depth, "intruders": N, "ms_per_launch": pms,
-                      "kernel": "mcts_playout_kernel<0, true> (nodes_single_randintru.py model, FP64 bound)"}}
+                      "kernel": "mcts_playout_kernel<0, true> (nodes_single_randintru.py model; one warp per playout, intruders out of reach culled exactly)"}}
 
 
 def bench_her_replay(device):

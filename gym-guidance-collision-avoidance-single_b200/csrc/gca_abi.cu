@@ -631,8 +631,8 @@ int gca_mcts_playouts(const gca_mcts_config* cfg, int n_intruders, const double*
   if (!cfg || n_intruders < 0 || n_roots < 0 || playouts <= 0 || depth < 0 || (n_roots > 0 && (!roots || !rewards)))
     return fail(GCA_ERR_INVALID, "bad arguments");
   if (cfg->simulate_frame <= 0) return fail(GCA_ERR_INVALID, "simulate_frame must be positive");
-  if (cfg->random_intruders && (size_t)n_intruders * 6 * 4 * sizeof(double) > 200 * 1024)
-    return fail(GCA_ERR_INVALID, "random_intruders playouts keep 4 x 6 N doubles in shared memory: at most 1066 intruders");
+  if (cfg->random_intruders && (size_t)n_intruders * 52 * 4 > 200 * 1024)
+    return fail(GCA_ERR_INVALID, "random_intruders playouts keep 4 x 52 N bytes in shared memory: at most 984 intruders");
   GCA_CUDA(cudaSetDevice(device));
   GCA_CUDA(launch_mcts_playouts(cfg, n_intruders, roots, (long long)n_roots, playouts, depth, first_action, seed,
                                 root_id0, rewards, first_out, flags, (cudaStream_t)stream));

@@ -60,6 +60,7 @@ struct MctsArgs {
   long long tape_stride;
   long long* cursor;
   int first_frame;
+  int cull;                 // random_intruders playouts: drop the intruders that cannot come within the separation radius
 };
 
 __device__ __forceinline__ void mcts_uniform2(const MctsArgs& a, uint32_t root, uint32_t playout, uint32_t what,
@@ -134,7 +135,12 @@ __global__ void __launch_bounds__(kMctsWarps * 32) mcts_playout_kernel(const Mct
 
   // ---- intruders: lane i + 32 r holds (x, y, vx, vy)
   double ix[RC > 0 ? RC : 1], iy[RC > 0 ? RC : 1], ivx[RC > 0 ? RC : 1], ivy[RC > 0 ? RC : 1];
-  double* sm = mcts_smem + (size_t)warp_in_block * PER * a.near;    // RC == 0 only
+  // RC == 0 only: this warp's intruders, then (RND) their original indices - what the Philox draws are addressed by
+  const size_t warp_doubles = (size_t)PER * a.near + (RND ? ((size_t)a.near + 1) / 2 : 0);
+  double* sm = mcts_smem + (size_t)warp_in_block * warp_doubles;
+  int* sidx = reinterpret_cast<int*>(sm + (size_t)PER * a.near);
+  int n_eff = a.near;                                               // intruders this playout simulates
+  (void)sidx;
   if constexpr (RC > 0) {
 #pragma unroll
     for (int r = 0; r < RC; ++r) {
@@ -144,6 +150,37 @@ __global__ void __launch_bounds__(kMctsWarps * 32) mcts_playout_kernel(const Mct
       const double2 w = v ? reinterpret_cast<const double2*>(st)[2 * i + 1] : make_double2(0., 0.);
       ix[r] = p.x; iy[r] = p.y; ivx[r] = w.x; ivy[r] = w.y;
     }
+  } else if constexpr (RND) {
+    // Without position / speed noise every aircraft moves at most its speed per sub-frame (an intruder: its root
+    // velocity until it first turns, then `speed` along its heading; the ownship: clamp(...) <= max_speed).  An
+    // intruder further away at the root than both reaches plus the separation radius can never raise the conflict
+    // flag in this playout, and nothing else of it is observable (reward and flags are the only outputs): it is
+    // dropped.  The survivors keep their index - the draws of intruder i are addressed by i - so the playout is
+    // bit-identical to the one that simulates all N (what the oracle does); typically ~10 of 80 remain.
+    const double frames = (double)a.depth * (double)c.simulate_frame;
+    const double own_reach = fmax(fabs(c.max_speed), fabs(c.min_speed)) * frames;
+    n_eff = 0;
+    for (int base = 0; base < a.near; base += 32) {
+      const int i = base + lane;
+      double v[6] = {0., 0., 0., 0., 0., 0.};
+      bool keep = false;
+      if (i < a.near) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) v[q] = st[6 * i + q];
+        const double dx = v[0] - own[0], dy = v[1] - own[1];
+        const double reach = fmax(sqrt(v[2] * v[2] + v[3] * v[3]), fabs(v[4])) * frames;
+        keep = !a.cull || !(sqrt(dx * dx + dy * dy) > own_reach + reach + c.minimum_separation + 2.0);   // (NaN: kept)
+      }
+      const uint32_t mask = __ballot_sync(FULL, keep);
+      const int at = n_eff + __popc(mask & ((1u << lane) - 1u));
+      if (keep) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) sm[6 * at + q] = v[q];
+        sidx[at] = i;
+      }
+      n_eff += __popc(mask);
+    }
+    __syncwarp();
   } else {
     for (int j = lane; j < PER * a.near; j += 32) sm[j] = st[j];
     __syncwarp();
@@ -225,16 +262,18 @@ __global__ void __launch_bounds__(kMctsWarps * 32) mcts_playout_kernel(const Mct
             }
           }
         } else {
-          for (int i = lane; i < a.near; i += 32) {
-            const double npx = mcts_normal(a, c.position_sigma, root, playout, GCA_MCTS_DRAW_INTRUDER + (uint32_t)i, 2 * gfu);
-            const double npy = mcts_normal(a, c.position_sigma, root, playout, GCA_MCTS_DRAW_INTRUDER + (uint32_t)i, 2 * gfu + 1);
+          for (int i = lane; i < n_eff; i += 32) {
+            uint32_t ii = (uint32_t)i;                                // the intruder's own index addresses its draws
+            if constexpr (RND) ii = (uint32_t)sidx[i];
+            const double npx = mcts_normal(a, c.position_sigma, root, playout, GCA_MCTS_DRAW_INTRUDER + ii, 2 * gfu);
+            const double npy = mcts_normal(a, c.position_sigma, root, playout, GCA_MCTS_DRAW_INTRUDER + ii, 2 * gfu + 1);
             const double x = __dadd_rn(sm[PER * i], __dadd_rn(sm[PER * i + 2], npx));
             const double y = __dadd_rn(sm[PER * i + 1], __dadd_rn(sm[PER * i + 3], npy));
             sm[PER * i] = x;
             sm[PER * i + 1] = y;
             if constexpr (RND) {                                      // the turn follows the advance (:64-71)
               double delta;
-              if (mcts_turn(a, root, playout, (uint32_t)i, gfu, delta)) {
+              if (mcts_turn(a, root, playout, ii, gfu, delta)) {
                 double tsn, tcs;
                 const double h = __dadd_rn(sm[6 * i + 5], delta);
                 gca_sincos(h, &tsn, &tcs);
@@ -669,7 +708,8 @@ cudaError_t launch_mcts_playouts(const gca_mcts_config* cfg, int n, const double
   const size_t shared_smem = (((size_t)tf * 4 + 15) & ~(size_t)15) + sizeof(double2) * (size_t)tf * (size_t)a.near;
   const unsigned pblocks = (unsigned)((total + kMctsWarps - 1) / kMctsWarps);
   if (cfg->random_intruders) {                // every playout moves its own intruders: one warp per playout
-    const size_t smem = sizeof(double) * kMctsWarps * 6 * (size_t)a.near;
+    const size_t smem = sizeof(double) * kMctsWarps * (6 * (size_t)a.near + ((size_t)a.near + 1) / 2);
+    a.cull = cfg->position_sigma == 0.0 && cfg->speed_sigma == 0.0 && !getenv("GCA_MCTS_NO_CULL");
     cudaError_t e = cudaFuncSetAttribute(mcts_playout_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     mcts_playout_kernel<0, true><<<pblocks, kMctsWarps * 32, smem, st>>>(a);

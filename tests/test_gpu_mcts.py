@@ -77,6 +77,14 @@ def test_warp_per_playout_kernel_bit_exact(n, roots_n, playouts, depth, monkeypa
     test_playouts_bit_exact_vs_oracle(n, roots_n, playouts, depth, {})
 
 
+def test_random_intruder_playouts_without_culling_bit_exact(monkeypatch):
+    """The random-intruder playout kernel drops the intruders that cannot reach the ownship within the playout (exact:
+    results are compared with the oracle, which simulates all of them, above); with the culling switched off
+    (GCA_MCTS_NO_CULL) the kernel must give the same bits."""
+    monkeypatch.setenv("GCA_MCTS_NO_CULL", "1")
+    test_playouts_bit_exact_vs_oracle(80, 24, 30, 3, RND)
+
+
 def _random_roots(n, roots_n, seed, six=False):
     """Raw observations: 4 values per intruder (Simulators/SingleAircraftMCTSEnv), or six - + speed, heading - for the
     random-intruder model."""

@@ -1,3 +1,4 @@
-# scratch GPU run: every kernel at small / ragged sizes (compute-sanitizer is closed on this pool: plain run as a crash check)
+# scratch GPU run
 set -x
-timeout 600 python tools/sanitize.py > gpurun_out/san_plain.log 2>&1; echo rc=$?; tail -12 gpurun_out/san_plain.log
+python -m pytest tests/test_gpu_mcts.py -m gpu -x -q > gpurun_out/mcts_pytest.log 2>&1; tail -5 gpurun_out/mcts_pytest.log
+python tools/mctsrnd_bench.py > gpurun_out/mctsrnd_bench.json 2> gpurun_out/mctsrnd_bench.err; cat gpurun_out/mctsrnd_bench.json; tail -3 gpurun_out/mctsrnd_bench.err
