@@ -1,4 +1,6 @@
-# scratch GPU run
+# scratch GPU run: A/B of compile-time knobs on the headline step
 set -x
-python -m pytest tests/test_gpu_mcts.py -m gpu -x -q > gpurun_out/mcts_pytest.log 2>&1; tail -5 gpurun_out/mcts_pytest.log
-python tools/mctsrnd_bench.py > gpurun_out/mctsrnd_bench.json 2> gpurun_out/mctsrnd_bench.err; cat gpurun_out/mctsrnd_bench.json; tail -3 gpurun_out/mctsrnd_bench.err
+python tools/ab_step.py 2>&1 | tail -3
+GCA_LIB=$PWD/gym-guidance-collision-avoidance-single_b200/lib/ab/libgca_pdl.so python tools/ab_step.py 2>&1 | tail -3
+GCA_LIB=$PWD/gym-guidance-collision-avoidance-single_b200/lib/ab/libgca_w2.so python tools/ab_step.py 2>&1 | tail -3
+python tools/ab_step.py 2>&1 | tail -3
