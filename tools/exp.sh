@@ -1,5 +1,3 @@
-# scratch GPU run: parity suite and smoke on the current tree
+# scratch GPU run: one full capture of the turn / observation pass of the random-intruder env
 set -x
-python -m pytest tests -m gpu -q > gpurun_out/r1_pytest_gpu.log 2>&1; tail -3 gpurun_out/r1_pytest_gpu.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-python tools/mctsrnd_bench.py 2>/dev/null | cut -c1-220
+ncu --set full --clock-control none --cache-control none --import-source on -k regex:turn_obs -s 3 -c 1 -f -o gpurun_out/r1_prof_turn python tools/mctsrnd_bench.py > gpurun_out/r1_ncu_turn.log 2>&1; tail -3 gpurun_out/r1_ncu_turn.log
