@@ -88,6 +88,17 @@ def test_variant_table_matches_reference_reward_rows():
     assert (r.r_wall, r.r_goal, r.wall_kind, r.max_steps, r.obs_kind) == (-10, 10000, abi.WALL_PENALTY, 1000, abi.OBS_NONE)
     r = rows["SingleAircraftMCTSEnv"]
     assert (r.r_nmac, r.r_conflict, r.r_goal, r.obs_kind, r.heading_sigma) == (-1.0, -0.5, 1.0, abi.OBS_RAW, np.radians(4))
+    r = rows["SingleAircraftMCTSRandIntruderEnv"]      # Simulators/SingleAircraftMCTSRandIntruderEnv.py:133-140, :166-174, :183
+    assert (r.obs_kind, r.intruder_turns, r.turn_prob, r.turn_max_deg, r.position_drift) == (abi.OBS_RAW6, 1, 0.1, 10.0, 10 / 30)
+    assert variants.obs_dim(r, 80) == 488 and abi.load().gca_obs_dim(ctypes.byref(r), 80) == 488
+    assert all(rows[k].intruder_turns == 0 and rows[k].position_drift == 0.0 for k in rows if k != "SingleAircraftMCTSRandIntruderEnv")
+    from Algorithms.MCTS.config_single import Config as MctsConfig
+    m = abi.make_mcts_config(MctsConfig, random_intruders=True)     # nodes_single_randintru.py:47, :64-65
+    assert (m.random_intruders, m.turn_prob, m.turn_max_deg) == (1, 0.1, 10.0) and abi.make_mcts_config(MctsConfig).random_intruders == 0
+    import Simulators.SingleAircraftMCTSRandIntruderEnv as rnd_mod
+    import Algorithms.MCTS.nodes_single_randintru as rnd_nodes
+    assert rnd_mod.SingleAircraftEnv.VARIANT == "SingleAircraftMCTSRandIntruderEnv"
+    assert rnd_nodes.SingleAircraftState.RANDOM_INTRUDERS and rnd_nodes.SingleAircraftState.model_config().random_intruders == 1
     assert Config.intruder_size == 0 and Sim.intruder_size == 80          # Q28
     assert (Config.minimum_separation, Config.NMAC_dist, Config.initial_min_dist, Config.goal_radius) == (18.5, 5.0, 100.0, 20.0)
     assert variants.obs_dim(rows["SingleAircraftEnv"], 80) == 328 and variants.obs_dim(rows["SingleAircraftHEREnv"], 80) == 326
