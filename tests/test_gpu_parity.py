@@ -224,14 +224,16 @@ def test_step_host_equals_device_path():
     assert h2d == 2048 * 4 and d2h == 2048 * (328 * 4 + 4 + 1 + 1)
 
 
-def test_state_roundtrip_and_independence_of_batch_split():
+@pytest.mark.parametrize("vk", ["env", "mctsrnd"])
+def test_state_roundtrip_and_independence_of_batch_split(vk):
     """set_state(get_state()) is the identity, and env b evolves the same whatever batch it sits in
     (Philox is keyed by the global env id: the basis of multi-GPU sharding)."""
     from gca_b200.batched import BatchedAircraftEnv
     torch = _torch()
-    cfgc = config_class("env")
-    whole = BatchedAircraftEnv("SingleAircraftEnv", 600, cfgc, n_intruders=40, seed=5)
-    part = BatchedAircraftEnv("SingleAircraftEnv", 200, cfgc, n_intruders=40, seed=5, env_id0=400)
+    cfgc = config_class(vk)
+    name = GOLDEN_VARIANTS[vk]
+    whole = BatchedAircraftEnv(name, 600, cfgc, n_intruders=40, seed=5)
+    part = BatchedAircraftEnv(name, 200, cfgc, n_intruders=40, seed=5, env_id0=400)
     whole.reset(); part.reset()
     rng = np.random.RandomState(1)
     for _ in range(25):
@@ -240,7 +242,7 @@ def test_state_roundtrip_and_independence_of_batch_split():
     sw, sp = whole.get_state(), part.get_state()
     for k in STATE_KEYS:
         assert np.array_equal(sw[k][400:], sp[k]), k
-    clone = BatchedAircraftEnv("SingleAircraftEnv", 600, cfgc, n_intruders=40, seed=5)
+    clone = BatchedAircraftEnv(name, 600, cfgc, n_intruders=40, seed=5)
     clone.set_state(sw)
     a = torch.as_tensor(rng.randint(0, 9, 600).astype(np.int32), device="cuda")
     o1 = whole.step(a)[0].cpu().numpy()
