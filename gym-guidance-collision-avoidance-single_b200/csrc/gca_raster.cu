@@ -250,8 +250,9 @@ __global__ void __launch_bounds__(kRasterThreads, 2) raster_kernel(const RasterA
         }
         const float2 v = *reinterpret_cast<const float2*>(s.ivel + ivel_offset(s, (size_t)env, i));
         // the intruder's heading is constant for life (:207-211); its direction is that of the velocity
+        // (a zero velocity - only gca_set_state can make one - has no direction: drawn with heading 0, never a NaN pose)
         const float len = __fsqrt_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)));
-        const float ch = __fdiv_rn(v.x, len), sh = __fdiv_rn(v.y, len);
+        const float ch = len > 0.0f ? __fdiv_rn(v.x, len) : 1.0f, sh = len > 0.0f ? __fdiv_rn(v.y, len) : 0.0f;
         p = make_float4(px, py, sh, -ch);
       }
       pose[tid] = p;

@@ -2,12 +2,16 @@
 
 The reference draws three 32x32 RGBA sprites (PKG/images/{aircraft,goal,intruder}.png,
 PKG/SingleAircraftStackEnv.py:193-212).  Those files are the reference's assets and are not
-copied here: `default_sprites()` builds look-alikes procedurally (an aircraft silhouette nose-up in
-yellow / red, a five-pointed green star, anti-aliased alpha), and `load_sprites(dir)` loads the
-original PNGs when the user points at a checkout of the reference.
+shipped with the product: `resolve_sprites()` loads the ORIGINAL PNGs when it is told where a checkout of
+the reference (or just its images directory) is - constructor argument `sprite_dir=` or the environment
+variables GCA_SPRITE_DIR / GCA_REFERENCE - and only then is the picture the reference's picture
+(pinned to an independent renderer in tests/test_gpu_raster.py).  Without one it falls back, with a
+warning, to `default_sprites()`: look-alikes built procedurally (an aircraft silhouette nose-up in
+yellow / red, a five-pointed green star, anti-aliased alpha) - same geometry, different texels.
 Layout: uint8 [3, 32, 32, 4] = (ownship, goal, intruder) x rows top->bottom x columns x RGBA.
 """
 import os
+import warnings
 
 import numpy as np
 
@@ -67,3 +71,38 @@ def load_sprites(image_dir):
             raise ValueError("%s must be %dx%d" % (name, SIZE, SIZE))
         out[idx] = a
     return out
+
+
+_IMAGES_SUBDIR = os.path.join("gym_guidance_collision_avoidance_single", "envs", "images")
+
+
+def find_sprite_dir(sprite_dir=None):
+    """Directory holding the reference's aircraft.png / goal.png / intruder.png, or None.  `sprite_dir` (argument),
+    then $GCA_SPRITE_DIR, then $GCA_REFERENCE; each may be the images directory itself or the root of a checkout."""
+    for cand in (sprite_dir, os.environ.get("GCA_SPRITE_DIR"), os.environ.get("GCA_REFERENCE")):
+        if not cand:
+            continue
+        for d in (cand, os.path.join(cand, _IMAGES_SUBDIR)):
+            if os.path.isfile(os.path.join(d, "aircraft.png")):
+                return d
+        if cand is sprite_dir:
+            raise FileNotFoundError("sprite_dir=%r holds no aircraft.png (nor %s under it)" % (cand, _IMAGES_SUBDIR))
+    return None
+
+
+def resolve_sprites(sprites=None, sprite_dir=None):
+    """The texture array the rasteriser gets: an explicit array, else the reference's PNGs (find_sprite_dir), else the
+    look-alikes - with a warning, because the frames then differ from the reference's by construction."""
+    if sprites is not None:
+        sp = np.ascontiguousarray(sprites, np.uint8)
+        if sp.shape != (3, SIZE, SIZE, 4):
+            raise ValueError("sprites must be uint8 [3, 32, 32, 4]")
+        return sp
+    d = find_sprite_dir(sprite_dir)
+    if d is not None:
+        return load_sprites(d)
+    warnings.warn("SingleAircraftStackEnv: the reference's sprite PNGs were not found (pass sprite_dir= or set "
+                  "GCA_SPRITE_DIR / GCA_REFERENCE to a checkout of the reference); drawing procedural look-alikes - "
+                  "geometry, draw order and post-processing are the reference's, the texels are not", RuntimeWarning,
+                  stacklevel=3)
+    return default_sprites()

@@ -23,7 +23,7 @@ class ImageBatch(object):
     """B StackEnv instances: fused step kernel + rasteriser, frames kept in a k-plane ring on the GPU."""
 
     def __init__(self, num_envs, config=None, n_intruders=None, frame_stack=1, device=0, seed=0, env_id0=0,
-                 mode="fast", sprites=None):
+                 mode="fast", sprites=None, sprite_dir=None):
         torch = _torch()
         if config is None:
             from gym_guidance_collision_avoidance_single.envs.config import Config as config
@@ -32,8 +32,7 @@ class ImageBatch(object):
         b = self.batch
         self.num_envs, self.k = b.num_envs, int(frame_stack)
         self.H, self.W = int(config.window_height) // 4, int(config.window_width) // 4
-        sp = _sprites.default_sprites() if sprites is None else np.ascontiguousarray(sprites, np.uint8)
-        assert sp.shape == (3, 32, 32, 4)
+        sp = _sprites.resolve_sprites(sprites, sprite_dir)     # the reference's PNGs when a checkout is known
         self.sprites = torch.as_tensor(sp, device=b.device)
         self.ring = torch.zeros((self.num_envs, self.k, self.H, self.W), dtype=torch.uint8, device=b.device)
         self.slot = 0
@@ -82,8 +81,8 @@ class SingleAircraftStackEnv(_SingleBase):
     non-terminal wall penalty, goal reward 10000 (Q18)."""
     VARIANT = "SingleAircraftStackEnv"
 
-    def __init__(self, device=0, seed=None, mode="faithful", time_limit=0, sprites=None):
-        self._sprites_arg = sprites
+    def __init__(self, device=0, seed=None, mode="faithful", time_limit=0, sprites=None, sprite_dir=None):
+        self._sprites_arg = _sprites.resolve_sprites(sprites, sprite_dir)
         self._img = None
         _SingleBase.__init__(self, device=device, seed=seed, mode=mode, time_limit=time_limit)
 
@@ -97,8 +96,7 @@ class SingleAircraftStackEnv(_SingleBase):
         dim = (self.window_width // 4, self.window_height // 4, 1)
         self.observation_space = Box(low=0, high=255, shape=dim, dtype=np.uint8)
         self.action_space = Discrete(9)
-        sp = _sprites.default_sprites() if self._sprites_arg is None else np.ascontiguousarray(self._sprites_arg, np.uint8)
-        self._sp = torch.as_tensor(sp, device=self._batch.device)
+        self._sp = torch.as_tensor(self._sprites_arg, device=self._batch.device)
         self._img = torch.zeros((1, 1, dim[1], dim[0]), dtype=torch.uint8, device=self._batch.device)
 
     def _format_obs(self):

@@ -36,6 +36,18 @@ VARIANTS = {
 }
 
 
+def default_config_class(variant):
+    """The Config class the reference's class of this name reads when none is given: the Simulators/ copies (Config-
+    driven reward row `rewards=None`, or the nearest-n observation) `import config` = Simulators/config.py (it has
+    NMAC_penalty / sparse_reward / n / diagonal ...), the registered classes the package's envs/config.py."""
+    row = VARIANTS[variant]
+    if row[4] is None or row[1] == abi.OBS_NEAREST:
+        from Simulators.config import Config
+    else:
+        from gym_guidance_collision_avoidance_single.envs.config import Config
+    return Config
+
+
 def make_config(variant, cfg_cls, time_limit=0):
     """Snapshot the class attributes of `cfg_cls` (the reference's Config idiom,
     PKG/SingleAircraftEnv.py:49-64, :286-297) into a gca_config for `variant`."""

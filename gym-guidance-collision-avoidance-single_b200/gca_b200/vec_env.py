@@ -37,20 +37,19 @@ _CLASS_OF = {
 
 class AircraftVecEnv(object):
     def __init__(self, env, num_envs, config=None, n_intruders=None, mode="fast", device=0, seed=0, env_id0=0,
-                 host=False, time_limit=None, frame_stack=1, sprites=None):
-        """frame_stack / sprites apply to the image variant only (SingleAircraftStackEnv): k > 1 is baselines'
-        VecFrameStack(venv, k) (common/vec_env/vec_frame_stack.py) with the frames kept in a ring on the device."""
+                 host=False, time_limit=None, frame_stack=1, sprites=None, sprite_dir=None):
+        """frame_stack / sprites / sprite_dir apply to the image variant only (SingleAircraftStackEnv): k > 1 is baselines'
+        VecFrameStack(venv, k) (common/vec_env/vec_frame_stack.py) with the frames kept in a ring on the device;
+        sprite_dir points at the reference's images (gca_b200/sprites.py)."""
         variant = _CLASS_OF.get(env, env)
         registered = env in _CLASS_OF
         self._image = None
         if variant == "SingleAircraftStackEnv":
-            self._init_image(num_envs, config, n_intruders, mode, device, seed, env_id0, host, frame_stack, sprites)
+            self._init_image(num_envs, config, n_intruders, mode, device, seed, env_id0, host, frame_stack, sprites, sprite_dir)
             return
         if config is None:
-            if variant in ("SingleAircraftMCTSEnv", "SingleAircraftDiscrete9HEREnv"):
-                from Simulators.config import Config as config
-            else:
-                from gym_guidance_collision_avoidance_single.envs.config import Config as config
+            from .variants import default_config_class
+            config = default_config_class(variant)
         self.variant = variant
         self.num_envs = int(num_envs)
         self.host = bool(host)
@@ -68,23 +67,24 @@ class AircraftVecEnv(object):
                 desired_goal=Box(-np.inf, np.inf, shape=(2,), dtype="float32"),
                 achieved_goal=Box(-np.inf, np.inf, shape=(2,), dtype="float32"),
                 observation=Box(-np.inf, np.inf, shape=(b.obs_dim,), dtype="float32")))
-        else:
+        else:   # (the random-intruder env declares 4 N + 8 and returns 6 N + 8 values, Simulators/SingleAircraftMCTSRandIntruderEnv.py:52: kept)
             self.observation_space = Box(low=-1000, high=1000, shape=(4 * n + 8,), dtype=np.float32)
         if b.continuous:
             self.action_space = Box(low=-1, high=1, shape=(2,), dtype=np.float32)
         else:
-            self.action_space = Discrete(3 if b.cfg.action_kind == abi.ACT_DISCRETE3 else 9)
+            # Discrete(3): PKG/SingleAircraftDiscreteHEREnv.py and Simulators/SingleAircraftDiscrete3HEREnv.py (heading only)
+            self.action_space = Discrete(3 if b.cfg.action_kind in (abi.ACT_DISCRETE3, abi.ACT_DISCRETE3_HEADING) else 9)
         self._pending = None
         self.closed = False
 
-    def _init_image(self, num_envs, config, n_intruders, mode, device, seed, env_id0, host, frame_stack, sprites):
+    def _init_image(self, num_envs, config, n_intruders, mode, device, seed, env_id0, host, frame_stack, sprites, sprite_dir=None):
         from .stack import ImageBatch
         if host:
             raise ValueError("the image variant keeps its frames on the device (host=False)")
         self.variant = "SingleAircraftStackEnv"
         self.num_envs, self.host = int(num_envs), False
         self._image = ImageBatch(num_envs, config, n_intruders=n_intruders, frame_stack=frame_stack, device=device,
-                                 seed=seed, env_id0=env_id0, mode=mode, sprites=sprites)
+                                 seed=seed, env_id0=env_id0, mode=mode, sprites=sprites, sprite_dir=sprite_dir)
         self.batch = self._image.batch
         k = self._image.k
         # PKG/SingleAircraftStackEnv.py:34-35 (200 x 200 x 1 uint8), repeated k times on the last axis by VecFrameStack

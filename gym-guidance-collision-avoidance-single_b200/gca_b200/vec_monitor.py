@@ -98,6 +98,13 @@ class AircraftVecMonitor(object):
         import torch
         obs, rews, dones, infos = self.venv.step_wait()
         b = self.venv.batch
+        ret = (obs, rews, dones, infos)
+        if getattr(self.venv, "host", False):
+            # host=True hands out numpy views of pinned buffers: the accumulators live on the device, so the 6 bytes per
+            # env of (reward, done, info) go back up (never a host pointer into a device kernel)
+            rews = torch.as_tensor(np.ascontiguousarray(rews), device=b.device)
+            dones = torch.as_tensor(np.ascontiguousarray(dones).astype(np.uint8), device=b.device)
+            infos = torch.as_tensor(np.ascontiguousarray(infos, np.uint8), device=b.device)
         abi.check(b.lib.gca_monitor_update(rews.data_ptr(), 1 if rews.dtype == torch.float64 else 0, dones.data_ptr(),
                                            self.num_envs, self.eprets.data_ptr(), self.eplens.data_ptr(),
                                            self._ring.data_ptr(), self.cap, self._count.data_ptr(),
@@ -107,7 +114,7 @@ class AircraftVecMonitor(object):
                                          b.device.index or 0, C.c_void_p(torch.cuda.current_stream(b.device).cuda_stream)))
         self._times[self._step & 0xffffffff] = round(time.time() - self.tstart, 6)
         self._step += 1
-        return obs, rews, dones, infos
+        return ret
 
     def step(self, actions):
         self.step_async(actions)

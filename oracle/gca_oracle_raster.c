@@ -61,7 +61,7 @@ int gca_oracle_raster(const gca_config* cfg, const gca_oracle_batch* b, const un
       const float vx = b->st.ivel[2 * k], vy = b->st.ivel[2 * k + 1];
       const float len = sqrtf(vx * vx + vy * vy);
       p.cx = (float)b->st.ipos[2 * k]; p.cy = (float)b->st.ipos[2 * k + 1];
-      p.rc = vy / len; p.rs = -(vx / len); p.tex = 2;
+      p.rc = len > 0.0f ? vy / len : 0.0f; p.rs = len > 0.0f ? -(vx / len) : -1.0f; p.tex = 2;   /* (no direction: heading 0) */
       draw(fb, W, H, p, sprites + 2 * 32 * 32 * 4);
     }
     if (rgb) memcpy(rgb + (size_t)e * W * H * 3, fb, (size_t)W * H * 3);

@@ -30,7 +30,7 @@ sys.path[:0] = [os.path.join(HERE, "_gymstub"), REF, os.path.join(REF, "Simulato
                 os.path.join(REF, "Algorithms", "MCTS")]
 
 from gym_guidance_collision_avoidance_single.envs import (  # noqa: E402
-    SingleAircraftEnv, SingleAircraft2Env, SingleAircraftHEREnv, SingleAircraftDiscreteHEREnv)
+    SingleAircraftEnv, SingleAircraft2Env, SingleAircraftHEREnv, SingleAircraftDiscreteHEREnv, SingleAircraftStackEnv)
 from gym_guidance_collision_avoidance_single.envs.config import Config as PkgConfig  # noqa: E402
 import SingleAircraftMCTSEnv as mcts_env_mod  # noqa: E402  (Simulators/, uses Simulators/config.py)
 import SingleAircraftDiscrete9HEREnv as d9her_mod  # noqa: E402  (Simulators/, nearest-n observation)
@@ -171,6 +171,9 @@ def override(env, kind, rng, n):
                 it.position[:] = np.float32(p)
             else:
                 it.position = np.asarray(p, np.float64)
+    elif kind == "near_maxsteps":            # StackEnv: `steps >= max_steps` fires inside the trace (:134-136)
+        env.steps = int(env.max_steps - rng.randint(2, 30))
+        d.position[:] = np.float32(rng.uniform(150, 650, 2))
     # anything else (e.g. near_intruder with n == 0): leave the reset state alone
 
 
@@ -186,9 +189,12 @@ VARIANTS = {
     "simenv": (simenv_mod.SingleAircraftEnv, SimConfigMod.Config, "d9"),
     "rndenv": (rndenv_mod.SingleAircraftRandomEnv, SimConfigMod.Config, "d9"),
     "mctsrnd": (mctsrnd_mod.SingleAircraftEnv, SimConfigMod.Config, "t33"),
+    # the dynamics of the image env (max_steps rule, non-terminal wall penalty, goal +10000); its observation is the GL
+    # frame, which cannot be drawn here: _get_ob is replaced by an empty array so that render() is never called
+    "stack": (SingleAircraftStackEnv, PkgConfig, "d9"),
 }
 # np.argpartition(dist_array, Config.n) of the nearest-n observation needs more than n = 4 intruders
-PLANS = {"mctsrnd": {1: (4, 40), 3: (5, 40), 80: (3, 30)}, "simenv": {3: (3, 40), 80: (2, 25)}, "rndenv": {3: (3, 40), 80: (2, 25)}, "d9her": {5: (5, 40), 12: (5, 40), 80: (3, 30)}, "d3her": {5: (5, 40), 12: (5, 40), 80: (3, 30)}}
+PLANS = {"stack": {0: (3, 40), 3: (6, 40), 80: (3, 30)}, "mctsrnd": {1: (4, 40), 3: (5, 40), 80: (3, 30)}, "simenv": {3: (3, 40), 80: (2, 25)}, "rndenv": {3: (3, 40), 80: (2, 25)}, "d9her": {5: (5, 40), 12: (5, 40), 80: (3, 30)}, "d3her": {5: (5, 40), 12: (5, 40), 80: (3, 30)}}
 
 
 def sample_action(kind, rng):
@@ -227,6 +233,8 @@ def run_trace(variant, n, seed, kind, T):
     rng = np.random.RandomState((1000003 * seed + 17) % (2 ** 32))   # private: never touches the global stream
     np.random.seed(seed)
     env = cls()                                          # HER ctors reset() here; draws discarded
+    if variant == "stack":
+        env._get_ob = lambda: np.zeros(0)                # (the frame: make_stack_frame_golden)
     rec = {k: [] for k in ("actions", "obs", "ag", "dg", "reward", "reward_is_int", "done", "info", "event", "nearest",
                            "reward_is_f32",
                            "no_conflict", "cur_before", "cur_after", "cur_after_reset", "reset_obs",
@@ -320,7 +328,7 @@ def make_env_goldens():
         for n, (per_kind, T) in PLANS.get(variant, plan).items():
             traces, kind_ids = [], []
             seed = 100 * n + 7
-            for ki, kind in enumerate(kinds):
+            for ki, kind in enumerate(kinds + (["near_maxsteps"] if variant == "stack" else [])):
                 if n == 0 and kind in ("near_intruder", "edge_intruders"):
                     continue
                 for _ in range(per_kind):
@@ -504,6 +512,88 @@ def make_mctsrnd_model_goldens():
     return meta
 
 
+# ----------------------------------------------------------------------------- StackEnv picture
+def _load_rgba(path):
+    from PIL import Image
+    return np.asarray(Image.open(path).convert("RGBA"), np.uint8)
+
+
+def render_independent(own_pos, own_heading, goal, ipos, iheading, sprites_rgba, W=800, H=800):
+    """An INDEPENDENT software rendition of PKG/SingleAircraftStackEnv.py:179-214 + gym's rendering.Viewer (white
+    clear; each sprite a 32x32 textured quad centred on the entity, rotated by heading - pi/2, goal unrotated;
+    GL_LINEAR texture filter; GL_SRC_ALPHA / GL_ONE_MINUS_SRC_ALPHA blending into an 8-bit colour buffer; draw order
+    ownship, goal, intruders; returned array flipped so that row 0 is y = H).  float64 numpy + scipy.ndimage
+    bilinear sampling: shares no code and no arithmetic with csrc/gca_raster_spec.h.  Returns uint8 [H, W, 3]."""
+    from scipy import ndimage
+    fb = np.full((H, W, 3), 255.0)                                     # row 0 = top of the picture
+    def draw(cx, cy, rot, tex):
+        texf = tex[::-1].astype(np.float64)                            # row index = v, 0 at the bottom of the image
+        x0, x1 = max(int(math.floor(cx - 24)), 0), min(int(math.ceil(cx + 24)), W - 1)
+        y0, y1 = max(int(math.floor(cy - 24)), 0), min(int(math.ceil(cy + 24)), H - 1)
+        if x0 > x1 or y0 > y1:
+            return
+        X, Y = np.meshgrid(np.arange(x0, x1 + 1) + 0.5, np.arange(y0, y1 + 1) + 0.5)   # pixel centres, world units
+        dx, dy = X - cx, Y - cy
+        c, s_ = math.cos(rot), math.sin(rot)
+        lx, ly = c * dx + s_ * dy, -s_ * dx + c * dy                   # quad-local coordinates
+        inside = (lx >= -16) & (lx < 16) & (ly >= -16) & (ly < 16)
+        coords = np.stack([ly + 15.5, lx + 15.5])                      # texel centres at integer + 0.5
+        samp = np.stack([ndimage.map_coordinates(texf[:, :, k], coords, order=1, mode="nearest") for k in range(4)], -1)
+        alpha = samp[..., 3:4] / 255.0
+        rows = (H - 1) - np.arange(y0, y1 + 1)                         # world row y -> picture row
+        dst = fb[rows[:, None], np.arange(x0, x1 + 1)[None, :]]
+        out = np.rint(samp[..., :3] * alpha + dst * (1.0 - alpha))     # 8-bit colour buffer after every draw
+        fb[rows[:, None], np.arange(x0, x1 + 1)[None, :]] = np.where(inside[..., None], out, dst)
+    draw(float(own_pos[0]), float(own_pos[1]), own_heading - math.pi / 2, sprites_rgba[0])
+    draw(float(goal[0]), float(goal[1]), 0.0, sprites_rgba[1])
+    for p, h in zip(ipos, iheading):
+        draw(float(p[0]), float(p[1]), h - math.pi / 2, sprites_rgba[2])
+    return np.clip(fb, 0, 255).astype(np.uint8)
+
+
+def make_stack_frame_golden():
+    """Frames of the image env: states taken from the unmodified reference StackEnv (reset + a few steps, engineered
+    starts so that sprites overlap each other and the map border), drawn with the reference's own PNG sprites by
+    render_independent(), then the reference's preprocess_frame (real cv2: RGB2GRAY + INTER_AREA 4x)."""
+    import cv2
+    img_dir = os.path.join(REF, "gym_guidance_collision_avoidance_single", "envs", "images")
+    sprites = np.stack([_load_rgba(os.path.join(img_dir, f)) for f in ("aircraft.png", "goal.png", "intruder.png")])
+    rec = {k: [] for k in ("own_pos", "own_hs", "goal", "ipos", "ivel", "iheading", "n", "frame")}
+    NMAX = 80
+    rng = np.random.RandomState(31)
+    for n, kind, seed, steps in ((0, "plain", 1, 0), (3, "plain", 2, 3), (3, "near_intruder", 3, 2), (3, "near_goal", 4, 1),
+                                 (3, "near_wall", 5, 2), (12, "edge_intruders", 6, 4), (80, "plain", 7, 0),
+                                 (80, "mid", 8, 5), (80, "near_intruder", 9, 3), (80, "edge_intruders", 10, 6)):
+        PkgConfig.intruder_size = n
+        np.random.seed(1000 + seed)
+        env = SingleAircraftStackEnv()
+        env._get_ob = lambda: np.zeros(0)
+        env.reset()
+        override(env, kind, rng, n)
+        for _ in range(steps):
+            _, _, done, _ = env.step(int(rng.randint(9)))
+            if done:
+                env.reset()
+        d = env.drone
+        ipos = np.zeros((NMAX, 2)); ivel = np.zeros((NMAX, 2), np.float32); ihd = np.zeros(NMAX)
+        for i, it in enumerate(env.intruder_list):
+            ipos[i], ivel[i], ihd[i] = np.asarray(it.position, np.float64), it.velocity, it.heading
+        rgb = render_independent(d.position, d.heading, env.goal.position, ipos[:n], ihd[:n], sprites)
+        frame = env.preprocess_frame(rgb)[:, :, 0]                     # PKG/SingleAircraftStackEnv.py:104-108, real cv2
+        rec["own_pos"].append(np.asarray(d.position, np.float32)); rec["own_hs"].append((d.heading, d.speed))
+        rec["goal"].append(np.asarray(env.goal.position, np.float64)); rec["ipos"].append(ipos); rec["ivel"].append(ivel)
+        rec["iheading"].append(ihd); rec["n"].append(n); rec["frame"].append(frame)
+    out = {k: np.asarray(v) for k, v in rec.items()}
+    np.savez_compressed(os.path.join(HERE, "stack_frames.npz"), **out)
+    # the sprites themselves, as test vectors (the product never ships them: gca_b200/sprites.py)
+    import shutil
+    os.makedirs(os.path.join(HERE, "sprites"), exist_ok=True)
+    for f in ("aircraft.png", "goal.png", "intruder.png"):
+        shutil.copyfile(os.path.join(img_dir, f), os.path.join(HERE, "sprites", f))
+        os.chmod(os.path.join(HERE, "sprites", f), 0o644)
+    return {"stack_frames": {"frames": len(rec["n"]), "non_white_pixels": [int((f != 255).sum()) for f in rec["frame"]]}}
+
+
 def make_her_reward_golden():
     """compute_reward of both GoalEnv variants on random + engineered pairs."""
     rng = np.random.RandomState(5)
@@ -607,6 +697,8 @@ def main():
             meta.update(make_d9her_reward_golden())
         if "her_sampler" in only.split(","):
             meta.update(make_her_sampler_golden())
+        if "stack" in only.split(","):
+            meta.update(make_stack_frame_golden())
         if "mctsrnd_model" in only.split(","):
             meta.update(make_mctsrnd_model_goldens())
         with open(os.path.join(HERE, "META.json"), "w") as f:
@@ -624,6 +716,7 @@ def main():
     meta.update(make_her_reward_golden())
     meta.update(make_d9her_reward_golden())
     meta.update(make_her_sampler_golden())
+    meta.update(make_stack_frame_golden())
     with open(os.path.join(HERE, "META.json"), "w") as f:
         json.dump(meta, f, indent=1, sort_keys=True)
 

@@ -9,8 +9,8 @@ sincos/log (gca_math.h) everything is bit-exact, in both modes, at every size.
 import numpy as np
 import pytest
 
-from helpers import (GOAL_VARIANTS, GOLDEN_CASES, GOLDEN_N, GOLDEN_VARIANTS, STATE_KEYS, assert_state_equal, config_class, golden_actions,
-                     golden_config, golden_state, load_trace)
+from helpers import (FAST_TOL, GOAL_VARIANTS, GOLDEN_CASES, GOLDEN_N, GOLDEN_VARIANTS, STATE_KEYS, assert_state_equal, config_class,
+                     fast_obs_tol, golden_actions, golden_config, golden_state, load_trace)
 
 pytestmark = pytest.mark.gpu
 
@@ -57,8 +57,9 @@ def test_golden_replay_faithful(vk, n):
     her = vk in GOAL_VARIANTS
 
     # reset from the tape start
+    D = env.obs_dim                                              # 0 for the image env: its vector observation is empty
     env.set_tape(tape)
-    obs = env.reset().cpu().numpy()
+    obs = env.reset().cpu().numpy()[:, :D]
     ref.reset()
     assert np.array_equal(env.tape_cursor.cpu().numpy(), np.broadcast_to(g["cur_reset0"], (B,)))
     assert_state_equal(env.get_state(), ref.state, "reset vs oracle %s n=%d" % (vk, n))
@@ -73,7 +74,7 @@ def test_golden_replay_faithful(vk, n):
     env.set_state(st)
     for k, v in st.items():
         ref.state[k][...] = v
-    assert close(env.observe().cpu().numpy(), g["obs0"])
+    assert close(env.observe().cpu().numpy()[:, :D], g["obs0"])
 
     acts = golden_actions(vk, g)
     exact = total = 0
@@ -81,7 +82,7 @@ def test_golden_replay_faithful(vk, n):
         what = "%s n=%d step %d" % (vk, n, t)
         obs, rew, done, info = env.step(gpu_actions(env, acts[:, t]), auto_reset=False)
         ref.step(acts[:, t])
-        obs, rew, done, info = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy(), info.cpu().numpy()
+        obs, rew, done, info = obs.cpu().numpy()[:, :D], rew.cpu().numpy(), done.cpu().numpy(), info.cpu().numpy()
         # --- against the reference itself
         assert np.array_equal(info, g["event"][:, t]), what
         assert np.array_equal(done, g["done"][:, t]), what
@@ -109,15 +110,78 @@ def test_golden_replay_faithful(vk, n):
             env.reset(mask=done)
             ref.reset(mask=done)
             rows = np.nonzero(done)[0]
-            assert close(env.obs.cpu().numpy()[rows], g["reset_obs"][rows, t]), what
-            assert np.array_equal(env.obs.cpu().numpy()[rows], ref.obs[rows]), what
+            assert close(env.obs.cpu().numpy()[rows, :D], g["reset_obs"][rows, t]), what
+            assert np.array_equal(env.obs.cpu().numpy()[rows, :D], ref.obs[rows]), what
         assert np.array_equal(env.tape_cursor.cpu().numpy(), g["cur_after_reset"][:, t]), what
     env.close()
     print("%s n=%d: %d/%d step outputs bit-identical to the reference" % (vk, n, exact, total))
 
 
+@pytest.mark.parametrize("vk,n", GOLDEN_CASES)
+def test_golden_replay_fast(vk, n):
+    """The fp32 ("fast") mode - what bench.py measures - against the traces recorded from the unmodified reference:
+    free-running replay from the recorded start state with the recorded draws.  Flags, done, conflict counters,
+    per-intruder conflict flags and the number of draws consumed must be IDENTICAL over the whole horizon; positions,
+    observations, rewards inside the stated fp32 tolerance (helpers.FAST_TOL).  And every bit
+    equals the oracle's f32_positions twin evaluated with the shared sincos / log."""
+    from oracle import oracle as orc
+    g = load_trace(vk, n)
+    B = g["tape"].shape[0]
+    tape = np.nan_to_num(g["tape"], nan=0.0)
+    env = make_gpu(vk, n, B, "fast", "tape")
+    ref = make_oracle(vk, n, B, 0, orc.TRIG_SHARED, tape=tape, f32=True)
+    D = env.obs_dim
+    st = golden_state(g, "s0_")
+    st["ipos"] = st["ipos"].astype(np.float32).astype(np.float64)   # the fast mode's storage rule (a retried spawn's f64
+    st["ipos_is_f64"][...] = 0                                      # position is kept rounded to f32: Q3 dropped)
+    env.set_state(st)
+    env.set_tape(tape, cursor=np.broadcast_to(g["cur_reset0"], (B,)))
+    for k, v in st.items():
+        ref.state[k][...] = v
+    ref.cursor[...] = g["cur_reset0"]
+    f64 = lambda x: x.cpu().numpy().astype(np.float64)
+    otol = fast_obs_tol(vk)
+    assert np.abs(f64(env.observe())[:, :D] - g["obs0"]).max(initial=0) <= otol
+    acts = golden_actions(vk, g)
+    worst = {"pos": 0.0, "obs": 0.0, "reward": 0.0}
+    for t in range(acts.shape[1]):
+        what = "%s n=%d step %d" % (vk, n, t)
+        obs, rew, done, info = env.step(gpu_actions(env, acts[:, t]), auto_reset=False)
+        ref.step(acts[:, t])
+        done, info = done.cpu().numpy(), info.cpu().numpy()
+        # --- against the reference itself: exact flags and draw counts
+        assert np.array_equal(info, g["event"][:, t]) and np.array_equal(done, g["done"][:, t]), what
+        assert np.array_equal(env.tape_cursor.cpu().numpy(), g["cur_after"][:, t]), what
+        state = env.get_state()
+        want = golden_state(g, "sa_", (slice(None), t))
+        assert np.array_equal(state["no_conflict"], want["no_conflict"]) and np.array_equal(state["iflag"], want["iflag"]), what
+        # --- values inside the stated tolerance
+        dp = max(np.abs(state["own_pos"] - want["own_pos"]).max(), np.abs(state["ipos"] - want["ipos"]).max(initial=0))
+        do = np.abs(f64(obs)[:, :D] - g["obs"][:, t]).max(initial=0)
+        dr = np.abs(f64(rew) - g["reward"][:, t]).max()
+        assert dp <= FAST_TOL["pos"] and do <= otol and dr <= FAST_TOL["reward"], (what, dp, do, dr)
+        worst = {"pos": max(worst["pos"], dp), "obs": max(worst["obs"], do), "reward": max(worst["reward"], dr)}
+        if vk in GOAL_VARIANTS:
+            gtol = FAST_TOL["pos"] if vk == "dher" else FAST_TOL["obs"]
+            assert np.abs(f64(env.achieved) - g["ag"][:, t]).max() <= gtol and np.abs(f64(env.desired) - g["dg"][:, t]).max() <= gtol
+        if vk == "d3her":
+            assert np.abs(f64(env.nearest) - g["nearest"][:, t]).max() <= FAST_TOL["nearest"], what
+        # --- against the oracle twin: every bit
+        assert np.array_equal(obs.cpu().numpy()[:, :D], ref.obs.astype(np.float32)), what
+        assert np.array_equal(rew.cpu().numpy(), ref.reward.astype(np.float32)), what
+        assert_state_equal(state, ref.state, what + " vs oracle", skip=())
+        if done.any():
+            env.reset(mask=done)
+            ref.reset(mask=done)
+            rows = np.nonzero(done)[0]
+            assert np.abs(f64(env.obs)[rows, :D] - g["reset_obs"][rows, t]).max(initial=0) <= otol, what
+        assert np.array_equal(env.tape_cursor.cpu().numpy(), g["cur_after_reset"][:, t]), what
+    env.close()
+    print("%s n=%d fast mode: max |d| positions %.2e px, observation %.2e, reward %.2e" % (vk, n, worst["pos"], worst["obs"], worst["reward"]))
+
+
 @pytest.mark.parametrize("vk,n", [("env", 80), ("env2", 80), ("her", 3), ("dher", 80), ("mcts", 80), ("d9her", 80),
-                                  ("d9her", 12), ("d3her", 80), ("mctsrnd", 80), ("mctsrnd", 3)])
+                                  ("d9her", 12), ("d3her", 80), ("mctsrnd", 80), ("mctsrnd", 3), ("stack", 80), ("stack", 3)])
 def test_teacher_forced_single_steps(vk, n):
     """Load each recorded reference state, take ONE step, compare with the next recorded state
     (chaotic divergence cannot hide a bug)."""
@@ -134,7 +198,7 @@ def test_teacher_forced_single_steps(vk, n):
         assert np.array_equal(info.cpu().numpy()[ok], g["event"][ok, t])
         assert np.array_equal(done.cpu().numpy()[ok], g["done"][ok, t])
         assert close(rew.cpu().numpy()[ok], g["reward"][ok, t])
-        assert close(obs.cpu().numpy()[ok], g["obs"][ok, t])
+        assert close(obs.cpu().numpy()[ok][:, :env.obs_dim], g["obs"][ok, t])
         st = env.get_state()
         want = golden_state(g, "sa_", (slice(None), t))
         assert np.array_equal(st["no_conflict"][ok], want["no_conflict"][ok])

@@ -1,6 +1,7 @@
-"""StackEnv image observation on the GPU: every pixel against the CPU restatement (which is the
-specification), the 4-frame ring against VecFrameStack's roll semantics, and the
-variant's reward / termination rules through the facade."""
+"""StackEnv image observation on the GPU: every pixel against the CPU restatement (the specification,
+DESIGN.md 4.5), against frames of an independent renderer drawn with the reference's own sprites, the
+4-frame ring against VecFrameStack's roll semantics, and the variant's reward / termination rules through the
+facade."""
 import numpy as np
 import pytest
 
@@ -14,15 +15,50 @@ def _cfg():
     return Config
 
 
-@pytest.mark.parametrize("n,B,mode", [(80, 24, "fast"), (80, 8, "faithful"), (0, 4, "fast"), (126, 6, "fast"), (5, 40, "fast")])
-def test_frames_equal_cpu_restatement(n, B, mode):
+def _sprite_set(which):
+    import os
+    if which == "reference":                                  # the reference's PNGs (committed as test vectors)
+        return sprites.load_sprites(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sprites"))
+    return sprites.default_sprites()
+
+
+def test_frames_match_independent_renderer_gpu():
+    """The CUDA rasteriser with the reference's sprites against frames that an independent renderer (float64 numpy +
+    scipy bilinear, tests/golden/make_golden.py:render_independent) drew from states of the unmodified reference
+    StackEnv, post-processed by the reference's own cv2 calls.  Bound stated in tests/test_raster_cpu.py."""
+    from gca_b200.stack import ImageBatch
+    from test_raster_cpu import check_frame, golden_frames
+    g, sp = golden_frames()
+    differ = 0
+    for mode in ("fast", "faithful"):
+        for k in range(len(g["n"])):
+            n = int(g["n"][k])
+            env = ImageBatch(3, _cfg(), n_intruders=n, mode=mode, seed=1, sprites=sp)
+            env.reset()
+            st = env.batch.get_state()
+            st["own_pos"][:], st["own_hs"][:], st["goal"][:] = g["own_pos"][k], g["own_hs"][k], g["goal"][k]
+            st["ipos"][:], st["ivel"][:] = g["ipos"][k][:n], g["ivel"][k][:n]
+            st["ipos_is_f64"][:] = 0
+            env.batch.set_state(st)
+            env._raster(None)
+            f = env.frame().cpu().numpy()[..., 0]
+            for b in range(3):
+                differ += check_frame(f[b], g["frame"][k], "%s frame %d (N = %d)" % (mode, k, n))
+            env.close()
+    print("pixels differing from the independent renderer:", differ)
+
+
+@pytest.mark.parametrize("n,B,mode,which", [(80, 24, "fast", "reference"), (80, 8, "faithful", "reference"), (0, 4, "fast", "reference"),
+                                            (126, 6, "fast", "reference"), (5, 40, "fast", "reference"), (80, 24, "fast", "lookalike"),
+                                            (33, 16, "faithful", "lookalike")])
+def test_frames_equal_cpu_restatement(n, B, mode, which):
     import torch
     from gca_b200.stack import ImageBatch
     from oracle import oracle as orc
-    env = ImageBatch(B, _cfg(), n_intruders=n, mode=mode, seed=11)
+    sp = _sprite_set(which)
+    env = ImageBatch(B, _cfg(), n_intruders=n, mode=mode, seed=11, sprites=sp)
     ref = orc.OracleEnv(variants.make_config("SingleAircraftStackEnv", _cfg()), B, n, draws=1, trig=orc.TRIG_SHARED,
                         seed=11, f32_positions=(mode == "fast"), auto_reset=True)
-    sp = sprites.default_sprites()
     f = env.reset().cpu().numpy()[..., 0]
     ref.reset()
     assert np.array_equal(f, ref.raster(sp))
@@ -51,7 +87,7 @@ def test_frame_stack_ring_equals_vec_frame_stack():
     from gca_b200.stack import ImageBatch
     B, k = 12, 4
     cfg = _cfg()
-    env = ImageBatch(B, cfg, n_intruders=20, frame_stack=k, seed=3)
+    env = ImageBatch(B, cfg, n_intruders=20, frame_stack=k, seed=3, sprites=_sprite_set("reference"))
     first = env.reset().cpu().numpy()
     stacked = np.zeros((B, 200, 200, k), np.uint8)          # vec_frame_stack.py:26-30
     stacked[..., -1:] = first
@@ -80,7 +116,7 @@ def test_stack_env_facade_rules():
     cfg.max_steps = 5
     try:
         from gca_b200.stack import SingleAircraftStackEnv
-        env = SingleAircraftStackEnv(seed=1)
+        env = SingleAircraftStackEnv(seed=1, sprites=_sprite_set("reference"))
     finally:
         cfg.intruder_size = 0
         cfg.max_steps = 1000

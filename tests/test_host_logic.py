@@ -104,6 +104,47 @@ def test_variant_table_matches_reference_reward_rows():
     assert variants.obs_dim(rows["SingleAircraftEnv"], 80) == 328 and variants.obs_dim(rows["SingleAircraftHEREnv"], 80) == 326
 
 
+def test_every_variant_builds_its_config_from_its_default_config_class():
+    """AircraftVecEnv(env, ..., config=None): the Config class comes from the variant table (the Simulators/ copies read
+    Simulators/config.py: NMAC_penalty / sparse_reward / n / diagonal; the registered classes the package's)."""
+    from gym_guidance_collision_avoidance_single.envs.config import Config
+    from Simulators.config import Config as Sim
+    for name in variants.VARIANTS:
+        cls = variants.default_config_class(name)
+        assert cls is (Config if name in ("SingleAircraftEnv", "SingleAircraft2Env", "SingleAircraftHEREnv",
+                                          "SingleAircraftDiscreteHEREnv", "SingleAircraftStackEnv") else Sim), name
+        c = variants.make_config(name, cls)                       # (raised AttributeError for four Simulators variants)
+        assert abi.load().gca_obs_dim(ctypes.byref(c), 10) == variants.obs_dim(c, 10)
+    assert variants.make_config("SingleAircraftDiscrete3HEREnv", Sim).action_kind == abi.ACT_DISCRETE3_HEADING
+
+
+def test_sprite_resolution(tmp_path, monkeypatch):
+    """gca_b200/sprites.py: the reference's PNGs when a checkout is known (argument or environment), else look-alikes
+    with a warning."""
+    from gca_b200 import sprites
+    fix = os.path.join(ROOT, "tests", "golden", "sprites")
+    monkeypatch.delenv("GCA_SPRITE_DIR", raising=False)
+    monkeypatch.delenv("GCA_REFERENCE", raising=False)
+    with pytest.warns(RuntimeWarning, match="look-alikes"):
+        sp = sprites.resolve_sprites()
+    assert np.array_equal(sp, sprites.default_sprites())
+    real = sprites.resolve_sprites(sprite_dir=fix)
+    assert real.shape == (3, 32, 32, 4) and not np.array_equal(real, sp)
+    assert 0.35 < (real[0, :, :, 3] > 0).mean() < 0.5              # SURVEY appendix D: aircraft.png 40.5 % opaque
+    monkeypatch.setenv("GCA_SPRITE_DIR", fix)
+    assert np.array_equal(sprites.resolve_sprites(), real)
+    monkeypatch.delenv("GCA_SPRITE_DIR")
+    co = tmp_path / "checkout" / "gym_guidance_collision_avoidance_single" / "envs" / "images"
+    co.mkdir(parents=True)
+    for f in os.listdir(fix):
+        (co / f).write_bytes(open(os.path.join(fix, f), "rb").read())
+    monkeypatch.setenv("GCA_REFERENCE", str(tmp_path / "checkout"))
+    assert np.array_equal(sprites.resolve_sprites(), real)
+    with pytest.raises(FileNotFoundError):
+        sprites.resolve_sprites(sprite_dir=str(tmp_path))
+    assert np.array_equal(sprites.resolve_sprites(sprites=sp), sp)
+
+
 def test_registry_and_spaces():
     import gym_guidance_collision_avoidance_single as pkg
     assert len(pkg.registry) == 5

@@ -4,8 +4,8 @@ info, conflict counter, the number of draws consumed and the full object state, 
 import numpy as np
 import pytest
 
-from helpers import (GOAL_VARIANTS, GOLDEN_CASES, GOLDEN_N, GOLDEN_VARIANTS, assert_state_equal, golden_actions, golden_config, golden_state,
-                     load_trace)
+from helpers import (FAST_TOL, GOAL_VARIANTS, GOLDEN_CASES, GOLDEN_N, GOLDEN_VARIANTS, assert_state_equal, fast_obs_tol, golden_actions,
+                     golden_config, golden_state, load_trace)
 from oracle import oracle as orc
 
 
@@ -71,8 +71,48 @@ def test_free_running_replay_matches_reference(vk, n):
         assert np.array_equal(env.cursor, g["cur_after_reset"][:, t]), what
 
 
+@pytest.mark.parametrize("vk,n", GOLDEN_CASES)
+def test_fast_mode_replay_within_tolerance_of_reference(vk, n):
+    """The fp32 ("fast") mode - the mode every headline number is measured on - against the reference traces, free
+    running from the recorded start state with the recorded draws: flags, done, counters and draw counts identical,
+    values inside helpers.FAST_TOL.  (The oracle's f32_positions variant is what the CUDA fast mode is bit-exact to,
+    tests/test_gpu_parity.py::test_golden_replay_fast repeats this on the device.)"""
+    g = load_trace(vk, n)
+    B = g["tape"].shape[0]
+    env = orc.OracleEnv(golden_config(vk), B, n, draws=0, trig=orc.TRIG_LIBM, tape=np.nan_to_num(g["tape"], nan=0.0),
+                        f32_positions=True)
+    for k, v in golden_state(g, "s0_").items():
+        env.state[k][...] = v
+    env.cursor[...] = g["cur_reset0"]
+    acts = golden_actions(vk, g)
+    f32 = lambda x: np.asarray(x).astype(np.float32).astype(np.float64)      # what the fast mode hands out
+    otol = fast_obs_tol(vk)
+    for t in range(acts.shape[1]):
+        what = "%s n=%d step %d" % (vk, n, t)
+        obs, rew, done, info = env.step(acts[:, t])
+        assert np.array_equal(info, g["event"][:, t]) and np.array_equal(done, g["done"][:, t]), what
+        assert np.array_equal(env.cursor, g["cur_after"][:, t]), what
+        assert np.array_equal(env.state["no_conflict"], g["no_conflict"][:, t]), what
+        want = golden_state(g, "sa_", (slice(None), t))
+        assert np.array_equal(env.state["iflag"], want["iflag"]), what
+        assert np.abs(env.state["own_pos"] - want["own_pos"]).max() <= FAST_TOL["pos"], what
+        if n:
+            assert np.abs(env.state["ipos"] - want["ipos"]).max() <= FAST_TOL["pos"], what
+        if obs.shape[1]:
+            assert np.abs(f32(obs) - g["obs"][:, t]).max() <= otol, what
+        assert np.abs(f32(rew) - g["reward"][:, t]).max() <= FAST_TOL["reward"], what
+        if vk in GOAL_VARIANTS:
+            gtol = FAST_TOL["pos"] if vk == "dher" else FAST_TOL["obs"]     # DiscreteHER goals are raw pixels
+            assert np.abs(f32(env.achieved) - g["ag"][:, t]).max() <= gtol and np.abs(f32(env.desired) - g["dg"][:, t]).max() <= gtol
+        if vk == "d3her":
+            assert np.abs(env.nearest - g["nearest"][:, t]).max() <= FAST_TOL["nearest"], what
+        if done.any():
+            env.reset(mask=done)
+        assert np.array_equal(env.cursor, g["cur_after_reset"][:, t]), what
+
+
 @pytest.mark.parametrize("vk,n", [("env", 80), ("env2", 3), ("her", 80), ("dher", 3), ("mcts", 80),
-                                  ("mctsrnd", 80), ("mctsrnd", 3)])
+                                  ("mctsrnd", 80), ("mctsrnd", 3), ("stack", 80)])
 def test_auto_reset_equals_step_then_reset(vk, n):
     """auto_reset folds the VecEnv contract (dummy_vec_env.py:52-55) into step."""
     g = load_trace(vk, n)
