@@ -6,19 +6,22 @@
 
 One "step" = one gca_step over one batch of 65,536 environments per GPU (SingleAircraft2Env,
 continuous actions, 80 intruders, fast mode, Philox draws, VecEnv auto-reset, observation
-written every step): 4 kernels - ownship, intruders (the streaming pass), finish, spawn.
-Prints ONE JSON line (rank 0).
+written every step): 2 kernels - the main kernel (ownship role + the streaming pass over the
+intruders) and the finish (+ spawn phase).  Prints ONE JSON line (rank 0).
 
   value      whole-job env-steps/s, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e        the same metric through the host-buffer C-ABI call (gca_step_host): actions come
              from pinned host memory and obs/reward/done/info are copied back every step
-  roofline   the dominant kernel (step_intruders_kernel): its algorithmic bytes per launch / its
-             launch duration, measured live with CUDA events between the kernels of the step
+  roofline   the dominant kernel (step_intruders_kernel): its algorithmic bytes per launch (40 N per
+             env) / its launch duration, measured live with CUDA events between the kernels of the step
              (gca_profile_*), vs the measured HBM peak; `step` gives the same for the whole step
-  cpu_baseline  the CPU oracle port on the box's host cores, on a bounded sample (rank 0, N=1)
+  cpu_baseline  the CPU oracle port on the box's host cores, on a bounded sample (rank 0, N=1), and
+             `python_reference`: the unmodified reference's own Python loop as timed in the build
+             container (profiles/python_reference_timing.json; the reference cannot travel to the box)
 
---impl reference times the CPU oracle port alone (the reference is Python and cannot travel to
-the GPU box; the port is pinned bit-exact to it by tests/test_oracle_golden.py).
+--impl reference times the CPU oracle port alone, with the oracle library only (no libgca.so, no
+product package): the reference is Python and cannot travel to the GPU box; the port is pinned
+bit-exact to it by tests/test_oracle_golden.py.
 """
 import argparse
 import json
@@ -48,6 +51,14 @@ def workload_name():
             "Philox draws, auto-reset, vector obs written every step" % (VARIANT, ENVS_PER_GPU, N_INTRUDERS))
 
 
+def workload_config(**extra):
+    """`config` of the JSON line: the same keys in both arms (ours / reference)."""
+    cfg = {"workload": workload_name(), "envs_per_gpu": ENVS_PER_GPU, "intruders": N_INTRUDERS, "variant": VARIANT,
+           "mode": "fast", "draws": "philox", "auto_reset": True, "sample": None, "l2": None, "launch": None}
+    cfg.update(extra)
+    return cfg
+
+
 def algorithmic_bytes_per_env_step(n, continuous=True):
     """DESIGN.md 'Algorithmic bytes': what one env-step must move in fast mode."""
     per_intruder = 8 + 8 + 8 + 16            # read pos, read vel, write pos, write 4 f32 obs entries
@@ -60,9 +71,26 @@ def algorithmic_bytes_per_env_step(n, continuous=True):
 
 
 def streaming_bytes_per_env_step(n):
-    """Algorithmic bytes of the dominant kernel alone (step_intruders_kernel): per intruder 8 (pos r) + 8 (vel r)
-    + 8 (pos w) + 16 (obs entries w); per env and 8-intruder work item 16 (ownship hand-over record)."""
-    return 40 * n + 16 * ((n + 7) // 8)
+    """Algorithmic bytes of the dominant kernel alone (step_intruders_kernel): per intruder 8 (pos r) +
+    8 (vel r) + 8 (pos w) + 16 (obs entries w) = 40."""
+    return 40 * n
+
+
+def handover_bytes_per_env_step(n):
+    """NOT algorithmic: the 16-byte ownship record every 8-intruder work item of the streaming pass re-reads (an
+    implementation overhead, served by the L2; reported beside the roofline, never inside it)."""
+    return 16 * ((n + 7) // 8)
+
+
+def python_reference_figures():
+    """The unmodified reference's own Python step loop, timed in the BUILD container by
+    tools/time_python_reference.py (BASELINE.md section 3 protocol): it cannot run on the GPU box (no gym, the
+    reference tree does not travel), so the line carries the committed figures with their provenance."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "python_reference_timing.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
 
 
 def measured_peaks():
@@ -143,10 +171,10 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------------------- CPU arm
 def oracle_shards(cores, envs, seed):
-    from gca_b200 import variants
-    from gym_guidance_collision_avoidance_single.envs.config import Config
+    """(nothing of the product is imported here: the workload's gca_config is written out in oracle/structs.py)"""
     from oracle import oracle as orc
-    cfg = variants.make_config(VARIANT, Config)
+    from oracle import structs
+    cfg = structs.bench_workload_config()
     per = envs // cores
     shards = []
     for c in range(cores):
@@ -184,22 +212,28 @@ def run_cpu(steps, warmup, sample_envs=None, budget_s=20.0):
     dt = time.perf_counter() - t0
     pool.shutdown()
     value = per * cores * steps / dt
-    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d envs x %d intruders x %d steps (%.1f s), C oracle port (oracle/gca_oracle.c), %d threads"
-                      % (per * cores, N_INTRUDERS, steps, dt, cores)}, steps, dt
+    out = {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": "%d envs x %d intruders x %d steps (%.1f s), C oracle port (oracle/gca_oracle.c), %d threads"
+                     % (per * cores, N_INTRUDERS, steps, dt, cores), "sample_envs": per * cores, "sample_steps": steps}
+    py = python_reference_figures()
+    if py is not None:
+        out["python_reference"] = py
+    return out, steps, dt
 
 
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import __graft_entry__ as ge
-    ge.build()
+    import subprocess
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")], stdout=sys.stderr)   # the oracle ONLY
     cb, steps, dt = run_cpu(args.steps, args.warmup, budget_s=60.0)
+    assert "gca_b200" not in sys.modules, "the reference arm must not import the product"
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-            "config": {"workload": workload_name()},
+            "config": workload_config(sample="%d envs x %d steps on %d host threads (bounded sample of the workload)"
+                                             % (cb["sample_envs"], cb["sample_steps"], cb["cores"])),
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -244,7 +278,8 @@ def main_gpu(args):
         torch.cuda.synchronize()
 
     K, W = args.steps, max(args.warmup, 3)
-    # K steps = full graph replays (GRAPH_STEPS launches each) + an eager remainder
+    # K steps = full replays of a CUDA graph of G = min(K, GRAPH_STEPS) steps + an eager remainder
+    G = max(1, min(K, GRAPH_STEPS))
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
@@ -254,7 +289,7 @@ def main_gpu(args):
     torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
-        for i in range(GRAPH_STEPS):
+        for i in range(G):
             env.step(actions[i])
     graph.replay()                                    # one untimed replay
     torch.cuda.synchronize()
@@ -265,10 +300,12 @@ def main_gpu(args):
     barrier()
     start.record()
     done_steps = 0
-    for _ in range(K // GRAPH_STEPS):
+    replays = K // G
+    for _ in range(replays):
         graph.replay()
-        done_steps += GRAPH_STEPS
-    for i in range(K - done_steps):
+        done_steps += G
+    eager_steps = K - done_steps
+    for i in range(eager_steps):
         env.step(actions[i])
     stop.record()
     barrier()
@@ -322,10 +359,11 @@ def main_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32+f64", "data": "synthetic",
-            "config": {"workload": workload_name(), "envs_per_gpu": B, "intruders": N,
-                       "l2": "per-step footprint %.0f MB (state+obs) exceeds the 126 MB L2; no flush between steps"
-                             % (bytes_per_step / 1e6),
-                       "launch": "CUDA graph of %d steps (%d kernels each), replayed" % (GRAPH_STEPS, kernels_per_step)},
+            "config": workload_config(
+                sample="the whole workload: %d envs per GPU x %d steps" % (B, K),
+                l2="per-step footprint %.0f MB (state+obs) exceeds the 126 MB L2; no flush between steps" % (bytes_per_step / 1e6),
+                launch="%d replay(s) of a CUDA graph of %d steps + %d eager step(s); %d kernels per step"
+                       % (replays, G, eager_steps, kernels_per_step)),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Ke, "api": "BatchedAircraftEnv.step_host -> gca_step_host (pinned host buffers)",
@@ -335,37 +373,67 @@ def main_gpu(args):
             "roofline": {"bound": "hbm", "kernel": "step_intruders_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                          "bytes_per_env_step": streaming_bytes_per_env_step(N), "kernel_ms": launch_ms,
+                         "overhead_bytes_per_env_step": handover_bytes_per_env_step(N),
+                         "overhead_note": "the 16-byte ownship record each 8-intruder work item re-reads (L2 hits): not algorithmic, not in `achieved`",
                          "share_of_step": launch_ms / prof_step_ms if prof_step_ms else None,
-                         "timing": "CUDA events between the kernels of %d eager steps (gca_profile_*); an event interval "
-                                   "includes the drain / launch gap around the kernel (about 7 us here), so achieved is a "
-                                   "lower bound: the kernel itself takes kernel_us_ncu in the committed ncu capture and "
-                                   "35.3 us by device timestamps inside the replayed graph (DESIGN.md section 7)" % prof["steps"],
+                         "timing": "CUDA events between the kernels of %d eager steps (gca_profile_*); the kernel is the main "
+                                   "kernel of the step (its first blocks play the ownship role, the others stream the "
+                                   "intruders); an event interval includes the drain / launch gap around the kernel, so "
+                                   "achieved is a lower bound (kernel_us_ncu: the committed ncu capture)" % prof["steps"],
                          "kernel_us_ncu": ncu_kernel_us(),
-                         "kernels_ms": {"own": prof["own_ms"] / max(prof["steps"], 1),
-                                        "intruders": launch_ms,
-                                        "finish": prof["finish_ms"] / max(prof["steps"], 1),
-                                        "spawn": prof["spawn_ms"] / max(prof["steps"], 1)},
+                         "kernels_ms": {"main (ownship role + streaming pass)": launch_ms,
+                                        "finish + spawn phase": prof["finish_ms"] / max(prof["steps"], 1)},
                          "step": {"achieved": step_gbs, "frac": step_gbs / peak,
                                   "bytes_per_env_step": algorithmic_bytes_per_env_step(N), "ms": step_ms}},
         }
         if world == 1 and not kernel_only:
             cb, _, _ = run_cpu(10 ** 9, 1, budget_s=12.0)
             line["cpu_baseline"] = cb
-        if not kernel_only and (world == 1 or os.environ.get("GCA_BENCH_EXTRAS") == "1"):
-            # the other configs / metrics of BASELINE.json; at N > 1 they would only repeat rank 0's single-GPU numbers
-            # while the other ranks wait in the barrier (GCA_BENCH_EXTRAS=1 forces them)
-            line["mcts"] = bench_mcts(local, with_cpu=(world == 1))
-            line["her"] = bench_her(local)
-            line["stack"] = bench_stack(local)
-            line["d9her"] = bench_d9her(local)
-            line["mctsrnd"] = bench_mctsrnd(local)
-            line["her_replay"] = bench_her_replay(local)
-            line["n0"] = bench_n0(local)
-            line["faithful"] = bench_faithful(local)
+    env.check()
+    env.close()
+    # ---- the other configs / metrics of BASELINE.json.  EVERY rank runs them on its own shard (independent envs /
+    # roots: no collective on the data path); a leg's time is the MAX over ranks and its value the whole-job aggregate,
+    # like the headline.  At N > 1 only the BASELINE configs (#3 HER, #4 MCTS, #5 stack) run; the rest is N = 1 detail.
+    extras = {}
+    if not kernel_only:
+        legs = [("her", bench_her), ("mcts", lambda d: bench_mcts(d, with_cpu=(world == 1 and rank == 0))), ("stack", bench_stack)]
+        if world == 1:
+            legs += [("d9her", bench_d9her), ("mctsrnd", bench_mctsrnd), ("her_replay", bench_her_replay), ("n0", bench_n0),
+                     ("faithful", bench_faithful)]
+        for name, fn in legs:
+            if world > 1:
+                dist.barrier()
+            extras[name] = reduce_leg(fn(local), world, dist if world > 1 else None)
+    if rank == 0:
+        line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+_MS_KEYS = ("ms_per_step", "ms_per_launch")
+
+
+def reduce_leg(d, world, dist):
+    """Whole-job figure of a leg every rank ran on its own shard: time = MAX over ranks, value = world x the units one
+    rank processed / that time (nested dicts with a `value` and a ms key are treated alike)."""
+    if not isinstance(d, dict):
+        return d
+    out = {}
+    for k, v in d.items():
+        out[k] = reduce_leg(v, world, dist) if isinstance(v, dict) else v
+    key = next((k for k in _MS_KEYS if k in d), None)
+    if dist is not None and key is not None and isinstance(d.get("value"), (int, float)):
+        import torch
+        t = torch.tensor([float(d[key])], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        out["value"] = world * d["value"] * d[key] / ms
+        out[key] = ms
+        out["n_gpus"] = world
+        out["per_rank"] = {k: d[k] for k in ("envs", "roots", "batch") if k in d}
+    return out
 
 
 def bench_mcts(device, with_cpu):
@@ -398,19 +466,9 @@ def bench_mcts(device, with_cpu):
     # FP64 roofline of the playout kernel: f64 operations per launch counted by ncu (profiles/mcts_kernel_ncu.json,
     # same workload) / the launch time measured here, against the measured non-fused DMUL+DADD peak of this pool's
     # B200 (profiles/fp64_peak.json; the parity contract forbids contracting the reference's mul/add pairs into FMAs)
-    try:
-        with open(os.path.join(ROOT, "profiles", "mcts_kernel_ncu.json")) as f:
-            prof = json.load(f)
-            ops = float(prof["f64_ops_per_launch"])
-        with open(os.path.join(ROOT, "profiles", "fp64_peak.json")) as f:
-            peak = float(json.load(f)["dmul_dadd_tflops"])
-        ach = ops / (ms * 1e-3) / 1e12
-        out["roofline"] = {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                           "peak_source": "measured (tools/fp64_peak.cu, separate DMUL+DADD)",
-                           "ops_per_launch": ops, "kernel": prof.get("kernel"),
-                           "fp64_pipe_pct_ncu": prof.get("fp64_pipe_pct_of_peak_sustained_active")}
-    except Exception:
-        pass
+    rl = fp64_roofline("mcts_kernel_ncu.json", ms)
+    if rl:
+        out["roofline"] = rl
     # device-resident UCT search: decisions/s = best_action(100 simulations, depth 3) per root
     try:
         R2 = 65536
@@ -430,22 +488,57 @@ def bench_mcts(device, with_cpu):
                          "roots": R2, "simulations": P, "depth": depth, "ms_per_launch": ms2,
                          "simulations_per_sec": R2 * P / (ms2 * 1e-3),
                          "api": "gca_mcts_search (UCT tree per root resident on the device, one lane per root)"}
+        rl2 = fp64_roofline("mcts_search_ncu.json", ms2)
+        if rl2:
+            out["search"]["roofline"] = rl2
     except Exception as exc:                                          # pragma: no cover
         out["search"] = {"error": str(exc)}
     env.close()
     if with_cpu:
+        # same protocol as the step baseline: the C oracle port on ALL host cores (ctypes releases the GIL), one shard
+        # of roots per thread, a bounded sample
+        from concurrent.futures import ThreadPoolExecutor
         from oracle import oracle as orc
-        sample = roots[:8].cpu().numpy()
+        cores = os.cpu_count() or 1
+        per = 4
+        host_roots = roots[: per * cores].cpu().numpy() if roots.shape[0] >= per * cores else roots.cpu().numpy().repeat(
+            (per * cores + R - 1) // R, 0)[: per * cores]
+        shards = [host_roots[c * per:(c + 1) * per] for c in range(cores)]
+        pool = ThreadPoolExecutor(cores)
         t0 = time.perf_counter()
-        orc.mcts_search_philox(cfg, 80, sample, P, depth, seed=2)
-        out["search"]["cpu_baseline"] = {"value": 8 / (time.perf_counter() - t0), "unit": "searches/s", "cores": 1,
-                                         "kind": "port", "sample": "8 roots x 100 simulations, C oracle port, 1 thread"}
-        t0 = time.perf_counter()
-        orc.mcts_playouts(cfg, 80, sample, 50, depth, seed=6)
+        list(pool.map(lambda sh: orc.mcts_search_philox(cfg, 80, sh, P, depth, seed=2), shards))
         dt = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": 8 * 50 / dt, "unit": "rollouts/s", "cores": 1, "kind": "port",
-                               "sample": "8 roots x 50 playouts, C oracle port (oracle/gca_oracle_mcts.c), 1 thread"}
+        out["search"]["cpu_baseline"] = {"value": per * cores / dt, "unit": "searches/s", "cores": cores, "kind": "port",
+                                         "sample": "%d roots x %d simulations (%.1f s), C oracle port, %d threads" % (per * cores, P, dt, cores)}
+        t0 = time.perf_counter()
+        list(pool.map(lambda sh: orc.mcts_playouts(cfg, 80, sh, 50, depth, seed=6), shards))
+        dt = time.perf_counter() - t0
+        pool.shutdown()
+        out["cpu_baseline"] = {"value": per * cores * 50 / dt, "unit": "rollouts/s", "cores": cores, "kind": "port",
+                               "sample": "%d roots x 50 playouts (%.1f s), C oracle port (oracle/gca_oracle_mcts.c), %d threads"
+                                         % (per * cores, dt, cores)}
+        py = python_reference_figures()
+        if py is not None and "mcts" in py:
+            out["cpu_baseline"]["python_reference"] = py["mcts"]
     return out
+
+
+def fp64_roofline(profile_name, ms):
+    """FP64 roofline of a kernel: f64 operations per launch counted by ncu on the same workload (profiles/<name>.json) /
+    the launch time measured live, against the measured non-fused DMUL+DADD peak of this pool's B200
+    (profiles/fp64_peak.json; the parity contract forbids contracting the reference's mul/add pairs into FMAs)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", profile_name)) as f:
+            prof = json.load(f)
+        with open(os.path.join(ROOT, "profiles", "fp64_peak.json")) as f:
+            peak = float(json.load(f)["dmul_dadd_tflops"])
+        ops = float(prof["f64_ops_per_launch"])
+        ach = ops / (ms * 1e-3) / 1e12
+        return {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "peak_source": "measured (tools/fp64_peak.cu, separate DMUL+DADD)", "ops_per_launch": ops,
+                "kernel": prof.get("kernel"), "fp64_pipe_pct_ncu": prof.get("fp64_pipe_pct_of_peak_sustained_active")}
+    except Exception:
+        return None
 
 
 def bench_her(device):
@@ -593,6 +686,7 @@ def bench_mctsrnd(device):
             "hbm_frac": gbs / peak, "note": "CUDA graph of %d steps replayed" % GRAPH_STEPS,
             "model": {"metric": "mcts_rollouts_per_sec", "value": R * P / (pms * 1e-3), "unit": "rollouts/s", "roots": R,
                       "playouts_per_root": P, "depth": depth, "intruders": N, "ms_per_launch": pms,
+                      "roofline": fp64_roofline("mctsrnd_model_ncu.json", pms),
                       "kernel": "mcts_playout_kernel<0, true> (nodes_single_randintru.py model; one warp per playout, intruders out of reach culled exactly)"}}
 
 

@@ -1,6 +1,7 @@
 // gca_abi.cu - the C ABI of include/gca.h: handle lifetime, argument checking, state
 // marshalling and the host-buffer (end-to-end) path.  No exception crosses the boundary.
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdlib>
 #include <limits>
@@ -274,13 +275,24 @@ int gca_create(const gca_config* cfg, int n_envs, int n_intruders, int mode, int
   if (!rc) rc = dev_alloc(e, &s.ev_near, (size_t)s.T * 32);
   if (!rc) rc = dev_alloc(e, &s.reset_list, (size_t)s.T * 32);
   if (!rc) rc = dev_alloc(e, &s.reset_count, 1);
-  s.respawn_cap = (int)std::min<size_t>((size_t)s.T * 128, (size_t)1 << 30);   // kTileRespawnCap records per tile
-  if (!rc) rc = dev_alloc(e, &s.respawn_list, (size_t)s.respawn_cap);
-  if (!rc) rc = dev_alloc(e, &s.respawn_count, (size_t)s.T);
+  s.respawn_cap = 0;                                  // (respawn records live in shared memory: step_finish_kernel)
+  if (!rc) rc = dev_alloc(e, &s.respawn_list, 1);
+  if (!rc) rc = dev_alloc(e, &s.respawn_count, 1);
+  if (!rc) rc = dev_alloc(e, &s.pre, (size_t)s.T * 32);
+  if (!rc) rc = dev_alloc(e, &s.step_seq, 1);
+  if (!rc) rc = dev_alloc(e, &s.error_flag, 1);
   if (!rc) rc = dev_alloc(e, &s.ivel, vel_plane_bytes(s));
   if (!rc) rc = dev_alloc(e, &s.cflag, flag_plane_words(s));
   if (!rc) rc = dev_alloc(e, &s.dflag, mode == GCA_MODE_FAITHFUL ? flag_plane_words(s) : 1);
   if (!rc && keeps_ihs(*cfg) && n_intruders > 0) rc = dev_alloc(e, &s.ihs, (size_t)s.T * (size_t)s.N * 32);
+  if (!rc) {
+    // the event words are consumed AND cleared by the finish of every step (PHILOX handles): they start out clear
+    std::vector<int> none((size_t)s.T * 32, INT_MAX);
+    std::vector<uint32_t> inf((size_t)s.T * 32, 0x7f800000u);
+    if (cudaMemcpy(s.ev_nmac, none.data(), none.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(s.ev_near, inf.data(), inf.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess)
+      rc = fail(GCA_ERR_CUDA, "initialising the event words failed");
+  }
   if (rc) {
     gca_destroy(e);
     return rc;
@@ -356,6 +368,16 @@ int gca_step(gca_env* e, const void* actions, const gca_tape* tape, int auto_res
 int gca_step_launches(gca_env* e) {
   if (!e) return fail(GCA_ERR_INVALID, "env is NULL");
   return step_launch_count(e->draws == GCA_DRAWS_TAPE, e->s.N, e->cfg.obs_kind, e->cfg.intruder_turns && e->s.ihs);
+}
+
+int gca_check(gca_env* e) {
+  if (!e) return fail(GCA_ERR_INVALID, "env is NULL");
+  GCA_CUDA(cudaSetDevice(e->device));
+  GCA_CUDA(cudaDeviceSynchronize());
+  int flag = 0;
+  GCA_CUDA(cudaMemcpy(&flag, e->s.error_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag) return fail(GCA_ERR_STATE, "a streaming lane timed out waiting for its ownship record (step_intruders_kernel)");
+  return GCA_OK;
 }
 
 int gca_profile_enable(gca_env* e, int on) {

@@ -58,6 +58,12 @@ struct DevState {
   uint32_t* respawn_list; // [respawn_cap] (env << 8 | intruder) of the intruders that left the map in this step (PHILOX)
   int* respawn_count;     // [T] records of each tile's segment of respawn_list
   int respawn_cap;
+  // PHILOX handles (two kernels per step, see gca_step.cu)
+  double2* pre;           // [T*32] what the ownship role settled before the intruders were looked at: (reward candidate,
+                          //        bits: info | done << 8) of wall / goal / default / max-steps - the finish takes it unless an
+                          //        intruder event outranks it
+  uint32_t* step_seq;     // [1] steps launched on this handle; own_b.w of step k carries stamp k + 1 (valid under graph replay)
+  int* error_flag;        // [1] set by a streaming lane whose ownship record never arrived (never, unless dispatch order broke)
   size_t pos_plane;       // bytes of one position plane
   int B, N, T, U, W, Wd;
 };
@@ -145,6 +151,7 @@ struct StepArgs {
   uint32_t key0, key1, env_id0;
   int D;                  // observation row length
   int auto_reset;
+  int own_blocks;         // PHILOX: leading blocks of step_intruders_kernel that play the ownship role (0: TAPE, own kernel)
   void* obs;
   void* achieved;
   void* desired;

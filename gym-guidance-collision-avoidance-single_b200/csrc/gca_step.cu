@@ -175,24 +175,33 @@ __device__ __forceinline__ Draws<TAPE> make_draws(const StepArgs& a, size_t me, 
 }
 
 // ------------------------------------------------------------------------------ 1. ownship
-// Ownship.step(a)   PKG/SingleAircraftEnv.py:299-309 (2Env :291-301, DiscreteHER :301-311)
+// Ownship.step(a)   PKG/SingleAircraftEnv.py:299-309 (2Env :291-301, DiscreteHER :301-311) for env `me`.
+// TAPE handles (parity replays): a kernel of its own, which also clears the env's event words.
+// PHILOX handles: the ownship ROLE of step_intruders_kernel (the first blocks of its grid).  It publishes the 16-byte
+// record the streaming role waits for - (x, y) first, then (bits, stamp) behind a fence - as soon as the new position
+// is known, and then settles everything of the step that does not depend on the intruders while the streaming role is
+// already running: the ownship / goal tail of the observation (:115-124) and the reward the step returns unless an
+// intruder event outranks it (wall / goal / default / max steps, :173-183) -> DevState::pre.
+__device__ __forceinline__ void st_release_pair(float* p, float x, float y) {
+  asm volatile("st.volatile.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ float4 ld_volatile_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
 template <bool FAITH, bool TAPE>
-__global__ void __launch_bounds__(128) step_own_kernel(const StepArgs a) {
+__device__ __forceinline__ void own_update(const StepArgs& a, const size_t me, const uint32_t stamp, const bool publish) {
   using R = real_t<FAITH>;
   const DevState& s = a.s;
   const gca_config& c = a.cfg;
-  if (PDL_EARLY) pdl_launch_dependents();
-  pdl_wait();
-  GCA_KSTAMP_IN(0);
-  const size_t me = (size_t)blockIdx.x * 128 + threadIdx.x;
-  if (me >= (size_t)s.T * 32) return;
-  if (me >= (size_t)s.B) {                                // padding lanes of the last tile
-    s.own_b[me] = make_float4(0.f, 0.f, 0.f, 0.f);
-    return;
-  }
+  const Derived& k = a.k;
   float2 pos = s.own_pos[me];
   double2 hs = s.own_hs[me];
   int4 cnt = s.counters[me];
+  double2 goal = make_double2(0., 0.);
+  if constexpr (!TAPE) goal = s.goal[me];
   Draws<TAPE> d = make_draws<TAPE>(a, me, (uint32_t)cnt.z);
   double f0, f1 = 0.0;
   if (c.action_kind == GCA_ACT_CONTINUOUS2) {
@@ -223,24 +232,65 @@ __global__ void __launch_bounds__(128) step_own_kernel(const StepArgs a) {
   pos = make_float2((float)__dadd_rn((double)pos.x, vel.x), (float)__dadd_rn((double)pos.y, vel.y));
   cnt.y += 1;                                                     // StackEnv :118
   const bool maxstep_hit = c.max_steps > 0 && cnt.y >= c.max_steps;   // StackEnv :134-136: the intruder loop never runs
+  const uint32_t bits = (maxstep_hit ? 0u : kOwnRuns) | ((uint32_t)(cnt.z & 1) * kOwnPlane);
+  if constexpr (TAPE) {
+    s.own_b[me] = make_float4(pos.x, pos.y, __uint_as_float(bits), 0.f);
+  } else if (publish) {
+    float* rec = reinterpret_cast<float*>(&s.own_b[me]);
+    st_release_pair(rec, pos.x, pos.y);
+    __threadfence();                                              // (x, y) are visible before the stamp is
+    st_release_pair(rec + 2, __uint_as_float(bits), __uint_as_float(stamp));
+  }
   s.own_pos[me] = pos;
   s.own_hs[me] = hs;
   s.own_vel[me] = vel;
   s.own_vel_f32[me] = 0;
   s.counters[me] = cnt;
-  if constexpr (TAPE) a.cursor[me] = d.cur;
-  const uint32_t bits = (maxstep_hit ? 0u : kOwnRuns) | ((uint32_t)(cnt.z & 1) * kOwnPlane);
-  s.own_b[me] = make_float4(pos.x, pos.y, __uint_as_float(bits), 0.f);
-  for (int w = 0; w < s.W; ++w) {
-    const size_t fi = flag_index(s, me, w);
-    s.ev_conf[fi] = 0u;
-    s.ev_gone[fi] = 0u;
+  if constexpr (TAPE) {
+    a.cursor[me] = d.cur;
+    for (int w = 0; w < s.W; ++w) {
+      const size_t fi = flag_index(s, me, w);
+      s.ev_conf[fi] = 0u;
+      s.ev_gone[fi] = 0u;
+    }
+    s.ev_nmac[me] = INT_MAX;
+    if (c.shaped_nearest) s.ev_near[me] = 0x7f800000u;            // +inf
+    if (me == 0) *s.reset_count = 0;
+  } else {
+    // _terminal_reward() below the intruder loop   :173-183 and the variant rows of SURVEY.md 8(a)
+    double reward;
+    int info, done = 0;
+    if (maxstep_hit) {
+      reward = 0.0; done = 1; info = GCA_INFO_MAXSTEPS;
+    } else if (c.wall_kind != GCA_WALL_NONE && !in_map_f32(k, pos.x, pos.y)) {
+      reward = c.r_wall; done = c.wall_kind == GCA_WALL_TERMINAL; info = GCA_INFO_WALL;
+    } else {
+      const double dg = dist_f64((double)pos.x, (double)pos.y, goal.x, goal.y);
+      if (dg < c.goal_radius) {
+        reward = c.r_goal; done = 1; info = GCA_INFO_GOAL;
+      } else {
+        reward = c.shaped_default ? ddiv_prepared(k, -dg, k.dv_shape, k.rc_shape) : c.r_default;
+        info = GCA_INFO_NONE;
+      }
+    }
+    s.pre[me] = make_double2(reward, __longlong_as_double((long long)(info | (done << 8))));
+    write_obs_own<FAITH>(a, me, pos.x, pos.y, vel.x, vel.y, false, hs.x, hs.y, goal.x, goal.y);   // :115-124
   }
-  s.ev_nmac[me] = INT_MAX;
-  if (c.shaped_nearest) s.ev_near[me] = 0x7f800000u;              // +inf
-  if (me == 0) {
-    *s.reset_count = 0;
+}
+
+template <bool FAITH, bool TAPE>
+__global__ void __launch_bounds__(128) step_own_kernel(const StepArgs a) {
+  const DevState& s = a.s;
+  if (PDL_EARLY) pdl_launch_dependents();
+  pdl_wait();
+  GCA_KSTAMP_IN(0);
+  const size_t me = (size_t)blockIdx.x * 128 + threadIdx.x;
+  if (me >= (size_t)s.T * 32) return;
+  if (me >= (size_t)s.B) {                                // padding lanes of the last tile
+    s.own_b[me] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
   }
+  own_update<FAITH, TAPE>(a, me, 0u, false);
   GCA_KSTAMP_OUT(0);
 }
 
@@ -249,9 +299,23 @@ __global__ void __launch_bounds__(128) step_own_kernel(const StepArgs a) {
 // streaming pass recorded, then rewards, observation tail, counters, auto-reset.  Called by the warp that
 // completed the tile's last work item (or by step_finish_kernel when there are no intruders).  The event
 // words were produced by other warps of the same launch: they are read with ld.global.cg (L2).
+// per warp of step_finish_kernel (PHILOX): what the spawn phase of the same kernel needs of the tile's envs
+struct WarpScratch {
+  uint32_t list[kTileRespawnCap];   // (lane of the env << 8 | intruder): the intruders that left the map in this step
+  float2 pos[32];                   // the ownship the respawns keep their distance from (this step's position)
+  int tick[32];                     // tick of this step; -1: the env finished and was reset (its respawns are moot)
+  int n_jobs;
+};
+struct BlockScratch {               // per block: the envs that finished under auto-reset (their N spawns, one warp per 32)
+  int env[128];
+  int count;
+};
+
 template <bool FAITH, bool TAPE>
-__device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, const int lane) {
+__device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, const int lane, WarpScratch* ws,
+                                            BlockScratch* bs) {
   using R = real_t<FAITH>;
+  constexpr bool PRE = !TAPE;                             // the ownship role already settled the intruder-free part
   const DevState& s = a.s;
   const gca_config& c = a.cfg;
   const Derived& k = a.k;
@@ -264,9 +328,10 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
 #endif
 
   float2 pos = make_float2(0.f, 0.f);
-  double2 hs = make_double2(0., 0.), vel = make_double2(0., 0.), goal = make_double2(0., 0.);
+  double2 hs = make_double2(0., 0.), vel = make_double2(0., 0.), goal = make_double2(0., 0.), pre = make_double2(0., 0.);
   int4 cnt = make_int4(0, 0, 0, 0);
   int stop = INT_MAX;
+  uint32_t near_bits = 0x7f800000u;                       // FAST + shaped_nearest: smallest squared distance of the step (+inf: none)
   constexpr int kWordsAhead = 4;                          // N <= 128: the env's event / flag words live in registers
   uint32_t wc[kWordsAhead], wg[kWordsAhead], wf[kWordsAhead];
 #pragma unroll
@@ -274,9 +339,13 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
   if (has_env) {
     // everything this lane needs is requested before any of it is looked at: one round trip
     pos = s.own_pos[me];
-    hs = s.own_hs[me];
-    vel = s.own_vel[me];
-    goal = s.goal[me];
+    if constexpr (PRE) {
+      pre = s.pre[me];
+    } else {
+      hs = s.own_hs[me];
+      vel = s.own_vel[me];
+      goal = s.goal[me];
+    }
     cnt = s.counters[me];
     if (s.N > 0) {
       stop = __ldcg(&s.ev_nmac[me]);
@@ -287,7 +356,18 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
           wc[w] = __ldcg(&s.ev_conf[fi]);
           wg[w] = __ldcg(&s.ev_gone[fi]);
           wf[w] = s.cflag[fi];
+          if constexpr (PRE) {                            // consumed: the words are clear again for the next step
+            if (wc[w]) s.ev_conf[fi] = 0u;
+            if (wg[w]) s.ev_gone[fi] = 0u;
+          }
         }
+      }
+      if constexpr (!FAITH) {
+        if (c.shaped_nearest) near_bits = __ldcg(&s.ev_near[me]);
+      }
+      if constexpr (PRE) {
+        if (stop != INT_MAX) s.ev_nmac[me] = INT_MAX;
+        if (near_bits != 0x7f800000u) s.ev_near[me] = 0x7f800000u;
       }
     }
   }
@@ -334,7 +414,7 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
       // streaming pass recorded (sqrt is monotone).  After an NMAC at `stop` the visited prefix has no other distance
       // below NMAC_dist (it would have ended the loop earlier), so the minimum is the distance of `stop` itself.
       if (stop == INT_MAX) {
-        dnear = (double)__fsqrt_rn(__uint_as_float(__ldcg(&s.ev_near[me])));
+        dnear = (double)__fsqrt_rn(__uint_as_float(near_bits));
       } else {
         const float2 p = *reinterpret_cast<const float2*>(pbase + ipos_offset(s, false, me, stop));
         dnear = (double)__fsqrt_rn(dist2_f32(pos.x, pos.y, p.x, p.y));
@@ -381,7 +461,12 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
       for (int w = 0; w < s.W; ++w) {                     // N > 128: word by word
         const uint32_t vis = visited_mask(w);
         const size_t fi = flag_index(s, me, w);
-        const uint32_t conf = __ldcg(&s.ev_conf[fi]) & vis, gone = __ldcg(&s.ev_gone[fi]) & vis;
+        const uint32_t conf_all = __ldcg(&s.ev_conf[fi]), gone_all = __ldcg(&s.ev_gone[fi]);
+        if constexpr (PRE) {
+          if (conf_all) s.ev_conf[fi] = 0u;
+          if (gone_all) s.ev_gone[fi] = 0u;
+        }
+        const uint32_t conf = conf_all & vis, gone = gone_all & vis;
         if ((conf | gone) == 0u) continue;
         const uint32_t cf = s.cflag[fi];
         newconf += __popc(conf & ~cf);
@@ -415,11 +500,10 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
       }
       job_total = __shfl_sync(FULL, job_off, 31);
       job_off -= job_mine;
-      // every tile owns a fixed segment of the respawn list: no batch-wide counter (2,048 warps adding to one address
-      // cost each of them ~3 us of waiting), the spawn kernel reads the per-tile counts
-      job_base = tile * kTileRespawnCap;
+      // the records go to the warp's shared scratch: the spawn phase of the same kernel runs them one lane each
+      job_base = 0;
     }
-    if (lane == 0) s.respawn_count[tile] = job_total;     // (0 when the spawns were made in place)
+    if (lane == 0) ws->n_jobs = job_total < kTileRespawnCap ? job_total : kTileRespawnCap;   // (0 when the spawns were made in place)
   }
 #ifdef GCA_PHASE_TIMING
   fin_t2 = gtime();
@@ -440,12 +524,17 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
     // _terminal_reward()   :143-184 and the variant rows of SURVEY.md 8(a)
     double reward;
     int info;
+    bool is_default = false;                               // the `return -dist/1200, False, ''` row: the nearest-intruder term applies
     if (maxstep_hit) {
       reward = 0.0; done = true; info = GCA_INFO_MAXSTEPS;
     } else if (nmac) {
       reward = c.r_nmac; done = true; info = GCA_INFO_NMAC;
     } else if (conf_any) {
       reward = c.r_conflict; info = GCA_INFO_CONFLICT;
+    } else if constexpr (PRE) {                            // wall / goal / default: settled by the ownship role (own_update)
+      const int bits = (int)__double_as_longlong(pre.y);
+      reward = pre.x; info = bits & 0xff; done = (bits >> 8) != 0;
+      is_default = info == GCA_INFO_NONE;
     } else if (c.wall_kind != GCA_WALL_NONE && !in_map_f32(k, pos.x, pos.y)) {
       reward = c.r_wall; done = c.wall_kind == GCA_WALL_TERMINAL; info = GCA_INFO_WALL;
     } else {
@@ -455,18 +544,19 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
       } else {
         reward = c.shaped_default ? ddiv_prepared(k, -dg, k.dv_shape, k.rc_shape) : c.r_default;
         info = GCA_INFO_NONE;
-        if (c.shaped_nearest) {                            // :225-232 (NumPy 2 weak scalars: an f32 distance stays f32)
-          const double thr = 3 * c.minimum_separation;
-          const bool lt = near_set ? (near64 ? dnear < thr : (float)dnear < (float)thr) : dnear < thr;
-          if (lt) {
-            if (near64) {
-              const double r = __dadd_rn(__dmul_rn(c.conflict_coeff, dnear), -0.1);
-              reward = __dadd_rn(reward, r);
-            } else {
-              const float r = __fadd_rn(__fmul_rn((float)c.conflict_coeff, (float)dnear), -(float)0.1);
-              reward = c.shaped_default ? __dadd_rn(reward, (double)r) : (double)__fadd_rn((float)c.r_default, r);
-            }
-          }
+        is_default = true;
+      }
+    }
+    if (is_default && c.shaped_nearest) {                  // :225-232 (NumPy 2 weak scalars: an f32 distance stays f32)
+      const double thr = 3 * c.minimum_separation;
+      const bool lt = near_set ? (near64 ? dnear < thr : (float)dnear < (float)thr) : dnear < thr;
+      if (lt) {
+        if (near64) {
+          const double r = __dadd_rn(__dmul_rn(c.conflict_coeff, dnear), -0.1);
+          reward = __dadd_rn(reward, r);
+        } else {
+          const float r = __fadd_rn(__fmul_rn((float)c.conflict_coeff, (float)dnear), -(float)0.1);
+          reward = c.shaped_default ? __dadd_rn(reward, (double)r) : (double)__fadd_rn((float)c.r_default, r);
         }
       }
     }
@@ -475,8 +565,14 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
     a.done[me] = done ? 1 : 0;
     a.info[me] = (uint8_t)info;
     if (a.nearest) reinterpret_cast<R*>(a.nearest)[me] = (R)dnear;
-    if (!(done && a.auto_reset))                                   // (a finished env shows its reset observation, below)
-      write_obs_own<FAITH>(a, me, pos.x, pos.y, vel.x, vel.y, false, hs.x, hs.y, goal.x, goal.y);   // :115-124
+    if constexpr (!PRE) {                                          // (PRE: own_update wrote it; a reset overwrites it below)
+      if (!(done && a.auto_reset))                                 // (a finished env shows its reset observation, below)
+        write_obs_own<FAITH>(a, me, pos.x, pos.y, vel.x, vel.y, false, hs.x, hs.y, goal.x, goal.y);   // :115-124
+    }
+  }
+  if constexpr (PRE) {                                             // for the spawn phase (before a reset replaces pos)
+    ws->pos[lane] = pos;
+    ws->tick[lane] = (has_env && !(done && a.auto_reset)) ? cnt.z : -1;
   }
 
   if constexpr (!TAPE) {
@@ -490,7 +586,7 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
           while (rest) {
             const int j = __ffs(rest) - 1;
             rest &= rest - 1;
-            if (at < job_base + kTileRespawnCap) s.respawn_list[at] = ((uint32_t)me << 8) | (uint32_t)(w * 32 + j);
+            if (at < job_base + kTileRespawnCap) ws->list[at] = ((uint32_t)lane << 8) | (uint32_t)(w * 32 + j);
             else if (!(done && a.auto_reset)) respawn_own(w * 32 + j, set64_own[w]);   // (list full: > 4 respawns per env on average)
             ++at;
           }
@@ -546,10 +642,10 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
     const uint32_t rmask = __ballot_sync(FULL, resets);
     if (rmask) {
       int base = 0;
-      if (lane == 0) base = atomicAdd(s.reset_count, __popc(rmask));
+      if (lane == 0) base = atomicAdd(&bs->count, __popc(rmask));
       base = __shfl_sync(FULL, base, 0);
       if (resets) {
-        s.reset_list[base + __popc(rmask & ((1u << lane) - 1u))] = (int)me;
+        bs->env[base + __popc(rmask & ((1u << lane) - 1u))] = (int)me;
         draw_goal(d, c, goal.x, goal.y);   // Goal(random_pos()) :93
       }
 #ifdef GCA_PHASE_TIMING
@@ -582,81 +678,103 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
 #endif
 }
 
-// Every spawn of the step (PHILOX; queued by finish_tile): the respawns of intruders that left the map, one lane
-// each, and the N intruders of every env that finished under auto-reset, one warp per 32 of them.  Runs after the
-// streaming pass; the envs' ticks have already been incremented.
+// The spawn phase of a PHILOX step, run by the warps that just finished their tiles (no kernel of its own: a launch
+// boundary costs more than this work).  (i) reset_intruder() (PKG/SingleAircraftEnv.py:153-154, :229-238) for every
+// intruder of the tile that left the map, one LANE per spawn (records in the warp's scratch, ~14 per tile and step);
+// (ii) after a block-wide barrier, reset()'s N spawns (:80-88) of every env of the block that finished under
+// auto-reset, one WARP per 32 of them, whichever warp is free.  A spawn depends on (env, tick, intruder) and the
+// ownship position only, so who executes it does not matter.
 template <bool FAITH>
-__global__ void __launch_bounds__(128) spawn_kernel(const __grid_constant__ StepArgs a) {
-  if (PDL_EARLY) pdl_launch_dependents();
-  pdl_wait();
-  GCA_KSTAMP_IN(3);
+__device__ __forceinline__ void spawn_phase(const StepArgs& a, const int tile, const int wib, const int lane,
+                                            WarpScratch* ws, BlockScratch* bs) {
   const DevState& s = a.s;
-  const int lane = threadIdx.x & 31;
-  const int n_warps = gridDim.x * 4, rounds = s.W;
-  // jobs: one per tile (that tile's respawn records, usually one round of lanes), then `rounds` per finished env
-  const long long resp_warps = s.T, total = resp_warps + (long long)(*s.reset_count) * rounds;
-  for (long long job = (long long)blockIdx.x * 4 + (threadIdx.x >> 5); job < total; job += n_warps) {
-    Draws<false> d;
-    d.k0 = a.key0; d.k1 = a.key1;
-    if (job < resp_warps) {
-      // reset_intruder()   PKG/SingleAircraftEnv.py:153-154, :229-238
-      const int n_resp = min(s.respawn_count[job], kTileRespawnCap);
-      for (int at = lane; at < n_resp; at += 32) {
-        const uint32_t rec = s.respawn_list[job * kTileRespawnCap + at];
-        const size_t env = rec >> 8;
-        const int i = (int)(rec & 0xffu);
-        const int4 cnt = s.counters[env];
-        const float2 own = s.own_pos[env];
-        d.env = a.env_id0 + (uint32_t)env;
-        d.tick = (uint32_t)cnt.z - 1u;                      // the tick of the step that lost the intruder
-        // ep_steps == 0 after a step: the env finished and was reset (auto-reset); all its intruders are new anyway
-        if (cnt.y != 0 || !a.auto_reset) {
-          Intr<FAITH> it;
-          spawn<FAITH, false>(d, a.cfg, a.k, (uint32_t)i, own.x, own.y, it, ihs_slot(s, env, i));
-          store_ipos<FAITH>(s, cnt.z & 1, env, i, it);
-          store_ivel(s, env, i, it.vx, it.vy);
-          write_obs_intruder<FAITH>(a, obs_intruder_base<FAITH>(a, env), i, it);
-          if constexpr (FAITH) {
-            if (it.is64) atomicOr(&s.dflag[flag_index(s, env, i >> 5)], 1u << (i & 31));
-          }
-        }
-      }
-    } else {
-      // reset(): the intruders   PKG/SingleAircraftEnv.py:80-88 (the scalar part happened in finish_tile)
-      const long long rj = job - resp_warps;
-      const size_t env = (size_t)s.reset_list[rj / rounds];
-      const int r = (int)(rj % rounds), i = r * 32 + lane;
-      const int4 cnt = s.counters[env];
+  Draws<false> d;
+  d.k0 = a.key0; d.k1 = a.key1;
+  if (tile < s.T) {
+    __syncwarp();                                           // the records and per-env scratch of finish_tile
+    const int n_resp = ws->n_jobs;
+    for (int at = lane; at < n_resp; at += 32) {
+      const uint32_t rec = ws->list[at];
+      const int e = (int)(rec >> 8), i = (int)(rec & 0xffu);
+      const int tick = ws->tick[e];
+      if (tick < 0) continue;                               // the env finished and was reset: all its intruders are new anyway
+      const size_t env = (size_t)tile * 32 + e;
+      const float2 own = ws->pos[e];
       d.env = a.env_id0 + (uint32_t)env;
-      d.tick = (uint32_t)cnt.z - 1u;                        // the tick of the step that finished the env
-      bool wide = false;
-      if (i < s.N) {
-        Intr<FAITH> it;
-        const float2 own = s.own_pos[env];                 // (50, 50) :72-76, or the random start finish_tile drew
-        spawn<FAITH, false>(d, a.cfg, a.k, GCA_SLOT_RESET | (uint32_t)i, own.x, own.y, it, ihs_slot(s, env, i));
-        store_ipos<FAITH>(s, cnt.z & 1, env, i, it);
-        store_ivel(s, env, i, it.vx, it.vy);
-        write_obs_intruder<FAITH>(a, obs_intruder_base<FAITH>(a, env), i, it);
-        wide = it.is64;
-      }
-      const uint32_t dw = __ballot_sync(FULL, wide);
-      if (lane == 0) {
-        s.cflag[flag_index(s, env, r)] = 0u;
-        if constexpr (FAITH) s.dflag[flag_index(s, env, r)] = dw;
+      d.tick = (uint32_t)tick;
+      Intr<FAITH> it;
+      spawn<FAITH, false>(d, a.cfg, a.k, (uint32_t)i, own.x, own.y, it, ihs_slot(s, env, i));
+      store_ipos<FAITH>(s, (tick & 1) ^ 1, env, i, it);     // the plane this step wrote
+      store_ivel(s, env, i, it.vx, it.vy);
+      write_obs_intruder<FAITH>(a, obs_intruder_base<FAITH>(a, env), i, it);
+      if constexpr (FAITH) {
+        if (it.is64) atomicOr(&s.dflag[flag_index(s, env, i >> 5)], 1u << (i & 31));
       }
     }
   }
-  GCA_KSTAMP_OUT(3);
+  __syncthreads();                                          // every warp's resets are queued, their scalar state stored
+  const int rounds = s.W, total = bs->count * rounds;
+  for (int job = wib; job < total; job += 4) {
+    const size_t env = (size_t)bs->env[job / rounds];
+    const int r = job % rounds, i = r * 32 + lane;
+    const int4 cnt = s.counters[env];                       // (tick already incremented by finish_tile)
+    d.env = a.env_id0 + (uint32_t)env;
+    d.tick = (uint32_t)cnt.z - 1u;                          // the tick of the step that finished the env
+    bool wide = false;
+    if (i < s.N) {
+      Intr<FAITH> it;
+      const float2 own = s.own_pos[env];                    // (50, 50) :72-76, or the random start finish_tile drew
+      spawn<FAITH, false>(d, a.cfg, a.k, GCA_SLOT_RESET | (uint32_t)i, own.x, own.y, it, ihs_slot(s, env, i));
+      store_ipos<FAITH>(s, cnt.z & 1, env, i, it);
+      store_ivel(s, env, i, it.vx, it.vy);
+      write_obs_intruder<FAITH>(a, obs_intruder_base<FAITH>(a, env), i, it);
+      wide = it.is64;
+    }
+    const uint32_t dw = __ballot_sync(FULL, wide);
+    if (lane == 0) {
+      s.cflag[flag_index(s, env, r)] = 0u;
+      if constexpr (FAITH) s.dflag[flag_index(s, env, r)] = dw;
+    }
+  }
 }
 
+// TAPE: finish only (respawns / resets replay the tape in place).  PHILOX: finish + spawn phase; the last kernel of
+// the step's fixed part, so it also counts the step (DevState::step_seq, the stamp of the next step's ownship records).
 template <bool FAITH, bool TAPE>
 __global__ void __launch_bounds__(128) step_finish_kernel(const __grid_constant__ StepArgs a) {
+  __shared__ WarpScratch ws[TAPE ? 1 : 4];
+  __shared__ BlockScratch bs;
   if (PDL_EARLY) pdl_launch_dependents();
+  if (!TAPE && threadIdx.x == 0) bs.count = 0;
   pdl_wait();
   GCA_KSTAMP_IN(2);
-  const long long tile = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (tile < a.s.T) finish_tile<FAITH, TAPE>(a, (int)tile, threadIdx.x & 31);
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long tile = (long long)blockIdx.x * 4 + wib;
+  if constexpr (TAPE) {
+    if (tile < a.s.T) finish_tile<FAITH, TAPE>(a, (int)tile, lane, nullptr, nullptr);
+  } else {
+    __syncthreads();
+    if (tile < a.s.T) finish_tile<FAITH, TAPE>(a, (int)tile, lane, &ws[wib], &bs);
+    if (a.s.N > 0) spawn_phase<FAITH>(a, (int)(tile < a.s.T ? tile : a.s.T), wib, lane, &ws[wib], &bs);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.s.step_seq += 1u;
+  }
   GCA_KSTAMP_OUT(2);
+}
+
+// No intruders (the package default, PKG/config.py:8 `intruder_size = 0`), PHILOX: nothing runs between the ownship
+// update and the finish, so the whole step is ONE kernel, thread = env (warp = tile, as in the finish).
+template <bool FAITH>
+__global__ void __launch_bounds__(128) step_n0_kernel(const __grid_constant__ StepArgs a) {
+  __shared__ WarpScratch ws[4];
+  __shared__ BlockScratch bs;
+  if (threadIdx.x == 0) bs.count = 0;
+  pdl_wait();
+  __syncthreads();
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long tile = (long long)blockIdx.x * 4 + wib;
+  const size_t me = (size_t)tile * 32 + lane;
+  if (me < (size_t)a.s.B) own_update<FAITH, false>(a, me, 0u, false);
+  if (tile < a.s.T) finish_tile<FAITH, false>(a, (int)tile, lane, &ws[wib], &bs);   // (reads back what this thread stored)
 }
 
 // ------------------------------------------------------------------------------ 2. intruders (the streaming pass)
@@ -680,9 +798,27 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
   __shared__ __align__(16) uint8_t stage_smem[kWarpsB * kWarpSmem];
   const DevState& s = a.s;
   const Derived& k = a.k;
+  // ---- PHILOX handles: the first own_blocks blocks of the grid are the OWNSHIP ROLE (thread = env).  Blocks are
+  // dispatched in index order, so every record a streaming lane waits for below belongs to a block that is already
+  // running or done (the forward-progress argument of a decoupled look-back scan).
+  uint32_t stamp = 0u;
+  if (a.own_blocks > 0) {
+    stamp = *s.step_seq + 1u;
+    if (blockIdx.x < (unsigned)a.own_blocks) {
+      const size_t env = (size_t)blockIdx.x * (kWarpsB * 32) + threadIdx.x;
+      if (env < (size_t)s.B) {
+        own_update<FAITH, false>(a, env, stamp, true);
+      } else if (env < (size_t)s.T * 32) {                // padding lanes of the last tile
+        float* rec = reinterpret_cast<float*>(&s.own_b[env]);
+        st_release_pair(rec, 0.f, 0.f);
+        st_release_pair(rec + 2, 0.f, __uint_as_float(stamp));
+      }
+      return;
+    }
+  }
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int n_chunks = (s.U + kChunkUnits - 1) / kChunkUnits;
-  const long long work = (long long)blockIdx.x * kWarpsB + wib;
+  const long long work = (long long)(blockIdx.x - (unsigned)a.own_blocks) * kWarpsB + wib;
   if (work >= (long long)s.T * n_chunks) return;          // (no block-wide barrier below)
   const int tile = (int)(work / n_chunks), ch = (int)(work - (long long)tile * n_chunks);
   const size_t me = (size_t)tile * 32 + lane;
@@ -701,7 +837,23 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
 #pragma unroll
     for (int g = 0; g < kChunkUnits; ++g) vv[g] = ldg_stream(vsrc + g * 512, pol);
   }
-  const float4 ob = s.own_b[me];
+  float4 ob;
+  if (a.own_blocks > 0) {
+    // wait for this step's ownship record of the lane's env: (bits, stamp) is stored behind a fence after (x, y), and
+    // a 16-byte aligned vector load is served from one sector - a matching stamp comes with its position
+    int spins = 0;
+    for (;;) {
+      ob = ld_volatile_f4(&s.own_b[me]);
+      if (__all_sync(FULL, __float_as_uint(ob.w) == stamp)) break;
+      if (++spins > (1 << 22)) {                          // ~0.5 s: dispatch order broke - fail loudly, do not hang
+        if (lane == 0) atomicExch(s.error_flag, 1);
+        break;
+      }
+      __nanosleep(32);
+    }
+  } else {
+    ob = s.own_b[me];
+  }
   const uint32_t bits = __float_as_uint(ob.z);
   const bool runs = (bits & kOwnRuns) != 0;               // false: the reference's loop never ran for this env (max steps)
   const int par = (bits & kOwnPlane) ? 1 : 0;
@@ -1118,9 +1270,12 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned blocks, unsigne
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
-// ev (nullable): 5 events recorded before / between / after the kernels of the step (gca_profile_*)
+// ev (nullable): 5 events recorded before / between / after the kernels of the step (gca_profile_*):
+//   TAPE    0 own 1 streaming 2 finish 3 (-) 4
+//   PHILOX  0 (-) 1 ownship role + streaming 2 finish + spawn phase 3 nearest / turn pass 4
 template <bool FAITH, bool TAPE>
-static cudaError_t launch_step_t(const StepArgs& a, cudaStream_t st, cudaEvent_t* ev) {
+static cudaError_t launch_step_t(const StepArgs& a0, cudaStream_t st, cudaEvent_t* ev) {
+  StepArgs a = a0;
   const DevState& s = a.s;
   const unsigned env_blocks = (unsigned)(((size_t)s.T * 32 + 127) / 128);
   // profiling events; inside a stream capture they must be EXTERNAL records to become event-record nodes of the graph
@@ -1133,11 +1288,21 @@ static cudaError_t launch_step_t(const StepArgs& a, cudaStream_t st, cudaEvent_t
     else cudaEventRecord(ev[i], st);
   };
   mark(0);
-  launch_pdl(step_own_kernel<FAITH, TAPE>, env_blocks, 128, st, a);
+  a.own_blocks = 0;
+  if constexpr (TAPE) launch_pdl(step_own_kernel<FAITH, TAPE>, env_blocks, 128, st, a);
   mark(1);
+  if (!TAPE && s.N == 0) {
+    if constexpr (!TAPE) launch_pdl(step_n0_kernel<FAITH>, env_blocks, 128, st, a);
+    mark(2);
+    mark(3);
+    mark(4);
+    return cudaGetLastError();
+  }
   if (s.N > 0) {
+    static_assert(kWarpsB * 32 == 128, "the ownship role is thread = env in blocks of 128");
     const int n_chunks = (s.U + kChunkUnits - 1) / kChunkUnits;
-    const unsigned blocks = (unsigned)(((long long)s.T * n_chunks + kWarpsB - 1) / kWarpsB);
+    a.own_blocks = TAPE ? 0 : (int)env_blocks;
+    const unsigned blocks = (unsigned)(((long long)s.T * n_chunks + kWarpsB - 1) / kWarpsB) + (unsigned)a.own_blocks;
     if constexpr (FAITH) {
       if (a.k.has_drift) launch_pdl(step_intruders_kernel<true, 0, true>, blocks, kWarpsB * 32, st, a);
       else launch_pdl(step_intruders_kernel<true, 0>, blocks, kWarpsB * 32, st, a);
@@ -1153,13 +1318,6 @@ static cudaError_t launch_step_t(const StepArgs& a, cudaStream_t st, cudaEvent_t
   mark(2);
   launch_pdl(step_finish_kernel<FAITH, TAPE>, (unsigned)((s.T + 3) / 4), 128, st, a);
   mark(3);
-  if constexpr (!TAPE) {
-    if (s.N > 0) {                                        // one warp per tile + half as many again for the reset jobs
-      const long long want = ((long long)s.T + s.T / 2 + 3) / 4;   // (the warps loop if more is queued)
-      const unsigned blocks = (unsigned)(want < 2368 ? want : 2368);
-      launch_pdl(spawn_kernel<FAITH>, blocks, 128, st, a);
-    }
-  }
   if (a.cfg.obs_kind == GCA_OBS_NEAREST)
     launch_pdl(nearest_obs_kernel<FAITH>, (unsigned)(((size_t)s.B + 31) / 32), 128, st, a);
   if (has_turn_pass(a)) launch_pdl(turn_obs_kernel<FAITH, !TAPE>, turn_blocks(s), 128, st, a);
@@ -1174,7 +1332,9 @@ cudaError_t launch_step(bool faith, bool tape, const StepArgs& a, cudaStream_t s
 
 // kernels one gca_step launches for this configuration (bench.py's gpu_launches)
 int step_launch_count(bool tape, int n_intruders, int obs_kind, bool turns) {
-  return 2 + (n_intruders > 0 ? 1 : 0) + (!tape && n_intruders > 0 ? 1 : 0) + (obs_kind == GCA_OBS_NEAREST ? 1 : 0) +
+  if (!tape && n_intruders == 0) return 1 + (obs_kind == GCA_OBS_NEAREST ? 1 : 0);   // step_n0_kernel
+  // TAPE: own, streaming, finish.  PHILOX: ownship role + streaming, finish + spawn phase.
+  return (tape ? 2 : 1) + (n_intruders > 0 ? 1 : 0) + (obs_kind == GCA_OBS_NEAREST ? 1 : 0) +
          (n_intruders > 0 && (obs_kind == GCA_OBS_RAW6 || turns) ? 1 : 0);
 }
 

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GCA_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libgca.so")
 
-GCA_ABI_VERSION = 5
+GCA_ABI_VERSION = 6
 
 MODE_FAITHFUL, MODE_FAST = 0, 1
 DRAWS_TAPE, DRAWS_PHILOX = 0, 1
@@ -133,6 +133,7 @@ def load():
         "gca_observe": ([vp, P(GcaOut), vp], C.c_int),
         "gca_read_counters": ([vp, vp, vp], C.c_int),
         "gca_step_launches": ([vp], C.c_int),
+        "gca_check": ([vp], C.c_int),
         "gca_profile_enable": ([vp, i32], C.c_int),
         "gca_profile_read": ([vp, P(GcaStepProfile)], C.c_int),
         "gca_compute_reward": ([vp, vp, i64, C.c_double, i32, i32, vp, i32, vp], C.c_int),

@@ -140,8 +140,12 @@ class BatchedAircraftEnv(object):
 
     @property
     def kernels_per_step(self):
-        """Kernels one step launches (ownship, intruders, finish, spawn)."""
+        """Kernels one step launches (gca_step_launches: 2 for a Philox handle with intruders)."""
         return self.lib.gca_step_launches(self._h)
+
+    def check(self):
+        """Synchronise and raise if an earlier asynchronous step failed on the device (gca_check)."""
+        abi.check(self.lib.gca_check(self._h))
 
     def profile(self, on):
         """Per-kernel device timing of step() (CUDA events between the kernels; not inside a graph capture)."""
@@ -224,6 +228,7 @@ class BatchedAircraftEnv(object):
         st = self._state_arrays()
         view = abi.GcaHostState(*[st[name].ctypes.data for name, _, _ in _STATE_FIELDS])
         abi.check(self.lib.gca_get_state(self._h, C.byref(view)))
+        self.check()
         return st
 
     def set_state(self, state):

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GCA_ABI_VERSION 5
+#define GCA_ABI_VERSION 6
 
 typedef enum gca_status {
   GCA_OK = 0,
@@ -200,9 +200,16 @@ int gca_reset(gca_env* env, const uint8_t* mask, const gca_tape* tape, const gca
 int gca_step(gca_env* env, const void* actions, const gca_tape* tape, int auto_reset,
              const gca_out* out, void* stream);
 
-/* Number of kernels one gca_step launches for this handle (ownship, intruders, finish, spawn, and the observation
- * pass of the NEAREST / RAW6 kinds: 2 to 5). */
+/* Number of kernels one gca_step launches for this handle.  GCA_DRAWS_PHILOX: 1 without intruders; else 2 (the main
+ * kernel = ownship role + streaming pass, then finish + spawn phase) + 1 for the observation pass of the NEAREST /
+ * RAW6 kinds.  GCA_DRAWS_TAPE (parity replays): ownship, streaming pass, finish (+ the observation pass). */
 int gca_step_launches(gca_env* env);
+
+/* Synchronises the device and reports a device-side failure of an earlier asynchronous gca_step: GCA_ERR_STATE if a
+ * streaming lane gave up waiting for its env's ownship record (the main kernel's ownship role and streaming role
+ * hand over through memory inside one launch; the wait is bounded so that a broken assumption fails loudly instead
+ * of hanging the GPU).  GCA_OK otherwise.  No reference counterpart. */
+int gca_check(gca_env* env);
 
 /* Diagnostics: per-kernel device time of gca_step.  While enabled, every gca_step records CUDA events
  * between its kernels on the caller's stream (do not enable inside a stream capture); gca_profile_read
@@ -211,7 +218,10 @@ int gca_step_launches(gca_env* env);
  * clock around a search in Algorithms/MCTS/Agent.py:36-43). */
 typedef struct gca_step_profile {
   int64_t steps;
-  double own_ms, intruders_ms, finish_ms, spawn_ms; /* summed over `steps` recorded steps */
+  /* summed over `steps` recorded steps.  GCA_DRAWS_PHILOX (two kernels per step): own_ms = 0, intruders_ms = the
+   * main kernel (ownship role + streaming pass), finish_ms = finish + spawn phase, spawn_ms = the nearest-n / turn
+   * pass of the variants that have one.  GCA_DRAWS_TAPE: ownship kernel, streaming pass, finish, 0. */
+  double own_ms, intruders_ms, finish_ms, spawn_ms;
 } gca_step_profile;
 int gca_profile_enable(gca_env* env, int on);
 int gca_profile_read(gca_env* env, gca_step_profile* out);

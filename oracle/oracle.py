@@ -1,8 +1,9 @@
 """ctypes wrapper of the CPU oracle (oracle/libgca_oracle.so).
 
 TEST INFRASTRUCTURE, NOT PRODUCT: imported only by tests/, __graft_entry__.smoke() and the
-cpu_baseline / --impl reference legs of bench.py.  It reuses the product's ctypes struct
-definitions (the oracle may look at the product; never the other way round).
+cpu_baseline / --impl reference legs of bench.py.  It imports nothing of the product: its ctypes
+struct definitions are its own (oracle/structs.py; a config built by the product's variants.make_config
+has the same layout and is passed by address).
 """
 import ctypes as C
 import os
@@ -23,8 +24,11 @@ def build(force=False):
 
 
 def _abi():
-    from gca_b200 import abi
-    return abi
+    try:
+        from . import structs
+    except ImportError:                      # imported as a top-level module
+        import structs
+    return structs
 
 
 class OracleBatch(C.Structure):
@@ -52,12 +56,13 @@ def lib():
     ]
     L = C.CDLL(LIB)
     P = C.POINTER
-    L.gca_oracle_step.argtypes = [P(abi.GcaConfig), P(OracleBatch), C.c_void_p]
-    L.gca_oracle_reset.argtypes = [P(abi.GcaConfig), P(OracleBatch), C.c_void_p]
-    L.gca_oracle_observe.argtypes = [P(abi.GcaConfig), P(OracleBatch)]
+    CFG = C.c_void_p                         # gca_config by address: the product's and the oracle's mirrors are the same bytes
+    L.gca_oracle_step.argtypes = [CFG, P(OracleBatch), C.c_void_p]
+    L.gca_oracle_reset.argtypes = [CFG, P(OracleBatch), C.c_void_p]
+    L.gca_oracle_observe.argtypes = [CFG, P(OracleBatch)]
     L.gca_oracle_compute_reward.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_void_p]
     L.gca_oracle_compute_reward_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_void_p]
-    L.gca_oracle_obs_dim.argtypes = [P(abi.GcaConfig), C.c_int]
+    L.gca_oracle_obs_dim.argtypes = [CFG, C.c_int]
     L.gca_oracle_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.gca_oracle_philox4x32_10.restype = None
     L.gca_oracle_sincos.argtypes = [C.c_double, C.c_int, P(C.c_double), P(C.c_double)]
@@ -68,14 +73,14 @@ def lib():
     L.gca_oracle_philox_uniform2.restype = None
     L.gca_oracle_philox_normal2.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
     L.gca_oracle_philox_normal2.restype = None
-    MC = abi.GcaMctsConfig
     vp, i32, i64, u32, u64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_uint32, C.c_uint64, C.c_double
-    L.gca_oracle_mcts_move.argtypes = [P(MC), i32, vp, i32, i32, i32, vp, vp, u64, u32, i32, vp, vp]
-    L.gca_oracle_mcts_rollout.argtypes = [P(MC), i32, vp, i32, i32, i32, vp, vp, u64, u32, u32, i32, vp, vp, vp]
-    L.gca_oracle_mcts_playouts.argtypes = [P(MC), i32, vp, i64, i32, i32, vp, u64, u32, i32, vp, vp, vp]
-    L.gca_oracle_mcts_search.argtypes = [P(MC), i32, vp, i32, i32, vp, vp, i32, vp, vp, vp, vp]
-    L.gca_oracle_mcts_search_philox.argtypes = [P(MC), i32, vp, i64, i32, i32, u64, u32, i32, vp, vp, vp, vp]
-    L.gca_oracle_raster.argtypes = [P(abi.GcaConfig), P(OracleBatch), vp, vp, vp]
+    MC = vp                                  # gca_mcts_config by address
+    L.gca_oracle_mcts_move.argtypes = [MC, i32, vp, i32, i32, i32, vp, vp, u64, u32, i32, vp, vp]
+    L.gca_oracle_mcts_rollout.argtypes = [MC, i32, vp, i32, i32, i32, vp, vp, u64, u32, u32, i32, vp, vp, vp]
+    L.gca_oracle_mcts_playouts.argtypes = [MC, i32, vp, i64, i32, i32, vp, u64, u32, i32, vp, vp, vp]
+    L.gca_oracle_mcts_search.argtypes = [MC, i32, vp, i32, i32, vp, vp, i32, vp, vp, vp, vp]
+    L.gca_oracle_mcts_search_philox.argtypes = [MC, i32, vp, i64, i32, i32, u64, u32, i32, vp, vp, vp, vp]
+    L.gca_oracle_raster.argtypes = [CFG, P(OracleBatch), vp, vp, vp]
     _lib = L
     return L
 

@@ -143,6 +143,8 @@ def test_golden_replay_fast(vk, n):
     otol = fast_obs_tol(vk)
     assert np.abs(f64(env.observe())[:, :D] - g["obs0"]).max(initial=0) <= otol
     acts = golden_actions(vk, g)
+    if env.continuous:                         # the fast mode takes its actions as f32 (a VecEnv action buffer)
+        acts = acts.astype(np.float32).astype(np.float64)
     worst = {"pos": 0.0, "obs": 0.0, "reward": 0.0}
     for t in range(acts.shape[1]):
         what = "%s n=%d step %d" % (vk, n, t)
@@ -387,7 +389,7 @@ def test_kernels_per_step_and_profile():
     dominant kernel."""
     torch = _torch()
     env = make_gpu("env", 80, 4096, "fast", "philox", seed=1)
-    assert env.kernels_per_step == 4                      # ownship, intruders, finish, spawn
+    assert env.kernels_per_step == 2                      # ownship role + streaming pass; finish + spawn phase
     env.reset()
     a = torch.zeros(4096, dtype=torch.int32, device="cuda")
     env.profile(True)
@@ -395,19 +397,19 @@ def test_kernels_per_step_and_profile():
         env.step(a)
     p = env.read_profile()
     env.profile(False)
-    assert p["steps"] == 5 and p["intruders_ms"] > 0 and p["own_ms"] > 0 and p["finish_ms"] > 0 and p["spawn_ms"] > 0
+    assert p["steps"] == 5 and p["intruders_ms"] > 0 and p["finish_ms"] > 0 and p["own_ms"] >= 0 and p["spawn_ms"] >= 0
     env.step(a)
     assert env.read_profile()["steps"] == 0
     env.close()
     e0 = make_gpu("env", 0, 64, "fast", "philox", seed=1)
-    assert e0.kernels_per_step == 2                       # no intruders: ownship + finish
+    assert e0.kernels_per_step == 1                       # no intruders: one kernel (ownship + finish, thread = env)
     e0.close()
     g = load_trace("env", 3)
     et = make_gpu("env", 3, g["tape"].shape[0], "faithful", "tape")
     assert et.kernels_per_step == 3                       # tape replay respawns in place: no spawn kernel
     et.close()
     er = make_gpu("mctsrnd", 80, 64, "fast", "philox", seed=1)
-    assert er.kernels_per_step == 5                       # + the turn / six-entry observation pass
+    assert er.kernels_per_step == 3                       # + the turn / six-entry observation pass
     er.close()
 
 

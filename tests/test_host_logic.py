@@ -158,7 +158,47 @@ def test_registry_and_spaces():
     assert Discrete(9).contains(8) and not Discrete(9).contains(9)
 
 
+def test_oracle_struct_mirrors_and_bench_workload_config():
+    """oracle/structs.py (the oracle's own mirror of include/gca.h, so that bench.py's reference arm needs nothing of
+    the product) against the product's mirror, and its written-out workload config against the variant table."""
+    from oracle import structs
+    from gym_guidance_collision_avoidance_single.envs.config import Config
+    for name in ("GcaConfig", "GcaHostState", "GcaMctsConfig"):
+        a, b = getattr(abi, name), getattr(structs, name)
+        assert ctypes.sizeof(a) == ctypes.sizeof(b)
+        assert [(n, getattr(a, n).offset, getattr(a, n).size) for n, _ in a._fields_] == \
+               [(n, getattr(b, n).offset, getattr(b, n).size) for n, _ in b._fields_], name
+    import bench
+    want = variants.make_config(bench.VARIANT, Config)
+    got = structs.bench_workload_config()
+    assert bytes(got) == bytes(want)
+    src = open(os.path.join(ROOT, "oracle", "oracle.py")).read() + open(os.path.join(ROOT, "oracle", "structs.py")).read()
+    assert "import gca_b200" not in src and "from gca_b200" not in src
+
+
+def test_bench_reference_arm_runs_without_the_product():
+    """`bench.py --impl reference`: oracle library only - neither libgca.so nor the gca_b200 package is loaded."""
+    import json
+    import subprocess
+    import sys
+    code = ("import sys, json; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '2', '--warmup', '1']; "
+            "import bench; bench.run_cpu.__defaults__ = (64, 0.5); bench.main(); "
+            "assert 'gca_b200' not in sys.modules and 'torch' not in sys.modules; "
+            "maps = open('/proc/self/maps').read(); assert 'libgca.so' not in maps and 'libgca_oracle.so' in maps")
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert set(line["config"]) == set(bench_config_keys())
+
+
+def bench_config_keys():
+    import bench
+    return bench.workload_config().keys()
+
+
 def test_bench_algorithmic_bytes():
     import bench
     assert bench.algorithmic_bytes_per_env_step(80) == 40 * 80 + 12 + 159
     assert bench.algorithmic_bytes_per_env_step(0, continuous=False) == 155
+    assert bench.streaming_bytes_per_env_step(80) == 3200 and bench.handover_bytes_per_env_step(80) == 160
