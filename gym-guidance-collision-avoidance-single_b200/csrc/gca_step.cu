@@ -55,7 +55,7 @@ extern "C" int gca_debug_fin(unsigned long long* host) { return (int)cudaMemcpyF
 extern "C" int gca_debug_kstamps(unsigned long long* host, int reset) {
   int rc = (int)cudaMemcpyFromSymbol(host, g_kstamp, sizeof(g_kstamp));
   if (reset) {
-    unsigned long long init[8] = {~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0};
+    unsigned long long init[8] = {~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, ~0ull};
     rc |= (int)cudaMemcpyToSymbol(g_kstamp, init, sizeof(init));
   }
   return rc;
@@ -351,7 +351,7 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
       stop = __ldcg(&s.ev_nmac[me]);
 #pragma unroll
       for (int w = 0; w < kWordsAhead; ++w) {
-        if (w < s.W) {
+        if (w < s.W && s.W <= kWordsAhead) {              // (N > 128: the word-by-word path below reads and clears them)
           const size_t fi = flag_index(s, me, w);
           wc[w] = __ldcg(&s.ev_conf[fi]);
           wg[w] = __ldcg(&s.ev_gone[fi]);
@@ -712,6 +712,9 @@ __device__ __forceinline__ void spawn_phase(const StepArgs& a, const int tile, c
       }
     }
   }
+#ifdef GCA_PHASE_TIMING
+  if (lane == 0 && tile < 2048 && tile < s.T) g_fin[tile * 8 + 7] = gtime();
+#endif
   __syncthreads();                                          // every warp's resets are queued, their scalar state stored
   const int rounds = s.W, total = bs->count * rounds;
   for (int job = wib; job < total; job += 4) {
@@ -805,6 +808,7 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
   if (a.own_blocks > 0) {
     stamp = *s.step_seq + 1u;
     if (blockIdx.x < (unsigned)a.own_blocks) {
+      GCA_KSTAMP_IN(0);
       const size_t env = (size_t)blockIdx.x * (kWarpsB * 32) + threadIdx.x;
       if (env < (size_t)s.B) {
         own_update<FAITH, false>(a, env, stamp, true);
@@ -813,6 +817,7 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
         st_release_pair(rec, 0.f, 0.f);
         st_release_pair(rec + 2, 0.f, __uint_as_float(stamp));
       }
+      GCA_KSTAMP_OUT(0);
       return;
     }
   }
@@ -838,6 +843,7 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
     for (int g = 0; g < kChunkUnits; ++g) vv[g] = ldg_stream(vsrc + g * 512, pol);
   }
   float4 ob;
+  GCA_KSTAMP_IN(3);                                       // (timing builds: first streaming block in / first record seen)
   if (a.own_blocks > 0) {
     // wait for this step's ownship record of the lane's env: (bits, stamp) is stored behind a fence after (x, y), and
     // a 16-byte aligned vector load is served from one sector - a matching stamp comes with its position
@@ -854,6 +860,9 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
   } else {
     ob = s.own_b[me];
   }
+#ifdef GCA_PHASE_TIMING
+  if (threadIdx.x == 0) atomicMin(&g_kstamp[7], gtime());
+#endif
   const uint32_t bits = __float_as_uint(ob.z);
   const bool runs = (bits & kOwnRuns) != 0;               // false: the reference's loop never ran for this env (max steps)
   const int par = (bits & kOwnPlane) ? 1 : 0;
