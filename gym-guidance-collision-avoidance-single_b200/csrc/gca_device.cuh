@@ -63,7 +63,14 @@ struct DevState {
                           //        bits: info | done << 8) of wall / goal / default / max-steps - the finish takes it unless an
                           //        intruder event outranks it
   uint32_t* step_seq;     // [1] steps launched on this handle; own_b.w of step k carries stamp k + 1 (valid under graph replay)
-  int* error_flag;        // [1] set by a streaming lane whose ownship record never arrived (never, unless dispatch order broke)
+  int* error_flag;        // [1] bit 0: a streaming lane's ownship record never arrived (dispatch order broke); forecast step:
+                          //     bit 1: a departure forecast disagrees with the advance, bit 2: a conflict in an env not classified hot
+  // forecast step (gca_step_fc.cu): three slots rotating with the env's tick z - a step reads slot z % 3, fills slot
+  // (z + 1) % 3 and clears slot (z + 2) % 3
+  uint32_t* fc_gone;      // [3][T][Wd][32] bit i: intruder i leaves the map at its next advance
+  uint32_t* fc_near;      // [3][T*32] f32 bits of the smallest squared ownship-intruder distance of the current state
+  float* fc_vmax;         // [T*32] upper bound of the distance an intruder of the env covers per step
+  uint32_t* exit_count;   // [1] blocks of the streaming kernel that are done with this step
   size_t pos_plane;       // bytes of one position plane
   int B, N, T, U, W, Wd;
 };
@@ -152,6 +159,7 @@ struct StepArgs {
   int D;                  // observation row length
   int auto_reset;
   int own_blocks;         // PHILOX: leading blocks of step_intruders_kernel that play the ownship role (0: TAPE, own kernel)
+  int head_ctas;          // forecast step: blocks of step_head_kernel (each owns every head_ctas-th group of 128 envs)
   void* obs;
   void* achieved;
   void* desired;

@@ -37,6 +37,7 @@
 
 #include "gca_device.cuh"
 #include "gca_launch.h"
+#include "gca_step_common.cuh"
 
 namespace gca {
 
@@ -78,16 +79,9 @@ constexpr int kWarpsB = GCA_WARPS_B;              // work items per block of the
 // staging row of one lane: 8 intruders x 16 bytes of observation entries, plus 16 bytes so that the row stride is
 // an odd multiple of 16 (conflict-free 16-byte shared accesses across a quarter warp)
 constexpr uint32_t kObsRow = 16u * kChunkIntr + 16u;
-constexpr uint32_t kOwnRuns = 1u, kOwnPlane = 2u; // bits of own_b.z
 #ifndef PDL_EARLY
 #define PDL_EARLY 0
 #endif
-
-// Programmatic dependent launch: the kernels of a step are launched with programmatic stream serialization, so
-// the next grid is staged (and its blocks scheduled as slots free up) while the current one drains.  A kernel
-// calls pdl_wait() before it touches anything an earlier kernel of the stream wrote.
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // reset(): PKG/SingleAircraftEnv.py:66-98 for env `env`, executed by the whole warp; positions go to `plane`.
 // PHILOX: lanes = intruders.  TAPE: lane `owner` replays the reference's sequential draw order.
@@ -140,40 +134,6 @@ __device__ __forceinline__ void reset_env_warp(const StepArgs& a, size_t env, in
   }
 }
 
-// ownship state right after reset: (50, 50), min speed, heading pi/4 (PKG/SingleAircraftEnv.py:72-76), or with
-// random_start random_pos(), random_speed(), random_heading() drawn in that order BEFORE the intruders
-// (Simulators/SingleAircraftDiscrete9HEREnv.py:78-82); f32 position and velocity (Aircraft.__init__ :269-276)
-template <bool TAPE>
-__device__ __forceinline__ void reset_ownship(const gca_config& c, Draws<TAPE>& d, float2& pos, double2& hs, double2& vel) {
-  double sn, cs;
-  if (c.random_start) {
-    double x, y, speed, heading;
-    draw_pos(d, c, GCA_SLOT_OWN_RESET, GCA_BLOCK_POS, x, y);
-    draw_speed_heading(d, c, GCA_SLOT_OWN_RESET, speed, heading);
-    pos = make_float2((float)x, (float)y);
-    hs = make_double2(heading, speed);
-  } else {
-    pos = make_float2(50.0f, 50.0f);
-    hs = make_double2(3.141592653589793 / 4, c.min_speed);
-  }
-  gca_sincos(hs.x, &sn, &cs);
-  vel = make_double2((double)(float)__dmul_rn(hs.y, cs), (double)(float)__dmul_rn(hs.y, sn));
-}
-
-template <bool TAPE>
-__device__ __forceinline__ Draws<TAPE> make_draws(const StepArgs& a, size_t me, uint32_t tick) {
-  Draws<TAPE> d;
-  if constexpr (TAPE) {
-    d.tape = a.tape + me * (size_t)a.tape_stride;
-    d.cur = a.cursor[me];
-  } else {
-    d.k0 = a.key0; d.k1 = a.key1;
-    d.env = a.env_id0 + (uint32_t)me;
-    d.tick = tick;
-  }
-  return d;
-}
-
 // ------------------------------------------------------------------------------ 1. ownship
 // Ownship.step(a)   PKG/SingleAircraftEnv.py:299-309 (2Env :291-301, DiscreteHER :301-311) for env `me`.
 // TAPE handles (parity replays): a kernel of its own, which also clears the env's event words.
@@ -182,15 +142,6 @@ __device__ __forceinline__ Draws<TAPE> make_draws(const StepArgs& a, size_t me, 
 // is known, and then settles everything of the step that does not depend on the intruders while the streaming role is
 // already running: the ownship / goal tail of the observation (:115-124) and the reward the step returns unless an
 // intruder event outranks it (wall / goal / default / max steps, :173-183) -> DevState::pre.
-__device__ __forceinline__ void st_release_pair(float* p, float x, float y) {
-  asm volatile("st.volatile.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(x), "f"(y) : "memory");
-}
-__device__ __forceinline__ float4 ld_volatile_f4(const float4* p) {
-  float4 v;
-  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-  return v;
-}
-
 template <bool FAITH, bool TAPE>
 __device__ __forceinline__ void own_update(const StepArgs& a, const size_t me, const uint32_t stamp, const bool publish) {
   using R = real_t<FAITH>;
@@ -787,11 +738,21 @@ __global__ void __launch_bounds__(128) step_n0_kernel(const __grid_constant__ St
 // entries start 24 bytes into the row: 8-byte stores.  0 = generic (any layout, both modes): per-lane stores.
 // DRIFT: every advance adds Config.position_sigma to the velocity (the random-intruder env); generic layout only, so the
 // instruction streams of the other instantiations are what they were without it.
-template <bool FAITH, int OM, bool DRIFT = false>
-__global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __grid_constant__ StepArgs a) {
+// FC: the streaming role of the forecast step (gca_step_fc.cu).  step_head_kernel, launched just before with a
+// programmatic launch edge, publishes the ownship records and - concurrently with this pass - replaces the intruders
+// that the previous step FORECAST to leave the map in this one, and advances whole envs itself where the reference's
+// sequential semantics can matter (a conflict is possible, or the env finishes and is reset).  This pass therefore
+// (i) stores nothing for an intruder whose forecast bit is set (the head writes its successor) and nothing at all for
+// an env whose record carries kOwnSkip, (ii) forecasts the departures of the NEXT step from the positions it stores
+// (the same f32 sum the next step will make) and (iii) keeps the smallest squared distance of the new state, from
+// which the next head decides which envs can possibly see a conflict.  Nothing runs after it.
+template <bool FAITH, int OM, bool DRIFT = false, bool FC = false>
+__global__ void __launch_bounds__(kWarpsB * 32, (FC && !FAITH) ? 8 : 1) step_intruders_kernel(const __grid_constant__ StepArgs a) {
   static_assert(!(DRIFT && OM), "a handle with a position drift takes the generic observation path");
-  if (PDL_EARLY) pdl_launch_dependents();
-  pdl_wait();
+  if constexpr (!FC) {                                    // (FC: ordered against the head by the records, against the
+    if (PDL_EARLY) pdl_launch_dependents();               //  previous step by the head's own wait)
+    pdl_wait();
+  }
   GCA_KSTAMP_IN(1);
   using R = real_t<FAITH>;
   static_assert(!(FAITH && OM), "the specialised observation path is FAST only");
@@ -805,7 +766,8 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
   // dispatched in index order, so every record a streaming lane waits for below belongs to a block that is already
   // running or done (the forward-progress argument of a decoupled look-back scan).
   uint32_t stamp = 0u;
-  if (a.own_blocks > 0) {
+  if constexpr (FC) stamp = *s.step_seq + 1u;
+  if (!FC && a.own_blocks > 0) {
     stamp = *s.step_seq + 1u;
     if (blockIdx.x < (unsigned)a.own_blocks) {
       GCA_KSTAMP_IN(0);
@@ -824,7 +786,8 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int n_chunks = (s.U + kChunkUnits - 1) / kChunkUnits;
   const long long work = (long long)(blockIdx.x - (unsigned)a.own_blocks) * kWarpsB + wib;
-  if (work >= (long long)s.T * n_chunks) return;          // (no block-wide barrier below)
+  do {                                                    // (one pass; `break` = this warp has no work item)
+  if (work >= (long long)s.T * n_chunks) break;
   const int tile = (int)(work / n_chunks), ch = (int)(work - (long long)tile * n_chunks);
   const size_t me = (size_t)tile * 32 + lane;
   const bool has_env = me < (size_t)s.B;
@@ -844,7 +807,7 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
   }
   float4 ob;
   GCA_KSTAMP_IN(3);                                       // (timing builds: first streaming block in / first record seen)
-  if (a.own_blocks > 0) {
+  if (FC || a.own_blocks > 0) {
     // wait for this step's ownship record of the lane's env: (bits, stamp) is stored behind a fence after (x, y), and
     // a 16-byte aligned vector load is served from one sector - a matching stamp comes with its position
     int spins = 0;
@@ -867,6 +830,16 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
   const bool runs = (bits & kOwnRuns) != 0;               // false: the reference's loop never ran for this env (max steps)
   const int par = (bits & kOwnPlane) ? 1 : 0;
   const float ox = ob.x, oy = ob.y;
+  // forecast step: fcw bit j = intruder i0 + j leaves the map in this step and the head replaces it
+  const bool skip = FC && (bits & kOwnSkip) != 0u;
+  uint32_t fcw = 0u, fnext = 0u;
+  size_t fc_fi = 0, fc_next = 0;
+  if constexpr (FC) {
+    const uint32_t slot = (bits >> kOwnSlotShift) & 3u;
+    fc_fi = flag_index(s, me, i0 >> 5);
+    fc_next = (size_t)(slot == 2u ? 0u : slot + 1u);
+    if (runs && !skip) fcw = (s.fc_gone[(size_t)slot * flag_plane_words(s) + fc_fi] >> (i0 & 31)) & ((1u << n_here) - 1u);
+  }
   const size_t pos_off = (unit0 * kPosUnits * 32 + lane) * 16;
   const uint8_t* psrc = s.ipos + (size_t)par * s.pos_plane + pos_off;
   uint8_t* pdst = s.ipos + (size_t)(par ^ 1) * s.pos_plane + pos_off;
@@ -899,16 +872,54 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
         const float d0 = dist2_f32(ox, oy, np[g].x, np[g].y), d1 = dist2_f32(ox, oy, np[g].z, np[g].w);   // :151
         conf |= ((d0 < k.sep2_f ? 1u : 0u) | (d1 < k.sep2_f ? 2u : 0u)) << (2 * g);
         nmac |= ((d0 < k.nmac2_f ? 1u : 0u) | (d1 < k.nmac2_f ? 2u : 0u)) << (2 * g);
-        near2 = fminf(near2, fminf(d0, d1));
+        if constexpr (FC) {                                 // (a replaced intruder's distance is the head's business)
+          near2 = fminf(near2, fminf(((fcw >> (2 * g)) & 1u) ? near2 : d0, ((fcw >> (2 * g)) & 2u) ? near2 : d1));
+        } else {
+          near2 = fminf(near2, fminf(d0, d1));
+        }
+      }
+      if constexpr (FC) {
+        if (runs && !skip && (gone & ~fcw) != 0u) atomicOr(s.error_flag, 2);   // a departure that was not forecast: never
+        // (the other direction cannot be tested here: the head may already have stored the successor's velocity)
       }
       if (!runs) {                                          // nobody moves: carry the positions over
         gone = conf = nmac = 0;
 #pragma unroll
         for (int g = 0; g < kChunkUnits; ++g) np[g] = p[g];
-      }
-      if (has_env) {
+        if constexpr (FC) {
+          near2 = __uint_as_float(0x7f800000u);
 #pragma unroll
-        for (int g = 0; g < kChunkUnits; ++g) stg_stream(pdst + g * 512, np[g], pol);
+          for (int g = 0; g < kChunkUnits; ++g)
+            near2 = fminf(near2, fminf(dist2_f32(ox, oy, p[g].x, p[g].y), dist2_f32(ox, oy, p[g].z, p[g].w)));
+        }
+      }
+      if constexpr (FC) {
+        // the next step's departures: the sum and the test it will make on what is stored now
+#pragma unroll
+        for (int g = 0; g < kChunkUnits; ++g) {
+          float4 dv = vv[g];
+          if constexpr (DRIFT)
+            dv = make_float4(__fadd_rn(dv.x, k.drift_f), __fadd_rn(dv.y, k.drift_f), __fadd_rn(dv.z, k.drift_f),
+                             __fadd_rn(dv.w, k.drift_f));
+          const float qx0 = __fadd_rn(np[g].x, dv.x), qy0 = __fadd_rn(np[g].y, dv.y);
+          const float qx1 = __fadd_rn(np[g].z, dv.z), qy1 = __fadd_rn(np[g].w, dv.w);
+          const bool o0 = (__float_as_uint(qx0) > wbits) | (__float_as_uint(qy0) > hbits);
+          const bool o1 = (__float_as_uint(qx1) > wbits) | (__float_as_uint(qy1) > hbits);
+          fnext |= ((o0 ? 1u : 0u) | (o1 ? 2u : 0u)) << (2 * g);
+        }
+        fnext &= ~fcw;
+      }
+      if (has_env && !skip) {
+#pragma unroll
+        for (int g = 0; g < kChunkUnits; ++g) {
+          const uint32_t pb = FC ? (fcw >> (2 * g)) & 3u : 0u;
+          if (pb == 0u) {
+            stg_stream(pdst + g * 512, np[g], pol);
+          } else {                                          // (the head stores the replaced half)
+            if (!(pb & 1u)) stg_stream2(pdst + g * 512, np[g].x, np[g].y, pol);
+            if (!(pb & 2u)) stg_stream2(pdst + g * 512 + 8, np[g].z, np[g].w, pol);
+          }
+        }
       }
       if constexpr (OM != 0) {
         // observation entries -> this lane's staging row -> transposed write-out: 8 consecutive lanes store
@@ -920,6 +931,7 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
           row[2 * g] = obs_intruder_vec(k, np[g].x, np[g].y, vv[g].x, vv[g].y);
           row[2 * g + 1] = obs_intruder_vec(k, np[g].z, np[g].w, vv[g].z, vv[g].w);
         }
+        if constexpr (FC) *reinterpret_cast<uint32_t*>(row + kChunkIntr) = skip ? 0xffu : fcw;   // (the row's padding)
         __syncwarp();
         constexpr int kLanesPerEnv = kChunkIntr, kEnvsPerStore = 32 / kLanesPerEnv;
         const int sub = lane / kLanesPerEnv, chunk = lane % kLanesPerEnv;
@@ -930,7 +942,10 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
 #pragma unroll
         for (int it = 0; it < kLanesPerEnv; ++it) {
           const float4 val = *reinterpret_cast<const float4*>(src + it * kEnvsPerStore * kObsRow);
-          if (env_sub + kEnvsPerStore * it < (size_t)s.B) {
+          bool keep = true;
+          if constexpr (FC)
+            keep = !((*reinterpret_cast<const uint32_t*>(stg + (sub + it * kEnvsPerStore) * kObsRow + 16 * kChunkIntr) >> chunk) & 1u);
+          if (keep && env_sub + kEnvsPerStore * it < (size_t)s.B) {
             if constexpr (OM == 1) {
               stg_stream(dst + it * dstep, val, pol);
             } else {                                        // own-first rows: entries are only 8-byte aligned
@@ -939,14 +954,14 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
             }
           }
         }
-      } else if (has_env) {
+      } else if (has_env && !skip) {
 #pragma unroll
         for (int g = 0; g < kChunkUnits; ++g) {
           Intr<FAITH> n0, n1;
           n0.px = np[g].x; n0.py = np[g].y; n0.vx = vv[g].x; n0.vy = vv[g].y;
           n1.px = np[g].z; n1.py = np[g].w; n1.vx = vv[g].z; n1.vy = vv[g].w;
-          write_obs_intruder<FAITH>(a, obase, i0 + 2 * g, n0);
-          write_obs_intruder<FAITH>(a, obase, i0 + 2 * g + 1, n1);
+          if (!((fcw >> (2 * g)) & 1u)) write_obs_intruder<FAITH>(a, obase, i0 + 2 * g, n0);
+          if (!((fcw >> (2 * g)) & 2u)) write_obs_intruder<FAITH>(a, obase, i0 + 2 * g + 1, n1);
         }
       }
     }
@@ -987,13 +1002,24 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
           conf |= (lt_sep ? 1u : 0u) << j;
           nmac |= (lt_nmac ? 1u : 0u) << j;
         }
-        if (has_env) *reinterpret_cast<double2*>(pdst + j * 512) = make_double2(it.px, it.py);
+        if constexpr (FC) {
+          if (!((fcw >> j) & 1u)) {
+            near2 = fminf(near2, dist2_f32(ox, oy, (float)it.px, (float)it.py));
+            Intr<FAITH> nx = it;
+            if (advance<FAITH, DRIFT>(k, nx)) fnext |= 1u << j;
+          }
+        }
+        if (has_env && !skip && !((fcw >> j) & 1u)) *reinterpret_cast<double2*>(pdst + j * 512) = make_double2(it.px, it.py);
         if (stage) {
           double o0, o1, o2, o3;
           obs_intruder_entries<FAITH>(a, it, o0, o1, o2, o3);
           row[2 * j] = make_double2(o0, o1);
           row[2 * j + 1] = make_double2(o2, o3);
         }
+      }
+      if constexpr (FC) {
+        if (runs && !skip && (gone & ~fcw) != 0u) atomicOr(s.error_flag, 2);
+        if (stage) *reinterpret_cast<uint32_t*>(stg + lane * kObsRow64 + 32 * kChunkIntr) = skip ? 0xffu : fcw;   // (row padding)
       }
       if (stage) {
         __syncwarp();
@@ -1003,7 +1029,10 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
         for (int it2 = 0; it2 < 16; ++it2) {
           const int e = sub + 2 * it2;
           const size_t env_e = (size_t)tile * 32 + e;
-          if (env_e < (size_t)s.B) {
+          bool keep = true;
+          if constexpr (FC)
+            keep = !((*reinterpret_cast<const uint32_t*>(stg + e * kObsRow64 + 32 * kChunkIntr) >> (piece >> 1)) & 1u);
+          if (keep && env_e < (size_t)s.B) {
             const double2 val = *reinterpret_cast<const double2*>(stg + e * kObsRow64 + piece * 16);
             double* dst = reinterpret_cast<double*>(a.obs) + env_e * (size_t)a.D + row_off + 2 * (size_t)piece;
             *reinterpret_cast<double2*>(dst) = val;
@@ -1012,7 +1041,7 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
       }
     }
   }
-  if (!fast_done && has_env) {
+  if (!fast_done && has_env && !skip) {
     // ---- generic: FAITHFUL positions (f64-capable) and the ragged last work item of a tile
     uint32_t dw = 0;
     if constexpr (FAITH) dw = s.dflag[flag_index(s, me, i0 >> 5)] >> (i0 & 31);
@@ -1036,12 +1065,31 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
         gone |= (oob ? 1u : 0u) << j;
         conf |= (lt_sep ? 1u : 0u) << j;
         nmac |= (lt_nmac ? 1u : 0u) << j;
-        if constexpr (!FAITH) near2 = fminf(near2, dist2_f32(ox, oy, it.px, it.py));
+        if constexpr (!FAITH && !FC) near2 = fminf(near2, dist2_f32(ox, oy, it.px, it.py));
+      }
+      if constexpr (FC) {
+        if ((fcw >> j) & 1u) continue;                        // the head stores its successor
+        near2 = fminf(near2, dist2_f32(ox, oy, (float)it.px, (float)it.py));
+        Intr<FAITH> nx = it;
+        if (advance<FAITH, DRIFT>(k, nx)) fnext |= 1u << j;
       }
       if constexpr (FAITH) *reinterpret_cast<double2*>(pdst + j * 512) = make_double2(it.px, it.py);
       else *reinterpret_cast<float2*>(pdst + (j >> 1) * 512 + (j & 1) * 8) = make_float2(it.px, it.py);
       write_obs_intruder<FAITH>(a, obase, i, it);
     }
+    if constexpr (FC) {
+      if (runs && (gone & ~fcw) != 0u) atomicOr(s.error_flag, 2);
+    }
+  }
+  if constexpr (FC) {
+    // ---- the forecast of the next step and the distance summary of the new state; a conflict here would mean the
+    // head's classification let an env through that it had to advance itself: flagged, never expected
+    if (has_env && !skip) {
+      if (fnext) atomicOr(&s.fc_gone[fc_next * flag_plane_words(s) + fc_fi], fnext << (i0 & 31));
+      atomicMin(&s.fc_near[fc_next * ((size_t)s.T * 32) + me], __float_as_uint(near2));
+      if (conf & ~fcw) atomicOr(s.error_flag, 4);             // (a replaced intruder's operands may be its successor's)
+    }
+    break;
   }
   // ---- record the (rare) events; i0 is a multiple of 8, so the 8 bits never straddle a word
   if (has_env) {
@@ -1052,6 +1100,21 @@ __global__ void __launch_bounds__(kWarpsB * 32) step_intruders_kernel(const __gr
     if (nmac) atomicMin(&s.ev_nmac[me], i0 + __ffs(nmac) - 1);
     if constexpr (!FAITH) {                                 // non-negative floats order like their bit patterns
       if (a.cfg.shaped_nearest && runs) atomicMin(&s.ev_near[me], __float_as_uint(near2));
+    }
+  }
+  } while (0);
+  if constexpr (FC) {
+    // The block that leaves last closes the step: it waits for the head kernel to be complete (it is, long since -
+    // this makes the order formal, so that the next step's head cannot start before this step's head has ended)
+    // and advances the step count the next records are stamped with.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned prev = atomicAdd(s.exit_count, 1u);
+      if (prev == gridDim.x - 1u) {
+        pdl_wait();
+        *s.exit_count = 0u;
+        *s.step_seq = stamp;
+      }
     }
   }
   GCA_KSTAMP_OUT(1);
@@ -1262,28 +1325,43 @@ static bool has_turn_pass(const StepArgs& a) {
 static unsigned turn_blocks(const DevState& s) { return (unsigned)((size_t)s.T * (size_t)((s.N + kTurnIntr - 1) / kTurnIntr)); }
 
 // ------------------------------------------------------------------------------ launchers
-// launch with programmatic stream serialization (see pdl_wait above)
-template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned blocks, unsigned threads, cudaStream_t st, Args&&... args) {
-  static const int use_pdl = std::getenv("GCA_NO_PDL") ? 0 : 1;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(blocks);
-  cfg.blockDim = dim3(threads);
-  cfg.dynamicSmemBytes = 0;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = use_pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
-}
-
 // ev (nullable): 5 events recorded before / between / after the kernels of the step (gca_profile_*):
 //   TAPE    0 own 1 streaming 2 finish 3 (-) 4
 //   PHILOX  0 (-) 1 ownship role + streaming 2 finish + spawn phase 3 nearest / turn pass 4
+// the streaming role of the forecast step (gca_step_fc.cu launches the head kernel right before it)
+cudaError_t launch_stream_fc(bool faith, const StepArgs& a, cudaStream_t st) {
+  const DevState& s = a.s;
+  const int n_chunks = (s.U + kChunkUnits - 1) / kChunkUnits;
+  const unsigned blocks = (unsigned)(((long long)s.T * n_chunks + kWarpsB - 1) / kWarpsB);
+  if (faith) {
+    if (a.k.has_drift) return launch_pdl(step_intruders_kernel<true, 0, true, true>, blocks, kWarpsB * 32, st, a);
+    return launch_pdl(step_intruders_kernel<true, 0, false, true>, blocks, kWarpsB * 32, st, a);
+  }
+  const bool own_first = a.cfg.obs_kind == GCA_OBS_HER || a.cfg.obs_kind == GCA_OBS_DHER;
+  const bool special = a.k.div1_ok && !a.k.has_drift;
+  if (special && a.cfg.obs_kind == GCA_OBS_VECTOR) return launch_pdl(step_intruders_kernel<false, 1, false, true>, blocks, kWarpsB * 32, st, a);
+  if (special && own_first) return launch_pdl(step_intruders_kernel<false, 2, false, true>, blocks, kWarpsB * 32, st, a);
+  if (a.k.has_drift) return launch_pdl(step_intruders_kernel<false, 0, true, true>, blocks, kWarpsB * 32, st, a);
+  return launch_pdl(step_intruders_kernel<false, 0, false, true>, blocks, kWarpsB * 32, st, a);
+}
+
+// the passes that need the FINAL intruder set of the step (PHILOX handles)
+cudaError_t launch_step_tail(bool faith, const StepArgs& a, cudaStream_t st) {
+  const DevState& s = a.s;
+  if (a.cfg.obs_kind == GCA_OBS_NEAREST) {
+    if (faith) launch_pdl(nearest_obs_kernel<true>, (unsigned)(((size_t)s.B + 31) / 32), 128, st, a);
+    else launch_pdl(nearest_obs_kernel<false>, (unsigned)(((size_t)s.B + 31) / 32), 128, st, a);
+  }
+  if (has_turn_pass(a)) {
+    if (faith) launch_pdl(turn_obs_kernel<true, true>, turn_blocks(s), 128, st, a);
+    else launch_pdl(turn_obs_kernel<false, true>, turn_blocks(s), 128, st, a);
+  }
+  return cudaGetLastError();
+}
+
 template <bool FAITH, bool TAPE>
 static cudaError_t launch_step_t(const StepArgs& a0, cudaStream_t st, cudaEvent_t* ev) {
+  if (forecast_step_applies(a0, TAPE)) return launch_step_fc(FAITH, a0, st, ev);
   StepArgs a = a0;
   const DevState& s = a.s;
   const unsigned env_blocks = (unsigned)(((size_t)s.T * 32 + 127) / 128);
