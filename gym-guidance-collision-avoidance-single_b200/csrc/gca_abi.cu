@@ -44,7 +44,7 @@ struct gca_env {
   uint32_t env_id0 = 0;
   DevState s{};
   int D = 0;
-  bool fc_valid = false;    // the forecast words describe the current state (forecast step, gca_step_fc.cu)
+  bool fc_valid = false;    // the forecast words describe the current state (forecast step, gca_step_fc.cuh)
   // host path (gca_step_host / gca_reset_host)
   cudaStream_t stream = nullptr;
   void* d_actions = nullptr;
@@ -113,6 +113,7 @@ Derived derive(const gca_config& c) {
   k.sep2_d = sq_threshold<double>(c.minimum_separation);
   k.nmac2_d = sq_threshold<double>(c.nmac_dist);
   k.init2_d = sq_threshold<double>(c.initial_min_dist);
+  k.goal2_d = sq_threshold<double>(c.goal_radius);
   k.win_w = (float)c.window_width;
   k.win_h = (float)c.window_height;
   k.ob_w = (float)c.ob_window_width;
@@ -283,10 +284,12 @@ int gca_create(const gca_config* cfg, int n_envs, int n_intruders, int mode, int
   if (!rc) rc = dev_alloc(e, &s.step_seq, 1);
   if (!rc) rc = dev_alloc(e, &s.error_flag, 1);
   if (!rc) rc = dev_alloc(e, &s.exit_count, 1);
+  if (!rc) rc = dev_alloc(e, &s.head_sync, 2);
   if (!rc && draws == GCA_DRAWS_PHILOX && n_intruders > 0) {
     rc = dev_alloc(e, &s.fc_gone, 3 * flag_plane_words(s));
     if (!rc) rc = dev_alloc(e, &s.fc_near, 3 * (size_t)s.T * 32);
     if (!rc) rc = dev_alloc(e, &s.fc_vmax, (size_t)s.T * 32);
+    if (!rc) rc = dev_alloc(e, &s.fc_queue, 4 + 2 * (size_t)s.T * 32);
   }
   if (!rc) rc = dev_alloc(e, &s.ivel, vel_plane_bytes(s));
   if (!rc) rc = dev_alloc(e, &s.cflag, flag_plane_words(s));

@@ -71,6 +71,9 @@ struct DevState {
   uint32_t* fc_near;      // [3][T*32] f32 bits of the smallest squared ownship-intruder distance of the current state
   float* fc_vmax;         // [T*32] upper bound of the distance an intruder of the env covers per step
   uint32_t* exit_count;   // [1] blocks of the streaming kernel that are done with this step
+  uint32_t* head_sync;    // [2] (blocks of the head kernel that are done with this step, stamp of the step whose head is complete)
+  int* fc_queue;          // [4 + 2 T*32] (hot envs, finished envs, job cursor, tail blocks done), then the two env lists:
+                          // the warp jobs of the tail kernel
   size_t pos_plane;       // bytes of one position plane
   int B, N, T, U, W, Wd;
 };
@@ -115,6 +118,7 @@ __host__ __device__ inline size_t flag_index(const DevState& s, size_t env, int 
 struct Derived {
   float sep2_f, nmac2_f, init2_f;     // f32 distances (thr taken as f32, NumPy 2 weak scalars)
   double sep2_d, nmac2_d, init2_d;    // f64 distances
+  double goal2_d;                     // goal_radius, for the squared f64 ownship-goal distance (dist2_f64)
   float win_w, win_h;                 // Box bounds are f32 (PKG/SingleAircraftEnv.py:38-41)
   float ob_w, ob_h, inv_ob_w, inv_ob_h;   // x / Config.window_* in f32, and RN(1/.) for gca_div_const_f32
   float ms, den, inv_den;             // normalize_velocity: (v + ms) / den in f32

@@ -43,12 +43,14 @@ namespace gca {
 
 // Optional kernel-level timestamps (build with -DGCA_PHASE_TIMING): first block in / last block out per kernel.
 #ifdef GCA_PHASE_TIMING
-__device__ unsigned long long g_kstamp[8];   // [kernel][start, end]
+__device__ unsigned long long g_kstamp[16];  // [kernel][start, end], then single stamps
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+__device__ unsigned long long g_cta[8192 * 2];   // per block of the streaming kernel: first instruction, last instruction
+extern "C" int gca_debug_cta(unsigned long long* host) { return (int)cudaMemcpyFromSymbol(host, g_cta, sizeof(g_cta)); }
 __device__ unsigned long long g_fin[2048 * 8];   // per tile: finish start, end, respawn iterations, resets
 extern "C" int gca_debug_fin(unsigned long long* host) { return (int)cudaMemcpyFromSymbol(host, g_fin, sizeof(g_fin)); }
 #define GCA_KSTAMP_IN(kid) do { if (threadIdx.x == 0) atomicMin(&g_kstamp[2 * (kid)], gtime()); } while (0)
@@ -56,7 +58,7 @@ extern "C" int gca_debug_fin(unsigned long long* host) { return (int)cudaMemcpyF
 extern "C" int gca_debug_kstamps(unsigned long long* host, int reset) {
   int rc = (int)cudaMemcpyFromSymbol(host, g_kstamp, sizeof(g_kstamp));
   if (reset) {
-    unsigned long long init[8] = {~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, ~0ull};
+    unsigned long long init[16] = {~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, ~0ull, ~0ull, 0, ~0ull, 0, 0, 0, 0, 0};
     rc |= (int)cudaMemcpyToSymbol(g_kstamp, init, sizeof(init));
   }
   return rc;
@@ -731,6 +733,10 @@ __global__ void __launch_bounds__(128) step_n0_kernel(const __grid_constant__ St
   if (tile < a.s.T) finish_tile<FAITH, false>(a, (int)tile, lane, &ws[wib], &bs);   // (reads back what this thread stored)
 }
 
+}  // namespace gca
+#include "gca_step_fc.cuh"   // the forecast step: ownship role, jobs kernel, launch_step_fc (one translation unit: shared timing stamps)
+namespace gca {
+
 // ------------------------------------------------------------------------------ 2. intruders (the streaming pass)
 // OM: 1 = the observation is GCA_OBS_VECTOR with the one-correction division exact (the registered ids'
 // layout; FAST only): entries are computed without run-time layout tests and leave through the transposed
@@ -749,24 +755,38 @@ __global__ void __launch_bounds__(128) step_n0_kernel(const __grid_constant__ St
 template <bool FAITH, int OM, bool DRIFT = false, bool FC = false>
 __global__ void __launch_bounds__(kWarpsB * 32, (FC && !FAITH) ? 8 : 1) step_intruders_kernel(const __grid_constant__ StepArgs a) {
   static_assert(!(DRIFT && OM), "a handle with a position drift takes the generic observation path");
-  if constexpr (!FC) {                                    // (FC: ordered against the head by the records, against the
-    if (PDL_EARLY) pdl_launch_dependents();               //  previous step by the head's own wait)
+  if constexpr (!FC) {
+    if (PDL_EARLY) pdl_launch_dependents();
     pdl_wait();
+  } else {
+    pdl_wait();                                           // the previous step (its tail kernel closed it) is complete
+    pdl_launch_dependents();                              // the tail kernel may be scheduled once the last block of this grid is resident
   }
   GCA_KSTAMP_IN(1);
+#ifdef GCA_PHASE_TIMING
+  if (threadIdx.x == 0 && blockIdx.x < 8192) g_cta[2 * blockIdx.x] = gtime();
+#endif
   using R = real_t<FAITH>;
   static_assert(!(FAITH && OM), "the specialised observation path is FAST only");
   // observation staging: FAST specialised layouts 8 x 16 bytes per lane, FAITHFUL 8 x 32 bytes per lane (+ 16: odd stride)
   constexpr uint32_t kObsRow64 = 32u * kChunkIntr + 16u;
   constexpr uint32_t kWarpSmem = OM ? 32 * kObsRow : (FAITH ? 32 * kObsRow64 : 16);
-  __shared__ __align__(16) uint8_t stage_smem[kWarpsB * kWarpSmem];
+  constexpr uint32_t kStageBytes = (FC && kWarpsB * kWarpSmem < kJobCap * 4u) ? kJobCap * 4u : kWarpsB * kWarpSmem;   // (the head role's job list)
+  __shared__ __align__(16) uint8_t stage_smem[kStageBytes];
   const DevState& s = a.s;
   const Derived& k = a.k;
   // ---- PHILOX handles: the first own_blocks blocks of the grid are the OWNSHIP ROLE (thread = env).  Blocks are
   // dispatched in index order, so every record a streaming lane waits for below belongs to a block that is already
   // running or done (the forward-progress argument of a decoupled look-back scan).
   uint32_t stamp = 0u;
-  if constexpr (FC) stamp = *s.step_seq + 1u;
+  bool head_block = false;
+  if constexpr (FC) {
+    stamp = *s.step_seq + 1u;
+    if (blockIdx.x < (unsigned)a.head_ctas) {               // the head role of the forecast step (gca_step_fc.cuh)
+      head_role_fc<FAITH>(a, stamp, reinterpret_cast<uint32_t*>(stage_smem));
+      head_block = true;
+    }
+  }
   if (!FC && a.own_blocks > 0) {
     stamp = *s.step_seq + 1u;
     if (blockIdx.x < (unsigned)a.own_blocks) {
@@ -785,9 +805,9 @@ __global__ void __launch_bounds__(kWarpsB * 32, (FC && !FAITH) ? 8 : 1) step_int
   }
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int n_chunks = (s.U + kChunkUnits - 1) / kChunkUnits;
-  const long long work = (long long)(blockIdx.x - (unsigned)a.own_blocks) * kWarpsB + wib;
+  const long long work = (long long)(blockIdx.x - (unsigned)(FC ? a.head_ctas : a.own_blocks)) * kWarpsB + wib;
   do {                                                    // (one pass; `break` = this warp has no work item)
-  if (work >= (long long)s.T * n_chunks) break;
+  if (head_block || work >= (long long)s.T * n_chunks) break;
   const int tile = (int)(work / n_chunks), ch = (int)(work - (long long)tile * n_chunks);
   const size_t me = (size_t)tile * 32 + lane;
   const bool has_env = me < (size_t)s.B;
@@ -824,7 +844,7 @@ __global__ void __launch_bounds__(kWarpsB * 32, (FC && !FAITH) ? 8 : 1) step_int
     ob = s.own_b[me];
   }
 #ifdef GCA_PHASE_TIMING
-  if (threadIdx.x == 0) atomicMin(&g_kstamp[7], gtime());
+  if (threadIdx.x == 0) { atomicMin(&g_kstamp[7], gtime()); }
 #endif
   const uint32_t bits = __float_as_uint(ob.z);
   const bool runs = (bits & kOwnRuns) != 0;               // false: the reference's loop never ran for this env (max steps)
@@ -1087,7 +1107,22 @@ __global__ void __launch_bounds__(kWarpsB * 32, (FC && !FAITH) ? 8 : 1) step_int
     if (has_env && !skip) {
       if (fnext) atomicOr(&s.fc_gone[fc_next * flag_plane_words(s) + fc_fi], fnext << (i0 & 31));
       atomicMin(&s.fc_near[fc_next * ((size_t)s.T * 32) + me], __float_as_uint(near2));
-      if (conf & ~fcw) atomicOr(s.error_flag, 4);             // (a replaced intruder's operands may be its successor's)
+    }
+    // ---- conflicts (PKG/SingleAircraftEnv.py:157-163, :169-170).  An env that reaches this point cannot see an NMAC
+    // in this step (the head advances those itself), so the order of the reference's loop does not matter: any
+    // intruder inside minimum_separation makes the step's return (r_conflict, False, 'c') - the head wrote what the
+    // step returns otherwise BEFORE it published the record -, sets its flag (which never clears, Q8) and counts if
+    // the flag was False.  A replaced intruder's test is the head's (its operands may already be its successor's).
+    const uint32_t cbits = conf & ~fcw;
+    if (has_env && !skip && cbits) {
+      if (nmac & cbits) atomicOr(s.error_flag, 4);            // the head's classification let an NMAC through: never
+      reinterpret_cast<R*>(a.reward)[me] = (R)a.cfg.r_conflict;
+      a.info[me] = (uint8_t)GCA_INFO_CONFLICT;
+      const uint32_t fresh = (cbits << (i0 & 31)) & ~s.cflag[fc_fi];
+      if (fresh) {
+        atomicOr(&s.cflag[fc_fi], fresh);
+        atomicAdd(&s.counters[me].x, __popc(fresh));
+      }
     }
     break;
   }
@@ -1103,20 +1138,10 @@ __global__ void __launch_bounds__(kWarpsB * 32, (FC && !FAITH) ? 8 : 1) step_int
     }
   }
   } while (0);
-  if constexpr (FC) {
-    // The block that leaves last closes the step: it waits for the head kernel to be complete (it is, long since -
-    // this makes the order formal, so that the next step's head cannot start before this step's head has ended)
-    // and advances the step count the next records are stamped with.
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const unsigned prev = atomicAdd(s.exit_count, 1u);
-      if (prev == gridDim.x - 1u) {
-        pdl_wait();
-        *s.exit_count = 0u;
-        *s.step_seq = stamp;
-      }
-    }
-  }
+#ifdef GCA_PHASE_TIMING
+  __syncthreads();
+  if (threadIdx.x == 0 && blockIdx.x < 8192) g_cta[2 * blockIdx.x + 1] = gtime();
+#endif
   GCA_KSTAMP_OUT(1);
 }
 
@@ -1331,8 +1356,18 @@ static unsigned turn_blocks(const DevState& s) { return (unsigned)((size_t)s.T *
 // the streaming role of the forecast step (gca_step_fc.cu launches the head kernel right before it)
 cudaError_t launch_stream_fc(bool faith, const StepArgs& a, cudaStream_t st) {
   const DevState& s = a.s;
+  static bool once = false;
+  if (!once) {
+    prefer_carveout(step_intruders_kernel<true, 0, true, true>);
+    prefer_carveout(step_intruders_kernel<true, 0, false, true>);
+    prefer_carveout(step_intruders_kernel<false, 1, false, true>);
+    prefer_carveout(step_intruders_kernel<false, 2, false, true>);
+    prefer_carveout(step_intruders_kernel<false, 0, true, true>);
+    prefer_carveout(step_intruders_kernel<false, 0, false, true>);
+    once = true;
+  }
   const int n_chunks = (s.U + kChunkUnits - 1) / kChunkUnits;
-  const unsigned blocks = (unsigned)(((long long)s.T * n_chunks + kWarpsB - 1) / kWarpsB);
+  const unsigned blocks = (unsigned)(((long long)s.T * n_chunks + kWarpsB - 1) / kWarpsB) + (unsigned)a.head_ctas;
   if (faith) {
     if (a.k.has_drift) return launch_pdl(step_intruders_kernel<true, 0, true, true>, blocks, kWarpsB * 32, st, a);
     return launch_pdl(step_intruders_kernel<true, 0, false, true>, blocks, kWarpsB * 32, st, a);

@@ -12,6 +12,9 @@ constexpr uint32_t kOwnRuns = 1u;       // the reference's intruder loop runs fo
 constexpr uint32_t kOwnPlane = 2u;      // parity of the env's current position plane
 constexpr uint32_t kOwnSkip = 4u;       // forecast step: another role advances this env (hot / resetting): the lane does nothing
 constexpr uint32_t kOwnSlotShift = 3u;  // forecast step: bits 3-4 = tick % 3, the forecast slot this step reads
+constexpr uint32_t kOwnConf = 32u;      // forecast step: an intruder can be inside minimum_separation after this step
+constexpr uint32_t kOwnHot = 64u;       // forecast step: class of the env for the jobs kernel - a warp replays the reference's loop
+constexpr uint32_t kOwnReset = 128u;    //                                                   - the env finished: reset()'s spawns
 
 // Programmatic dependent launch: the kernels of a step are launched with programmatic stream serialization, so
 // the next grid is staged (and its blocks scheduled as slots free up) while the current one drains.  A kernel
@@ -56,6 +59,9 @@ __device__ __forceinline__ Draws<TAPE> make_draws(const StepArgs& a, size_t me, 
 __device__ __forceinline__ void st_release_pair(float* p, float x, float y) {
   asm volatile("st.volatile.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(x), "f"(y) : "memory");
 }
+__device__ __forceinline__ void st_release_quad(float* p, float x, float y, float z, float w) {
+  asm volatile("st.volatile.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
 __device__ __forceinline__ float4 ld_volatile_f4(const float4* p) {
   float4 v;
   asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
@@ -76,6 +82,28 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned blocks, unsigne
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+// Kernels that are meant to share SMs must agree on the L1 / shared-memory split: an SM only changes it when it is
+// idle, so blocks of a kernel that prefers another split wait until the resident kernel has left the SM (measured:
+// the streaming kernel started 21 us late behind a persistent head kernel with the default preference).
+inline int shared_carveout_percent() {
+  static const int pct = std::getenv("GCA_CARVEOUT") ? std::atoi(std::getenv("GCA_CARVEOUT")) : 72;   // 164 KB of 228 KB
+  return pct;
+}
+template <typename... KArgs>
+static void prefer_carveout(void (*kernel)(KArgs...)) {
+  cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel), cudaFuncAttributePreferredSharedMemoryCarveout, shared_carveout_percent());
+}
+
+// plain stream-ordered launch (for kernels that do not call pdl_wait)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_plain(void (*kernel)(KArgs...), unsigned blocks, unsigned threads, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(threads);
+  cfg.stream = st;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 

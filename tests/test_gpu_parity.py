@@ -458,3 +458,20 @@ def test_random_configurations_bit_exact_vs_oracle(case):
     assert_state_equal(env.get_state(), ref.state, "final state", skip=())
     env.close()
     print(vk, mode, "W,H", W, H, "N", n, "B", B)
+
+
+@pytest.mark.gpu
+def test_forecast_step_bit_exact_vs_oracle_in_subprocess():
+    """The opt-in forecast step (GCA_FORECAST=1: head role + streaming pass side by side, tail kernel for hot envs and
+    resets, csrc/gca_step_fc.cuh) must give the same bits as the default step: the Philox rollouts against the oracle
+    and the full-size case, re-run in a subprocess with the switch set (it is read once per process)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, GCA_FORECAST="1")
+    here = os.path.abspath(__file__)
+    sel = "test_philox_rollout_bit_exact_vs_oracle or test_full_size_bit_exact_vs_oracle or test_state_roundtrip"
+    out = subprocess.run([sys.executable, "-m", "pytest", here, "-x", "-q", "-m", "gpu", "-k", sel, "-p", "no:cacheprovider"],
+                         env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert " passed" in out.stdout

@@ -24,16 +24,17 @@ from gca_b200.batched import BatchedAircraftEnv  # noqa: E402
 from gym_guidance_collision_avoidance_single.envs.config import Config  # noqa: E402
 
 B, N = 65536, int(os.environ.get("GCA_N", "80"))
+PRE = int(os.environ.get("GCA_PRESTEPS", "300"))
 env = BatchedAircraftEnv("SingleAircraft2Env", B, Config, n_intruders=N, mode="fast", seed=1)
 env.reset()
 acts = [torch.rand((B, 2), device="cuda") * 2 - 1 for _ in range(8)]
 lib = abi.load()
 lib.gca_debug_kstamps.argtypes = [C.c_void_p, C.c_int]
-buf = np.zeros(8, np.uint64)
+buf = np.zeros(16, np.uint64)
 g1 = torch.cuda.CUDAGraph()
 side = torch.cuda.Stream()
 with torch.cuda.stream(side):
-    for i in range(300):
+    for i in range(PRE):
         env.step(acts[i % 8])
 torch.cuda.synchronize()
 with torch.cuda.graph(g1):
@@ -42,45 +43,42 @@ g8 = torch.cuda.CUDAGraph()
 with torch.cuda.graph(g8):
     for i in range(8):
         env.step(acts[i])
-names = ["own role", "main kernel (in: first block, out: last streaming block)", "finish kernel"]
 
 
 def show(st, label):
-    t0 = int(min(st[0], st[2]))
+    t0 = int(min(st[0], st[2], st[4]))
     rel = lambda v: (int(v) - t0) / 1e3
     print(label)
-    print("  own role          first in %7.2f   last out %7.2f" % (rel(st[0]), rel(st[1])))
-    print("  main kernel       first in %7.2f   last streaming block out %7.2f" % (rel(st[2]), rel(st[3])))
-    print("  streaming role    first block in %7.2f   first record seen %7.2f" % (rel(st[6]), rel(st[7])))
-    print("  finish kernel     first in %7.2f   last out %7.2f" % (rel(st[4]), rel(st[5])))
+    print("  ownship kernel    first in %7.2f   last out %7.2f   first record out %7.2f   last record out %7.2f" % (rel(st[0]), rel(st[1]), rel(st[8]), rel(st[9])))
+    print("  jobs / finish     first in %7.2f   last out %7.2f   (respawns %d, hot envs %d, resets %d)" % (rel(st[4]), rel(st[5]), st[12], st[13], st[14]))
+    print("  streaming kernel  first in %7.2f   last out %7.2f   first record seen %7.2f" % (rel(st[2]), rel(st[3]), rel(st[7])))
+    print("  tail kernel       first in %7.2f   last out %7.2f" % (rel(st[10]), rel(st[11])))
 
 
 for rep in range(3):
-    g8.replay()
-torch.cuda.synchronize()
-for rep in range(3):
-    # steady state: 8 steps of a graph, then ONE more step as its own graph, stamped
     g8.replay()
     lib.gca_debug_kstamps(buf.ctypes.data, 1)          # (syncs through the symbol copy)
     g8.replay()
     torch.cuda.synchronize()
     lib.gca_debug_kstamps(buf.ctypes.data, 1)
     st = buf.astype(np.int64)
-    print("8-step graph: first in .. last out = %.2f us per step" % ((st[5] - min(st[0], st[2])) / 8e3))
+    print("8-step graph: first in .. last out = %.2f us per step" % ((max(st[1], st[3], st[5], st[11]) - min(st[0], st[2], st[4])) / 8e3))
     g1.replay()
     torch.cuda.synchronize()
     lib.gca_debug_kstamps(buf.ctypes.data, 1)
     show(buf.astype(np.int64), "single-step graph (us, relative to the first block of the step):")
-fb = np.zeros(2048 * 8, np.uint64)
-lib.gca_debug_fin.argtypes = [C.c_void_p]
-lib.gca_debug_fin(fb.ctypes.data)
-f = fb.astype(np.int64).reshape(2048, 8)
-dur = (f[:, 1] - f[:, 0]) / 1e3
-print("finish_tile per tile (us): mean %.2f p50 %.2f p90 %.2f p99 %.2f max %.2f" % (dur.mean(), np.median(dur), np.percentile(dur, 90), np.percentile(dur, 99), dur.max()))
-sp = (f[:, 7] - f[:, 1]) / 1e3
-print("spawn phase (i) per tile (us): mean %.2f p50 %.2f p99 %.2f max %.2f" % (sp.mean(), np.median(sp), np.percentile(sp, 99), sp.max()))
-print("finish start (rel to first) p10 %.1f p50 %.1f p90 %.1f max %.1f ; finish_tile end max %.1f ; spawn (i) end max %.1f" % tuple(
-    [(np.percentile(f[:, 0], q) - f[:, 0].min()) / 1e3 for q in (10, 50, 90, 100)] + [(f[:, 1].max() - f[:, 0].min()) / 1e3, (f[:, 7].max() - f[:, 0].min()) / 1e3]))
-print("finish phases (us, mean): loads %.2f  replay %.2f  reward+stores %.2f  reset+counters %.2f" % (
-    ((f[:, 4] - f[:, 0]) / 1e3).mean(), ((f[:, 5] - f[:, 4]) / 1e3).mean(), ((f[:, 6] - f[:, 5]) / 1e3).mean(), ((f[:, 1] - f[:, 6]) / 1e3).mean()))
 env.check()
+# per-block timeline of the streaming kernel of the last single-step graph
+cb = np.zeros(8192 * 2, np.uint64)
+lib.gca_debug_cta.argtypes = [C.c_void_p]
+lib.gca_debug_cta(cb.ctypes.data)
+c = cb.astype(np.int64).reshape(8192, 2)
+c = c[(c[:, 0] > 0) & (c[:, 1] > 0)]
+t0 = c[:, 0].min()
+start, end = (c[:, 0] - t0) / 1e3, (c[:, 1] - t0) / 1e3
+print("streaming blocks: %d, lifetime us mean %.2f p50 %.2f p90 %.2f max %.2f" % (len(c), (end - start).mean(), np.median(end - start), np.percentile(end - start, 90), (end - start).max()))
+edges = np.arange(0, end.max() + 4, 4.0)
+for lo in edges:
+    m = (end >= lo) & (end < lo + 4)
+    if m.any():
+        print("  t=%5.1f..%5.1f  blocks finished %5d  mean lifetime %.2f  resident at t %d" % (lo, lo + 4, m.sum(), (end - start)[m].mean(), ((start <= lo) & (end > lo)).sum()))
