@@ -93,6 +93,55 @@ def python_reference_figures():
         return None
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's host thread to the cores of the NUMA node its GPU hangs off, so that the pinned buffers it
+    allocates next (first touch) are local to the GPU's PCIe root.  Returns what to restore, or None."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"old": None, "note": "GPU %s reports no NUMA node (single-node host)" % bdf}
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        old = os.sched_getaffinity(0)
+        use = cpus & old
+        if not use:
+            return {"old": None, "note": "NUMA node %d has no core this process may use" % node}
+        os.sched_setaffinity(0, use)
+        return {"old": old, "note": "host thread and pinned buffers on NUMA node %d (%d cores) of GPU %s" % (node, len(use), bdf)}
+    except Exception as e:     # no sysfs / no permission: leave the placement to the OS
+        return {"old": None, "note": "not bound (%s)" % type(e).__name__}
+
+
+def restore_affinity(numa):
+    if numa and numa.get("old"):
+        try:
+            os.sched_setaffinity(0, numa["old"])
+        except Exception:
+            pass
+
+
+def measure_d2h_ceiling(torch, nbytes, barrier, copies=8):
+    """Time `copies` device->host copies of nbytes into pinned memory (what one e2e step downloads), all ranks at once."""
+    src = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    dst = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(copies):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    return {"seconds": time.perf_counter() - t0, "copies": copies}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -330,21 +379,45 @@ def main_gpu(args):
     # ---- end to end through the host-buffer C-ABI call (GCA_BENCH_KERNEL_ONLY=1 skips it for ncu captures)
     kernel_only = os.environ.get("GCA_BENCH_KERNEL_ONLY") == "1"
     host_actions = [a.cpu().numpy() for a in actions[:8]]
+    numa = bind_to_gpu_numa_node(local)               # before the pinned buffers are allocated (first touch)
     for i in range(3):
         env.step_host(host_actions[i % 8])
     Ke = 3 if kernel_only else max(3, min(K, 300))
+
+    def wall_max(seconds):
+        te = torch.tensor([seconds], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return float(te.item())
+
+    # (a) one step at a time: upload, step, download, synchronise
     barrier()
     t0 = time.perf_counter()
     for i in range(Ke):
         obs, rew, dn, info = env.step_host(host_actions[i % 8])
         _ = float(rew[0])
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * Ke / float(te.item())
+    e2e_serial = world * B * Ke / wall_max(time.perf_counter() - t0)
+    # (b) VecEnv step_async / step_wait with two steps in flight: the download of step t runs under the kernels of t + 1
+    for i in range(2):
+        env.step_host_begin(host_actions[i % 8])
+        env.step_host_wait()
+    barrier()
+    t0 = time.perf_counter()
+    env.step_host_begin(host_actions[0])
+    for i in range(1, Ke):
+        env.step_host_begin(host_actions[i % 8])
+        obs, rew, dn, info = env.step_host_wait()
+        _ = float(rew[0])
+    obs, rew, dn, info = env.step_host_wait()
+    _ = float(rew[0])
+    torch.cuda.synchronize()
+    e2e_value = world * B * Ke / wall_max(time.perf_counter() - t0)
     h2d, d2h = env.host_io_bytes()
+    # (c) what the host link gives this rank while every rank downloads at once: the ceiling of (a) and (b)
+    link = measure_d2h_ceiling(torch, d2h, barrier)
+    link_gbs = d2h * link["copies"] / wall_max(link["seconds"]) / 1e9
+    restore_affinity(numa)
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -366,8 +439,17 @@ def main_gpu(args):
                        % (replays, G, eager_steps, kernels_per_step)),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": Ke, "api": "BatchedAircraftEnv.step_host -> gca_step_host (pinned host buffers)",
+                    "steps": Ke,
+                    "api": "BatchedAircraftEnv.step_host_begin / step_host_wait -> gca_step_host_begin / _wait (pinned host "
+                           "buffers, two steps in flight: the download of step t under the kernels of step t + 1)",
+                    "serial_value": e2e_serial,
+                    "serial_api": "BatchedAircraftEnv.step_host -> gca_step_host (one step at a time)",
                     "host_link_gbs": (h2d + d2h) * (e2e_value / world / B) / 1e9,
+                    "link_ceiling_gbs": link_gbs,
+                    "link_ceiling_note": "per rank: %d device->host copies of %d bytes into pinned memory, every rank at "
+                                         "once, max over ranks - what the host memory system gives one rank with %d "
+                                         "GPU(s) downloading" % (link["copies"], d2h, world),
+                    "numa": numa.get("note") if numa else None,
                     "note": "bound by the device->host copy of the observations over PCIe, not by the kernels"},
             "gpu_launches": K * kernels_per_step,
             "roofline": {"bound": "hbm", "kernel": "step_intruders_kernel", "achieved": achieved, "peak": peak,

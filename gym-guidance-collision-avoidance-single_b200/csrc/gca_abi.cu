@@ -45,10 +45,13 @@ struct gca_env {
   DevState s{};
   int D = 0;
   bool fc_valid = false;    // the forecast words describe the current state (forecast step, gca_step_fc.cuh)
-  // host path (gca_step_host / gca_reset_host)
-  cudaStream_t stream = nullptr;
-  void* d_actions = nullptr;
-  gca_out d_out{};
+  // host path (gca_step_host[_begin / _wait] / gca_reset_host): compute stream, download stream, two sets of
+  // device-side buffers and the events that order them
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  void* d_actions[2] = {nullptr, nullptr};
+  gca_out d_out[2] = {};
+  cudaEvent_t ev_step[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+  unsigned long long host_begun = 0, host_waited = 0;
   std::vector<void*> allocs;
   // gca_profile_*
   bool profiling = false;
@@ -318,6 +321,11 @@ int gca_destroy(gca_env* e) {
   for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
   for (cudaEvent_t ev : e->prof_pool) cudaEventDestroy(ev);
   if (e->stream) cudaStreamDestroy(e->stream);
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (e->ev_step[i]) cudaEventDestroy(e->ev_step[i]);
+    if (e->ev_copy[i]) cudaEventDestroy(e->ev_copy[i]);
+  }
   delete e;
   return GCA_OK;
 }
@@ -445,54 +453,113 @@ int gca_read_counters(gca_env* e, int32_t* counters, void* stream) {
 }
 
 // ------------------------------------------------------------------------------ host-buffer path
+static void release_host_path(gca_env* e) {
+  if (e->stream) cudaStreamDestroy(e->stream);
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  e->stream = e->copy_stream = nullptr;
+  for (int i = 0; i < 2; ++i) {
+    if (e->ev_step[i]) cudaEventDestroy(e->ev_step[i]);
+    if (e->ev_copy[i]) cudaEventDestroy(e->ev_copy[i]);
+    e->ev_step[i] = e->ev_copy[i] = nullptr;
+  }
+}
+
 static int ensure_host_path(gca_env* e) {
   if (e->stream) return GCA_OK;
   if (e->draws != GCA_DRAWS_PHILOX) return fail(GCA_ERR_STATE, "the host-buffer path needs GCA_DRAWS_PHILOX");
   GCA_CUDA(cudaSetDevice(e->device));
-  GCA_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   const size_t B = (size_t)e->s.B, rs = real_size(e);
   int rc = GCA_OK;
   uint8_t* p = nullptr;
-  if (!rc) { rc = dev_alloc(e, &p, B * 2 * sizeof(double)); e->d_actions = p; }
-  if (!rc) { rc = dev_alloc(e, &p, B * (size_t)e->D * rs); e->d_out.obs = p; }
-  if (!rc) { rc = dev_alloc(e, &p, B * 2 * rs); e->d_out.achieved = p; }
-  if (!rc) { rc = dev_alloc(e, &p, B * 2 * rs); e->d_out.desired = p; }
-  if (!rc) { rc = dev_alloc(e, &p, B * rs); e->d_out.reward = p; }
-  if (!rc) { rc = dev_alloc(e, &p, B); e->d_out.done = p; }
-  if (!rc) { rc = dev_alloc(e, &p, B); e->d_out.info = p; }
-  return rc;
+  for (int k = 0; k < 2 && !rc; ++k) {
+    if (!rc) { rc = dev_alloc(e, &p, B * 2 * sizeof(double)); e->d_actions[k] = p; }
+    if (!rc) { rc = dev_alloc(e, &p, B * (size_t)e->D * rs); e->d_out[k].obs = p; }
+    if (!rc) { rc = dev_alloc(e, &p, B * 2 * rs); e->d_out[k].achieved = p; }
+    if (!rc) { rc = dev_alloc(e, &p, B * 2 * rs); e->d_out[k].desired = p; }
+    if (!rc) { rc = dev_alloc(e, &p, B * rs); e->d_out[k].reward = p; }
+    if (!rc) { rc = dev_alloc(e, &p, B); e->d_out[k].done = p; }
+    if (!rc) { rc = dev_alloc(e, &p, B); e->d_out[k].info = p; }
+    if (!rc && e->cfg.shaped_nearest) { rc = dev_alloc(e, &p, B * rs); e->d_out[k].nearest = p; }
+  }
+  if (rc) return rc;                                       // (the buffers stay in e->allocs; the path stays unset)
+  cudaStream_t st = nullptr, cs = nullptr;
+  cudaError_t ce = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && ce == cudaSuccess; ++i) {
+    ce = cudaEventCreateWithFlags(&e->ev_step[i], cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->ev_copy[i], cudaEventDisableTiming);
+  }
+  e->stream = st;
+  e->copy_stream = cs;
+  if (ce != cudaSuccess) {
+    release_host_path(e);
+    return cuda_fail(ce, "creating the host path's streams / events");
+  }
+  return GCA_OK;
 }
 
-static int copy_out(gca_env* e, const gca_out* h, bool with_reward) {
+// downloads of one set of device-side outputs, enqueued on `st`
+static int enqueue_copy_out(gca_env* e, const gca_out& d, const gca_out* h, bool with_reward, cudaStream_t st) {
   const size_t B = (size_t)e->s.B, rs = real_size(e);
   const bool her = e->cfg.obs_kind == GCA_OBS_HER || e->cfg.obs_kind == GCA_OBS_DHER || e->cfg.obs_kind == GCA_OBS_NEAREST;
-  if (h->obs && e->D) GCA_CUDA(cudaMemcpyAsync(h->obs, e->d_out.obs, B * (size_t)e->D * rs, cudaMemcpyDeviceToHost, e->stream));
-  if (her && h->achieved) GCA_CUDA(cudaMemcpyAsync(h->achieved, e->d_out.achieved, B * 2 * rs, cudaMemcpyDeviceToHost, e->stream));
-  if (her && h->desired) GCA_CUDA(cudaMemcpyAsync(h->desired, e->d_out.desired, B * 2 * rs, cudaMemcpyDeviceToHost, e->stream));
-  if (with_reward && h->reward) GCA_CUDA(cudaMemcpyAsync(h->reward, e->d_out.reward, B * rs, cudaMemcpyDeviceToHost, e->stream));
-  if (h->done) GCA_CUDA(cudaMemcpyAsync(h->done, e->d_out.done, B, cudaMemcpyDeviceToHost, e->stream));
-  if (h->info) GCA_CUDA(cudaMemcpyAsync(h->info, e->d_out.info, B, cudaMemcpyDeviceToHost, e->stream));
-  GCA_CUDA(cudaStreamSynchronize(e->stream));
+  if (h->obs && e->D) GCA_CUDA(cudaMemcpyAsync(h->obs, d.obs, B * (size_t)e->D * rs, cudaMemcpyDeviceToHost, st));
+  if (her && h->achieved) GCA_CUDA(cudaMemcpyAsync(h->achieved, d.achieved, B * 2 * rs, cudaMemcpyDeviceToHost, st));
+  if (her && h->desired) GCA_CUDA(cudaMemcpyAsync(h->desired, d.desired, B * 2 * rs, cudaMemcpyDeviceToHost, st));
+  if (with_reward && h->reward) GCA_CUDA(cudaMemcpyAsync(h->reward, d.reward, B * rs, cudaMemcpyDeviceToHost, st));
+  if (h->done) GCA_CUDA(cudaMemcpyAsync(h->done, d.done, B, cudaMemcpyDeviceToHost, st));
+  if (h->info) GCA_CUDA(cudaMemcpyAsync(h->info, d.info, B, cudaMemcpyDeviceToHost, st));
+  if (h->nearest && d.nearest) GCA_CUDA(cudaMemcpyAsync(h->nearest, d.nearest, B * rs, cudaMemcpyDeviceToHost, st));
+  return GCA_OK;
+}
+
+int gca_step_host_begin(gca_env* e, const void* actions_host, int auto_reset, const gca_out* host_out) {
+  if (!e) return fail(GCA_ERR_INVALID, "env is NULL");
+  if (!actions_host || !host_out) return fail(GCA_ERR_INVALID, "actions/out is NULL");
+  if (int rc = ensure_host_path(e)) return rc;
+  if (e->host_begun - e->host_waited >= 2) return fail(GCA_ERR_STATE, "two steps are already in flight: call gca_step_host_wait first");
+  const int k = (int)(e->host_begun & 1ull);
+  const size_t B = (size_t)e->s.B;
+  const size_t abytes = e->cfg.action_kind == GCA_ACT_CONTINUOUS2 ? B * 2 * real_size(e) : B * sizeof(int32_t);
+  GCA_CUDA(cudaMemcpyAsync(e->d_actions[k], actions_host, abytes, cudaMemcpyHostToDevice, e->stream));
+  // buffer set k was last downloaded by the step begun two calls ago: its copy must have read it
+  if (e->host_begun >= 2) GCA_CUDA(cudaStreamWaitEvent(e->stream, e->ev_copy[k], 0));
+  if (int rc = gca_step(e, e->d_actions[k], nullptr, auto_reset, &e->d_out[k], e->stream)) return rc;
+  GCA_CUDA(cudaEventRecord(e->ev_step[k], e->stream));
+  GCA_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_step[k], 0));
+  if (int rc = enqueue_copy_out(e, e->d_out[k], host_out, true, e->copy_stream)) return rc;
+  GCA_CUDA(cudaEventRecord(e->ev_copy[k], e->copy_stream));
+  e->host_begun += 1;
+  return GCA_OK;
+}
+
+int gca_step_host_wait(gca_env* e) {
+  if (!e) return fail(GCA_ERR_INVALID, "env is NULL");
+  if (e->host_begun == e->host_waited) return fail(GCA_ERR_STATE, "no step in flight");
+  GCA_CUDA(cudaSetDevice(e->device));
+  GCA_CUDA(cudaEventSynchronize(e->ev_copy[(int)(e->host_waited & 1ull)]));
+  e->host_waited += 1;
   return GCA_OK;
 }
 
 int gca_step_host(gca_env* e, const void* actions_host, int auto_reset, const gca_out* host_out) {
   if (!e) return fail(GCA_ERR_INVALID, "env is NULL");
-  if (!actions_host || !host_out) return fail(GCA_ERR_INVALID, "actions/out is NULL");
-  if (int rc = ensure_host_path(e)) return rc;
-  const size_t B = (size_t)e->s.B;
-  const size_t abytes = e->cfg.action_kind == GCA_ACT_CONTINUOUS2 ? B * 2 * real_size(e) : B * sizeof(int32_t);
-  GCA_CUDA(cudaMemcpyAsync(e->d_actions, actions_host, abytes, cudaMemcpyHostToDevice, e->stream));
-  if (int rc = gca_step(e, e->d_actions, nullptr, auto_reset, &e->d_out, e->stream)) return rc;
-  return copy_out(e, host_out, true);
+  while (e->host_begun != e->host_waited)                  // (steps begun asynchronously come first)
+    if (int rc = gca_step_host_wait(e)) return rc;
+  if (int rc = gca_step_host_begin(e, actions_host, auto_reset, host_out)) return rc;
+  return gca_step_host_wait(e);
 }
 
 int gca_reset_host(gca_env* e, const gca_out* host_out) {
   if (!e) return fail(GCA_ERR_INVALID, "env is NULL");
   if (!host_out) return fail(GCA_ERR_INVALID, "out is NULL");
   if (int rc = ensure_host_path(e)) return rc;
-  if (int rc = gca_reset(e, nullptr, nullptr, &e->d_out, e->stream)) return rc;
-  return copy_out(e, host_out, false);
+  while (e->host_begun != e->host_waited)
+    if (int rc = gca_step_host_wait(e)) return rc;
+  GCA_CUDA(cudaStreamSynchronize(e->copy_stream));
+  if (int rc = gca_reset(e, nullptr, nullptr, &e->d_out[0], e->stream)) return rc;
+  if (int rc = enqueue_copy_out(e, e->d_out[0], host_out, false, e->stream)) return rc;
+  GCA_CUDA(cudaStreamSynchronize(e->stream));
+  return GCA_OK;
 }
 
 // ------------------------------------------------------------------------------ full-state access
@@ -604,6 +671,16 @@ int gca_compute_reward(const void* ag, const void* g, int64_t m, double radius, 
   if (kind != GCA_OBS_HER && kind != GCA_OBS_DHER) return fail(GCA_ERR_INVALID, "kind must be GCA_OBS_HER or GCA_OBS_DHER");
   GCA_CUDA(cudaSetDevice(device));
   GCA_CUDA(launch_compute_reward(ag, g, (long long)m, radius, kind, is_f64, out, (cudaStream_t)stream));
+  return GCA_OK;
+}
+
+int gca_input_reward(const void* rows, int64_t m, int dim, int is_f64, const gca_input_reward_cfg* cfg, double* out,
+                     uint8_t* done, int device, void* stream) {
+  if (m < 0 || !cfg || (m > 0 && (!rows || !out))) return fail(GCA_ERR_INVALID, "bad buffers");
+  if (dim < 4 || (cfg->has_intruders && cfg->n_listed > 0 && (cfg->n_listed - 1) * 4 + 5 >= dim))
+    return fail(GCA_ERR_INVALID, "rows are shorter than the entries compute_input_reward reads");
+  GCA_CUDA(cudaSetDevice(device));
+  GCA_CUDA(launch_input_reward(rows, (long long)m, dim, is_f64, cfg, out, done, (cudaStream_t)stream));
   return GCA_OK;
 }
 

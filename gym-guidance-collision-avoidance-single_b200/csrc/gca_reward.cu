@@ -43,6 +43,55 @@ cudaError_t launch_compute_reward(const void* ag, const void* g, long long m, do
   return cudaGetLastError();
 }
 
+// compute_input_reward(new_inputs) of Simulators/SingleAircraftDiscrete9HEREnv.py:244-276 for m relabelled
+// (observation + goal) rows at once: thread = row.  The reference's arithmetic, statement by statement: the
+// un-normalisation products and metric()'s differences / squares in the dtype of the row (NumPy scalars), the square
+// root in f64 (math.sqrt), the listed intruders read with stride 4 although each has 5 entries (idx * 4 + 4: kept),
+// the first listed intruder inside minimum_separation decides (conflict, or NMAC inside NMAC_dist), then goal /
+// step penalty / shaped default.  done = (r == 10 or r == -10), the literals of Algorithms/pytorch/agent_her.py:117.
+template <typename T>
+__global__ void __launch_bounds__(256) input_reward_kernel(const T* __restrict__ rows, long long m, int dim,
+                                                           const gca_input_reward_cfg c, double* __restrict__ out,
+                                                           uint8_t* __restrict__ done) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const T* v = rows + i * (long long)dim;
+  const T w = (T)c.window_width, h = (T)c.window_height;   // (a Python number: it takes the array scalar's dtype)
+  auto metric = [](T x1, T y1, T x2, T y2) {
+    const T dx = x1 - x2, dy = y1 - y2;                    // (-fmad=false: single multiplies and adds)
+    return sqrt((double)(dx * dx + dy * dy));
+  };
+  const T ownx = v[0] * w, owny = v[1] * h, gx = v[dim - 2] * w, gy = v[dim - 1] * h;
+  const double dist_goal = metric(ownx, owny, gx, gy);
+  double r;
+  bool settled = false;
+  if (c.has_intruders) {
+    for (int idx = 0; idx < c.n_listed && !settled; ++idx) {
+      const T ix = v[idx * 4 + 4] * w, iy = v[idx * 4 + 5] * h;
+      const double d = metric(ownx, owny, ix, iy);
+      if (d < c.minimum_separation) {
+        r = d < c.nmac_dist ? c.nmac_penalty : c.conflict_penalty;
+        settled = true;
+      }
+    }
+  }
+  if (!settled) {
+    if (dist_goal < c.goal_radius) r = c.goal_reward;
+    else r = c.sparse_reward ? c.step_penalty : -dist_goal / 1200.0;
+  }
+  out[i] = r;
+  if (done) done[i] = (r == 10.0 || r == -10.0) ? 1 : 0;
+}
+
+cudaError_t launch_input_reward(const void* rows, long long m, int dim, int is_f64, const gca_input_reward_cfg* cfg,
+                                double* out, uint8_t* done, cudaStream_t st) {
+  if (m <= 0) return cudaSuccess;
+  const unsigned blocks = (unsigned)((m + 255) / 256);
+  if (is_f64) input_reward_kernel<double><<<blocks, 256, 0, st>>>((const double*)rows, m, dim, *cfg, out, done);
+  else input_reward_kernel<float><<<blocks, 256, 0, st>>>((const float*)rows, m, dim, *cfg, out, done);
+  return cudaGetLastError();
+}
+
 // VecMonitor.step_wait (baselines common/vec_env/vec_monitor.py:21-37) for the whole batch: thread = env.  Finished
 // episodes are appended to a device ring (warp-aggregated slot reservation: one atomic per warp).
 template <typename R>

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GCA_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libgca.so")
 
-GCA_ABI_VERSION = 6
+GCA_ABI_VERSION = 7
 
 MODE_FAITHFUL, MODE_FAST = 0, 1
 DRAWS_TAPE, DRAWS_PHILOX = 0, 1
@@ -62,6 +62,13 @@ class GcaHerDraws(C.Structure):
 
 class GcaHerTransitions(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("o", "u", "g", "ag", "o_2", "ag_2", "r", "episode", "t", "future_t")]
+
+
+class GcaInputRewardCfg(C.Structure):
+    """gca_input_reward_cfg of include/gca.h"""
+    _fields_ = [(n, C.c_double) for n in ("window_width", "window_height", "minimum_separation", "nmac_dist", "goal_radius",
+                                          "conflict_penalty", "nmac_penalty", "goal_reward", "step_penalty")] + \
+               [(n, C.c_int32) for n in ("n_listed", "has_intruders", "sparse_reward", "reserved")]
 
 
 class GcaMctsConfig(C.Structure):
@@ -128,6 +135,8 @@ def load():
         "gca_step": ([vp, vp, P(GcaTape), i32, P(GcaOut), vp], C.c_int),
         "gca_step_host": ([vp, vp, i32, P(GcaOut)], C.c_int),
         "gca_reset_host": ([vp, P(GcaOut)], C.c_int),
+        "gca_step_host_begin": ([vp, vp, i32, P(GcaOut)], C.c_int),
+        "gca_step_host_wait": ([vp], C.c_int),
         "gca_get_state": ([vp, P(GcaHostState)], C.c_int),
         "gca_set_state": ([vp, P(GcaHostState)], C.c_int),
         "gca_observe": ([vp, P(GcaOut), vp], C.c_int),
@@ -137,6 +146,7 @@ def load():
         "gca_profile_enable": ([vp, i32], C.c_int),
         "gca_profile_read": ([vp, P(GcaStepProfile)], C.c_int),
         "gca_compute_reward": ([vp, vp, i64, C.c_double, i32, i32, vp, i32, vp], C.c_int),
+        "gca_input_reward": ([vp, i64, i32, i32, P(GcaInputRewardCfg), vp, vp, i32, vp], C.c_int),
         "gca_raster": ([vp, vp, vp, i64, i64, i32, i32, vp, vp], C.c_int),
         "gca_monitor_update": ([vp, i32, vp, i64, vp, vp, vp, i64, vp, u32, i32, vp], C.c_int),
         "gca_stats_update": ([vp, vp, i64, vp, i32, vp], C.c_int),

@@ -170,8 +170,10 @@ class BatchedAircraftEnv(object):
         return out
 
     # ------------------------------------------------------------------ host-buffer (end-to-end) API
-    def _host_buffers(self):
+    def _host_buffers(self, which=0):
         if self._host is None:
+            self._host = [None, None]
+        if self._host[which] is None:
             torch = _torch()
             B = self.num_envs
             pin = dict(pin_memory=True)
@@ -189,8 +191,8 @@ class BatchedAircraftEnv(object):
                              h["achieved"].data_ptr() if self.is_goal_env else None,
                              h["desired"].data_ptr() if self.is_goal_env else None,
                              h["reward"].data_ptr(), h["done"].data_ptr(), h["info"].data_ptr())
-            self._host = (h, out, {k: v.numpy() for k, v in h.items()})
-        return self._host
+            self._host[which] = (h, out, {k: v.numpy() for k, v in h.items()})
+        return self._host[which]
 
     def host_io_bytes(self):
         """(host->device, device->host) bytes moved by one step_host call."""
@@ -210,6 +212,24 @@ class BatchedAircraftEnv(object):
         views["actions"][...] = np.asarray(actions).reshape(views["actions"].shape)
         abi.check(self.lib.gca_step_host(self._h, h["actions"].data_ptr(), 1 if auto_reset else 0, C.byref(out)))
         self.launches += self.kernels_per_step
+        return views["obs"], views["reward"], views["done"], views["info"]
+
+    def step_host_begin(self, actions, auto_reset=True):
+        """VecEnv.step_async on host memory (gca_step_host_begin): returns at once; at most two steps in flight.  The
+        download of this step overlaps the kernels of the next one begun before step_host_wait() is called."""
+        which = self._host_turn = getattr(self, "_host_turn", 1) ^ 1
+        h, out, views = self._host_buffers(which)
+        views["actions"][...] = np.asarray(actions).reshape(views["actions"].shape)
+        abi.check(self.lib.gca_step_host_begin(self._h, h["actions"].data_ptr(), 1 if auto_reset else 0, C.byref(out)))
+        self.launches += self.kernels_per_step
+        self._host_pending = getattr(self, "_host_pending", []) + [which]
+
+    def step_host_wait(self):
+        """VecEnv.step_wait: (obs, reward, done, info) of the oldest step begun - views of one of two pinned buffer sets,
+        valid until the step after next is begun."""
+        which = self._host_pending.pop(0)
+        abi.check(self.lib.gca_step_host_wait(self._h))
+        views = self._host_buffers(which)[2]
         return views["obs"], views["reward"], views["done"], views["info"]
 
     def reset_host(self):

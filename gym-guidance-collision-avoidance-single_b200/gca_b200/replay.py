@@ -112,3 +112,63 @@ class HerReplayBuffer(object):
 
     def clear_buffer(self):
         self.current_size = 0
+
+
+def make_input_reward_cfg(config):
+    """gca_input_reward_cfg from a Simulators-style Config class (the attributes compute_input_reward reads,
+    Simulators/SingleAircraftDiscrete9HEREnv.py:52-58, :244-276)."""
+    c = config
+    return abi.GcaInputRewardCfg(float(c.window_width), float(c.window_height), float(c.minimum_separation),
+                                 float(c.NMAC_dist), float(c.goal_radius), float(c.conflict_penalty), float(c.NMAC_penalty),
+                                 float(c.goal_reward), float(c.step_penalty), int(c.n), 1 if c.intruder_size != 0 else 0,
+                                 1 if c.sparse_reward else 0, 0)
+
+
+def compute_input_reward(new_inputs, config):
+    """env.compute_input_reward (Simulators/SingleAircraftDiscrete9HEREnv.py:244-276) for a batch of relabelled
+    (observation + goal) rows on the device: new_inputs CUDA tensor [M, dim], float32 or float64.
+    Returns (reward float64 [M], done uint8 [M]) with done = r == 10 or r == -10 (agent_her.py:117)."""
+    torch = _torch()
+    lib = abi.load()
+    x = new_inputs.contiguous()
+    assert x.dim() == 2 and x.dtype in (torch.float32, torch.float64)
+    m, dim = x.shape
+    r = torch.empty((m,), dtype=torch.float64, device=x.device)
+    d = torch.empty((m,), dtype=torch.uint8, device=x.device)
+    cfg = make_input_reward_cfg(config)
+    abi.check(lib.gca_input_reward(x.data_ptr(), m, dim, 1 if x.dtype == torch.float64 else 0, C.byref(cfg), r.data_ptr(),
+                                   d.data_ptr(), x.device.index or 0,
+                                   C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
+    return r, d
+
+
+def relabel_episode(obs, next_obs, goals, config, k=4, futures=None, generator=None):
+    """The HER part of Agent.add (Algorithms/pytorch/agent_her.py:93-117) for one finished episode, on the device.
+
+    obs, next_obs: CUDA tensors [T, dim_o] (s and s_n of every step), goals: [T, 2] (g).  For every step t and each of
+    the k relabels, a future step f in [t, T) is drawn (np.random.randint(t, T); pass `futures` int64 [T, k] to replay
+    recorded draws), its next observation's first two entries become the desired goal, and the reward of the relabelled
+    transition is compute_input_reward(concat(new_ob, desired)).  Returns the dict of the (1 + k) T transitions the
+    reference pushes into its memory, in its order: inputs, new_inputs [T, 1 + k, dim_o + 2], reward float64
+    [T, 1 + k] (slot 0: NaN - the environment's reward of the original transition is the caller's), done uint8
+    [T, 1 + k] (slot 0: 0 - likewise), futures [T, k]."""
+    torch = _torch()
+    T, dim_o = obs.shape
+    dev = obs.device
+    if futures is None:
+        u = torch.rand((T, k), device=dev, generator=generator, dtype=torch.float64)
+        t0 = torch.arange(T, device=dev, dtype=torch.float64)[:, None]
+        futures = torch.minimum((t0 + torch.floor(u * (T - t0))).to(torch.int64), torch.full((1, 1), T - 1, device=dev))
+    futures = futures.to(torch.int64)
+    desired = next_obs[futures][..., :2]                                    # g_n[:2] of the future transition
+    all_goals = torch.cat([goals[:, None, :].to(obs.dtype), desired], 1)    # slot 0: the episode's own goal
+    ob_rep = obs[:, None, :].expand(T, 1 + k, dim_o)
+    nob_rep = next_obs[:, None, :].expand(T, 1 + k, dim_o)
+    inputs = torch.cat([ob_rep, all_goals], -1).contiguous()
+    new_inputs = torch.cat([nob_rep, all_goals], -1).contiguous()
+    r, d = compute_input_reward(new_inputs[:, 1:, :].reshape(T * k, dim_o + 2), config)
+    reward = torch.full((T, 1 + k), float("nan"), dtype=torch.float64, device=dev)
+    done = torch.zeros((T, 1 + k), dtype=torch.uint8, device=dev)
+    reward[:, 1:] = r.view(T, k)
+    done[:, 1:] = d.view(T, k)
+    return {"inputs": inputs, "new_inputs": new_inputs, "reward": reward, "done": done, "futures": futures}

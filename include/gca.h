@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GCA_ABI_VERSION 6
+#define GCA_ABI_VERSION 7
 
 typedef enum gca_status {
   GCA_OK = 0,
@@ -231,6 +231,16 @@ int gca_profile_read(gca_env* env, gca_step_profile* out);
  * same shapes; pinned memory recommended) and synchronises.  PHILOX draws only. */
 int gca_step_host(gca_env* env, const void* actions_host, int auto_reset, const gca_out* host_out);
 int gca_reset_host(gca_env* env, const gca_out* host_out);
+/* The asynchronous form (VecEnv.step_async / step_wait of baselines common/vec_env/__init__.py:76-100): _begin enqueues
+ * the upload of the actions, the step and the download of its outputs into `host_out` and returns; _wait blocks until
+ * the outputs of the OLDEST step begun and not yet waited for are in host memory.  Two steps may be in flight: the
+ * device-side outputs are double-buffered and the download runs on a stream of its own, so the download of step t
+ * overlaps the kernels of step t + 1 (give the two steps different host buffers; `actions_host` must stay valid until
+ * the matching _wait).  gca_step_host = _begin + _wait.  A handle driven through the host path must not also be
+ * driven through gca_step / gca_reset on another stream without a device synchronisation in between: the host path
+ * orders its work on its own streams. */
+int gca_step_host_begin(gca_env* env, const void* actions_host, int auto_reset, const gca_out* host_out);
+int gca_step_host_wait(gca_env* env);
 
 /* _get_ob() of the current state without stepping (PKG/SingleAircraftEnv.py:100-126). */
 int gca_observe(gca_env* env, const gca_out* out, void* stream);
@@ -251,6 +261,23 @@ int gca_set_state(gca_env* env, const gca_host_state* src);
  * ag, g: device [m][2], f64 when is_f64 else f32; out: device float[m]. */
 int gca_compute_reward(const void* ag, const void* g, int64_t m, double radius, int kind,
                        int is_f64, float* out, int device, void* stream);
+
+/* compute_input_reward(new_inputs) of Simulators/SingleAircraftDiscrete9HEREnv.py:244-276, the reward the repo's own
+ * HER learner gives a relabelled transition (Algorithms/pytorch/agent_her.py:107-117), for m rows at once.
+ * rows: device [m][dim] (observation + desired goal: own x, y at 0-1, the listed intruders from entry 4 on, read with
+ * the reference's stride of 4, the goal in the last two entries), f64 when is_f64 else f32.  out: device double[m]
+ * (the reference returns Python floats); done (nullable): device uint8[m], r == 10 or r == -10 (agent_her.py:117). */
+typedef struct gca_input_reward_cfg {
+  double window_width, window_height;     /* Config.window_width / window_height (the un-normalisation) */
+  double minimum_separation, nmac_dist, goal_radius;
+  double conflict_penalty, nmac_penalty, goal_reward, step_penalty;
+  int32_t n_listed;                       /* Config.n */
+  int32_t has_intruders;                  /* Config.intruder_size != 0 */
+  int32_t sparse_reward;                  /* Config.sparse_reward */
+  int32_t reserved;
+} gca_input_reward_cfg;
+int gca_input_reward(const void* rows, int64_t m, int dim, int is_f64, const gca_input_reward_cfg* cfg, double* out,
+                     uint8_t* done, int device, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * MCTS forward model (Algorithms/MCTS/nodes_single.py) - batched device-side playouts.

@@ -475,3 +475,41 @@ def test_forecast_step_bit_exact_vs_oracle_in_subprocess():
                          env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
     assert " passed" in out.stdout
+
+
+def test_host_path_async_equals_device_path():
+    """gca_step_host_begin / _wait (two steps in flight, double-buffered downloads) return, step for step, what the
+    device-resident path returns for the same seed and actions; mixing in the synchronous gca_step_host keeps the order."""
+    import torch
+    B, n, T = 777, 20, 24
+    a = make_gpu("env2", n, B, "fast", "philox", seed=31)
+    b = make_gpu("env2", n, B, "fast", "philox", seed=31)
+    assert np.array_equal(a.reset().cpu().numpy(), b.reset_host())
+    rng = np.random.RandomState(2)
+    acts = [rng.uniform(-1, 1, (B, 2)).astype(np.float32) for _ in range(T)]
+    want = []
+    for t in range(T):
+        o, r, d, i = a.step(torch.as_tensor(acts[t], device="cuda"))
+        want.append((o.cpu().numpy().copy(), r.cpu().numpy().copy(), d.cpu().numpy().copy(), i.cpu().numpy().copy()))
+
+    def same(got, t):
+        for x, y in zip(got, want[t]):
+            assert np.array_equal(np.asarray(x), y), t
+    b.step_host_begin(acts[0])
+    for t in range(1, 10):                       # pipelined: step t is begun before step t - 1 is waited for
+        b.step_host_begin(acts[t])
+        same(b.step_host_wait(), t - 1)
+    same(b.step_host_wait(), 9)
+    for t in range(10, 14):                      # synchronous calls in between
+        same(b.step_host(acts[t]), t)
+    b.step_host_begin(acts[14])
+    b.step_host_begin(acts[15])
+    with pytest.raises(Exception):
+        b.step_host_begin(acts[16])              # a third step in flight is refused
+    same(b.step_host_wait(), 14)
+    same(b.step_host_wait(), 15)
+    for t in range(16, T):
+        b.step_host_begin(acts[t])
+        same(b.step_host_wait(), t)
+    a.close()
+    b.close()
