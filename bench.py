@@ -582,19 +582,26 @@ def bench_mcts(device, with_cpu):
         from concurrent.futures import ThreadPoolExecutor
         from oracle import oracle as orc
         cores = os.cpu_count() or 1
-        per = 4
-        host_roots = roots[: per * cores].cpu().numpy() if roots.shape[0] >= per * cores else roots.cpu().numpy().repeat(
-            (per * cores + R - 1) // R, 0)[: per * cores]
-        shards = [host_roots[c * per:(c + 1) * per] for c in range(cores)]
+        all_roots = roots.cpu().numpy()
         pool = ThreadPoolExecutor(cores)
-        t0 = time.perf_counter()
-        list(pool.map(lambda sh: orc.mcts_search_philox(cfg, 80, sh, P, depth, seed=2), shards))
-        dt = time.perf_counter() - t0
+
+        def timed(fn, per, budget_s=4.0):
+            """grow the sample (roots per thread) until one pass takes about budget_s seconds of wall clock"""
+            while True:
+                n = per * cores
+                host_roots = all_roots[:n] if all_roots.shape[0] >= n else all_roots.repeat((n + R - 1) // R, 0)[:n]
+                shards = [host_roots[c * per:(c + 1) * per] for c in range(cores)]
+                t0 = time.perf_counter()
+                list(pool.map(fn, shards))
+                dt = time.perf_counter() - t0
+                if dt >= budget_s / 2 or per >= (1 << 16):
+                    return per, dt
+                per = int(min(1 << 16, max(per * 2, per * budget_s / max(dt, 1e-3))))
+
+        per, dt = timed(lambda sh: orc.mcts_search_philox(cfg, 80, sh, P, depth, seed=2), 4)
         out["search"]["cpu_baseline"] = {"value": per * cores / dt, "unit": "searches/s", "cores": cores, "kind": "port",
                                          "sample": "%d roots x %d simulations (%.1f s), C oracle port, %d threads" % (per * cores, P, dt, cores)}
-        t0 = time.perf_counter()
-        list(pool.map(lambda sh: orc.mcts_playouts(cfg, 80, sh, 50, depth, seed=6), shards))
-        dt = time.perf_counter() - t0
+        per, dt = timed(lambda sh: orc.mcts_playouts(cfg, 80, sh, 50, depth, seed=6), 16)
         pool.shutdown()
         out["cpu_baseline"] = {"value": per * cores * 50 / dt, "unit": "rollouts/s", "cores": cores, "kind": "port",
                                "sample": "%d roots x 50 playouts (%.1f s), C oracle port (oracle/gca_oracle_mcts.c), %d threads"
