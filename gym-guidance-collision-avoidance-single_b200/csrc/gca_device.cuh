@@ -561,38 +561,56 @@ __device__ __forceinline__ void write_obs_own(const StepArgs& a, size_t env, flo
   const bool of = own_first(c);
   R* row = reinterpret_cast<R*>(a.obs) + env * (size_t)a.D;
   R* o = row + (of ? 0 : (c.obs_kind == GCA_OBS_RAW6 ? 6 : 4) * (size_t)a.s.N);
+  // the eight entries of a goal-last row start on a 16-byte boundary (4 N or 6 N entries precede them in rows of
+  // 4 N + 8 / 6 N + 8): they leave as 16-byte stores (two in f32, four in f64) instead of eight scalar ones
+  auto store8 = [&](R v0, R v1, R v2, R v3, R v4, R v5, R v6, R v7) {
+    if (reinterpret_cast<uintptr_t>(o) & 15u) {             // (6 N + 8 entries per row with N odd: every other row)
+      o[0] = v0; o[1] = v1; o[2] = v2; o[3] = v3; o[4] = v4; o[5] = v5; o[6] = v6; o[7] = v7;
+      return;
+    }
+    if constexpr (FAITH) {
+      double2* q = reinterpret_cast<double2*>(o);
+      q[0] = make_double2(v0, v1); q[1] = make_double2(v2, v3); q[2] = make_double2(v4, v5); q[3] = make_double2(v6, v7);
+    } else {
+      float4* q = reinterpret_cast<float4*>(o);
+      q[0] = make_float4(v0, v1, v2, v3); q[1] = make_float4(v4, v5, v6, v7);
+    }
+  };
   if (c.obs_kind == GCA_OBS_RAW || c.obs_kind == GCA_OBS_RAW6) {
-    o[0] = (R)px; o[1] = (R)py; o[2] = (R)vx; o[3] = (R)vy; o[4] = (R)speed; o[5] = (R)heading;
-    o[6] = (R)gx; o[7] = (R)gy;
+    store8((R)px, (R)py, (R)vx, (R)vy, (R)speed, (R)heading, (R)gx, (R)gy);
     return;
   }
   const Derived& k = a.k;
   const float nx = div_prepared(k, px, k.ob_w, k.inv_ob_w), ny = div_prepared(k, py, k.ob_h, k.inv_ob_h);
+  R e2, e3;
+  if (vel_is_f32) {
+    e2 = (R)norm_vel_f32(k, (float)vx);
+    e3 = (R)norm_vel_f32(k, (float)vy);
+  } else {
+    e2 = (R)norm_vel_f64(c, k, vx);
+    e3 = (R)norm_vel_f64(c, k, vy);
+  }
+  const R e4 = (R)ddiv_prepared(k, __dadd_rn(speed, -c.ob_min_speed), k.dv_speed, k.rc_speed);
+  const R e5 = (R)ddiv_prepared(k, heading, k.dv_2pi, k.rc_2pi);
+  if (!of) {
+    store8((R)nx, (R)ny, e2, e3, e4, e5, (R)ddiv_prepared(k, gx, k.dv_w, k.rc_w), (R)ddiv_prepared(k, gy, k.dv_h, k.rc_h));
+    return;
+  }
   o[0] = (R)nx;
   o[1] = (R)ny;
-  if (vel_is_f32) {
-    o[2] = (R)norm_vel_f32(k, (float)vx);
-    o[3] = (R)norm_vel_f32(k, (float)vy);
+  o[2] = e2;
+  o[3] = e3;
+  o[4] = e4;
+  o[5] = e5;
+  R* ag = reinterpret_cast<R*>(a.achieved) + 2 * env;
+  R* dg = reinterpret_cast<R*>(a.desired) + 2 * env;
+  if (c.obs_kind == GCA_OBS_HER) {
+    ag[0] = (R)nx; ag[1] = (R)ny;
+    dg[0] = (R)ddiv_prepared(k, gx, k.dv_w, k.rc_w);
+    dg[1] = (R)ddiv_prepared(k, gy, k.dv_h, k.rc_h);
   } else {
-    o[2] = (R)norm_vel_f64(c, k, vx);
-    o[3] = (R)norm_vel_f64(c, k, vy);
-  }
-  o[4] = (R)ddiv_prepared(k, __dadd_rn(speed, -c.ob_min_speed), k.dv_speed, k.rc_speed);
-  o[5] = (R)ddiv_prepared(k, heading, k.dv_2pi, k.rc_2pi);
-  if (!of) {
-    o[6] = (R)ddiv_prepared(k, gx, k.dv_w, k.rc_w);
-    o[7] = (R)ddiv_prepared(k, gy, k.dv_h, k.rc_h);
-  } else {
-    R* ag = reinterpret_cast<R*>(a.achieved) + 2 * env;
-    R* dg = reinterpret_cast<R*>(a.desired) + 2 * env;
-    if (c.obs_kind == GCA_OBS_HER) {
-      ag[0] = (R)nx; ag[1] = (R)ny;
-      dg[0] = (R)ddiv_prepared(k, gx, k.dv_w, k.rc_w);
-      dg[1] = (R)ddiv_prepared(k, gy, k.dv_h, k.rc_h);
-    } else {
-      ag[0] = (R)px; ag[1] = (R)py;
-      dg[0] = (R)gx; dg[1] = (R)gy;
-    }
+    ag[0] = (R)px; ag[1] = (R)py;
+    dg[0] = (R)gx; dg[1] = (R)gy;
   }
 }
 

@@ -74,6 +74,12 @@ extern "C" int gca_debug_kstamps(unsigned long long* host, int reset) {
 #ifndef GCA_WARPS_B
 #define GCA_WARPS_B 4
 #endif
+#ifndef GCA_N0_MINB
+#define GCA_N0_MINB 1                             // blocks per SM the no-intruder kernel is compiled for
+#endif
+#ifndef GCA_FAITH_MINB
+#define GCA_FAITH_MINB 1                          // blocks per SM the FAITHFUL streaming kernel is compiled for
+#endif
 constexpr int kChunkUnits = GCA_CHUNK_UNITS;      // 16-byte units (intruder pairs) per lane and work item
 constexpr int kChunkIntr = 2 * kChunkUnits;       // 8 intruders
 constexpr int kTileRespawnCap = 128;              // respawn records per tile (32 envs) and step; beyond that the lane spawns in place
@@ -720,7 +726,7 @@ __global__ void __launch_bounds__(128) step_finish_kernel(const __grid_constant_
 // No intruders (the package default, PKG/config.py:8 `intruder_size = 0`), PHILOX: nothing runs between the ownship
 // update and the finish, so the whole step is ONE kernel, thread = env (warp = tile, as in the finish).
 template <bool FAITH>
-__global__ void __launch_bounds__(128) step_n0_kernel(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(128, GCA_N0_MINB) step_n0_kernel(const __grid_constant__ StepArgs a) {
   __shared__ WarpScratch ws[4];
   __shared__ BlockScratch bs;
   if (threadIdx.x == 0) bs.count = 0;
@@ -753,7 +759,7 @@ namespace gca {
 // (the same f32 sum the next step will make) and (iii) keeps the smallest squared distance of the new state, from
 // which the next head decides which envs can possibly see a conflict.  Nothing runs after it.
 template <bool FAITH, int OM, bool DRIFT = false, bool FC = false>
-__global__ void __launch_bounds__(kWarpsB * 32, (FC && !FAITH) ? 8 : 1) step_intruders_kernel(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(kWarpsB * 32, FAITH ? GCA_FAITH_MINB : (FC ? 8 : 1)) step_intruders_kernel(const __grid_constant__ StepArgs a) {
   static_assert(!(DRIFT && OM), "a handle with a position drift takes the generic observation path");
   if constexpr (!FC) {
     if (PDL_EARLY) pdl_launch_dependents();
