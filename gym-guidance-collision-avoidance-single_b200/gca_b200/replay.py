@@ -172,3 +172,67 @@ def relabel_episode(obs, next_obs, goals, config, k=4, futures=None, generator=N
     reward[:, 1:] = r.view(T, k)
     done[:, 1:] = d.view(T, k)
     return {"inputs": inputs, "new_inputs": new_inputs, "reward": reward, "done": done, "futures": futures}
+
+
+class AgentHerMemory(object):
+    """The replay memory of the repo's own DQN-HER learner (Algorithms/pytorch/agent_her.py: `ReplayBuffer` :119-149, a
+    deque(maxlen=buffer_size) of (state, action, reward, next_state, done), filled by `Agent.add` :93-117) as a ring of
+    CUDA tensors.  `add_episode` is Agent.add for one finished episode - the transitions as they happened plus, with HER,
+    k relabelled copies of each (future draws, desired goal, compute_input_reward: relabel_episode above), appended
+    in the reference's order; `sample` returns what ReplayBuffer.sample returns (float states [batch, dim], long actions
+    [batch, 1], float rewards / next_states / dones), drawn without replacement like random.sample."""
+
+    def __init__(self, dim_inputs, buffer_size, batch_size, config, device=0, dtype=None, her=True, k=4, seed=0):
+        torch = _torch()
+        dev = torch.device("cuda", device)
+        dt = dtype or torch.float32
+        self.capacity, self.batch_size, self.config, self.her, self.k = int(buffer_size), int(batch_size), config, her, int(k)
+        self.states = torch.zeros((self.capacity, dim_inputs), dtype=dt, device=dev)
+        self.next_states = torch.zeros((self.capacity, dim_inputs), dtype=dt, device=dev)
+        self.actions = torch.zeros((self.capacity, 1), dtype=torch.int64, device=dev)
+        self.rewards = torch.zeros((self.capacity, 1), dtype=torch.float32, device=dev)
+        self.dones = torch.zeros((self.capacity, 1), dtype=torch.float32, device=dev)
+        self.size = 0
+        self._next = 0
+        self._gen = torch.Generator(device=dev)
+        self._gen.manual_seed(int(seed))
+
+    def __len__(self):
+        return self.size
+
+    def _append(self, states, actions, rewards, next_states, dones):
+        torch = _torch()
+        n = states.shape[0]
+        idx = (self._next + torch.arange(n, device=states.device)) % self.capacity      # deque(maxlen): oldest out first
+        self.states[idx] = states.to(self.states.dtype)
+        self.next_states[idx] = next_states.to(self.states.dtype)
+        self.actions[idx] = actions.reshape(n, 1).to(torch.int64)
+        self.rewards[idx] = rewards.reshape(n, 1).to(torch.float32)
+        self.dones[idx] = dones.reshape(n, 1).to(torch.float32)
+        self._next = (self._next + n) % self.capacity
+        self.size = min(self.capacity, self.size + n)
+
+    def add_episode(self, obs, actions, rewards, next_obs, goals, dones, futures=None):
+        """Agent.add(episode_experience, env): obs / next_obs [T, dim_o], actions [T], rewards [T], goals [T, 2],
+        dones [T] as CUDA tensors (the episode's (s, a, r, s_n, g, done) tuples stacked)."""
+        torch = _torch()
+        T = obs.shape[0]
+        if not self.her:
+            self._append(torch.cat([obs, goals.to(obs.dtype)], -1), actions, rewards, torch.cat([next_obs, goals.to(obs.dtype)], -1), dones)
+            return None
+        tr = relabel_episode(obs, next_obs, goals, self.config, k=self.k, futures=futures, generator=self._gen)
+        reward = tr["reward"].clone()
+        done = tr["done"].to(torch.float32)
+        reward[:, 0] = rewards.to(torch.float64)                     # slot 0: the transition as it happened
+        done[:, 0] = dones.to(torch.float32)
+        a = actions.reshape(T, 1).expand(T, 1 + self.k)
+        d = tr["inputs"].shape[-1]
+        self._append(tr["inputs"].reshape(-1, d), a.reshape(-1), reward.reshape(-1), tr["new_inputs"].reshape(-1, d),
+                     done.reshape(-1))
+        return tr
+
+    def sample(self):
+        torch = _torch()
+        assert self.size >= self.batch_size
+        idx = torch.randperm(self.size, device=self.states.device, generator=self._gen)[: self.batch_size]
+        return (self.states[idx].float(), self.actions[idx], self.rewards[idx], self.next_states[idx].float(), self.dones[idx])

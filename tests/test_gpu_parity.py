@@ -470,7 +470,8 @@ def test_forecast_step_bit_exact_vs_oracle_in_subprocess():
     import sys
     env = dict(os.environ, GCA_FORECAST="1")
     here = os.path.abspath(__file__)
-    sel = "test_philox_rollout_bit_exact_vs_oracle or test_full_size_bit_exact_vs_oracle or test_state_roundtrip"
+    sel = ("test_philox_rollout_bit_exact_vs_oracle or test_full_size_bit_exact_vs_oracle or test_state_roundtrip or "
+           "test_long_rollout_with_explicit_masked_resets_vs_oracle or test_random_configurations_bit_exact_vs_oracle")
     out = subprocess.run([sys.executable, "-m", "pytest", here, "-x", "-q", "-m", "gpu", "-k", sel, "-p", "no:cacheprovider"],
                          env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]

@@ -96,3 +96,43 @@ def test_relabel_episode_equals_agent_her_add():
                                   torch.as_tensor(goal, device="cuda"), c, k=k)
     f2 = out2["futures"].cpu().numpy()
     assert (f2 >= np.arange(T)[:, None]).all() and (f2 < T).all()
+
+
+def test_agent_her_memory_holds_what_agent_add_pushes():
+    """AgentHerMemory.add_episode = Agent.add (agent_her.py:93-117): (1 + k) T entries in the reference's order
+    (the transition as it happened, then its k relabels), ring semantics of deque(maxlen), sample() shapes / dtypes."""
+    import torch
+    from gca_b200 import replay
+    c = _config()
+    rng = np.random.RandomState(8)
+    T, dim_o, k = 11, 24, 4
+    s = rng.uniform(0.05, 0.95, (T, dim_o)).astype(np.float32)
+    s_n = np.roll(s, -1, axis=0)
+    goal = np.repeat(rng.uniform(0.1, 0.9, (1, 2)).astype(np.float32), T, 0)
+    a = rng.randint(0, 9, T)
+    r = rng.uniform(-1, 0, T)
+    dn = np.zeros(T); dn[-1] = 1
+    futures = np.stack([rng.randint(t, T, k) for t in range(T)])
+    mem = replay.AgentHerMemory(dim_o + 2, buffer_size=3 * T * (1 + k) - 7, batch_size=32, config=c, k=k, seed=1)
+    dev = lambda x: torch.as_tensor(x, device="cuda")
+    for rep in range(3):                                             # the third episode wraps the ring
+        mem.add_episode(dev(s), dev(a), dev(r), dev(s_n), dev(goal), dev(dn), futures=dev(futures))
+    assert len(mem) == mem.capacity
+    # the last episode's entries are the newest ones of the ring, in Agent.add's order
+    n = T * (1 + k)
+    idx = (mem._next - n + np.arange(n)) % mem.capacity
+    st, ns = mem.states.cpu().numpy()[idx], mem.next_states.cpu().numpy()[idx]
+    rw, dd, ac = mem.rewards.cpu().numpy()[idx, 0], mem.dones.cpu().numpy()[idx, 0], mem.actions.cpu().numpy()[idx, 0]
+    j = 0
+    for t in range(T):
+        assert np.array_equal(st[j], np.concatenate([s[t], goal[t]])) and np.array_equal(ns[j], np.concatenate([s_n[t], goal[t]]))
+        assert rw[j] == np.float32(r[t]) and dd[j] == dn[t] and ac[j] == a[t]
+        j += 1
+        for q in range(k):
+            desired = s_n[futures[t, q]][:2]
+            assert np.array_equal(st[j], np.concatenate([s[t], desired]))
+            assert rw[j] == np.float32(_input_reward_numpy(np.concatenate([s_n[t], desired]), c)) and ac[j] == a[t]
+            j += 1
+    states, actions, rewards, next_states, dones = mem.sample()
+    assert states.shape == (32, dim_o + 2) and states.dtype == torch.float32 and actions.dtype == torch.int64
+    assert actions.shape == rewards.shape == dones.shape == (32, 1) and next_states.shape == states.shape
