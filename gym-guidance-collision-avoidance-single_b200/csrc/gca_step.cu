@@ -74,9 +74,6 @@ extern "C" int gca_debug_kstamps(unsigned long long* host, int reset) {
 #ifndef GCA_WARPS_B
 #define GCA_WARPS_B 4
 #endif
-#ifndef GCA_N0_MINB
-#define GCA_N0_MINB 1                             // blocks per SM the no-intruder kernel is compiled for
-#endif
 #ifndef GCA_FAITH_MINB
 #define GCA_FAITH_MINB 1                          // blocks per SM the FAITHFUL streaming kernel is compiled for
 #endif
@@ -725,8 +722,12 @@ __global__ void __launch_bounds__(128) step_finish_kernel(const __grid_constant_
 
 // No intruders (the package default, PKG/config.py:8 `intruder_size = 0`), PHILOX: nothing runs between the ownship
 // update and the finish, so the whole step is ONE kernel, thread = env (warp = tile, as in the finish).
-template <bool FAITH>
-__global__ void __launch_bounds__(128, GCA_N0_MINB) step_n0_kernel(const __grid_constant__ StepArgs a) {
+// Two builds: MINB = 1 (94 registers, 5 blocks per SM: the shortest chain - batches that fit the GPU in a wave or two
+// are bound by that latency: 5.3 us per step at 65,536 envs) and MINB = 8 (64 registers with a few spills, 8 blocks per
+// SM: once the batch is many waves deep the kernel is bound by memory latency at low occupancy, and 32 instead of 20
+// warps per SM take the 4 Mi-env step from 230 to 166 us = 61 % of the measured HBM peak on its 155 B per env-step).
+template <bool FAITH, int MINB>
+__global__ void __launch_bounds__(128, MINB) step_n0_kernel(const __grid_constant__ StepArgs a) {
   __shared__ WarpScratch ws[4];
   __shared__ BlockScratch bs;
   if (threadIdx.x == 0) bs.count = 0;
@@ -1420,7 +1421,10 @@ static cudaError_t launch_step_t(const StepArgs& a0, cudaStream_t st, cudaEvent_
   if constexpr (TAPE) launch_pdl(step_own_kernel<FAITH, TAPE>, env_blocks, 128, st, a);
   mark(1);
   if (!TAPE && s.N == 0) {
-    if constexpr (!TAPE) launch_pdl(step_n0_kernel<FAITH>, env_blocks, 128, st, a);
+    if constexpr (!TAPE) {
+      if (s.B > (1 << 18)) launch_pdl(step_n0_kernel<FAITH, 8>, env_blocks, 128, st, a);
+      else launch_pdl(step_n0_kernel<FAITH, 1>, env_blocks, 128, st, a);
+    }
     mark(2);
     mark(3);
     mark(4);
