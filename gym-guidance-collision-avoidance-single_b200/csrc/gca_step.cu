@@ -1,10 +1,13 @@
 // gca_step.cu - step / reset / observe of the batched simulator (sm_100a).
 //
-// One step = three launches on the caller's stream, each shaped for what bounds it:
+// One step of a PHILOX handle = two launches on the caller's stream (tape replays: three, the ownship role as a kernel
+// of its own; no intruders: one, step_n0_kernel), each part shaped for what bounds it:
 //
-//   step_own_kernel        thread = env.  Ownship kinematics (PKG/SingleAircraftEnv.py:299-309): all
-//                          of it f64 (Philox + Box-Muller, sincos, clamp), ~80 bytes per env.
-//                          FP64-pipe bound, a few microseconds.
+//   ownship role           thread = env; the leading blocks of step_intruders_kernel's grid (tape handles:
+//                          step_own_kernel).  Ownship kinematics (PKG/SingleAircraftEnv.py:299-309): all of it f64
+//                          (Philox + Box-Muller, sincos, clamp).  Publishes the 16-byte record the streaming role
+//                          waits for, then settles what the ownship alone decides (reward candidate, observation
+//                          tail) while the stream is already running.  FP64 latency bound.
 //   step_intruders_kernel  warp = 8 intruders x 32 envs, lane = env.  THE streaming pass: advance, map
 //                          test, separation test on the squared distance, observation entries.  It
 //                          reads one position plane and writes the other (gca_device.cuh), so it is
@@ -22,11 +25,12 @@
 //   step_finish_kernel     warp = 32 envs, lane = env.  Replays the reference's sequential loop
 //                          semantics from the recorded masks (PKG/SingleAircraftEnv.py:149-170): first
 //                          NMAC index wins and everything after it is put back where it was (Q9),
-//                          respawns happen in index order with the reference's draw order, a replaced
-//                          intruder is tested with its old distance and starts with conflict False (Q7),
-//                          the flag never clears otherwise (Q8); then wall / goal / reward / done, the
-//                          ownship + goal tail of the observation, counters, and the VecEnv auto-reset
-//                          (warp-cooperative, lanes = intruders).
+//                          a replaced intruder is tested with its old distance and starts with conflict False (Q7),
+//                          the flag never clears otherwise (Q8); then the step's return (an intruder event outranks
+//                          what the ownship role settled), counters, the scalar part of the VecEnv auto-reset; and
+//                          in the same launch the spawn phase: one lane per respawn, one warp per 32 spawns of a
+//                          reset (tape handles respawn in place, in the reference's draw order).
+// The opt-in forecast step (GCA_FORECAST=1) lives in gca_step_fc.cuh.
 // Every byte of intruder state is read once and written once per step; nothing is staged in HBM except
 // 16 bytes per env (ownship position for the streaming pass) and the event words.
 #include <climits>
