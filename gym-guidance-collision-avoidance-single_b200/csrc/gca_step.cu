@@ -268,6 +268,8 @@ struct WarpScratch {
 };
 struct BlockScratch {               // per block: the envs that finished under auto-reset (their N spawns, one warp per 32)
   int env[128];
+  int tick[128];                    // the tick of the step that finished the env
+  float2 pos[128];                  // the ownship its new intruders keep their distance from (reset position)
   int count;
 };
 
@@ -582,6 +584,7 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
 #endif
   // ---- VecEnv auto-reset: the observation handed back for a finished env is reset()'s (dummy_vec_env.py:52-55)
   const bool resets = a.auto_reset && has_env && done;
+  int reset_slot = -1;
   if constexpr (TAPE) {
     uint32_t dmask = __ballot_sync(FULL, resets);
     while (dmask) {                                                 // the tape is sequential: one env at a time
@@ -605,7 +608,8 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
       if (lane == 0) base = atomicAdd(&bs->count, __popc(rmask));
       base = __shfl_sync(FULL, base, 0);
       if (resets) {
-        bs->env[base + __popc(rmask & ((1u << lane) - 1u))] = (int)me;
+        reset_slot = base + __popc(rmask & ((1u << lane) - 1u));
+        bs->env[reset_slot] = (int)me;
         draw_goal(d, c, goal.x, goal.y);   // Goal(random_pos()) :93
       }
 #ifdef GCA_PHASE_TIMING
@@ -614,7 +618,13 @@ __device__ __forceinline__ void finish_tile(const StepArgs& a, const int tile, c
     }
   }
   if (resets) {
-    if constexpr (!TAPE) reset_ownship<TAPE>(c, d, pos, hs, vel);     // (spawn_kernel reads the new position)
+    if constexpr (!TAPE) {
+      reset_ownship<TAPE>(c, d, pos, hs, vel);
+      if (reset_slot >= 0) {                                          // (the spawn phase reads them from shared memory)
+        bs->pos[reset_slot] = pos;
+        bs->tick[reset_slot] = cnt.z;
+      }
+    }
     s.own_pos[me] = pos;
     s.own_hs[me] = hs;
     s.own_vel[me] = vel;
@@ -680,15 +690,15 @@ __device__ __forceinline__ void spawn_phase(const StepArgs& a, const int tile, c
   for (int job = wib; job < total; job += 4) {
     const size_t env = (size_t)bs->env[job / rounds];
     const int r = job % rounds, i = r * 32 + lane;
-    const int4 cnt = s.counters[env];                       // (tick already incremented by finish_tile)
+    const int tick = bs->tick[job / rounds];                // the tick of the step that finished the env
     d.env = a.env_id0 + (uint32_t)env;
-    d.tick = (uint32_t)cnt.z - 1u;                          // the tick of the step that finished the env
+    d.tick = (uint32_t)tick;
     bool wide = false;
     if (i < s.N) {
       Intr<FAITH> it;
-      const float2 own = s.own_pos[env];                    // (50, 50) :72-76, or the random start finish_tile drew
+      const float2 own = bs->pos[job / rounds];             // (50, 50) :72-76, or the random start finish_tile drew
       spawn<FAITH, false>(d, a.cfg, a.k, GCA_SLOT_RESET | (uint32_t)i, own.x, own.y, it, ihs_slot(s, env, i));
-      store_ipos<FAITH>(s, cnt.z & 1, env, i, it);
+      store_ipos<FAITH>(s, (tick & 1) ^ 1, env, i, it);      // the plane this step wrote = the env's next current plane
       store_ivel(s, env, i, it.vx, it.vy);
       write_obs_intruder<FAITH>(a, obs_intruder_base<FAITH>(a, env), i, it);
       wide = it.is64;
