@@ -212,6 +212,7 @@ class BatchedAircraftEnv(object):
         views["actions"][...] = np.asarray(actions).reshape(views["actions"].shape)
         abi.check(self.lib.gca_step_host(self._h, h["actions"].data_ptr(), 1 if auto_reset else 0, C.byref(out)))
         self.launches += self.kernels_per_step
+        self.last_host_views = views
         return views["obs"], views["reward"], views["done"], views["info"]
 
     def step_host_begin(self, actions, auto_reset=True):
@@ -229,13 +230,14 @@ class BatchedAircraftEnv(object):
         valid until the step after next is begun."""
         which = self._host_pending.pop(0)
         abi.check(self.lib.gca_step_host_wait(self._h))
-        views = self._host_buffers(which)[2]
+        views = self.last_host_views = self._host_buffers(which)[2]
         return views["obs"], views["reward"], views["done"], views["info"]
 
     def reset_host(self):
         h, out, views = self._host_buffers()
         abi.check(self.lib.gca_reset_host(self._h, C.byref(out)))
         self.launches += 1
+        self.last_host_views = views
         return views["obs"]
 
     # ------------------------------------------------------------------ full state

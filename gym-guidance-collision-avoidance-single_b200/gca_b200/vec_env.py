@@ -102,7 +102,7 @@ class AircraftVecEnv(object):
         if not b.is_goal_env:
             return obs
         if self.host:
-            _, _, views = b._host_buffers()
+            views = b.last_host_views                    # the pinned buffer set the last host call filled
             return {"observation": views["obs"], "achieved_goal": views["achieved"], "desired_goal": views["desired"]}
         return {"observation": b.obs, "achieved_goal": b.achieved, "desired_goal": b.desired}
 
@@ -121,7 +121,9 @@ class AircraftVecEnv(object):
             _, rew, done, info = self._image.step(actions, auto_reset=True)
             self._pending = ("img", (rew, done, info))
         elif self.host:
-            self._pending = ("host", np.asarray(actions))
+            # gca_step_host_begin: upload, step and download are enqueued; step_wait blocks on the download
+            self.batch.step_host_begin(np.asarray(actions), auto_reset=True)
+            self._pending = ("host", None)
         else:
             # the launch is asynchronous on the current CUDA stream: this IS the async half
             self._pending = ("dev", self.batch.step(actions, auto_reset=True))
@@ -135,7 +137,7 @@ class AircraftVecEnv(object):
             rew, done, info = payload
             return self._image_obs(), rew, done, info
         if kind == "host":
-            obs, rew, done, info = self.batch.step_host(payload, auto_reset=True)
+            obs, rew, done, info = self.batch.step_host_wait()
             return self._pack_obs(obs), rew, done.astype(bool), info
         obs, rew, done, info = payload
         return self._pack_obs(obs), rew, done, info
