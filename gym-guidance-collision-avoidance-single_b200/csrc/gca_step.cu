@@ -989,9 +989,17 @@ __global__ void __launch_bounds__(kWarpsB * 32, FAITH ? GCA_FAITH_MINB : (FC ? 8
           if (keep && env_sub + kEnvsPerStore * it < (size_t)s.B) {
             if constexpr (OM == 1) {
               stg_stream(dst + it * dstep, val, pol);
-            } else {                                        // own-first rows: entries are only 8-byte aligned
-              stg_stream2(dst + it * dstep, val.x, val.y, pol);
-              stg_stream2(dst + it * dstep + 2, val.z, val.w, pol);
+            } else {
+              // own-first rows (4 N + 6 entries, the intruders from entry 6 on): an entry is 16-byte aligned in every
+              // other row only, and the 128-byte pieces of neighbouring work items share 32-byte sectors.  Plain stores
+              // (no evict_first hint) let the L2 merge those shared sectors before they go to DRAM: 55.9 -> 52.1 us per
+              // step at 65,536 x 80 together with the 16-byte store where the row allows it.
+              if ((reinterpret_cast<uintptr_t>(dst + it * dstep) & 15u) == 0) {
+                *reinterpret_cast<float4*>(dst + it * dstep) = val;
+              } else {
+                *reinterpret_cast<float2*>(dst + it * dstep) = make_float2(val.x, val.y);
+                *reinterpret_cast<float2*>(dst + it * dstep + 2) = make_float2(val.z, val.w);
+              }
             }
           }
         }
