@@ -646,8 +646,7 @@ def bench_her(device):
 
     def one(i):
         env.step(acts[i % 8])
-        ag = env.achieved.unsqueeze(0).expand(k, B, 2).reshape(k * B, 2)
-        return compute_reward(ag, goals.reshape(k * B, 2), Config.goal_radius, abi.OBS_HER)
+        return compute_reward(env.achieved, goals, Config.goal_radius, abi.OBS_HER)     # [B, 2] against [k, B, 2]
     for i in range(5):
         one(i)
     torch.cuda.synchronize()

@@ -670,7 +670,16 @@ int gca_compute_reward(const void* ag, const void* g, int64_t m, double radius, 
   if (m < 0 || (m > 0 && (!ag || !g || !out))) return fail(GCA_ERR_INVALID, "bad buffers");
   if (kind != GCA_OBS_HER && kind != GCA_OBS_DHER) return fail(GCA_ERR_INVALID, "kind must be GCA_OBS_HER or GCA_OBS_DHER");
   GCA_CUDA(cudaSetDevice(device));
-  GCA_CUDA(launch_compute_reward(ag, g, (long long)m, radius, kind, is_f64, out, (cudaStream_t)stream));
+  GCA_CUDA(launch_compute_reward(ag, (long long)m, g, (long long)m, radius, kind, is_f64, out, (cudaStream_t)stream));
+  return GCA_OK;
+}
+
+int gca_compute_reward_tiled(const void* ag, int64_t n_ag, const void* g, int64_t m, double radius, int kind, int is_f64,
+                             float* out, int device, void* stream) {
+  if (m < 0 || n_ag <= 0 || (m > 0 && (!ag || !g || !out)) || m % n_ag) return fail(GCA_ERR_INVALID, "bad buffers (m must be a multiple of n_ag)");
+  if (kind != GCA_OBS_HER && kind != GCA_OBS_DHER) return fail(GCA_ERR_INVALID, "kind must be GCA_OBS_HER or GCA_OBS_DHER");
+  GCA_CUDA(cudaSetDevice(device));
+  GCA_CUDA(launch_compute_reward(ag, (long long)n_ag, g, (long long)m, radius, kind, is_f64, out, (cudaStream_t)stream));
   return GCA_OK;
 }
 

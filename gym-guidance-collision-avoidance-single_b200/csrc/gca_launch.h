@@ -15,8 +15,8 @@ cudaError_t launch_stream_fc(bool faith, const StepArgs& a, cudaStream_t st);
 cudaError_t launch_step_tail(bool faith, const StepArgs& a, cudaStream_t st);
 cudaError_t launch_reset(bool faith, bool tape, const StepArgs& a, cudaStream_t st);
 cudaError_t launch_observe(bool faith, const StepArgs& a, cudaStream_t st);
-cudaError_t launch_compute_reward(const void* ag, const void* g, long long m, double radius, int kind, int is_f64,
-                                  float* out, cudaStream_t st);
+cudaError_t launch_compute_reward(const void* ag, long long n_ag, const void* g, long long m, double radius, int kind,
+                                  int is_f64, float* out, cudaStream_t st);
 cudaError_t launch_input_reward(const void* rows, long long m, int dim, int is_f64, const gca_input_reward_cfg* cfg,
                                 double* out, uint8_t* done, cudaStream_t st);
 cudaError_t launch_mcts_playouts(const gca_mcts_config* cfg, int n, const double* roots, long long n_roots, int playouts,

@@ -4,15 +4,19 @@
 // np.linalg.norm(x, axis=-1) = sqrt(add.reduce(x*x)): plain multiply / add, in the input dtype.
 // 20 bytes per pair (f32) or 36 (f64): purely HBM-bound, 16-byte loads, grid-stride.
 #include "gca_launch.h"
+#include "gca_step_common.cuh"
 
 namespace gca {
 
 template <typename T, typename T2>
-__global__ void __launch_bounds__(256) reward_kernel(const T2* __restrict__ ag, const T2* __restrict__ g, long long m,
-                                                     double radius, int kind, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) reward_kernel(const T2* __restrict__ ag, long long n_ag, const T2* __restrict__ g,
+                                                     long long m, double radius, int kind, float* __restrict__ out) {
+  // launched with programmatic stream serialization: staged while the step's last kernel drains, and the next step's
+  // first kernel is staged while this one runs (a plain launch between two steps cost ~2 us at each boundary)
+  pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
-    const T2 a = ag[i], b = g[i];
+    const T2 a = ag[n_ag == m ? i : i % n_ag], b = g[i];     // (n_ag < m: the achieved goals repeat, k substitute goals each)
     bool gt, lt;
     if constexpr (sizeof(T) == 8) {
       const double dx = __dadd_rn(a.x, -b.x), dy = __dadd_rn(a.y, -b.y);
@@ -29,18 +33,16 @@ __global__ void __launch_bounds__(256) reward_kernel(const T2* __restrict__ ag, 
   }
 }
 
-cudaError_t launch_compute_reward(const void* ag, const void* g, long long m, double radius, int kind, int is_f64,
-                                  float* out, cudaStream_t st) {
+cudaError_t launch_compute_reward(const void* ag, long long n_ag, const void* g, long long m, double radius, int kind,
+                                  int is_f64, float* out, cudaStream_t st) {
   if (m <= 0) return cudaSuccess;
   long long blocks = (m + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (is_f64)
-    reward_kernel<double, double2><<<(unsigned)blocks, 256, 0, st>>>((const double2*)ag, (const double2*)g, m, radius,
-                                                                      kind, out);
-  else
-    reward_kernel<float, float2><<<(unsigned)blocks, 256, 0, st>>>((const float2*)ag, (const float2*)g, m, radius, kind,
-                                                                    out);
-  return cudaGetLastError();
+    return launch_pdl(reward_kernel<double, double2>, (unsigned)blocks, 256, st, (const double2*)ag, n_ag, (const double2*)g,
+                      m, radius, kind, out);
+  return launch_pdl(reward_kernel<float, float2>, (unsigned)blocks, 256, st, (const float2*)ag, n_ag, (const float2*)g, m,
+                    radius, kind, out);
 }
 
 // compute_input_reward(new_inputs) of Simulators/SingleAircraftDiscrete9HEREnv.py:244-276 for m relabelled

@@ -146,6 +146,7 @@ def load():
         "gca_profile_enable": ([vp, i32], C.c_int),
         "gca_profile_read": ([vp, P(GcaStepProfile)], C.c_int),
         "gca_compute_reward": ([vp, vp, i64, C.c_double, i32, i32, vp, i32, vp], C.c_int),
+        "gca_compute_reward_tiled": ([vp, i64, vp, i64, C.c_double, i32, i32, vp, i32, vp], C.c_int),
         "gca_input_reward": ([vp, i64, i32, i32, P(GcaInputRewardCfg), vp, vp, i32, vp], C.c_int),
         "gca_raster": ([vp, vp, vp, i64, i64, i32, i32, vp, vp], C.c_int),
         "gca_monitor_update": ([vp, i32, vp, i64, vp, vp, vp, i64, vp, u32, i32, vp], C.c_int),

@@ -276,9 +276,16 @@ def compute_reward(achieved_goal, desired_goal, radius, kind):
     if ag.dtype != g.dtype:                      # mixed f32/f64 promotes to f64, like numpy
         ag, g = ag.to(torch.float64), g.to(torch.float64)
     ag, g = ag.contiguous(), g.contiguous()
-    m = ag.numel() // 2
-    out = torch.empty(ag.shape[:-1], dtype=torch.float32, device=ag.device)
-    abi.check(lib.gca_compute_reward(ag.data_ptr(), g.data_ptr(), m, float(radius), kind,
-                                     1 if ag.dtype == torch.float64 else 0, out.data_ptr(), ag.device.index or 0,
-                                     C.c_void_p(torch.cuda.current_stream(ag.device).cuda_stream)))
+    m, n_ag = g.numel() // 2, ag.numel() // 2
+    out = torch.empty(g.shape[:-1], dtype=torch.float32, device=ag.device)
+    stream = C.c_void_p(torch.cuda.current_stream(ag.device).cuda_stream)
+    is64 = 1 if ag.dtype == torch.float64 else 0
+    if n_ag == m:
+        abi.check(lib.gca_compute_reward(ag.data_ptr(), g.data_ptr(), m, float(radius), kind, is64, out.data_ptr(),
+                                         ag.device.index or 0, stream))
+    else:           # achieved [B, 2] against desired [k, B, 2]: the k relabels of every transition, ag not copied k times
+        if n_ag <= 0 or m % n_ag:
+            raise ValueError("desired_goal must hold a whole number of goals per achieved goal")
+        abi.check(lib.gca_compute_reward_tiled(ag.data_ptr(), n_ag, g.data_ptr(), m, float(radius), kind, is64,
+                                               out.data_ptr(), ag.device.index or 0, stream))
     return out

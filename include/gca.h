@@ -261,6 +261,10 @@ int gca_set_state(gca_env* env, const gca_host_state* src);
  * ag, g: device [m][2], f64 when is_f64 else f32; out: device float[m]. */
 int gca_compute_reward(const void* ag, const void* g, int64_t m, double radius, int kind,
                        int is_f64, float* out, int device, void* stream);
+/* The same with the achieved goals repeating: ag [n_ag][2], g [m][2], m = k * n_ag, out[i] = reward(ag[i % n_ag], g[i]) -
+ * the relabel of DDPG.py:308-315 (k substitute goals per transition) without materialising the k copies of ag. */
+int gca_compute_reward_tiled(const void* ag, int64_t n_ag, const void* g, int64_t m, double radius, int kind, int is_f64,
+                             float* out, int device, void* stream);
 
 /* compute_input_reward(new_inputs) of Simulators/SingleAircraftDiscrete9HEREnv.py:244-276, the reward the repo's own
  * HER learner gives a relabelled transition (Algorithms/pytorch/agent_her.py:107-117), for m rows at once.

@@ -338,6 +338,13 @@ def test_compute_reward_matches_reference():
     ag = rng.uniform(0, 800, (4 * 65536, 2)); gg = ag + rng.uniform(-30, 30, ag.shape)
     assert np.array_equal(compute_reward(dev(ag), dev(gg), 20.0, abi.OBS_DHER).cpu().numpy(),
                           orc.compute_reward(ag, gg, 20.0, abi.OBS_DHER))
+    # the same relabel without the k copies of the achieved goals (gca_compute_reward_tiled): [B, 2] against [k, B, 2]
+    agb = ag[:65536]
+    gk = (agb[None] + rng.uniform(-30, 30, (4, 65536, 2)))
+    got = compute_reward(dev(agb), dev(gk), 20.0, abi.OBS_DHER).cpu().numpy()
+    assert got.shape == (4, 65536)
+    assert np.array_equal(got, orc.compute_reward(np.broadcast_to(agb, gk.shape).reshape(-1, 2), gk.reshape(-1, 2), 20.0,
+                                                  abi.OBS_DHER).reshape(4, 65536))
 
 
 @pytest.mark.parametrize("vk", ["env2", "mctsrnd"])
