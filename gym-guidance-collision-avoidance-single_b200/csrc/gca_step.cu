@@ -196,10 +196,9 @@ __device__ __forceinline__ void own_update(const StepArgs& a, const size_t me, c
   if constexpr (TAPE) {
     s.own_b[me] = make_float4(pos.x, pos.y, __uint_as_float(bits), 0.f);
   } else if (publish) {
-    float* rec = reinterpret_cast<float*>(&s.own_b[me]);
-    st_release_pair(rec, pos.x, pos.y);
-    __threadfence();                                              // (x, y) are visible before the stamp is
-    st_release_pair(rec + 2, __uint_as_float(bits), __uint_as_float(stamp));
+    // one 16-byte store, read with one 16-byte load: both are single transactions on one 32-byte sector, so a matching
+    // stamp comes with its position (no fence: nothing else has to be visible to the streaming lanes)
+    st_release_quad(reinterpret_cast<float*>(&s.own_b[me]), pos.x, pos.y, __uint_as_float(bits), __uint_as_float(stamp));
   }
   s.own_pos[me] = pos;
   s.own_hs[me] = hs;
@@ -816,9 +815,7 @@ __global__ void __launch_bounds__(kWarpsB * 32, FAITH ? GCA_FAITH_MINB : (FC ? 8
       if (env < (size_t)s.B) {
         own_update<FAITH, false>(a, env, stamp, true);
       } else if (env < (size_t)s.T * 32) {                // padding lanes of the last tile
-        float* rec = reinterpret_cast<float*>(&s.own_b[env]);
-        st_release_pair(rec, 0.f, 0.f);
-        st_release_pair(rec + 2, 0.f, __uint_as_float(stamp));
+        st_release_quad(reinterpret_cast<float*>(&s.own_b[env]), 0.f, 0.f, 0.f, __uint_as_float(stamp));
       }
       GCA_KSTAMP_OUT(0);
       return;
@@ -849,8 +846,8 @@ __global__ void __launch_bounds__(kWarpsB * 32, FAITH ? GCA_FAITH_MINB : (FC ? 8
   float4 ob;
   GCA_KSTAMP_IN(3);                                       // (timing builds: first streaming block in / first record seen)
   if (FC || a.own_blocks > 0) {
-    // wait for this step's ownship record of the lane's env: (bits, stamp) is stored behind a fence after (x, y), and
-    // a 16-byte aligned vector load is served from one sector - a matching stamp comes with its position
+    // wait for this step's ownship record of the lane's env: it is stored with one 16-byte store and read with one
+    // 16-byte aligned vector load, both served from one sector - a matching stamp comes with its position
     int spins = 0;
     for (;;) {
       ob = ld_volatile_f4(&s.own_b[me]);

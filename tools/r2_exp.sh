@@ -1,3 +1,3 @@
-L=$PWD/gym-guidance-collision-avoidance-single_b200/lib
-python tools/her_step_probe.py 2>/dev/null | tail -1
-for x in 1 2 3; do GCA_LIB=$L/libgca_exp$x.so python tools/her_step_probe.py 2>/dev/null | tail -1; done
+GCA_BENCH_KERNEL_ONLY=1 timeout 300 python bench.py --steps 1000 --warmup 10 | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('headline', d['ms_per_step'], d['roofline']['kernels_ms'])"
+GCA_BENCH_KERNEL_ONLY=1 timeout 300 python bench.py --steps 20 --warmup 3 | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('steps20', d['ms_per_step'])"
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
