@@ -82,3 +82,18 @@ for lo in edges:
     m = (end >= lo) & (end < lo + 4)
     if m.any():
         print("  t=%5.1f..%5.1f  blocks finished %5d  mean lifetime %.2f  resident at t %d" % (lo, lo + 4, m.sum(), (end - start)[m].mean(), ((start <= lo) & (end > lo)).sum()))
+# per-tile phases of the finish kernel (default step): start, loads, replay, reward + stores, reset + counters, spawn (i)
+if not os.environ.get("GCA_FORECAST"):
+    fb = np.zeros(2048 * 8, np.uint64)
+    lib.gca_debug_fin.argtypes = [C.c_void_p]
+    lib.gca_debug_fin(fb.ctypes.data)
+    f = fb.astype(np.int64).reshape(2048, 8)
+    f = f[f[:, 0] > 0]
+    dur = (f[:, 1] - f[:, 0]) / 1e3
+    print("finish_tile per tile (us): mean %.2f p50 %.2f p90 %.2f p99 %.2f max %.2f" % (dur.mean(), np.median(dur), np.percentile(dur, 90), np.percentile(dur, 99), dur.max()))
+    print("finish phases (us, mean): loads %.2f  replay %.2f  reward+stores %.2f  reset+counters %.2f  spawn phase (i) %.2f" % (
+        ((f[:, 4] - f[:, 0]) / 1e3).mean(), ((f[:, 5] - f[:, 4]) / 1e3).mean(), ((f[:, 6] - f[:, 5]) / 1e3).mean(),
+        ((f[:, 1] - f[:, 6]) / 1e3).mean(), ((f[:, 7] - f[:, 1]) / 1e3).mean()))
+    t0 = f[:, 0].min()
+    print("relative to the first finish warp: finish_tile starts p50 %.2f max %.2f; ends max %.2f; spawn (i) ends max %.2f" % (
+        (np.median(f[:, 0]) - t0) / 1e3, (f[:, 0].max() - t0) / 1e3, (f[:, 1].max() - t0) / 1e3, (f[:, 7].max() - t0) / 1e3))
