@@ -811,7 +811,8 @@ __global__ void __launch_bounds__(kWarpsB * 32, FAITH ? GCA_FAITH_MINB : (FC ? 8
     stamp = *s.step_seq + 1u;
     if (blockIdx.x < (unsigned)a.own_blocks) {
       GCA_KSTAMP_IN(0);
-      const size_t env = (size_t)blockIdx.x * (kWarpsB * 32) + threadIdx.x;
+      // (odd steps walk the batch backwards, like the streaming role below: the records needed first come first)
+      const size_t env = (size_t)((stamp & 1u) ? (unsigned)a.own_blocks - 1u - blockIdx.x : blockIdx.x) * (kWarpsB * 32) + threadIdx.x;
       if (env < (size_t)s.B) {
         own_update<FAITH, false>(a, env, stamp, true);
       } else if (env < (size_t)s.T * 32) {                // padding lanes of the last tile
@@ -826,7 +827,10 @@ __global__ void __launch_bounds__(kWarpsB * 32, FAITH ? GCA_FAITH_MINB : (FC ? 8
   const long long work = (long long)(blockIdx.x - (unsigned)(FC ? a.head_ctas : a.own_blocks)) * kWarpsB + wib;
   do {                                                    // (one pass; `break` = this warp has no work item)
   if (head_block || work >= (long long)s.T * n_chunks) break;
-  const int tile = (int)(work / n_chunks), ch = (int)(work - (long long)tile * n_chunks);
+  // Philox handles walk the tiles forwards in even steps and backwards in odd ones: the plane this step reads is the
+  // plane the previous step wrote, and what it wrote LAST is what is most likely still in the L2 (43.3 -> 42.6 us)
+  const int tile_fwd = (int)(work / n_chunks), ch = (int)(work - (long long)tile_fwd * n_chunks);
+  const int tile = (!FC && a.own_blocks > 0 && (stamp & 1u)) ? s.T - 1 - tile_fwd : tile_fwd;
   const size_t me = (size_t)tile * 32 + lane;
   const bool has_env = me < (size_t)s.B;
   const int u0 = ch * kChunkUnits, i0 = 2 * u0;
