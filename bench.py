@@ -463,6 +463,10 @@ def main_gpu(args):
                                    "intruders); an event interval includes the drain / launch gap around the kernel, so "
                                    "achieved is a lower bound (kernel_us_ncu: the committed ncu capture)" % prof["steps"],
                          "kernel_us_ncu": ncu_kernel_us(),
+                         "l2_note": "achieved = ALGORITHMIC bytes / live time. In the graph the DRAM traffic is lower than that: "
+                                    "the position plane a step writes (plain stores) is largely still in the 126 MB L2 when "
+                                    "the next step reads it (tiles walked in alternating directions) and is discarded after "
+                                    "the read instead of written back; `traffic` is the cold, serialised ncu capture",
                          "kernels_ms": {"main (ownship role + streaming pass)": launch_ms,
                                         "finish + spawn phase": prof["finish_ms"] / max(prof["steps"], 1)},
                          "step": {"achieved": step_gbs, "frac": step_gbs / peak,
