@@ -184,6 +184,14 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
+// The opposite hint for the few megabytes that a LATER kernel of the same step reads first (what the ownship role
+// leaves for the finish: position, counters, reward candidate): evict_last keeps them in the L2
+// across the 200 MB stream, so the finish kernel's first loads are L2 hits instead of DRAM round trips.
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ float4 ldg_stream(const void* ptr, uint64_t pol) {
   float4 v;
   asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
