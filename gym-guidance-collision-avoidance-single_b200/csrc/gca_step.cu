@@ -1018,14 +1018,15 @@ __global__ void __launch_bounds__(kWarpsB * 32, FAITH ? GCA_FAITH_MINB : (FC ? 8
               stg_stream(dst + it * dstep, val, pol);
             } else {
               // own-first rows (4 N + 6 entries, the intruders from entry 6 on): an entry is 16-byte aligned in every
-              // other row only, and the 128-byte pieces of neighbouring work items share 32-byte sectors.  Plain stores
-              // (no evict_first hint) let the L2 merge those shared sectors before they go to DRAM: 55.9 -> 52.1 us per
-              // step at 65,536 x 80 together with the 16-byte store where the row allows it.
+              // other row only (one 16-byte store there, two 8-byte stores elsewhere).  History: with every position
+              // store marked evict_first, plain observation stores were faster here (the sectors that two work items
+              // share got merged in the L2: 55.9 -> 52.1 us); since the position plane is kept in the L2 on purpose
+              // the observation stream must not compete with it, and evict_first is the better hint again (50.1 -> 49.3).
               if ((reinterpret_cast<uintptr_t>(dst + it * dstep) & 15u) == 0) {
-                *reinterpret_cast<float4*>(dst + it * dstep) = val;
+                stg_stream(dst + it * dstep, val, pol);
               } else {
-                *reinterpret_cast<float2*>(dst + it * dstep) = make_float2(val.x, val.y);
-                *reinterpret_cast<float2*>(dst + it * dstep + 2) = make_float2(val.z, val.w);
+                stg_stream2(dst + it * dstep, val.x, val.y, pol);
+                stg_stream2(dst + it * dstep + 2, val.z, val.w, pol);
               }
             }
           }
