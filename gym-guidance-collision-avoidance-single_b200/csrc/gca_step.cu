@@ -1481,9 +1481,8 @@ static cudaError_t launch_step_t(const StepArgs& a0, cudaStream_t st, cudaEvent_
     return cudaGetLastError();
   }
   if (s.N > 0) {
-    static_assert(kWarpsB * 32 == 128, "the ownship role is thread = env in blocks of 128");
     const int n_chunks = (s.U + kChunkUnits - 1) / kChunkUnits;
-    a.own_blocks = TAPE ? 0 : (int)env_blocks;
+    a.own_blocks = TAPE ? 0 : (int)(((size_t)s.T * 32 + kWarpsB * 32 - 1) / (kWarpsB * 32));   // (thread = env, blocks of the streaming kernel's size)
     const unsigned blocks = (unsigned)(((long long)s.T * n_chunks + kWarpsB - 1) / kWarpsB) + (unsigned)a.own_blocks;
     if constexpr (FAITH) {
       if (a.k.has_drift) launch_pdl(step_intruders_kernel<true, 0, true>, blocks, kWarpsB * 32, st, a);
