@@ -57,6 +57,12 @@ __device__ unsigned long long g_cta[8192 * 2];   // per block of the streaming k
 extern "C" int gca_debug_cta(unsigned long long* host) { return (int)cudaMemcpyFromSymbol(host, g_cta, sizeof(g_cta)); }
 __device__ unsigned long long g_fin[2048 * 8];   // per tile: finish start, end, respawn iterations, resets
 extern "C" int gca_debug_fin(unsigned long long* host) { return (int)cudaMemcpyFromSymbol(host, g_fin, sizeof(g_fin)); }
+__device__ unsigned int g_lat[8 * 64];            // position-load latency of the streaming pass: [eighth of the walk][64-cycle bucket]
+extern "C" int gca_debug_lat(unsigned int* host, int clear) {
+  int rc = (int)cudaMemcpyFromSymbol(host, g_lat, sizeof(g_lat));
+  if (clear) { static unsigned int zero[8 * 64]; rc |= (int)cudaMemcpyToSymbol(g_lat, zero, sizeof(zero)); }
+  return rc;
+}
 #define GCA_KSTAMP_IN(kid) do { if (threadIdx.x == 0) atomicMin(&g_kstamp[2 * (kid)], gtime()); } while (0)
 #define GCA_KSTAMP_OUT(kid) do { if (threadIdx.x == 0) atomicMax(&g_kstamp[2 * (kid) + 1], gtime()); } while (0)
 extern "C" int gca_debug_kstamps(unsigned long long* host, int reset) {
@@ -904,8 +910,20 @@ __global__ void __launch_bounds__(kWarpsB * 32, FAITH ? GCA_FAITH_MINB : (FC ? 8
       // ---- all 8 intruders at once, straight-line
       fast_done = true;
       float4 p[kChunkUnits], np[kChunkUnits];
+#ifdef GCA_PHASE_TIMING
+      const long long lat_t0 = clock64();
+#endif
 #pragma unroll
       for (int g = 0; g < kChunkUnits; ++g) p[g] = ldg_stream(psrc + g * 512, pol);
+#ifdef GCA_PHASE_TIMING
+      {
+        float sink = 0.f;
+        for (int g = 0; g < kChunkUnits; ++g) sink += p[g].x + p[g].w;
+        if (__any_sync(FULL, sink == 1.2345e38f)) atomicAdd(&g_lat[0], 1u);   // (never true: makes the warp wait for the data here)
+        const long long dt = clock64() - lat_t0;
+        if (lane == 0) atomicAdd(&g_lat[min(7, tile_fwd * 8 / s.T) * 64 + (int)min(63ll, dt >> 6)], 1u);
+      }
+#endif
       const uint32_t wbits = __float_as_uint(k.win_w), hbits = __float_as_uint(k.win_h);
 #pragma unroll
       for (int g = 0; g < kChunkUnits; ++g) {

@@ -97,3 +97,19 @@ if not os.environ.get("GCA_FORECAST"):
     t0 = f[:, 0].min()
     print("relative to the first finish warp: finish_tile starts p50 %.2f max %.2f; ends max %.2f; spawn (i) ends max %.2f" % (
         (np.median(f[:, 0]) - t0) / 1e3, (f[:, 0].max() - t0) / 1e3, (f[:, 1].max() - t0) / 1e3, (f[:, 7].max() - t0) / 1e3))
+# position-load latency of the streaming pass (clock64 cycles from issue to data), by eighth of the walk order:
+# what the previous step wrote last is read first - L2 hits there show as a low-latency mode
+lb = np.zeros(8 * 64, np.uint32)
+lib.gca_debug_lat.argtypes = [C.c_void_p, C.c_int]
+lib.gca_debug_lat(lb.ctypes.data, 1)
+for rep in range(2):
+    g8.replay()
+    torch.cuda.synchronize()
+    lib.gca_debug_lat(lb.ctypes.data, 1)
+    h = lb.astype(np.int64).reshape(8, 64)
+    print("position-load latency histogram (work items per 256-cycle bin: 0-255, 256-511, ...; last bin = 3840+), 8 steps:")
+    for o in range(8):
+        row = h[o].reshape(16, 4).sum(1)
+        cdf = np.cumsum(h[o]) / max(1, h[o].sum())
+        med = int(np.searchsorted(cdf, 0.5)) * 64
+        print("  eighth %d of the walk: median %5d cycles  " % (o, med) + " ".join("%5d" % v for v in row))
