@@ -27,6 +27,7 @@
 // not by HBM: a root state (2.6 KB at N = 80) is read once per playout and stays in registers.
 #include <cstdlib>
 
+#include <algorithm>
 #include "gca_launch.h"
 
 namespace gca {
@@ -398,6 +399,91 @@ __global__ void __launch_bounds__(kSharedThreads) mcts_playout_shared_kernel(con
   }
 }
 
+// ---- the same, several roots per CTA and one depth at a time.  With one CTA per root the playouts of a root fill
+// 100 of 128 lanes (the fourth warp runs 4 lanes) and the [depth * simulate_frame][near] candidate array (38 KB at
+// N = 80) holds the CTA count per SM to five.  Here the lanes of a CTA are the playouts of R consecutive roots laid
+// end to end (4 roots x 100 playouts = 400 of 416 lanes), and the candidate lists exist for ONE depth at a time
+// (simulate_frame sub-frames: 12.8 KB per root at N = 80): per depth, phase 1 advances every intruder of the R roots
+// through the depth's sub-frames from where the previous depth left it (running position in shared memory, the same
+// chain of additions), then every lane runs its playout's move of that depth.  A lane's arithmetic is exactly that of
+// mcts_playout_shared_kernel - same results, bit for bit.
+constexpr int kPackThreads = 512;             // 2 CTAs x 512 threads x 64 registers fill the register file
+constexpr int kPackMaxRoots = 8;
+
+__global__ void __launch_bounds__(kPackThreads, 2) mcts_playout_packed_kernel(const MctsArgs a, const int R) {
+  extern __shared__ __align__(16) uint8_t mcts_sh[];
+  const gca_mcts_config& c = a.c;
+  const int F = c.simulate_frame, near = a.near;
+  // layout: cnt [R][F] ints | xs [R][near] double2 | cand [R][F][near] double2
+  int* cnt = reinterpret_cast<int*>(mcts_sh);
+  double2* xs = reinterpret_cast<double2*>(mcts_sh + (((size_t)R * F * 4 + 15) & ~(size_t)15));
+  double2* cand = xs + (size_t)R * near;
+  const long long r0 = (long long)blockIdx.x * R;
+  const int r_here = (int)min((long long)R, a.n_roots - r0);
+  const int q = threadIdx.x, rl = q / a.playouts, p = q - rl * a.playouts;
+  const bool active = rl < r_here;
+  const long long r_idx = r0 + (active ? rl : 0);
+  const uint32_t root = a.root_id0 + (uint32_t)r_idx;
+  const double* own = a.roots + r_idx * a.L + a.per * a.n;
+  const double gx = own[6], gy = own[7];
+  const long long pid = r_idx * a.playouts + p;
+  double ox = own[0], oy = own[1], vy_prev = own[3], heading = own[5];
+  int flags = 0, first = -1;
+  const bool cull = c.speed_sigma == 0.0;
+  const double vmax = fmax(fabs(c.min_speed), fabs(c.max_speed));
+  for (int depth = 0; depth < a.depth; ++depth) {
+    for (int f = threadIdx.x; f < r_here * F; f += blockDim.x) cnt[f] = 0;
+    __syncthreads();
+    // ---- phase 1 of this depth: thread = (root, intruder)
+    for (int idx = threadIdx.x; idx < r_here * near; idx += blockDim.x) {
+      const int jr = idx / near, i = idx - jr * near;
+      const double* st = a.roots + (r0 + jr) * a.L;
+      const double* jo = st + a.per * a.n;
+      const double ox0 = jo[0], oy0 = jo[1];
+      const double2 v0 = reinterpret_cast<const double2*>(st)[2 * i + 1];
+      double2 pos = depth == 0 ? reinterpret_cast<const double2*>(st)[2 * i] : xs[(size_t)jr * near + i];
+      double x = pos.x, y = pos.y;
+      const double vx = __dadd_rn(v0.x, 0.0), vy = __dadd_rn(v0.y, 0.0);     // vx + normal(0, 0) :54-57
+      for (int f = 0; f < F; ++f) {
+        x = __dadd_rn(x, vx);
+        y = __dadd_rn(y, vy);
+        bool in = true;
+        if (cull) {
+          const double reach = c.minimum_separation + (double)(depth * F + f + 1) * vmax * 1.000001 + 0.5;
+          const double dx = x - ox0, dy = y - oy0;
+          in = !(dx * dx + dy * dy >= reach * reach);
+        }
+        if (in) cand[((size_t)jr * F + f) * near + atomicAdd(&cnt[jr * F + f], 1)] = make_double2(x, y);
+      }
+      xs[(size_t)jr * near + i] = make_double2(x, y);
+    }
+    __syncthreads();
+    // ---- phase 2 of this depth: lane = playout (lane_move indexes the lists by global sub-frame: shift the bases)
+    if (active && !flags) {
+      int act;
+      if (depth == 0 && a.first_action && a.first_action[pid] >= 0) act = a.first_action[pid];
+      else act = mcts_action(a, root, (uint32_t)p, (uint32_t)depth);
+      if (first < 0) first = act;
+      flags = lane_move(a, cnt + (rl - depth) * F, cand + (ptrdiff_t)(rl - depth) * F * near, root, (uint32_t)p, depth, act, gx, gy,
+                        ox, oy, vy_prev, heading);
+    }
+    __syncthreads();
+  }
+  if (active) {
+    double reward;
+    if (flags & (GCA_MCTS_WALL | GCA_MCTS_CONFLICT)) reward = 0.0;
+    else if (flags & GCA_MCTS_GOAL) reward = 1.0;
+    else {
+      const double dx = __dadd_rn(ox, -gx), dy = __dadd_rn(oy, -gy);
+      const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+      reward = __dadd_rn(1.0, -__ddiv_rn(dist, 1200.0));
+    }
+    a.rewards[pid] = reward;
+    if (a.first_out) a.first_out[pid] = (int8_t)first;
+    if (a.flags) a.flags[pid] = (uint8_t)flags;
+  }
+}
+
 // ------------------------------------------------------------------------------ device-resident UCT search
 // MCTS(root).best_action(simulations, search_depth) (search_single.py:8-22; tree_policy / expand / best_child /
 // backpropagate: common.py:47-52, nodes_single.py:188-210) for a batch of roots, position_sigma == 0.  Because the
@@ -714,6 +800,20 @@ cudaError_t launch_mcts_playouts(const gca_mcts_config* cfg, int n, const double
     if (e != cudaSuccess) return e;
     mcts_playout_kernel<0, true><<<pblocks, kMctsWarps * 32, smem, st>>>(a);
     return cudaGetLastError();
+  }
+  if (cfg->position_sigma == 0.0 && playouts <= kPackThreads && depth > 0 && !getenv("GCA_MCTS_WARP_KERNEL") && !getenv("GCA_MCTS_NO_PACK")) {
+    // several roots per CTA, candidate lists of one depth at a time (mcts_playout_packed_kernel)
+    const size_t F = (size_t)cfg->simulate_frame;
+    auto pack_smem = [&](int r) { return (((size_t)r * F * 4 + 15) & ~(size_t)15) + sizeof(double2) * (size_t)r * (size_t)a.near * (1 + F); };
+    int R = (int)std::min<long long>(std::min<long long>(kPackMaxRoots, kPackThreads / playouts), n_roots);
+    while (R > 1 && 2 * pack_smem(R) > 200 * 1024) --R;      // two CTAs per SM
+    if (pack_smem(R) <= 200 * 1024) {
+      const unsigned threads = (unsigned)(((long long)R * playouts + 31) / 32 * 32);
+      cudaError_t e = cudaFuncSetAttribute(mcts_playout_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pack_smem(R));
+      if (e != cudaSuccess) return e;
+      mcts_playout_packed_kernel<<<(unsigned)((n_roots + R - 1) / R), threads, pack_smem(R), st>>>(a, R);
+      return cudaGetLastError();
+    }
   }
   if (cfg->position_sigma == 0.0 && shared_smem <= 160 * 1024 && !getenv("GCA_MCTS_WARP_KERNEL")) {
     cudaError_t e = cudaFuncSetAttribute(mcts_playout_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shared_smem);

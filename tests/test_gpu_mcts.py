@@ -77,6 +77,15 @@ def test_warp_per_playout_kernel_bit_exact(n, roots_n, playouts, depth, monkeypa
     test_playouts_bit_exact_vs_oracle(n, roots_n, playouts, depth, {})
 
 
+@pytest.mark.parametrize("n,roots_n,playouts,depth", [(80, 37, 100, 3), (3, 9, 50, 3), (80, 5, 500, 2)])
+def test_one_root_per_cta_kernel_bit_exact(n, roots_n, playouts, depth, monkeypatch):
+    """position_sigma == 0 packs several roots into a CTA (mcts_playout_packed_kernel; 37 roots = a ragged last CTA);
+    the one-root-per-CTA kernel (more than 448 playouts per root, or GCA_MCTS_NO_PACK) must give the same bits."""
+    test_playouts_bit_exact_vs_oracle(n, roots_n, playouts, depth, {})
+    monkeypatch.setenv("GCA_MCTS_NO_PACK", "1")
+    test_playouts_bit_exact_vs_oracle(n, roots_n, playouts, depth, {})
+
+
 def test_random_intruder_playouts_without_culling_bit_exact(monkeypatch):
     """The random-intruder playout kernel drops the intruders that cannot reach the ownship within the playout (exact:
     results are compared with the oracle, which simulates all of them, above); with the culling switched off
