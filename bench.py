@@ -766,11 +766,11 @@ def bench_mctsrnd(device):
     torch.cuda.synchronize()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
-    for rep_i in range(3):
+    for rep_i in range(10):
         mcts.playouts(roots, P, depth=depth, cfg=mcfg, seed=2 + rep_i)
     stop.record()
     torch.cuda.synchronize()
-    pms = start.elapsed_time(stop) / 3
+    pms = start.elapsed_time(stop) / 10
     env.close()
     peak, _ = measured_peaks()
     bytes_per_env_step = 80 * N + 122
@@ -781,7 +781,9 @@ def bench_mctsrnd(device):
             "model": {"metric": "mcts_rollouts_per_sec", "value": R * P / (pms * 1e-3), "unit": "rollouts/s", "roots": R,
                       "playouts_per_root": P, "depth": depth, "intruders": N, "ms_per_launch": pms,
                       "roofline": fp64_roofline("mctsrnd_model_ncu.json", pms),
-                      "kernel": "mcts_playout_kernel<0, true> (nodes_single_randintru.py model; one warp per playout, intruders out of reach culled exactly)"}}
+                      "kernel": "mcts_playout_rnd_lane_kernel (nodes_single_randintru.py model; one playout per lane, two roots per CTA, "
+                                "intruders out of reach culled exactly once per root; bound by instruction issue - one Philox block per "
+                                "intruder and sub-frame -, the FP64 fraction is reported for comparison with the other MCTS kernels)"}}
 
 
 def bench_her_replay(device):

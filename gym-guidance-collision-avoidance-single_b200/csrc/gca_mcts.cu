@@ -484,6 +484,164 @@ __global__ void __launch_bounds__(kPackThreads, 2) mcts_playout_packed_kernel(co
   }
 }
 
+// ---- the random-intruder model (nodes_single_randintru.py), one playout per LANE.  In mcts_playout_kernel<0, true> a
+// warp runs one playout with lane = intruder (after the exact cull ~10 of 32 lanes) or lane = sub-frame (10 of 32) -
+// a third of every instruction does work.  Here the lanes of a CTA are the playouts of R consecutive roots laid end
+// to end; a warp per root culls the root's intruders once into shared memory (the survivors and their original
+// indices - the draws of intruder i are addressed by i), and every lane then runs its playout sequentially on a
+// private copy of the survivors (thread-local arrays: position, velocity and heading change per playout) - the same
+// operations in the same order per playout and intruder as the warp kernel, so the same bits.
+#ifndef GCA_LANE_THREADS
+#define GCA_LANE_THREADS 256
+#endif
+#ifndef GCA_LANE_MINB
+#define GCA_LANE_MINB 3
+#endif
+constexpr int kLaneThreads = GCA_LANE_THREADS;     // measured at 100 playouts per root: 256 threads (2 roots, 200 of 224 lanes), 3 CTAs per SM at 79
+                                                   // registers: 4.3e8 rollouts/s; 512 x 1 (112 registers) 3.6e8, 512 x 2 / 128 x 8 (64, spills) 3.8e8
+constexpr int kLaneMaxRoots = 8;
+constexpr int kLaneMaxNear = 80;              // thread-local arrays; larger models take the warp-per-playout kernel
+
+__global__ void __launch_bounds__(kLaneThreads, GCA_LANE_MINB) mcts_playout_rnd_lane_kernel(const MctsArgs a, const int R) {
+  extern __shared__ __align__(16) uint8_t mcts_sh[];
+  const gca_mcts_config& c = a.c;
+  const int F = c.simulate_frame, near = a.near;
+  // layout: neff [R] ints (padded to 16 B) | sidx [R][near] ints | base [R][near][6] doubles
+  int* neff = reinterpret_cast<int*>(mcts_sh);
+  int* sidx = neff + 16;
+  double* base = reinterpret_cast<double*>(mcts_sh + (((size_t)(16 + (size_t)R * near) * 4 + 15) & ~(size_t)15));
+  const long long r0 = (long long)blockIdx.x * R;
+  const int r_here = (int)min((long long)R, a.n_roots - r0);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  // ---- cull, a warp per root (see mcts_playout_kernel for the bound)
+  const double frames = (double)a.depth * (double)F;
+  const double own_reach = fmax(fabs(c.max_speed), fabs(c.min_speed)) * frames;
+  for (int jr = wib; jr < r_here; jr += n_warps) {
+    const double* st = a.roots + (r0 + jr) * a.L;
+    const double* jo = st + a.per * a.n;
+    int n_eff = 0;
+    for (int b0 = 0; b0 < near; b0 += 32) {
+      const int i = b0 + lane;
+      double v[6] = {0., 0., 0., 0., 0., 0.};
+      bool keep = false;
+      if (i < near) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) v[q] = st[6 * i + q];
+        const double dx = v[0] - jo[0], dy = v[1] - jo[1];
+        const double reach = fmax(sqrt(v[2] * v[2] + v[3] * v[3]), fabs(v[4])) * frames;
+        keep = !a.cull || !(sqrt(dx * dx + dy * dy) > own_reach + reach + c.minimum_separation + 2.0);   // (NaN: kept)
+      }
+      const uint32_t mask = __ballot_sync(FULL, keep);
+      const int at = n_eff + __popc(mask & ((1u << lane) - 1u));
+      if (keep) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) base[((size_t)jr * near + at) * 6 + q] = v[q];
+        sidx[jr * near + at] = i;
+      }
+      n_eff += __popc(mask);
+    }
+    if (lane == 0) neff[jr] = n_eff;
+  }
+  __syncthreads();
+  // ---- lane = playout
+  const int q = threadIdx.x, rl = q / a.playouts, p = q - rl * a.playouts;
+  if (rl >= r_here) return;
+  const long long r_idx = r0 + rl;
+  const uint32_t root = a.root_id0 + (uint32_t)r_idx, playout = (uint32_t)p;
+  const double* own = a.roots + r_idx * a.L + a.per * a.n;
+  const long long pid = r_idx * a.playouts + p;
+  const int n_eff = neff[rl];
+  const int* my_idx = sidx + rl * near;
+  const double* my_base = base + (size_t)rl * near * 6;
+  double X[kLaneMaxNear], Y[kLaneMaxNear], VX[kLaneMaxNear], VY[kLaneMaxNear], H[kLaneMaxNear];
+  for (int j = 0; j < n_eff; ++j) {
+    X[j] = my_base[6 * j]; Y[j] = my_base[6 * j + 1]; VX[j] = my_base[6 * j + 2]; VY[j] = my_base[6 * j + 3];
+    H[j] = my_base[6 * j + 5];
+  }
+  constexpr int kTurnQueue = 8;
+  int turn_j[kTurnQueue], n_turns = 0;
+  double turn_d[kTurnQueue];
+  auto apply_turn = [&](int j, double delta) {
+    double tsn, tcs;
+    const double h = __dadd_rn(H[j], delta);
+    gca_sincos(h, &tsn, &tcs);
+    VX[j] = __dmul_rn(my_base[6 * j + 4], tcs);
+    VY[j] = __dmul_rn(my_base[6 * j + 4], tsn);
+    H[j] = h;
+  };
+  double ox = own[0], oy = own[1], speed = own[4], heading = own[5];
+  const double gx = own[6], gy = own[7];
+  int flags = 0, first = -1;
+  for (int depth = 0; depth < a.depth && !flags; ++depth) {
+    int act;
+    if (depth == 0 && a.first_action && a.first_action[pid] >= 0) act = a.first_action[pid];
+    else act = mcts_action(a, root, playout, (uint32_t)depth);
+    if (first < 0) first = act;
+    const double d_heading = __dmul_rn((double)(act / 3 - 1), c.d_heading);
+    const double accel = __dmul_rn((double)(act % 3 - 1), c.d_speed);
+    for (int f = 0; f < F; ++f) {
+      const uint32_t gf = (uint32_t)(depth * F + f);
+      const double nh = mcts_normal(a, c.heading_sigma, root, playout, GCA_MCTS_DRAW_HEADING, gf);
+      const double nsp = mcts_normal(a, c.speed_sigma, root, playout, GCA_MCTS_DRAW_SPEED, gf);
+      heading = __dadd_rn(heading, d_heading);                        // state[-3] += d_heading
+      heading = __dadd_rn(heading, nh);                               // state[-3] += normal(0, heading_sigma)
+      double sn, cs;
+      gca_sincos(heading, &sn, &cs);
+      double sp = clamp_speed(c, __dadd_rn(speed, accel));            // state[-4] += a; state[-4] = clamp(state[-4])
+      sp = __dadd_rn(sp, nsp);                                        // += normal(0, speed_sigma)
+      speed = sp;
+      ox = __dadd_rn(ox, __dmul_rn(sp, cs));
+      oy = __dadd_rn(oy, __dmul_rn(sp, sn));
+      // order inside a sub-frame: wall, then conflict, then goal (nodes_single.py:80-98); what the intruders do in a
+      // sub-frame that ends the playout is not observable
+      if (!(0.0 < ox && ox < c.window_width) || !(0.0 < oy && oy < c.window_height)) { flags = GCA_MCTS_WALL; break; }
+      bool hit = false;
+      for (int j = 0; j < n_eff; ++j) {
+        const uint32_t ii = (uint32_t)my_idx[j];                      // the intruder's own index addresses its draws
+        const double npx = mcts_normal(a, c.position_sigma, root, playout, GCA_MCTS_DRAW_INTRUDER + ii, 2 * gf);
+        const double npy = mcts_normal(a, c.position_sigma, root, playout, GCA_MCTS_DRAW_INTRUDER + ii, 2 * gf + 1);
+        const double x = __dadd_rn(X[j], __dadd_rn(VX[j], npx));
+        const double y = __dadd_rn(Y[j], __dadd_rn(VY[j], npy));
+        X[j] = x;
+        Y[j] = y;
+        // the turn follows the advance (:64-71) and touches nothing but this intruder's velocity and heading, which the
+        // NEXT sub-frame reads: the (rare, 10 %) turns of a sub-frame are queued and made after the loop, where the lanes
+        // that have one run the sincos together instead of one or two lanes at a time inside the loop
+        double delta;
+        if (mcts_turn(a, root, playout, ii, gf, delta)) {
+          if (n_turns == kTurnQueue) {                                // (queue full: make the oldest now)
+            --n_turns;
+            apply_turn(turn_j[n_turns], turn_d[n_turns]);
+          }
+          turn_j[n_turns] = j;
+          turn_d[n_turns] = delta;
+          ++n_turns;
+        }
+        const double dx = __dadd_rn(x, -ox), dy = __dadd_rn(y, -oy);
+        hit |= __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < a.sep2;
+      }
+      while (n_turns > 0) {
+        --n_turns;
+        apply_turn(turn_j[n_turns], turn_d[n_turns]);
+      }
+      if (hit) { flags = GCA_MCTS_CONFLICT; break; }
+      const double dx = __dadd_rn(ox, -gx), dy = __dadd_rn(oy, -gy);
+      if (__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < a.sep2) { flags = GCA_MCTS_GOAL; break; }
+    }
+  }
+  double reward;
+  if (flags & (GCA_MCTS_WALL | GCA_MCTS_CONFLICT)) reward = 0.0;
+  else if (flags & GCA_MCTS_GOAL) reward = 1.0;
+  else {
+    const double dx = __dadd_rn(ox, -gx), dy = __dadd_rn(oy, -gy);
+    const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    reward = __dadd_rn(1.0, -__ddiv_rn(dist, 1200.0));
+  }
+  a.rewards[pid] = reward;
+  if (a.first_out) a.first_out[pid] = (int8_t)first;
+  if (a.flags) a.flags[pid] = (uint8_t)flags;
+}
+
 // ------------------------------------------------------------------------------ device-resident UCT search
 // MCTS(root).best_action(simulations, search_depth) (search_single.py:8-22; tree_policy / expand / best_child /
 // backpropagate: common.py:47-52, nodes_single.py:188-210) for a batch of roots, position_sigma == 0.  Because the
@@ -796,6 +954,16 @@ cudaError_t launch_mcts_playouts(const gca_mcts_config* cfg, int n, const double
   if (cfg->random_intruders) {                // every playout moves its own intruders: one warp per playout
     const size_t smem = sizeof(double) * kMctsWarps * (6 * (size_t)a.near + ((size_t)a.near + 1) / 2);
     a.cull = cfg->position_sigma == 0.0 && cfg->speed_sigma == 0.0 && !getenv("GCA_MCTS_NO_CULL");
+    if (a.near <= kLaneMaxNear && playouts <= kLaneThreads && !getenv("GCA_MCTS_WARP_KERNEL")) {
+      // one playout per lane, several roots per CTA (mcts_playout_rnd_lane_kernel)
+      const int R = (int)std::min<long long>(std::min<long long>(kLaneMaxRoots, kLaneThreads / playouts), n_roots);
+      const size_t lsm = (((size_t)(16 + (size_t)R * a.near) * 4 + 15) & ~(size_t)15) + sizeof(double) * 6 * (size_t)R * (size_t)a.near;
+      const unsigned threads = (unsigned)(((long long)R * playouts + 31) / 32 * 32);
+      cudaError_t e = cudaFuncSetAttribute(mcts_playout_rnd_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm);
+      if (e != cudaSuccess) return e;
+      mcts_playout_rnd_lane_kernel<<<(unsigned)((n_roots + R - 1) / R), threads, lsm, st>>>(a, R);
+      return cudaGetLastError();
+    }
     cudaError_t e = cudaFuncSetAttribute(mcts_playout_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     mcts_playout_kernel<0, true><<<pblocks, kMctsWarps * 32, smem, st>>>(a);

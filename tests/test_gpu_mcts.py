@@ -69,12 +69,17 @@ def test_playouts_bit_exact_vs_oracle(n, roots_n, playouts, depth, over):
     print("n=%d flags histogram" % n, np.bincount(want_fl.ravel(), minlength=5).tolist())
 
 
-@pytest.mark.parametrize("n,roots_n,playouts,depth", [(80, 48, 40, 3), (200, 8, 12, 3), (80, 6, 8, 4)])
-def test_warp_per_playout_kernel_bit_exact(n, roots_n, playouts, depth, monkeypatch):
-    """position_sigma == 0 takes the root-cooperative kernel; the warp-per-playout kernel (any sigma) must keep
-    giving the same bits (GCA_MCTS_WARP_KERNEL forces it)."""
+@pytest.mark.parametrize("n,roots_n,playouts,depth,over", [
+    (80, 48, 40, 3, {}), (200, 8, 12, 3, {}), (80, 6, 8, 4, {}),
+    (80, 21, 100, 3, RND), (5, 7, 30, 3, dict(RND, speed_sigma=0.05, position_sigma=0.3, turn_prob=0.5)),
+])
+def test_warp_per_playout_kernel_bit_exact(n, roots_n, playouts, depth, over, monkeypatch):
+    """position_sigma == 0 takes the root-cooperative kernel and the random-intruder model the lane-per-playout kernel;
+    the warp-per-playout kernels (any sigma, any N) must keep giving the same bits (GCA_MCTS_WARP_KERNEL forces them)."""
+    if over:
+        test_playouts_bit_exact_vs_oracle(n, roots_n, playouts, depth, over)     # (lane-per-playout kernel, ragged last CTA)
     monkeypatch.setenv("GCA_MCTS_WARP_KERNEL", "1")
-    test_playouts_bit_exact_vs_oracle(n, roots_n, playouts, depth, {})
+    test_playouts_bit_exact_vs_oracle(n, roots_n, playouts, depth, over)
 
 
 @pytest.mark.parametrize("n,roots_n,playouts,depth", [(80, 37, 100, 3), (3, 9, 50, 3), (80, 5, 500, 2)])
