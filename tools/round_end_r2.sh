@@ -19,7 +19,7 @@ PY
 python /tmp/mcts_only.py > gpurun_out/r2_mcts_plain.log 2>&1 || exit 1
 M=smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,gpu__time_duration.sum,sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active
 ncu --metrics $M --clock-control none -k regex:mcts_search_kernel -c 1 --csv --log-file gpurun_out/r2_mcts_search_ops.csv python /tmp/mcts_only.py > /dev/null 2>&1
-ncu --metrics $M --clock-control none -k regex:"mcts_playout_kernel" -s 2 -c 1 --csv --log-file gpurun_out/r2_mctsrnd_model_ops.csv python /tmp/mcts_only.py > /dev/null 2>&1
-ncu --metrics $M --clock-control none -k regex:mcts_playout_shared -s 3 -c 1 --csv --log-file gpurun_out/r2_mcts_ops.csv python /tmp/mcts_only.py > /dev/null 2>&1
+ncu --metrics $M --clock-control none -k regex:mcts_playout_rnd_lane -s 2 -c 1 --csv --log-file gpurun_out/r2_mctsrnd_model_ops.csv python /tmp/mcts_only.py > /dev/null 2>&1
+ncu --metrics $M --clock-control none -k regex:mcts_playout_packed -s 3 -c 1 --csv --log-file gpurun_out/r2_mcts_ops.csv python /tmp/mcts_only.py > /dev/null 2>&1
 tail -4 gpurun_out/r2_mcts_search_ops.csv gpurun_out/r2_mctsrnd_model_ops.csv gpurun_out/r2_mcts_ops.csv | cut -c1-400
 tail -c 600 gpurun_out/r2_bench_n1.err
