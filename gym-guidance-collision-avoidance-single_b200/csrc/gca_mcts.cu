@@ -331,6 +331,9 @@ __global__ void __launch_bounds__(kMctsWarps * 32) mcts_playout_kernel(const Mct
 // instructions per playout at N = 80 (the 79 x 30 distance tests collapse to ~45).
 constexpr int kSharedThreads = 128;
 
+// COMPACT: cnt[gf] .. cnt[gf + 1] delimit the sub-frame's candidates in one packed list (the search workspace);
+// otherwise cnt[gf] candidates at cand[gf * near] (the shared-memory layouts of the playout kernels)
+template <bool COMPACT = false>
 __device__ __forceinline__ int lane_move(const MctsArgs& a, const int* __restrict__ cnt, const double2* __restrict__ cand,
                                          uint32_t root, uint32_t sim, int depth, int act, double gx, double gy,
                                          double& ox, double& oy, double& vy_prev, double& heading);
@@ -667,14 +670,35 @@ static_assert(sizeof(TreeNode) == 80, "tree node layout");
 // One lane runs the whole move, sub-frame by sub-frame.  (Batching the state-independent noise / sincos chains of
 // several sub-frames for instruction-level parallelism was measured: 2 at a time -5 %, 5 at a time -25 % - the extra
 // registers cost more occupancy than the parallel chains return.)
+template <bool COMPACT>
 __device__ __forceinline__ int lane_move(const MctsArgs& a, const int* __restrict__ cnt, const double2* __restrict__ cand,
                                          uint32_t root, uint32_t sim, int depth, int act, double gx, double gy,
                                          double& ox, double& oy, double& vy_prev, double& heading) {
   const gca_mcts_config& c = a.c;
   const int F = c.simulate_frame;
   const double d_heading = __dmul_rn((double)(act / 3 - 1), c.d_heading);
+  // COMPACT (global memory, one lane per root): the list bounds and the first four candidates of sub-frame f + 1 are
+  // requested while sub-frame f computes - two dependent round trips per sub-frame otherwise.  The slots behind a
+  // sub-frame's last candidate are inside the root's list area (read and ignored).
+  int e0 = 0, e1 = 0;
+  double2 q[4] = {};
+  if constexpr (COMPACT) {
+    e0 = cnt[depth * F];
+    e1 = cnt[depth * F + 1];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) q[j] = cand[e0 + j];
+  }
   for (int f = 0; f < F; ++f) {
     const int gf = depth * F + f;
+    int e2 = e1;
+    double2 qn[4] = {};
+    if constexpr (COMPACT) {
+      if (f + 1 < F) {
+        e2 = cnt[gf + 2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) qn[j] = cand[e1 + j];
+      }
+    }
     const double nh = mcts_normal(a, c.heading_sigma, root, sim, GCA_MCTS_DRAW_HEADING, (uint32_t)gf);
     const double nsp = mcts_normal(a, c.speed_sigma, root, sim, GCA_MCTS_DRAW_SPEED, (uint32_t)gf);
     double sp = clamp_speed(c, vy_prev);                              // state[-4] = clamp(state[-5])  (Q23)
@@ -689,12 +713,29 @@ __device__ __forceinline__ int lane_move(const MctsArgs& a, const int* __restric
     vy_prev = vy;
     if (!(0.0 < ox && ox < c.window_width) || !(0.0 < oy && oy < c.window_height)) return GCA_MCTS_WALL;
     bool hit = false;
-    const double2* cf = cand + (size_t)gf * a.near;
-    const int nc = cnt[gf];
-    for (int k = 0; k < nc; ++k) {
-      const double2 q = cf[k];
-      const double dx = __dadd_rn(q.x, -ox), dy = __dadd_rn(q.y, -oy);
-      hit |= __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < a.sep2;
+    const double2* cf = COMPACT ? cand + e0 : cand + (size_t)gf * a.near;
+    const int nc = COMPACT ? e1 - e0 : cnt[gf];
+    if constexpr (COMPACT) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double dx = __dadd_rn(q[j].x, -ox), dy = __dadd_rn(q[j].y, -oy);
+        hit |= (j < nc) & (__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < a.sep2);
+      }
+      for (int k = 4; k < nc; ++k) {                                  // (rarely more than four)
+        const double2 r = cf[k];
+        const double dx = __dadd_rn(r.x, -ox), dy = __dadd_rn(r.y, -oy);
+        hit |= __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < a.sep2;
+      }
+      e0 = e1;
+      e1 = e2;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) q[j] = qn[j];
+    } else {
+      for (int k = 0; k < nc; ++k) {
+        const double2 q = cf[k];
+        const double dx = __dadd_rn(q.x, -ox), dy = __dadd_rn(q.y, -oy);
+        hit |= __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < a.sep2;
+      }
     }
     if (hit) return GCA_MCTS_CONFLICT;
     const double dx = __dadd_rn(ox, -gx), dy = __dadd_rn(oy, -gy);
@@ -711,9 +752,14 @@ __device__ __forceinline__ double lane_reward(int flags, double ox, double oy, d
   return __dadd_rn(1.0, -__ddiv_rn(dist, 1200.0));
 }
 
-// intruder trajectories of one root -> per-sub-frame candidate lists (shared by both users)
-__device__ __forceinline__ void build_candidates(const MctsArgs& a, const double* st, int TF, int* cnt, double2* cand,
-                                                 int tid, int nthreads) {
+// intruder trajectories of one root -> per-sub-frame candidate lists, PACKED: ends[0] = 0 and ends[f + 1] = end of
+// sub-frame f's candidates in `cand` (so ends[f] is where they start).  Two passes over the same deterministic
+// trajectories: count, exclusive scan, place.  Packed because the search reads them one LANE per root: with the
+// [sub-frame][near] layout of the playout kernels every sub-frame of every root sat in a cache line of its own (38 KB
+// per root at N = 80 for ~45 candidates); now a root's lists are ~1 KB, contiguous.
+template <bool PLACE>
+__device__ __forceinline__ void walk_candidates(const MctsArgs& a, const double* st, int TF, int* ends, double2* cand, int tid,
+                                                int nthreads) {
   const gca_mcts_config& c = a.c;
   const double* own = st + a.per * a.n;
   const double ox0 = own[0], oy0 = own[1];
@@ -733,7 +779,10 @@ __device__ __forceinline__ void build_candidates(const MctsArgs& a, const double
         const double dx = x - ox0, dy = y - oy0;
         in = !(dx * dx + dy * dy >= reach * reach);
       }
-      if (in) cand[(size_t)f * a.near + atomicAdd(&cnt[f], 1)] = make_double2(x, y);
+      if (in) {
+        const int at = atomicAdd(&ends[f + 1], 1);          // count, or (PLACE) the sub-frame's fill pointer
+        if (PLACE) cand[at] = make_double2(x, y);
+      }
     }
   }
 }
@@ -741,11 +790,23 @@ __device__ __forceinline__ void build_candidates(const MctsArgs& a, const double
 __global__ void __launch_bounds__(128) mcts_candidates_kernel(const MctsArgs a) {
   const int TF = a.depth * a.c.simulate_frame;
   uint8_t* ws = a.workspace + (size_t)blockIdx.x * a.ws_root_stride;
-  int* cnt = reinterpret_cast<int*>(ws);
+  int* ends = reinterpret_cast<int*>(ws);                                     // [TF + 1]
   double2* cand = reinterpret_cast<double2*>(ws + a.ws_cand_off);
-  for (int f = threadIdx.x; f < TF; f += 128) cnt[f] = 0;
+  const double* st = a.roots + (long long)blockIdx.x * a.L;
+  for (int f = threadIdx.x; f <= TF; f += 128) ends[f] = 0;
   __syncthreads();
-  build_candidates(a, a.roots + (long long)blockIdx.x * a.L, TF, cnt, cand, threadIdx.x, 128);
+  walk_candidates<false>(a, st, TF, ends, cand, threadIdx.x, 128);            // ends[f + 1] = count of sub-frame f
+  __syncthreads();
+  if (threadIdx.x == 0) {                                                     // -> where sub-frame f's candidates start
+    int run = 0;
+    for (int f = 0; f < TF; ++f) {
+      const int n = ends[f + 1];
+      ends[f + 1] = run;
+      run += n;
+    }
+  }
+  __syncthreads();
+  walk_candidates<true>(a, st, TF, ends, cand, threadIdx.x, 128);             // fill pointers end at the sub-frame's end
 }
 
 __global__ void __launch_bounds__(128) mcts_search_kernel(const MctsArgs a) {
@@ -771,11 +832,24 @@ __global__ void __launch_bounds__(128) mcts_search_kernel(const MctsArgs a) {
     const double lg2 = __dmul_rn(2.0, gca_log((double)nv.n));
     int best = -1;
     double best_w = 0.0;
-    for (int k = 0; k < nv.n_children; ++k) {
-      const int ci = nv.children[k];
-      const double cn = (double)nodes[ci].n;
-      const double w = __dadd_rn(__ddiv_rn(nodes[ci].q, cn), __dmul_rn(c_param, __dsqrt_rn(__ddiv_rn(lg2, cn))));
-      if (best < 0 || w > best_w) { best = ci; best_w = w; }
+    // the children's statistics are requested together (each sits in a cache line of its own: one round trip instead
+    // of one per child), then scored in order
+    const int nch = nv.n_children;
+    int cidx[9], cvis[9];
+    double cq[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      cidx[k] = k < nch ? nv.children[k] : 0;
+      cvis[k] = nodes[cidx[k]].n;
+      cq[k] = nodes[cidx[k]].q;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      if (k < nch) {
+        const double cn = (double)cvis[k];
+        const double w = __dadd_rn(__ddiv_rn(cq[k], cn), __dmul_rn(c_param, __dsqrt_rn(__ddiv_rn(lg2, cn))));
+        if (best < 0 || w > best_w) { best = cidx[k]; best_w = w; }
+      }
     }
     return best;
   };
@@ -805,7 +879,7 @@ __global__ void __launch_bounds__(128) mcts_search_kernel(const MctsArgs a) {
       int act;
       if (expand) act = --nodes[v].untried;
       else act = mcts_action(a, root, (uint32_t)s, (uint32_t)depth);
-      flags = lane_move(a, cnt, cand, root, (uint32_t)s, depth, act, gx, gy, ox, oy, vy, heading);
+      flags = lane_move<true>(a, cnt, cand, root, (uint32_t)s, depth, act, gx, gy, ox, oy, vy, heading);
       ++depth;
       if (expand) {                                                   // the new child: the state after this one move
         TreeNode ch{};
@@ -1008,8 +1082,8 @@ cudaError_t launch_mcts_playouts(const gca_mcts_config* cfg, int n, const double
 }
 
 static void search_layout(int near, long long tf, int sims, size_t* cand_off, size_t* node_off, size_t* stride) {
-  *cand_off = ((size_t)tf * 4 + 15) & ~(size_t)15;
-  *node_off = *cand_off + sizeof(double2) * (size_t)tf * (size_t)near;
+  *cand_off = (((size_t)tf + 1) * 4 + 15) & ~(size_t)15;         // ends[tf + 1], then the packed candidates (worst case tf * near)
+  *node_off = *cand_off + sizeof(double2) * ((size_t)tf * (size_t)near + 3);   // (+ 3: lane_move reads candidates four at a time)
   *stride = *node_off + sizeof(TreeNode) * ((size_t)sims + 1);
 }
 
