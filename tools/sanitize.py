@@ -12,9 +12,10 @@ from gca_b200.batched import BatchedAircraftEnv  # noqa: E402
 from gca_b200.stack import ImageBatch  # noqa: E402
 from gym_guidance_collision_avoidance_single.envs.config import Config  # noqa: E402
 
+QUICK = os.environ.get("GCA_SANITIZE_QUICK") == "1"        # (one env variant only: the MCTS kernels are the subject)
 for variant, B, N, mode in [("SingleAircraft2Env", 1000, 80, "fast"), ("SingleAircraftEnv", 77, 33, "fast"),
                             ("SingleAircraftHEREnv", 300, 80, "fast"), ("SingleAircraftEnv", 130, 7, "faithful"),
-                            ("SingleAircraftEnv", 64, 0, "fast"), ("SingleAircraftDiscreteHEREnv", 90, 200, "fast")]:
+                            ("SingleAircraftEnv", 64, 0, "fast"), ("SingleAircraftDiscreteHEREnv", 90, 200, "fast")][:1 if QUICK else None]:
     env = BatchedAircraftEnv(variant, B, Config, n_intruders=N, mode=mode, seed=3)
     env.reset()
     for t in range(60):
@@ -78,14 +79,22 @@ cfg = abi.make_mcts_config(MctsConfig)
 env = BatchedAircraftEnv("SingleAircraftMCTSEnv", 48, SimConfig, n_intruders=80, mode="faithful", seed=2)
 roots = env.reset().clone()
 env.close()
-mcts.playouts(roots, 37, depth=3, cfg=cfg, seed=1)
+mcts.playouts(roots, 37, depth=3, cfg=cfg, seed=1)                  # packed kernel: 8 roots per CTA
+mcts.playouts(roots[:13], 100, depth=3, cfg=cfg, seed=1)            # 5 roots per CTA, ragged last CTA
+os.environ["GCA_MCTS_NO_PACK"] = "1"
+mcts.playouts(roots, 37, depth=3, cfg=cfg, seed=1)                  # one root per CTA
+del os.environ["GCA_MCTS_NO_PACK"]
 os.environ["GCA_MCTS_WARP_KERNEL"] = "1"
 mcts.playouts(roots, 11, depth=3, cfg=cfg, seed=1)
 del os.environ["GCA_MCTS_WARP_KERNEL"]
 mcts.search(roots, 60, 3, cfg=cfg, seed=4)
 mcts.move(roots.clone(), torch.randint(0, 9, (48,), device="cuda", dtype=torch.int32), cfg)
 rcfg = abi.make_mcts_config(MctsConfig, random_intruders=True)      # the nodes_single_randintru.py model
-mcts.playouts(rnd_roots, 9, depth=3, cfg=rcfg, seed=1)
+mcts.playouts(rnd_roots, 9, depth=3, cfg=rcfg, seed=1)              # lane-per-playout kernel, 8 roots per CTA
+mcts.playouts(rnd_roots[:7], 100, depth=3, cfg=rcfg, seed=1)        # 2 roots per CTA, ragged last CTA
+os.environ["GCA_MCTS_WARP_KERNEL"] = "1"
+mcts.playouts(rnd_roots, 9, depth=3, cfg=rcfg, seed=1)              # warp-per-playout kernel
+del os.environ["GCA_MCTS_WARP_KERNEL"]
 mcts.move(rnd_roots.clone(), torch.randint(0, 9, (24,), device="cuda", dtype=torch.int32), rcfg)
 torch.cuda.synchronize()
 print("ok mcts", flush=True)
